@@ -1,0 +1,271 @@
+#!/usr/bin/env python
+"""bench.py -- SR frames/s of the EDVR hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+A "step" is one pass of the hot path (rvsr_engine_forward) over one batch of B synthetic
+5x3x180x320 LQ windows per GPU -> B 3x720x1280 frames (BASELINE cfg2: full 64-ch PCD + TSA +
+10 ResBlocks, fp16 storage / fp32 accumulate).  One process per GPU; windows are independent,
+so ranks shard them with no data-path collective ("weak" scaling: per-GPU work fixed).
+Rank 0 prints ONE JSON line.  See DESIGN.md section "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+CFG = dict(nf=64, nc=3, nframes=5, groups=8, front_RBs=5, back_RBs=10, w_TSA=True)
+H, W = 180, 320
+GFLOP_PER_WINDOW = 976.70  # forward-hook count on the reference modules
+METRIC = "SR frames/sec (5-frame window, 180x320->720x1280)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sus=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, src="fallback")
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, dev):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(dev)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, reasons = [], set()
+        for line in self.f:
+            c = [t.strip() for t in line.split(",")]
+            if len(c) < 8:
+                continue
+            try:
+                sm.append(float(c[1]))
+                out["sm_max_mhz"] = float(c[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            hi = sorted(sm)[len(sm) // 2:]  # samples under load = the upper half
+            out["sm_mhz"] = statistics.median(hi)
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+def cpu_reference_step(sd, x, threads):
+    """One pass of the CPU restatement of the reference path (oracle/) -- the only place the
+    bench executes oracle/ code, and only as the reported CPU baseline."""
+    import torch
+    from oracle import edvr_oracle as O
+    torch.set_num_threads(threads)
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        O.edvr_forward(sd, x, groups=CFG["groups"], w_TSA=True, upsample=True)
+    return time.perf_counter() - t0
+
+
+def cpu_sample(steps, warmup):
+    """Bounded sample: 5x3x90x160 windows (1/4 of the pixels of the cfg2 window, same network);
+    frames/s is scaled by the pixel ratio (the network is fully convolutional)."""
+    import torch
+    from helpers import edvr_state_shapes
+    from synth import synth_input, synth_state_dict
+    sd = synth_state_dict(edvr_state_shapes("EDVR", **CFG), 7)
+    h, w = 92, 160  # multiples of 4 (two stride-2 levels), ~1/4 of 180x320
+    x = synth_input((1, 5, 3, h, w), 8)
+    cores = os.cpu_count() or 1
+    for _ in range(warmup):
+        cpu_reference_step(sd, x, cores)
+    ts = [cpu_reference_step(sd, x, cores) for _ in range(steps)]
+    t = statistics.median(ts)
+    frac = (h * w) / float(H * W)
+    return dict(value=frac / t, unit="frames/s", cores=cores, kind="port",
+                sample="%d x one 5x3x%dx%d window (%.2f of a cfg2 window's pixels) through oracle/edvr_oracle.py "
+                       "(torch CPU convs + OpenMP C DCN), median %.2f s/step, scaled by pixel ratio" %
+                       (steps, h, w, frac, t)), t
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    steps = max(1, min(args.steps, 5))
+    warm = max(0, min(args.warmup, 1))
+    cb, t = cpu_sample(steps, warm)
+    line = dict(metric=METRIC, value=cb["value"], unit="frames/s", n_gpus=args.gpus, steps=steps, warmup=warm,
+                ms_per_step=t * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", impl="reference",
+                config=dict(workload="cfg2: 5x3x180x320 LQ window, EDVR nf=64 5 frames PCD+TSA+10RB -> 3x720x1280",
+                            note="reference has no CPU DCN (deform_conv.py:109-110 raises); this arm is the oracle "
+                                 "port on host cores, bounded to a quarter-size window per step"),
+                cpu_baseline=cb, e2e=dict(value=cb["value"], unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=1, help="windows per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from helpers import edvr_state_shapes
+    from realvsr_b200.archs import EDVR_arch as E
+    from synth import synth_input, synth_state_dict
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    args.warmup = max(args.warmup, 3)
+    B, K = args.batch, args.steps
+    dt = torch.float16 if args.precision == "fp16" else torch.float32
+
+    net = E.EDVR(**CFG).eval()
+    net.load_state_dict(synth_state_dict(edvr_state_shapes("EDVR", **CFG), 7), strict=True)
+    net = net.to(dev).to(dt)
+    net.exec_path = "engine"
+    n_clips = 8  # rotate inputs; a step's activation working set (~1.5 GB fp16 at B=1) is >> the 126 MB L2
+    clips = [synth_input((B, 5, 3, H, W), 1000 + 17 * rank + i).to(dev).to(dt) for i in range(n_clips)]
+    eng = net._get_engine(clips[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for i in range(args.warmup):
+            y = net(clips[i % n_clips])
+        barrier()
+        sampler = ClockSampler(local) if rank == 0 else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            y = net(clips[i % n_clips])
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = eng.last_launch_count() * K
+        clocks = sampler.stop() if sampler else None
+
+        # ---- end to end through the public host-buffer call (H2D + forward + D2H every step)
+        hosts = [c.cpu().pin_memory() for c in clips]
+        out_host = torch.empty(B, 3, 4 * H, 4 * W, dtype=dt).pin_memory()
+        for i in range(2):
+            eng.forward_host(hosts[i], out_host)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            eng.forward_host(hosts[i % n_clips], out_host)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        barrier()
+
+    t = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, e2e_ms_max = float(t[0]), float(t[1])
+
+    line = None
+    if rank == 0:
+        pk = peaks()
+        # ---- roofline of the dominant kernel: per-launch CUDA events inside full forwards
+        with torch.no_grad():
+            rows = eng.profile(clips[0], steps=3)
+        agg = {}
+        for r in rows:
+            a = agg.setdefault(r["label"], dict(ms=0.0, flops=0.0, bytes=0.0, n=0))
+            a["ms"] += r["ms"]; a["flops"] += r["flops"]; a["bytes"] += r["bytes"]; a["n"] += 1
+        total_ms = sum(a["ms"] for a in agg.values())
+        top = sorted(agg.items(), key=lambda kv: -kv[1]["ms"])
+        name, a = top[0]
+        ai = a["flops"] / max(a["bytes"], 1.0)
+        ridge = pk["tf_sus"] * 1e12 / (pk["hbm"] * 1e9)
+        if ai >= ridge * 0.5:  # conv-class kernels sit at or above the ridge: tensor roofline
+            ach = a["flops"] / (a["ms"] * 1e-3) / 1e12
+            roof = dict(bound="tensor", achieved=ach, peak=pk["tf_sus"], unit="TFLOP/s", frac=ach / pk["tf_sus"])
+        else:
+            ach = a["bytes"] / (a["ms"] * 1e-3) / 1e9
+            roof = dict(bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"])
+        roof.update(traffic=None, kernel=name, launches_per_step=a["n"], ms_per_launch=a["ms"] / a["n"],
+                    share_of_step=a["ms"] / total_ms, peak_source=pk["src"] + (" sustained bf16" if roof["bound"] == "tensor" else " copy"),
+                    algorithmic_per_launch=dict(gflop=a["flops"] / a["n"] / 1e9, mbytes=a["bytes"] / a["n"] / 1e6))
+        kernels = [dict(kernel=k, ms=v["ms"], n=v["n"], tflops=(v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 else 0,
+                        gbs=(v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else 0) for k, v in top[:12]]
+        value = world * B * K / (ms_max * 1e-3)
+        line = dict(metric=METRIC, value=value, unit="frames/s", n_gpus=world, steps=K, warmup=args.warmup,
+                    ms_per_step=ms_max / K, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="f16" if args.precision == "fp16" else "f32", data="synthetic",
+                    config=dict(workload="cfg2: 5x3x180x320 LQ window, EDVR nf=64 5 frames groups=8 PCD+TSA+5/10 RB -> 3x720x1280",
+                                windows_per_gpu_per_step=B, accumulate="f32",
+                                l2="8 rotating input clips; per-step activation working set >> 126 MB L2",
+                                gflop_per_window=GFLOP_PER_WINDOW,
+                                whole_step_tflops=GFLOP_PER_WINDOW * B * K / (ms_max * 1e-3) / 1e3),
+                    e2e=dict(value=world * B * K / (e2e_ms_max * 1e-3), unit="frames/s",
+                             h2d_bytes_per_step=int(hosts[0].numel() * hosts[0].element_size()),
+                             d2h_bytes_per_step=int(out_host.numel() * out_host.element_size()),
+                             api="EDVREngine.forward_host -> rvsr_engine_forward_host (pinned host buffers)"),
+                    gpu_launches=launches, clocks=clocks, roofline=roof, kernels=kernels)
+        if world == 1 and not args.no_cpu_baseline:
+            cb, _ = cpu_sample(steps=2, warmup=1)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

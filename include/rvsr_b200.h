@@ -1,0 +1,149 @@
+/*
+ * rvsr_b200.h -- C ABI of the B200-native RealVSR/EDVR hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every entry
+ * point names the reference interface it replaces (paths relative to the reference
+ * repo IanYeung/RealVSR, codes/models/archs/).
+ *
+ * Conventions (all entry points):
+ *   - return 0 on success, a negative RVSR_E_* code on failure; never throws.
+ *     rvsr_last_error() returns a thread-local message for the last failure.
+ *   - all device work is enqueued on the cudaStream_t passed as `stream` (void*),
+ *     no host synchronisation, no allocation inside per-call entry points; the caller
+ *     owns every buffer including the workspace.
+ *   - dtype codes: RVSR_F32 = 0, RVSR_F16 = 1.
+ *   - "NCHW" tensors are contiguous like the reference's; the engine's private
+ *     activation layout (channel-blocked [N][C/8][H][W][8]) never crosses this ABI.
+ */
+#ifndef RVSR_B200_H
+#define RVSR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RVSR_F32 0
+#define RVSR_F16 1
+
+#define RVSR_OK 0
+#define RVSR_E_INVALID (-1)     /* bad argument / unsupported shape (reference: AT_ERROR / shape_check) */
+#define RVSR_E_CUDA (-2)        /* CUDA runtime error (reference only printf'd these, .cu:794-798) */
+#define RVSR_E_WORKSPACE (-3)   /* workspace too small */
+#define RVSR_E_STATE (-4)       /* engine not finalised / weight missing */
+#define RVSR_E_UNSUPPORTED (-5) /* valid in the reference but not built here yet */
+
+#define RVSR_ACT_NONE 0
+#define RVSR_ACT_LRELU 1 /* LeakyReLU(0.1), EDVR_arch.py:96 */
+#define RVSR_ACT_RELU 2
+
+/* ------------------------------------------------------------------ misc */
+int rvsr_version(void);
+const char *rvsr_last_error(void);
+/* 1 if the current device is sm_100 (B200); 0 otherwise; <0 on CUDA error. */
+int rvsr_device_ok(void);
+
+/* ------------------------------------------------------------------ DCNv2 operator
+ * Replaces the reference's pybind module `deform_conv_cuda`
+ * (dcn/src/deform_conv_cuda.cpp:687-701), v2 functions.
+ */
+
+/* modulated_deform_conv_cuda_forward (deform_conv_cuda.cpp:490-569) +
+ * modulated_deformable_im2col_gpu_kernel (deform_conv_cuda_kernel.cu:571-633), fused:
+ * gather and contraction happen in one kernel, no `columns` buffer, bias added in the
+ * epilogue.  All tensors NCHW of `dtype`; bias may be NULL (with_bias=false).
+ * offset [B, dg*2*kh*kw, Ho, Wo], mask [B, dg*kh*kw, Ho, Wo] (already sigmoid-ed).
+ * workspace: rvsr_mdcn_fwd_workspace_bytes(). */
+size_t rvsr_mdcn_fwd_workspace_bytes(int B, int C, int H, int W, int Cout, int kh, int kw,
+                                     int stride, int pad, int dil, int groups, int dg, int dtype);
+int rvsr_mdcn_fwd(const void *input, const void *offset, const void *mask, const void *weight,
+                  const void *bias, void *output, int B, int C, int H, int W, int Cout, int kh,
+                  int kw, int stride, int pad, int dil, int groups, int dg, int dtype,
+                  void *workspace, size_t workspace_bytes, void *stream);
+
+/* modulated_deform_conv_cuda_backward (deform_conv_cuda.cpp:571-685) + the col2im /
+ * col2im_coord kernels (deform_conv_cuda_kernel.cu:635-767).  grad_input, grad_offset,
+ * grad_mask are overwritten; grad_weight and grad_bias (may be NULL) must be zeroed by
+ * the caller and are accumulated into, like the reference (cpp:659-671). fp32 only. */
+size_t rvsr_mdcn_bwd_workspace_bytes(int B, int C, int H, int W, int Cout, int kh, int kw,
+                                     int stride, int pad, int dil, int groups, int dg, int dtype);
+int rvsr_mdcn_bwd(const void *input, const void *offset, const void *mask, const void *weight,
+                  const void *grad_output, void *grad_input, void *grad_offset, void *grad_mask,
+                  void *grad_weight, void *grad_bias, int B, int C, int H, int W, int Cout, int kh,
+                  int kw, int stride, int pad, int dil, int groups, int dg, int dtype,
+                  void *workspace, size_t workspace_bytes, void *stream);
+
+/* ModulatedDeformConvPack.forward with extra_offset_mask=True (dcn/deform_conv.py:274-292):
+ * conv_offset_mask(feat) -> chunk/cat/sigmoid -> modulated deform conv of x, optional
+ * LeakyReLU(0.1) (EDVR_arch.py:107,:130).  NCHW in / NCHW out; 3x3, stride 1, pad 1, dil 1,
+ * groups 1 (the only configuration EDVR_arch.py:73-94 instantiates). */
+size_t rvsr_mdcn_pack_fwd_workspace_bytes(int B, int C, int H, int W, int Cout, int dg, int dtype);
+int rvsr_mdcn_pack_fwd(const void *x, const void *feat, const void *w_offset_mask,
+                       const void *b_offset_mask, const void *weight, const void *bias, void *y,
+                       int B, int C, int H, int W, int Cout, int dg, int act, int dtype,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------ EDVR engine
+ * Replaces EDVR.forward / EDVR_NoUp.forward (EDVR_arch.py:258-320, :358-404) and everything
+ * they call (PCD_Align :98-132, TSA_Fusion :168-208, ResidualBlock_noBN arch_util.py:135-139)
+ * for inference.  Constructor arguments mirror EDVR.__init__ (EDVR_arch.py:212-213). */
+typedef struct rvsr_edvr_config {
+    int nf, nc, nframes, groups, front_RBs, back_RBs;
+    int center;    /* -1 => nframes / 2 (EDVR_arch.py:217) */
+    int predeblur; /* must be 0 (RVSR_E_UNSUPPORTED otherwise; not used by any shipped YAML) */
+    int HR_in;     /* must be 0 */
+    int w_TSA;
+    int upsample;  /* 1 = EDVR (x4 pixel-shuffle tail), 0 = EDVR_NoUp */
+    int precision; /* RVSR_F32: fp32 storage, SIMT kernels (strict parity);
+                      RVSR_F16: fp16 storage, fp32 accumulate, tcgen05 kernels */
+} rvsr_edvr_config;
+
+typedef struct rvsr_engine rvsr_engine;
+
+int rvsr_engine_create(const rvsr_edvr_config *cfg, rvsr_engine **out);
+void rvsr_engine_destroy(rvsr_engine *e);
+/* Hand the engine one state_dict tensor (reference key names) as a
+ * contiguous fp32 DEVICE buffer in PyTorch OIHW order; the engine copies/repacks it into
+ * its private layout on `stream`.  Unknown names -> RVSR_E_INVALID. */
+int rvsr_engine_set_weight(rvsr_engine *e, const char *name, const float *dev_ptr,
+                           const int64_t *shape, int ndim, void *stream);
+/* Check every tensor of the state_dict contract has been supplied; build packed weights. */
+int rvsr_engine_finalize(rvsr_engine *e, void *stream);
+/* Number of expected state_dict tensors and their names (for strict-load checks). */
+int rvsr_engine_num_weights(const rvsr_engine *e);
+const char *rvsr_engine_weight_name(const rvsr_engine *e, int i);
+
+size_t rvsr_engine_workspace_bytes(const rvsr_engine *e, int B, int H, int W);
+/* x: [B, nframes, nc, H, W] NCHW DEVICE tensor of x_dtype; out: [B, nc, sH, sW] of out_dtype
+ * (s = 4 for EDVR, 1 for EDVR_NoUp).  H and W must be multiples of 4. */
+int rvsr_engine_forward(rvsr_engine *e, const void *x, int x_dtype, void *out, int out_dtype,
+                        int B, int H, int W, void *workspace, size_t workspace_bytes,
+                        void *stream);
+/* Same, but x/out are HOST buffers (pinned for overlap): stages through `dev_in`/`dev_out`
+ * device staging buffers supplied by the caller (sizes = the tensors'), H2D + forward + D2H on
+ * `stream`; the caller synchronises.  This is what util.single_forward
+ * (codes/utils/util.py:222-237) amounts to: .to(device) -> model -> .float().cpu(). */
+int rvsr_engine_forward_host(rvsr_engine *e, const void *x_host, int x_dtype, void *out_host,
+                             int out_dtype, int B, int H, int W, void *dev_in, void *dev_out,
+                             void *workspace, size_t workspace_bytes, void *stream);
+/* How many kernels the last rvsr_engine_forward enqueued (bench.py's gpu_launches). */
+int rvsr_engine_last_launch_count(const rvsr_engine *e);
+/* Per-launch profiling: when on, every kernel launch of rvsr_engine_forward is bracketed by
+ * CUDA events on the launching stream.  profile_collect() waits for them and returns the
+ * number of entries (or <0); profile_entry() reads one: label ("tc:<weight>", "simt:<weight>",
+ * "glue:<op>"), device milliseconds, algorithmic FLOPs and bytes of that launch. */
+int rvsr_engine_set_profiling(rvsr_engine *e, int on);
+int rvsr_engine_profile_collect(rvsr_engine *e);
+int rvsr_engine_profile_entry(const rvsr_engine *e, int i, char *label, int label_cap, float *ms,
+                              double *flops, double *bytes);
+/* Debug/parity taps: copy an internal activation (C-blocked) out as NCHW fp32.
+ * names: "L1","L2","L3","aligned","fused".  Valid after a forward with the same workspace. */
+int rvsr_engine_read_tap(rvsr_engine *e, const char *name, float *dst_dev, size_t dst_elems,
+                         void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RVSR_B200_H */

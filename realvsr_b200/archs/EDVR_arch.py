@@ -1,0 +1,311 @@
+"""Host-side mirror of the reference's ``codes/models/archs/EDVR_arch.py``.
+
+Same classes, constructor arguments, sub-module / parameter names (the state_dict contract:
+reference test scripts load weights with strict=True, test_RealVSR_wi_GT.py:77) and forward
+signatures:
+
+    EDVR(nf, nc, nframes, groups, front_RBs, back_RBs, center, predeblur, HR_in, w_TSA)   ref :211-320
+    EDVR_NoUp(...)                                                                          ref :323-404
+    PCD_Align(nf, groups)  ref :62-132      TSA_Fusion(nf, nframes, center)  ref :135-208
+    Predeblur_ResNet_Pyramid(nf, HR_in)  ref :15-59
+
+Two execution paths, both on this package's own CUDA kernels for the deformable conv:
+
+* engine path  -- inference (no autograd) on CUDA tensors: the whole forward is ONE call into
+  the C++ engine (rvsr_engine_forward); weights are re-handed to the engine whenever a
+  parameter changes.  This is the B200 hot path.
+* module path  -- training / autograd, or the rarely used predeblur / HR_in options: the same
+  graph expressed with nn.Conv2d modules plus ``ModulatedDeformConvPack`` (our DCN operator
+  with its own backward), structured like the reference so autograd works unchanged.
+
+There is no CPU path (the reference's DCN is CUDA-only as well, deform_conv.py:109-110).
+"""
+import functools
+import os
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import arch_util
+from .dcn.deform_conv import ModulatedDeformConvPack as DCN
+from .. import engine as _engine
+
+
+def _conv3(cin, cout, stride=1):
+    return nn.Conv2d(cin, cout, 3, stride, 1, bias=True)
+
+
+def _up2(t):
+    return F.interpolate(t, scale_factor=2, mode='bilinear', align_corners=False)
+
+
+class Predeblur_ResNet_Pyramid(nn.Module):
+    def __init__(self, nf=128, HR_in=False):
+        super(Predeblur_ResNet_Pyramid, self).__init__()
+        self.HR_in = bool(HR_in)
+        if self.HR_in:
+            self.conv_first_1 = _conv3(3, nf)
+            self.conv_first_2 = _conv3(nf, nf, 2)
+            self.conv_first_3 = _conv3(nf, nf, 2)
+        else:
+            self.conv_first = _conv3(3, nf)
+        for name in ('RB_L1_1', 'RB_L1_2', 'RB_L1_3', 'RB_L1_4', 'RB_L1_5', 'RB_L2_1', 'RB_L2_2', 'RB_L3_1'):
+            setattr(self, name, arch_util.ResidualBlock_noBN(nf=nf))
+        self.deblur_L2_conv = _conv3(nf, nf, 2)
+        self.deblur_L3_conv = _conv3(nf, nf, 2)
+        self.lrelu = nn.LeakyReLU(negative_slope=0.1, inplace=True)
+
+    def forward(self, x):
+        act = self.lrelu
+        if self.HR_in:
+            l1 = act(self.conv_first_3(act(self.conv_first_2(act(self.conv_first_1(x))))))
+        else:
+            l1 = act(self.conv_first(x))
+        l2 = act(self.deblur_L2_conv(l1))
+        l3 = act(self.deblur_L3_conv(l2))
+        l2 = self.RB_L2_1(l2) + _up2(self.RB_L3_1(l3))
+        l1 = self.RB_L1_2(self.RB_L1_1(l1)) + _up2(self.RB_L2_2(l2))
+        return self.RB_L1_5(self.RB_L1_4(self.RB_L1_3(l1)))
+
+
+class PCD_Align(nn.Module):
+    """Pyramid (3 levels), Cascading, Deformable alignment of one neighbour frame to the reference frame."""
+
+    def __init__(self, nf=64, groups=8):
+        super(PCD_Align, self).__init__()
+        dcn = functools.partial(DCN, nf, nf, 3, stride=1, padding=1, dilation=1, deformable_groups=groups,
+                                extra_offset_mask=True)
+        # registration order = reference order (state_dict key order)
+        self.L3_offset_conv1 = _conv3(nf * 2, nf)
+        self.L3_offset_conv2 = _conv3(nf, nf)
+        self.L3_dcnpack = dcn()
+        self.L2_offset_conv1 = _conv3(nf * 2, nf)
+        self.L2_offset_conv2 = _conv3(nf * 2, nf)
+        self.L2_offset_conv3 = _conv3(nf, nf)
+        self.L2_dcnpack = dcn()
+        self.L2_fea_conv = _conv3(nf * 2, nf)
+        self.L1_offset_conv1 = _conv3(nf * 2, nf)
+        self.L1_offset_conv2 = _conv3(nf * 2, nf)
+        self.L1_offset_conv3 = _conv3(nf, nf)
+        self.L1_dcnpack = dcn()
+        self.L1_fea_conv = _conv3(nf * 2, nf)
+        self.cas_offset_conv1 = _conv3(nf * 2, nf)
+        self.cas_offset_conv2 = _conv3(nf, nf)
+        self.cas_dcnpack = dcn()
+        self.lrelu = nn.LeakyReLU(negative_slope=0.1, inplace=True)
+
+    def forward(self, nbr_fea_l, ref_fea_l):
+        """nbr_fea_l, ref_fea_l: [L1, L2, L3] features, each [B, C, H, W] -> aligned L1 feature."""
+        act, cat = self.lrelu, torch.cat
+        off3 = act(self.L3_offset_conv2(act(self.L3_offset_conv1(cat([nbr_fea_l[2], ref_fea_l[2]], 1)))))
+        fea3 = act(self.L3_dcnpack([nbr_fea_l[2], off3]))
+        off2 = act(self.L2_offset_conv1(cat([nbr_fea_l[1], ref_fea_l[1]], 1)))
+        off2 = act(self.L2_offset_conv2(cat([off2, _up2(off3) * 2], 1)))  # offsets double with resolution
+        off2 = act(self.L2_offset_conv3(off2))
+        fea2 = self.L2_dcnpack([nbr_fea_l[1], off2])
+        fea2 = act(self.L2_fea_conv(cat([fea2, _up2(fea3)], 1)))
+        off1 = act(self.L1_offset_conv1(cat([nbr_fea_l[0], ref_fea_l[0]], 1)))
+        off1 = act(self.L1_offset_conv2(cat([off1, _up2(off2) * 2], 1)))
+        off1 = act(self.L1_offset_conv3(off1))
+        fea1 = self.L1_dcnpack([nbr_fea_l[0], off1])
+        fea1 = self.L1_fea_conv(cat([fea1, _up2(fea2)], 1))  # no activation here (reference :125)
+        offc = act(self.cas_offset_conv2(act(self.cas_offset_conv1(cat([fea1, ref_fea_l[0]], 1)))))
+        return act(self.cas_dcnpack([fea1, offc]))
+
+
+class TSA_Fusion(nn.Module):
+    """Temporal (correlation with the centre frame, sigmoid) and spatial (3-level pyramid) attention fusion."""
+
+    def __init__(self, nf=64, nframes=5, center=2):
+        super(TSA_Fusion, self).__init__()
+        self.center = center
+        c1 = lambda cin: nn.Conv2d(cin, nf, 1, 1, bias=True)  # noqa: E731
+        self.tAtt_1 = _conv3(nf, nf)
+        self.tAtt_2 = _conv3(nf, nf)
+        self.fea_fusion = c1(nframes * nf)
+        self.sAtt_1 = c1(nframes * nf)
+        self.maxpool = nn.MaxPool2d(3, stride=2, padding=1)
+        self.avgpool = nn.AvgPool2d(3, stride=2, padding=1)
+        self.sAtt_2 = c1(nf * 2)
+        self.sAtt_3 = _conv3(nf, nf)
+        self.sAtt_4 = c1(nf)
+        self.sAtt_5 = _conv3(nf, nf)
+        self.sAtt_L1 = c1(nf)
+        self.sAtt_L2 = _conv3(nf * 2, nf)
+        self.sAtt_L3 = _conv3(nf, nf)
+        self.sAtt_add_1 = c1(nf)
+        self.sAtt_add_2 = c1(nf)
+        self.lrelu = nn.LeakyReLU(negative_slope=0.1, inplace=True)
+
+    def forward(self, aligned_fea):
+        B, N, C, H, W = aligned_fea.size()
+        act = self.lrelu
+        emb_ref = self.tAtt_2(aligned_fea[:, self.center].clone())
+        emb = self.tAtt_1(aligned_fea.reshape(-1, C, H, W)).view(B, N, -1, H, W)
+        prob = torch.sigmoid((emb * emb_ref.unsqueeze(1)).sum(2, keepdim=True))  # [B, N, 1, H, W]
+        weighted = (aligned_fea * prob).reshape(B, N * C, H, W)
+        fea = act(self.fea_fusion(weighted))
+        att = act(self.sAtt_1(weighted))
+        att = act(self.sAtt_2(torch.cat([self.maxpool(att), self.avgpool(att)], 1)))
+        att_l = act(self.sAtt_L1(att))
+        att_l = act(self.sAtt_L2(torch.cat([self.maxpool(att_l), self.avgpool(att_l)], 1)))
+        att_l = _up2(act(self.sAtt_L3(att_l)))
+        att = act(self.sAtt_3(att)) + att_l
+        att = self.sAtt_5(_up2(act(self.sAtt_4(att))))
+        att_add = self.sAtt_add_2(act(self.sAtt_add_1(att)))
+        return fea * torch.sigmoid(att) * 2 + att_add
+
+
+class _EDVRBase(nn.Module):
+    """Shared body of EDVR (x4 pixel-shuffle tail) and EDVR_NoUp (same-resolution tail)."""
+    _upsample = True
+
+    def _build(self, nf, nc, nframes, groups, front_RBs, back_RBs, center, predeblur, HR_in, w_TSA):
+        self.nf, self.nc = nf, nc
+        self.center = nframes // 2 if center is None else center
+        self.is_predeblur = bool(predeblur)
+        self.HR_in = bool(HR_in)
+        self.w_TSA = w_TSA
+        self._cfg = dict(nf=nf, nc=nc, nframes=nframes, groups=groups, front_RBs=front_RBs, back_RBs=back_RBs,
+                         center=self.center, predeblur=self.is_predeblur, HR_in=self.HR_in, w_TSA=bool(w_TSA),
+                         upsample=self._upsample)
+        rb = functools.partial(arch_util.ResidualBlock_noBN, nf=nf)
+        if self._upsample and self.is_predeblur:
+            self.pre_deblur = Predeblur_ResNet_Pyramid(nf=nf, HR_in=self.HR_in)
+            self.conv_1x1 = nn.Conv2d(nf, nf, 1, 1, bias=True)
+        elif self._upsample and self.HR_in:
+            self.conv_first_1 = _conv3(nc, nf)
+            self.conv_first_2 = _conv3(nf, nf, 2)
+            self.conv_first_3 = _conv3(nf, nf, 2)
+        else:
+            self.conv_first = _conv3(nc, nf)
+        self.feature_extraction = arch_util.make_layer(rb, front_RBs)
+        self.fea_L2_conv1 = _conv3(nf, nf, 2)
+        self.fea_L2_conv2 = _conv3(nf, nf)
+        self.fea_L3_conv1 = _conv3(nf, nf, 2)
+        self.fea_L3_conv2 = _conv3(nf, nf)
+        self.pcd_align = PCD_Align(nf=nf, groups=groups)
+        if self.w_TSA:
+            self.tsa_fusion = TSA_Fusion(nf=nf, nframes=nframes, center=self.center)
+        else:
+            self.tsa_fusion = nn.Conv2d(nframes * nf, nf, 1, 1, bias=True)
+        self.recon_trunk = arch_util.make_layer(rb, back_RBs)
+        if self._upsample:
+            self.upconv1 = _conv3(nf, nf * 4)
+            self.upconv2 = _conv3(nf, 64 * 4)  # the reference hard-codes 64 from here on (:250-253)
+            self.pixel_shuffle = nn.PixelShuffle(2)
+        self.HRconv = _conv3(64, 64)
+        self.conv_last = _conv3(64, nc)
+        self.lrelu = nn.LeakyReLU(negative_slope=0.1, inplace=True)
+        # 'auto': engine for inference on CUDA, modules when autograd is needed.
+        # 'module' forces the nn.Module graph; 'engine' raises instead of falling back.
+        self.exec_path = os.environ.get("RVSR_EXEC_PATH", "auto")
+        # engine arithmetic: None = follow the input dtype (fp32 in -> fp32 SIMT kernels,
+        # fp16 in -> tensor-core kernels); 'fp16' runs fp32 inputs through the fp16 engine.
+        self.engine_precision = os.environ.get("RVSR_ENGINE_PRECISION") or None
+        self.__dict__['_engines'] = {}  # (device index, precision) -> [EDVREngine, weight stamp]
+
+    # ------------------------------------------------------------------ engine path
+    def _engine_ok(self, x):
+        if self.exec_path == "module":
+            return False
+        ok = (x.is_cuda and not self.is_predeblur and not self.HR_in and self.nf % 8 == 0
+              and x.dtype in (torch.float32, torch.float16)
+              and not (torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))))
+        if not ok and self.exec_path == "engine":
+            raise RuntimeError("realvsr_b200: exec_path='engine' but this call needs the module path "
+                               "(autograd enabled, non-CUDA input, or predeblur/HR_in)")
+        return ok
+
+    def _weight_stamp(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _get_engine(self, x):
+        prec = self.engine_precision or ("fp16" if x.dtype == torch.float16 else "fp32")
+        key = (x.device.index, prec)
+        slot = self._engines.get(key)
+        if slot is None:
+            slot = [_engine.EDVREngine(precision=prec, device=x.device, **self._cfg), None]
+            self._engines[key] = slot
+        stamp = self._weight_stamp()
+        if slot[1] != stamp:
+            slot[0].load_state_dict(self.state_dict(), strict=True)
+            slot[1] = stamp
+        return slot[0]
+
+    def forward(self, x):
+        if self._engine_ok(x):
+            return self._get_engine(x)(x)
+        return self._forward_modules(x)
+
+    # ------------------------------------------------------------------ module path (autograd-capable)
+    def _forward_modules(self, x):
+        B, N, C, H, W = x.size()
+        act = self.lrelu
+        x_center = x[:, self.center].contiguous()
+        frames = x.reshape(-1, C, H, W)
+        if self._upsample and self.is_predeblur:
+            l1 = self.conv_1x1(self.pre_deblur(frames))
+            if self.HR_in:
+                H, W = H // 4, W // 4
+        elif self._upsample and self.HR_in:
+            l1 = act(self.conv_first_3(act(self.conv_first_2(act(self.conv_first_1(frames))))))
+            H, W = H // 4, W // 4
+        else:
+            l1 = act(self.conv_first(frames))
+        l1 = self.feature_extraction(l1)
+        l2 = act(self.fea_L2_conv2(act(self.fea_L2_conv1(l1))))
+        l3 = act(self.fea_L3_conv2(act(self.fea_L3_conv1(l2))))
+        pyr = [l1.view(B, N, -1, H, W), l2.view(B, N, -1, H // 2, W // 2), l3.view(B, N, -1, H // 4, W // 4)]
+        ref = [lv[:, self.center].contiguous() for lv in pyr]
+        aligned = torch.stack([self.pcd_align([lv[:, i].contiguous() for lv in pyr], ref) for i in range(N)], 1)
+        fea = self.tsa_fusion(aligned if self.w_TSA else aligned.view(B, -1, H, W))
+        out = self.recon_trunk(fea)
+        if self._upsample:
+            out = act(self.pixel_shuffle(self.upconv1(out)))
+            out = act(self.pixel_shuffle(self.upconv2(out)))
+        out = self.conv_last(act(self.HRconv(out)))
+        if self._upsample and not self.HR_in:
+            base = F.interpolate(x_center, scale_factor=4, mode='bilinear', align_corners=False)
+        else:
+            base = x_center
+        return out + base
+
+
+class EDVR(_EDVRBase):
+    _upsample = True
+
+    def __init__(self, nf=64, nc=3, nframes=5, groups=8, front_RBs=5, back_RBs=10, center=None, predeblur=False,
+                 HR_in=False, w_TSA=True):
+        super(EDVR, self).__init__()
+        self._build(nf, nc, nframes, groups, front_RBs, back_RBs, center, predeblur, HR_in, w_TSA)
+
+
+class EDVR_NoUp(_EDVRBase):
+    """The variant RealVSR ships (scale 1): no pixel-shuffle tail, output = conv_last + centre frame.
+    As in the reference, predeblur / HR_in are accepted and ignored by this class (:335-339, :358-404)."""
+    _upsample = False
+
+    def __init__(self, nf=64, nc=3, nframes=5, groups=8, front_RBs=5, back_RBs=10, center=None, predeblur=False,
+                 HR_in=False, w_TSA=True):
+        super(EDVR_NoUp, self).__init__()
+        self._build(nf, nc, nframes, groups, front_RBs, back_RBs, center, False, False, w_TSA)
+        self.is_predeblur, self.HR_in = bool(predeblur), bool(HR_in)  # stored like the reference, unused
+        self._cfg.update(predeblur=False, HR_in=False)
+
+    def _engine_ok(self, x):
+        keep = self.is_predeblur, self.HR_in
+        self.is_predeblur = self.HR_in = False
+        try:
+            return super(EDVR_NoUp, self)._engine_ok(x)
+        finally:
+            self.is_predeblur, self.HR_in = keep
+
+    def _forward_modules(self, x):
+        keep = self.is_predeblur, self.HR_in
+        self.is_predeblur = self.HR_in = False
+        try:
+            return super(EDVR_NoUp, self)._forward_modules(x)
+        finally:
+            self.is_predeblur, self.HR_in = keep

@@ -1,0 +1,249 @@
+// api.cu -- the extern "C" surface declared in include/rvsr_b200.h.
+#include <new>
+
+#include "engine.cuh"
+
+struct rvsr_engine {
+    rvsr::Engine impl;
+    explicit rvsr_engine(const rvsr_edvr_config &c) : impl(c) {}
+};
+
+namespace rvsr {
+int expand_grouped_weight(const float *w, float *dst, int Cout, int C, int K, int groups, cudaStream_t s);
+
+namespace {
+struct Carver {  // carve the caller's workspace (or just count, when base == nullptr)
+    char *base;
+    size_t cap, off = 0;
+    bool ok = true;
+    void *take(size_t bytes) {
+        const size_t a = align_up(off, 256);
+        off = a + align_up(bytes, 256);
+        if (base == nullptr) return nullptr;
+        if (off > cap) { ok = false; return nullptr; }
+        return base + a;
+    }
+};
+
+struct DcnDims {
+    int B, C, H, W, Cout, kh, kw, stride, pad, dil, groups, dg, Ho, Wo, K;
+};
+int dcn_dims(DcnDims &d, int B, int C, int H, int W, int Cout, int kh, int kw, int stride, int pad, int dil,
+             int groups, int dg) {
+    // the reference's checks: deform_conv_cuda.cpp:511-516 and the shape math at :518-521
+    RVSR_CHECK_ARG(B >= 0 && C > 0 && H > 0 && W > 0 && Cout > 0, "dcn: bad tensor sizes");
+    RVSR_CHECK_ARG(kh > 0 && kw > 0 && stride > 0 && pad >= 0 && dil > 0, "dcn: bad conv parameters");
+    RVSR_CHECK_ARG(groups > 0 && C % groups == 0 && Cout % groups == 0,
+                   "Input shape and kernel channels wont match: (%d vs groups %d)", C, groups);
+    RVSR_CHECK_ARG(dg > 0 && C % dg == 0, "dcn: channels %d not divisible by deformable groups %d", C, dg);
+    d = {B, C, H, W, Cout, kh, kw, stride, pad, dil, groups, dg, 0, 0, kh * kw};
+    d.Ho = (H + 2 * pad - (dil * (kh - 1) + 1)) / stride + 1;
+    d.Wo = (W + 2 * pad - (dil * (kw - 1) + 1)) / stride + 1;
+    RVSR_CHECK_ARG(d.Ho > 0 && d.Wo > 0, "dcn: convolution input is too small");
+    RVSR_CHECK_ARG(d.K == 9 || d.K == 1, "dcn: only 3x3 / 1x1 kernels are built");
+    return RVSR_OK;
+}
+
+struct DcnWs {
+    void *x_c8;
+    float *off32, *mask32, *w32, *b32, *wdense, *wpack;
+};
+void carve_dcn(Carver &cv, const DcnDims &d, int dtype, DcnWs &ws) {
+    const size_t es = dtype == RVSR_F16 ? 2 : 4;
+    const size_t po = (size_t)d.Ho * d.Wo;
+    ws.x_c8 = cv.take((size_t)d.B * cdiv(d.C, 8) * d.H * d.W * 8 * es);
+    ws.off32 = ws.mask32 = ws.w32 = ws.b32 = nullptr;
+    if (dtype == RVSR_F16) {
+        ws.off32 = (float *)cv.take((size_t)d.B * d.dg * 2 * d.K * po * 4);
+        ws.mask32 = (float *)cv.take((size_t)d.B * d.dg * d.K * po * 4);
+        ws.w32 = (float *)cv.take((size_t)d.Cout * (d.C / d.groups) * d.K * 4);
+        ws.b32 = (float *)cv.take((size_t)d.Cout * 4);
+    }
+    ws.wdense = d.groups > 1 ? (float *)cv.take((size_t)d.Cout * d.C * d.K * 4) : nullptr;
+    ws.wpack = (float *)cv.take((size_t)cdiv(d.C, 8) * d.K * 8 * cdiv(d.Cout, 64) * 64 * 4);
+}
+
+template <typename T>
+int mdcn_fwd_t(const DcnDims &d, const void *input, const void *offset, const void *mask, const void *weight,
+               const void *bias, void *output, int dtype, const DcnWs &ws, int act, cudaStream_t s) {
+    const size_t po = (size_t)d.Ho * d.Wo;
+    RVSR_TRY((launch_pack_nchw<T, T>((const T *)input, (T *)ws.x_c8, d.B, d.C, d.H, d.W, s)));
+    const float *off = (const float *)offset, *msk = (const float *)mask, *w = (const float *)weight,
+                *b = (const float *)bias;
+    if (dtype == RVSR_F16) {
+        RVSR_TRY(launch_convert_f16_f32(offset, ws.off32, (long long)d.B * d.dg * 2 * d.K * po, s));
+        RVSR_TRY(launch_convert_f16_f32(mask, ws.mask32, (long long)d.B * d.dg * d.K * po, s));
+        RVSR_TRY(launch_convert_f16_f32(weight, ws.w32, (long long)d.Cout * (d.C / d.groups) * d.K, s));
+        if (bias) RVSR_TRY(launch_convert_f16_f32(bias, ws.b32, d.Cout, s));
+        off = ws.off32; msk = ws.mask32; w = ws.w32; b = bias ? ws.b32 : nullptr;
+    }
+    if (d.groups > 1) {
+        RVSR_TRY(expand_grouped_weight(w, ws.wdense, d.Cout, d.C, d.K, d.groups, s));
+        w = ws.wdense;
+    }
+    const int cout_pad = cdiv(d.Cout, 64) * 64, cin = d.C;
+    RVSR_TRY(pack_weight_simt(w, ws.wpack, d.Cout, d.C, d.kh, &cin, 1, cout_pad, s));
+    DcnOp op = {};
+    op.x.ptr = ws.x_c8; op.x.image_stride = (long long)cdiv(d.C, 8) * d.H * d.W * 8; op.x.C = d.C;
+    op.x.frames = 1; op.x.fixed_frame = -1;
+    op.offset = off; op.mask = msk;
+    op.offset_image_stride = (long long)d.dg * 2 * d.K * po;
+    op.mask_image_stride = (long long)d.dg * d.K * po;
+    op.w_simt = ws.wpack; op.bias = b; op.out = output; op.out_image_stride = (long long)d.Cout * po;
+    op.N = d.B; op.H = d.H; op.W = d.W; op.Cout = d.Cout; op.kh = d.kh; op.kw = d.kw; op.stride = d.stride;
+    op.pad = d.pad; op.dil = d.dil; op.dg = d.dg; op.act = act; op.out_mode = OUT_NCHW_T;
+    return launch_dcn_simt<T>(op, s);
+}
+}  // namespace
+}  // namespace rvsr
+
+using namespace rvsr;
+
+extern "C" {
+
+int rvsr_version(void) { return 100; }
+const char *rvsr_last_error(void) { return get_error(); }
+
+int rvsr_device_ok(void) {
+    int dev = 0;
+    cudaDeviceProp p;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&p, dev) != cudaSuccess) {
+        set_error("no usable CUDA device");
+        return RVSR_E_CUDA;
+    }
+    return p.major == 10 ? 1 : 0;
+}
+
+size_t rvsr_mdcn_fwd_workspace_bytes(int B, int C, int H, int W, int Cout, int kh, int kw, int stride, int pad,
+                                     int dil, int groups, int dg, int dtype) {
+    DcnDims d;
+    if (dcn_dims(d, B, C, H, W, Cout, kh, kw, stride, pad, dil, groups, dg) != RVSR_OK) return 0;
+    Carver cv{nullptr, 0};
+    DcnWs ws;
+    carve_dcn(cv, d, dtype, ws);
+    return cv.off + 256;
+}
+
+int rvsr_mdcn_fwd(const void *input, const void *offset, const void *mask, const void *weight, const void *bias,
+                  void *output, int B, int C, int H, int W, int Cout, int kh, int kw, int stride, int pad, int dil,
+                  int groups, int dg, int dtype, void *workspace, size_t workspace_bytes, void *stream) {
+    DcnDims d;
+    RVSR_TRY(dcn_dims(d, B, C, H, W, Cout, kh, kw, stride, pad, dil, groups, dg));
+    RVSR_CHECK_ARG(dtype == RVSR_F32 || dtype == RVSR_F16, "dcn: bad dtype %d", dtype);
+    if (B == 0) return RVSR_OK;
+    RVSR_CHECK_ARG(input && offset && mask && weight && output && workspace, "dcn: null buffer");
+    Carver cv{(char *)workspace, workspace_bytes};
+    const size_t mis = (size_t)((uintptr_t)workspace % 256);
+    if (mis) { cv.base += 256 - mis; cv.cap -= 256 - mis; }
+    DcnWs ws;
+    carve_dcn(cv, d, dtype, ws);
+    if (!cv.ok) { set_error("dcn: workspace too small (%zu bytes)", workspace_bytes); return RVSR_E_WORKSPACE; }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == RVSR_F16)
+        return mdcn_fwd_t<__half>(d, input, offset, mask, weight, bias, output, dtype, ws, RVSR_ACT_NONE, s);
+    return mdcn_fwd_t<float>(d, input, offset, mask, weight, bias, output, dtype, ws, RVSR_ACT_NONE, s);
+}
+
+size_t rvsr_mdcn_bwd_workspace_bytes(int, int, int, int, int, int, int, int, int, int, int, int, int) { return 0; }
+int rvsr_mdcn_bwd(const void *, const void *, const void *, const void *, const void *, void *, void *, void *,
+                  void *, void *, int, int, int, int, int, int, int, int, int, int, int, int, int, void *, size_t,
+                  void *) {
+    set_error("rvsr_mdcn_bwd: not built yet");
+    return RVSR_E_UNSUPPORTED;
+}
+
+size_t rvsr_mdcn_pack_fwd_workspace_bytes(int, int, int, int, int, int, int) { return 0; }
+int rvsr_mdcn_pack_fwd(const void *, const void *, const void *, const void *, const void *, const void *, void *,
+                       int, int, int, int, int, int, int, int, void *, size_t, void *) {
+    set_error("rvsr_mdcn_pack_fwd: not built yet");
+    return RVSR_E_UNSUPPORTED;
+}
+
+int rvsr_engine_create(const rvsr_edvr_config *cfg, rvsr_engine **out) {
+    RVSR_CHECK_ARG(cfg != nullptr && out != nullptr, "engine_create: null argument");
+    RVSR_CHECK_ARG(cfg->nf > 0 && cfg->nc > 0 && cfg->nc <= 8 && cfg->nframes > 0 && cfg->groups > 0,
+                   "engine_create: bad config");
+    RVSR_CHECK_ARG(cfg->front_RBs >= 0 && cfg->back_RBs >= 0, "engine_create: bad block counts");
+    RVSR_CHECK_ARG(cfg->precision == RVSR_F32 || cfg->precision == RVSR_F16, "engine_create: bad precision");
+    if (cfg->predeblur || cfg->HR_in) {
+        set_error("engine_create: predeblur / HR_in are not built (use the module path)");
+        return RVSR_E_UNSUPPORTED;
+    }
+    if (cfg->nf % 8 != 0 || cfg->nf % cfg->groups != 0 || cfg->nframes > RVSR_MAX_SRC) {
+        set_error("engine_create: needs nf %% 8 == 0, nf %% groups == 0, nframes <= %d", RVSR_MAX_SRC);
+        return RVSR_E_UNSUPPORTED;
+    }
+    if (!cfg->upsample && cfg->nf != 64) {
+        set_error("engine_create: EDVR_NoUp needs nf == 64 (HRconv is hard-wired to 64 channels, EDVR_arch.py:348)");
+        return RVSR_E_INVALID;
+    }
+    RVSR_CHECK_ARG(cfg->center < cfg->nframes, "engine_create: center %d >= nframes", cfg->center);
+    rvsr_engine *e = new (std::nothrow) rvsr_engine(*cfg);
+    RVSR_CHECK_ARG(e != nullptr, "engine_create: out of host memory");
+    *out = e;
+    return RVSR_OK;
+}
+void rvsr_engine_destroy(rvsr_engine *e) { delete e; }
+int rvsr_engine_set_weight(rvsr_engine *e, const char *name, const float *dev_ptr, const int64_t *shape, int ndim,
+                           void *stream) {
+    RVSR_CHECK_ARG(e != nullptr, "null engine");
+    return e->impl.set_weight(name, dev_ptr, shape, ndim, (cudaStream_t)stream);
+}
+int rvsr_engine_finalize(rvsr_engine *e, void *stream) {
+    RVSR_CHECK_ARG(e != nullptr, "null engine");
+    return e->impl.finalize((cudaStream_t)stream);
+}
+int rvsr_engine_num_weights(const rvsr_engine *e) { return e ? (int)e->impl.names().size() : 0; }
+const char *rvsr_engine_weight_name(const rvsr_engine *e, int i) {
+    if (e == nullptr || i < 0 || i >= (int)e->impl.names().size()) return nullptr;
+    return e->impl.names()[i].c_str();
+}
+size_t rvsr_engine_workspace_bytes(const rvsr_engine *e, int B, int H, int W) {
+    return e ? const_cast<rvsr_engine *>(e)->impl.workspace_bytes(B, H, W) : 0;
+}
+int rvsr_engine_forward(rvsr_engine *e, const void *x, int x_dtype, void *out, int out_dtype, int B, int H, int W,
+                        void *workspace, size_t workspace_bytes, void *stream) {
+    RVSR_CHECK_ARG(e != nullptr, "null engine");
+    return e->impl.forward(x, x_dtype, out, out_dtype, B, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+int rvsr_engine_forward_host(rvsr_engine *e, const void *x_host, int x_dtype, void *out_host, int out_dtype, int B,
+                             int H, int W, void *dev_in, void *dev_out, void *workspace, size_t workspace_bytes,
+                             void *stream) {
+    RVSR_CHECK_ARG(e != nullptr, "null engine");
+    RVSR_CHECK_ARG(x_host && out_host && dev_in && dev_out, "forward_host: null buffer");
+    const rvsr_edvr_config &c = e->impl.cfg();
+    cudaStream_t s = (cudaStream_t)stream;
+    const int sc = c.upsample ? 4 : 1;
+    const size_t in_bytes = (size_t)B * c.nframes * c.nc * H * W * (x_dtype == RVSR_F16 ? 2 : 4);
+    const size_t out_bytes = (size_t)B * c.nc * H * sc * W * sc * (out_dtype == RVSR_F16 ? 2 : 4);
+    RVSR_CUDA(cudaMemcpyAsync(dev_in, x_host, in_bytes, cudaMemcpyHostToDevice, s));
+    RVSR_TRY(e->impl.forward(dev_in, x_dtype, dev_out, out_dtype, B, H, W, workspace, workspace_bytes, s));
+    RVSR_CUDA(cudaMemcpyAsync(out_host, dev_out, out_bytes, cudaMemcpyDeviceToHost, s));
+    return RVSR_OK;
+}
+int rvsr_engine_last_launch_count(const rvsr_engine *e) { return e ? e->impl.last_launches() : 0; }
+int rvsr_engine_set_profiling(rvsr_engine *e, int on) {
+    RVSR_CHECK_ARG(e != nullptr, "null engine");
+    e->impl.set_profiling(on != 0);
+    return RVSR_OK;
+}
+int rvsr_engine_profile_collect(rvsr_engine *e) {
+    RVSR_CHECK_ARG(e != nullptr, "null engine");
+    return e->impl.prof_collect();
+}
+int rvsr_engine_profile_entry(const rvsr_engine *e, int i, char *label, int label_cap, float *ms, double *flops,
+                              double *bytes) {
+    RVSR_CHECK_ARG(e != nullptr && i >= 0 && i < (int)e->impl.prof().size(), "profile_entry: bad index");
+    const ProfEntry &p = e->impl.prof()[i];
+    if (label != nullptr && label_cap > 0) snprintf(label, (size_t)label_cap, "%s", p.label.c_str());
+    if (ms) *ms = p.ms;
+    if (flops) *flops = p.flops;
+    if (bytes) *bytes = p.bytes;
+    return RVSR_OK;
+}
+int rvsr_engine_read_tap(rvsr_engine *e, const char *name, float *dst_dev, size_t dst_elems, void *stream) {
+    RVSR_CHECK_ARG(e != nullptr, "null engine");
+    return e->impl.read_tap(name, dst_dev, dst_elems, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,177 @@
+// common.cuh -- shared helpers for the rvsr_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "../../include/rvsr_b200.h"
+
+namespace rvsr {
+
+// ---------------------------------------------------------------- errors
+void set_error(const char *fmt, ...);
+const char *get_error();
+
+#define RVSR_CHECK_ARG(cond, ...)                 \
+    do {                                          \
+        if (!(cond)) {                            \
+            ::rvsr::set_error(__VA_ARGS__);       \
+            return RVSR_E_INVALID;                \
+        }                                         \
+    } while (0)
+
+#define RVSR_CUDA(expr)                                                                   \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            ::rvsr::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),     \
+                              __FILE__, __LINE__);                                        \
+            return RVSR_E_CUDA;                                                           \
+        }                                                                                 \
+    } while (0)
+
+#define RVSR_LAUNCH_CHECK()                                                               \
+    do {                                                                                  \
+        cudaError_t _e = cudaGetLastError();                                              \
+        if (_e != cudaSuccess) {                                                          \
+            ::rvsr::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \
+                              __FILE__, __LINE__);                                        \
+            return RVSR_E_CUDA;                                                           \
+        }                                                                                 \
+    } while (0)
+
+#define RVSR_TRY(expr)            \
+    do {                          \
+        int _rc = (expr);         \
+        if (_rc != RVSR_OK) return _rc; \
+    } while (0)
+
+// ---------------------------------------------------------------- scalar type helpers
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
+
+// One pixel of one channel block: 8 channels.  16 B for half, 32 B for float.
+template <typename T> struct alignas(sizeof(T) * 8) Vec8 { T v[8]; };
+
+template <typename T> __device__ __forceinline__ void load8(const T *p, float (&f)[8]);
+template <> __device__ __forceinline__ void load8<float>(const float *p, float (&f)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+template <> __device__ __forceinline__ void load8<__half>(const __half *p, float (&f)[8]) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4 *>(p));
+    const __half2 *h = reinterpret_cast<const __half2 *>(&a);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 t = __half22float2(h[i]);
+        f[2 * i] = t.x; f[2 * i + 1] = t.y;
+    }
+}
+template <typename T> __device__ __forceinline__ void store8(T *p, const float (&f)[8]);
+template <> __device__ __forceinline__ void store8<float>(float *p, const float (&f)[8]) {
+    reinterpret_cast<float4 *>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+    reinterpret_cast<float4 *>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
+template <> __device__ __forceinline__ void store8<__half>(__half *p, const float (&f)[8]) {
+    uint4 a;
+    __half2 *h = reinterpret_cast<__half2 *>(&a);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+    *reinterpret_cast<uint4 *>(p) = a;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == RVSR_ACT_LRELU) return v > 0.f ? v : 0.1f * v;
+    if (act == RVSR_ACT_RELU) return v > 0.f ? v : 0.f;
+    return v;
+}
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + __expf(-v)); }
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---------------------------------------------------------------- op descriptors
+// A conv input: a channel-blocked tensor [n][C/8][H][W][8].  `frames`/`fixed_frame`
+// implement the PCD "reference frame" broadcast (EDVR_arch.py:291-303): with
+// fixed_frame >= 0, image n reads image (n / frames) * frames + fixed_frame.
+struct Src {
+    const void *ptr;
+    long long image_stride;  // elements between consecutive images
+    int C;                   // channels (multiple of 8 in storage)
+    int frames, fixed_frame;
+};
+#define RVSR_MAX_SRC 7
+
+enum OutMode {
+    OUT_C8 = 0,           // channel-blocked, same resolution
+    OUT_C8_SHUFFLE2 = 1,  // nn.PixelShuffle(2) fused into the store (EDVR_arch.py:311-312)
+    OUT_PLANAR_F32 = 2,   // [n][Cout][H][W] fp32; channels >= sig_from get a sigmoid (offset/mask conv)
+    OUT_NCHW_T = 3,       // [n][Cout][H][W] of T (operator-level API)
+};
+
+struct ConvOp {
+    Src src[RVSR_MAX_SRC];
+    int nsrc;
+    const float *w_simt;   // packed fp32 [sum chunks][taps][8][CoutPad]
+    const void *w_tc;      // packed fp16 UMMA layout (tc kernels) or null
+    const float *bias;     // [Cout] fp32 or null
+    void *out;
+    long long out_image_stride;
+    const void *residual;  // same layout as out (OUT_C8 only), added after the activation
+    long long res_image_stride;
+    int N, H, W;           // images, input height/width
+    int Cout, ks, stride;  // pad = ks / 2
+    int act, out_mode, sig_from;
+};
+
+struct DcnOp {
+    Src x;                 // sampled features
+    const float *offset;   // planar fp32 [n][dg*2*K][Ho][Wo]
+    const float *mask;     // planar fp32 [n][dg*K][Ho][Wo], already sigmoid-ed
+    long long offset_image_stride, mask_image_stride;
+    const float *w_simt;   // packed like ConvOp
+    const void *w_tc;
+    const float *bias;
+    void *out;
+    long long out_image_stride;
+    int N, H, W, Cout, kh, kw, stride, pad, dil, dg;
+    int act, out_mode;
+};
+
+// ---------------------------------------------------------------- kernel launchers (simt_kernels.cu)
+template <typename T> int launch_conv_simt(const ConvOp &op, cudaStream_t s);
+template <typename T> int launch_dcn_simt(const DcnOp &op, cudaStream_t s);
+template <typename T, typename Tin>
+int launch_pack_nchw(const Tin *src, T *dst, int N, int C, int H, int W, cudaStream_t s);
+template <typename T, typename Tout>
+int launch_unpack_nchw(const T *src, Tout *dst, int N, int C, int H, int W, cudaStream_t s);
+template <typename T>
+int launch_upsample2x(const T *src, T *dst, int N, int C, int H, int W, float scale, cudaStream_t s);
+template <typename T>
+int launch_pool_maxavg(const T *src, T *dst_max, T *dst_avg, int N, int C, int H, int W, cudaStream_t s);
+template <typename T>
+int launch_tsa_temporal(const T *emb, const T *emb_ref, const T *aligned, T *out, int B, int frames,
+                        int C, int H, int W, cudaStream_t s);
+template <typename T>
+int launch_tsa_final(const T *fea, const T *att, const T *att_add, T *out, long long n, cudaStream_t s);
+template <typename T, typename Tin, typename Tout>
+int launch_final_add(const T *res_c8, const Tin *x, Tout *out, int B, int frames, int center, int nc,
+                     int H, int W, int scale, cudaStream_t s);
+int launch_convert_f16_f32(const void *src, float *dst, long long n, cudaStream_t s);
+int launch_fill_f32(float *dst, float v, long long n, cudaStream_t s);
+
+// weight packing (host-callable, device work on stream)
+int pack_weight_simt(const float *w_oihw, float *dst, int Cout, int Cin_total, int ks,
+                     const int *src_channels, int nsrc, int cout_pad, cudaStream_t s);
+int pack_weight_dcn_simt(const float *w_oihw, float *dst, int Cout, int C, int K, int cout_pad,
+                         cudaStream_t s);
+
+}  // namespace rvsr

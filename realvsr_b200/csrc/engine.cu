@@ -1,0 +1,543 @@
+// engine.cu -- EDVR / EDVR_NoUp inference as one C++ call (see include/rvsr_b200.h).
+//
+// What it replaces in the reference (IanYeung/RealVSR, codes/models/archs/EDVR_arch.py):
+//   EDVR.forward :258-320, EDVR_NoUp.forward :358-404, PCD_Align.forward :98-132,
+//   TSA_Fusion.forward :168-208, ResidualBlock_noBN (arch_util.py:135-139),
+//   ModulatedDeformConvPack.forward (dcn/deform_conv.py:274-292).
+//
+// Differences in structure (not in results):
+//   * the N per-frame PCD passes the reference runs in a Python loop (:297-303) are one
+//     batch of B*N images; the "reference frame" operand is a broadcast view, not a clone;
+//   * torch.cat([a, b]) -> conv is a two-source convolution (no concat copy);
+//   * activation, bias, residual add, pixel-shuffle are conv epilogues;
+//   * activations live in a channel-blocked layout [N][C/8][H][W][8] so that one pixel of
+//     one deformable group (nf/groups = 8 channels in every shipped config) is one 128-bit load.
+#include "engine.cuh"
+
+#include <stdarg.h>
+
+namespace rvsr {
+
+// ---------------------------------------------------------------- error string
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char *get_error() { return g_err; }
+
+// ---------------------------------------------------------------- state_dict contract
+void Engine::expect(const std::string &name, std::vector<int64_t> shape) {
+    names_.push_back(name);
+    RawWeight w;
+    w.shape = std::move(shape);
+    raw_[name] = w;
+}
+void Engine::expect_conv(const std::string &name, int co, int ci, int k) {
+    expect(name + ".weight", {co, ci, k, k});
+    expect(name + ".bias", {co});
+}
+
+Engine::Engine(const rvsr_edvr_config &cfg) : cfg_(cfg) {
+    if (cfg_.center < 0) cfg_.center = cfg_.nframes / 2;
+    const int nf = cfg_.nf, N = cfg_.nframes;
+    // Same order as the reference modules register their parameters.
+    expect_conv("conv_first", nf, cfg_.nc, 3);
+    for (int i = 0; i < cfg_.front_RBs; ++i) {
+        expect_conv("feature_extraction." + std::to_string(i) + ".conv1", nf, nf, 3);
+        expect_conv("feature_extraction." + std::to_string(i) + ".conv2", nf, nf, 3);
+    }
+    for (const char *n : {"fea_L2_conv1", "fea_L2_conv2", "fea_L3_conv1", "fea_L3_conv2"}) expect_conv(n, nf, nf, 3);
+    const std::string p = "pcd_align.";
+    auto dcn = [&](const std::string &n) {
+        expect(p + n + ".weight", {nf, nf, 3, 3});
+        expect(p + n + ".bias", {nf});
+        expect_conv(p + n + ".conv_offset_mask", cfg_.groups * 27, nf, 3);
+    };
+    expect_conv(p + "L3_offset_conv1", nf, 2 * nf, 3);
+    expect_conv(p + "L3_offset_conv2", nf, nf, 3);
+    dcn("L3_dcnpack");
+    expect_conv(p + "L2_offset_conv1", nf, 2 * nf, 3);
+    expect_conv(p + "L2_offset_conv2", nf, 2 * nf, 3);
+    expect_conv(p + "L2_offset_conv3", nf, nf, 3);
+    dcn("L2_dcnpack");
+    expect_conv(p + "L2_fea_conv", nf, 2 * nf, 3);
+    expect_conv(p + "L1_offset_conv1", nf, 2 * nf, 3);
+    expect_conv(p + "L1_offset_conv2", nf, 2 * nf, 3);
+    expect_conv(p + "L1_offset_conv3", nf, nf, 3);
+    dcn("L1_dcnpack");
+    expect_conv(p + "L1_fea_conv", nf, 2 * nf, 3);
+    expect_conv(p + "cas_offset_conv1", nf, 2 * nf, 3);
+    expect_conv(p + "cas_offset_conv2", nf, nf, 3);
+    dcn("cas_dcnpack");
+    if (cfg_.w_TSA) {
+        const std::string t = "tsa_fusion.";
+        expect_conv(t + "tAtt_1", nf, nf, 3);
+        expect_conv(t + "tAtt_2", nf, nf, 3);
+        expect_conv(t + "fea_fusion", nf, N * nf, 1);
+        expect_conv(t + "sAtt_1", nf, N * nf, 1);
+        expect_conv(t + "sAtt_2", nf, 2 * nf, 1);
+        expect_conv(t + "sAtt_3", nf, nf, 3);
+        expect_conv(t + "sAtt_4", nf, nf, 1);
+        expect_conv(t + "sAtt_5", nf, nf, 3);
+        expect_conv(t + "sAtt_L1", nf, nf, 1);
+        expect_conv(t + "sAtt_L2", nf, 2 * nf, 3);
+        expect_conv(t + "sAtt_L3", nf, nf, 3);
+        expect_conv(t + "sAtt_add_1", nf, nf, 1);
+        expect_conv(t + "sAtt_add_2", nf, nf, 1);
+    } else {
+        expect_conv("tsa_fusion", nf, N * nf, 1);
+    }
+    for (int i = 0; i < cfg_.back_RBs; ++i) {
+        expect_conv("recon_trunk." + std::to_string(i) + ".conv1", nf, nf, 3);
+        expect_conv("recon_trunk." + std::to_string(i) + ".conv2", nf, nf, 3);
+    }
+    if (cfg_.upsample) {
+        expect_conv("upconv1", nf * 4, nf, 3);
+        expect_conv("upconv2", 64 * 4, nf, 3);  // literal 64, EDVR_arch.py:250
+    }
+    expect_conv("HRconv", 64, 64, 3);
+    expect_conv("conv_last", cfg_.nc, 64, 3);
+}
+
+Engine::~Engine() {
+    prof_clear();
+    for (void *p : owned_) cudaFree(p);
+}
+
+int Engine::set_weight(const char *name, const float *dev_ptr, const int64_t *shape, int ndim, cudaStream_t s) {
+    auto it = raw_.find(name ? name : "");
+    RVSR_CHECK_ARG(it != raw_.end(), "unexpected key in state_dict: \"%s\"", name ? name : "(null)");
+    RawWeight &w = it->second;
+    bool same = (int)w.shape.size() == ndim;
+    for (int i = 0; same && i < ndim; ++i) same = w.shape[i] == shape[i];
+    RVSR_CHECK_ARG(same, "size mismatch for %s", name);
+    RVSR_CHECK_ARG(dev_ptr != nullptr, "null pointer for %s", name);
+    size_t n = 1;
+    for (int64_t d : w.shape) n *= (size_t)d;
+    if (w.dev == nullptr) {
+        RVSR_CUDA(cudaMalloc(&w.dev, n * sizeof(float)));
+        owned_.push_back(w.dev);
+    }
+    RVSR_CUDA(cudaMemcpyAsync(w.dev, dev_ptr, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    w.set = true;
+    finalized_ = false;
+    return RVSR_OK;
+}
+
+int Engine::finalize(cudaStream_t s) {
+    for (const auto &n : names_)
+        if (!raw_[n].set) {
+            set_error("missing key in state_dict: \"%s\"", n.c_str());
+            return RVSR_E_STATE;
+        }
+    for (const auto &n : names_) {
+        const size_t pos = n.rfind(".weight");
+        if (pos == std::string::npos || pos + 7 != n.size()) continue;
+        const std::string base = n.substr(0, pos);
+        const RawWeight &w = raw_[n];
+        PackedConv &pc = packed_[base];
+        pc.Cout = (int)w.shape[0];
+        pc.Cin = (int)w.shape[1];
+        pc.ks = (int)w.shape[2];
+        pc.bias = raw_[base + ".bias"].dev;
+        const int cout_pad = cdiv(pc.Cout, 64) * 64;
+        const size_t bytes = (size_t)cdiv(pc.Cin, 8) * pc.ks * pc.ks * 8 * cout_pad * sizeof(float);
+        if (pc.w_simt == nullptr) {
+            RVSR_CUDA(cudaMalloc(&pc.w_simt, bytes));
+            owned_.push_back(pc.w_simt);
+        }
+        const int cin = pc.Cin;
+        RVSR_TRY(pack_weight_simt(w.dev, pc.w_simt, pc.Cout, pc.Cin, pc.ks, &cin, 1, cout_pad, s));
+        if (cfg_.precision == RVSR_F16) {
+            const bool is_dcn = base.size() > 8 && base.compare(base.size() - 8, 8, "_dcnpack") == 0;
+            const bool shuffle = (base == "upconv1" || base == "upconv2");
+            const size_t tb = is_dcn ? tc_dcn_weight_bytes(pc.Cout, pc.Cin, pc.ks * pc.ks)
+                                     : tc_conv_weight_bytes(pc.Cout, pc.Cin, pc.ks);
+            if (tb > 0) {
+                if (pc.w_tc == nullptr) {
+                    RVSR_CUDA(cudaMalloc(&pc.w_tc, tb));
+                    owned_.push_back(pc.w_tc);
+                }
+                if (is_dcn)
+                    RVSR_TRY(pack_weight_dcn_tc(w.dev, pc.w_tc, pc.Cout, pc.Cin, pc.ks * pc.ks, s));
+                else
+                    RVSR_TRY(pack_weight_tc(w.dev, pc.w_tc, pc.Cout, pc.Cin, pc.ks, shuffle ? 1 : 0, s));
+            }
+        }
+    }
+    finalized_ = true;
+    return RVSR_OK;
+}
+
+// ---------------------------------------------------------------- forward plan
+namespace {
+
+template <typename T> struct Plan {
+    Engine *eng;
+    Arena &ar;
+    bool dry;
+    cudaStream_t s;
+    const std::map<std::string, PackedConv> &packed;
+    bool use_tc;
+    int launches = 0;
+    int rc = RVSR_OK;
+
+    Act make(int N, int C, int H, int W) {
+        Act a;
+        a.N = N; a.C = C; a.H = H; a.W = W;
+        a.p = ar.alloc((size_t)a.elems() * sizeof(T));
+        if (a.p == nullptr && rc == RVSR_OK) {
+            set_error("workspace too small");
+            rc = RVSR_E_WORKSPACE;
+        }
+        return a;
+    }
+    static Src src_of(const Act &a) {
+        Src r;
+        r.ptr = a.p; r.image_stride = a.image_elems(); r.C = a.C; r.frames = 1; r.fixed_frame = -1;
+        return r;
+    }
+    // image n reads the `frame`-th image of its group of `frames` (PCD reference features)
+    static Src src_fixed(const Act &a, int frames, int frame) {
+        Src r = src_of(a);
+        r.frames = frames; r.fixed_frame = frame;
+        return r;
+    }
+    // B images, image b reads image b*frames + frame of `a` (TSA: per-frame slices of a [B*N] tensor)
+    static Src src_slice(const Act &a, int frames, int frame) {
+        Src r = src_of(a);
+        r.ptr = reinterpret_cast<const T *>(a.p) + (long long)frame * a.image_elems();
+        r.image_stride = a.image_elems() * frames;
+        return r;
+    }
+    const PackedConv *get(const std::string &name) {
+        auto it = packed.find(name);
+        if (it == packed.end()) {
+            if (rc == RVSR_OK) { set_error("engine: no packed weights for %s", name.c_str()); rc = RVSR_E_STATE; }
+            return nullptr;
+        }
+        return &it->second;
+    }
+    void note(int r) {
+        ++launches;
+        if (r != RVSR_OK && rc == RVSR_OK) rc = r;
+    }
+    // every kernel launch goes through here: counted, and (in profiling mode) bracketed by
+    // CUDA events on the launching stream with its algorithmic flops / bytes attached
+    template <typename F> void launch(const std::string &label, double flops, double bytes, F &&f) {
+        ProfEntry *pe = eng->prof_begin(label, flops, bytes, s);
+        note(f());
+        eng->prof_end(pe, s);
+    }
+
+    // generic convolution with fused epilogue; out allocated here
+    Act conv(const std::string &name, std::initializer_list<Src> srcs, int N, int H, int W, int act,
+             int stride = 1, int out_mode = OUT_C8, const Act *residual = nullptr, int sig_from = 1 << 30) {
+        const PackedConv *pc = get(name);
+        if (pc == nullptr) return Act();
+        const int Ho = stride == 1 ? H : (H - 1) / 2 + 1, Wo = stride == 1 ? W : (W - 1) / 2 + 1;
+        Act o;
+        if (out_mode == OUT_C8_SHUFFLE2) {
+            o = make(N, pc->Cout / 4, 2 * Ho, 2 * Wo);
+        } else if (out_mode == OUT_PLANAR_F32) {
+            o.N = N; o.C = pc->Cout; o.H = Ho; o.W = Wo;
+            o.p = ar.alloc((size_t)N * pc->Cout * Ho * Wo * sizeof(float));
+            if (o.p == nullptr && rc == RVSR_OK) { set_error("workspace too small"); rc = RVSR_E_WORKSPACE; }
+        } else {
+            o = make(N, pc->Cout, Ho, Wo);
+        }
+        if (dry || rc != RVSR_OK) return o;
+        ConvOp op = {};
+        int cin = 0;
+        for (const Src &sr : srcs) { op.src[op.nsrc++] = sr; cin += sr.C; }
+        if (cin != pc->Cin && !(pc->Cin < 8 && cin == pc->Cin)) {
+            set_error("engine: %s expects %d input channels, got %d", name.c_str(), pc->Cin, cin);
+            rc = RVSR_E_INVALID;
+            return o;
+        }
+        op.w_simt = pc->w_simt; op.w_tc = pc->w_tc; op.bias = pc->bias;
+        op.out = o.p;
+        op.out_image_stride = out_mode == OUT_PLANAR_F32 ? (long long)pc->Cout * Ho * Wo : o.image_elems();
+        if (residual != nullptr) { op.residual = residual->p; op.res_image_stride = residual->image_elems(); }
+        op.N = N; op.H = H; op.W = W; op.Cout = pc->Cout; op.ks = pc->ks; op.stride = stride;
+        op.act = act; op.out_mode = out_mode; op.sig_from = sig_from;
+        const double px = (double)N * Ho * Wo;
+        const double flops = 2.0 * cin * pc->Cout * pc->ks * pc->ks * px;
+        const double obytes = out_mode == OUT_PLANAR_F32 ? px * pc->Cout * 4 : px * pc->Cout * sizeof(T);
+        const double bytes = (double)N * H * W * cin * sizeof(T) + obytes + (residual ? obytes : 0);
+        const bool tc = use_tc && tc_conv_supported(op);
+        launch((tc ? "tc:" : "simt:") + name, flops, bytes, [&] { return tc ? launch_conv_tc(op, s) : launch_conv_simt<T>(op, s); });
+        return o;
+    }
+
+    // ModulatedDeformConvPack with extra_offset_mask=True (deform_conv.py:274-292)
+    Act dcn_pack(const std::string &name, const Act &x, const Act &feat, int dg, int act) {
+        const int K = 9;
+        // conv_offset_mask -> planar fp32 [N][27*dg][H][W]; first 18*dg = offsets (o1|o2 of chunk(3)
+        // concatenated back = the first two thirds), last 9*dg = sigmoid(mask)
+        Act om = conv(name + ".conv_offset_mask", {src_of(feat)}, feat.N, feat.H, feat.W, RVSR_ACT_NONE, 1,
+                      OUT_PLANAR_F32, nullptr, 2 * dg * K);
+        const PackedConv *pc = get(name);
+        if (pc == nullptr) return Act();
+        Act o = make(x.N, pc->Cout, x.H, x.W);
+        if (dry || rc != RVSR_OK) return o;
+        DcnOp op = {};
+        op.x = src_of(x);
+        op.offset = reinterpret_cast<const float *>(om.p);
+        op.mask = op.offset + (long long)2 * dg * K * x.H * x.W;
+        op.offset_image_stride = op.mask_image_stride = (long long)3 * dg * K * x.H * x.W;
+        op.w_simt = pc->w_simt; op.w_tc = pc->w_tc; op.bias = pc->bias;
+        op.out = o.p; op.out_image_stride = o.image_elems();
+        op.N = x.N; op.H = x.H; op.W = x.W; op.Cout = pc->Cout;
+        op.kh = op.kw = 3; op.stride = 1; op.pad = 1; op.dil = 1; op.dg = dg;
+        op.act = act; op.out_mode = OUT_C8;
+        const double px = (double)x.N * x.H * x.W;
+        const double flops = (2.0 * x.C * pc->Cout * K + 8.0 * x.C * K) * px;  // contraction + gather
+        const double bytes = px * (x.C * sizeof(T) + 3.0 * dg * K * 4 + pc->Cout * sizeof(T));
+        const bool tc = use_tc && tc_dcn_supported(op);
+        launch((tc ? "tc:" : "simt:") + name, flops, bytes, [&] { return tc ? launch_dcn_tc(op, s) : launch_dcn_simt<T>(op, s); });
+        return o;
+    }
+    Act up2(const Act &a, float scale) {
+        Act o = make(a.N, a.C, 2 * a.H, 2 * a.W);
+        if (!dry && rc == RVSR_OK)
+            launch("glue:upsample2x", 0, (double)a.elems() * sizeof(T) * 5, [&] {
+                return launch_upsample2x<T>((const T *)a.p, (T *)o.p, a.N, a.C, a.H, a.W, scale, s); });
+        return o;
+    }
+    void pools(const Act &a, Act &mx, Act &av) {
+        mx = make(a.N, a.C, (a.H - 1) / 2 + 1, (a.W - 1) / 2 + 1);
+        av = make(a.N, a.C, mx.H, mx.W);
+        if (!dry && rc == RVSR_OK)
+            launch("glue:pool_maxavg", 0, (double)a.elems() * sizeof(T) * 1.5, [&] {
+                return launch_pool_maxavg<T>((const T *)a.p, (T *)mx.p, (T *)av.p, a.N, a.C, a.H, a.W, s); });
+    }
+    Act resblocks(const std::string &prefix, int count, Act cur) {
+        for (int i = 0; i < count; ++i) {
+            const std::string b = prefix + "." + std::to_string(i);
+            Act t = conv(b + ".conv1", {src_of(cur)}, cur.N, cur.H, cur.W, RVSR_ACT_RELU);
+            cur = conv(b + ".conv2", {src_of(t)}, cur.N, cur.H, cur.W, RVSR_ACT_NONE, 1, OUT_C8, &cur);
+        }
+        return cur;
+    }
+};
+
+}  // namespace
+
+template <typename T>
+int Engine::run(Arena &ar, bool dry, const void *x, int x_dtype, void *out, int out_dtype, int B, int H, int W,
+                cudaStream_t s) {
+    const int nf = cfg_.nf, N = cfg_.nframes, nc = cfg_.nc, dg = cfg_.groups, ctr = cfg_.center;
+    const int NB = B * N;
+    const int LR = RVSR_ACT_LRELU, NONE = RVSR_ACT_NONE;
+    Plan<T> P{this, ar, dry, s, packed_, cfg_.precision == RVSR_F16};
+    using PT = Plan<T>;
+
+    // ---- LQ frames -> channel-blocked
+    Act xin = P.make(NB, nc, H, W);
+    if (!dry && P.rc == RVSR_OK)
+        P.launch("glue:pack_input", 0, (double)xin.elems() * sizeof(T) * 1.4, [&] {
+            return x_dtype == RVSR_F32 ? launch_pack_nchw<T, float>((const float *)x, (T *)xin.p, NB, nc, H, W, s)
+                                       : launch_pack_nchw<T, __half>((const __half *)x, (T *)xin.p, NB, nc, H, W, s); });
+    // ---- per-frame feature pyramid (EDVR_arch.py:276-283)
+    Act L1 = P.conv("conv_first", {PT::src_of(xin)}, NB, H, W, LR);
+    L1 = P.resblocks("feature_extraction", cfg_.front_RBs, L1);
+    Act L2 = P.conv("fea_L2_conv1", {PT::src_of(L1)}, NB, H, W, LR, 2);
+    L2 = P.conv("fea_L2_conv2", {PT::src_of(L2)}, NB, L2.H, L2.W, LR);
+    Act L3 = P.conv("fea_L3_conv1", {PT::src_of(L2)}, NB, L2.H, L2.W, LR, 2);
+    L3 = P.conv("fea_L3_conv2", {PT::src_of(L3)}, NB, L3.H, L3.W, LR);
+
+    // ---- PCD alignment of all N frames at once (EDVR_arch.py:98-132, :297-303)
+    const std::string p = "pcd_align.";
+    Act o3 = P.conv(p + "L3_offset_conv1", {PT::src_of(L3), PT::src_fixed(L3, N, ctr)}, NB, L3.H, L3.W, LR);
+    o3 = P.conv(p + "L3_offset_conv2", {PT::src_of(o3)}, NB, L3.H, L3.W, LR);
+    Act f3 = P.dcn_pack(p + "L3_dcnpack", L3, o3, dg, LR);
+
+    Act o2 = P.conv(p + "L2_offset_conv1", {PT::src_of(L2), PT::src_fixed(L2, N, ctr)}, NB, L2.H, L2.W, LR);
+    Act o3u = P.up2(o3, 2.f);
+    o2 = P.conv(p + "L2_offset_conv2", {PT::src_of(o2), PT::src_of(o3u)}, NB, L2.H, L2.W, LR);
+    o2 = P.conv(p + "L2_offset_conv3", {PT::src_of(o2)}, NB, L2.H, L2.W, LR);
+    Act f2 = P.dcn_pack(p + "L2_dcnpack", L2, o2, dg, NONE);
+    Act f3u = P.up2(f3, 1.f);
+    f2 = P.conv(p + "L2_fea_conv", {PT::src_of(f2), PT::src_of(f3u)}, NB, L2.H, L2.W, LR);
+
+    Act o1 = P.conv(p + "L1_offset_conv1", {PT::src_of(L1), PT::src_fixed(L1, N, ctr)}, NB, H, W, LR);
+    Act o2u = P.up2(o2, 2.f);
+    o1 = P.conv(p + "L1_offset_conv2", {PT::src_of(o1), PT::src_of(o2u)}, NB, H, W, LR);
+    o1 = P.conv(p + "L1_offset_conv3", {PT::src_of(o1)}, NB, H, W, LR);
+    Act f1 = P.dcn_pack(p + "L1_dcnpack", L1, o1, dg, NONE);
+    Act f2u = P.up2(f2, 1.f);
+    f1 = P.conv(p + "L1_fea_conv", {PT::src_of(f1), PT::src_of(f2u)}, NB, H, W, NONE);  // no lrelu (:125)
+
+    Act oc = P.conv(p + "cas_offset_conv1", {PT::src_of(f1), PT::src_fixed(L1, N, ctr)}, NB, H, W, LR);
+    oc = P.conv(p + "cas_offset_conv2", {PT::src_of(oc)}, NB, H, W, LR);
+    Act aligned = P.dcn_pack(p + "cas_dcnpack", f1, oc, dg, LR);
+
+    // ---- fusion
+    Act fused;
+    auto frame_sources = [&](const Act &a) {
+        std::vector<Src> v;
+        for (int i = 0; i < N; ++i) v.push_back(PT::src_slice(a, N, i));
+        return v;
+    };
+    auto conv_frames = [&](const std::string &name, const Act &a, int act) {
+        // 1x1 conv over the N*nf channels of [B, N*C, H, W] == N sources of nf channels
+        std::vector<Src> v = frame_sources(a);
+        switch (N) {
+            case 1: return P.conv(name, {v[0]}, B, H, W, act);
+            case 2: return P.conv(name, {v[0], v[1]}, B, H, W, act);
+            case 3: return P.conv(name, {v[0], v[1], v[2]}, B, H, W, act);
+            case 4: return P.conv(name, {v[0], v[1], v[2], v[3]}, B, H, W, act);
+            case 5: return P.conv(name, {v[0], v[1], v[2], v[3], v[4]}, B, H, W, act);
+            case 6: return P.conv(name, {v[0], v[1], v[2], v[3], v[4], v[5]}, B, H, W, act);
+            default: return P.conv(name, {v[0], v[1], v[2], v[3], v[4], v[5], v[6]}, B, H, W, act);
+        }
+    };
+    if (cfg_.w_TSA) {
+        const std::string t = "tsa_fusion.";
+        Act emb_ref = P.conv(t + "tAtt_2", {PT::src_slice(aligned, N, ctr)}, B, H, W, NONE);
+        Act emb = P.conv(t + "tAtt_1", {PT::src_of(aligned)}, NB, H, W, NONE);
+        Act ali = P.make(NB, nf, H, W);
+        if (!dry && P.rc == RVSR_OK)
+            P.launch("glue:tsa_temporal", 4.0 * ali.elems(), (double)ali.elems() * sizeof(T) * 4, [&] {
+                return launch_tsa_temporal<T>((const T *)emb.p, (const T *)emb_ref.p, (const T *)aligned.p,
+                                              (T *)ali.p, B, N, nf, H, W, s); });
+        Act fea = conv_frames(t + "fea_fusion", ali, LR);
+        Act att = conv_frames(t + "sAtt_1", ali, LR);
+        Act mx, av;
+        P.pools(att, mx, av);
+        att = P.conv(t + "sAtt_2", {PT::src_of(mx), PT::src_of(av)}, B, mx.H, mx.W, LR);
+        Act attL = P.conv(t + "sAtt_L1", {PT::src_of(att)}, B, att.H, att.W, LR);
+        Act mx2, av2;
+        P.pools(attL, mx2, av2);
+        attL = P.conv(t + "sAtt_L2", {PT::src_of(mx2), PT::src_of(av2)}, B, mx2.H, mx2.W, LR);
+        attL = P.conv(t + "sAtt_L3", {PT::src_of(attL)}, B, attL.H, attL.W, LR);
+        Act attLu = P.up2(attL, 1.f);
+        att = P.conv(t + "sAtt_3", {PT::src_of(att)}, B, att.H, att.W, LR, 1, OUT_C8, &attLu);  // lrelu, then + att_L
+        att = P.conv(t + "sAtt_4", {PT::src_of(att)}, B, att.H, att.W, LR);
+        Act attu = P.up2(att, 1.f);
+        att = P.conv(t + "sAtt_5", {PT::src_of(attu)}, B, H, W, NONE);
+        Act add = P.conv(t + "sAtt_add_1", {PT::src_of(att)}, B, H, W, LR);
+        add = P.conv(t + "sAtt_add_2", {PT::src_of(add)}, B, H, W, NONE);
+        fused = P.make(B, nf, H, W);
+        if (!dry && P.rc == RVSR_OK)
+            P.launch("glue:tsa_final", 0, (double)fused.elems() * sizeof(T) * 4, [&] {
+                return launch_tsa_final<T>((const T *)fea.p, (const T *)att.p, (const T *)add.p, (T *)fused.p,
+                                           fused.elems(), s); });
+    } else {
+        fused = conv_frames("tsa_fusion", aligned, NONE);
+    }
+
+    // ---- reconstruction (EDVR_arch.py:310-319 / :398-403)
+    Act r = P.resblocks("recon_trunk", cfg_.back_RBs, fused);
+    int scale = 1;
+    if (cfg_.upsample) {
+        r = P.conv("upconv1", {PT::src_of(r)}, B, H, W, LR, 1, OUT_C8_SHUFFLE2);
+        r = P.conv("upconv2", {PT::src_of(r)}, B, r.H, r.W, LR, 1, OUT_C8_SHUFFLE2);
+        scale = 4;
+    }
+    r = P.conv("HRconv", {PT::src_of(r)}, B, r.H, r.W, LR);
+    Act last = P.conv("conv_last", {PT::src_of(r)}, B, r.H, r.W, NONE);
+    if (!dry && P.rc == RVSR_OK) {
+        const T *lp = (const T *)last.p;
+        P.launch("glue:final_add_base", 0, (double)last.elems() * sizeof(T) + (double)B * nc * last.H * last.W * 4, [&] {
+            if (x_dtype == RVSR_F32 && out_dtype == RVSR_F32)
+                return launch_final_add<T, float, float>(lp, (const float *)x, (float *)out, B, N, ctr, nc, H, W, scale, s);
+            if (x_dtype == RVSR_F32)
+                return launch_final_add<T, float, __half>(lp, (const float *)x, (__half *)out, B, N, ctr, nc, H, W, scale, s);
+            if (out_dtype == RVSR_F32)
+                return launch_final_add<T, __half, float>(lp, (const __half *)x, (float *)out, B, N, ctr, nc, H, W, scale, s);
+            return launch_final_add<T, __half, __half>(lp, (const __half *)x, (__half *)out, B, N, ctr, nc, H, W, scale, s);
+        });
+    }
+    if (!dry) {
+        taps_.clear();
+        taps_["L1"] = L1; taps_["L2"] = L2; taps_["L3"] = L3; taps_["aligned"] = aligned; taps_["fused"] = fused;
+        tap_dtype_ = sizeof(T) == 4 ? RVSR_F32 : RVSR_F16;
+        launches_ = P.launches;
+    }
+    return P.rc;
+}
+
+ProfEntry *Engine::prof_begin(const std::string &label, double flops, double bytes, cudaStream_t s) {
+    if (!profiling_) return nullptr;
+    prof_.emplace_back();
+    ProfEntry &e = prof_.back();
+    e.label = label; e.flops = flops; e.bytes = bytes;
+    if (cudaEventCreate(&e.e0) != cudaSuccess || cudaEventCreate(&e.e1) != cudaSuccess) return nullptr;
+    cudaEventRecord(e.e0, s);
+    return &e;
+}
+void Engine::prof_end(ProfEntry *e, cudaStream_t s) {
+    if (e != nullptr) cudaEventRecord(e->e1, s);
+}
+void Engine::prof_clear() {
+    for (ProfEntry &e : prof_) {
+        if (e.e0) cudaEventDestroy(e.e0);
+        if (e.e1) cudaEventDestroy(e.e1);
+    }
+    prof_.clear();
+}
+int Engine::prof_collect() {
+    for (ProfEntry &e : prof_) {
+        if (e.e0 == nullptr || e.e1 == nullptr) continue;
+        if (cudaEventSynchronize(e.e1) != cudaSuccess || cudaEventElapsedTime(&e.ms, e.e0, e.e1) != cudaSuccess) {
+            set_error("profile: event timing failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return RVSR_E_CUDA;
+        }
+    }
+    return (int)prof_.size();
+}
+
+static int check_dims(const rvsr_edvr_config &c, int B, int H, int W) {
+    RVSR_CHECK_ARG(B >= 0 && H > 0 && W > 0, "engine: bad input size B=%d H=%d W=%d", B, H, W);
+    RVSR_CHECK_ARG(H % 4 == 0 && W % 4 == 0, "engine: H and W must be multiples of 4 (got %dx%d)", H, W);
+    (void)c;
+    return RVSR_OK;
+}
+
+size_t Engine::workspace_bytes(int B, int H, int W) {
+    if (check_dims(cfg_, B, H, W) != RVSR_OK) return 0;
+    Arena ar;
+    if (cfg_.precision == RVSR_F16)
+        run<__half>(ar, true, nullptr, RVSR_F32, nullptr, RVSR_F32, B, H, W, nullptr);
+    else
+        run<float>(ar, true, nullptr, RVSR_F32, nullptr, RVSR_F32, B, H, W, nullptr);
+    return ar.peak + 4096;
+}
+
+int Engine::forward(const void *x, int x_dtype, void *out, int out_dtype, int B, int H, int W, void *ws,
+                    size_t ws_bytes, cudaStream_t s) {
+    if (!finalized_) {
+        set_error("engine: weights not finalised");
+        return RVSR_E_STATE;
+    }
+    RVSR_TRY(check_dims(cfg_, B, H, W));
+    RVSR_CHECK_ARG(x_dtype == RVSR_F32 || x_dtype == RVSR_F16, "engine: bad x dtype %d", x_dtype);
+    RVSR_CHECK_ARG(out_dtype == RVSR_F32 || out_dtype == RVSR_F16, "engine: bad out dtype %d", out_dtype);
+    if (B == 0) return RVSR_OK;
+    RVSR_CHECK_ARG(x != nullptr && out != nullptr && ws != nullptr, "engine: null buffer");
+    prof_clear();
+    prof_.reserve(1024);  // entries must not move while a forward holds pointers to them
+    Arena ar;
+    ar.base = reinterpret_cast<char *>(ws);
+    ar.cap = ws_bytes;
+    const size_t mis = (size_t)(reinterpret_cast<uintptr_t>(ws) % 1024);
+    if (mis) { ar.base += 1024 - mis; ar.cap -= 1024 - mis; }
+    if (cfg_.precision == RVSR_F16) return run<__half>(ar, false, x, x_dtype, out, out_dtype, B, H, W, s);
+    return run<float>(ar, false, x, x_dtype, out, out_dtype, B, H, W, s);
+}
+
+int Engine::read_tap(const char *name, float *dst, size_t dst_elems, cudaStream_t s) {
+    auto it = taps_.find(name ? name : "");
+    RVSR_CHECK_ARG(it != taps_.end(), "engine: unknown tap %s", name ? name : "(null)");
+    const Act &a = it->second;
+    RVSR_CHECK_ARG(dst_elems >= (size_t)a.N * a.C * a.H * a.W, "engine: tap buffer too small");
+    if (tap_dtype_ == RVSR_F32) return launch_unpack_nchw<float, float>((const float *)a.p, dst, a.N, a.C, a.H, a.W, s);
+    return launch_unpack_nchw<__half, float>((const __half *)a.p, dst, a.N, a.C, a.H, a.W, s);
+}
+
+}  // namespace rvsr

@@ -1,0 +1,112 @@
+// engine.cuh -- the EDVR inference engine behind rvsr_engine_* (see include/rvsr_b200.h).
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace rvsr {
+
+// Bump allocator over the caller-provided workspace.  With base == nullptr it only counts,
+// which is how rvsr_engine_workspace_bytes() sizes the workspace from the same code path
+// that later runs the forward.
+struct Arena {
+    char *base = nullptr;
+    size_t cap = 0, off = 0, peak = 0;
+    bool overflow = false;
+    void *alloc(size_t bytes) {
+        const size_t a = align_up(off, 1024);
+        off = a + align_up(bytes, 1024);
+        if (off > peak) peak = off;
+        if (base == nullptr) return reinterpret_cast<void *>(size_t(1024));  // dry run: non-null dummy
+        if (off > cap) { overflow = true; return nullptr; }
+        return base + a;
+    }
+    size_t mark() const { return off; }
+    void release(size_t m) { off = m; }
+};
+
+// Channel-blocked activation [N][C8][H][W][8].
+struct Act {
+    void *p = nullptr;
+    int N = 0, C = 0, H = 0, W = 0;
+    int C8() const { return (C + 7) / 8; }
+    long long image_elems() const { return (long long)C8() * H * W * 8; }
+    long long elems() const { return image_elems() * N; }
+};
+
+struct PackedConv {
+    float *w_simt = nullptr;  // [chunks][taps][8][cout_pad] fp32
+    void *w_tc = nullptr;     // fp16 UMMA layout (tc_kernels.cu) or null
+    float *bias = nullptr;    // fp32 [Cout]
+    int Cout = 0, Cin = 0, ks = 0;
+};
+
+struct RawWeight {
+    std::vector<int64_t> shape;
+    float *dev = nullptr;
+    bool set = false;
+};
+
+struct ProfEntry {
+    std::string label;
+    double flops = 0, bytes = 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    float ms = 0.f;
+};
+
+class Engine {
+  public:
+    // per-launch profiling (CUDA events on the launching stream)
+    void set_profiling(bool on) { profiling_ = on; }
+    ProfEntry *prof_begin(const std::string &label, double flops, double bytes, cudaStream_t s);
+    void prof_end(ProfEntry *e, cudaStream_t s);
+    int prof_collect();
+    void prof_clear();
+    const std::vector<ProfEntry> &prof() const { return prof_; }
+
+    explicit Engine(const rvsr_edvr_config &cfg);
+    ~Engine();
+    int set_weight(const char *name, const float *dev_ptr, const int64_t *shape, int ndim, cudaStream_t s);
+    int finalize(cudaStream_t s);
+    size_t workspace_bytes(int B, int H, int W);
+    int forward(const void *x, int x_dtype, void *out, int out_dtype, int B, int H, int W, void *ws,
+                size_t ws_bytes, cudaStream_t s);
+    int read_tap(const char *name, float *dst, size_t dst_elems, cudaStream_t s);
+    const std::vector<std::string> &names() const { return names_; }
+    int last_launches() const { return launches_; }
+    const rvsr_edvr_config &cfg() const { return cfg_; }
+
+  private:
+    template <typename T>
+    int run(Arena &ar, bool dry, const void *x, int x_dtype, void *out, int out_dtype, int B, int H, int W,
+            cudaStream_t s);
+    void expect(const std::string &name, std::vector<int64_t> shape);
+    void expect_conv(const std::string &name, int co, int ci, int k);
+
+    rvsr_edvr_config cfg_;
+    std::vector<std::string> names_;
+    std::map<std::string, RawWeight> raw_;
+    std::map<std::string, PackedConv> packed_;
+    std::map<std::string, Act> taps_;
+    int tap_dtype_ = RVSR_F32;
+    bool finalized_ = false;
+    int launches_ = 0;
+    std::vector<void *> owned_;  // cudaMalloc'ed buffers
+    bool profiling_ = false;
+    std::vector<ProfEntry> prof_;
+};
+
+// tc_kernels.cu: tcgen05 paths (fp16 storage).  Return RVSR_E_UNSUPPORTED when the shape is
+// not covered so the caller can route the op to the CUDA-core kernel instead.
+bool tc_conv_supported(const ConvOp &op);
+int launch_conv_tc(const ConvOp &op, cudaStream_t s);
+size_t tc_conv_weight_bytes(int Cout, int Cin, int ks);
+int pack_weight_tc(const float *w_oihw, void *dst, int Cout, int Cin, int ks, int shuffle, cudaStream_t s);
+bool tc_dcn_supported(const DcnOp &op);
+int launch_dcn_tc(const DcnOp &op, cudaStream_t s);
+size_t tc_dcn_weight_bytes(int Cout, int C, int K);
+int pack_weight_dcn_tc(const float *w_oihw, void *dst, int Cout, int C, int K, cudaStream_t s);
+
+}  // namespace rvsr

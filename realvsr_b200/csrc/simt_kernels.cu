@@ -1,0 +1,661 @@
+// simt_kernels.cu -- CUDA-core kernels of the rvsr_b200 hot path.
+//
+// Two families live here:
+//  (1) the fp32-accumulate "tile GEMM" convolution / deformable-convolution kernels that
+//      serve the strict-parity fp32 mode, odd shapes (Cin = 3, stride 2, tiny nf) and act as
+//      the cross-check for the tcgen05 kernels in tc_kernels.cu;
+//  (2) the bandwidth-bound glue ops (layout pack/unpack, x2 bilinear upsample, 3/2/1 pools,
+//      TSA temporal attention, final fusion) used by BOTH precisions: 128-bit vector
+//      accesses over the channel-blocked layout, one pass, nothing materialised twice.
+//
+// Reference semantics being reproduced (IanYeung/RealVSR, codes/models/archs/):
+//   DCN sample/gather  dcn/src/deform_conv_cuda_kernel.cu:467-497, :571-633
+//   DCN contraction    dcn/src/deform_conv_cuda.cpp:539-568
+//   upsample / pools / attention   EDVR_arch.py:111-124, :154-155, :175-207
+#include "common.cuh"
+
+namespace rvsr {
+
+static constexpr int TILE_W = 8, TILE_H = 8, TILE_P = 64;  // output pixels per CTA
+static constexpr int TILE_CO = 64;                         // output channels per CTA
+static constexpr int NTHREADS = 256;
+
+__device__ __forceinline__ long long src_image(const Src &s, int n) {
+    const int m = s.fixed_frame >= 0 ? (n / s.frames) * s.frames + s.fixed_frame : n;
+    return (long long)m * s.image_stride;
+}
+
+// ---------------------------------------------------------------- shared consumer
+// acc[j][k]: output channel co0 + j, pixel 4*pg + k of the tile.
+template <typename T>
+__device__ __forceinline__ void tile_epilogue(float (&acc)[4][4], const float *bias, void *out_,
+                                              long long out_image_stride, const void *res_,
+                                              long long res_image_stride, int n, int Cout, int Ho,
+                                              int Wo, int oy0, int ox0, int pg, int co0, int act,
+                                              int out_mode, int sig_from) {
+    const int Co8 = (Cout + 7) / 8;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int p = pg * 4 + k;
+        const int oy = oy0 + p / TILE_W, ox = ox0 + p % TILE_W;
+        if (oy >= Ho || ox >= Wo) continue;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int co = co0 + j;
+            float t = acc[j][k] + ((bias != nullptr && co < Cout) ? bias[co] : 0.f);
+            v[j] = apply_act(t, act);
+        }
+        if (out_mode == OUT_C8) {
+            if (co0 >= Co8 * 8) continue;
+            const long long e = ((((long long)(co0 / 8)) * Ho + oy) * Wo + ox) * 8 + (co0 % 8);
+            T *o = reinterpret_cast<T *>(out_) + (long long)n * out_image_stride + e;
+            if (res_ != nullptr) {
+                const T *r = reinterpret_cast<const T *>(res_) + (long long)n * res_image_stride + e;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] += to_f<T>(r[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = from_f<T>(co0 + j < Cout ? v[j] : 0.f);
+        } else if (out_mode == OUT_C8_SHUFFLE2) {
+            // out[n, c, 2y+i, 2x+j] = in[n, 4c+2i+j, y, x]
+            if (co0 >= Cout) continue;
+            const int c = co0 / 4, C2 = Cout / 4, C28 = (C2 + 7) / 8;
+            (void)C28;
+            T *o = reinterpret_cast<T *>(out_) + (long long)n * out_image_stride;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int yy = 2 * oy + (j >> 1), xx = 2 * ox + (j & 1);
+                o[((((long long)(c / 8)) * (2 * Ho) + yy) * (2 * Wo) + xx) * 8 + (c % 8)] = from_f<T>(v[j]);
+            }
+        } else if (out_mode == OUT_PLANAR_F32) {
+            float *o = reinterpret_cast<float *>(out_) + (long long)n * out_image_stride;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int co = co0 + j;
+                if (co < Cout) o[((long long)co * Ho + oy) * Wo + ox] = co >= sig_from ? sigmoidf_(v[j]) : v[j];
+            }
+        } else {  // OUT_NCHW_T
+            T *o = reinterpret_cast<T *>(out_) + (long long)n * out_image_stride;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int co = co0 + j;
+                if (co < Cout) o[((long long)co * Ho + oy) * Wo + ox] = from_f<T>(v[j]);
+            }
+        }
+    }
+}
+
+template <int ROWS>
+__device__ __forceinline__ void tile_fma(const float (*col)[TILE_P], const float (*wt)[TILE_CO],
+                                         float (&acc)[4][4], int pg, int cg) {
+#pragma unroll 8
+    for (int r = 0; r < ROWS; ++r) {
+        const float4 a = *reinterpret_cast<const float4 *>(&col[r][pg * 4]);
+        const float4 b = *reinterpret_cast<const float4 *>(&wt[r][cg * 4]);
+        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[j][k] = fmaf(bv[j], av[k], acc[j][k]);
+    }
+}
+
+template <int ROWS>
+__device__ __forceinline__ void load_weight_tile(float (*wt)[TILE_CO], const float *w, long long row0,
+                                                 int cout_pad, int cb) {
+    for (int i = threadIdx.x; i < ROWS * (TILE_CO / 4); i += NTHREADS) {
+        const int r = i / (TILE_CO / 4), c4 = i % (TILE_CO / 4);
+        *reinterpret_cast<float4 *>(&wt[r][c4 * 4]) =
+            __ldg(reinterpret_cast<const float4 *>(w + (row0 + r) * cout_pad + cb * TILE_CO) + c4);
+    }
+}
+
+// ---------------------------------------------------------------- convolution (ks x ks, pad ks/2)
+template <typename T, int KS>
+__global__ void __launch_bounds__(NTHREADS) conv_simt_kernel(const ConvOp op) {
+    constexpr int KK = KS * KS, ROWS = KK * 8;
+    __shared__ __align__(16) float col[ROWS][TILE_P];
+    __shared__ __align__(16) float wt[ROWS][TILE_CO];
+    const int pad = KS / 2;
+    const int Ho = (op.H + 2 * pad - KS) / op.stride + 1, Wo = (op.W + 2 * pad - KS) / op.stride + 1;
+    const int ntx = (Wo + TILE_W - 1) / TILE_W;
+    const int ox0 = (blockIdx.x % ntx) * TILE_W, oy0 = (blockIdx.x / ntx) * TILE_H;
+    const int cb = blockIdx.y, n = blockIdx.z;
+    const int cout_pad = ((op.Cout + TILE_CO - 1) / TILE_CO) * TILE_CO;
+    const int pg = threadIdx.x % 16, cg = threadIdx.x / 16;
+    float acc[4][4] = {};
+    int chunk_base = 0;
+    for (int s = 0; s < op.nsrc; ++s) {
+        const Src &src = op.src[s];
+        const int C8 = (src.C + 7) / 8;
+        const T *base = reinterpret_cast<const T *>(src.ptr) + src_image(src, n);
+        for (int q = 0; q < C8; ++q) {
+            __syncthreads();
+            load_weight_tile<ROWS>(wt, op.w_simt, (long long)(chunk_base + q) * ROWS, cout_pad, cb);
+            for (int i = threadIdx.x; i < TILE_P * KK; i += NTHREADS) {
+                const int p = i % TILE_P, t = i / TILE_P;
+                const int oy = oy0 + p / TILE_W, ox = ox0 + p % TILE_W;
+                const int iy = oy * op.stride - pad + t / KS, ix = ox * op.stride - pad + t % KS;
+                float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (oy < Ho && ox < Wo && iy >= 0 && iy < op.H && ix >= 0 && ix < op.W)
+                    load8<T>(base + ((((long long)q) * op.H + iy) * op.W + ix) * 8, v);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) col[t * 8 + c][p] = v[c];
+            }
+            __syncthreads();
+            tile_fma<ROWS>(col, wt, acc, pg, cg);
+        }
+        chunk_base += C8;
+    }
+    tile_epilogue<T>(acc, op.bias, op.out, op.out_image_stride, op.residual, op.res_image_stride, n,
+                     op.Cout, Ho, Wo, oy0, ox0, pg, cb * TILE_CO + cg * 4, op.act, op.out_mode,
+                     op.sig_from);
+}
+
+template <typename T> int launch_conv_simt(const ConvOp &op, cudaStream_t s) {
+    RVSR_CHECK_ARG(op.ks == 1 || op.ks == 3, "conv: kernel size %d not supported", op.ks);
+    RVSR_CHECK_ARG(op.stride == 1 || op.stride == 2, "conv: stride %d not supported", op.stride);
+    RVSR_CHECK_ARG(op.nsrc >= 1 && op.nsrc <= RVSR_MAX_SRC, "conv: %d sources", op.nsrc);
+    RVSR_CHECK_ARG(op.out_mode != OUT_C8_SHUFFLE2 || op.Cout % 4 == 0, "conv: shuffle needs Cout%%4==0");
+    const int pad = op.ks / 2;
+    const int Ho = (op.H + 2 * pad - op.ks) / op.stride + 1, Wo = (op.W + 2 * pad - op.ks) / op.stride + 1;
+    dim3 grid(cdiv(Wo, TILE_W) * cdiv(Ho, TILE_H), cdiv(op.Cout, TILE_CO), op.N);
+    if (grid.x == 0 || grid.z == 0) return RVSR_OK;
+    RVSR_CHECK_ARG(grid.z <= 65535 && grid.y <= 65535, "conv: too many images");
+    if (op.ks == 3)
+        conv_simt_kernel<T, 3><<<grid, NTHREADS, 0, s>>>(op);
+    else
+        conv_simt_kernel<T, 1><<<grid, NTHREADS, 0, s>>>(op);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+template int launch_conv_simt<float>(const ConvOp &, cudaStream_t);
+template int launch_conv_simt<__half>(const ConvOp &, cudaStream_t);
+
+// ---------------------------------------------------------------- modulated deformable conv
+// Bilinear sample of one channel block (8 channels) at (py, px); zero unless
+// -1 < py < H and -1 < px < W; each corner individually bounds-checked
+// (deform_conv_cuda_kernel.cu:480-495, :618).
+template <typename T>
+__device__ __forceinline__ void sample8(const T *plane, int H, int W, float py, float px, float (&v)[8]) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = 0.f;
+    if (!(py > -1.f && px > -1.f && py < (float)H && px < (float)W)) return;
+    const float fy = floorf(py), fx = floorf(px);
+    const int y0 = (int)fy, x0 = (int)fx, y1 = y0 + 1, x1 = x0 + 1;
+    const float ly = py - fy, lx = px - fx, hy = 1.f - ly, hx = 1.f - lx;
+    float t[8];
+    if (y0 >= 0 && x0 >= 0) {
+        load8<T>(plane + ((long long)y0 * W + x0) * 8, t);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = fmaf(hy * hx, t[c], v[c]);
+    }
+    if (y0 >= 0 && x1 <= W - 1) {
+        load8<T>(plane + ((long long)y0 * W + x1) * 8, t);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = fmaf(hy * lx, t[c], v[c]);
+    }
+    if (y1 <= H - 1 && x0 >= 0) {
+        load8<T>(plane + ((long long)y1 * W + x0) * 8, t);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = fmaf(ly * hx, t[c], v[c]);
+    }
+    if (y1 <= H - 1 && x1 <= W - 1) {
+        load8<T>(plane + ((long long)y1 * W + x1) * 8, t);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = fmaf(ly * lx, t[c], v[c]);
+    }
+}
+
+template <typename T, int K>
+__global__ void __launch_bounds__(NTHREADS) dcn_simt_kernel(const DcnOp op) {
+    constexpr int ROWS = K * 8;
+    __shared__ __align__(16) float col[ROWS][TILE_P];
+    __shared__ __align__(16) float wt[ROWS][TILE_CO];
+    const int Ho = (op.H + 2 * op.pad - (op.dil * (op.kh - 1) + 1)) / op.stride + 1;
+    const int Wo = (op.W + 2 * op.pad - (op.dil * (op.kw - 1) + 1)) / op.stride + 1;
+    const int ntx = (Wo + TILE_W - 1) / TILE_W;
+    const int ox0 = (blockIdx.x % ntx) * TILE_W, oy0 = (blockIdx.x / ntx) * TILE_H;
+    const int cb = blockIdx.y, n = blockIdx.z;
+    const int cout_pad = ((op.Cout + TILE_CO - 1) / TILE_CO) * TILE_CO;
+    const int pg = threadIdx.x % 16, cg = threadIdx.x / 16;
+    const int C = op.x.C, C8 = (C + 7) / 8, cpg = C / op.dg;
+    const long long plane = (long long)Ho * Wo;
+    const T *xb = reinterpret_cast<const T *>(op.x.ptr) + src_image(op.x, n);
+    const float *off = op.offset + (long long)n * op.offset_image_stride;
+    const float *msk = op.mask + (long long)n * op.mask_image_stride;
+    float acc[4][4] = {};
+    for (int q = 0; q < C8; ++q) {
+        __syncthreads();
+        load_weight_tile<ROWS>(wt, op.w_simt, (long long)q * ROWS, cout_pad, cb);
+        const T *xq = xb + (long long)q * op.H * op.W * 8;
+        for (int i = threadIdx.x; i < TILE_P * K; i += NTHREADS) {
+            const int p = i % TILE_P, t = i / TILE_P;
+            const int oy = oy0 + p / TILE_W, ox = ox0 + p % TILE_W;
+            float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (oy < Ho && ox < Wo) {
+                const long long pix = (long long)oy * Wo + ox;
+                const float by = (float)(oy * op.stride - op.pad + (t / op.kw) * op.dil);
+                const float bx = (float)(ox * op.stride - op.pad + (t % op.kw) * op.dil);
+                int gprev = -1;
+                float m = 0.f, v[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int ch = q * 8 + c;
+                    if (ch >= C) break;
+                    const int g = ch / cpg;
+                    if (g != gprev) {  // one coordinate pair + mask per (deformable group, tap)
+                        gprev = g;
+                        const float dy = __ldg(off + ((long long)g * 2 * K + 2 * t) * plane + pix);
+                        const float dx = __ldg(off + ((long long)g * 2 * K + 2 * t + 1) * plane + pix);
+                        m = __ldg(msk + ((long long)g * K + t) * plane + pix);
+                        sample8<T>(xq, op.H, op.W, by + dy, bx + dx, v);
+                    }
+                    r[c] = m * v[c];
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) col[t * 8 + c][p] = r[c];
+        }
+        __syncthreads();
+        tile_fma<ROWS>(col, wt, acc, pg, cg);
+    }
+    tile_epilogue<T>(acc, op.bias, op.out, op.out_image_stride, nullptr, 0, n, op.Cout, Ho, Wo, oy0, ox0,
+                     pg, cb * TILE_CO + cg * 4, op.act, op.out_mode, 0);
+}
+
+template <typename T> int launch_dcn_simt(const DcnOp &op, cudaStream_t s) {
+    const int K = op.kh * op.kw;
+    RVSR_CHECK_ARG(K == 9 || K == 1, "dcn: only 3x3 and 1x1 kernels are built (got %dx%d)", op.kh, op.kw);
+    RVSR_CHECK_ARG(op.dg > 0 && op.x.C % op.dg == 0, "dcn: channels %d not divisible by deformable groups %d",
+                   op.x.C, op.dg);
+    const int Ho = (op.H + 2 * op.pad - (op.dil * (op.kh - 1) + 1)) / op.stride + 1;
+    const int Wo = (op.W + 2 * op.pad - (op.dil * (op.kw - 1) + 1)) / op.stride + 1;
+    RVSR_CHECK_ARG(Ho > 0 && Wo > 0, "dcn: empty output");
+    dim3 grid(cdiv(Wo, TILE_W) * cdiv(Ho, TILE_H), cdiv(op.Cout, TILE_CO), op.N);
+    if (grid.z == 0) return RVSR_OK;
+    RVSR_CHECK_ARG(grid.z <= 65535, "dcn: too many images");
+    if (K == 9)
+        dcn_simt_kernel<T, 9><<<grid, NTHREADS, 0, s>>>(op);
+    else
+        dcn_simt_kernel<T, 1><<<grid, NTHREADS, 0, s>>>(op);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+template int launch_dcn_simt<float>(const DcnOp &, cudaStream_t);
+template int launch_dcn_simt<__half>(const DcnOp &, cudaStream_t);
+
+// ---------------------------------------------------------------- weight packing
+// dst[((chunk*KK + t)*8 + ci) * cout_pad + co] = w[co][cin(chunk, ci)][t]   (zero padded)
+__global__ void pack_weight_simt_kernel(const float *__restrict__ w, float *__restrict__ dst, int Cout,
+                                        int Cin_total, int KK, int nsrc, int c0, int c1, int c2, int c3,
+                                        int c4, int c5, int c6, int cout_pad, long long total) {
+    const int cs[RVSR_MAX_SRC] = {c0, c1, c2, c3, c4, c5, c6};
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int co = (int)(i % cout_pad);
+        long long r = i / cout_pad;
+        const int ci = (int)(r % 8);
+        r /= 8;
+        const int t = (int)(r % KK);
+        int chunk = (int)(r / KK);
+        int cin_off = 0, cin = -1;
+        for (int s = 0; s < nsrc; ++s) {
+            const int c8 = (cs[s] + 7) / 8;
+            if (chunk < c8) {
+                if (chunk * 8 + ci < cs[s]) cin = cin_off + chunk * 8 + ci;
+                break;
+            }
+            chunk -= c8;
+            cin_off += cs[s];
+        }
+        dst[i] = (cin >= 0 && co < Cout) ? w[((long long)co * Cin_total + cin) * KK + t] : 0.f;
+    }
+}
+
+int pack_weight_simt(const float *w_oihw, float *dst, int Cout, int Cin_total, int ks, const int *src_channels,
+                     int nsrc, int cout_pad, cudaStream_t s) {
+    RVSR_CHECK_ARG(nsrc >= 1 && nsrc <= RVSR_MAX_SRC, "pack: %d sources", nsrc);
+    int c[RVSR_MAX_SRC] = {0, 0, 0, 0, 0, 0, 0};
+    int chunks = 0, sum = 0;
+    for (int i = 0; i < nsrc; ++i) {
+        c[i] = src_channels[i];
+        chunks += (c[i] + 7) / 8;
+        sum += c[i];
+    }
+    RVSR_CHECK_ARG(sum == Cin_total, "pack: source channels %d != weight input channels %d", sum, Cin_total);
+    const long long total = (long long)chunks * ks * ks * 8 * cout_pad;
+    const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+    pack_weight_simt_kernel<<<blocks, 256, 0, s>>>(w_oihw, dst, Cout, Cin_total, ks * ks, nsrc, c[0], c[1],
+                                                   c[2], c[3], c[4], c[5], c[6], cout_pad, total);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+
+// ---------------------------------------------------------------- layout pack / unpack
+template <typename T, typename Tin>
+__global__ void pack_nchw_kernel(const Tin *__restrict__ src, T *__restrict__ dst, int C, int H, int W,
+                                 long long total) {
+    const int C8 = (C + 7) / 8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W);
+        long long r = i / W;
+        const int y = (int)(r % H);
+        r /= H;
+        const int q = (int)(r % C8);
+        const long long n = r / C8;
+        float v[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int ch = q * 8 + c;
+            v[c] = ch < C ? to_f<Tin>(src[((n * C + ch) * H + y) * W + x]) : 0.f;
+        }
+        store8<T>(dst + i * 8, v);
+    }
+}
+template <typename T, typename Tin>
+int launch_pack_nchw(const Tin *src, T *dst, int N, int C, int H, int W, cudaStream_t s) {
+    const long long total = (long long)N * ((C + 7) / 8) * H * W;
+    if (total == 0) return RVSR_OK;
+    pack_nchw_kernel<T, Tin><<<(int)((total + 255) / 256 < 8192 ? (total + 255) / 256 : 8192), 256, 0, s>>>(
+        src, dst, C, H, W, total);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+template int launch_pack_nchw<float, float>(const float *, float *, int, int, int, int, cudaStream_t);
+template int launch_pack_nchw<__half, float>(const float *, __half *, int, int, int, int, cudaStream_t);
+template int launch_pack_nchw<float, __half>(const __half *, float *, int, int, int, int, cudaStream_t);
+template int launch_pack_nchw<__half, __half>(const __half *, __half *, int, int, int, int, cudaStream_t);
+
+template <typename T, typename Tout>
+__global__ void unpack_nchw_kernel(const T *__restrict__ src, Tout *__restrict__ dst, int C, int H, int W,
+                                   long long total) {
+    const int C8 = (C + 7) / 8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W);
+        long long r = i / W;
+        const int y = (int)(r % H);
+        r /= H;
+        const int ch = (int)(r % C);
+        const long long n = r / C;
+        dst[i] = (Tout)to_f<T>(src[((((n * C8 + ch / 8) * H + y) * W) + x) * 8 + ch % 8]);
+    }
+}
+template <typename T, typename Tout>
+int launch_unpack_nchw(const T *src, Tout *dst, int N, int C, int H, int W, cudaStream_t s) {
+    const long long total = (long long)N * C * H * W;
+    if (total == 0) return RVSR_OK;
+    unpack_nchw_kernel<T, Tout><<<(int)((total + 255) / 256 < 8192 ? (total + 255) / 256 : 8192), 256, 0, s>>>(
+        src, dst, C, H, W, total);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+template int launch_unpack_nchw<float, float>(const float *, float *, int, int, int, int, cudaStream_t);
+template int launch_unpack_nchw<__half, float>(const __half *, float *, int, int, int, int, cudaStream_t);
+
+__global__ void convert_f16_f32_kernel(const __half *__restrict__ src, float *__restrict__ dst, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        dst[i] = __half2float(src[i]);
+}
+int launch_convert_f16_f32(const void *src, float *dst, long long n, cudaStream_t s) {
+    if (n == 0) return RVSR_OK;
+    convert_f16_f32_kernel<<<(int)((n + 255) / 256 < 8192 ? (n + 255) / 256 : 8192), 256, 0, s>>>(
+        reinterpret_cast<const __half *>(src), dst, n);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+__global__ void fill_f32_kernel(float *dst, float v, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        dst[i] = v;
+}
+int launch_fill_f32(float *dst, float v, long long n, cudaStream_t s) {
+    if (n == 0) return RVSR_OK;
+    fill_f32_kernel<<<(int)((n + 255) / 256 < 8192 ? (n + 255) / 256 : 8192), 256, 0, s>>>(dst, v, n);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+
+// ---------------------------------------------------------------- x2 bilinear upsample (align_corners=False)
+// F.interpolate(scale_factor=2, mode='bilinear') optionally times `scale`
+// (EDVR_arch.py:111-112: upsampled offsets are multiplied by 2 after interpolation).
+template <typename T>
+__global__ void upsample2x_kernel(const T *__restrict__ src, T *__restrict__ dst, int H, int W, float scale,
+                                  long long total) {
+    const int Ho = 2 * H, Wo = 2 * W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % Wo);
+        long long r = i / Wo;
+        const int oy = (int)(r % Ho);
+        const long long pl = r / Ho;  // (image, channel block)
+        const float sy = fmaxf(0.5f * (oy + 0.5f) - 0.5f, 0.f), sx = fmaxf(0.5f * (ox + 0.5f) - 0.5f, 0.f);
+        const int y0 = (int)sy, x0 = (int)sx;
+        const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+        const float ly = sy - y0, lx = sx - x0;
+        const T *p = src + pl * H * W * 8;
+        float a[8], b[8], c[8], d[8], o[8];
+        load8<T>(p + ((long long)y0 * W + x0) * 8, a);
+        load8<T>(p + ((long long)y0 * W + x1) * 8, b);
+        load8<T>(p + ((long long)y1 * W + x0) * 8, c);
+        load8<T>(p + ((long long)y1 * W + x1) * 8, d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            o[k] = scale * ((1.f - ly) * ((1.f - lx) * a[k] + lx * b[k]) + ly * ((1.f - lx) * c[k] + lx * d[k]));
+        store8<T>(dst + i * 8, o);
+    }
+}
+template <typename T>
+int launch_upsample2x(const T *src, T *dst, int N, int C, int H, int W, float scale, cudaStream_t s) {
+    const long long total = (long long)N * ((C + 7) / 8) * (2 * H) * (2 * W);
+    if (total == 0) return RVSR_OK;
+    upsample2x_kernel<T><<<(int)((total + 255) / 256 < 16384 ? (total + 255) / 256 : 16384), 256, 0, s>>>(
+        src, dst, H, W, scale, total);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+template int launch_upsample2x<float>(const float *, float *, int, int, int, int, float, cudaStream_t);
+template int launch_upsample2x<__half>(const __half *, __half *, int, int, int, int, float, cudaStream_t);
+
+// ---------------------------------------------------------------- MaxPool2d(3,2,1) + AvgPool2d(3,2,1) in one pass
+// max pads with -inf; avg divides by 9 always (count_include_pad=True) -- EDVR_arch.py:154-155.
+template <typename T>
+__global__ void pool_maxavg_kernel(const T *__restrict__ src, T *__restrict__ dmax, T *__restrict__ davg, int H,
+                                   int W, long long total) {
+    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % Wo);
+        long long r = i / Wo;
+        const int oy = (int)(r % Ho);
+        const long long pl = r / Ho;
+        const T *p = src + pl * H * W * 8;
+        float mx[8], sm[8], v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { mx[k] = -INFINITY; sm[k] = 0.f; }
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int y = 2 * oy + dy, x = 2 * ox + dx;
+                if (y < 0 || y >= H || x < 0 || x >= W) continue;
+                load8<T>(p + ((long long)y * W + x) * 8, v);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { mx[k] = fmaxf(mx[k], v[k]); sm[k] += v[k]; }
+            }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sm[k] *= (1.f / 9.f);
+        store8<T>(dmax + i * 8, mx);
+        store8<T>(davg + i * 8, sm);
+    }
+}
+template <typename T>
+int launch_pool_maxavg(const T *src, T *dst_max, T *dst_avg, int N, int C, int H, int W, cudaStream_t s) {
+    const long long total = (long long)N * ((C + 7) / 8) * ((H - 1) / 2 + 1) * ((W - 1) / 2 + 1);
+    if (total == 0) return RVSR_OK;
+    pool_maxavg_kernel<T><<<(int)((total + 255) / 256 < 16384 ? (total + 255) / 256 : 16384), 256, 0, s>>>(
+        src, dst_max, dst_avg, H, W, total);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+template int launch_pool_maxavg<float>(const float *, float *, float *, int, int, int, int, cudaStream_t);
+template int launch_pool_maxavg<__half>(const __half *, __half *, __half *, int, int, int, int, cudaStream_t);
+
+// ---------------------------------------------------------------- TSA temporal attention (EDVR_arch.py:175-181)
+// One warp handles 32 consecutive pixels of one (batch, frame); each lane owns a pixel and
+// walks the channel blocks: cor = sum_c emb[c]*emb_ref[c]; out = aligned * sigmoid(cor).
+template <typename T>
+__global__ void tsa_temporal_kernel(const T *__restrict__ emb, const T *__restrict__ emb_ref,
+                                    const T *__restrict__ aligned, T *__restrict__ out, int frames, int C8,
+                                    long long HW, long long total) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long pix = i % HW;
+        const long long bn = i / HW;  // b * frames + frame
+        const long long b = bn / frames;
+        const T *e = emb + bn * C8 * HW * 8, *er = emb_ref + b * C8 * HW * 8;
+        float cor = 0.f, u[8], w[8];
+        for (int q = 0; q < C8; ++q) {
+            load8<T>(e + (q * HW + pix) * 8, u);
+            load8<T>(er + (q * HW + pix) * 8, w);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) cor = fmaf(u[k], w[k], cor);
+        }
+        const float pr = sigmoidf_(cor);
+        const T *a = aligned + bn * C8 * HW * 8;
+        T *o = out + bn * C8 * HW * 8;
+        for (int q = 0; q < C8; ++q) {
+            load8<T>(a + (q * HW + pix) * 8, u);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) u[k] *= pr;
+            store8<T>(o + (q * HW + pix) * 8, u);
+        }
+    }
+}
+template <typename T>
+int launch_tsa_temporal(const T *emb, const T *emb_ref, const T *aligned, T *out, int B, int frames, int C,
+                        int H, int W, cudaStream_t s) {
+    const long long HW = (long long)H * W, total = (long long)B * frames * HW;
+    if (total == 0) return RVSR_OK;
+    tsa_temporal_kernel<T><<<(int)((total + 127) / 128 < 16384 ? (total + 127) / 128 : 16384), 128, 0, s>>>(
+        emb, emb_ref, aligned, out, frames, (C + 7) / 8, HW, total);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+template int launch_tsa_temporal<float>(const float *, const float *, const float *, float *, int, int, int,
+                                        int, int, cudaStream_t);
+template int launch_tsa_temporal<__half>(const __half *, const __half *, const __half *, __half *, int, int,
+                                         int, int, int, cudaStream_t);
+
+// fea * sigmoid(att) * 2 + att_add   (EDVR_arch.py:205-207)
+template <typename T>
+__global__ void tsa_final_kernel(const T *__restrict__ fea, const T *__restrict__ att,
+                                 const T *__restrict__ att_add, T *__restrict__ out, long long n8) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
+         i += (long long)gridDim.x * blockDim.x) {
+        float f[8], a[8], d[8];
+        load8<T>(fea + i * 8, f);
+        load8<T>(att + i * 8, a);
+        load8<T>(att_add + i * 8, d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = f[k] * sigmoidf_(a[k]) * 2.f + d[k];
+        store8<T>(out + i * 8, f);
+    }
+}
+template <typename T>
+int launch_tsa_final(const T *fea, const T *att, const T *att_add, T *out, long long n, cudaStream_t s) {
+    const long long n8 = n / 8;
+    if (n8 == 0) return RVSR_OK;
+    tsa_final_kernel<T><<<(int)((n8 + 255) / 256 < 16384 ? (n8 + 255) / 256 : 16384), 256, 0, s>>>(
+        fea, att, att_add, out, n8);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+template int launch_tsa_final<float>(const float *, const float *, const float *, float *, long long, cudaStream_t);
+template int launch_tsa_final<__half>(const __half *, const __half *, const __half *, __half *, long long,
+                                      cudaStream_t);
+
+// ---------------------------------------------------------------- out = conv_last + base  (EDVR_arch.py:314-319, :401-403)
+// res_c8: [B][1][sH][sW][8] (nc <= 8 channels used); x: [B][frames][nc][H][W] NCHW;
+// base = x4 bilinear (align_corners=False) of the centre LQ frame, or the frame itself (scale 1).
+template <typename T, typename Tin, typename Tout>
+__global__ void final_add_kernel(const T *__restrict__ res, const Tin *__restrict__ x, Tout *__restrict__ out,
+                                 int frames, int center, int nc, int H, int W, int scale, long long total) {
+    const int Ho = H * scale, Wo = W * scale;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % Wo);
+        long long r = i / Wo;
+        const int oy = (int)(r % Ho);
+        const long long b = r / Ho;
+        float v[8];
+        load8<T>(res + i * 8, v);
+        const Tin *xc = x + ((b * frames + center) * nc) * (long long)H * W;
+        if (scale == 1) {
+            for (int c = 0; c < nc; ++c)
+                out[((b * nc + c) * Ho + oy) * (long long)Wo + ox] =
+                    (Tout)(v[c] + to_f<Tin>(xc[((long long)c * H + oy) * W + ox]));
+        } else {
+            const float inv = 1.f / scale;
+            const float sy = fmaxf(inv * (oy + 0.5f) - 0.5f, 0.f), sx = fmaxf(inv * (ox + 0.5f) - 0.5f, 0.f);
+            const int y0 = (int)sy, x0 = (int)sx;
+            const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+            const float ly = sy - y0, lx = sx - x0;
+            for (int c = 0; c < nc; ++c) {
+                const Tin *pc = xc + (long long)c * H * W;
+                const float base =
+                    (1.f - ly) * ((1.f - lx) * to_f<Tin>(pc[y0 * W + x0]) + lx * to_f<Tin>(pc[y0 * W + x1])) +
+                    ly * ((1.f - lx) * to_f<Tin>(pc[y1 * W + x0]) + lx * to_f<Tin>(pc[y1 * W + x1]));
+                out[((b * nc + c) * Ho + oy) * (long long)Wo + ox] = (Tout)(v[c] + base);
+            }
+        }
+    }
+}
+template <typename Tout> __device__ __forceinline__ Tout cast_out(float v);
+template <typename T, typename Tin, typename Tout>
+int launch_final_add(const T *res_c8, const Tin *x, Tout *out, int B, int frames, int center, int nc, int H,
+                     int W, int scale, cudaStream_t s) {
+    RVSR_CHECK_ARG(nc <= 8, "final_add: nc %d > 8", nc);
+    const long long total = (long long)B * H * scale * W * scale;
+    if (total == 0) return RVSR_OK;
+    final_add_kernel<T, Tin, Tout><<<(int)((total + 255) / 256 < 16384 ? (total + 255) / 256 : 16384), 256, 0, s>>>(
+        res_c8, x, out, frames, center, nc, H, W, scale, total);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+#define INST_FINAL(T, Tin, Tout) \
+    template int launch_final_add<T, Tin, Tout>(const T *, const Tin *, Tout *, int, int, int, int, int, int, int, cudaStream_t);
+INST_FINAL(float, float, float)
+INST_FINAL(float, __half, float)
+INST_FINAL(float, float, __half)
+INST_FINAL(float, __half, __half)
+INST_FINAL(__half, float, float)
+INST_FINAL(__half, __half, float)
+INST_FINAL(__half, float, __half)
+INST_FINAL(__half, __half, __half)
+
+}  // namespace rvsr
+
+// ---------------------------------------------------------------- grouped -> dense weight (operator-level API only)
+namespace rvsr {
+__global__ void expand_grouped_weight_kernel(const float *__restrict__ w, float *__restrict__ dst, int Cout, int C,
+                                             int K, int groups, long long total) {
+    const int cin_g = C / groups, cout_g = Cout / groups;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i % K);
+        const int c = (int)((i / K) % C);
+        const int co = (int)(i / ((long long)K * C));
+        dst[i] = (c / cin_g == co / cout_g) ? w[((long long)co * cin_g + c % cin_g) * K + t] : 0.f;
+    }
+}
+int expand_grouped_weight(const float *w, float *dst, int Cout, int C, int K, int groups, cudaStream_t s) {
+    const long long total = (long long)Cout * C * K;
+    expand_grouped_weight_kernel<<<(int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096), 256, 0, s>>>(
+        w, dst, Cout, C, K, groups, total);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+}  // namespace rvsr

@@ -1,0 +1,167 @@
+"""Python handle on the C++ EDVR inference engine (rvsr_engine_* in include/rvsr_b200.h).
+
+PyTorch is used only for device memory and the current CUDA stream; all compute is the
+library's own kernels.  One engine per (device, precision); weights are handed over as
+fp32 device tensors under the reference's state_dict key names.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+_PRECISION = {"fp32": _lib.F32, "fp16": _lib.F16}
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return _lib.F32
+    if t.dtype == torch.float16:
+        return _lib.F16
+    raise RuntimeError("realvsr_b200 engine: unsupported dtype %s" % t.dtype)
+
+
+class EDVREngine:
+    def __init__(self, nf=64, nc=3, nframes=5, groups=8, front_RBs=5, back_RBs=10, center=None, predeblur=False,
+                 HR_in=False, w_TSA=True, upsample=True, precision="fp16", device=None):
+        self.L = _lib.lib()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.cfg = _lib.EdvrConfig(nf, nc, nframes, groups, front_RBs, back_RBs, -1 if center is None else center,
+                                   int(bool(predeblur)), int(bool(HR_in)), int(bool(w_TSA)), int(bool(upsample)),
+                                   _PRECISION[precision])
+        self.precision = precision
+        self.scale = 4 if upsample else 1
+        h = ctypes.c_void_p()
+        _lib.check(self.L.rvsr_engine_create(ctypes.byref(self.cfg), ctypes.byref(h)), "engine_create")
+        self.h = h
+        self._ws = None
+        self._staging = {}
+        self.loaded = False
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.L.rvsr_engine_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ weights
+    def weight_names(self):
+        n = self.L.rvsr_engine_num_weights(self.h)
+        return [self.L.rvsr_engine_weight_name(self.h, i).decode() for i in range(n)]
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def load_state_dict(self, sd, strict=True):
+        """Strict like the reference's test scripts (test_RealVSR_wi_GT.py:77): unexpected or
+        missing keys raise RuntimeError.  A leading 'module.' (DataParallel) is stripped like
+        base_model.load_network does (base_model.py:104-114)."""
+        with torch.cuda.device(self.device):
+            for k, v in sd.items():
+                name = k[7:] if k.startswith("module.") else k
+                t = v.detach().to(device=self.device, dtype=torch.float32).contiguous()
+                shape = (ctypes.c_int64 * t.dim())(*t.shape)
+                try:
+                    _lib.check(self.L.rvsr_engine_set_weight(self.h, name.encode(), ctypes.c_void_p(t.data_ptr()),
+                                                             shape, t.dim(), self._stream()), "load_state_dict")
+                except RuntimeError:
+                    if strict:
+                        raise
+            _lib.check(self.L.rvsr_engine_finalize(self.h, self._stream()), "load_state_dict")
+            torch.cuda.current_stream(self.device).synchronize()  # source tensors may be temporaries
+        self.loaded = True
+
+    # ------------------------------------------------------------------ forward
+    def _workspace(self, B, H, W):
+        need = self.L.rvsr_engine_workspace_bytes(self.h, B, H, W)
+        if need == 0:
+            _lib.check(_lib.E_INVALID, "workspace_bytes")
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def forward(self, x, out_dtype=None):
+        """x: [B, N, C, H, W] CUDA tensor (fp32 or fp16) -> [B, C, sH, sW] of out_dtype (default x.dtype)."""
+        if not x.is_cuda:
+            raise NotImplementedError("realvsr_b200 engine runs on CUDA tensors only (no CPU fallback)")
+        if x.dim() != 5 or x.shape[1] != self.cfg.nframes or x.shape[2] != self.cfg.nc:
+            raise RuntimeError("expected input [B, %d, %d, H, W], got %s" % (self.cfg.nframes, self.cfg.nc,
+                                                                               tuple(x.shape)))
+        x = x.contiguous()
+        B, _, _, H, W = x.shape
+        out = torch.empty(B, self.cfg.nc, H * self.scale, W * self.scale, device=x.device,
+                          dtype=out_dtype or x.dtype)
+        with torch.cuda.device(self.device):
+            ws = self._workspace(B, H, W)
+            _lib.check(self.L.rvsr_engine_forward(self.h, ctypes.c_void_p(x.data_ptr()), _dt(x),
+                                                  ctypes.c_void_p(out.data_ptr()), _dt(out), B, H, W,
+                                                  ctypes.c_void_p(ws.data_ptr()), ws.numel(), self._stream()),
+                       "engine_forward")
+        return out
+
+    __call__ = forward
+
+    def forward_host(self, x_host, out_host=None):
+        """Host tensors in, host tensors out (pinned for async copies): H2D + forward + D2H on
+        the current stream, then a stream synchronise -- what the reference's
+        util.single_forward (utils/util.py:222-237) does around the model."""
+        B, _, _, H, W = x_host.shape
+        key = (tuple(x_host.shape), x_host.dtype)
+        if key not in self._staging:
+            self._staging.clear()
+            self._staging[key] = (torch.empty(x_host.shape, dtype=x_host.dtype, device=self.device),
+                                  torch.empty(B, self.cfg.nc, H * self.scale, W * self.scale,
+                                              dtype=x_host.dtype, device=self.device))
+        din, dout = self._staging[key]
+        if out_host is None:
+            out_host = torch.empty(dout.shape, dtype=dout.dtype, pin_memory=True)
+        with torch.cuda.device(self.device):
+            ws = self._workspace(B, H, W)
+            _lib.check(self.L.rvsr_engine_forward_host(
+                self.h, ctypes.c_void_p(x_host.data_ptr()), _dt(x_host), ctypes.c_void_p(out_host.data_ptr()),
+                _dt(out_host), B, H, W, ctypes.c_void_p(din.data_ptr()), ctypes.c_void_p(dout.data_ptr()),
+                ctypes.c_void_p(ws.data_ptr()), ws.numel(), self._stream()), "engine_forward_host")
+            torch.cuda.current_stream(self.device).synchronize()
+        return out_host
+
+    def last_launch_count(self):
+        return self.L.rvsr_engine_last_launch_count(self.h)
+
+    def profile(self, x, steps=3):
+        """Run `steps` forwards with per-launch CUDA-event timing; returns a list of dicts
+        {label, ms, flops, bytes} (ms averaged over the steps), in launch order."""
+        rows = None
+        _lib.check(self.L.rvsr_engine_set_profiling(self.h, 1))
+        try:
+            for _ in range(steps):
+                self.forward(x)
+                n = self.L.rvsr_engine_profile_collect(self.h)
+                if n < 0:
+                    _lib.check(n, "profile_collect")
+                cur = []
+                buf = ctypes.create_string_buffer(128)
+                ms, fl, by = ctypes.c_float(), ctypes.c_double(), ctypes.c_double()
+                for i in range(n):
+                    _lib.check(self.L.rvsr_engine_profile_entry(self.h, i, buf, 128, ctypes.byref(ms),
+                                                                ctypes.byref(fl), ctypes.byref(by)))
+                    cur.append(dict(label=buf.value.decode(), ms=ms.value, flops=fl.value, bytes=by.value))
+                if rows is None:
+                    rows = cur
+                else:
+                    for r, c in zip(rows, cur):
+                        r["ms"] += c["ms"]
+            for r in rows:
+                r["ms"] /= steps
+        finally:
+            self.L.rvsr_engine_set_profiling(self.h, 0)
+        return rows
+
+    def read_tap(self, name, shape):
+        dst = torch.empty(shape, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.rvsr_engine_read_tap(self.h, name.encode(), ctypes.c_void_p(dst.data_ptr()),
+                                                   dst.numel(), self._stream()), "read_tap")
+        return dst

@@ -1,0 +1,76 @@
+"""CPU tests of the boundary: the C-ABI library loads and exports exactly the symbols that
+include/rvsr_b200.h declares; host-side argument validation works without a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from realvsr_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "rvsr_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rvsr_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_all_exported_and_bound():
+    names = _declared()
+    assert len(names) >= 20
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(L, n), "library does not export %s" % n
+    assert sorted(_lib.SIGNATURES.keys()) == names, "python binding and header drifted"
+    assert _lib.lib().rvsr_version() >= 100
+
+
+def test_engine_config_validation_without_gpu():
+    L = _lib.lib()
+    h = ctypes.c_void_p()
+    bad = _lib.EdvrConfig(64, 3, 5, 8, 5, 10, -1, 1, 0, 1, 1, _lib.F16)  # predeblur: not built
+    assert L.rvsr_engine_create(ctypes.byref(bad), ctypes.byref(h)) == _lib.E_UNSUPPORTED
+    assert b"predeblur" in L.rvsr_last_error()
+    bad = _lib.EdvrConfig(16, 3, 5, 8, 5, 10, -1, 0, 0, 1, 0, _lib.F16)  # NoUp needs nf == 64
+    assert L.rvsr_engine_create(ctypes.byref(bad), ctypes.byref(h)) == _lib.E_INVALID
+    with pytest.raises(NotImplementedError):
+        _lib.check(_lib.E_UNSUPPORTED)
+    with pytest.raises(RuntimeError):
+        _lib.check(_lib.E_INVALID)
+
+
+def test_engine_state_dict_contract_names():
+    from helpers import edvr_state_shapes
+    L = _lib.lib()
+    for up, kw in ((1, dict(nf=64, nframes=5, groups=8, front_RBs=5, back_RBs=10, w_TSA=True)),
+                   (0, dict(nf=64, nframes=3, groups=8, front_RBs=5, back_RBs=10, w_TSA=False))):
+        cfg = _lib.EdvrConfig(kw["nf"], 3, kw["nframes"], kw["groups"], kw["front_RBs"], kw["back_RBs"], -1, 0, 0,
+                              int(kw["w_TSA"]), up, _lib.F32)
+        h = ctypes.c_void_p()
+        assert L.rvsr_engine_create(ctypes.byref(cfg), ctypes.byref(h)) == 0
+        names = [L.rvsr_engine_weight_name(h, i).decode() for i in range(L.rvsr_engine_num_weights(h))]
+        assert names == list(edvr_state_shapes("EDVR" if up else "EDVR_NoUp", **kw).keys())
+        # workspace sizing is host-only arithmetic: 0 for bad dims, >0 and monotone otherwise
+        assert L.rvsr_engine_workspace_bytes(h, 1, 30, 32) == 0
+        a, b = L.rvsr_engine_workspace_bytes(h, 1, 32, 32), L.rvsr_engine_workspace_bytes(h, 2, 32, 32)
+        assert 0 < a < b
+        L.rvsr_engine_destroy(h)
+
+
+def test_dcn_argument_validation_without_gpu():
+    L = _lib.lib()
+    # channels not divisible by deformable groups -> INVALID (reference: AT_ERROR)
+    rc = L.rvsr_mdcn_fwd(None, None, None, None, None, None, 1, 10, 8, 8, 8, 3, 3, 1, 1, 1, 1, 4, 0, None, 0, None)
+    assert rc == _lib.E_INVALID
+    assert L.rvsr_mdcn_fwd_workspace_bytes(1, 16, 8, 8, 8, 3, 3, 1, 1, 1, 1, 4, 0) > 0
+    # empty batch is a no-op, like the reference
+    assert L.rvsr_mdcn_fwd(None, None, None, None, None, None, 0, 16, 8, 8, 8, 3, 3, 1, 1, 1, 1, 4, 0, None, 0, None) == 0
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
+        _lib.lib()

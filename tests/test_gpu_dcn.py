@@ -1,0 +1,114 @@
+"""GPU parity tests of the DCNv2 operator through the C ABI (rvsr_mdcn_fwd via the
+autograd Function in realvsr_b200/archs/dcn/deform_conv.py).
+
+Tolerances (north_star: 1e-3 relative, fp32): fp32 path asserts 1e-4 of max|ref| (only the
+summation order differs from the oracle); fp16 I/O asserts 2e-3 against the fp32 oracle
+evaluated on the same fp16-rounded inputs (fp32 coordinates / blend / accumulate inside)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import realvsr_b200.archs.dcn.deform_conv  # noqa: F401
+from helpers import GOLDEN, rel_err
+from oracle import edvr_oracle as O
+from synth import synth_normal
+
+D = sys.modules['realvsr_b200.archs.dcn.deform_conv']
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _case(B, C, H, W, Cout, dg, groups=1, stride=1, pad=1, dil=1, k=3, off_std=3.0, seed=100):
+    Ho = (H + 2 * pad - (dil * (k - 1) + 1)) // stride + 1
+    Wo = (W + 2 * pad - (dil * (k - 1) + 1)) // stride + 1
+    x = synth_normal((B, C, H, W), seed)
+    off = synth_normal((B, dg * 2 * k * k, Ho, Wo), seed + 1, std=off_std)
+    msk = torch.sigmoid(synth_normal((B, dg * k * k, Ho, Wo), seed + 2))
+    w = synth_normal((Cout, C // groups, k, k), seed + 3, std=0.1)
+    b = synth_normal((Cout,), seed + 4)
+    return x, off, msk, w, b, (stride, pad, dil, groups, dg)
+
+
+CASES = [
+    dict(B=2, C=16, H=11, W=13, Cout=12, dg=4),                       # ragged tile edges, offsets leave the image
+    dict(B=1, C=64, H=24, W=40, Cout=64, dg=8),                       # EDVR shape class (8 ch / group)
+    dict(B=1, C=8, H=16, W=16, Cout=8, dg=8),                         # 1 channel per group (tiny arch)
+    dict(B=2, C=8, H=12, W=9, Cout=6, dg=4, groups=2, stride=2),      # conv groups + stride 2
+    dict(B=1, C=16, H=10, W=10, Cout=16, dg=2, pad=2, dil=2),         # dilation
+    dict(B=1, C=24, H=9, W=7, Cout=70, dg=3),                         # Cout > one tile, C not /16
+    dict(B=1, C=16, H=8, W=8, Cout=8, dg=2, k=1, pad=0),              # 1x1 kernel
+    dict(B=1, C=16, H=6, W=6, Cout=8, dg=4, off_std=40.0),            # everything out of range -> bias only
+]
+
+
+@pytest.mark.parametrize("cfg", CASES)
+def test_mdcn_fwd_fp32_vs_oracle(cfg):
+    x, off, msk, w, b, (s, p, d, g, dg) = _case(**cfg)
+    ref = O.dcn_forward(x, off, msk, w, b, s, p, d, g, dg)
+    y = D.modulated_deform_conv(x.to(DEV), off.to(DEV), msk.to(DEV), w.to(DEV), b.to(DEV), s, p, d, g, dg)
+    assert y.shape == ref.shape and y.dtype == torch.float32
+    assert rel_err(y.cpu(), ref) < 1e-4
+
+
+@pytest.mark.parametrize("cfg", CASES[:4])
+def test_mdcn_fwd_fp16_vs_oracle(cfg):
+    x, off, msk, w, b, (s, p, d, g, dg) = _case(**cfg)
+    h = lambda t: t.half().float()  # noqa: E731
+    ref = O.dcn_forward(h(x), h(off), h(msk), h(w), h(b), s, p, d, g, dg)
+    y = D.modulated_deform_conv(x.to(DEV).half(), off.to(DEV).half(), msk.to(DEV).half(), w.to(DEV).half(),
+                                b.to(DEV).half(), s, p, d, g, dg)
+    assert y.dtype == torch.float16
+    assert rel_err(y.float().cpu(), ref) < 2e-3
+
+
+def test_mdcn_fwd_matches_reference_generated_golden():
+    z = np.load(os.path.join(GOLDEN, "dcn_unit.npz"))
+    B, C, H, W, Cout, dg = [int(v) for v in z["dims"]]
+    x = synth_normal((B, C, H, W), 71); off = synth_normal((B, dg * 18, H, W), 72, std=4.0)
+    msk = torch.sigmoid(synth_normal((B, dg * 9, H, W), 73).double()).float()
+    w = synth_normal((Cout, C, 3, 3), 74, std=0.1); b = synth_normal((Cout,), 75)
+    y = D.modulated_deform_conv(x.to(DEV), off.to(DEV), msk.to(DEV), w.to(DEV), b.to(DEV), 1, 1, 1, 1, dg)
+    assert rel_err(y.cpu(), torch.from_numpy(z["out"]).float()) < 1e-4
+
+
+def test_mdcn_zero_offset_is_half_conv_and_no_bias():
+    x = synth_normal((2, 16, 20, 20), 5).to(DEV)
+    w = synth_normal((16, 16, 3, 3), 6, std=0.1).to(DEV)
+    y = D.modulated_deform_conv(x, torch.zeros(2, 2 * 18, 20, 20, device=DEV),
+                                torch.full((2, 2 * 9, 20, 20), 0.5, device=DEV), w, None, 1, 1, 1, 1, 2)
+    assert rel_err(y, 0.5 * torch.nn.functional.conv2d(x, w, padding=1)) < 1e-4
+
+
+def test_mdcn_error_behaviour():
+    x, off, msk, w, b, (s, p, d, g, dg) = _case(B=1, C=16, H=8, W=8, Cout=8, dg=4)
+    with pytest.raises(NotImplementedError):            # CPU tensors, like the reference
+        D.modulated_deform_conv(x, off, msk, w, b, s, p, d, g, dg)
+    with pytest.raises(RuntimeError):                   # non-contiguous input (reference TORCH_CHECK)
+        D.modulated_deform_conv(x.to(DEV).transpose(2, 3), off.to(DEV), msk.to(DEV), w.to(DEV), b.to(DEV), s, p, d,
+                                g, dg)
+    with pytest.raises(RuntimeError):                   # channels % deformable groups
+        D.modulated_deform_conv(x.to(DEV)[:, :15].contiguous(), off.to(DEV), msk.to(DEV), w.to(DEV)[:, :15].contiguous(),
+                                b.to(DEV), s, p, d, g, dg)
+    y = D.modulated_deform_conv(x.to(DEV)[:0], off.to(DEV)[:0], msk.to(DEV)[:0], w.to(DEV), b.to(DEV), s, p, d, g, dg)
+    assert y.shape[0] == 0                              # empty batch
+
+
+def test_mdcn_fwd_vs_reference_cuda_extension():
+    """Second oracle: the reference's own deform_conv_cuda extension, compiled unmodified
+    from /root/reference into oracle/_ref (oracle/build_ref.py)."""
+    from oracle.build_ref import load_ref
+    ref_ext = load_ref()
+    if ref_ext is None:
+        pytest.skip("oracle/_ref not built")
+    x, off, msk, w, b, (s, p, d, g, dg) = _case(B=2, C=64, H=20, W=28, Cout=64, dg=8, off_std=2.0)
+    xd, od, md, wd, bd = [t.to(DEV) for t in (x, off, msk, w, b)]
+    out_ref = xd.new_empty(2, 64, 20, 28)
+    ref_ext.modulated_deform_conv_cuda_forward(xd, wd, bd, xd.new_empty(0), od, md, out_ref, xd.new_empty(0), 3, 3,
+                                               s, s, p, p, d, d, g, dg, True)
+    y = D.modulated_deform_conv(xd, od, md, wd, bd, s, p, d, g, dg)
+    # the reference GEMM (cuBLAS addmm_) may run in TF32; both sides only agree to ~1e-3
+    assert rel_err(y, out_ref) < 1e-3
+    assert rel_err(out_ref.cpu(), O.dcn_forward(x, off, msk, w, b, s, p, d, g, dg)) < 1e-3

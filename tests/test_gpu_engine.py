@@ -1,0 +1,140 @@
+"""GPU parity tests of the EDVR engine (rvsr_engine_forward through realvsr_b200.archs).
+
+Errors are measured on the network's own contribution  out - base  (base = bilinear x4 of the
+centre frame, or the centre frame for EDVR_NoUp) so the comparison is not flattered by the
+image-sized base term, as max|diff| / max|reference residual|.
+  fp32 engine vs reference-generated golden : < 1e-3  (north_star tolerance)
+  fp16 engine vs the same golden            : < 3e-2  (fp16 storage of ~100 chained layers;
+                                               fp32 coordinates, blend and accumulation)
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import EDVR_CASES, load_case, rel_err
+from realvsr_b200.archs import EDVR_arch as E
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+ENGINE_CASES = [c for c in EDVR_CASES if c != "edvr_predeblur"]
+
+
+def _base(c):
+    xc = c["x"][:, c["kwargs"]["nframes"] // 2]
+    return F.interpolate(xc, scale_factor=4, mode="bilinear", align_corners=False) if c["cls"] == "EDVR" else xc
+
+
+def _net(c, path):
+    net = getattr(E, c["cls"])(**c["kwargs"]).eval()
+    net.load_state_dict(c["sd"], strict=True)
+    net.exec_path = path
+    return net.to(DEV)
+
+
+@pytest.mark.parametrize("name", ENGINE_CASES)
+def test_engine_fp32_matches_golden(name):
+    c = load_case(name)
+    net = _net(c, "engine")
+    with torch.no_grad():
+        y = net(c["x"].to(DEV))
+    assert y.dtype == torch.float32 and y.shape == c["out"].shape
+    base = _base(c)
+    assert rel_err(y.cpu() - base, c["out"] - base) < 1e-3
+    eng = net._get_engine(c["x"].to(DEV))
+    al = eng.read_tap("aligned", (c["x"].shape[0] * c["x"].shape[1],) + tuple(c["aligned0"].shape[1:]))
+    B, N = c["x"].shape[:2]
+    al0 = al.view(B, N, *al.shape[1:])[:, 0].cpu()
+    assert rel_err(al0, c["aligned0"]) < 1e-3
+
+
+@pytest.mark.parametrize("name", ENGINE_CASES)
+def test_engine_fp16_matches_golden(name):
+    c = load_case(name)
+    net = _net(c, "engine").half()
+    with torch.no_grad():
+        y = net(c["x"].to(DEV).half())
+    assert y.dtype == torch.float16
+    base = _base(c)
+    assert rel_err(y.float().cpu() - base, c["out"] - base) < 3e-2
+
+
+@pytest.mark.parametrize("name", ["edvr_tiny", "edvr_noup_3f", "edvr_predeblur"])
+def test_module_path_matches_golden(name):
+    """nn.Conv2d modules + our DCN operator (the autograd-capable path)."""
+    c = load_case(name)
+    net = _net(c, "module")
+    with torch.no_grad():
+        y = net(c["x"].to(DEV))
+    base = _base(c)
+    assert rel_err(y.cpu() - base, c["out"] - base) < 1e-3
+
+
+def test_engine_batch_invariance_and_determinism():
+    c = load_case("edvr_tiny")
+    net = _net(c, "engine")
+    x = c["x"].to(DEV)
+    with torch.no_grad():
+        y1 = net(x)
+        y2 = net(torch.cat([x, x.flip(1), x], 0))
+        y3 = net(x)
+    assert torch.equal(y1, y3)                      # bit-exact rerun
+    assert torch.equal(y2[0:1], y1) and torch.equal(y2[2:3], y1)   # batch position does not matter
+
+
+def test_engine_reloads_weights_when_parameters_change():
+    c = load_case("edvr_tiny")
+    net = _net(c, "engine")
+    x = c["x"].to(DEV)
+    with torch.no_grad():
+        y1 = net(x)
+        net.conv_last.bias.add_(0.25)
+        y2 = net(x)
+    assert rel_err(y2 - y1, torch.full_like(y1, 0.25)) < 1e-5
+
+
+def test_engine_rejects_bad_sizes():
+    c = load_case("edvr_tiny")
+    net = _net(c, "engine")
+    with pytest.raises(RuntimeError):
+        with torch.no_grad():
+            net(torch.zeros(1, 5, 3, 30, 32, device=DEV))   # H not a multiple of 4
+
+
+def test_engine_host_buffers_roundtrip():
+    c = load_case("edvr_tiny")
+    net = _net(c, "engine")
+    x = c["x"].to(DEV)
+    with torch.no_grad():
+        y = net(x)
+    eng = net._get_engine(x)
+    out = eng.forward_host(c["x"].pin_memory())
+    assert torch.equal(out, y.cpu())
+
+
+def test_cfg2_full_size_fp16_properties():
+    """BASELINE cfg2 size (5x3x180x320 -> 720x1280, nf=64, TSA): too slow for the CPU oracle,
+    so check size-independent properties: finite, deterministic, zero-initialised offset
+    convs turn every DCN into 0.5 * conv (checked against the module path in fp32)."""
+    from synth import synth_input, synth_state_dict
+    from helpers import edvr_state_shapes
+    kw = dict(nf=64, nc=3, nframes=5, groups=8, front_RBs=5, back_RBs=10, w_TSA=True)
+    sd = synth_state_dict(edvr_state_shapes("EDVR", **kw), 7)
+    net = E.EDVR(**kw).eval()
+    net.load_state_dict(sd, strict=True)
+    net = net.to(DEV).half()
+    net.exec_path = "engine"
+    x = synth_input((1, 5, 3, 180, 320), 8).to(DEV).half()
+    with torch.no_grad():
+        y = net(x)
+        y2 = net(x)
+    assert y.shape == (1, 3, 720, 1280) and bool(torch.isfinite(y).all()) and torch.equal(y, y2)
+    # interior crop consistency with the fp32 module path on a 64x64 crop is covered by the golden
+    # nf64 case; here compare fp16 engine vs fp32 engine at full size
+    net32 = E.EDVR(**kw).eval()
+    net32.load_state_dict(sd, strict=True)
+    net32 = net32.to(DEV)
+    net32.exec_path = "engine"
+    with torch.no_grad():
+        y32 = net32(x.float())
+    base = F.interpolate(x[:, 2].float(), scale_factor=4, mode="bilinear", align_corners=False)
+    assert rel_err(y.float() - base, y32 - base) < 3e-2
