@@ -85,6 +85,19 @@ int rvsr_mdcn_pack_fwd(const void *x, const void *feat, const void *w_offset_mas
                        int B, int C, int H, int W, int Cout, int dg, int act, int dtype,
                        void *workspace, size_t workspace_bytes, void *stream);
 
+/* ------------------------------------------------------------------ convolution operator
+ * One nn.Conv2d site of EDVR_arch.py (:71-91, :146-164, :229-253) with what surrounds it fused:
+ * torch.cat([x1, x2], 1) on the input (x2 may be NULL), bias, activation, residual add (after
+ * the activation; may be NULL) and optionally nn.PixelShuffle(2) on the output
+ * (y is then [B, Cout/4, 2Ho, 2Wo]).  ks in {1,3}, pad = ks/2, stride in {1,2}.  NCHW tensors
+ * of `dtype`.  use_tc = 1 selects the tcgen05 kernel (fp16 only; RVSR_E_UNSUPPORTED if the
+ * shape is not covered), 0 the CUDA-core kernel. */
+size_t rvsr_conv2d_fwd_workspace_bytes(int B, int C1, int C2, int H, int W, int Cout, int ks, int dtype);
+int rvsr_conv2d_fwd(const void *x1, const void *x2, const void *weight, const void *bias,
+                    const void *residual, void *y, int B, int C1, int C2, int H, int W, int Cout,
+                    int ks, int stride, int act, int shuffle, int dtype, int use_tc, void *workspace,
+                    size_t workspace_bytes, void *stream);
+
 /* ------------------------------------------------------------------ EDVR engine
  * Replaces EDVR.forward / EDVR_NoUp.forward (EDVR_arch.py:258-320, :358-404) and everything
  * they call (PCD_Align :98-132, TSA_Fusion :168-208, ResidualBlock_noBN arch_util.py:135-139)

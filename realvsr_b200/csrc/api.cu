@@ -159,6 +159,101 @@ int rvsr_mdcn_pack_fwd(const void *, const void *, const void *, const void *, c
     return RVSR_E_UNSUPPORTED;
 }
 
+size_t rvsr_conv2d_fwd_workspace_bytes(int B, int C1, int C2, int H, int W, int Cout, int ks, int dtype) {
+    const size_t es = dtype == RVSR_F16 ? 2 : 4;
+    const size_t px = (size_t)B * H * W;
+    const int Cin = C1 + C2;
+    size_t n = 0;
+    n += align_up(px * (size_t)cdiv(C1 > 16 ? C1 : 16, 8) * 8 * es, 256) + align_up(px * (size_t)cdiv(C2 > 0 ? C2 : 1, 8) * 8 * es, 256);
+    n += 2 * align_up(px * 4 * (size_t)cdiv(Cout, 8) * 8 * es, 256);            // out (maybe shuffled) + residual
+    n += 2 * align_up((size_t)Cout * (Cin + 16) * ks * ks * 4, 256);             // fp32 weight copy + padded copy
+    n += align_up((size_t)cdiv(Cin + 16, 8) * ks * ks * 8 * cdiv(Cout, 64) * 64 * 4, 256);  // simt pack
+    n += align_up(tc_conv_weight_bytes(Cout, Cin, ks) + 256, 256) + align_up((size_t)Cout * 4, 256);
+    return n + 4096;
+}
+
+}  // extern "C"
+
+template <typename T>
+static int conv2d_fwd_t(const void *x1, const void *x2, const void *weight, const void *bias, const void *residual,
+                        void *y, int B, int C1, int C2, int H, int W, int Cout, int ks, int stride, int act,
+                        int shuffle, int dtype, int use_tc, Carver &cv, cudaStream_t s) {
+    const size_t es = sizeof(T);
+    const int Cin = C1 + C2, KK = ks * ks;
+    const int Ho = stride == 1 ? H : (H - 1) / 2 + 1, Wo = stride == 1 ? W : (W - 1) / 2 + 1;
+    const bool tc = use_tc && dtype == RVSR_F16;
+    const int C1s = (tc && C2 == 0 && C1 < 16) ? 16 : C1;   // tensor-core K granularity (see engine.cu finalize)
+    const size_t px = (size_t)B * H * W, pxo = (size_t)B * Ho * Wo;
+    T *a1 = (T *)cv.take(px * cdiv(C1s, 8) * 8 * es);
+    T *a2 = C2 > 0 ? (T *)cv.take(px * cdiv(C2, 8) * 8 * es) : nullptr;
+    const int Cst = shuffle ? Cout / 4 : Cout;
+    const size_t out_elems = (shuffle ? pxo * 4 : pxo) * cdiv(Cst, 8) * 8;
+    T *o = (T *)cv.take(out_elems * es);
+    T *r = residual ? (T *)cv.take(out_elems * es) : nullptr;
+    float *w32 = (float *)cv.take((size_t)Cout * Cin * KK * 4);
+    float *wpad = (float *)cv.take((size_t)Cout * (Cin + 16) * KK * 4);
+    float *b32 = (float *)cv.take((size_t)Cout * 4);
+    const int CinS = C1s + C2;
+    const int cout_pad = cdiv(Cout, 64) * 64;
+    float *wsimt = (float *)cv.take((size_t)cdiv(CinS, 8) * KK * 8 * cout_pad * 4);
+    void *wtc = tc ? cv.take(tc_conv_weight_bytes(Cout, CinS, ks) + 16) : nullptr;
+    if (!cv.ok) { set_error("conv2d: workspace too small"); return RVSR_E_WORKSPACE; }
+    RVSR_TRY((launch_pack_nchw<T, T>((const T *)x1, a1, B, C1, H, W, s, C1s)));
+    if (C2 > 0) RVSR_TRY((launch_pack_nchw<T, T>((const T *)x2, a2, B, C2, H, W, s)));
+    if (residual) RVSR_TRY((launch_pack_nchw<T, T>((const T *)residual, r, B, Cout, Ho, Wo, s)));
+    const float *w = (const float *)weight, *b = (const float *)bias;
+    if (dtype == RVSR_F16) {
+        RVSR_TRY(launch_convert_f16_f32(weight, w32, (long long)Cout * Cin * KK, s));
+        w = w32;
+        if (bias) { RVSR_TRY(launch_convert_f16_f32(bias, b32, Cout, s)); b = b32; }
+    }
+    if (C1s != C1) { RVSR_TRY(pad_weight_cin(w, wpad, Cout, C1, C1s, KK, s)); w = wpad; }
+    const int cins = CinS;
+    RVSR_CHECK_ARG(C1 % 8 == 0 || C2 == 0, "conv2d: first source must have a multiple of 8 channels when concatenating");
+    RVSR_TRY(pack_weight_simt(w, wsimt, Cout, CinS, ks, &cins, 1, cout_pad, s));
+    if (tc && tc_conv_weight_bytes(Cout, CinS, ks) > 0) RVSR_TRY(pack_weight_tc(w, wtc, Cout, CinS, ks, shuffle, s));
+    ConvOp op = {};
+    op.src[0] = Src{a1, (long long)cdiv(C1s, 8) * H * W * 8, C1s, 1, -1};
+    op.nsrc = 1;
+    if (C2 > 0) { op.src[1] = Src{a2, (long long)cdiv(C2, 8) * H * W * 8, C2, 1, -1}; op.nsrc = 2; }
+    op.w_simt = wsimt; op.w_tc = (tc && tc_conv_weight_bytes(Cout, CinS, ks) > 0) ? wtc : nullptr; op.bias = b;
+    op.out = o; op.out_image_stride = (long long)(out_elems / B);
+    op.residual = r; op.res_image_stride = op.out_image_stride;
+    op.N = B; op.H = H; op.W = W; op.Cout = Cout; op.ks = ks; op.stride = stride; op.act = act;
+    op.out_mode = shuffle ? OUT_C8_SHUFFLE2 : OUT_C8; op.sig_from = 1 << 30;
+    if (tc) {
+        if (!tc_conv_supported(op)) { set_error("conv2d: configuration not covered by the tcgen05 kernel"); return RVSR_E_UNSUPPORTED; }
+        RVSR_TRY(launch_conv_tc(op, s));
+    } else {
+        RVSR_TRY(launch_conv_simt<T>(op, s));
+    }
+    if (shuffle) return launch_unpack_nchw<T, T>(o, (T *)y, B, Cst, 2 * Ho, 2 * Wo, s);
+    return launch_unpack_nchw<T, T>(o, (T *)y, B, Cout, Ho, Wo, s);
+}
+
+extern "C" {
+
+int rvsr_conv2d_fwd(const void *x1, const void *x2, const void *weight, const void *bias, const void *residual, void *y,
+                    int B, int C1, int C2, int H, int W, int Cout, int ks, int stride, int act, int shuffle, int dtype,
+                    int use_tc, void *workspace, size_t workspace_bytes, void *stream) {
+    RVSR_CHECK_ARG(B >= 0 && C1 > 0 && C2 >= 0 && H > 0 && W > 0 && Cout > 0, "conv2d: bad sizes");
+    RVSR_CHECK_ARG(ks == 1 || ks == 3, "conv2d: kernel size %d not built", ks);
+    RVSR_CHECK_ARG(stride == 1 || stride == 2, "conv2d: stride %d not built", stride);
+    RVSR_CHECK_ARG(dtype == RVSR_F32 || dtype == RVSR_F16, "conv2d: bad dtype");
+    RVSR_CHECK_ARG(!shuffle || (Cout % 4 == 0 && residual == nullptr), "conv2d: pixel-shuffle needs Cout %% 4 == 0");
+    if (B == 0) return RVSR_OK;
+    RVSR_CHECK_ARG(x1 && weight && y && workspace, "conv2d: null buffer");
+    Carver cv{(char *)workspace, workspace_bytes};
+    const size_t mis = (size_t)((uintptr_t)workspace % 256);
+    if (mis) { cv.base += 256 - mis; cv.cap -= 256 - mis; }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == RVSR_F16)
+        return conv2d_fwd_t<__half>(x1, x2, weight, bias, residual, y, B, C1, C2, H, W, Cout, ks, stride, act, shuffle,
+                                    dtype, use_tc, cv, s);
+    return conv2d_fwd_t<float>(x1, x2, weight, bias, residual, y, B, C1, C2, H, W, Cout, ks, stride, act, shuffle, dtype,
+                               0, cv, s);
+}
+
 int rvsr_engine_create(const rvsr_edvr_config *cfg, rvsr_engine **out) {
     RVSR_CHECK_ARG(cfg != nullptr && out != nullptr, "engine_create: null argument");
     RVSR_CHECK_ARG(cfg->nf > 0 && cfg->nc > 0 && cfg->nc <= 8 && cfg->nframes > 0 && cfg->groups > 0,

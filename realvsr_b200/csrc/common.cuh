@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include <string>
 
@@ -95,6 +96,40 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + __expf(-v)); }
 
+// Bilinear sample of one channel block (8 channels) at (py, px); zero unless
+// -1 < py < H and -1 < px < W; each corner individually bounds-checked
+// (deform_conv_cuda_kernel.cu:480-495, :618).
+template <typename T>
+__device__ __forceinline__ void sample8(const T *plane, int H, int W, float py, float px, float (&v)[8]) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = 0.f;
+    if (!(py > -1.f && px > -1.f && py < (float)H && px < (float)W)) return;
+    const float fy = floorf(py), fx = floorf(px);
+    const int y0 = (int)fy, x0 = (int)fx, y1 = y0 + 1, x1 = x0 + 1;
+    const float ly = py - fy, lx = px - fx, hy = 1.f - ly, hx = 1.f - lx;
+    float t[8];
+    if (y0 >= 0 && x0 >= 0) {
+        load8<T>(plane + ((long long)y0 * W + x0) * 8, t);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = fmaf(hy * hx, t[c], v[c]);
+    }
+    if (y0 >= 0 && x1 <= W - 1) {
+        load8<T>(plane + ((long long)y0 * W + x1) * 8, t);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = fmaf(hy * lx, t[c], v[c]);
+    }
+    if (y1 <= H - 1 && x0 >= 0) {
+        load8<T>(plane + ((long long)y1 * W + x0) * 8, t);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = fmaf(ly * hx, t[c], v[c]);
+    }
+    if (y1 <= H - 1 && x1 <= W - 1) {
+        load8<T>(plane + ((long long)y1 * W + x1) * 8, t);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = fmaf(ly * lx, t[c], v[c]);
+    }
+}
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -150,7 +185,8 @@ struct DcnOp {
 template <typename T> int launch_conv_simt(const ConvOp &op, cudaStream_t s);
 template <typename T> int launch_dcn_simt(const DcnOp &op, cudaStream_t s);
 template <typename T, typename Tin>
-int launch_pack_nchw(const Tin *src, T *dst, int N, int C, int H, int W, cudaStream_t s);
+int launch_pack_nchw(const Tin *src, T *dst, int N, int C, int H, int W, cudaStream_t s, int Cdst = 0);
+int pad_weight_cin(const float *w, float *dst, int Cout, int Cin, int Cpad, int KK, cudaStream_t s);
 template <typename T, typename Tout>
 int launch_unpack_nchw(const T *src, Tout *dst, int N, int C, int H, int W, cudaStream_t s);
 template <typename T>

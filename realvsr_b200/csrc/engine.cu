@@ -15,6 +15,7 @@
 #include "engine.cuh"
 
 #include <stdarg.h>
+#include <stdlib.h>
 
 namespace rvsr {
 
@@ -143,6 +144,17 @@ int Engine::finalize(cudaStream_t s) {
         pc.Cin = (int)w.shape[1];
         pc.ks = (int)w.shape[2];
         pc.bias = raw_[base + ".bias"].dev;
+        const float *wsrc = w.dev;
+        if (cfg_.precision == RVSR_F16 && pc.Cin < 16) {
+            // tensor-core K granularity is 16 channels: the LQ frames are stored zero-padded to 16
+            // channels and conv_first's weight gets matching zero input channels
+            float *padded = nullptr;
+            RVSR_CUDA(cudaMalloc(&padded, (size_t)pc.Cout * 16 * pc.ks * pc.ks * sizeof(float)));
+            owned_.push_back(padded);
+            RVSR_TRY(pad_weight_cin(w.dev, padded, pc.Cout, pc.Cin, 16, pc.ks * pc.ks, s));
+            wsrc = padded;
+            pc.Cin = 16;
+        }
         const int cout_pad = cdiv(pc.Cout, 64) * 64;
         const size_t bytes = (size_t)cdiv(pc.Cin, 8) * pc.ks * pc.ks * 8 * cout_pad * sizeof(float);
         if (pc.w_simt == nullptr) {
@@ -150,7 +162,7 @@ int Engine::finalize(cudaStream_t s) {
             owned_.push_back(pc.w_simt);
         }
         const int cin = pc.Cin;
-        RVSR_TRY(pack_weight_simt(w.dev, pc.w_simt, pc.Cout, pc.Cin, pc.ks, &cin, 1, cout_pad, s));
+        RVSR_TRY(pack_weight_simt(wsrc, pc.w_simt, pc.Cout, pc.Cin, pc.ks, &cin, 1, cout_pad, s));
         if (cfg_.precision == RVSR_F16) {
             const bool is_dcn = base.size() > 8 && base.compare(base.size() - 8, 8, "_dcnpack") == 0;
             const bool shuffle = (base == "upconv1" || base == "upconv2");
@@ -162,9 +174,9 @@ int Engine::finalize(cudaStream_t s) {
                     owned_.push_back(pc.w_tc);
                 }
                 if (is_dcn)
-                    RVSR_TRY(pack_weight_dcn_tc(w.dev, pc.w_tc, pc.Cout, pc.Cin, pc.ks * pc.ks, s));
+                    RVSR_TRY(pack_weight_dcn_tc(wsrc, pc.w_tc, pc.Cout, pc.Cin, pc.ks * pc.ks, s));
                 else
-                    RVSR_TRY(pack_weight_tc(w.dev, pc.w_tc, pc.Cout, pc.Cin, pc.ks, shuffle ? 1 : 0, s));
+                    RVSR_TRY(pack_weight_tc(wsrc, pc.w_tc, pc.Cout, pc.Cin, pc.ks, shuffle ? 1 : 0, s));
             }
         }
     }
@@ -253,7 +265,7 @@ template <typename T> struct Plan {
         ConvOp op = {};
         int cin = 0;
         for (const Src &sr : srcs) { op.src[op.nsrc++] = sr; cin += sr.C; }
-        if (cin != pc->Cin && !(pc->Cin < 8 && cin == pc->Cin)) {
+        if (cin != pc->Cin) {
             set_error("engine: %s expects %d input channels, got %d", name.c_str(), pc->Cin, cin);
             rc = RVSR_E_INVALID;
             return o;
@@ -333,15 +345,19 @@ int Engine::run(Arena &ar, bool dry, const void *x, int x_dtype, void *out, int 
     const int nf = cfg_.nf, N = cfg_.nframes, nc = cfg_.nc, dg = cfg_.groups, ctr = cfg_.center;
     const int NB = B * N;
     const int LR = RVSR_ACT_LRELU, NONE = RVSR_ACT_NONE;
-    Plan<T> P{this, ar, dry, s, packed_, cfg_.precision == RVSR_F16};
+    // RVSR_DISABLE_TC=1 routes the fp16 engine through the CUDA-core kernels (debug / cross-check)
+    static const bool tc_off = getenv("RVSR_DISABLE_TC") != nullptr && getenv("RVSR_DISABLE_TC")[0] == '1';
+    Plan<T> P{this, ar, dry, s, packed_, cfg_.precision == RVSR_F16 && !tc_off};
     using PT = Plan<T>;
 
     // ---- LQ frames -> channel-blocked
-    Act xin = P.make(NB, nc, H, W);
+    const int nc_store = (cfg_.precision == RVSR_F16 && nc < 16) ? 16 : nc;  // see finalize(): K granularity
+    Act xin = P.make(NB, nc_store, H, W);
     if (!dry && P.rc == RVSR_OK)
         P.launch("glue:pack_input", 0, (double)xin.elems() * sizeof(T) * 1.4, [&] {
-            return x_dtype == RVSR_F32 ? launch_pack_nchw<T, float>((const float *)x, (T *)xin.p, NB, nc, H, W, s)
-                                       : launch_pack_nchw<T, __half>((const __half *)x, (T *)xin.p, NB, nc, H, W, s); });
+            return x_dtype == RVSR_F32
+                       ? launch_pack_nchw<T, float>((const float *)x, (T *)xin.p, NB, nc, H, W, s, nc_store)
+                       : launch_pack_nchw<T, __half>((const __half *)x, (T *)xin.p, NB, nc, H, W, s, nc_store); });
     // ---- per-frame feature pyramid (EDVR_arch.py:276-283)
     Act L1 = P.conv("conv_first", {PT::src_of(xin)}, NB, H, W, LR);
     L1 = P.resblocks("feature_extraction", cfg_.front_RBs, L1);

@@ -174,40 +174,6 @@ template int launch_conv_simt<float>(const ConvOp &, cudaStream_t);
 template int launch_conv_simt<__half>(const ConvOp &, cudaStream_t);
 
 // ---------------------------------------------------------------- modulated deformable conv
-// Bilinear sample of one channel block (8 channels) at (py, px); zero unless
-// -1 < py < H and -1 < px < W; each corner individually bounds-checked
-// (deform_conv_cuda_kernel.cu:480-495, :618).
-template <typename T>
-__device__ __forceinline__ void sample8(const T *plane, int H, int W, float py, float px, float (&v)[8]) {
-#pragma unroll
-    for (int c = 0; c < 8; ++c) v[c] = 0.f;
-    if (!(py > -1.f && px > -1.f && py < (float)H && px < (float)W)) return;
-    const float fy = floorf(py), fx = floorf(px);
-    const int y0 = (int)fy, x0 = (int)fx, y1 = y0 + 1, x1 = x0 + 1;
-    const float ly = py - fy, lx = px - fx, hy = 1.f - ly, hx = 1.f - lx;
-    float t[8];
-    if (y0 >= 0 && x0 >= 0) {
-        load8<T>(plane + ((long long)y0 * W + x0) * 8, t);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) v[c] = fmaf(hy * hx, t[c], v[c]);
-    }
-    if (y0 >= 0 && x1 <= W - 1) {
-        load8<T>(plane + ((long long)y0 * W + x1) * 8, t);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) v[c] = fmaf(hy * lx, t[c], v[c]);
-    }
-    if (y1 <= H - 1 && x0 >= 0) {
-        load8<T>(plane + ((long long)y1 * W + x0) * 8, t);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) v[c] = fmaf(ly * hx, t[c], v[c]);
-    }
-    if (y1 <= H - 1 && x1 <= W - 1) {
-        load8<T>(plane + ((long long)y1 * W + x1) * 8, t);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) v[c] = fmaf(ly * lx, t[c], v[c]);
-    }
-}
-
 template <typename T, int K>
 __global__ void __launch_bounds__(NTHREADS) dcn_simt_kernel(const DcnOp op) {
     constexpr int ROWS = K * 8;
@@ -335,9 +301,9 @@ int pack_weight_simt(const float *w_oihw, float *dst, int Cout, int Cin_total, i
 
 // ---------------------------------------------------------------- layout pack / unpack
 template <typename T, typename Tin>
-__global__ void pack_nchw_kernel(const Tin *__restrict__ src, T *__restrict__ dst, int C, int H, int W,
+__global__ void pack_nchw_kernel(const Tin *__restrict__ src, T *__restrict__ dst, int C, int Cdst, int H, int W,
                                  long long total) {
-    const int C8 = (C + 7) / 8;
+    const int C8 = (Cdst + 7) / 8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         const int x = (int)(i % W);
@@ -356,18 +322,19 @@ __global__ void pack_nchw_kernel(const Tin *__restrict__ src, T *__restrict__ ds
     }
 }
 template <typename T, typename Tin>
-int launch_pack_nchw(const Tin *src, T *dst, int N, int C, int H, int W, cudaStream_t s) {
-    const long long total = (long long)N * ((C + 7) / 8) * H * W;
+int launch_pack_nchw(const Tin *src, T *dst, int N, int C, int H, int W, cudaStream_t s, int Cdst) {
+    if (Cdst < C) Cdst = C;
+    const long long total = (long long)N * ((Cdst + 7) / 8) * H * W;
     if (total == 0) return RVSR_OK;
     pack_nchw_kernel<T, Tin><<<(int)((total + 255) / 256 < 8192 ? (total + 255) / 256 : 8192), 256, 0, s>>>(
-        src, dst, C, H, W, total);
+        src, dst, C, Cdst, H, W, total);
     RVSR_LAUNCH_CHECK();
     return RVSR_OK;
 }
-template int launch_pack_nchw<float, float>(const float *, float *, int, int, int, int, cudaStream_t);
-template int launch_pack_nchw<__half, float>(const float *, __half *, int, int, int, int, cudaStream_t);
-template int launch_pack_nchw<float, __half>(const __half *, float *, int, int, int, int, cudaStream_t);
-template int launch_pack_nchw<__half, __half>(const __half *, __half *, int, int, int, int, cudaStream_t);
+template int launch_pack_nchw<float, float>(const float *, float *, int, int, int, int, cudaStream_t, int);
+template int launch_pack_nchw<__half, float>(const float *, __half *, int, int, int, int, cudaStream_t, int);
+template int launch_pack_nchw<float, __half>(const __half *, float *, int, int, int, int, cudaStream_t, int);
+template int launch_pack_nchw<__half, __half>(const __half *, __half *, int, int, int, int, cudaStream_t, int);
 
 template <typename T, typename Tout>
 __global__ void unpack_nchw_kernel(const T *__restrict__ src, Tout *__restrict__ dst, int C, int H, int W,
@@ -395,6 +362,7 @@ int launch_unpack_nchw(const T *src, Tout *dst, int N, int C, int H, int W, cuda
 }
 template int launch_unpack_nchw<float, float>(const float *, float *, int, int, int, int, cudaStream_t);
 template int launch_unpack_nchw<__half, float>(const __half *, float *, int, int, int, int, cudaStream_t);
+template int launch_unpack_nchw<__half, __half>(const __half *, __half *, int, int, int, int, cudaStream_t);
 
 __global__ void convert_f16_f32_kernel(const __half *__restrict__ src, float *__restrict__ dst, long long n) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
@@ -636,6 +604,24 @@ INST_FINAL(__half, __half, float)
 INST_FINAL(__half, float, __half)
 INST_FINAL(__half, __half, __half)
 
+}  // namespace rvsr
+
+// zero-pad the input-channel dimension of an OIHW weight (conv_first: 3 -> 16 for the tensor-core path)
+namespace rvsr {
+__global__ void pad_cin_kernel(const float *__restrict__ w, float *__restrict__ dst, int Cin, int Cpad, int KK, long long total) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i % KK);
+        const int c = (int)((i / KK) % Cpad);
+        const long long co = i / ((long long)KK * Cpad);
+        dst[i] = c < Cin ? w[(co * Cin + c) * KK + t] : 0.f;
+    }
+}
+int pad_weight_cin(const float *w, float *dst, int Cout, int Cin, int Cpad, int KK, cudaStream_t s) {
+    const long long total = (long long)Cout * Cpad * KK;
+    pad_cin_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(w, dst, Cin, Cpad, KK, total);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
 }  // namespace rvsr
 
 // ---------------------------------------------------------------- grouped -> dense weight (operator-level API only)

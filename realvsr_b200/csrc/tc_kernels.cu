@@ -1,12 +1,680 @@
-// tc_kernels.cu -- tcgen05 / TMA kernels (placeholder until the SIMT path is validated).
+// tc_kernels.cu -- tcgen05 / TMEM / TMA kernels of the rvsr_b200 hot path (sm_100a only).
+//
+//   conv_tc_kernel<KS, NT>   3x3 / 1x1 convolution as an im2col-free implicit GEMM:
+//       * one TMA load per (tile, source) brings a (4+KS-1) x 32-pixel halo of every 8-channel
+//         block into shared memory, ONCE; the nine taps are nine shifted *views* of that tile,
+//         expressed purely through the UMMA shared-memory descriptor start address;
+//       * tcgen05.mma (M=128 pixels, N=NT output channels, K=16 channels) accumulates all taps
+//         and all sources (fused torch.cat) into a TMEM accumulator, double buffered;
+//       * four epilogue warps drain TMEM (tcgen05.ld), add bias, activation, residual, and
+//         store 128-bit channel blocks (optionally pixel-shuffled, subsampled for stride 2,
+//         or as planar fp32 + sigmoid for the DCN offset/mask prediction).
+//   dcn_tc_kernel            modulated deformable 3x3 conv: gather warps sample the input
+//       bilinearly (fp32 coordinates and blend), scale by the mask, and write fp16 A-operand
+//       tiles straight into the UMMA core-matrix layout in shared memory -- the reference's
+//       9x-inflated `columns` buffer never exists; tcgen05.mma contracts each tap as soon as
+//       it is gathered.
+//
+// Shared-memory operand layout (both kernels): K-major, SWIZZLE_NONE "core matrices" of
+// 8 rows x 16 bytes (8 fp16 channels).  Activations are stored channel-blocked
+// [N][C/8][H][W][8], so a pixel of a channel block IS one core-matrix row: rows (pixels) are
+// 16 B apart, 8-row groups 128 B apart (SBO), channel blocks one plane apart (LBO).  A tap
+// (dy, dx) is the same tile with the start address advanced by (dy*32 + dx) * 16 bytes.
+//
+// Reference semantics: nn.Conv2d sites of EDVR_arch.py (:71-91, :146-164, :229-253) and the
+// DCN of dcn/src/deform_conv_cuda_kernel.cu:467-497, :571-633 + deform_conv_cuda.cpp:539-568.
+#include <cuda.h>
+
 #include "engine.cuh"
+
 namespace rvsr {
-bool tc_conv_supported(const ConvOp &) { return false; }
-int launch_conv_tc(const ConvOp &, cudaStream_t) { set_error("tc conv not built"); return RVSR_E_UNSUPPORTED; }
-size_t tc_conv_weight_bytes(int, int, int) { return 0; }
-int pack_weight_tc(const float *, void *, int, int, int, int, cudaStream_t) { return RVSR_OK; }
-bool tc_dcn_supported(const DcnOp &) { return false; }
-int launch_dcn_tc(const DcnOp &, cudaStream_t) { set_error("tc dcn not built"); return RVSR_E_UNSUPPORTED; }
-size_t tc_dcn_weight_bytes(int, int, int) { return 0; }
-int pack_weight_dcn_tc(const float *, void *, int, int, int, cudaStream_t) { return RVSR_OK; }
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug traps (reported as a launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tmap, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]; fp16 inputs, fp32 accumulate.  One thread issues.
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start>>4   [16,30) LBO>>4 (K-direction core-matrix stride)   [32,46) SBO>>4 (8-row group stride)
+//   [46,48) version=1 [61,64) layout type = 0
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// Instruction descriptor for kind::f16: fp16 A/B (K-major both), fp32 D, M=128, N.
+__host__ __device__ constexpr uint32_t make_idesc(int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24); }
+
+// ---------------------------------------------------------------- shared epilogue
+struct EpiArgs {
+    const float *bias_s;  // smem, NT floats for this pass (0 beyond Cout)
+    void *out;
+    long long out_image_stride;
+    const __half *residual;
+    long long res_image_stride;
+    int H, W, Cout, act, out_mode, sig_from, subsample;
+};
+
+// 16 consecutive accumulator columns [col0, col0+16) of one pixel (n, y, x) of N-pass `pss`.
+template <int NT>
+__device__ __forceinline__ void epilogue16(const EpiArgs &e, float (&v)[16], int col0, int pss, int n, int y, int x) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i] + e.bias_s[col0 + i], e.act);
+    if (e.out_mode == OUT_C8) {
+        int Ho = e.H, Wo = e.W;
+        if (e.subsample) {
+            if ((y | x) & 1) return;
+            y >>= 1; x >>= 1; Ho = (e.H - 1) / 2 + 1; Wo = (e.W - 1) / 2 + 1;
+        }
+        const int Co8 = (e.Cout + 7) / 8;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int q = (pss * NT + col0) / 8 + j;
+            if (q >= Co8) continue;
+            const long long off = ((((long long)q) * Ho + y) * Wo + x) * 8;
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = v[j * 8 + i];
+            if (e.residual != nullptr) {
+                float r[8];
+                load8<__half>(e.residual + (long long)n * e.res_image_stride + off, r);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] += r[i];
+            }
+            store8<__half>(reinterpret_cast<__half *>(e.out) + (long long)n * e.out_image_stride + off, o);
+        }
+    } else if (e.out_mode == OUT_C8_SHUFFLE2) {
+        // columns were permuted at pack time: col = ij * (NT/4) + c_local, channel c = pss*(NT/4) + c_local,
+        // out[n, c, 2y + (ij>>1), 2x + (ij&1)]   (nn.PixelShuffle(2): in-channel 4c + ij)
+        constexpr int CP = NT / 4;
+        const int ij = col0 / CP, c0 = pss * CP + col0 % CP;
+        const int C2 = e.Cout / 4, yy = 2 * y + (ij >> 1), xx = 2 * x + (ij & 1);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int q = c0 / 8 + j;
+            if (q * 8 >= C2) continue;
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = v[j * 8 + i];
+            store8<__half>(reinterpret_cast<__half *>(e.out) + (long long)n * e.out_image_stride +
+                               ((((long long)q) * (2 * e.H) + yy) * (2 * e.W) + xx) * 8, o);
+        }
+    } else {  // OUT_PLANAR_F32
+        float *o = reinterpret_cast<float *>(e.out) + (long long)n * e.out_image_stride;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int co = pss * NT + col0 + i;
+            if (co < e.Cout) o[((long long)co * e.H + y) * e.W + x] = co >= e.sig_from ? sigmoidf_(v[i]) : v[i];
+        }
+    }
+}
+
+// ---------------------------------------------------------------- convolution
+struct alignas(64) TcConvParams {
+    CUtensorMap tmap[RVSR_MAX_SRC];
+    int src_pstride[RVSR_MAX_SRC];  // channel-block planes between consecutive images of a source
+    int src_frames[RVSR_MAX_SRC], src_fixed[RVSR_MAX_SRC];
+    int nsrc, C8s, nstages;
+    const __half *w;  // [pass][tap][Q][NT][8]
+    const float *bias;
+    void *out;
+    long long out_image_stride;
+    const __half *residual;
+    long long res_image_stride;
+    int N, H, W, Cout, act, out_mode, sig_from, subsample;
+    int tiles_x, tiles_y, num_tiles;
+};
+
+constexpr int TC_ROWS = 4, TC_TW = 32;
+constexpr int TC_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+__host__ __device__ constexpr int acc_stride(int NT) { return NT <= 32 ? 32 : (NT <= 64 ? 64 : 128); }
+
+template <int KS, int NT>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcConvParams p) {
+    constexpr int KK = KS * KS, PAD = KS / 2, VALID = TC_TW - (KS - 1), HALO_ROWS = TC_ROWS + KS - 1;
+    constexpr int PLANE_BYTES = HALO_ROWS * TC_TW * 16;
+    constexpr int ACC = acc_stride(NT), TMEM_COLS = 2 * ACC;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int Q = p.nsrc * p.C8s;  // channel blocks over all sources
+    const uint32_t w_bytes = (uint32_t)Q * KK * NT * 16;
+    const uint32_t stage_bytes = (uint32_t)p.C8s * PLANE_BYTES;
+    uint8_t *w_s = smem;
+    uint8_t *stage_s = smem + w_bytes;
+    float *bias_s = reinterpret_cast<float *>(stage_s + (size_t)p.nstages * stage_bytes + 128);  // +128: tap overrun slack
+    uint64_t *bars = reinterpret_cast<uint64_t *>(bias_s + NT);
+    // bars: [0,S) full, [S,2S) empty, 2S wfull, 2S+1..2 tfull, 2S+3..4 tempty, then the TMEM base address
+    const int S = p.nstages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * S + 5);
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pss = blockIdx.y;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2 * S + 3; ++i) mbar_init(BAR(i), 1);
+        mbar_init(BAR(2 * S + 3), 4);
+        mbar_init(BAR(2 * S + 4), 4);
+        fence_barrier_init();
+    }
+    for (int i = threadIdx.x; i < NT; i += TC_THREADS) {
+        const int co = pss * NT + i;
+        float b = 0.f;
+        if (p.bias != nullptr) {
+            if (p.out_mode == OUT_C8_SHUFFLE2) {
+                const int c = pss * (NT / 4) + i % (NT / 4), ij = i / (NT / 4);
+                b = (4 * c + ij) < p.Cout ? p.bias[4 * c + ij] : 0.f;
+            } else if (co < p.Cout) {
+                b = p.bias[co];
+            }
+        }
+        bias_s[i] = b;
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---- weights for this N-pass: resident for the CTA's lifetime
+            mbar_expect_tx(BAR(2 * S), w_bytes);
+            const uint8_t *wg = reinterpret_cast<const uint8_t *>(p.w) + (size_t)pss * w_bytes;
+            for (uint32_t o = 0; o < w_bytes; o += 32768) {
+                const uint32_t n = w_bytes - o < 32768 ? w_bytes - o : 32768;
+                bulk_load(smem_u32(w_s + o), wg + o, n, BAR(2 * S));
+            }
+            // ---- halo tiles
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, n = tile / (p.tiles_x * p.tiles_y);
+                for (int s = 0; s < p.nsrc; ++s, ++it) {
+                    const int st = it % S;
+                    mbar_wait(BAR(S + st), ((it / S) & 1) ^ 1);
+                    mbar_expect_tx(BAR(st), stage_bytes);
+                    const int img = p.src_fixed[s] >= 0 ? (n / p.src_frames[s]) * p.src_frames[s] + p.src_fixed[s] : n;
+                    tma_load_3d(smem_u32(stage_s + (size_t)st * stage_bytes), &p.tmap[s], BAR(st),
+                                (tx * VALID - PAD) * 8, ty * TC_ROWS - PAD, img * p.src_pstride[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(NT);
+            mbar_wait(BAR(2 * S), 0);
+            uint32_t it = 0, t = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++t) {
+                const uint32_t buf = t & 1;
+                mbar_wait(BAR(2 * S + 3 + buf), ((t >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d = tmem_base + buf * ACC;
+                uint32_t acc = 0;
+                for (int s = 0; s < p.nsrc; ++s, ++it) {
+                    const int st = it % S;
+                    mbar_wait(BAR(st), (it / S) & 1);
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(stage_s + (size_t)st * stage_bytes);
+                    const uint32_t b0 = smem_u32(w_s) + (uint32_t)(s * p.C8s) * (NT * 16);
+#pragma unroll 1
+                    for (int tap = 0; tap < KK; ++tap) {
+                        const uint32_t a_tap = a0 + (uint32_t)((tap / KS) * TC_TW + (tap % KS)) * 16;
+                        const uint32_t b_tap = b0 + (uint32_t)(tap * Q) * (NT * 16);
+                        for (int kk = 0; kk < p.C8s / 2; ++kk) {
+                            umma_f16(d, make_desc(a_tap + (uint32_t)(2 * kk) * PLANE_BYTES, PLANE_BYTES, 128),
+                                     make_desc(b_tap + (uint32_t)(2 * kk) * (NT * 16), NT * 16, 128), idesc, acc);
+                            acc = 1;
+                        }
+                    }
+                    umma_commit(BAR(S + st));  // stage reusable once these MMAs have read it
+                }
+                umma_commit(BAR(2 * S + 1 + buf));  // accumulator complete
+            }
+        }
+    } else {
+        const int lq = warp & 3;  // TMEM lane quarter this warp may access == tile row
+        EpiArgs e{bias_s, p.out, p.out_image_stride, p.residual, p.res_image_stride, p.H, p.W, p.Cout, p.act,
+                  p.out_mode, p.sig_from, p.subsample};
+        uint32_t t = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++t) {
+            const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, n = tile / (p.tiles_x * p.tiles_y);
+            const uint32_t buf = t & 1;
+            mbar_wait(BAR(2 * S + 1 + buf), (t >> 1) & 1);
+            tc_fence_after();
+            const int y = ty * TC_ROWS + lq, x = tx * VALID + lane;
+            const bool valid = lane < VALID && y < p.H && x < p.W;
+            const uint32_t taddr = tmem_base + buf * ACC + ((uint32_t)(lq * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < NT; c0 += 16) {
+                float v[16];
+                tmem_ld16(taddr + c0, v);
+                if (valid) epilogue16<NT>(e, v, c0, pss, n, y, x);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(2 * S + 3 + buf));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------- host side: tensor maps, packing, launch
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+static int tc_pick_nt(int Cout) {
+    if (Cout <= 16) return 16;
+    if (Cout <= 64) return 64;
+    if (Cout == 216) return 112;  // DCN offset/mask prediction with 8 deformable groups: 2 passes of 112
+    if (Cout % 128 == 0) return 128;
+    if (Cout % 64 == 0) return 64;
+    return 0;
+}
+static int tc_passes(int Cout, int NT) { return (Cout + NT - 1) / NT; }
+static int pad16(int c) { return (c + 15) / 16 * 16; }
+
+size_t tc_conv_weight_bytes(int Cout, int Cin, int ks) {
+    const int NT = tc_pick_nt(Cout);
+    if (NT == 0 || (ks != 1 && ks != 3)) return 0;
+    return (size_t)tc_passes(Cout, NT) * ks * ks * (pad16(Cin) / 8) * NT * 16;
+}
+size_t tc_dcn_weight_bytes(int Cout, int C, int K) { return (Cout == 64 && C == 64 && K == 9) ? tc_conv_weight_bytes(64, 64, 3) : 0; }
+
+__global__ void pack_weight_tc_kernel(const float *__restrict__ w, __half *__restrict__ dst, int Cout, int Cin, int KK,
+                                      int Q, int NT, int shuffle, long long total) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int e = (int)(i % 8);
+        long long r = i / 8;
+        const int n = (int)(r % NT);
+        r /= NT;
+        const int q = (int)(r % Q);
+        r /= Q;
+        const int tap = (int)(r % KK);
+        const int pss = (int)(r / KK);
+        const int cin = q * 8 + e;
+        const int co = shuffle ? 4 * (pss * (NT / 4) + n % (NT / 4)) + n / (NT / 4) : pss * NT + n;
+        dst[i] = __float2half_rn((co < Cout && cin < Cin) ? w[((long long)co * Cin + cin) * KK + tap] : 0.f);
+    }
+}
+int pack_weight_tc(const float *w_oihw, void *dst, int Cout, int Cin, int ks, int shuffle, cudaStream_t s) {
+    const int NT = tc_pick_nt(Cout);
+    RVSR_CHECK_ARG(NT != 0, "tc pack: unsupported Cout %d", Cout);
+    const int Q = pad16(Cin) / 8;
+    const long long total = (long long)tc_passes(Cout, NT) * ks * ks * Q * NT * 8;
+    pack_weight_tc_kernel<<<(int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096), 256, 0, s>>>(
+        w_oihw, reinterpret_cast<__half *>(dst), Cout, Cin, ks * ks, Q, NT, shuffle, total);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+int pack_weight_dcn_tc(const float *w_oihw, void *dst, int Cout, int C, int K, cudaStream_t s) {
+    RVSR_CHECK_ARG(K == 9, "tc dcn pack: 3x3 only");
+    return pack_weight_tc(w_oihw, dst, Cout, C, 3, 0, s);
+}
+
+static constexpr size_t TC_SMEM_LIMIT = 232448 - 1024;  // 227 KB opt-in maximum minus alignment slack
+
+struct TcConvPlan {
+    int NT, passes, KS, C8s, nstages;
+    size_t smem;
+};
+static bool tc_conv_plan(const ConvOp &op, TcConvPlan &pl) {
+    if (op.w_tc == nullptr || (op.ks != 1 && op.ks != 3) || op.nsrc < 1) return false;
+    if (!(op.stride == 1 || (op.stride == 2 && op.ks == 3 && op.out_mode == OUT_C8 && op.H % 2 == 0 && op.W % 2 == 0)))
+        return false;
+    if (op.out_mode != OUT_C8 && op.out_mode != OUT_C8_SHUFFLE2 && op.out_mode != OUT_PLANAR_F32) return false;
+    if (op.residual != nullptr && op.out_mode != OUT_C8) return false;
+    const int C = op.src[0].C;
+    for (int i = 0; i < op.nsrc; ++i)
+        if (op.src[i].C != C) return false;
+    if (C % 16 != 0 || C > 64) return false;
+    pl.NT = tc_pick_nt(op.Cout);
+    if (pl.NT == 0) return false;
+    if (op.out_mode == OUT_C8_SHUFFLE2 && (pl.NT % 64 != 0 || op.Cout % pl.NT != 0)) return false;
+    pl.passes = tc_passes(op.Cout, pl.NT);
+    pl.KS = op.ks;
+    pl.C8s = C / 8;
+    const size_t wb = (size_t)op.nsrc * pl.C8s * op.ks * op.ks * pl.NT * 16;
+    const size_t stage = (size_t)pl.C8s * (TC_ROWS + op.ks - 1) * TC_TW * 16;
+    const size_t fixed = wb + 128 + pl.NT * 4 + 256;
+    if (fixed + 2 * stage > TC_SMEM_LIMIT) return false;
+    pl.nstages = (int)((TC_SMEM_LIMIT - fixed) / stage);
+    if (pl.nstages > 6) pl.nstages = 6;
+    pl.smem = fixed + pl.nstages * stage + 1024;
+    return true;
+}
+bool tc_conv_supported(const ConvOp &op) {
+    TcConvPlan pl;
+    return tc_conv_plan(op, pl) && get_encode() != nullptr;
+}
+
+template <int KS, int NT> static int launch_conv_tc_t(const TcConvParams &p, const TcConvPlan &pl, int sms, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        RVSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT + 1024));
+        attr_set = true;
+    }
+    int gx = sms / pl.passes;
+    if (gx < 1) gx = 1;
+    if (gx > p.num_tiles) gx = p.num_tiles;
+    conv_tc_kernel<KS, NT><<<dim3(gx, pl.passes), TC_THREADS, pl.smem, s>>>(p);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+int launch_conv_tc(const ConvOp &op, cudaStream_t s) {
+    TcConvPlan pl;
+    RVSR_CHECK_ARG(tc_conv_plan(op, pl), "tc conv: unsupported configuration");
+    EncodeTiledFn enc = get_encode();
+    RVSR_CHECK_ARG(enc != nullptr, "tc conv: cuTensorMapEncodeTiled unavailable");
+    TcConvParams p;
+    memset(&p, 0, sizeof(p));
+    const int halo_rows = TC_ROWS + op.ks - 1;
+    const long long plane = (long long)op.H * op.W * 8;
+    for (int i = 0; i < op.nsrc; ++i) {
+        const Src &sr = op.src[i];
+        RVSR_CHECK_ARG(sr.image_stride % plane == 0, "tc conv: image stride is not a whole number of planes");
+        p.src_pstride[i] = (int)(sr.image_stride / plane);
+        p.src_frames[i] = sr.frames > 0 ? sr.frames : 1;
+        p.src_fixed[i] = sr.fixed_frame;
+        const cuuint64_t dims[3] = {(cuuint64_t)op.W * 8, (cuuint64_t)op.H,
+                                    (cuuint64_t)(op.N - 1) * p.src_pstride[i] + pl.C8s};
+        const cuuint64_t strides[2] = {(cuuint64_t)op.W * 16, (cuuint64_t)op.H * op.W * 16};
+        const cuuint32_t box[3] = {(cuuint32_t)TC_TW * 8, (cuuint32_t)halo_rows, (cuuint32_t)pl.C8s};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&p.tmap[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(sr.ptr), dims, strides, box,
+                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("tc conv: cuTensorMapEncodeTiled failed (%d) W=%d H=%d planes=%llu", (int)r, op.W, op.H,
+                      (unsigned long long)dims[2]);
+            return RVSR_E_CUDA;
+        }
+    }
+    p.nsrc = op.nsrc; p.C8s = pl.C8s; p.nstages = pl.nstages;
+    p.w = reinterpret_cast<const __half *>(op.w_tc); p.bias = op.bias;
+    p.out = op.out; p.out_image_stride = op.out_image_stride;
+    p.residual = reinterpret_cast<const __half *>(op.residual); p.res_image_stride = op.res_image_stride;
+    p.N = op.N; p.H = op.H; p.W = op.W; p.Cout = op.Cout; p.act = op.act; p.out_mode = op.out_mode;
+    p.sig_from = op.sig_from; p.subsample = op.stride == 2 ? 1 : 0;
+    const int valid = TC_TW - (op.ks - 1);
+    p.tiles_x = cdiv(op.W, valid); p.tiles_y = cdiv(op.H, TC_ROWS);
+    p.num_tiles = p.tiles_x * p.tiles_y * op.N;
+    if (p.num_tiles == 0) return RVSR_OK;
+    const int sms = sm_count();
+#define RVSR_TC_CASE(KS_, NT_) \
+    if (op.ks == KS_ && pl.NT == NT_) return launch_conv_tc_t<KS_, NT_>(p, pl, sms, s);
+    RVSR_TC_CASE(3, 16) RVSR_TC_CASE(3, 64) RVSR_TC_CASE(3, 112) RVSR_TC_CASE(3, 128)
+    RVSR_TC_CASE(1, 16) RVSR_TC_CASE(1, 64) RVSR_TC_CASE(1, 128)
+#undef RVSR_TC_CASE
+    set_error("tc conv: no kernel instance for ks=%d NT=%d", op.ks, pl.NT);
+    return RVSR_E_UNSUPPORTED;
+}
+
+// ---------------------------------------------------------------- modulated deformable conv (gather -> UMMA)
+struct TcDcnParams {
+    const __half *x;
+    long long x_image_stride;
+    const float *offset, *mask;
+    long long off_stride, mask_stride;
+    const __half *w;
+    const float *bias;
+    __half *out;
+    long long out_image_stride;
+    int N, H, W, cpg, act;
+    int tiles_x, tiles_y, num_tiles;
+};
+constexpr int DCN_GATHER_WARPS = 8, DCN_THREADS = 32 * (1 + DCN_GATHER_WARPS + 4), DCN_STAGES = 4;
+constexpr int DCN_TAP_BYTES = 8 * 128 * 16;  // 8 channel blocks x 128 pixels x 16 B
+
+__global__ void __launch_bounds__(DCN_THREADS, 1) dcn_tc_kernel(const __grid_constant__ TcDcnParams p) {
+    constexpr int NT = 64, K = 9, Q = 8, ACC = 64, TMEM_COLS = 128;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr uint32_t w_bytes = Q * K * NT * 16;
+    uint8_t *w_s = smem;
+    uint8_t *tap_s = smem + w_bytes;
+    float *bias_s = reinterpret_cast<float *>(tap_s + DCN_STAGES * DCN_TAP_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(bias_s + NT);
+    constexpr int S = DCN_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * S + 5);
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < S; ++i) mbar_init(BAR(i), DCN_GATHER_WARPS);  // full: one arrive per gather warp
+        for (int i = S; i < 2 * S + 3; ++i) mbar_init(BAR(i), 1);
+        mbar_init(BAR(2 * S + 3), 4);
+        mbar_init(BAR(2 * S + 4), 4);
+        fence_barrier_init();
+    }
+    for (int i = threadIdx.x; i < NT; i += DCN_THREADS) bias_s[i] = p.bias != nullptr ? p.bias[i] : 0.f;
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(BAR(2 * S), w_bytes);
+            for (uint32_t o = 0; o < w_bytes; o += 24576)
+                bulk_load(smem_u32(w_s + o), reinterpret_cast<const uint8_t *>(p.w) + o, 24576, BAR(2 * S));
+            constexpr uint32_t idesc = make_idesc(NT);
+            mbar_wait(BAR(2 * S), 0);
+            uint32_t it = 0, t = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++t) {
+                const uint32_t buf = t & 1;
+                mbar_wait(BAR(2 * S + 3 + buf), ((t >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + buf * ACC;
+                for (int tap = 0; tap < K; ++tap, ++it) {
+                    const int st = it % S;
+                    mbar_wait(BAR(st), (it / S) & 1);
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(tap_s + st * DCN_TAP_BYTES);
+                    const uint32_t b0 = smem_u32(w_s) + (uint32_t)(tap * Q) * (NT * 16);
+#pragma unroll
+                    for (int kk = 0; kk < Q / 2; ++kk)
+                        umma_f16(d, make_desc(a0 + (uint32_t)(2 * kk) * 2048, 2048, 128),
+                                 make_desc(b0 + (uint32_t)(2 * kk) * (NT * 16), NT * 16, 128), idesc, (tap | kk) ? 1u : 0u);
+                    umma_commit(BAR(S + st));
+                }
+                umma_commit(BAR(2 * S + 1 + buf));
+            }
+        }
+    } else if (warp <= DCN_GATHER_WARPS) {
+        // ---- gather: thread -> pixel m of the tile and 4 of the 8 channel blocks
+        const int gt = threadIdx.x - 32;
+        const int m = gt & 127, qh = gt >> 7;
+        const long long plane = (long long)p.H * p.W;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, n = tile / (p.tiles_x * p.tiles_y);
+            const int y = ty * TC_ROWS + (m >> 5), x = tx * TC_TW + (m & 31);
+            const bool valid = y < p.H && x < p.W;
+            const long long pix = (long long)y * p.W + x;
+            const float *off = p.offset + (long long)n * p.off_stride + pix;
+            const float *msk = p.mask + (long long)n * p.mask_stride + pix;
+            const __half *xb = p.x + (long long)n * p.x_image_stride;
+            for (int tap = 0; tap < K; ++tap, ++it) {
+                const int st = it % S;
+                mbar_wait(BAR(S + st), ((it / S) & 1) ^ 1);
+                uint8_t *dst = tap_s + st * DCN_TAP_BYTES + m * 16;
+                const float by = (float)(y - 1 + tap / 3), bx = (float)(x - 1 + tap % 3);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int q = qh + 2 * i;
+                    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    if (valid) {
+                        const int g = (q * 8) / p.cpg;
+                        const float dy = __ldg(off + ((long long)g * 18 + 2 * tap) * plane);
+                        const float dx = __ldg(off + ((long long)g * 18 + 2 * tap + 1) * plane);
+                        const float mk = __ldg(msk + ((long long)g * 9 + tap) * plane);
+                        sample8<__half>(xb + (long long)q * plane * 8, p.H, p.W, by + dy, bx + dx, v);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) v[c] *= mk;
+                    }
+                    uint4 pk;
+                    __half2 *h = reinterpret_cast<__half2 *>(&pk);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) h[c] = __floats2half2_rn(v[2 * c], v[2 * c + 1]);
+                    *reinterpret_cast<uint4 *>(dst + q * 2048) = pk;
+                }
+                fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(st));
+            }
+        }
+    } else {
+        const int lq = warp & 3;
+        EpiArgs e{bias_s, p.out, p.out_image_stride, nullptr, 0, p.H, p.W, NT, p.act, OUT_C8, 0, 0};
+        uint32_t t = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++t) {
+            const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, n = tile / (p.tiles_x * p.tiles_y);
+            const uint32_t buf = t & 1;
+            mbar_wait(BAR(2 * S + 1 + buf), (t >> 1) & 1);
+            tc_fence_after();
+            const int y = ty * TC_ROWS + lq, x = tx * TC_TW + lane;
+            const bool valid = y < p.H && x < p.W;
+            const uint32_t taddr = tmem_base + buf * ACC + ((uint32_t)(lq * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < NT; c0 += 16) {
+                float v[16];
+                tmem_ld16(taddr + c0, v);
+                if (valid) epilogue16<NT>(e, v, c0, 0, n, y, x);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(2 * S + 3 + buf));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+bool tc_dcn_supported(const DcnOp &op) {
+    if (op.w_tc == nullptr || op.x.C != 64 || op.Cout != 64 || op.kh != 3 || op.kw != 3) return false;
+    if (op.stride != 1 || op.pad != 1 || op.dil != 1 || op.out_mode != OUT_C8) return false;
+    const int cpg = op.x.C / op.dg;
+    if (cpg * op.dg != 64 || cpg % 8 != 0) return false;
+    if (op.x.fixed_frame >= 0) return false;
+    return true;
+}
+
+int launch_dcn_tc(const DcnOp &op, cudaStream_t s) {
+    RVSR_CHECK_ARG(tc_dcn_supported(op), "tc dcn: unsupported configuration");
+    TcDcnParams p;
+    p.x = reinterpret_cast<const __half *>(op.x.ptr); p.x_image_stride = op.x.image_stride;
+    p.offset = op.offset; p.mask = op.mask; p.off_stride = op.offset_image_stride; p.mask_stride = op.mask_image_stride;
+    p.w = reinterpret_cast<const __half *>(op.w_tc); p.bias = op.bias;
+    p.out = reinterpret_cast<__half *>(op.out); p.out_image_stride = op.out_image_stride;
+    p.N = op.N; p.H = op.H; p.W = op.W; p.cpg = op.x.C / op.dg; p.act = op.act;
+    p.tiles_x = cdiv(op.W, TC_TW); p.tiles_y = cdiv(op.H, TC_ROWS); p.num_tiles = p.tiles_x * p.tiles_y * op.N;
+    if (p.num_tiles == 0) return RVSR_OK;
+    const size_t smem = 8 * 9 * 64 * 16 + DCN_STAGES * DCN_TAP_BYTES + 64 * 4 + 256 + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        RVSR_CUDA(cudaFuncSetAttribute(dcn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    int gx = sm_count();
+    if (gx > p.num_tiles) gx = p.num_tiles;
+    dcn_tc_kernel<<<gx, DCN_THREADS, smem, s>>>(p);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+
 }  // namespace rvsr

@@ -1,0 +1,47 @@
+"""Functional wrappers over the operator-level C ABI (include/rvsr_b200.h).
+
+``conv2d_fused`` is one nn.Conv2d site of the reference's EDVR_arch.py together with what
+surrounds it there: the torch.cat in front, bias, activation, residual add and pixel shuffle.
+NCHW CUDA tensors in and out; all compute is the library's own kernels.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+ACT = {None: _lib.ACT_NONE, "none": _lib.ACT_NONE, "lrelu": _lib.ACT_LRELU, "relu": _lib.ACT_RELU}
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def conv2d_fused(x, weight, bias=None, x2=None, residual=None, stride=1, act=None, shuffle=False, use_tc=None):
+    """y = [pixel_shuffle2](act(conv(cat(x, x2), weight, pad=k//2, stride) + bias) + residual)."""
+    if not x.is_cuda:
+        raise NotImplementedError("realvsr_b200.ops.conv2d_fused: CUDA tensors only (no CPU fallback)")
+    if x.dtype not in (torch.float32, torch.float16):
+        raise RuntimeError("conv2d_fused: float32/float16 only")
+    dt = _lib.F16 if x.dtype == torch.float16 else _lib.F32
+    if use_tc is None:
+        use_tc = dt == _lib.F16
+    x = x.contiguous()
+    B, C1, H, W = x.shape
+    C2 = 0 if x2 is None else x2.shape[1]
+    Cout, Cin, ks, _ = weight.shape
+    if Cin != C1 + C2:
+        raise RuntimeError("conv2d_fused: weight expects %d input channels, got %d" % (Cin, C1 + C2))
+    Ho, Wo = (H, W) if stride == 1 else ((H - 1) // 2 + 1, (W - 1) // 2 + 1)
+    y = x.new_empty((B, Cout // 4, 2 * Ho, 2 * Wo) if shuffle else (B, Cout, Ho, Wo))
+    L = _lib.lib()
+    cast = lambda t: None if t is None else t.to(x.dtype).contiguous()  # noqa: E731
+    w, b, x2, residual = cast(weight), cast(bias), cast(x2), cast(residual)
+    with torch.cuda.device(x.device):
+        ws = torch.empty(L.rvsr_conv2d_fwd_workspace_bytes(B, C1, C2, H, W, Cout, ks, dt), dtype=torch.uint8,
+                         device=x.device)
+        _lib.check(L.rvsr_conv2d_fwd(_p(x), _p(x2), _p(w), _p(b), _p(residual), _p(y), B, C1, C2, H, W, Cout, ks,
+                                     stride, ACT[act], int(bool(shuffle)), dt, int(bool(use_tc)), _p(ws), ws.numel(),
+                                     ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)),
+                   "conv2d_fused")
+    return y
