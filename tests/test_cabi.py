@@ -69,6 +69,14 @@ def test_dcn_argument_validation_without_gpu():
     assert L.rvsr_mdcn_fwd(None, None, None, None, None, None, 0, 16, 8, 8, 8, 3, 3, 1, 1, 1, 1, 4, 0, None, 0, None) == 0
 
 
+def test_conv_argument_validation_without_gpu():
+    L = _lib.lib()
+    args = lambda B, ks: (None, None, None, None, None, None, B, 64, 0, 8, 8, 64, ks, 1, 0, 0, 1, 1, None, 0, None)  # noqa: E731
+    assert L.rvsr_conv2d_fwd(*args(0, 3)) == 0            # empty batch: no-op
+    assert L.rvsr_conv2d_fwd(*args(1, 5)) == _lib.E_INVALID  # 5x5 kernels are not built
+    assert L.rvsr_conv2d_fwd_workspace_bytes(1, 64, 64, 16, 16, 64, 3, 1) > 0
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "_lib", None)
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
