@@ -145,7 +145,7 @@ int Engine::finalize(cudaStream_t s) {
         pc.ks = (int)w.shape[2];
         pc.bias = raw_[base + ".bias"].dev;
         const float *wsrc = w.dev;
-        if (cfg_.precision == RVSR_F16 && pc.Cin < 16) {
+        if (cfg_.precision == RVSR_F16 && base == "conv_first" && pc.Cin < 16) {
             // tensor-core K granularity is 16 channels: the LQ frames are stored zero-padded to 16
             // channels and conv_first's weight gets matching zero input channels
             float *padded = nullptr;

@@ -123,59 +123,105 @@ struct EpiArgs {
     int H, W, Cout, act, out_mode, sig_from, subsample;
 };
 
-// 16 consecutive accumulator columns [col0, col0+16) of one pixel (n, y, x) of N-pass `pss`.
-template <int NT>
-__device__ __forceinline__ void epilogue16(const EpiArgs &e, float (&v)[16], int col0, int pss, int n, int y, int x) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i] + e.bias_s[col0 + i], e.act);
-    if (e.out_mode == OUT_C8) {
-        int Ho = e.H, Wo = e.W;
-        if (e.subsample) {
-            if ((y | x) & 1) return;
-            y >>= 1; x >>= 1; Ho = (e.H - 1) / 2 + 1; Wo = (e.W - 1) / 2 + 1;
-        }
+// Epilogue of one pixel (TMEM lane) of one tile: the accumulator's NT columns are split in
+// 16-column groups; with NH = 2 two warps share a TMEM lane quarter and take alternate groups.
+// Residual blocks are fetched BEFORE waiting for the accumulator so their latency overlaps the MMAs.
+template <int NT, int NH> struct EpiTile {
+    static constexpr int NG = NT / 16;                 // 16-column groups in the accumulator
+    static constexpr int MY = (NG + NH - 1) / NH;      // groups per warp (upper bound)
+    uint4 res[MY * 2];
+    bool has_res;
+
+    __device__ __forceinline__ void prefetch(const EpiArgs &e, int half, int pss, int n, int y, int x, bool valid) {
+        has_res = false;
+        if (e.out_mode != OUT_C8 || e.residual == nullptr || !valid) return;
+        has_res = true;
         const int Co8 = (e.Cout + 7) / 8;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int q = (pss * NT + col0) / 8 + j;
-            if (q >= Co8) continue;
-            const long long off = ((((long long)q) * Ho + y) * Wo + x) * 8;
-            float o[8];
+        for (int gi = 0; gi < MY; ++gi) {
+            const int c0 = (gi * NH + half) * 16;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = v[j * 8 + i];
-            if (e.residual != nullptr) {
-                float r[8];
-                load8<__half>(e.residual + (long long)n * e.res_image_stride + off, r);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) o[i] += r[i];
+            for (int j = 0; j < 2; ++j) {
+                const int q = (pss * NT + c0) / 8 + j;
+                res[gi * 2 + j] = make_uint4(0, 0, 0, 0);
+                if (c0 < NT && q < Co8)
+                    res[gi * 2 + j] = __ldg(reinterpret_cast<const uint4 *>(
+                        e.residual + (long long)n * e.res_image_stride + ((((long long)q) * e.H + y) * e.W + x) * 8));
             }
-            store8<__half>(reinterpret_cast<__half *>(e.out) + (long long)n * e.out_image_stride + off, o);
-        }
-    } else if (e.out_mode == OUT_C8_SHUFFLE2) {
-        // columns were permuted at pack time: col = ij * (NT/4) + c_local, channel c = pss*(NT/4) + c_local,
-        // out[n, c, 2y + (ij>>1), 2x + (ij&1)]   (nn.PixelShuffle(2): in-channel 4c + ij)
-        constexpr int CP = NT / 4;
-        const int ij = col0 / CP, c0 = pss * CP + col0 % CP;
-        const int C2 = e.Cout / 4, yy = 2 * y + (ij >> 1), xx = 2 * x + (ij & 1);
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int q = c0 / 8 + j;
-            if (q * 8 >= C2) continue;
-            float o[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = v[j * 8 + i];
-            store8<__half>(reinterpret_cast<__half *>(e.out) + (long long)n * e.out_image_stride +
-                               ((((long long)q) * (2 * e.H) + yy) * (2 * e.W) + xx) * 8, o);
-        }
-    } else {  // OUT_PLANAR_F32
-        float *o = reinterpret_cast<float *>(e.out) + (long long)n * e.out_image_stride;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int co = pss * NT + col0 + i;
-            if (co < e.Cout) o[((long long)co * e.H + y) * e.W + x] = co >= e.sig_from ? sigmoidf_(v[i]) : v[i];
         }
     }
-}
+
+    __device__ __forceinline__ void run(const EpiArgs &e, uint32_t taddr, int half, int pss, int n, int y, int x, bool valid) {
+#pragma unroll
+        for (int gi = 0; gi < MY; ++gi) {
+            const int c0 = (gi * NH + half) * 16;
+            if (c0 >= NT) break;  // warp-uniform
+            float v[16];
+            tmem_ld16(taddr + c0, v);
+            if (!valid) continue;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i] + e.bias_s[c0 + i], e.act);
+            if (e.out_mode == OUT_C8) {
+                int yy = y, xx = x, Ho = e.H, Wo = e.W;
+                if (e.subsample) {
+                    if ((y | x) & 1) continue;
+                    yy >>= 1; xx >>= 1; Ho = (e.H - 1) / 2 + 1; Wo = (e.W - 1) / 2 + 1;
+                }
+                const int Co8 = (e.Cout + 7) / 8;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int q = (pss * NT + c0) / 8 + j;
+                    if (q >= Co8) continue;
+                    float o[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o[i] = v[j * 8 + i];
+                    if (has_res) {
+                        const __half2 *h = reinterpret_cast<const __half2 *>(&res[gi * 2 + j]);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float2 f = __half22float2(h[i]);
+                            o[2 * i] += f.x; o[2 * i + 1] += f.y;
+                        }
+                    }
+                    store8<__half>(reinterpret_cast<__half *>(e.out) + (long long)n * e.out_image_stride +
+                                       ((((long long)q) * Ho + yy) * Wo + xx) * 8, o);
+                }
+            } else if (e.out_mode == OUT_C8_SHUFFLE2) {
+                // columns were permuted at pack time: col = ij * (NT/4) + c_local, channel c = pss*(NT/4) + c_local,
+                // out[n, c, 2y + (ij>>1), 2x + (ij&1)]   (nn.PixelShuffle(2): in-channel 4c + ij)
+                constexpr int CP = NT / 4 > 0 ? NT / 4 : 1;
+                const int ij = c0 / CP, cc0 = pss * CP + c0 % CP;
+                const int C2 = e.Cout / 4, yy = 2 * y + (ij >> 1), xx = 2 * x + (ij & 1);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int q = cc0 / 8 + j;
+                    if (q * 8 >= C2) continue;
+                    float o[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o[i] = v[j * 8 + i];
+                    store8<__half>(reinterpret_cast<__half *>(e.out) + (long long)n * e.out_image_stride +
+                                       ((((long long)q) * (2 * e.H) + yy) * (2 * e.W) + xx) * 8, o);
+                }
+            } else {  // OUT_PLANAR_F32: one coalesced 128 B store per channel per warp
+                const int co0 = pss * NT + c0;
+                const long long plane = (long long)e.H * e.W;
+                float *o = reinterpret_cast<float *>(e.out) + (long long)n * e.out_image_stride + (long long)co0 * plane +
+                           (long long)y * e.W + x;
+                if (co0 >= e.sig_from) {  // warp-uniform: whole group is mask channels
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = __fdividef(1.f, 1.f + __expf(-v[i]));
+                } else if (co0 + 16 > e.sig_from) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (co0 + i >= e.sig_from) v[i] = __fdividef(1.f, 1.f + __expf(-v[i]));
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (co0 + i < e.Cout) o[i * plane] = v[i];
+            }
+        }
+    }
+};
 
 // ---------------------------------------------------------------- convolution
 struct alignas(64) TcConvParams {
@@ -194,7 +240,8 @@ struct alignas(64) TcConvParams {
 };
 
 constexpr int TC_ROWS = 4, TC_TW = 32;
-constexpr int TC_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = 32 * (2 + TC_EPI_WARPS);  // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: epilogue
 __host__ __device__ constexpr int acc_stride(int NT) { return NT <= 32 ? 32 : (NT <= 64 ? 64 : 128); }
 
 template <int KS, int NT>
@@ -220,8 +267,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2 * S + 3; ++i) mbar_init(BAR(i), 1);
-        mbar_init(BAR(2 * S + 3), 4);
-        mbar_init(BAR(2 * S + 4), 4);
+        mbar_init(BAR(2 * S + 3), TC_EPI_WARPS);
+        mbar_init(BAR(2 * S + 4), TC_EPI_WARPS);
         fence_barrier_init();
     }
     for (int i = threadIdx.x; i < NT; i += TC_THREADS) {
@@ -281,42 +328,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     const int st = it % S;
                     mbar_wait(BAR(st), (it / S) & 1);
                     tc_fence_after();
-                    const uint32_t a0 = smem_u32(stage_s + (size_t)st * stage_bytes);
-                    const uint32_t b0 = smem_u32(w_s) + (uint32_t)(s * p.C8s) * (NT * 16);
-#pragma unroll 1
+                    // One thread issues every MMA, so the issue loop must be a handful of instructions per
+                    // MMA: descriptors differ only in the 14-bit start-address field, so advance that field
+                    // (16-byte units) with 32-bit adds on the low word instead of rebuilding 64-bit values.
+                    const uint64_t adesc0 = make_desc(smem_u32(stage_s + (size_t)st * stage_bytes), PLANE_BYTES, 128);
+                    const uint64_t bdesc0 = make_desc(smem_u32(w_s) + (uint32_t)(s * p.C8s) * (NT * 16), NT * 16, 128);
+                    const uint32_t a_hi = (uint32_t)(adesc0 >> 32), b_hi = (uint32_t)(bdesc0 >> 32);
+                    const uint32_t a_lo0 = (uint32_t)adesc0, b_lo0 = (uint32_t)bdesc0;
+                    const uint32_t b_tap_step = (uint32_t)Q * (NT * 16 / 16);  // per tap, in 16 B units
+                    const int nk = p.C8s / 2;
+#pragma unroll
                     for (int tap = 0; tap < KK; ++tap) {
-                        const uint32_t a_tap = a0 + (uint32_t)((tap / KS) * TC_TW + (tap % KS)) * 16;
-                        const uint32_t b_tap = b0 + (uint32_t)(tap * Q) * (NT * 16);
-                        for (int kk = 0; kk < p.C8s / 2; ++kk) {
-                            umma_f16(d, make_desc(a_tap + (uint32_t)(2 * kk) * PLANE_BYTES, PLANE_BYTES, 128),
-                                     make_desc(b_tap + (uint32_t)(2 * kk) * (NT * 16), NT * 16, 128), idesc, acc);
-                            acc = 1;
+                        const uint32_t a_lo = a_lo0 + (uint32_t)((tap / KS) * TC_TW + (tap % KS));
+                        const uint32_t b_lo = b_lo0 + (uint32_t)tap * b_tap_step;
+                        if (nk == 4) {
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                umma_f16(d, ((uint64_t)a_hi << 32) | (a_lo + (uint32_t)kk * (2 * PLANE_BYTES / 16)),
+                                         ((uint64_t)b_hi << 32) | (b_lo + (uint32_t)kk * (2 * NT)), idesc,
+                                         (s | tap | kk) ? 1u : acc);
+                        } else {
+                            for (int kk = 0; kk < nk; ++kk)
+                                umma_f16(d, ((uint64_t)a_hi << 32) | (a_lo + (uint32_t)kk * (2 * PLANE_BYTES / 16)),
+                                         ((uint64_t)b_hi << 32) | (b_lo + (uint32_t)kk * (2 * NT)), idesc,
+                                         (s | tap | kk) ? 1u : acc);
                         }
                     }
+                    acc = 1;
                     umma_commit(BAR(S + st));  // stage reusable once these MMAs have read it
                 }
                 umma_commit(BAR(2 * S + 1 + buf));  // accumulator complete
             }
         }
     } else {
-        const int lq = warp & 3;  // TMEM lane quarter this warp may access == tile row
+        const int lq = warp & 3;              // TMEM lane quarter this warp may access == tile row
+        const int half = (warp - 2) >> 2;     // two warps per quarter take alternate 16-column groups
         EpiArgs e{bias_s, p.out, p.out_image_stride, p.residual, p.res_image_stride, p.H, p.W, p.Cout, p.act,
                   p.out_mode, p.sig_from, p.subsample};
+        EpiTile<NT, 2> ep;
         uint32_t t = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++t) {
             const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, n = tile / (p.tiles_x * p.tiles_y);
             const uint32_t buf = t & 1;
-            mbar_wait(BAR(2 * S + 1 + buf), (t >> 1) & 1);
-            tc_fence_after();
             const int y = ty * TC_ROWS + lq, x = tx * VALID + lane;
             const bool valid = lane < VALID && y < p.H && x < p.W;
-            const uint32_t taddr = tmem_base + buf * ACC + ((uint32_t)(lq * 32) << 16);
-#pragma unroll 1
-            for (int c0 = 0; c0 < NT; c0 += 16) {
-                float v[16];
-                tmem_ld16(taddr + c0, v);
-                if (valid) epilogue16<NT>(e, v, c0, pss, n, y, x);
-            }
+            ep.prefetch(e, half, pss, n, y, x, valid);
+            mbar_wait(BAR(2 * S + 1 + buf), (t >> 1) & 1);
+            tc_fence_after();
+            ep.run(e, tmem_base + buf * ACC + ((uint32_t)(lq * 32) << 16), half, pss, n, y, x, valid);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(2 * S + 3 + buf));
@@ -515,7 +574,7 @@ struct TcDcnParams {
     int N, H, W, cpg, act;
     int tiles_x, tiles_y, num_tiles;
 };
-constexpr int DCN_GATHER_WARPS = 8, DCN_THREADS = 32 * (1 + DCN_GATHER_WARPS + 4), DCN_STAGES = 4;
+constexpr int DCN_GATHER_WARPS = 16, DCN_THREADS = 32 * (1 + DCN_GATHER_WARPS + 4), DCN_STAGES = 4;
 constexpr int DCN_TAP_BYTES = 8 * 128 * 16;  // 8 channel blocks x 128 pixels x 16 B
 
 __global__ void __launch_bounds__(DCN_THREADS, 1) dcn_tc_kernel(const __grid_constant__ TcDcnParams p) {
@@ -575,43 +634,82 @@ __global__ void __launch_bounds__(DCN_THREADS, 1) dcn_tc_kernel(const __grid_con
             }
         }
     } else if (warp <= DCN_GATHER_WARPS) {
-        // ---- gather: thread -> pixel m of the tile and 4 of the 8 channel blocks
+        // ---- gather: thread -> pixel m of the tile and 2 of the 8 channel blocks (q = qq, qq + 4).
+        // Branch-free: corner addresses are clamped into the image and out-of-range corners get a zero
+        // weight, so all 8 corner loads (2 blocks x 4 corners, 128 bit each) are issued back to back;
+        // the next tap's offsets/mask are fetched before the current tap is blended.
         const int gt = threadIdx.x - 32;
-        const int m = gt & 127, qh = gt >> 7;
+        const int m = gt & 127, qq = gt >> 7;
         const long long plane = (long long)p.H * p.W;
+        const float Hf = (float)p.H, Wf = (float)p.W;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, n = tile / (p.tiles_x * p.tiles_y);
             const int y = ty * TC_ROWS + (m >> 5), x = tx * TC_TW + (m & 31);
             const bool valid = y < p.H && x < p.W;
-            const long long pix = (long long)y * p.W + x;
-            const float *off = p.offset + (long long)n * p.off_stride + pix;
-            const float *msk = p.mask + (long long)n * p.mask_stride + pix;
+            const long long pix = valid ? (long long)y * p.W + x : 0;
             const __half *xb = p.x + (long long)n * p.x_image_stride;
+            const float *off[2], *msk[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int g = ((qq + 4 * i) * 8) / p.cpg;
+                off[i] = p.offset + (long long)n * p.off_stride + (long long)g * 18 * plane + pix;
+                msk[i] = p.mask + (long long)n * p.mask_stride + (long long)g * 9 * plane + pix;
+            }
+            float dy[2], dx[2], mk[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) { dy[i] = __ldg(off[i]); dx[i] = __ldg(off[i] + plane); mk[i] = __ldg(msk[i]); }
             for (int tap = 0; tap < K; ++tap, ++it) {
                 const int st = it % S;
-                mbar_wait(BAR(S + st), ((it / S) & 1) ^ 1);
-                uint8_t *dst = tap_s + st * DCN_TAP_BYTES + m * 16;
                 const float by = (float)(y - 1 + tap / 3), bx = (float)(x - 1 + tap % 3);
+                uint4 c[2][4];
+                float w[2][4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int q = qh + 2 * i;
-                    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    if (valid) {
-                        const int g = (q * 8) / p.cpg;
-                        const float dy = __ldg(off + ((long long)g * 18 + 2 * tap) * plane);
-                        const float dx = __ldg(off + ((long long)g * 18 + 2 * tap + 1) * plane);
-                        const float mk = __ldg(msk + ((long long)g * 9 + tap) * plane);
-                        sample8<__half>(xb + (long long)q * plane * 8, p.H, p.W, by + dy, bx + dx, v);
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) v[c] *= mk;
-                    }
-                    uint4 pk;
-                    __half2 *h = reinterpret_cast<__half2 *>(&pk);
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) h[c] = __floats2half2_rn(v[2 * c], v[2 * c + 1]);
-                    *reinterpret_cast<uint4 *>(dst + q * 2048) = pk;
+                for (int i = 0; i < 2; ++i) {
+                    const float py = by + dy[i], px = bx + dx[i];
+                    const bool inside = valid && py > -1.f && px > -1.f && py < Hf && px < Wf;
+                    const float fy = floorf(inside ? py : 0.f), fx = floorf(inside ? px : 0.f);
+                    const int y0 = (int)fy, x0 = (int)fx;
+                    const float ly = py - fy, lx = px - fx, hy = 1.f - ly, hx = 1.f - lx;
+                    const float m_in = inside ? mk[i] : 0.f;                 // mask folded into the weights
+                    const float wy0 = y0 >= 0 ? hy * m_in : 0.f, wy1 = y0 + 1 <= p.H - 1 ? ly * m_in : 0.f;
+                    const float wx0 = x0 >= 0 ? hx : 0.f, wx1 = x0 + 1 <= p.W - 1 ? lx : 0.f;
+                    w[i][0] = wy0 * wx0; w[i][1] = wy0 * wx1; w[i][2] = wy1 * wx0; w[i][3] = wy1 * wx1;
+                    const int y0c = max(y0, 0), y1c = min(y0 + 1, p.H - 1), x0c = max(x0, 0), x1c = min(x0 + 1, p.W - 1);
+                    const uint4 *pl = reinterpret_cast<const uint4 *>(xb + (long long)(qq + 4 * i) * plane * 8);
+                    c[i][0] = __ldg(pl + y0c * p.W + x0c); c[i][1] = __ldg(pl + y0c * p.W + x1c);
+                    c[i][2] = __ldg(pl + y1c * p.W + x0c); c[i][3] = __ldg(pl + y1c * p.W + x1c);
                 }
+                if (tap + 1 < K) {
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        dy[i] = __ldg(off[i] + (long long)(2 * tap + 2) * plane);
+                        dx[i] = __ldg(off[i] + (long long)(2 * tap + 3) * plane);
+                        mk[i] = __ldg(msk[i] + (long long)(tap + 1) * plane);
+                    }
+                }
+                uint4 pk[2];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const __half2 *h = reinterpret_cast<const __half2 *>(&c[i][k]);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 f = __half22float2(h[j]);
+                            v[2 * j] = fmaf(w[i][k], f.x, v[2 * j]);
+                            v[2 * j + 1] = fmaf(w[i][k], f.y, v[2 * j + 1]);
+                        }
+                    }
+                    __half2 *h = reinterpret_cast<__half2 *>(&pk[i]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+                }
+                mbar_wait(BAR(S + st), ((it / S) & 1) ^ 1);  // stage free (its MMAs have completed)
+                uint8_t *dst = tap_s + st * DCN_TAP_BYTES + m * 16;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) *reinterpret_cast<uint4 *>(dst + (qq + 4 * i) * 2048) = pk[i];
                 fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR(st));
@@ -620,6 +718,8 @@ __global__ void __launch_bounds__(DCN_THREADS, 1) dcn_tc_kernel(const __grid_con
     } else {
         const int lq = warp & 3;
         EpiArgs e{bias_s, p.out, p.out_image_stride, nullptr, 0, p.H, p.W, NT, p.act, OUT_C8, 0, 0};
+        EpiTile<NT, 1> ep;
+        ep.has_res = false;
         uint32_t t = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++t) {
             const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, n = tile / (p.tiles_x * p.tiles_y);
@@ -627,14 +727,7 @@ __global__ void __launch_bounds__(DCN_THREADS, 1) dcn_tc_kernel(const __grid_con
             mbar_wait(BAR(2 * S + 1 + buf), (t >> 1) & 1);
             tc_fence_after();
             const int y = ty * TC_ROWS + lq, x = tx * TC_TW + lane;
-            const bool valid = y < p.H && x < p.W;
-            const uint32_t taddr = tmem_base + buf * ACC + ((uint32_t)(lq * 32) << 16);
-#pragma unroll 1
-            for (int c0 = 0; c0 < NT; c0 += 16) {
-                float v[16];
-                tmem_ld16(taddr + c0, v);
-                if (valid) epilogue16<NT>(e, v, c0, 0, n, y, x);
-            }
+            ep.run(e, tmem_base + buf * ACC + ((uint32_t)(lq * 32) << 16), 0, 0, n, y, x, y < p.H && x < p.W);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(2 * S + 3 + buf));
