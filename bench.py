@@ -243,6 +243,8 @@ def main():
                     algorithmic_per_launch=dict(gflop=a["flops"] / a["n"] / 1e9, mbytes=a["bytes"] / a["n"] / 1e6))
         kernels = [dict(kernel=k, ms=v["ms"], n=v["n"], tflops=(v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 else 0,
                         gbs=(v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else 0) for k, v in top[:12]]
+        if os.environ.get("RVSR_BENCH_DUMP"):
+            json.dump(dict(total_ms=total_ms, rows=rows), open(os.environ["RVSR_BENCH_DUMP"], "w"), indent=0)
         value = world * B * K / (ms_max * 1e-3)
         line = dict(metric=METRIC, value=value, unit="frames/s", n_gpus=world, steps=K, warmup=args.warmup,
                     ms_per_step=ms_max / K, higher_is_better=True, scaling="weak", vs_baseline=None,
@@ -256,7 +258,8 @@ def main():
                              h2d_bytes_per_step=int(hosts[0].numel() * hosts[0].element_size()),
                              d2h_bytes_per_step=int(out_host.numel() * out_host.element_size()),
                              api="EDVREngine.forward_host -> rvsr_engine_forward_host (pinned host buffers)"),
-                    gpu_launches=launches, clocks=clocks, roofline=roof, kernels=kernels)
+                    gpu_launches=launches, clocks=clocks, roofline=roof, kernels=kernels,
+                    profile_sum_ms=total_ms)
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = cpu_sample(steps=2, warmup=1)
             line["cpu_baseline"] = cb

@@ -123,13 +123,34 @@ struct EpiArgs {
     int H, W, Cout, act, out_mode, sig_from, subsample;
 };
 
-// Epilogue of one pixel (TMEM lane) of one tile: the accumulator's NT columns are split in
-// 16-column groups; with NH = 2 two warps share a TMEM lane quarter and take alternate groups.
-// Residual blocks are fetched BEFORE waiting for the accumulator so their latency overlaps the MMAs.
+// Epilogue of one pixel (= TMEM lane) of one tile.  With NH = 2 two warps share a TMEM lane
+// quarter and take the lower / upper half of the NT accumulator columns.  Order of events:
+//   1. residual blocks are fetched BEFORE waiting for the accumulator (latency overlaps the MMAs);
+//   2. all tcgen05.ld of the warp's columns are issued, one wait, and the TMEM buffer is handed
+//      back to the MMA warp immediately;
+//   3. bias / activation / residual / fp16 pack / 128-bit stores run out of registers.
+// ACT is a template parameter for the common OUT_C8 mode (ACT = -1: runtime e.act).
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <int ACT> __device__ __forceinline__ float act_t(float v, int act_rt) {
+    if (ACT == RVSR_ACT_NONE) return v;
+    if (ACT == RVSR_ACT_LRELU) return fmaxf(v, 0.1f * v);
+    if (ACT == RVSR_ACT_RELU) return fmaxf(v, 0.f);
+    return apply_act(v, act_rt);
+}
+
 template <int NT, int NH> struct EpiTile {
-    static constexpr int NG = NT / 16;                 // 16-column groups in the accumulator
-    static constexpr int MY = (NG + NH - 1) / NH;      // groups per warp (upper bound)
+    static constexpr int HALFC = NH == 1 ? NT : ((NT / 2 + 15) / 16) * 16;  // columns per warp (upper bound)
+    static constexpr int MY = HALFC / 16;                                   // 16-column groups per warp
     uint4 res[MY * 2];
+    uint32_t acc[MY][16];
     bool has_res;
 
     __device__ __forceinline__ void prefetch(const EpiArgs &e, int half, int pss, int n, int y, int x, bool valid) {
@@ -137,56 +158,71 @@ template <int NT, int NH> struct EpiTile {
         if (e.out_mode != OUT_C8 || e.residual == nullptr || !valid) return;
         has_res = true;
         const int Co8 = (e.Cout + 7) / 8;
+        const uint4 *r = reinterpret_cast<const uint4 *>(e.residual + (long long)n * e.res_image_stride) + (long long)y * e.W + x;
+        const long long plane = (long long)e.H * e.W;
 #pragma unroll
-        for (int gi = 0; gi < MY; ++gi) {
-            const int c0 = (gi * NH + half) * 16;
+        for (int j = 0; j < MY * 2; ++j) {
+            const int c0 = half * HALFC + j * 8, q = (pss * NT + c0) / 8;
+            res[j] = make_uint4(0, 0, 0, 0);
+            if (c0 < NT && q < Co8) res[j] = __ldg(r + q * plane);
+        }
+    }
+    // issue every TMEM load of this warp's columns, wait once
+    __device__ __forceinline__ void load(uint32_t taddr, int half) {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int q = (pss * NT + c0) / 8 + j;
-                res[gi * 2 + j] = make_uint4(0, 0, 0, 0);
-                if (c0 < NT && q < Co8)
-                    res[gi * 2 + j] = __ldg(reinterpret_cast<const uint4 *>(
-                        e.residual + (long long)n * e.res_image_stride + ((((long long)q) * e.H + y) * e.W + x) * 8));
+        for (int g = 0; g < MY; ++g)
+            if (half * HALFC + g * 16 < NT) tmem_ld16_nowait(taddr + half * HALFC + g * 16, acc[g]);
+        tmem_ld_wait();
+    }
+
+    template <int ACT>
+    __device__ __forceinline__ void store_c8(const EpiArgs &e, int half, int pss, int n, int y, int x, bool valid) {
+        if (!valid) return;
+        int Ho = e.H, Wo = e.W;
+        if (e.subsample) {
+            if ((y | x) & 1) return;
+            y >>= 1; x >>= 1; Ho = (e.H - 1) / 2 + 1; Wo = (e.W - 1) / 2 + 1;
+        }
+        const int Co8 = (e.Cout + 7) / 8;
+        const long long plane = (long long)Ho * Wo;
+        uint4 *o = reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(e.out) + (long long)n * e.out_image_stride) +
+                   (long long)y * Wo + x;
+#pragma unroll
+        for (int j = 0; j < MY * 2; ++j) {
+            const int c0 = half * HALFC + j * 8, q = (pss * NT + c0) / 8;
+            if (c0 >= NT || q >= Co8) continue;
+            const float4 b0 = *reinterpret_cast<const float4 *>(e.bias_s + c0);
+            const float4 b1 = *reinterpret_cast<const float4 *>(e.bias_s + c0 + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = act_t<ACT>(__uint_as_float(acc[j >> 1][(j & 1) * 8 + i]) + bb[i], e.act);
+            if (has_res) {
+                const __half2 *h = reinterpret_cast<const __half2 *>(&res[j]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 f = __half22float2(h[i]);
+                    v[2 * i] += f.x; v[2 * i + 1] += f.y;
+                }
             }
+            uint4 pk;
+            __half2 *h = reinterpret_cast<__half2 *>(&pk);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+            o[q * plane] = pk;
         }
     }
 
-    __device__ __forceinline__ void run(const EpiArgs &e, uint32_t taddr, int half, int pss, int n, int y, int x, bool valid) {
+    __device__ __forceinline__ void store_other(const EpiArgs &e, int half, int pss, int n, int y, int x, bool valid) {
+        if (!valid) return;
 #pragma unroll
-        for (int gi = 0; gi < MY; ++gi) {
-            const int c0 = (gi * NH + half) * 16;
-            if (c0 >= NT) break;  // warp-uniform
+        for (int g = 0; g < MY; ++g) {
+            const int c0 = half * HALFC + g * 16;
+            if (c0 >= NT) break;
             float v[16];
-            tmem_ld16(taddr + c0, v);
-            if (!valid) continue;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i] + e.bias_s[c0 + i], e.act);
-            if (e.out_mode == OUT_C8) {
-                int yy = y, xx = x, Ho = e.H, Wo = e.W;
-                if (e.subsample) {
-                    if ((y | x) & 1) continue;
-                    yy >>= 1; xx >>= 1; Ho = (e.H - 1) / 2 + 1; Wo = (e.W - 1) / 2 + 1;
-                }
-                const int Co8 = (e.Cout + 7) / 8;
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int q = (pss * NT + c0) / 8 + j;
-                    if (q >= Co8) continue;
-                    float o[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) o[i] = v[j * 8 + i];
-                    if (has_res) {
-                        const __half2 *h = reinterpret_cast<const __half2 *>(&res[gi * 2 + j]);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float2 f = __half22float2(h[i]);
-                            o[2 * i] += f.x; o[2 * i + 1] += f.y;
-                        }
-                    }
-                    store8<__half>(reinterpret_cast<__half *>(e.out) + (long long)n * e.out_image_stride +
-                                       ((((long long)q) * Ho + yy) * Wo + xx) * 8, o);
-                }
-            } else if (e.out_mode == OUT_C8_SHUFFLE2) {
+            for (int i = 0; i < 16; ++i) v[i] = apply_act(__uint_as_float(acc[g][i]) + e.bias_s[c0 + i], e.act);
+            if (e.out_mode == OUT_C8_SHUFFLE2) {
                 // columns were permuted at pack time: col = ij * (NT/4) + c_local, channel c = pss*(NT/4) + c_local,
                 // out[n, c, 2y + (ij>>1), 2x + (ij&1)]   (nn.PixelShuffle(2): in-channel 4c + ij)
                 constexpr int CP = NT / 4 > 0 ? NT / 4 : 1;
@@ -219,6 +255,16 @@ template <int NT, int NH> struct EpiTile {
                 for (int i = 0; i < 16; ++i)
                     if (co0 + i < e.Cout) o[i * plane] = v[i];
             }
+        }
+    }
+
+    __device__ __forceinline__ void store(const EpiArgs &e, int half, int pss, int n, int y, int x, bool valid) {
+        if (e.out_mode == OUT_C8) {
+            if (e.act == RVSR_ACT_LRELU) store_c8<RVSR_ACT_LRELU>(e, half, pss, n, y, x, valid);
+            else if (e.act == RVSR_ACT_RELU) store_c8<RVSR_ACT_RELU>(e, half, pss, n, y, x, valid);
+            else store_c8<RVSR_ACT_NONE>(e, half, pss, n, y, x, valid);
+        } else {
+            store_other(e, half, pss, n, y, x, valid);
         }
     }
 };
@@ -375,10 +421,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             ep.prefetch(e, half, pss, n, y, x, valid);
             mbar_wait(BAR(2 * S + 1 + buf), (t >> 1) & 1);
             tc_fence_after();
-            ep.run(e, tmem_base + buf * ACC + ((uint32_t)(lq * 32) << 16), half, pss, n, y, x, valid);
+            ep.load(tmem_base + buf * ACC + ((uint32_t)(lq * 32) << 16), half);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(2 * S + 3 + buf));
+            if (lane == 0) mbar_arrive(BAR(2 * S + 3 + buf));  // accumulator is in registers: MMA may reuse the buffer
+            ep.store(e, half, pss, n, y, x, valid);
         }
     }
     tc_fence_before();
@@ -727,10 +774,11 @@ __global__ void __launch_bounds__(DCN_THREADS, 1) dcn_tc_kernel(const __grid_con
             mbar_wait(BAR(2 * S + 1 + buf), (t >> 1) & 1);
             tc_fence_after();
             const int y = ty * TC_ROWS + lq, x = tx * TC_TW + lane;
-            ep.run(e, tmem_base + buf * ACC + ((uint32_t)(lq * 32) << 16), 0, 0, n, y, x, y < p.H && x < p.W);
+            ep.load(tmem_base + buf * ACC + ((uint32_t)(lq * 32) << 16), 0);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(2 * S + 3 + buf));
+            ep.store(e, 0, 0, n, y, x, y < p.H && x < p.W);
         }
     }
     tc_fence_before();
