@@ -24,6 +24,7 @@
 // Reference semantics: nn.Conv2d sites of EDVR_arch.py (:71-91, :146-164, :229-253) and the
 // DCN of dcn/src/deform_conv_cuda_kernel.cu:467-497, :571-633 + deform_conv_cuda.cpp:539-568.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "engine.cuh"
 
@@ -283,18 +284,25 @@ struct alignas(64) TcConvParams {
     long long res_image_stride;
     int N, H, W, Cout, act, out_mode, sig_from, subsample;
     int tiles_x, tiles_y, num_tiles;
+    int debug;  // RVSR_TC_DEBUG bit mask for timing experiments only (results become garbage):
+                // 1 = issue no MMAs, 2 = no epilogue stores, 4 = no TMA halo loads, 8 = no TMEM loads
 };
 
 constexpr int TC_ROWS = 4, TC_TW = 32;
-constexpr int TC_EPI_WARPS = 8;
-constexpr int TC_THREADS = 32 * (2 + TC_EPI_WARPS);  // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: epilogue
+constexpr int TC_EPI_WARPS = 8, TC_MMA_WARPS = 2;
+// warp 0: TMA producer; warps 1-2: MMA issuers (alternate tiles -- one thread cannot issue tcgen05.mma
+// fast enough to keep the tensor pipe busy at N = 64); warp 3: TMEM allocator; warps 4-11: epilogue
+constexpr int TC_EPI_WARP0 = 4;
+constexpr int TC_THREADS = 32 * (TC_EPI_WARP0 + TC_EPI_WARPS);
+constexpr int TC_ACC_BUFS = 4;  // TMEM accumulators in flight (4 x 128 columns = all of TMEM for NT > 64)
 __host__ __device__ constexpr int acc_stride(int NT) { return NT <= 32 ? 32 : (NT <= 64 ? 64 : 128); }
 
 template <int KS, int NT>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcConvParams p) {
     constexpr int KK = KS * KS, PAD = KS / 2, VALID = TC_TW - (KS - 1), HALO_ROWS = TC_ROWS + KS - 1;
     constexpr int PLANE_BYTES = HALO_ROWS * TC_TW * 16;
-    constexpr int ACC = acc_stride(NT), TMEM_COLS = 2 * ACC;
+    constexpr int ACC = acc_stride(NT), NB = NT <= 64 ? TC_ACC_BUFS : 2, TMEM_COLS = NB * ACC;
+    constexpr int MMAW = NT <= 64 ? 2 : 1;  // issuer warps: N <= 64 MMAs are too short for a single issuing thread
     extern __shared__ __align__(1024) uint8_t smem[];
     const int Q = p.nsrc * p.C8s;  // channel blocks over all sources
     const uint32_t w_bytes = (uint32_t)Q * KK * NT * 16;
@@ -303,18 +311,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     uint8_t *stage_s = smem + w_bytes;
     float *bias_s = reinterpret_cast<float *>(stage_s + (size_t)p.nstages * stage_bytes + 128);  // +128: tap overrun slack
     uint64_t *bars = reinterpret_cast<uint64_t *>(bias_s + NT);
-    // bars: [0,S) full, [S,2S) empty, 2S wfull, 2S+1..2 tfull, 2S+3..4 tempty, then the TMEM base address
+    // bars: [0,S) full, [S,2S) empty, 2S wfull, then NB x tfull, NB x tempty, then the TMEM base address
     const int S = p.nstages;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * S + 5);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * S + 1 + 2 * NB);
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pss = blockIdx.y;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2 * S + 3; ++i) mbar_init(BAR(i), 1);
-        mbar_init(BAR(2 * S + 3), TC_EPI_WARPS);
-        mbar_init(BAR(2 * S + 4), TC_EPI_WARPS);
+        for (int i = 0; i < 2 * S + 1 + NB; ++i) mbar_init(BAR(i), 1);
+        for (int i = 0; i < NB; ++i) mbar_init(BAR(2 * S + 1 + NB + i), TC_EPI_WARPS);
         fence_barrier_init();
     }
     for (int i = threadIdx.x; i < NT; i += TC_THREADS) {
@@ -330,7 +337,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
         bias_s[i] = b;
     }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    if (warp == 3) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -352,6 +359,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 for (int s = 0; s < p.nsrc; ++s, ++it) {
                     const int st = it % S;
                     mbar_wait(BAR(S + st), ((it / S) & 1) ^ 1);
+                    if (p.debug & 4) { mbar_arrive(BAR(st)); continue; }
                     mbar_expect_tx(BAR(st), stage_bytes);
                     const int img = p.src_fixed[s] >= 0 ? (n / p.src_frames[s]) * p.src_frames[s] + p.src_fixed[s] : n;
                     tma_load_3d(smem_u32(stage_s + (size_t)st * stage_bytes), &p.tmap[s], BAR(st),
@@ -359,30 +367,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp <= MMAW) {
         if (lane == 0) {
+            // ---- MMA issuer(s).  This single thread's instruction stream is the critical path of the
+            // whole kernel (the tensor pipe needs a new N=64 MMA every 48 cycles), so: no divisions, no
+            // 64-bit descriptor rebuilds, running counters instead of modulo, everything unrolled.
             constexpr uint32_t idesc = make_idesc(NT);
+            const uint32_t mw = (uint32_t)(warp - 1);
+            const uint32_t nsrc = (uint32_t)p.nsrc, C8s = (uint32_t)p.C8s;
+            const uint64_t adesc0 = make_desc(smem_u32(stage_s), PLANE_BYTES, 128);
+            const uint64_t bdesc0 = make_desc(smem_u32(w_s), NT * 16, 128);
+            const uint32_t a_hi = (uint32_t)(adesc0 >> 32), b_hi = (uint32_t)(bdesc0 >> 32);
+            const uint32_t a_base = (uint32_t)adesc0, b_base = (uint32_t)bdesc0;
+            const uint32_t stage_units = stage_bytes >> 4;                 // descriptor address units are 16 B
+            const uint32_t b_src_step = C8s * (NT * 16 / 16), b_tap_step = (uint32_t)Q * (NT * 16 / 16);
+            const int nk = (p.debug & 1) ? 0 : (int)C8s / 2;
+            // stage ring position of this issuer's first tile, then advanced by MMAW tiles at a time
+            uint32_t st = (mw * nsrc) % (uint32_t)S, ph = ((mw * nsrc) / (uint32_t)S) & 1;
             mbar_wait(BAR(2 * S), 0);
-            uint32_t it = 0, t = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++t) {
-                const uint32_t buf = t & 1;
-                mbar_wait(BAR(2 * S + 3 + buf), ((t >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+            uint32_t t = mw;
+            for (int tile = blockIdx.x + (int)mw * gridDim.x; tile < p.num_tiles; tile += MMAW * gridDim.x, t += MMAW) {
+                const uint32_t buf = t % NB;
+                mbar_wait(BAR(2 * S + 1 + NB + buf), ((t / NB) & 1) ^ 1);  // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d = tmem_base + buf * ACC;
-                uint32_t acc = 0;
-                for (int s = 0; s < p.nsrc; ++s, ++it) {
-                    const int st = it % S;
-                    mbar_wait(BAR(st), (it / S) & 1);
+                uint32_t b_lo0 = b_base;
+                for (uint32_t s = 0; s < nsrc; ++s) {
+                    mbar_wait(BAR(st), ph);
                     tc_fence_after();
-                    // One thread issues every MMA, so the issue loop must be a handful of instructions per
-                    // MMA: descriptors differ only in the 14-bit start-address field, so advance that field
-                    // (16-byte units) with 32-bit adds on the low word instead of rebuilding 64-bit values.
-                    const uint64_t adesc0 = make_desc(smem_u32(stage_s + (size_t)st * stage_bytes), PLANE_BYTES, 128);
-                    const uint64_t bdesc0 = make_desc(smem_u32(w_s) + (uint32_t)(s * p.C8s) * (NT * 16), NT * 16, 128);
-                    const uint32_t a_hi = (uint32_t)(adesc0 >> 32), b_hi = (uint32_t)(bdesc0 >> 32);
-                    const uint32_t a_lo0 = (uint32_t)adesc0, b_lo0 = (uint32_t)bdesc0;
-                    const uint32_t b_tap_step = (uint32_t)Q * (NT * 16 / 16);  // per tap, in 16 B units
-                    const int nk = p.C8s / 2;
+                    const uint32_t a_lo0 = a_base + st * stage_units;
 #pragma unroll
                     for (int tap = 0; tap < KK; ++tap) {
                         const uint32_t a_lo = a_lo0 + (uint32_t)((tap / KS) * TC_TW + (tap % KS));
@@ -392,45 +405,50 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                             for (int kk = 0; kk < 4; ++kk)
                                 umma_f16(d, ((uint64_t)a_hi << 32) | (a_lo + (uint32_t)kk * (2 * PLANE_BYTES / 16)),
                                          ((uint64_t)b_hi << 32) | (b_lo + (uint32_t)kk * (2 * NT)), idesc,
-                                         (s | tap | kk) ? 1u : acc);
+                                         (tap | kk) ? 1u : (s ? 1u : 0u));
                         } else {
                             for (int kk = 0; kk < nk; ++kk)
                                 umma_f16(d, ((uint64_t)a_hi << 32) | (a_lo + (uint32_t)kk * (2 * PLANE_BYTES / 16)),
                                          ((uint64_t)b_hi << 32) | (b_lo + (uint32_t)kk * (2 * NT)), idesc,
-                                         (s | tap | kk) ? 1u : acc);
+                                         (tap | kk) ? 1u : (s ? 1u : 0u));
                         }
                     }
-                    acc = 1;
                     umma_commit(BAR(S + st));  // stage reusable once these MMAs have read it
+                    b_lo0 += b_src_step;
+                    if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
                 }
                 umma_commit(BAR(2 * S + 1 + buf));  // accumulator complete
+                if (MMAW > 1) {  // skip the stages of the tiles the other issuer(s) own
+                    st += (MMAW - 1) * nsrc;
+                    while (st >= (uint32_t)S) { st -= (uint32_t)S; ph ^= 1; }
+                }
             }
         }
-    } else {
-        const int lq = warp & 3;              // TMEM lane quarter this warp may access == tile row
-        const int half = (warp - 2) >> 2;     // two warps per quarter take alternate 16-column groups
+    } else if (warp >= TC_EPI_WARP0) {
+        const int lq = warp & 3;                         // TMEM lane quarter this warp may access == tile row
+        const int half = (warp - TC_EPI_WARP0) >> 2;     // two warps per quarter take the lower / upper columns
         EpiArgs e{bias_s, p.out, p.out_image_stride, p.residual, p.res_image_stride, p.H, p.W, p.Cout, p.act,
                   p.out_mode, p.sig_from, p.subsample};
         EpiTile<NT, 2> ep;
         uint32_t t = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++t) {
             const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, n = tile / (p.tiles_x * p.tiles_y);
-            const uint32_t buf = t & 1;
+            const uint32_t buf = t % NB;
             const int y = ty * TC_ROWS + lq, x = tx * VALID + lane;
             const bool valid = lane < VALID && y < p.H && x < p.W;
             ep.prefetch(e, half, pss, n, y, x, valid);
-            mbar_wait(BAR(2 * S + 1 + buf), (t >> 1) & 1);
+            mbar_wait(BAR(2 * S + 1 + buf), (t / NB) & 1);
             tc_fence_after();
-            ep.load(tmem_base + buf * ACC + ((uint32_t)(lq * 32) << 16), half);
+            if (!(p.debug & 8)) ep.load(tmem_base + buf * ACC + ((uint32_t)(lq * 32) << 16), half);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(2 * S + 3 + buf));  // accumulator is in registers: MMA may reuse the buffer
-            ep.store(e, half, pss, n, y, x, valid);
+            if (lane == 0) mbar_arrive(BAR(2 * S + 1 + NB + buf));  // accumulator is in registers: MMA may reuse the buffer
+            if (!(p.debug & 2)) ep.store(e, half, pss, n, y, x, valid);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+    if (warp == 3) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // ---------------------------------------------------------------- host side: tensor maps, packing, launch
@@ -498,7 +516,7 @@ int pack_weight_dcn_tc(const float *w_oihw, void *dst, int Cout, int C, int K, c
     return pack_weight_tc(w_oihw, dst, Cout, C, 3, 0, s);
 }
 
-static constexpr size_t TC_SMEM_LIMIT = 232448 - 1024;  // 227 KB opt-in maximum minus alignment slack
+static constexpr size_t TC_SMEM_LIMIT = 232448 - 1024 - 2048;  // 227 KB opt-in maximum minus alignment slack and static smem
 
 struct TcConvPlan {
     int NT, passes, KS, C8s, nstages;
@@ -598,6 +616,8 @@ int launch_conv_tc(const ConvOp &op, cudaStream_t s) {
     p.tiles_x = cdiv(op.W, valid); p.tiles_y = cdiv(op.H, TC_ROWS);
     p.num_tiles = p.tiles_x * p.tiles_y * op.N;
     if (p.num_tiles == 0) return RVSR_OK;
+    static const int dbg = getenv("RVSR_TC_DEBUG") ? atoi(getenv("RVSR_TC_DEBUG")) : 0;
+    p.debug = dbg;
     const int sms = sm_count();
 #define RVSR_TC_CASE(KS_, NT_) \
     if (op.ks == KS_ && pl.NT == NT_) return launch_conv_tc_t<KS_, NT_>(p, pl, sms, s);

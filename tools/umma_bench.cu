@@ -11,7 +11,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
            ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((uint64_t)(base_off & 7) << 49) | ((uint64_t)layout << 61);
 }
-struct Cfg { int N; uint32_t a_lbo, a_sbo, a_layout, a_shift, b_lbo, b_sbo, b_layout, kstep_a, kstep_b; int nmma; };
+struct Cfg { int N; uint32_t a_lbo, a_sbo, a_layout, a_shift, b_lbo, b_sbo, b_layout, kstep_a, kstep_b; int nmma; int conv_like; };
 
 __global__ void __launch_bounds__(128, 1) bench(Cfg c, long long *out) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -34,12 +34,20 @@ __global__ void __launch_bounds__(128, 1) bench(Cfg c, long long *out) {
     const uint32_t tmem = slot;
     if (threadIdx.x == 0) {
         const uint32_t idesc = (1u << 4) | ((uint32_t)(c.N >> 3) << 17) | ((128u >> 4) << 24);
-        const uint32_t a0 = smem_u32(smem) + c.a_shift, b0 = smem_u32(smem) + 100 * 1024;
+        const uint32_t a0 = smem_u32(smem) + c.a_shift, b0 = smem_u32(smem) + 32 * 1024;
         long long t0 = clock64();
         for (int i = 0; i < c.nmma; ++i) {
             const int k = i & 3;
-            const uint64_t ad = make_desc(a0 + k * c.kstep_a, c.a_lbo, c.a_sbo, c.a_layout, 0);
-            const uint64_t bd = make_desc(b0 + k * c.kstep_b, c.b_lbo, c.b_sbo, c.b_layout, 0);
+            uint32_t aoff = k * c.kstep_a, boff = k * c.kstep_b;
+            if (c.conv_like) {  // 9 taps x 4 k-steps: tap shifts of (dy*32+dx)*16 B on A, a fresh weight block per (tap, k) on B
+                const int j = i % 36, tap = j >> 2;
+                aoff = ((tap / 3) * 32 + tap % 3) * 16 + (j & 3) * c.kstep_a;
+                boff = (uint32_t)j * (c.N * 32);
+                if (c.conv_like == 2) boff = (j & 3) * (c.N * 32);      // A distinct, B reused
+                if (c.conv_like == 3) aoff = (j & 3) * c.kstep_a;       // B distinct, A reused
+            }
+            const uint64_t ad = make_desc(a0 + aoff, c.a_lbo, c.a_sbo, c.a_layout, 0);
+            const uint64_t bd = make_desc(b0 + boff, c.b_lbo, c.b_sbo, c.b_layout, 0);
             asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                          "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem), "l"(ad), "l"(bd), "r"(idesc), "r"(i ? 1u : 0u) : "memory");
         }
@@ -68,6 +76,13 @@ int main() {
         {"noswz N64  LBO128 SBO256 (std)", {64, 128, 256, 0, 0, 128, 256, 0, 4096, 2048, 4096}},
         {"noswz N128 LBO3072 aligned    ", {128, 3072, 128, 0, 0, 2048, 128, 0, 6144, 4096, 4096}},
         {"noswz N256 LBO3072 aligned    ", {256, 3072, 128, 0, 0, 4096, 128, 0, 6144, 8192, 4096}},
+        {"noswz N64  conv-like A+B distinct", {64, 3072, 128, 0, 0, 1024, 128, 0, 6144, 2048, 3600, 1}},
+        {"noswz N64  conv-like A distinct  ", {64, 3072, 128, 0, 0, 1024, 128, 0, 6144, 2048, 3600, 2}},
+        {"noswz N64  conv-like B distinct  ", {64, 3072, 128, 0, 0, 1024, 128, 0, 6144, 2048, 3600, 3}},
+        {"noswz N128 conv-like A+B distinct", {128, 3072, 128, 0, 0, 2048, 128, 0, 6144, 4096, 3600, 1}},
+        {"noswz N128 conv-like A distinct  ", {128, 3072, 128, 0, 0, 2048, 128, 0, 6144, 4096, 3600, 2}},
+        {"noswz N32  conv-like A+B distinct", {32, 3072, 128, 0, 0, 512, 128, 0, 6144, 1024, 3600, 1}},
+        {"noswz N16  conv-like A+B distinct", {16, 3072, 128, 0, 0, 256, 128, 0, 6144, 512, 3600, 1}},
         // 128B swizzle, K-major, rows of 128 B (64 fp16), 8-row atoms of 1024 B; k-step = +32 B
         {"sw128 N64  aligned            ", {64, 16, 1024, 2, 0, 16, 1024, 2, 32, 32, 4096}},
         {"sw128 N64  shift128 (1 row)   ", {64, 16, 1024, 2, 128, 16, 1024, 2, 32, 32, 4096}},
