@@ -161,10 +161,20 @@ class ModulatedDeformConvPack(ModulatedDeformConv):
         nn.init.zeros_(self.conv_offset_mask.weight)
         nn.init.zeros_(self.conv_offset_mask.bias)
 
+    def _fusable(self, x, feat):
+        return (x.is_cuda and not torch.is_grad_enabled() and self.kernel_size == (3, 3) and self.stride == 1
+                and self.padding == 1 and self.dilation == 1 and self.groups == 1 and self.bias is not None
+                and x.dtype in (torch.float32, torch.float16) and feat.shape == x.shape)
+
     def forward(self, x):
         feat = x
         if self.extra_offset_mask:
             x, feat = x[0], x[1]
+        if self._fusable(x, feat):
+            # inference: the whole pack is one C-ABI call (rvsr_mdcn_pack_fwd)
+            from ... import ops
+            return ops.mdcn_pack(x, feat, self.conv_offset_mask.weight, self.conv_offset_mask.bias, self.weight,
+                                 self.bias, self.deformable_groups)
         om = self.conv_offset_mask(feat)
         third = om.shape[1] // 3
         # chunk(3) then cat(o1, o2) == the first two thirds; the reference also computes a

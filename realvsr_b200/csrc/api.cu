@@ -152,11 +152,97 @@ int rvsr_mdcn_bwd(const void *, const void *, const void *, const void *, const 
     return RVSR_E_UNSUPPORTED;
 }
 
-size_t rvsr_mdcn_pack_fwd_workspace_bytes(int, int, int, int, int, int, int) { return 0; }
-int rvsr_mdcn_pack_fwd(const void *, const void *, const void *, const void *, const void *, const void *, void *,
-                       int, int, int, int, int, int, int, int, void *, size_t, void *) {
-    set_error("rvsr_mdcn_pack_fwd: not built yet");
-    return RVSR_E_UNSUPPORTED;
+size_t rvsr_mdcn_pack_fwd_workspace_bytes(int B, int C, int H, int W, int Cout, int dg, int dtype) {
+    if (B < 0 || C <= 0 || H <= 0 || W <= 0 || Cout <= 0 || dg <= 0) return 0;
+    const size_t es = dtype == RVSR_F16 ? 2 : 4, px = (size_t)B * H * W, c8 = (size_t)cdiv(C, 8) * 8;
+    size_t n = 2 * align_up(px * c8 * es, 256);                       // x, feat channel-blocked
+    n += align_up(px * 27 * dg * 4, 256);                             // offsets + mask (planar fp32 >= OM24)
+    n += align_up(px * (size_t)cdiv(Cout, 8) * 8 * es, 256);          // output channel-blocked
+    n += 2 * align_up((size_t)27 * dg * C * 9 * 4, 256) + 2 * align_up((size_t)Cout * C * 9 * 4, 256);  // fp32 copies
+    n += align_up((size_t)cdiv(C, 8) * 72 * cdiv(27 * dg, 64) * 64 * 4, 256) + align_up((size_t)cdiv(C, 8) * 72 * cdiv(Cout, 64) * 64 * 4, 256);
+    n += align_up(tc_conv_weight_bytes(27 * dg, C, 3, 2) + 256, 256) + align_up(tc_conv_weight_bytes(Cout, C, 3) + 256, 256);
+    n += 2 * align_up((size_t)(27 * dg + Cout) * 4, 256);
+    return n + 8192;
+}
+
+}  // extern "C"
+
+template <typename T>
+static int mdcn_pack_fwd_t(const void *x, const void *feat, const void *w_om, const void *b_om, const void *weight,
+                           const void *bias, void *y, int B, int C, int H, int W, int Cout, int dg, int act, int dtype,
+                           Carver &cv, cudaStream_t s) {
+    const size_t es = sizeof(T), px = (size_t)B * H * W;
+    const int Com = 27 * dg, C8 = cdiv(C, 8);
+    T *xa = (T *)cv.take(px * C8 * 8 * es), *fa = (T *)cv.take(px * C8 * 8 * es);
+    float *om = (float *)cv.take(px * Com * 4);
+    T *oa = (T *)cv.take(px * cdiv(Cout, 8) * 8 * es);
+    float *wom32 = (float *)cv.take((size_t)Com * C * 9 * 4), *w32 = (float *)cv.take((size_t)Cout * C * 9 * 4);
+    float *bom32 = (float *)cv.take((size_t)Com * 4), *b32 = (float *)cv.take((size_t)Cout * 4);
+    const int cp_om = cdiv(Com, 64) * 64, cp = cdiv(Cout, 64) * 64;
+    float *wom_simt = (float *)cv.take((size_t)C8 * 72 * cp_om * 4), *w_simt = (float *)cv.take((size_t)C8 * 72 * cp * 4);
+    const bool tc = dtype == RVSR_F16 && C == 64 && Cout == 64 && (C / dg) % 8 == 0 && tc_conv_weight_bytes(Com, C, 3, 2) > 0;
+    void *wom_tc = tc ? cv.take(tc_conv_weight_bytes(Com, C, 3, 2) + 16) : nullptr;
+    void *w_tc = tc ? cv.take(tc_conv_weight_bytes(Cout, C, 3) + 16) : nullptr;
+    if (!cv.ok) { set_error("mdcn_pack: workspace too small"); return RVSR_E_WORKSPACE; }
+    RVSR_TRY((launch_pack_nchw<T, T>((const T *)x, xa, B, C, H, W, s)));
+    RVSR_TRY((launch_pack_nchw<T, T>((const T *)feat, fa, B, C, H, W, s)));
+    const float *wom = (const float *)w_om, *bom = (const float *)b_om, *w = (const float *)weight, *b = (const float *)bias;
+    if (dtype == RVSR_F16) {
+        RVSR_TRY(launch_convert_f16_f32(w_om, wom32, (long long)Com * C * 9, s)); wom = wom32;
+        RVSR_TRY(launch_convert_f16_f32(weight, w32, (long long)Cout * C * 9, s)); w = w32;
+        if (b_om) { RVSR_TRY(launch_convert_f16_f32(b_om, bom32, Com, s)); bom = bom32; }
+        if (bias) { RVSR_TRY(launch_convert_f16_f32(bias, b32, Cout, s)); b = b32; }
+    }
+    const int cin = C;
+    const long long img = (long long)C8 * H * W * 8;
+    ConvOp co = {};
+    co.src[0] = Src{fa, img, C, 1, -1}; co.nsrc = 1; co.bias = bom; co.out = om;
+    co.N = B; co.H = H; co.W = W; co.Cout = Com; co.ks = 3; co.stride = 1; co.act = RVSR_ACT_NONE; co.sig_from = 18 * dg;
+    DcnOp d = {};
+    d.x = Src{xa, img, C, 1, -1}; d.bias = b; d.N = B; d.H = H; d.W = W; d.Cout = Cout; d.kh = d.kw = 3; d.stride = 1;
+    d.pad = 1; d.dil = 1; d.dg = dg; d.act = act;
+    if (tc) {
+        RVSR_TRY(pack_weight_tc(wom, wom_tc, Com, C, 3, 2, s));
+        RVSR_TRY(pack_weight_tc(w, w_tc, Cout, C, 3, 0, s));
+        co.w_tc = wom_tc; co.out_mode = OUT_OM24; co.dg = dg; co.out_image_stride = (long long)dg * 24 * H * W;
+        RVSR_CHECK_ARG(tc_conv_supported(co), "mdcn_pack: offset conv not covered by the tcgen05 kernel");
+        RVSR_TRY(launch_conv_tc(co, s));
+        d.w_tc = w_tc; d.om24 = om; d.om24_image_stride = co.out_image_stride; d.out = oa;
+        d.out_image_stride = (long long)cdiv(Cout, 8) * H * W * 8; d.out_mode = OUT_C8;
+        RVSR_CHECK_ARG(tc_dcn_supported(d), "mdcn_pack: DCN not covered by the tcgen05 kernel");
+        RVSR_TRY(launch_dcn_tc(d, s));
+        return launch_unpack_nchw<T, T>(oa, (T *)y, B, Cout, H, W, s);
+    }
+    RVSR_TRY(pack_weight_simt(wom, wom_simt, Com, C, 3, &cin, 1, cp_om, s));
+    RVSR_TRY(pack_weight_simt(w, w_simt, Cout, C, 3, &cin, 1, cp, s));
+    co.w_simt = wom_simt; co.out_mode = OUT_PLANAR_F32; co.out_image_stride = (long long)Com * H * W;
+    RVSR_TRY(launch_conv_simt<T>(co, s));
+    d.w_simt = w_simt; d.offset = om; d.mask = om + (long long)18 * dg * H * W;
+    d.offset_image_stride = d.mask_image_stride = (long long)Com * H * W;
+    d.out = y; d.out_image_stride = (long long)Cout * H * W; d.out_mode = OUT_NCHW_T;
+    return launch_dcn_simt<T>(d, s);
+}
+
+extern "C" {
+
+int rvsr_mdcn_pack_fwd(const void *x, const void *feat, const void *w_offset_mask, const void *b_offset_mask,
+                       const void *weight, const void *bias, void *y, int B, int C, int H, int W, int Cout, int dg,
+                       int act, int dtype, void *workspace, size_t workspace_bytes, void *stream) {
+    RVSR_CHECK_ARG(B >= 0 && C > 0 && H > 0 && W > 0 && Cout > 0, "mdcn_pack: bad sizes");
+    RVSR_CHECK_ARG(dg > 0 && C % dg == 0, "mdcn_pack: channels %d not divisible by deformable groups %d", C, dg);
+    RVSR_CHECK_ARG(dtype == RVSR_F32 || dtype == RVSR_F16, "mdcn_pack: bad dtype");
+    RVSR_CHECK_ARG(act == RVSR_ACT_NONE || act == RVSR_ACT_LRELU || act == RVSR_ACT_RELU, "mdcn_pack: bad activation");
+    if (B == 0) return RVSR_OK;
+    RVSR_CHECK_ARG(x && feat && w_offset_mask && weight && y && workspace, "mdcn_pack: null buffer");
+    Carver cv{(char *)workspace, workspace_bytes};
+    const size_t mis = (size_t)((uintptr_t)workspace % 256);
+    if (mis) { cv.base += 256 - mis; cv.cap -= 256 - mis; }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == RVSR_F16)
+        return mdcn_pack_fwd_t<__half>(x, feat, w_offset_mask, b_offset_mask, weight, bias, y, B, C, H, W, Cout, dg, act,
+                                       dtype, cv, s);
+    return mdcn_pack_fwd_t<float>(x, feat, w_offset_mask, b_offset_mask, weight, bias, y, B, C, H, W, Cout, dg, act, dtype,
+                                  cv, s);
 }
 
 size_t rvsr_conv2d_fwd_workspace_bytes(int B, int C1, int C2, int H, int W, int Cout, int ks, int dtype) {

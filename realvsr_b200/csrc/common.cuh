@@ -150,6 +150,10 @@ enum OutMode {
     OUT_C8_SHUFFLE2 = 1,  // nn.PixelShuffle(2) fused into the store (EDVR_arch.py:311-312)
     OUT_PLANAR_F32 = 2,   // [n][Cout][H][W] fp32; channels >= sig_from get a sigmoid (offset/mask conv)
     OUT_NCHW_T = 3,       // [n][Cout][H][W] of T (operator-level API)
+    OUT_OM24 = 4,         // DCN offsets+mask for the tcgen05 gather kernel: per pixel and deformable group
+                          // 24 words = 3 blocks of 32 B: [dy0 dx0 .. dy3 dx3][dy4 dx4 .. dy7 dx7]
+                          // [dy8 dx8 m01 m23 m45 m67 m8_ 0], offsets fp32, sigmoid(mask) as fp16 pairs;
+                          // memory [n][dg*3][H][W][8 words]
 };
 
 struct ConvOp {
@@ -165,6 +169,7 @@ struct ConvOp {
     int N, H, W;           // images, input height/width
     int Cout, ks, stride;  // pad = ks / 2
     int act, out_mode, sig_from;
+    int dg;                // OUT_OM24: deformable groups (Cout == 27 * dg)
 };
 
 struct DcnOp {
@@ -172,6 +177,8 @@ struct DcnOp {
     const float *offset;   // planar fp32 [n][dg*2*K][Ho][Wo]
     const float *mask;     // planar fp32 [n][dg*K][Ho][Wo], already sigmoid-ed
     long long offset_image_stride, mask_image_stride;
+    const void *om24;      // if non-null: offsets+mask in OUT_OM24 format (tcgen05 path), offset/mask unused
+    long long om24_image_stride;  // in 4-byte words
     const float *w_simt;   // packed like ConvOp
     const void *w_tc;
     const float *bias;

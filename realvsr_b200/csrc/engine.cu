@@ -166,8 +166,13 @@ int Engine::finalize(cudaStream_t s) {
         if (cfg_.precision == RVSR_F16) {
             const bool is_dcn = base.size() > 8 && base.compare(base.size() - 8, 8, "_dcnpack") == 0;
             const bool shuffle = (base == "upconv1" || base == "upconv2");
+            const bool is_om = base.size() > 17 && base.compare(base.size() - 17, 17, ".conv_offset_mask") == 0;
+            // the tcgen05 DCN kernel wants offsets/mask in OUT_OM24 order (needs nf == 64, whole 8-channel
+            // blocks per deformable group); otherwise the offset conv stays planar on the CUDA-core kernel
+            const int mode = shuffle ? 1 : ((is_om && tc_dcn_weight_bytes(cfg_.nf, cfg_.nf, 9) > 0 &&
+                                             (cfg_.nf / cfg_.groups) % 8 == 0) ? 2 : 0);
             const size_t tb = is_dcn ? tc_dcn_weight_bytes(pc.Cout, pc.Cin, pc.ks * pc.ks)
-                                     : tc_conv_weight_bytes(pc.Cout, pc.Cin, pc.ks);
+                                     : ((is_om && mode != 2) ? 0 : tc_conv_weight_bytes(pc.Cout, pc.Cin, pc.ks, mode));
             if (tb > 0) {
                 if (pc.w_tc == nullptr) {
                     RVSR_CUDA(cudaMalloc(&pc.w_tc, tb));
@@ -176,7 +181,7 @@ int Engine::finalize(cudaStream_t s) {
                 if (is_dcn)
                     RVSR_TRY(pack_weight_dcn_tc(wsrc, pc.w_tc, pc.Cout, pc.Cin, pc.ks * pc.ks, s));
                 else
-                    RVSR_TRY(pack_weight_tc(wsrc, pc.w_tc, pc.Cout, pc.Cin, pc.ks, shuffle ? 1 : 0, s));
+                    RVSR_TRY(pack_weight_tc(wsrc, pc.w_tc, pc.Cout, pc.Cin, pc.ks, mode, s));
             }
         }
     }
@@ -254,9 +259,10 @@ template <typename T> struct Plan {
         Act o;
         if (out_mode == OUT_C8_SHUFFLE2) {
             o = make(N, pc->Cout / 4, 2 * Ho, 2 * Wo);
-        } else if (out_mode == OUT_PLANAR_F32) {
+        } else if (out_mode == OUT_PLANAR_F32 || out_mode == OUT_OM24) {
             o.N = N; o.C = pc->Cout; o.H = Ho; o.W = Wo;
-            o.p = ar.alloc((size_t)N * pc->Cout * Ho * Wo * sizeof(float));
+            const size_t words = out_mode == OUT_OM24 ? (size_t)(pc->Cout / 27) * 24 : (size_t)pc->Cout;
+            o.p = ar.alloc((size_t)N * words * Ho * Wo * sizeof(float));
             if (o.p == nullptr && rc == RVSR_OK) { set_error("workspace too small"); rc = RVSR_E_WORKSPACE; }
         } else {
             o = make(N, pc->Cout, Ho, Wo);
@@ -272,15 +278,25 @@ template <typename T> struct Plan {
         }
         op.w_simt = pc->w_simt; op.w_tc = pc->w_tc; op.bias = pc->bias;
         op.out = o.p;
-        op.out_image_stride = out_mode == OUT_PLANAR_F32 ? (long long)pc->Cout * Ho * Wo : o.image_elems();
+        op.out_image_stride = out_mode == OUT_PLANAR_F32 ? (long long)pc->Cout * Ho * Wo
+                              : out_mode == OUT_OM24     ? (long long)(pc->Cout / 27) * 24 * Ho * Wo
+                                                         : o.image_elems();
+        op.dg = out_mode == OUT_OM24 ? pc->Cout / 27 : 0;
         if (residual != nullptr) { op.residual = residual->p; op.res_image_stride = residual->image_elems(); }
         op.N = N; op.H = H; op.W = W; op.Cout = pc->Cout; op.ks = pc->ks; op.stride = stride;
         op.act = act; op.out_mode = out_mode; op.sig_from = sig_from;
         const double px = (double)N * Ho * Wo;
         const double flops = 2.0 * cin * pc->Cout * pc->ks * pc->ks * px;
-        const double obytes = out_mode == OUT_PLANAR_F32 ? px * pc->Cout * 4 : px * pc->Cout * sizeof(T);
+        const double obytes = out_mode == OUT_PLANAR_F32 ? px * pc->Cout * 4
+                              : out_mode == OUT_OM24     ? px * (pc->Cout / 27) * 96.0
+                                                         : px * pc->Cout * sizeof(T);
         const double bytes = (double)N * H * W * cin * sizeof(T) + obytes + (residual ? obytes : 0);
         const bool tc = use_tc && tc_conv_supported(op);
+        if (out_mode == OUT_OM24 && !tc) {
+            set_error("engine: %s: OUT_OM24 needs the tcgen05 conv kernel", name.c_str());
+            rc = RVSR_E_STATE;
+            return o;
+        }
         launch((tc ? "tc:" : "simt:") + name, flops, bytes, [&] { return tc ? launch_conv_tc(op, s) : launch_conv_simt<T>(op, s); });
         return o;
     }
@@ -288,19 +304,28 @@ template <typename T> struct Plan {
     // ModulatedDeformConvPack with extra_offset_mask=True (deform_conv.py:274-292)
     Act dcn_pack(const std::string &name, const Act &x, const Act &feat, int dg, int act) {
         const int K = 9;
-        // conv_offset_mask -> planar fp32 [N][27*dg][H][W]; first 18*dg = offsets (o1|o2 of chunk(3)
-        // concatenated back = the first two thirds), last 9*dg = sigmoid(mask)
-        Act om = conv(name + ".conv_offset_mask", {src_of(feat)}, feat.N, feat.H, feat.W, RVSR_ACT_NONE, 1,
-                      OUT_PLANAR_F32, nullptr, 2 * dg * K);
         const PackedConv *pc = get(name);
-        if (pc == nullptr) return Act();
+        const PackedConv *pom = get(name + ".conv_offset_mask");
+        if (pc == nullptr || pom == nullptr) return Act();
+        // tcgen05 pair: offset conv writes OUT_OM24, gather kernel consumes it.  Otherwise planar fp32
+        // [N][27*dg][H][W]: first 18*dg = offsets (o1|o2 of chunk(3) concatenated back = the first two
+        // thirds), last 9*dg = sigmoid(mask).
+        const bool om24 = use_tc && pc->w_tc != nullptr && pom->w_tc != nullptr && x.C == 64 && pc->Cout == 64 &&
+                          feat.C == 64 && (x.C / dg) % 8 == 0 && sizeof(T) == 2;
+        Act om = conv(name + ".conv_offset_mask", {src_of(feat)}, feat.N, feat.H, feat.W, RVSR_ACT_NONE, 1,
+                      om24 ? OUT_OM24 : OUT_PLANAR_F32, nullptr, 2 * dg * K);
         Act o = make(x.N, pc->Cout, x.H, x.W);
         if (dry || rc != RVSR_OK) return o;
         DcnOp op = {};
         op.x = src_of(x);
-        op.offset = reinterpret_cast<const float *>(om.p);
-        op.mask = op.offset + (long long)2 * dg * K * x.H * x.W;
-        op.offset_image_stride = op.mask_image_stride = (long long)3 * dg * K * x.H * x.W;
+        if (om24) {
+            op.om24 = om.p;
+            op.om24_image_stride = (long long)dg * 24 * x.H * x.W;
+        } else {
+            op.offset = reinterpret_cast<const float *>(om.p);
+            op.mask = op.offset + (long long)2 * dg * K * x.H * x.W;
+            op.offset_image_stride = op.mask_image_stride = (long long)3 * dg * K * x.H * x.W;
+        }
         op.w_simt = pc->w_simt; op.w_tc = pc->w_tc; op.bias = pc->bias;
         op.out = o.p; op.out_image_stride = o.image_elems();
         op.N = x.N; op.H = x.H; op.W = x.W; op.Cout = pc->Cout;
@@ -308,8 +333,13 @@ template <typename T> struct Plan {
         op.act = act; op.out_mode = OUT_C8;
         const double px = (double)x.N * x.H * x.W;
         const double flops = (2.0 * x.C * pc->Cout * K + 8.0 * x.C * K) * px;  // contraction + gather
-        const double bytes = px * (x.C * sizeof(T) + 3.0 * dg * K * 4 + pc->Cout * sizeof(T));
-        const bool tc = use_tc && tc_dcn_supported(op);
+        const double bytes = px * (x.C * sizeof(T) + (om24 ? 96.0 * dg : 3.0 * dg * K * 4) + pc->Cout * sizeof(T));
+        const bool tc = om24 && tc_dcn_supported(op);
+        if (om24 && !tc) {
+            set_error("engine: %s: tcgen05 DCN kernel rejected an OUT_OM24 plan", name.c_str());
+            rc = RVSR_E_STATE;
+            return o;
+        }
         launch((tc ? "tc:" : "simt:") + name, flops, bytes, [&] { return tc ? launch_dcn_tc(op, s) : launch_dcn_simt<T>(op, s); });
         return o;
     }

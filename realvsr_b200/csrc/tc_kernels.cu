@@ -121,7 +121,7 @@ struct EpiArgs {
     long long out_image_stride;
     const __half *residual;
     long long res_image_stride;
-    int H, W, Cout, act, out_mode, sig_from, subsample;
+    int H, W, Cout, act, out_mode, sig_from, subsample, dg;
 };
 
 // Epilogue of one pixel (= TMEM lane) of one tile.  With NH = 2 two warps share a TMEM lane
@@ -259,8 +259,46 @@ template <int NT, int NH> struct EpiTile {
         }
     }
 
+    // OUT_OM24 (NT = 128, NH = 2): this warp holds two deformable groups x 32 columns
+    // [dy0 dx0 .. dy8 dx8 m0 .. m8 pad*5] (column order fixed at weight-pack time).
+    __device__ __forceinline__ void store_om24(const EpiArgs &e, int half, int pss, int n, int y, int x, bool valid) {
+        if (!valid) return;
+        if constexpr (NT == 128 && NH == 2) {
+            const long long plane = (long long)e.H * e.W;
+            uint4 *o = reinterpret_cast<uint4 *>(e.out) + ((long long)n * e.out_image_stride) / 4 + ((long long)y * e.W + x) * 2;
+#pragma unroll
+            for (int lgi = 0; lgi < 2; ++lgi) {
+                const int g = pss * 4 + half * 2 + lgi;
+                if (g >= e.dg) continue;
+                const float *b = e.bias_s + half * 64 + lgi * 32;
+                float v[27];
+#pragma unroll
+                for (int j = 0; j < 27; ++j) v[j] = __uint_as_float(acc[lgi * 2 + (j >> 4)][j & 15]) + b[j];
+#pragma unroll
+                for (int j = 18; j < 27; ++j) v[j] = __fdividef(1.f, 1.f + __expf(-v[j]));
+                uint4 *og = o + (long long)(g * 3) * plane * 2;
+                og[0] = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+                og[1] = make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7]));
+                og += plane * 2;
+                og[0] = make_uint4(__float_as_uint(v[8]), __float_as_uint(v[9]), __float_as_uint(v[10]), __float_as_uint(v[11]));
+                og[1] = make_uint4(__float_as_uint(v[12]), __float_as_uint(v[13]), __float_as_uint(v[14]), __float_as_uint(v[15]));
+                og += plane * 2;
+                uint32_t m[5];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const __half2 h = __floats2half2_rn(v[18 + 2 * k], k < 4 ? v[19 + 2 * k] : 0.f);
+                    m[k] = *reinterpret_cast<const uint32_t *>(&h);
+                }
+                og[0] = make_uint4(__float_as_uint(v[16]), __float_as_uint(v[17]), m[0], m[1]);
+                og[1] = make_uint4(m[2], m[3], m[4], 0u);
+            }
+        }
+    }
+
     __device__ __forceinline__ void store(const EpiArgs &e, int half, int pss, int n, int y, int x, bool valid) {
-        if (e.out_mode == OUT_C8) {
+        if (e.out_mode == OUT_OM24) {
+            store_om24(e, half, pss, n, y, x, valid);
+        } else if (e.out_mode == OUT_C8) {
             if (e.act == RVSR_ACT_LRELU) store_c8<RVSR_ACT_LRELU>(e, half, pss, n, y, x, valid);
             else if (e.act == RVSR_ACT_RELU) store_c8<RVSR_ACT_RELU>(e, half, pss, n, y, x, valid);
             else store_c8<RVSR_ACT_NONE>(e, half, pss, n, y, x, valid);
@@ -282,7 +320,7 @@ struct alignas(64) TcConvParams {
     long long out_image_stride;
     const __half *residual;
     long long res_image_stride;
-    int N, H, W, Cout, act, out_mode, sig_from, subsample;
+    int N, H, W, Cout, act, out_mode, sig_from, subsample, dg;
     int tiles_x, tiles_y, num_tiles;
     int debug;  // RVSR_TC_DEBUG bit mask for timing experiments only (results become garbage):
                 // 1 = issue no MMAs, 2 = no epilogue stores, 4 = no TMA halo loads, 8 = no TMEM loads
@@ -331,6 +369,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             if (p.out_mode == OUT_C8_SHUFFLE2) {
                 const int c = pss * (NT / 4) + i % (NT / 4), ij = i / (NT / 4);
                 b = (4 * c + ij) < p.Cout ? p.bias[4 * c + ij] : 0.f;
+            } else if (p.out_mode == OUT_OM24) {
+                const int g = pss * 4 + i / 32, j = i % 32;
+                if (g < p.dg && j < 27) b = p.bias[j < 18 ? g * 18 + j : 18 * p.dg + g * 9 + (j - 18)];
             } else if (co < p.Cout) {
                 b = p.bias[co];
             }
@@ -428,7 +469,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int lq = warp & 3;                         // TMEM lane quarter this warp may access == tile row
         const int half = (warp - TC_EPI_WARP0) >> 2;     // two warps per quarter take the lower / upper columns
         EpiArgs e{bias_s, p.out, p.out_image_stride, p.residual, p.res_image_stride, p.H, p.W, p.Cout, p.act,
-                  p.out_mode, p.sig_from, p.subsample};
+                  p.out_mode, p.sig_from, p.subsample, p.dg};
         EpiTile<NT, 2> ep;
         uint32_t t = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++t) {
@@ -467,26 +508,27 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-static int tc_pick_nt(int Cout) {
+static int tc_pick_nt(int Cout, int mode = 0) {
+    if (mode == 2) return (Cout % 27 == 0) ? 128 : 0;  // OUT_OM24: 4 deformable groups x 32 columns per pass
     if (Cout <= 16) return 16;
     if (Cout <= 64) return 64;
-    if (Cout == 216) return 112;  // DCN offset/mask prediction with 8 deformable groups: 2 passes of 112
     if (Cout % 128 == 0) return 128;
     if (Cout % 64 == 0) return 64;
     return 0;
 }
-static int tc_passes(int Cout, int NT) { return (Cout + NT - 1) / NT; }
+static int tc_passes(int Cout, int NT, int mode = 0) { return mode == 2 ? (Cout / 27 + 3) / 4 : (Cout + NT - 1) / NT; }
 static int pad16(int c) { return (c + 15) / 16 * 16; }
 
-size_t tc_conv_weight_bytes(int Cout, int Cin, int ks) {
-    const int NT = tc_pick_nt(Cout);
-    if (NT == 0 || (ks != 1 && ks != 3)) return 0;
-    return (size_t)tc_passes(Cout, NT) * ks * ks * (pad16(Cin) / 8) * NT * 16;
+size_t tc_conv_weight_bytes(int Cout, int Cin, int ks, int mode) {
+    const int NT = tc_pick_nt(Cout, mode);
+    if (NT == 0 || (ks != 1 && ks != 3) || (mode == 2 && ks != 3)) return 0;
+    return (size_t)tc_passes(Cout, NT, mode) * ks * ks * (pad16(Cin) / 8) * NT * 16;
 }
 size_t tc_dcn_weight_bytes(int Cout, int C, int K) { return (Cout == 64 && C == 64 && K == 9) ? tc_conv_weight_bytes(64, 64, 3) : 0; }
 
 __global__ void pack_weight_tc_kernel(const float *__restrict__ w, __half *__restrict__ dst, int Cout, int Cin, int KK,
-                                      int Q, int NT, int shuffle, long long total) {
+                                      int Q, int NT, int mode, long long total) {
+    const int dg = Cout / 27;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int e = (int)(i % 8);
         long long r = i / 8;
@@ -497,17 +539,25 @@ __global__ void pack_weight_tc_kernel(const float *__restrict__ w, __half *__res
         const int tap = (int)(r % KK);
         const int pss = (int)(r / KK);
         const int cin = q * 8 + e;
-        const int co = shuffle ? 4 * (pss * (NT / 4) + n % (NT / 4)) + n / (NT / 4) : pss * NT + n;
+        int co;
+        if (mode == 1) {  // pixel shuffle: column = ij * (NT/4) + c_local  <->  conv channel 4c + ij
+            co = 4 * (pss * (NT / 4) + n % (NT / 4)) + n / (NT / 4);
+        } else if (mode == 2) {  // OUT_OM24: column = local group * 32 + [dy0 dx0 .. dy8 dx8 m0 .. m8]
+            const int g = pss * 4 + n / 32, j = n % 32;
+            co = (g < dg && j < 27) ? (j < 18 ? g * 18 + j : 18 * dg + g * 9 + (j - 18)) : Cout;
+        } else {
+            co = pss * NT + n;
+        }
         dst[i] = __float2half_rn((co < Cout && cin < Cin) ? w[((long long)co * Cin + cin) * KK + tap] : 0.f);
     }
 }
-int pack_weight_tc(const float *w_oihw, void *dst, int Cout, int Cin, int ks, int shuffle, cudaStream_t s) {
-    const int NT = tc_pick_nt(Cout);
-    RVSR_CHECK_ARG(NT != 0, "tc pack: unsupported Cout %d", Cout);
+int pack_weight_tc(const float *w_oihw, void *dst, int Cout, int Cin, int ks, int mode, cudaStream_t s) {
+    const int NT = tc_pick_nt(Cout, mode);
+    RVSR_CHECK_ARG(NT != 0, "tc pack: unsupported Cout %d (mode %d)", Cout, mode);
     const int Q = pad16(Cin) / 8;
-    const long long total = (long long)tc_passes(Cout, NT) * ks * ks * Q * NT * 8;
+    const long long total = (long long)tc_passes(Cout, NT, mode) * ks * ks * Q * NT * 8;
     pack_weight_tc_kernel<<<(int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096), 256, 0, s>>>(
-        w_oihw, reinterpret_cast<__half *>(dst), Cout, Cin, ks * ks, Q, NT, shuffle, total);
+        w_oihw, reinterpret_cast<__half *>(dst), Cout, Cin, ks * ks, Q, NT, mode, total);
     RVSR_LAUNCH_CHECK();
     return RVSR_OK;
 }
@@ -526,16 +576,20 @@ static bool tc_conv_plan(const ConvOp &op, TcConvPlan &pl) {
     if (op.w_tc == nullptr || (op.ks != 1 && op.ks != 3) || op.nsrc < 1) return false;
     if (!(op.stride == 1 || (op.stride == 2 && op.ks == 3 && op.out_mode == OUT_C8 && op.H % 2 == 0 && op.W % 2 == 0)))
         return false;
-    if (op.out_mode != OUT_C8 && op.out_mode != OUT_C8_SHUFFLE2 && op.out_mode != OUT_PLANAR_F32) return false;
+    if (op.out_mode != OUT_C8 && op.out_mode != OUT_C8_SHUFFLE2 && op.out_mode != OUT_PLANAR_F32 &&
+        op.out_mode != OUT_OM24)
+        return false;
+    const int mode = op.out_mode == OUT_OM24 ? 2 : 0;
+    if (mode == 2 && (op.ks != 3 || op.stride != 1 || op.dg <= 0 || op.Cout != 27 * op.dg)) return false;
     if (op.residual != nullptr && op.out_mode != OUT_C8) return false;
     const int C = op.src[0].C;
     for (int i = 0; i < op.nsrc; ++i)
         if (op.src[i].C != C) return false;
     if (C % 16 != 0 || C > 64) return false;
-    pl.NT = tc_pick_nt(op.Cout);
+    pl.NT = tc_pick_nt(op.Cout, mode);
     if (pl.NT == 0) return false;
     if (op.out_mode == OUT_C8_SHUFFLE2 && (pl.NT % 64 != 0 || op.Cout % pl.NT != 0)) return false;
-    pl.passes = tc_passes(op.Cout, pl.NT);
+    pl.passes = tc_passes(op.Cout, pl.NT, mode);
     pl.KS = op.ks;
     pl.C8s = C / 8;
     const size_t wb = (size_t)op.nsrc * pl.C8s * op.ks * op.ks * pl.NT * 16;
@@ -611,7 +665,7 @@ int launch_conv_tc(const ConvOp &op, cudaStream_t s) {
     p.out = op.out; p.out_image_stride = op.out_image_stride;
     p.residual = reinterpret_cast<const __half *>(op.residual); p.res_image_stride = op.res_image_stride;
     p.N = op.N; p.H = op.H; p.W = op.W; p.Cout = op.Cout; p.act = op.act; p.out_mode = op.out_mode;
-    p.sig_from = op.sig_from; p.subsample = op.stride == 2 ? 1 : 0;
+    p.sig_from = op.sig_from; p.subsample = op.stride == 2 ? 1 : 0; p.dg = op.dg;
     const int valid = TC_TW - (op.ks - 1);
     p.tiles_x = cdiv(op.W, valid); p.tiles_y = cdiv(op.H, TC_ROWS);
     p.num_tiles = p.tiles_x * p.tiles_y * op.N;
@@ -621,7 +675,7 @@ int launch_conv_tc(const ConvOp &op, cudaStream_t s) {
     const int sms = sm_count();
 #define RVSR_TC_CASE(KS_, NT_) \
     if (op.ks == KS_ && pl.NT == NT_) return launch_conv_tc_t<KS_, NT_>(p, pl, sms, s);
-    RVSR_TC_CASE(3, 16) RVSR_TC_CASE(3, 64) RVSR_TC_CASE(3, 112) RVSR_TC_CASE(3, 128)
+    RVSR_TC_CASE(3, 16) RVSR_TC_CASE(3, 64) RVSR_TC_CASE(3, 128)
     RVSR_TC_CASE(1, 16) RVSR_TC_CASE(1, 64) RVSR_TC_CASE(1, 128)
 #undef RVSR_TC_CASE
     set_error("tc conv: no kernel instance for ks=%d NT=%d", op.ks, pl.NT);
@@ -632,8 +686,8 @@ int launch_conv_tc(const ConvOp &op, cudaStream_t s) {
 struct TcDcnParams {
     const __half *x;
     long long x_image_stride;
-    const float *offset, *mask;
-    long long off_stride, mask_stride;
+    const uint4 *om;          // OUT_OM24 offsets + mask
+    long long om_stride;      // uint4 units per image
     const __half *w;
     const float *bias;
     __half *out;
@@ -716,16 +770,22 @@ __global__ void __launch_bounds__(DCN_THREADS, 1) dcn_tc_kernel(const __grid_con
             const bool valid = y < p.H && x < p.W;
             const long long pix = valid ? (long long)y * p.W + x : 0;
             const __half *xb = p.x + (long long)n * p.x_image_stride;
-            const float *off[2], *msk[2];
+            // offsets / mask of this pixel's two deformable groups (OUT_OM24): 3 blocks of 32 B per group
+            const uint4 *om[2];
+            uint32_t cur[2][8], mw[2][5];
+            float dy8[2], dx8[2];
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 const int g = ((qq + 4 * i) * 8) / p.cpg;
-                off[i] = p.offset + (long long)n * p.off_stride + (long long)g * 18 * plane + pix;
-                msk[i] = p.mask + (long long)n * p.mask_stride + (long long)g * 9 * plane + pix;
+                om[i] = p.om + (long long)n * p.om_stride + ((long long)(g * 3) * plane + pix) * 2;
+                const uint4 a = __ldg(om[i]), b = __ldg(om[i] + 1);                       // taps 0..3
+                const uint4 c2 = __ldg(om[i] + 4 * plane), d2 = __ldg(om[i] + 4 * plane + 1);  // dy8 dx8 + masks
+                cur[i][0] = a.x; cur[i][1] = a.y; cur[i][2] = a.z; cur[i][3] = a.w;
+                cur[i][4] = b.x; cur[i][5] = b.y; cur[i][6] = b.z; cur[i][7] = b.w;
+                dy8[i] = __uint_as_float(c2.x); dx8[i] = __uint_as_float(c2.y);
+                mw[i][0] = c2.z; mw[i][1] = c2.w; mw[i][2] = d2.x; mw[i][3] = d2.y; mw[i][4] = d2.z;
             }
-            float dy[2], dx[2], mk[2];
-#pragma unroll
-            for (int i = 0; i < 2; ++i) { dy[i] = __ldg(off[i]); dx[i] = __ldg(off[i] + plane); mk[i] = __ldg(msk[i]); }
+#pragma unroll 1
             for (int tap = 0; tap < K; ++tap, ++it) {
                 const int st = it % S;
                 const float by = (float)(y - 1 + tap / 3), bx = (float)(x - 1 + tap % 3);
@@ -733,12 +793,15 @@ __global__ void __launch_bounds__(DCN_THREADS, 1) dcn_tc_kernel(const __grid_con
                 float w[2][4];
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    const float py = by + dy[i], px = bx + dx[i];
+                    const float dy = __uint_as_float(cur[i][0]), dx = __uint_as_float(cur[i][1]);
+                    const __half2 mh = *reinterpret_cast<const __half2 *>(&mw[i][0]);
+                    const float mk = (tap & 1) ? __high2float(mh) : __low2float(mh);
+                    const float py = by + dy, px = bx + dx;
                     const bool inside = valid && py > -1.f && px > -1.f && py < Hf && px < Wf;
                     const float fy = floorf(inside ? py : 0.f), fx = floorf(inside ? px : 0.f);
                     const int y0 = (int)fy, x0 = (int)fx;
                     const float ly = py - fy, lx = px - fx, hy = 1.f - ly, hx = 1.f - lx;
-                    const float m_in = inside ? mk[i] : 0.f;                 // mask folded into the weights
+                    const float m_in = inside ? mk : 0.f;                 // mask folded into the weights
                     const float wy0 = y0 >= 0 ? hy * m_in : 0.f, wy1 = y0 + 1 <= p.H - 1 ? ly * m_in : 0.f;
                     const float wx0 = x0 >= 0 ? hx : 0.f, wx1 = x0 + 1 <= p.W - 1 ? lx : 0.f;
                     w[i][0] = wy0 * wx0; w[i][1] = wy0 * wx1; w[i][2] = wy1 * wx0; w[i][3] = wy1 * wx1;
@@ -747,12 +810,22 @@ __global__ void __launch_bounds__(DCN_THREADS, 1) dcn_tc_kernel(const __grid_con
                     c[i][0] = __ldg(pl + y0c * p.W + x0c); c[i][1] = __ldg(pl + y0c * p.W + x1c);
                     c[i][2] = __ldg(pl + y1c * p.W + x0c); c[i][3] = __ldg(pl + y1c * p.W + x1c);
                 }
-                if (tap + 1 < K) {
+                // advance the per-group offset / mask shift registers to the next tap
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        dy[i] = __ldg(off[i] + (long long)(2 * tap + 2) * plane);
-                        dx[i] = __ldg(off[i] + (long long)(2 * tap + 3) * plane);
-                        mk[i] = __ldg(msk[i] + (long long)(tap + 1) * plane);
+                for (int i = 0; i < 2; ++i) {
+                    if (tap == 3) {  // taps 4..7 live in the second 32 B block
+                        const uint4 a = __ldg(om[i] + 2 * plane), b = __ldg(om[i] + 2 * plane + 1);
+                        cur[i][0] = a.x; cur[i][1] = a.y; cur[i][2] = a.z; cur[i][3] = a.w;
+                        cur[i][4] = b.x; cur[i][5] = b.y; cur[i][6] = b.z; cur[i][7] = b.w;
+                    } else if (tap == 7) {
+                        cur[i][0] = __float_as_uint(dy8[i]); cur[i][1] = __float_as_uint(dx8[i]);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) cur[i][k] = cur[i][k + 2];
+                    }
+                    if (tap & 1) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) mw[i][k] = mw[i][k + 1];
                     }
                 }
                 uint4 pk[2];
@@ -784,7 +857,7 @@ __global__ void __launch_bounds__(DCN_THREADS, 1) dcn_tc_kernel(const __grid_con
         }
     } else {
         const int lq = warp & 3;
-        EpiArgs e{bias_s, p.out, p.out_image_stride, nullptr, 0, p.H, p.W, NT, p.act, OUT_C8, 0, 0};
+        EpiArgs e{bias_s, p.out, p.out_image_stride, nullptr, 0, p.H, p.W, NT, p.act, OUT_C8, 0, 0, 0};
         EpiTile<NT, 1> ep;
         ep.has_res = false;
         uint32_t t = 0;
@@ -811,7 +884,7 @@ bool tc_dcn_supported(const DcnOp &op) {
     if (op.stride != 1 || op.pad != 1 || op.dil != 1 || op.out_mode != OUT_C8) return false;
     const int cpg = op.x.C / op.dg;
     if (cpg * op.dg != 64 || cpg % 8 != 0) return false;
-    if (op.x.fixed_frame >= 0) return false;
+    if (op.x.fixed_frame >= 0 || op.om24 == nullptr) return false;
     return true;
 }
 
@@ -819,7 +892,7 @@ int launch_dcn_tc(const DcnOp &op, cudaStream_t s) {
     RVSR_CHECK_ARG(tc_dcn_supported(op), "tc dcn: unsupported configuration");
     TcDcnParams p;
     p.x = reinterpret_cast<const __half *>(op.x.ptr); p.x_image_stride = op.x.image_stride;
-    p.offset = op.offset; p.mask = op.mask; p.off_stride = op.offset_image_stride; p.mask_stride = op.mask_image_stride;
+    p.om = reinterpret_cast<const uint4 *>(op.om24); p.om_stride = op.om24_image_stride / 4;
     p.w = reinterpret_cast<const __half *>(op.w_tc); p.bias = op.bias;
     p.out = reinterpret_cast<__half *>(op.out); p.out_image_stride = op.out_image_stride;
     p.N = op.N; p.H = op.H; p.W = op.W; p.cpg = op.x.C / op.dg; p.act = op.act;

@@ -45,3 +45,32 @@ def conv2d_fused(x, weight, bias=None, x2=None, residual=None, stride=1, act=Non
                                      ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)),
                    "conv2d_fused")
     return y
+
+
+def mdcn_pack(x, feat, w_offset_mask, b_offset_mask, weight, bias, deformable_groups, act=None):
+    """ModulatedDeformConvPack.forward with extra_offset_mask=True (reference dcn/deform_conv.py:274-292)
+    as ONE operator: conv_offset_mask(feat) -> split / sigmoid -> modulated deformable 3x3 conv of x
+    (+ optional activation).  fp16 inputs with 64 channels run the tcgen05 kernel pair (offsets and
+    mask never leave the fused format); everything else the CUDA-core kernels."""
+    if not x.is_cuda:
+        raise NotImplementedError("realvsr_b200.ops.mdcn_pack: CUDA tensors only (no CPU fallback)")
+    if x.dtype not in (torch.float32, torch.float16):
+        raise RuntimeError("mdcn_pack: float32/float16 only")
+    dt = _lib.F16 if x.dtype == torch.float16 else _lib.F32
+    x, feat = x.contiguous(), feat.to(x.dtype).contiguous()
+    B, C, H, W = x.shape
+    Cout = weight.shape[0]
+    if tuple(w_offset_mask.shape) != (27 * deformable_groups, C, 3, 3) or tuple(weight.shape[1:]) != (C, 3, 3):
+        raise RuntimeError("mdcn_pack: expects 3x3 kernels, conv_offset_mask with 27*deformable_groups outputs")
+    y = x.new_empty(B, Cout, H, W)
+    L = _lib.lib()
+    cast = lambda t: None if t is None else t.to(x.dtype).contiguous()  # noqa: E731
+    wom, bom, w, b = cast(w_offset_mask), cast(b_offset_mask), cast(weight), cast(bias)
+    with torch.cuda.device(x.device):
+        ws = torch.empty(max(1, L.rvsr_mdcn_pack_fwd_workspace_bytes(B, C, H, W, Cout, deformable_groups, dt)),
+                         dtype=torch.uint8, device=x.device)
+        _lib.check(L.rvsr_mdcn_pack_fwd(_p(x), _p(feat), _p(wom), _p(bom), _p(w), _p(b), _p(y), B, C, H, W, Cout,
+                                        deformable_groups, ACT[act], dt, _p(ws), ws.numel(),
+                                        ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)),
+                   "mdcn_pack")
+    return y

@@ -112,3 +112,68 @@ def test_mdcn_fwd_vs_reference_cuda_extension():
     # the reference GEMM (cuBLAS addmm_) may run in TF32; both sides only agree to ~1e-3
     assert rel_err(y, out_ref) < 1e-3
     assert rel_err(out_ref.cpu(), O.dcn_forward(x, off, msk, w, b, s, p, d, g, dg)) < 1e-3
+
+
+# ---------------------------------------------------------------- fused pack operator (rvsr_mdcn_pack_fwd)
+def _pack_case(B, C, H, W, Cout, dg, seed=500, off_w=0.05, off_b=1.0):
+    x = synth_normal((B, C, H, W), seed)
+    feat = synth_normal((B, C, H, W), seed + 1)
+    wom = synth_normal((27 * dg, C, 3, 3), seed + 2, std=off_w)
+    bom = synth_normal((27 * dg,), seed + 3, std=off_b)
+    w = synth_normal((Cout, C, 3, 3), seed + 4, std=(1.0 / (C * 9)) ** 0.5)
+    b = synth_normal((Cout,), seed + 5, std=0.3)
+    return x, feat, wom, bom, w, b
+
+
+def _pack_ref(x, feat, wom, bom, w, b, dg, act):
+    om = torch.nn.functional.conv2d(feat, wom, bom, padding=1)
+    off, msk = om[:, :18 * dg].contiguous(), torch.sigmoid(om[:, 18 * dg:]).contiguous()
+    y = O.dcn_forward(x, off, msk, w, b, 1, 1, 1, 1, dg)
+    return torch.nn.functional.leaky_relu(y, 0.1) if act == "lrelu" else y
+
+
+PACK_CASES = [dict(B=2, C=64, H=20, W=36, Cout=64, dg=8), dict(B=1, C=64, H=9, W=70, Cout=64, dg=8, off_b=3.0),
+              dict(B=1, C=64, H=16, W=32, Cout=64, dg=4), dict(B=1, C=16, H=12, W=12, Cout=16, dg=4),
+              dict(B=1, C=64, H=12, W=16, Cout=64, dg=1)]
+
+
+@pytest.mark.parametrize("cfg", PACK_CASES)
+@pytest.mark.parametrize("act", [None, "lrelu"])
+def test_mdcn_pack_fp32_vs_oracle(cfg, act):
+    from realvsr_b200 import ops
+    dg = cfg["dg"]
+    t = _pack_case(**cfg)
+    ref = _pack_ref(*t, dg, act)
+    y = ops.mdcn_pack(*[v.to(DEV) for v in t], dg, act=act)
+    assert rel_err(y.cpu(), ref) < 1e-4
+
+
+@pytest.mark.parametrize("cfg", PACK_CASES)
+def test_mdcn_pack_fp16_vs_oracle(cfg):
+    """64-channel cases run the tcgen05 pair (offset conv -> OUT_OM24 -> gather + UMMA).
+    Tolerance 4e-3: fp16 storage of x / weights / output, masks stored as fp16; offsets stay fp32."""
+    from realvsr_b200 import ops
+    dg = cfg["dg"]
+    t = [v.half().float() for v in _pack_case(**cfg)]
+    ref = _pack_ref(*t, dg, "lrelu")
+    y = ops.mdcn_pack(*[v.to(DEV).half() for v in t], dg, act="lrelu")
+    assert y.dtype == torch.float16
+    assert rel_err(y.float().cpu(), ref) < 4e-3
+
+
+def test_dcn_pack_module_inference_uses_fused_operator():
+    m = D.ModulatedDeformConvPack(64, 64, 3, stride=1, padding=1, dilation=1, deformable_groups=8,
+                                  extra_offset_mask=True).to(DEV)
+    torch.nn.init.normal_(m.conv_offset_mask.weight, std=0.05)
+    torch.nn.init.normal_(m.conv_offset_mask.bias, std=1.0)
+    x, feat = synth_normal((1, 64, 16, 24), 900).to(DEV), synth_normal((1, 64, 16, 24), 901).to(DEV)
+    with torch.no_grad():
+        y_fused = m([x, feat])
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False  # cuDNN's default TF32 convs are only ~1e-3 accurate
+    try:
+        with torch.enable_grad():  # autograd on -> unfused graph (torch conv + our DCN op)
+            y_graph = m([x, feat]).detach()
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    assert rel_err(y_fused, y_graph) < 1e-4
