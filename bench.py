@@ -4,8 +4,10 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
 
 A "step" is one pass of the hot path (rvsr_engine_forward) over one batch of B synthetic
-5x3x180x320 LQ windows per GPU -> B 3x720x1280 frames (BASELINE cfg2: full 64-ch PCD + TSA +
-10 ResBlocks, fp16 storage / fp32 accumulate).  One process per GPU; windows are independent,
+5x3x180x320 LQ windows per GPU -> B 3x720x1280 frames (BASELINE cfg2 window and network: full
+64-ch PCD + TSA + 5/10 ResBlocks, fp16 storage / fp32 accumulate).  B defaults to 4, the per-GPU
+share of BASELINE cfg3 (32 sliding windows over 8 GPUs), so per-GPU work is the same at every N
+(weak scaling); the single-window (B=1) latency is reported alongside as `single_window`.  One process per GPU; windows are independent,
 so ranks shard them with no data-path collective ("weak" scaling: per-GPU work fixed).
 Rank 0 prints ONE JSON line.  See DESIGN.md section "Measurement" for every field.
 """
@@ -144,7 +146,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=1, help="windows per GPU per step")
+    ap.add_argument("--batch", type=int, default=4,
+                    help="windows per GPU per step (default 4 = BASELINE cfg3's per-GPU share: 32 windows / 8 GPUs)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -212,6 +215,20 @@ def main():
         e2e_s = time.perf_counter() - t0
         barrier()
 
+    # ---- single-window latency (B = 1), device time
+    with torch.no_grad():
+        x1 = clips[0][:1].contiguous()
+        for _ in range(3):
+            net(x1)
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(max(K, 10)):
+            net(x1)
+        s1.record()
+        torch.cuda.synchronize()
+        ms_b1 = s0.elapsed_time(s1) / max(K, 10)
+
     t = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -224,8 +241,9 @@ def main():
         with torch.no_grad():
             rows = eng.profile(clips[0], steps=3)
         agg = {}
-        for r in rows:
-            a = agg.setdefault(r["label"], dict(ms=0.0, flops=0.0, bytes=0.0, n=0))
+        for r in rows:  # label = family:shape-class:weight-name -> aggregate per kernel (family + shape class)
+            key = ":".join(r["label"].split(":")[:2])
+            a = agg.setdefault(key, dict(ms=0.0, flops=0.0, bytes=0.0, n=0))
             a["ms"] += r["ms"]; a["flops"] += r["flops"]; a["bytes"] += r["bytes"]; a["n"] += 1
         total_ms = sum(a["ms"] for a in agg.values())
         top = sorted(agg.items(), key=lambda kv: -kv[1]["ms"])
@@ -238,7 +256,11 @@ def main():
         else:
             ach = a["bytes"] / (a["ms"] * 1e-3) / 1e9
             roof = dict(bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"])
-        roof.update(traffic=None, kernel=name, launches_per_step=a["n"], ms_per_launch=a["ms"] / a["n"],
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # dram bytes per launch from the committed ncu capture
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(name)
+        roof.update(traffic=traffic, kernel=name, launches_per_step=a["n"], ms_per_launch=a["ms"] / a["n"],
                     share_of_step=a["ms"] / total_ms, peak_source=pk["src"] + (" sustained bf16" if roof["bound"] == "tensor" else " copy"),
                     algorithmic_per_launch=dict(gflop=a["flops"] / a["n"] / 1e9, mbytes=a["bytes"] / a["n"] / 1e6))
         kernels = [dict(kernel=k, ms=v["ms"], n=v["n"], tflops=(v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 else 0,
@@ -259,7 +281,8 @@ def main():
                              d2h_bytes_per_step=int(out_host.numel() * out_host.element_size()),
                              api="EDVREngine.forward_host -> rvsr_engine_forward_host (pinned host buffers)"),
                     gpu_launches=launches, clocks=clocks, roofline=roof, kernels=kernels,
-                    profile_sum_ms=total_ms)
+                    profile_sum_ms=total_ms,
+                    single_window=dict(ms=ms_b1, frames_per_s=1e3 / ms_b1, note="B=1 forward, rank 0, device time"))
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = cpu_sample(steps=2, warmup=1)
             line["cpu_baseline"] = cb

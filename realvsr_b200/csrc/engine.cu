@@ -297,7 +297,11 @@ template <typename T> struct Plan {
             rc = RVSR_E_STATE;
             return o;
         }
-        launch((tc ? "tc:" : "simt:") + name, flops, bytes, [&] { return tc ? launch_conv_tc(op, s) : launch_conv_simt<T>(op, s); });
+        // label = <kernel family>:<shape class>:<weight name>; bench.py aggregates by the first two fields
+        const std::string kind = std::string(tc ? "tc:" : "simt:") + "conv" + std::to_string(pc->ks) + "x" + std::to_string(pc->ks) +
+                                 (out_mode == OUT_OM24 ? "_om24" : (out_mode == OUT_PLANAR_F32 ? "_planar" : "")) + "_co" +
+                                 std::to_string(pc->Cout) + ":";
+        launch(kind + name, flops, bytes, [&] { return tc ? launch_conv_tc(op, s) : launch_conv_simt<T>(op, s); });
         return o;
     }
 
@@ -340,13 +344,14 @@ template <typename T> struct Plan {
             rc = RVSR_E_STATE;
             return o;
         }
-        launch((tc ? "tc:" : "simt:") + name, flops, bytes, [&] { return tc ? launch_dcn_tc(op, s) : launch_dcn_simt<T>(op, s); });
+        launch(std::string(tc ? "tc:" : "simt:") + "dcn_gather_mma:" + name, flops, bytes,
+               [&] { return tc ? launch_dcn_tc(op, s) : launch_dcn_simt<T>(op, s); });
         return o;
     }
     Act up2(const Act &a, float scale) {
         Act o = make(a.N, a.C, 2 * a.H, 2 * a.W);
         if (!dry && rc == RVSR_OK)
-            launch("glue:upsample2x", 0, (double)a.elems() * sizeof(T) * 5, [&] {
+            launch("glue:upsample2x:", 0, (double)a.elems() * sizeof(T) * 5, [&] {
                 return launch_upsample2x<T>((const T *)a.p, (T *)o.p, a.N, a.C, a.H, a.W, scale, s); });
         return o;
     }
@@ -354,7 +359,7 @@ template <typename T> struct Plan {
         mx = make(a.N, a.C, (a.H - 1) / 2 + 1, (a.W - 1) / 2 + 1);
         av = make(a.N, a.C, mx.H, mx.W);
         if (!dry && rc == RVSR_OK)
-            launch("glue:pool_maxavg", 0, (double)a.elems() * sizeof(T) * 1.5, [&] {
+            launch("glue:pool_maxavg:", 0, (double)a.elems() * sizeof(T) * 1.5, [&] {
                 return launch_pool_maxavg<T>((const T *)a.p, (T *)mx.p, (T *)av.p, a.N, a.C, a.H, a.W, s); });
     }
     Act resblocks(const std::string &prefix, int count, Act cur) {
@@ -384,7 +389,7 @@ int Engine::run(Arena &ar, bool dry, const void *x, int x_dtype, void *out, int 
     const int nc_store = (cfg_.precision == RVSR_F16 && nc < 16) ? 16 : nc;  // see finalize(): K granularity
     Act xin = P.make(NB, nc_store, H, W);
     if (!dry && P.rc == RVSR_OK)
-        P.launch("glue:pack_input", 0, (double)xin.elems() * sizeof(T) * 1.4, [&] {
+        P.launch("glue:pack_input:", 0, (double)xin.elems() * sizeof(T) * 1.4, [&] {
             return x_dtype == RVSR_F32
                        ? launch_pack_nchw<T, float>((const float *)x, (T *)xin.p, NB, nc, H, W, s, nc_store)
                        : launch_pack_nchw<T, __half>((const __half *)x, (T *)xin.p, NB, nc, H, W, s, nc_store); });
@@ -448,7 +453,7 @@ int Engine::run(Arena &ar, bool dry, const void *x, int x_dtype, void *out, int 
         Act emb = P.conv(t + "tAtt_1", {PT::src_of(aligned)}, NB, H, W, NONE);
         Act ali = P.make(NB, nf, H, W);
         if (!dry && P.rc == RVSR_OK)
-            P.launch("glue:tsa_temporal", 4.0 * ali.elems(), (double)ali.elems() * sizeof(T) * 4, [&] {
+            P.launch("glue:tsa_temporal:", 4.0 * ali.elems(), (double)ali.elems() * sizeof(T) * 4, [&] {
                 return launch_tsa_temporal<T>((const T *)emb.p, (const T *)emb_ref.p, (const T *)aligned.p,
                                               (T *)ali.p, B, N, nf, H, W, s); });
         Act fea = conv_frames(t + "fea_fusion", ali, LR);
@@ -470,7 +475,7 @@ int Engine::run(Arena &ar, bool dry, const void *x, int x_dtype, void *out, int 
         add = P.conv(t + "sAtt_add_2", {PT::src_of(add)}, B, H, W, NONE);
         fused = P.make(B, nf, H, W);
         if (!dry && P.rc == RVSR_OK)
-            P.launch("glue:tsa_final", 0, (double)fused.elems() * sizeof(T) * 4, [&] {
+            P.launch("glue:tsa_final:", 0, (double)fused.elems() * sizeof(T) * 4, [&] {
                 return launch_tsa_final<T>((const T *)fea.p, (const T *)att.p, (const T *)add.p, (T *)fused.p,
                                            fused.elems(), s); });
     } else {
@@ -489,7 +494,7 @@ int Engine::run(Arena &ar, bool dry, const void *x, int x_dtype, void *out, int 
     Act last = P.conv("conv_last", {PT::src_of(r)}, B, r.H, r.W, NONE);
     if (!dry && P.rc == RVSR_OK) {
         const T *lp = (const T *)last.p;
-        P.launch("glue:final_add_base", 0, (double)last.elems() * sizeof(T) + (double)B * nc * last.H * last.W * 4, [&] {
+        P.launch("glue:final_add_base:", 0, (double)last.elems() * sizeof(T) + (double)B * nc * last.H * last.W * 4, [&] {
             if (x_dtype == RVSR_F32 && out_dtype == RVSR_F32)
                 return launch_final_add<T, float, float>(lp, (const float *)x, (float *)out, B, N, ctr, nc, H, W, scale, s);
             if (x_dtype == RVSR_F32)

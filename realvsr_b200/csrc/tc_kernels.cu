@@ -339,8 +339,8 @@ template <int KS, int NT>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcConvParams p) {
     constexpr int KK = KS * KS, PAD = KS / 2, VALID = TC_TW - (KS - 1), HALO_ROWS = TC_ROWS + KS - 1;
     constexpr int PLANE_BYTES = HALO_ROWS * TC_TW * 16;
-    constexpr int ACC = acc_stride(NT), NB = NT <= 64 ? TC_ACC_BUFS : 2, TMEM_COLS = NB * ACC;
-    constexpr int MMAW = NT <= 64 ? 2 : 1;  // issuer warps: N <= 64 MMAs are too short for a single issuing thread
+    constexpr int ACC = acc_stride(NT), NB = TC_ACC_BUFS, TMEM_COLS = NB * ACC;
+    constexpr int MMAW = 2;  // issuer warps: one thread cannot issue tcgen05.mma fast enough to keep the pipe busy
     extern __shared__ __align__(1024) uint8_t smem[];
     const int Q = p.nsrc * p.C8s;  // channel blocks over all sources
     const uint32_t w_bytes = (uint32_t)Q * KK * NT * 16;

@@ -23,6 +23,6 @@ print("dbg=%s B=%d total %.3f ms" % (os.environ.get("RVSR_TC_DEBUG", "0"), B, to
 for w in want:
     for r in rows:
         if r["label"].endswith(w):
-            print("%s %.1fus" % (w.split(".")[-2][:6] + "." + w.split(".")[-1] if "." in w else w, r["ms"] * 1e3), end="  ")
+            print("%s %.1fus" % (w[-24:], r["ms"] * 1e3), end="  ")
             break
 print()

@@ -1,5 +1,8 @@
-"""Run a couple of cfg2 forwards (fp16 engine) -- the target command for ncu captures.
-    ncu ... python tools/prof_forward.py [n_forwards]"""
+"""Target command for ncu captures: cfg2 forwards on the fp16 engine.
+    ncu ... python tools/prof_forward.py [n_forwards] [batch]
+Also writes the ordered launch labels of one forward to gpurun_out/launch_labels.json so the ncu
+launch list (same order) can be joined with kernel classes."""
+import json
 import os
 import sys
 
@@ -16,10 +19,17 @@ net = E.EDVR(**CFG).eval()
 net.load_state_dict(synth_state_dict(edvr_state_shapes("EDVR", **CFG), 7), strict=True)
 net = net.to("cuda:0").half()
 net.exec_path = "engine"
-x = synth_input((1, 5, 3, 180, 320), 8).to("cuda:0").half()
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+x = synth_input((B, 5, 3, 180, 320), 8).to("cuda:0").half()
 with torch.no_grad():
     for _ in range(n):
         y = net(x)
 torch.cuda.synchronize()
+if os.environ.get("RVSR_DUMP_LABELS"):
+    with torch.no_grad():
+        rows = net._get_engine(x).profile(x, steps=1)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump([dict(label=r["label"], flops=r["flops"], bytes=r["bytes"]) for r in rows],
+              open(os.path.join(ROOT, "gpurun_out", "launch_labels.json"), "w"))
 print("ok", tuple(y.shape), float(y.float().abs().mean()))
