@@ -11,6 +11,7 @@ struct rvsr_engine {
 namespace rvsr {
 int expand_grouped_weight(const float *w, float *dst, int Cout, int C, int K, int groups, cudaStream_t s);
 
+
 namespace {
 struct Carver {  // carve the caller's workspace (or just count, when base == nullptr)
     char *base;
@@ -144,12 +145,58 @@ int rvsr_mdcn_fwd(const void *input, const void *offset, const void *mask, const
     return mdcn_fwd_t<float>(d, input, offset, mask, weight, bias, output, dtype, ws, RVSR_ACT_NONE, s);
 }
 
-size_t rvsr_mdcn_bwd_workspace_bytes(int, int, int, int, int, int, int, int, int, int, int, int, int) { return 0; }
-int rvsr_mdcn_bwd(const void *, const void *, const void *, const void *, const void *, void *, void *, void *,
-                  void *, void *, int, int, int, int, int, int, int, int, int, int, int, int, int, void *, size_t,
-                  void *) {
-    set_error("rvsr_mdcn_bwd: not built yet");
-    return RVSR_E_UNSUPPORTED;
+static size_t mdcn_bwd_ws(const DcnDims &d) {
+    size_t n = 2 * align_up((size_t)d.B * cdiv(d.C, 8) * d.H * d.W * 8 * 4, 256);   // x and grad_x channel-blocked
+    n += 2 * align_up((size_t)d.Cout * d.C * d.K * 4, 256);                        // dense weight + dense grad
+    return n + 1024;
+}
+size_t rvsr_mdcn_bwd_workspace_bytes(int B, int C, int H, int W, int Cout, int kh, int kw, int stride, int pad, int dil,
+                                     int groups, int dg, int dtype) {
+    DcnDims d;
+    if (dtype != RVSR_F32 || dcn_dims(d, B, C, H, W, Cout, kh, kw, stride, pad, dil, groups, dg) != RVSR_OK) return 0;
+    return mdcn_bwd_ws(d);
+}
+int rvsr_mdcn_bwd(const void *input, const void *offset, const void *mask, const void *weight, const void *grad_output,
+                  void *grad_input, void *grad_offset, void *grad_mask, void *grad_weight, void *grad_bias, int B, int C,
+                  int H, int W, int Cout, int kh, int kw, int stride, int pad, int dil, int groups, int dg, int dtype,
+                  void *workspace, size_t workspace_bytes, void *stream) {
+    DcnDims d;
+    RVSR_TRY(dcn_dims(d, B, C, H, W, Cout, kh, kw, stride, pad, dil, groups, dg));
+    if (dtype != RVSR_F32) {
+        set_error("rvsr_mdcn_bwd: gradients are computed in fp32 (convert on the host side)");
+        return RVSR_E_UNSUPPORTED;
+    }
+    if (B == 0) return RVSR_OK;
+    RVSR_CHECK_ARG(input && offset && mask && weight && grad_output && grad_input && grad_offset && grad_mask &&
+                       grad_weight && workspace, "dcn bwd: null buffer");
+    Carver cv{(char *)workspace, workspace_bytes};
+    const size_t mis = (size_t)((uintptr_t)workspace % 256);
+    if (mis) { cv.base += 256 - mis; cv.cap -= 256 - mis; }
+    const size_t c8e = (size_t)d.B * cdiv(d.C, 8) * d.H * d.W * 8;
+    float *x8 = (float *)cv.take(c8e * 4), *gx8 = (float *)cv.take(c8e * 4);
+    float *wd = (float *)cv.take((size_t)d.Cout * d.C * d.K * 4), *gwd = (float *)cv.take((size_t)d.Cout * d.C * d.K * 4);
+    if (!cv.ok) { set_error("dcn bwd: workspace too small"); return RVSR_E_WORKSPACE; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t po = (size_t)d.Ho * d.Wo;
+    RVSR_TRY((launch_pack_nchw<float, float>((const float *)input, x8, d.B, d.C, d.H, d.W, s)));
+    RVSR_CUDA(cudaMemsetAsync(gx8, 0, c8e * 4, s));
+    RVSR_CUDA(cudaMemsetAsync(gwd, 0, (size_t)d.Cout * d.C * d.K * 4, s));
+    RVSR_CUDA(cudaMemsetAsync(grad_offset, 0, (size_t)d.B * d.dg * 2 * d.K * po * 4, s));
+    RVSR_CUDA(cudaMemsetAsync(grad_mask, 0, (size_t)d.B * d.dg * d.K * po * 4, s));
+    const float *w = (const float *)weight;
+    if (d.groups > 1) {
+        RVSR_TRY(expand_grouped_weight(w, wd, d.Cout, d.C, d.K, d.groups, s));
+        w = wd;
+    }
+    DcnBwdOp op = {};
+    op.x_c8 = x8; op.offset = (const float *)offset; op.mask = (const float *)mask; op.gout = (const float *)grad_output;
+    op.w_dense = w; op.gx_c8 = gx8; op.goffset = (float *)grad_offset; op.gmask = (float *)grad_mask; op.gw_dense = gwd;
+    op.gbias = (float *)grad_bias;
+    op.N = d.B; op.C = d.C; op.H = d.H; op.W = d.W; op.Cout = d.Cout; op.kh = d.kh; op.kw = d.kw; op.stride = d.stride;
+    op.pad = d.pad; op.dil = d.dil; op.dg = d.dg;
+    RVSR_TRY(launch_dcn_bwd_simt(op, s));
+    RVSR_TRY(fold_grouped_weight(gwd, (float *)grad_weight, d.Cout, d.C, d.K, d.groups, s));
+    return launch_unpack_nchw<float, float>(gx8, (float *)grad_input, d.B, d.C, d.H, d.W, s);
 }
 
 size_t rvsr_mdcn_pack_fwd_workspace_bytes(int B, int C, int H, int W, int Cout, int dg, int dtype) {

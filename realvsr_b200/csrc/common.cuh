@@ -188,6 +188,20 @@ struct DcnOp {
     int act, out_mode;
 };
 
+// DCN backward (fp32, CUDA-core): one launch produces all five gradients
+struct DcnBwdOp {
+    const float *x_c8;                  // [N][C8][H][W][8]
+    const float *offset, *mask, *gout;  // NCHW planar fp32
+    const float *w_dense;               // [Cout][C][K] (conv groups expanded to dense)
+    float *gx_c8;                       // [N][C8][H][W][8], zeroed by the caller
+    float *goffset, *gmask;             // NCHW planar, zeroed by the caller
+    float *gw_dense;                    // [Cout][C][K], accumulated into
+    float *gbias;                       // [Cout] or null, accumulated into
+    int N, C, H, W, Cout, kh, kw, stride, pad, dil, dg;
+};
+int launch_dcn_bwd_simt(const DcnBwdOp &op, cudaStream_t s);
+int fold_grouped_weight(const float *gd, float *gw, int Cout, int C, int K, int groups, cudaStream_t s);
+
 // ---------------------------------------------------------------- kernel launchers (simt_kernels.cu)
 template <typename T> int launch_conv_simt(const ConvOp &op, cudaStream_t s);
 template <typename T> int launch_dcn_simt(const DcnOp &op, cudaStream_t s);

@@ -645,3 +645,214 @@ int expand_grouped_weight(const float *w, float *dst, int Cout, int C, int K, in
     return RVSR_OK;
 }
 }  // namespace rvsr
+
+// ---------------------------------------------------------------- modulated deformable conv, backward (fp32)
+// Reference: modulated_deform_conv_cuda_backward (deform_conv_cuda.cpp:571-685) with its three kernels
+// (deform_conv_cuda_kernel.cu:635-767) and three GEMMs per sample.  Here one kernel per
+// (64-pixel tile, 8-channel block): it rebuilds the tile's modulated samples, forms
+// grad_col = W^T . grad_out for the tile in shared memory, and from that produces grad_input (atomic
+// scatter to <= 4 corners), grad_offset / grad_mask (atomic: several channel blocks can share a
+// deformable group), grad_weight (tile-local grad_out . col^T, then atomics) and grad_bias.
+// No columns buffer, no per-sample loop.  Summation order is nondeterministic like the reference's
+// atomicAdd col2im (deform_conv_cuda_kernel.cu:688).
+namespace rvsr {
+
+template <int K>
+__global__ void __launch_bounds__(NTHREADS) dcn_bwd_simt_kernel(const DcnBwdOp op) {
+    constexpr int ROWS = K * 8, RP = 5, CO = 64;  // rows per thread group (16 groups x 5 >= 72)
+    extern __shared__ __align__(16) float sm[];
+    float(*col)[TILE_P + 1] = reinterpret_cast<float(*)[TILE_P + 1]>(sm);                       // m * sample
+    float(*gcol)[TILE_P + 1] = reinterpret_cast<float(*)[TILE_P + 1]>(sm + ROWS * (TILE_P + 1));
+    float(*go)[TILE_P + 1] = reinterpret_cast<float(*)[TILE_P + 1]>(sm + 2 * ROWS * (TILE_P + 1));  // [CO][px]
+    float(*wt)[ROWS + 1] = reinterpret_cast<float(*)[ROWS + 1]>(sm + (2 * ROWS + CO) * (TILE_P + 1));  // [CO][row]
+    const int Ho = (op.H + 2 * op.pad - (op.dil * (op.kh - 1) + 1)) / op.stride + 1;
+    const int Wo = (op.W + 2 * op.pad - (op.dil * (op.kw - 1) + 1)) / op.stride + 1;
+    const int ntx = (Wo + TILE_W - 1) / TILE_W;
+    const int ox0 = (blockIdx.x % ntx) * TILE_W, oy0 = (blockIdx.x / ntx) * TILE_H;
+    const int q = blockIdx.y, n = blockIdx.z;
+    const int C = op.C, C8 = (C + 7) / 8, cpg = C / op.dg;
+    const long long plane = (long long)Ho * Wo, iplane = (long long)op.H * op.W;
+    const float *xq = op.x_c8 + ((long long)n * C8 + q) * iplane * 8;
+    float *gxq = op.gx_c8 + ((long long)n * C8 + q) * iplane * 8;
+    const float *off = op.offset + (long long)n * op.dg * 2 * K * plane;
+    const float *msk = op.mask + (long long)n * op.dg * K * plane;
+    const float *gout = op.gout + (long long)n * op.Cout * plane;
+
+    // 1. modulated samples of this tile / channel block (same producer as the forward kernel)
+    for (int i = threadIdx.x; i < TILE_P * K; i += NTHREADS) {
+        const int p = i % TILE_P, t = i / TILE_P;
+        const int oy = oy0 + p / TILE_W, ox = ox0 + p % TILE_W;
+        float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (oy < Ho && ox < Wo) {
+            const long long pix = (long long)oy * Wo + ox;
+            const float by = (float)(oy * op.stride - op.pad + (t / op.kw) * op.dil);
+            const float bx = (float)(ox * op.stride - op.pad + (t % op.kw) * op.dil);
+            int gprev = -1;
+            float m = 0.f, v[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int ch = q * 8 + c;
+                if (ch >= C) break;
+                const int g = ch / cpg;
+                if (g != gprev) {
+                    gprev = g;
+                    m = __ldg(msk + ((long long)g * K + t) * plane + pix);
+                    sample8<float>(xq, op.H, op.W, by + __ldg(off + ((long long)g * 2 * K + 2 * t) * plane + pix),
+                                   bx + __ldg(off + ((long long)g * 2 * K + 2 * t + 1) * plane + pix), v);
+                }
+                r[c] = m * v[c];
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) col[t * 8 + c][p] = r[c];
+    }
+    // 2. loop over output-channel slices: grad_col += W^T gout ; grad_weight += gout col^T ; grad_bias
+    const int pg = threadIdx.x % 16, rg = threadIdx.x / 16;
+    float acc[RP][4] = {};
+    for (int cs = 0; cs < op.Cout; cs += CO) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < CO * TILE_P; i += NTHREADS) {
+            const int o = i / TILE_P, p = i % TILE_P;
+            const int oy = oy0 + p / TILE_W, ox = ox0 + p % TILE_W;
+            go[o][p] = (cs + o < op.Cout && oy < Ho && ox < Wo) ? __ldg(gout + (long long)(cs + o) * plane + (long long)oy * Wo + ox) : 0.f;
+        }
+        for (int i = threadIdx.x; i < CO * ROWS; i += NTHREADS) {
+            const int o = i / ROWS, r = i % ROWS, t = r / 8, ch = q * 8 + r % 8;
+            wt[o][r] = (cs + o < op.Cout && ch < C) ? __ldg(op.w_dense + ((long long)(cs + o) * C + ch) * K + t) : 0.f;
+        }
+        __syncthreads();
+        for (int o = 0; o < CO; ++o) {
+            float a[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a[k] = go[o][pg * 4 + k];
+#pragma unroll
+            for (int j = 0; j < RP; ++j) {
+                const int r = rg * RP + j;
+                const float w = r < ROWS ? wt[o][r] : 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc[j][k] = fmaf(w, a[k], acc[j][k]);
+            }
+        }
+        // grad_weight: thread -> 4 output channels x 5 rows, reduce over the tile's 64 pixels
+        {
+            const int og = threadIdx.x / 16, rr = threadIdx.x % 16;
+            float gw[4][RP] = {};
+            for (int p = 0; p < TILE_P; ++p) {
+                float cv[RP];
+#pragma unroll
+                for (int j = 0; j < RP; ++j) cv[j] = rr * RP + j < ROWS ? col[rr * RP + j][p] : 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float g = go[og * 4 + i][p];
+#pragma unroll
+                    for (int j = 0; j < RP; ++j) gw[i][j] = fmaf(g, cv[j], gw[i][j]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < RP; ++j) {
+                    const int o = cs + og * 4 + i, r = rr * RP + j;
+                    if (o < op.Cout && r < ROWS && q * 8 + r % 8 < C && gw[i][j] != 0.f)
+                        atomicAdd(op.gw_dense + ((long long)o * C + q * 8 + r % 8) * K + r / 8, gw[i][j]);
+                }
+        }
+        if (q == 0 && op.gbias != nullptr && threadIdx.x < CO && cs + threadIdx.x < op.Cout) {
+            float sb = 0.f;
+            for (int p = 0; p < TILE_P; ++p) sb += go[threadIdx.x][p];
+            atomicAdd(op.gbias + cs + threadIdx.x, sb);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < RP; ++j)
+        if (rg * RP + j < ROWS)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) gcol[rg * RP + j][pg * 4 + k] = acc[j][k];
+    __syncthreads();
+    // 3. scatter: per (pixel, tap) walk the block's channels; coordinates once per deformable group
+    for (int i = threadIdx.x; i < TILE_P * K; i += NTHREADS) {
+        const int p = i % TILE_P, t = i / TILE_P;
+        const int oy = oy0 + p / TILE_W, ox = ox0 + p % TILE_W;
+        if (oy >= Ho || ox >= Wo) continue;
+        const long long pix = (long long)oy * Wo + ox;
+        const float by = (float)(oy * op.stride - op.pad + (t / op.kw) * op.dil);
+        const float bx = (float)(ox * op.stride - op.pad + (t % op.kw) * op.dil);
+        int c = 0;
+        while (c < 8 && q * 8 + c < C) {
+            const int g = (q * 8 + c) / cpg;
+            int cend = c;
+            while (cend < 8 && q * 8 + cend < C && (q * 8 + cend) / cpg == g) ++cend;
+            const long long oc = ((long long)g * 2 * K + 2 * t) * plane + pix, mc = ((long long)g * K + t) * plane + pix;
+            const float py = by + __ldg(off + oc), px = bx + __ldg(off + oc + plane), m = __ldg(msk + mc);
+            if (py > -1.f && px > -1.f && py < (float)op.H && px < (float)op.W) {
+                const float fy = floorf(py), fx = floorf(px);
+                const int y0 = (int)fy, x0 = (int)fx, y1 = y0 + 1, x1 = x0 + 1;
+                const float ly = py - fy, lx = px - fx, hy = 1.f - ly, hx = 1.f - lx;
+                const bool vy0 = y0 >= 0, vy1 = y1 <= op.H - 1, vx0 = x0 >= 0, vx1 = x1 <= op.W - 1;
+                float v00[8] = {}, v01[8] = {}, v10[8] = {}, v11[8] = {};
+                if (vy0 && vx0) load8<float>(xq + ((long long)y0 * op.W + x0) * 8, v00);
+                if (vy0 && vx1) load8<float>(xq + ((long long)y0 * op.W + x1) * 8, v01);
+                if (vy1 && vx0) load8<float>(xq + ((long long)y1 * op.W + x0) * 8, v10);
+                if (vy1 && vx1) load8<float>(xq + ((long long)y1 * op.W + x1) * 8, v11);
+                float g_dy = 0.f, g_dx = 0.f, g_m = 0.f;
+                for (int cc = c; cc < cend; ++cc) {
+                    const float gc = gcol[t * 8 + cc][p];
+                    const float val = hy * (hx * v00[cc] + lx * v01[cc]) + ly * (hx * v10[cc] + lx * v11[cc]);
+                    g_m += gc * val;
+                    g_dy += gc * m * (hx * (v10[cc] - v00[cc]) + lx * (v11[cc] - v01[cc]));
+                    g_dx += gc * m * (hy * (v01[cc] - v00[cc]) + ly * (v11[cc] - v10[cc]));
+                    const float gm = gc * m;
+                    if (vy0 && vx0) atomicAdd(gxq + ((long long)y0 * op.W + x0) * 8 + cc, gm * hy * hx);
+                    if (vy0 && vx1) atomicAdd(gxq + ((long long)y0 * op.W + x1) * 8 + cc, gm * hy * lx);
+                    if (vy1 && vx0) atomicAdd(gxq + ((long long)y1 * op.W + x0) * 8 + cc, gm * ly * hx);
+                    if (vy1 && vx1) atomicAdd(gxq + ((long long)y1 * op.W + x1) * 8 + cc, gm * ly * lx);
+                }
+                atomicAdd(op.goffset + (long long)n * op.dg * 2 * K * plane + oc, g_dy);
+                atomicAdd(op.goffset + (long long)n * op.dg * 2 * K * plane + oc + plane, g_dx);
+                atomicAdd(op.gmask + (long long)n * op.dg * K * plane + mc, g_m);
+            }
+            c = cend;
+        }
+    }
+}
+
+// dense [Cout][C][K] gradient -> grouped [Cout][C/groups][K], accumulated
+__global__ void fold_grouped_weight_kernel(const float *__restrict__ gd, float *__restrict__ gw, int Cout, int C, int K,
+                                           int groups, long long total) {
+    const int cin_g = C / groups, cout_g = Cout / groups;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i % K);
+        const int cl = (int)((i / K) % cin_g);
+        const int co = (int)(i / ((long long)K * cin_g));
+        gw[i] += gd[((long long)co * C + (co / cout_g) * cin_g + cl) * K + t];
+    }
+}
+
+int launch_dcn_bwd_simt(const DcnBwdOp &op, cudaStream_t s) {
+    const int K = op.kh * op.kw;
+    RVSR_CHECK_ARG(K == 9 || K == 1, "dcn bwd: only 3x3 and 1x1 kernels are built");
+    const int Ho = (op.H + 2 * op.pad - (op.dil * (op.kh - 1) + 1)) / op.stride + 1;
+    const int Wo = (op.W + 2 * op.pad - (op.dil * (op.kw - 1) + 1)) / op.stride + 1;
+    dim3 grid(cdiv(Wo, TILE_W) * cdiv(Ho, TILE_H), cdiv(op.C, 8), op.N);
+    if (grid.z == 0) return RVSR_OK;
+    RVSR_CHECK_ARG(grid.z <= 65535 && grid.y <= 65535, "dcn bwd: too many images / channels");
+    const int ROWS = K * 8;
+    const size_t smem = ((size_t)(2 * ROWS + 64) * (TILE_P + 1) + (size_t)64 * (ROWS + 1)) * sizeof(float);
+    if (K == 9) {
+        static bool set9 = false;
+        if (!set9) { RVSR_CUDA(cudaFuncSetAttribute(dcn_bwd_simt_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set9 = true; }
+        dcn_bwd_simt_kernel<9><<<grid, NTHREADS, smem, s>>>(op);
+    } else {
+        dcn_bwd_simt_kernel<1><<<grid, NTHREADS, smem, s>>>(op);
+    }
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+int fold_grouped_weight(const float *gd, float *gw, int Cout, int C, int K, int groups, cudaStream_t s) {
+    const long long total = (long long)Cout * (C / groups) * K;
+    fold_grouped_weight_kernel<<<(int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096), 256, 0, s>>>(gd, gw, Cout, C, K, groups, total);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+}  // namespace rvsr
