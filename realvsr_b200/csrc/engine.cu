@@ -248,6 +248,14 @@ template <typename T> struct Plan {
         ProfEntry *pe = eng->prof_begin(label, flops, bytes, s);
         note(f());
         eng->prof_end(pe, s);
+        static const bool sync_each = getenv("RVSR_SYNC_EACH") != nullptr;  // debug: find the launch that faults
+        if (sync_each && rc == RVSR_OK) {
+            const cudaError_t e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) {
+                set_error("launch '%s' failed: %s", label.c_str(), cudaGetErrorString(e));
+                rc = RVSR_E_CUDA;
+            }
+        }
     }
 
     // generic convolution with fused epilogue; out allocated here

@@ -332,15 +332,23 @@ constexpr int TC_EPI_WARPS = 8, TC_MMA_WARPS = 2;
 // fast enough to keep the tensor pipe busy at N = 64); warp 3: TMEM allocator; warps 4-11: epilogue
 constexpr int TC_EPI_WARP0 = 4;
 constexpr int TC_THREADS = 32 * (TC_EPI_WARP0 + TC_EPI_WARPS);
-constexpr int TC_ACC_BUFS = 4;  // TMEM accumulators in flight (4 x 128 columns = all of TMEM for NT > 64)
 __host__ __device__ constexpr int acc_stride(int NT) { return NT <= 32 ? 32 : (NT <= 64 ? 64 : 128); }
 
 template <int KS, int NT>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcConvParams p) {
     constexpr int KK = KS * KS, PAD = KS / 2, VALID = TC_TW - (KS - 1), HALO_ROWS = TC_ROWS + KS - 1;
     constexpr int PLANE_BYTES = HALO_ROWS * TC_TW * 16;
-    constexpr int ACC = acc_stride(NT), NB = TC_ACC_BUFS, TMEM_COLS = NB * ACC;
-    constexpr int MMAW = 2;  // issuer warps: one thread cannot issue tcgen05.mma fast enough to keep the pipe busy
+    constexpr int ACC = acc_stride(NT);
+    // Issuer warps (1..3): one thread cannot issue tcgen05.mma fast enough, and while an issuer handles its
+    // per-tile barriers / commits (~1.5k cycles) the others must keep the pipe full.  Tiles are dealt
+    // round-robin.  mbarrier waits are parity based, so every barrier must have ONE consumer that sees
+    // each phase in order: each issuer has its own "full" barrier per stage (the producer arms the one
+    // of the tile's issuer), and the number of TMEM accumulators is a multiple of the issuer count so an
+    // accumulator is always filled by the same issuer.
+    constexpr int MMAW = TC_MMA_WARPS;
+    constexpr int NB = MMAW == 3 ? (ACC <= 64 ? 6 : 3) : 4;  // accumulators in flight (4 x 128 columns = all of TMEM)
+    constexpr int TMEM_COLS = NB * ACC <= 32 ? 32 : NB * ACC <= 64 ? 64 : NB * ACC <= 128 ? 128 : NB * ACC <= 256 ? 256 : 512;
+    static_assert(NB * ACC <= 512 && NB % MMAW == 0, "TMEM accumulator plan");
     extern __shared__ __align__(1024) uint8_t smem[];
     const int Q = p.nsrc * p.C8s;  // channel blocks over all sources
     const uint32_t w_bytes = (uint32_t)Q * KK * NT * 16;
@@ -349,17 +357,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     uint8_t *stage_s = smem + w_bytes;
     float *bias_s = reinterpret_cast<float *>(stage_s + (size_t)p.nstages * stage_bytes + 128);  // +128: tap overrun slack
     uint64_t *bars = reinterpret_cast<uint64_t *>(bias_s + NT);
-    // bars: [0,S) full, [S,2S) empty, 2S wfull, then NB x tfull, NB x tempty, then the TMEM base address
+    // bars: MMAW x S full (per issuer), S empty, weights-full, NB accumulator-full, NB accumulator-empty, TMEM base
     const int S = p.nstages;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * S + 1 + 2 * NB);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + (MMAW + 1) * S + 1 + 2 * NB);
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    auto FULL = [&](int w, int st) { return BAR(w * S + st); };
+    auto EMPTY = [&](int st) { return BAR(MMAW * S + st); };
+    const uint32_t WFULL = BAR((MMAW + 1) * S);
+    auto TFULL = [&](int b) { return BAR((MMAW + 1) * S + 1 + b); };
+    auto TEMPTY = [&](int b) { return BAR((MMAW + 1) * S + 1 + NB + b); };
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pss = blockIdx.y;
+    // RVSR_TC_DEBUG & 16: per-role phase timing (clock64 sums over all tiles of CTA 0), printed at exit
+    __shared__ long long ph_acc[3][8];
+    const bool stamp = (p.debug & 16) && blockIdx.x == 0 && blockIdx.y == 0;
+    if (threadIdx.x < 24) ph_acc[threadIdx.x / 8][threadIdx.x % 8] = 0;
+    long long tprev = 0;
+#define PH_BEGIN() do { if (stamp) tprev = clock64(); } while (0)
+#define PH(role, k) do { if (stamp) { const long long tn = clock64(); ph_acc[role][k] += tn - tprev; tprev = tn; } } while (0)
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2 * S + 1 + NB; ++i) mbar_init(BAR(i), 1);
-        for (int i = 0; i < NB; ++i) mbar_init(BAR(2 * S + 1 + NB + i), TC_EPI_WARPS);
+        for (int i = 0; i < (MMAW + 1) * S + 1 + NB; ++i) mbar_init(BAR(i), 1);
+        for (int i = 0; i < NB; ++i) mbar_init(TEMPTY(i), TC_EPI_WARPS);
         fence_barrier_init();
     }
     for (int i = threadIdx.x; i < NT; i += TC_THREADS) {
@@ -387,24 +407,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     if (warp == 0) {
         if (lane == 0) {
             // ---- weights for this N-pass: resident for the CTA's lifetime
-            mbar_expect_tx(BAR(2 * S), w_bytes);
+            mbar_expect_tx(WFULL, w_bytes);
             const uint8_t *wg = reinterpret_cast<const uint8_t *>(p.w) + (size_t)pss * w_bytes;
             for (uint32_t o = 0; o < w_bytes; o += 32768) {
                 const uint32_t n = w_bytes - o < 32768 ? w_bytes - o : 32768;
-                bulk_load(smem_u32(w_s + o), wg + o, n, BAR(2 * S));
+                bulk_load(smem_u32(w_s + o), wg + o, n, WFULL);
             }
             // ---- halo tiles
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            uint32_t it = 0, tl = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
                 const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, n = tile / (p.tiles_x * p.tiles_y);
+                const int w = (int)(tl % MMAW);  // issuer that owns this tile
                 for (int s = 0; s < p.nsrc; ++s, ++it) {
                     const int st = it % S;
-                    mbar_wait(BAR(S + st), ((it / S) & 1) ^ 1);
-                    if (p.debug & 4) { mbar_arrive(BAR(st)); continue; }
-                    mbar_expect_tx(BAR(st), stage_bytes);
+                    PH_BEGIN();
+                    mbar_wait(EMPTY(st), ((it / S) & 1) ^ 1);
+                    PH(0, 0);
+                    if (p.debug & 4) { mbar_arrive(FULL(w, st)); PH(0, 1); continue; }
+                    mbar_expect_tx(FULL(w, st), stage_bytes);
                     const int img = p.src_fixed[s] >= 0 ? (n / p.src_frames[s]) * p.src_frames[s] + p.src_fixed[s] : n;
-                    tma_load_3d(smem_u32(stage_s + (size_t)st * stage_bytes), &p.tmap[s], BAR(st),
+                    tma_load_3d(smem_u32(stage_s + (size_t)st * stage_bytes), &p.tmap[s], FULL(w, st),
                                 (tx * VALID - PAD) * 8, ty * TC_ROWS - PAD, img * p.src_pstride[s]);
+                    PH(0, 1);
                 }
             }
         }
@@ -423,19 +447,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const uint32_t stage_units = stage_bytes >> 4;                 // descriptor address units are 16 B
             const uint32_t b_src_step = C8s * (NT * 16 / 16), b_tap_step = (uint32_t)Q * (NT * 16 / 16);
             const int nk = (p.debug & 1) ? 0 : (int)C8s / 2;
-            // stage ring position of this issuer's first tile, then advanced by MMAW tiles at a time
-            uint32_t st = (mw * nsrc) % (uint32_t)S, ph = ((mw * nsrc) / (uint32_t)S) & 1;
-            mbar_wait(BAR(2 * S), 0);
+            // stage ring position of this issuer's first tile, then advanced by MMAW tiles at a time;
+            // `par` holds, per stage, the parity of the next phase of THIS issuer's full barrier
+            uint32_t st = (mw * nsrc) % (uint32_t)S, par = 0;
+            mbar_wait(WFULL, 0);
             uint32_t t = mw;
             for (int tile = blockIdx.x + (int)mw * gridDim.x; tile < p.num_tiles; tile += MMAW * gridDim.x, t += MMAW) {
                 const uint32_t buf = t % NB;
-                mbar_wait(BAR(2 * S + 1 + NB + buf), ((t / NB) & 1) ^ 1);  // epilogue has drained this accumulator
+                if (mw == 0) PH_BEGIN();
+                mbar_wait(TEMPTY(buf), ((t / NB) & 1) ^ 1);  // epilogue has drained this accumulator
+                if (mw == 0) PH(1, 0);
                 tc_fence_after();
+                if (mw == 0) PH(1, 1);
                 const uint32_t d = tmem_base + buf * ACC;
                 uint32_t b_lo0 = b_base;
                 for (uint32_t s = 0; s < nsrc; ++s) {
-                    mbar_wait(BAR(st), ph);
+                    mbar_wait(FULL(mw, st), (par >> st) & 1);
+                    par ^= 1u << st;
+                    if (mw == 0) PH(1, 2);
                     tc_fence_after();
+                    if (mw == 0) PH(1, 3);
                     const uint32_t a_lo0 = a_base + st * stage_units;
 #pragma unroll
                     for (int tap = 0; tap < KK; ++tap) {
@@ -454,14 +485,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                                          (tap | kk) ? 1u : (s ? 1u : 0u));
                         }
                     }
-                    umma_commit(BAR(S + st));  // stage reusable once these MMAs have read it
+                    if (mw == 0) PH(1, 4);
+                    umma_commit(EMPTY(st));  // stage reusable once these MMAs have read it
+                    if (mw == 0) PH(1, 5);
                     b_lo0 += b_src_step;
-                    if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
+                    if (++st == (uint32_t)S) st = 0;
                 }
-                umma_commit(BAR(2 * S + 1 + buf));  // accumulator complete
+                umma_commit(TFULL(buf));  // accumulator complete
+                if (mw == 0) PH(1, 6);
                 if (MMAW > 1) {  // skip the stages of the tiles the other issuer(s) own
                     st += (MMAW - 1) * nsrc;
-                    while (st >= (uint32_t)S) { st -= (uint32_t)S; ph ^= 1; }
+                    while (st >= (uint32_t)S) st -= (uint32_t)S;
                 }
             }
         }
@@ -477,19 +511,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const uint32_t buf = t % NB;
             const int y = ty * TC_ROWS + lq, x = tx * VALID + lane;
             const bool valid = lane < VALID && y < p.H && x < p.W;
+            const bool es = warp == TC_EPI_WARP0 && lane == 0;
+            if (es) PH_BEGIN();
             ep.prefetch(e, half, pss, n, y, x, valid);
-            mbar_wait(BAR(2 * S + 1 + buf), (t / NB) & 1);
+            if (es) PH(2, 0);
+            mbar_wait(TFULL(buf), (t / NB) & 1);
+            if (es) PH(2, 1);
             tc_fence_after();
             if (!(p.debug & 8)) ep.load(tmem_base + buf * ACC + ((uint32_t)(lq * 32) << 16), half);
+            if (es) PH(2, 2);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(2 * S + 1 + NB + buf));  // accumulator is in registers: MMA may reuse the buffer
+            if (lane == 0) mbar_arrive(TEMPTY(buf));  // accumulator is in registers: MMA may reuse the buffer
+            if (es) PH(2, 3);
             if (!(p.debug & 2)) ep.store(e, half, pss, n, y, x, valid);
+            if (es) PH(2, 4);
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 3) tmem_dealloc(tmem_base, TMEM_COLS);
+    if (stamp && threadIdx.x == 0 && p.num_tiles > 1500) {
+        const int nt = (p.num_tiles + gridDim.x - 1) / gridDim.x;
+        printf("[tc conv KS=%d NT=%d nsrc=%d] tiles/CTA %d | per tile: producer wait-empty %lld issue %lld | issuer0 (per own tile) wait-tempty %lld fence %lld "
+               "wait-full %lld fence %lld mma-issue %lld commit-stage %lld commit-acc %lld | epilogue prefetch %lld wait-tfull %lld tmem-ld %lld arrive %lld store %lld\n",
+               KS, NT, p.nsrc, nt, ph_acc[0][0] / nt, ph_acc[0][1] / nt, ph_acc[1][0] * MMAW / nt, ph_acc[1][1] * MMAW / nt, ph_acc[1][2] * MMAW / nt,
+               ph_acc[1][3] * MMAW / nt, ph_acc[1][4] * MMAW / nt, ph_acc[1][5] * MMAW / nt, ph_acc[1][6] * MMAW / nt, ph_acc[2][0] / nt,
+               ph_acc[2][1] / nt, ph_acc[2][2] / nt, ph_acc[2][3] / nt, ph_acc[2][4] / nt);
+    }
+#undef PH
+#undef PH_BEGIN
 }
 
 // ---------------------------------------------------------------- host side: tensor maps, packing, launch
@@ -594,7 +645,7 @@ static bool tc_conv_plan(const ConvOp &op, TcConvPlan &pl) {
     pl.C8s = C / 8;
     const size_t wb = (size_t)op.nsrc * pl.C8s * op.ks * op.ks * pl.NT * 16;
     const size_t stage = (size_t)pl.C8s * (TC_ROWS + op.ks - 1) * TC_TW * 16;
-    const size_t fixed = wb + 128 + pl.NT * 4 + 256;
+    const size_t fixed = wb + 128 + pl.NT * 4 + 512;
     if (fixed + 2 * stage > TC_SMEM_LIMIT) return false;
     pl.nstages = (int)((TC_SMEM_LIMIT - fixed) / stage);
     if (pl.nstages > 6) pl.nstages = 6;
