@@ -148,37 +148,40 @@ template <int ACT> __device__ __forceinline__ float act_t(float v, int act_rt) {
 }
 
 template <int NT, int NH> struct EpiTile {
-    static constexpr int HALFC = NH == 1 ? NT : ((NT / 2 + 15) / 16) * 16;  // columns per warp (upper bound)
-    static constexpr int MY = HALFC / 16;                                   // 16-column groups per warp
-    uint4 res[MY * 2];
-    uint32_t acc[MY][16];
+    static constexpr int HALFC = NH == 1 ? NT : ((NT / NH + 15) / 16) * 16;  // columns per warp (upper bound)
+    static constexpr int CW = HALFC >= 32 ? 32 : 16;                         // columns per register chunk
+    static constexpr int NCH = HALFC / CW;                                   // chunks per warp
+    static constexpr bool RES = NT <= 64;  // residual add is only built for narrow tiles (register budget)
+    uint4 res[RES ? HALFC / 8 : 1];
+    uint32_t acc[CW / 16][16];
     bool has_res;
 
     __device__ __forceinline__ void prefetch(const EpiArgs &e, int half, int pss, int n, int y, int x, bool valid) {
         has_res = false;
-        if (e.out_mode != OUT_C8 || e.residual == nullptr || !valid) return;
+        if (!RES || e.out_mode != OUT_C8 || e.residual == nullptr || !valid) return;
         has_res = true;
-        const int Co8 = (e.Cout + 7) / 8;
-        const uint4 *r = reinterpret_cast<const uint4 *>(e.residual + (long long)n * e.res_image_stride) + (long long)y * e.W + x;
-        const long long plane = (long long)e.H * e.W;
+        if constexpr (RES) {
+            const int Co8 = (e.Cout + 7) / 8;
+            const uint4 *r = reinterpret_cast<const uint4 *>(e.residual + (long long)n * e.res_image_stride) + (long long)y * e.W + x;
+            const long long plane = (long long)e.H * e.W;
 #pragma unroll
-        for (int j = 0; j < MY * 2; ++j) {
-            const int c0 = half * HALFC + j * 8, q = (pss * NT + c0) / 8;
-            res[j] = make_uint4(0, 0, 0, 0);
-            if (c0 < NT && q < Co8) res[j] = __ldg(r + q * plane);
+            for (int j = 0; j < HALFC / 8; ++j) {
+                const int c0 = half * HALFC + j * 8, q = (pss * NT + c0) / 8;
+                res[j] = make_uint4(0, 0, 0, 0);
+                if (c0 < NT && q < Co8) res[j] = __ldg(r + q * plane);
+            }
         }
     }
-    // issue every TMEM load of this warp's columns, wait once
-    __device__ __forceinline__ void load(uint32_t taddr, int half) {
+    // TMEM -> registers for chunk `ch` of this warp's columns
+    __device__ __forceinline__ void load(uint32_t taddr, int half, int ch) {
 #pragma unroll
-        for (int g = 0; g < MY; ++g)
-            if (half * HALFC + g * 16 < NT) tmem_ld16_nowait(taddr + half * HALFC + g * 16, acc[g]);
+        for (int g = 0; g < CW / 16; ++g)
+            if (half * HALFC + ch * CW + g * 16 < NT) tmem_ld16_nowait(taddr + half * HALFC + ch * CW + g * 16, acc[g]);
         tmem_ld_wait();
     }
 
     template <int ACT>
-    __device__ __forceinline__ void store_c8(const EpiArgs &e, int half, int pss, int n, int y, int x, bool valid) {
-        if (!valid) return;
+    __device__ __forceinline__ void store_c8(const EpiArgs &e, int half, int ch, int pss, int n, int y, int x) {
         int Ho = e.H, Wo = e.W;
         if (e.subsample) {
             if ((y | x) & 1) return;
@@ -189,8 +192,8 @@ template <int NT, int NH> struct EpiTile {
         uint4 *o = reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(e.out) + (long long)n * e.out_image_stride) +
                    (long long)y * Wo + x;
 #pragma unroll
-        for (int j = 0; j < MY * 2; ++j) {
-            const int c0 = half * HALFC + j * 8, q = (pss * NT + c0) / 8;
+        for (int j = 0; j < CW / 8; ++j) {
+            const int c0 = half * HALFC + ch * CW + j * 8, q = (pss * NT + c0) / 8;
             if (c0 >= NT || q >= Co8) continue;
             const float4 b0 = *reinterpret_cast<const float4 *>(e.bias_s + c0);
             const float4 b1 = *reinterpret_cast<const float4 *>(e.bias_s + c0 + 4);
@@ -198,8 +201,8 @@ template <int NT, int NH> struct EpiTile {
             float v[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = act_t<ACT>(__uint_as_float(acc[j >> 1][(j & 1) * 8 + i]) + bb[i], e.act);
-            if (has_res) {
-                const __half2 *h = reinterpret_cast<const __half2 *>(&res[j]);
+            if (RES && has_res) {
+                const __half2 *h = reinterpret_cast<const __half2 *>(&res[RES ? ch * (CW / 8) + j : 0]);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float2 f = __half22float2(h[i]);
@@ -214,97 +217,115 @@ template <int NT, int NH> struct EpiTile {
         }
     }
 
-    __device__ __forceinline__ void store_other(const EpiArgs &e, int half, int pss, int n, int y, int x, bool valid) {
-        if (!valid) return;
+    // nn.PixelShuffle(2) fused into the store.  Columns were permuted at pack time:
+    // col = ij * (NT/4) + c_local, output channel c = pss*(NT/4) + c_local, out[n, c, 2y + (ij>>1), 2x + (ij&1)].
+    template <int ACT>
+    __device__ __forceinline__ void store_shuffle(const EpiArgs &e, int half, int ch, int pss, int n, int y, int x) {
+        constexpr int CP = NT / 4 > 8 ? NT / 4 : 8;  // channels per (i, j) sub-pixel in one N-pass
+        const int C2 = e.Cout / 4;
+        const long long plane2 = (long long)(2 * e.H) * (2 * e.W);  // (pixel, block) cells per output channel block
+        uint4 *ob = reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(e.out) + (long long)n * e.out_image_stride) +
+                    (long long)(pss * (CP / 8)) * plane2 + (long long)(2 * y) * (2 * e.W) + 2 * x;
 #pragma unroll
-        for (int g = 0; g < MY; ++g) {
-            const int c0 = half * HALFC + g * 16;
+        for (int j = 0; j < CW / 8; ++j) {
+            const int c0 = half * HALFC + ch * CW + j * 8;
+            if (c0 >= NT) continue;
+            const int ij = c0 / CP, k = (c0 % CP) / 8;  // sub-pixel and channel block within the pass
+            if ((pss * (CP / 8) + k) * 8 >= C2) continue;
+            const float4 b0 = *reinterpret_cast<const float4 *>(e.bias_s + c0);
+            const float4 b1 = *reinterpret_cast<const float4 *>(e.bias_s + c0 + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            uint4 pk;
+            __half2 *h = reinterpret_cast<__half2 *>(&pk);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                h[i] = __floats2half2_rn(act_t<ACT>(__uint_as_float(acc[j >> 1][(j & 1) * 8 + 2 * i]) + bb[2 * i], e.act),
+                                         act_t<ACT>(__uint_as_float(acc[j >> 1][(j & 1) * 8 + 2 * i + 1]) + bb[2 * i + 1], e.act));
+            ob[(long long)k * plane2 + (ij >> 1) * (2 * e.W) + (ij & 1)] = pk;
+        }
+    }
+
+    // planar fp32 [n][Cout][H][W] with sigmoid from channel sig_from on (CUDA-core DCN's input format)
+    __device__ __forceinline__ void store_planar(const EpiArgs &e, int half, int ch, int pss, int n, int y, int x) {
+        const long long plane = (long long)e.H * e.W;
+#pragma unroll
+        for (int g = 0; g < CW / 16; ++g) {
+            const int c0 = half * HALFC + ch * CW + g * 16;
             if (c0 >= NT) break;
-            float v[16];
+            const int co0 = pss * NT + c0;
+            float *o = reinterpret_cast<float *>(e.out) + (long long)n * e.out_image_stride + (long long)co0 * plane +
+                       (long long)y * e.W + x;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = apply_act(__uint_as_float(acc[g][i]) + e.bias_s[c0 + i], e.act);
-            if (e.out_mode == OUT_C8_SHUFFLE2) {
-                // columns were permuted at pack time: col = ij * (NT/4) + c_local, channel c = pss*(NT/4) + c_local,
-                // out[n, c, 2y + (ij>>1), 2x + (ij&1)]   (nn.PixelShuffle(2): in-channel 4c + ij)
-                constexpr int CP = NT / 4 > 0 ? NT / 4 : 1;
-                const int ij = c0 / CP, cc0 = pss * CP + c0 % CP;
-                const int C2 = e.Cout / 4, yy = 2 * y + (ij >> 1), xx = 2 * x + (ij & 1);
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int q = cc0 / 8 + j;
-                    if (q * 8 >= C2) continue;
-                    float o[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) o[i] = v[j * 8 + i];
-                    store8<__half>(reinterpret_cast<__half *>(e.out) + (long long)n * e.out_image_stride +
-                                       ((((long long)q) * (2 * e.H) + yy) * (2 * e.W) + xx) * 8, o);
-                }
-            } else {  // OUT_PLANAR_F32: one coalesced 128 B store per channel per warp
-                const int co0 = pss * NT + c0;
-                const long long plane = (long long)e.H * e.W;
-                float *o = reinterpret_cast<float *>(e.out) + (long long)n * e.out_image_stride + (long long)co0 * plane +
-                           (long long)y * e.W + x;
-                if (co0 >= e.sig_from) {  // warp-uniform: whole group is mask channels
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = __fdividef(1.f, 1.f + __expf(-v[i]));
-                } else if (co0 + 16 > e.sig_from) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (co0 + i >= e.sig_from) v[i] = __fdividef(1.f, 1.f + __expf(-v[i]));
-                }
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    if (co0 + i < e.Cout) o[i * plane] = v[i];
+            for (int i = 0; i < 16; ++i) {
+                float v = apply_act(__uint_as_float(acc[g][i]) + e.bias_s[c0 + i], e.act);
+                if (co0 + i >= e.sig_from) v = __fdividef(1.f, 1.f + __expf(-v));
+                if (co0 + i < e.Cout) o[i * plane] = v;
             }
         }
     }
 
-    // OUT_OM24 (NT = 128, NH = 2): this warp holds two deformable groups x 32 columns
+    // OUT_OM24 (NT = 128): one register chunk = one deformable group = 32 columns
     // [dy0 dx0 .. dy8 dx8 m0 .. m8 pad*5] (column order fixed at weight-pack time).
-    __device__ __forceinline__ void store_om24(const EpiArgs &e, int half, int pss, int n, int y, int x, bool valid) {
-        if (!valid) return;
-        if constexpr (NT == 128 && NH == 2) {
+    __device__ __forceinline__ void store_om24(const EpiArgs &e, int half, int ch, int pss, int n, int y, int x) {
+        if constexpr (NT == 128 && CW == 32) {
+            const int g = pss * 4 + (half * HALFC + ch * CW) / 32;
+            if (g >= e.dg) return;
             const long long plane = (long long)e.H * e.W;
-            uint4 *o = reinterpret_cast<uint4 *>(e.out) + ((long long)n * e.out_image_stride) / 4 + ((long long)y * e.W + x) * 2;
+            const float *b = e.bias_s + half * HALFC + ch * CW;
+            float v[27];
 #pragma unroll
-            for (int lgi = 0; lgi < 2; ++lgi) {
-                const int g = pss * 4 + half * 2 + lgi;
-                if (g >= e.dg) continue;
-                const float *b = e.bias_s + half * 64 + lgi * 32;
-                float v[27];
+            for (int j = 0; j < 27; ++j) v[j] = __uint_as_float(acc[j >> 4][j & 15]) + b[j];
 #pragma unroll
-                for (int j = 0; j < 27; ++j) v[j] = __uint_as_float(acc[lgi * 2 + (j >> 4)][j & 15]) + b[j];
+            for (int j = 18; j < 27; ++j) v[j] = __fdividef(1.f, 1.f + __expf(-v[j]));
+            uint4 *og = reinterpret_cast<uint4 *>(e.out) + ((long long)n * e.out_image_stride) / 4 +
+                        ((long long)(g * 3) * plane + (long long)y * e.W + x) * 2;
+            og[0] = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+            og[1] = make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7]));
+            og += plane * 2;
+            og[0] = make_uint4(__float_as_uint(v[8]), __float_as_uint(v[9]), __float_as_uint(v[10]), __float_as_uint(v[11]));
+            og[1] = make_uint4(__float_as_uint(v[12]), __float_as_uint(v[13]), __float_as_uint(v[14]), __float_as_uint(v[15]));
+            og += plane * 2;
+            uint32_t m[5];
 #pragma unroll
-                for (int j = 18; j < 27; ++j) v[j] = __fdividef(1.f, 1.f + __expf(-v[j]));
-                uint4 *og = o + (long long)(g * 3) * plane * 2;
-                og[0] = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
-                og[1] = make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7]));
-                og += plane * 2;
-                og[0] = make_uint4(__float_as_uint(v[8]), __float_as_uint(v[9]), __float_as_uint(v[10]), __float_as_uint(v[11]));
-                og[1] = make_uint4(__float_as_uint(v[12]), __float_as_uint(v[13]), __float_as_uint(v[14]), __float_as_uint(v[15]));
-                og += plane * 2;
-                uint32_t m[5];
-#pragma unroll
-                for (int k = 0; k < 5; ++k) {
-                    const __half2 h = __floats2half2_rn(v[18 + 2 * k], k < 4 ? v[19 + 2 * k] : 0.f);
-                    m[k] = *reinterpret_cast<const uint32_t *>(&h);
-                }
-                og[0] = make_uint4(__float_as_uint(v[16]), __float_as_uint(v[17]), m[0], m[1]);
-                og[1] = make_uint4(m[2], m[3], m[4], 0u);
+            for (int k = 0; k < 5; ++k) {
+                const __half2 h = __floats2half2_rn(v[18 + 2 * k], k < 4 ? v[19 + 2 * k] : 0.f);
+                m[k] = *reinterpret_cast<const uint32_t *>(&h);
             }
+            og[0] = make_uint4(__float_as_uint(v[16]), __float_as_uint(v[17]), m[0], m[1]);
+            og[1] = make_uint4(m[2], m[3], m[4], 0u);
         }
     }
 
-    __device__ __forceinline__ void store(const EpiArgs &e, int half, int pss, int n, int y, int x, bool valid) {
-        if (e.out_mode == OUT_OM24) {
-            store_om24(e, half, pss, n, y, x, valid);
-        } else if (e.out_mode == OUT_C8) {
-            if (e.act == RVSR_ACT_LRELU) store_c8<RVSR_ACT_LRELU>(e, half, pss, n, y, x, valid);
-            else if (e.act == RVSR_ACT_RELU) store_c8<RVSR_ACT_RELU>(e, half, pss, n, y, x, valid);
-            else store_c8<RVSR_ACT_NONE>(e, half, pss, n, y, x, valid);
+    __device__ __forceinline__ void store(const EpiArgs &e, int half, int ch, int pss, int n, int y, int x, bool valid) {
+        if (!valid) return;
+        if (e.out_mode == OUT_C8) {
+            if (e.act == RVSR_ACT_LRELU) store_c8<RVSR_ACT_LRELU>(e, half, ch, pss, n, y, x);
+            else if (e.act == RVSR_ACT_RELU) store_c8<RVSR_ACT_RELU>(e, half, ch, pss, n, y, x);
+            else store_c8<RVSR_ACT_NONE>(e, half, ch, pss, n, y, x);
+        } else if (e.out_mode == OUT_OM24) {
+            store_om24(e, half, ch, pss, n, y, x);
+        } else if (e.out_mode == OUT_C8_SHUFFLE2) {
+            if (e.act == RVSR_ACT_LRELU) store_shuffle<RVSR_ACT_LRELU>(e, half, ch, pss, n, y, x);
+            else store_shuffle<-1>(e, half, ch, pss, n, y, x);
         } else {
-            store_other(e, half, pss, n, y, x, valid);
+            store_planar(e, half, ch, pss, n, y, x);
         }
+    }
+
+    // Drain this warp's part of one accumulator: chunk by chunk (32 columns in registers at a time); `release`
+    // hands the TMEM buffer back to the MMA issuer right after the last chunk has been loaded.
+    template <typename Release>
+    __device__ __forceinline__ void run(const EpiArgs &e, uint32_t taddr, int half, int pss, int n, int y, int x, bool valid,
+                                        bool do_load, bool do_store, Release &&release) {
+        bool released = false;
+#pragma unroll 1
+        for (int ch = 0; ch < NCH; ++ch) {
+            if (half * HALFC + ch * CW >= NT) break;
+            if (do_load) load(taddr, half, ch);
+            if (ch == NCH - 1 || half * HALFC + (ch + 1) * CW >= NT) { release(); released = true; }
+            if (do_store) store(e, half, ch, pss, n, y, x, valid);
+        }
+        if (!released) release();  // a warp without columns (NT < NH * 16) still owes its arrival
     }
 };
 
@@ -327,7 +348,7 @@ struct alignas(64) TcConvParams {
 };
 
 constexpr int TC_ROWS = 4, TC_TW = 32;
-constexpr int TC_EPI_WARPS = 8, TC_MMA_WARPS = 2;
+constexpr int TC_EPI_WARPS = 16, TC_EPI_GROUPS = 2;  // two groups of 8 epilogue warps take alternate tiles
 // warp 0: TMA producer; warps 1-2: MMA issuers (alternate tiles -- one thread cannot issue tcgen05.mma
 // fast enough to keep the tensor pipe busy at N = 64); warp 3: TMEM allocator; warps 4-11: epilogue
 constexpr int TC_EPI_WARP0 = 4;
@@ -345,8 +366,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     // each phase in order: each issuer has its own "full" barrier per stage (the producer arms the one
     // of the tile's issuer), and the number of TMEM accumulators is a multiple of the issuer count so an
     // accumulator is always filled by the same issuer.
-    constexpr int MMAW = TC_MMA_WARPS;
-    constexpr int NB = MMAW == 3 ? (ACC <= 64 ? 6 : 3) : 4;  // accumulators in flight (4 x 128 columns = all of TMEM)
+    // The epilogue is latency bound per tile (~1.3k cycles), so two groups of epilogue warps take alternate
+    // tiles; the accumulator count is even so a buffer always belongs to the same group.
+    constexpr int MMAW = ACC <= 64 ? 3 : 2;
+    constexpr int NB = MMAW == 3 ? 6 : 4;  // accumulators in flight (4 x 128 columns = all of TMEM)
+    static_assert(NB % TC_EPI_GROUPS == 0, "accumulator -> epilogue group mapping must be fixed");
     constexpr int TMEM_COLS = NB * ACC <= 32 ? 32 : NB * ACC <= 64 ? 64 : NB * ACC <= 128 ? 128 : NB * ACC <= 256 ? 256 : 512;
     static_assert(NB * ACC <= 512 && NB % MMAW == 0, "TMEM accumulator plan");
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -379,7 +403,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < (MMAW + 1) * S + 1 + NB; ++i) mbar_init(BAR(i), 1);
-        for (int i = 0; i < NB; ++i) mbar_init(TEMPTY(i), TC_EPI_WARPS);
+        for (int i = 0; i < NB; ++i) mbar_init(TEMPTY(i), TC_EPI_WARPS / TC_EPI_GROUPS);
         fence_barrier_init();
     }
     for (int i = threadIdx.x; i < NT; i += TC_THREADS) {
@@ -501,12 +525,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
     } else if (warp >= TC_EPI_WARP0) {
         const int lq = warp & 3;                         // TMEM lane quarter this warp may access == tile row
-        const int half = (warp - TC_EPI_WARP0) >> 2;     // two warps per quarter take the lower / upper columns
+        constexpr int WPG = TC_EPI_WARPS / TC_EPI_GROUPS;            // warps per epilogue group
+        const int eg = (warp - TC_EPI_WARP0) / WPG;                  // this warp's group: tiles t == eg (mod groups)
+        const int half = ((warp - TC_EPI_WARP0) % WPG) >> 2;         // WPG / 4 warps per lane quarter split the columns
         EpiArgs e{bias_s, p.out, p.out_image_stride, p.residual, p.res_image_stride, p.H, p.W, p.Cout, p.act,
                   p.out_mode, p.sig_from, p.subsample, p.dg};
-        EpiTile<NT, 2> ep;
-        uint32_t t = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++t) {
+        EpiTile<NT, WPG / 4> ep;
+        uint32_t t = (uint32_t)eg;
+        for (int tile = blockIdx.x + eg * gridDim.x; tile < p.num_tiles; tile += TC_EPI_GROUPS * gridDim.x, t += TC_EPI_GROUPS) {
             const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, n = tile / (p.tiles_x * p.tiles_y);
             const uint32_t buf = t % NB;
             const int y = ty * TC_ROWS + lq, x = tx * VALID + lane;
@@ -518,13 +544,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             mbar_wait(TFULL(buf), (t / NB) & 1);
             if (es) PH(2, 1);
             tc_fence_after();
-            if (!(p.debug & 8)) ep.load(tmem_base + buf * ACC + ((uint32_t)(lq * 32) << 16), half);
             if (es) PH(2, 2);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(TEMPTY(buf));  // accumulator is in registers: MMA may reuse the buffer
-            if (es) PH(2, 3);
-            if (!(p.debug & 2)) ep.store(e, half, pss, n, y, x, valid);
+            ep.run(e, tmem_base + buf * ACC + ((uint32_t)(lq * 32) << 16), half, pss, n, y, x, valid, !(p.debug & 8), !(p.debug & 2), [&] {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(TEMPTY(buf));  // accumulator is in registers: the issuer may reuse the buffer
+            });
             if (es) PH(2, 4);
         }
     }
@@ -632,7 +657,7 @@ static bool tc_conv_plan(const ConvOp &op, TcConvPlan &pl) {
         return false;
     const int mode = op.out_mode == OUT_OM24 ? 2 : 0;
     if (mode == 2 && (op.ks != 3 || op.stride != 1 || op.dg <= 0 || op.Cout != 27 * op.dg)) return false;
-    if (op.residual != nullptr && op.out_mode != OUT_C8) return false;
+    if (op.residual != nullptr && (op.out_mode != OUT_C8 || op.Cout > 64)) return false;
     const int C = op.src[0].C;
     for (int i = 0; i < op.nsrc; ++i)
         if (op.src[i].C != C) return false;
@@ -918,11 +943,11 @@ __global__ void __launch_bounds__(DCN_THREADS, 1) dcn_tc_kernel(const __grid_con
             mbar_wait(BAR(2 * S + 1 + buf), (t >> 1) & 1);
             tc_fence_after();
             const int y = ty * TC_ROWS + lq, x = tx * TC_TW + lane;
-            ep.load(tmem_base + buf * ACC + ((uint32_t)(lq * 32) << 16), 0);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(2 * S + 3 + buf));
-            ep.store(e, 0, 0, n, y, x, y < p.H && x < p.W);
+            ep.run(e, tmem_base + buf * ACC + ((uint32_t)(lq * 32) << 16), 0, 0, n, y, x, y < p.H && x < p.W, true, true, [&] {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(2 * S + 3 + buf));
+            });
         }
     }
     tc_fence_before();
