@@ -774,6 +774,7 @@ struct TcDcnParams {
 constexpr int DCN_GATHER_WARPS = 16, DCN_THREADS = 32 * (1 + DCN_GATHER_WARPS + 4), DCN_STAGES = 4;
 constexpr int DCN_TAP_BYTES = 8 * 128 * 16;  // 8 channel blocks x 128 pixels x 16 B
 
+template <bool BLEND16>
 __global__ void __launch_bounds__(DCN_THREADS, 1) dcn_tc_kernel(const __grid_constant__ TcDcnParams p) {
     constexpr int NT = 64, K = 9, Q = 8, ACC = 64, TMEM_COLS = 128;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -907,20 +908,37 @@ __global__ void __launch_bounds__(DCN_THREADS, 1) dcn_tc_kernel(const __grid_con
                 uint4 pk[2];
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    if (BLEND16) {
+                        // fp16x2 blend: corner weights (mask folded in, computed in fp32) are rounded to fp16 and
+                        // the four corners are combined with HFMA2 -- 16 instructions instead of 32 conversions
+                        // + 32 FFMA; adds <= 3 fp16 roundings to a value that is stored as fp16 anyway.
+                        __half2 wk[4];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const __half2 *h = reinterpret_cast<const __half2 *>(&c[i][k]);
+                        for (int k = 0; k < 4; ++k) wk[k] = __float2half2_rn(w[i][k]);
+                        __half2 *o = reinterpret_cast<__half2 *>(&pk[i]);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const float2 f = __half22float2(h[j]);
-                            v[2 * j] = fmaf(w[i][k], f.x, v[2 * j]);
-                            v[2 * j + 1] = fmaf(w[i][k], f.y, v[2 * j + 1]);
+                            __half2 a = __hmul2(wk[0], reinterpret_cast<const __half2 *>(&c[i][0])[j]);
+                            a = __hfma2(wk[1], reinterpret_cast<const __half2 *>(&c[i][1])[j], a);
+                            a = __hfma2(wk[2], reinterpret_cast<const __half2 *>(&c[i][2])[j], a);
+                            o[j] = __hfma2(wk[3], reinterpret_cast<const __half2 *>(&c[i][3])[j], a);
                         }
-                    }
-                    __half2 *h = reinterpret_cast<__half2 *>(&pk[i]);
+                    } else {
+                        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+                        for (int k = 0; k < 4; ++k) {
+                            const __half2 *h = reinterpret_cast<const __half2 *>(&c[i][k]);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float2 f = __half22float2(h[j]);
+                                v[2 * j] = fmaf(w[i][k], f.x, v[2 * j]);
+                                v[2 * j + 1] = fmaf(w[i][k], f.y, v[2 * j + 1]);
+                            }
+                        }
+                        __half2 *h = reinterpret_cast<__half2 *>(&pk[i]);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+                    }
                 }
                 mbar_wait(BAR(S + st), ((it / S) & 1) ^ 1);  // stage free (its MMAs have completed)
                 uint8_t *dst = tap_s + st * DCN_TAP_BYTES + m * 16;
@@ -977,12 +995,18 @@ int launch_dcn_tc(const DcnOp &op, cudaStream_t s) {
     const size_t smem = 8 * 9 * 64 * 16 + DCN_STAGES * DCN_TAP_BYTES + 64 * 4 + 256 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        RVSR_CUDA(cudaFuncSetAttribute(dcn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RVSR_CUDA(cudaFuncSetAttribute(dcn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RVSR_CUDA(cudaFuncSetAttribute(dcn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
+    // RVSR_DCN_BLEND=fp32 keeps the bilinear blend in fp32 (one rounding per sample instead of four)
+    static const bool blend32 = getenv("RVSR_DCN_BLEND") != nullptr && strcmp(getenv("RVSR_DCN_BLEND"), "fp32") == 0;
     int gx = sm_count();
     if (gx > p.num_tiles) gx = p.num_tiles;
-    dcn_tc_kernel<<<gx, DCN_THREADS, smem, s>>>(p);
+    if (blend32)
+        dcn_tc_kernel<false><<<gx, DCN_THREADS, smem, s>>>(p);
+    else
+        dcn_tc_kernel<true><<<gx, DCN_THREADS, smem, s>>>(p);
     RVSR_LAUNCH_CHECK();
     return RVSR_OK;
 }
