@@ -57,6 +57,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
     __trap();
 }
+// Same, for roles that are idle most of the time (they wait on slower roles): back off between polls so
+// the spinning warps do not take issue slots from the warps doing the work.
+__device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        __nanosleep(128);
+    }
+    __trap();
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -771,7 +788,7 @@ struct TcDcnParams {
     int N, H, W, cpg, act;
     int tiles_x, tiles_y, num_tiles;
 };
-constexpr int DCN_GATHER_WARPS = 16, DCN_THREADS = 32 * (1 + DCN_GATHER_WARPS + 4), DCN_STAGES = 4;
+constexpr int DCN_GATHER_WARPS = 16, DCN_THREADS = 32 * (1 + DCN_GATHER_WARPS + 4), DCN_STAGES = 4;  // more stages cost L1 capacity (measured slower)
 constexpr int DCN_TAP_BYTES = 8 * 128 * 16;  // 8 channel blocks x 128 pixels x 16 B
 
 template <bool BLEND16>
@@ -818,7 +835,7 @@ __global__ void __launch_bounds__(DCN_THREADS, 1) dcn_tc_kernel(const __grid_con
                 const uint32_t d = tmem_base + buf * ACC;
                 for (int tap = 0; tap < K; ++tap, ++it) {
                     const int st = it % S;
-                    mbar_wait(BAR(st), (it / S) & 1);
+                    mbar_wait_idle(BAR(st), (it / S) & 1);
                     tc_fence_after();
                     const uint32_t a0 = smem_u32(tap_s + st * DCN_TAP_BYTES);
                     const uint32_t b0 = smem_u32(w_s) + (uint32_t)(tap * Q) * (NT * 16);
@@ -958,7 +975,7 @@ __global__ void __launch_bounds__(DCN_THREADS, 1) dcn_tc_kernel(const __grid_con
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++t) {
             const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, n = tile / (p.tiles_x * p.tiles_y);
             const uint32_t buf = t & 1;
-            mbar_wait(BAR(2 * S + 1 + buf), (t >> 1) & 1);
+            mbar_wait_idle(BAR(2 * S + 1 + buf), (t >> 1) & 1);  // a tile takes ~10k cycles to gather
             tc_fence_after();
             const int y = ty * TC_ROWS + lq, x = tx * TC_TW + lane;
             ep.run(e, tmem_base + buf * ACC + ((uint32_t)(lq * 32) << 16), 0, 0, n, y, x, y < p.H && x < p.W, true, true, [&] {
