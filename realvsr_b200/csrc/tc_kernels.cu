@@ -385,9 +385,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     // accumulator is always filled by the same issuer.
     // The epilogue is latency bound per tile (~1.3k cycles), so two groups of epilogue warps take alternate
     // tiles; the accumulator count is even so a buffer always belongs to the same group.
-    constexpr int MMAW = ACC <= 64 ? 3 : 2;
-    constexpr int NB = MMAW == 3 ? 6 : 4;  // accumulators in flight (4 x 128 columns = all of TMEM)
-    static_assert(NB % TC_EPI_GROUPS == 0, "accumulator -> epilogue group mapping must be fixed");
+    // Narrow tiles: 3 issuers, 6 accumulators, 2 epilogue groups.  Wide tiles (128 columns): 3 issuers,
+    // 3 accumulators (384 of 512 TMEM columns), ONE epilogue group of 16 warps (32 columns per warp).
+    constexpr int MMAW = 3;
+    constexpr int EG = ACC <= 64 ? TC_EPI_GROUPS : 1;
+    constexpr int NB = ACC <= 64 ? 6 : 3;
+    static_assert(NB % EG == 0 && NB % MMAW == 0, "accumulator -> issuer / epilogue group mapping must be fixed");
     constexpr int TMEM_COLS = NB * ACC <= 32 ? 32 : NB * ACC <= 64 ? 64 : NB * ACC <= 128 ? 128 : NB * ACC <= 256 ? 256 : 512;
     static_assert(NB * ACC <= 512 && NB % MMAW == 0, "TMEM accumulator plan");
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -420,7 +423,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < (MMAW + 1) * S + 1 + NB; ++i) mbar_init(BAR(i), 1);
-        for (int i = 0; i < NB; ++i) mbar_init(TEMPTY(i), TC_EPI_WARPS / TC_EPI_GROUPS);
+        for (int i = 0; i < NB; ++i) mbar_init(TEMPTY(i), TC_EPI_WARPS / EG);
         fence_barrier_init();
     }
     for (int i = threadIdx.x; i < NT; i += TC_THREADS) {
@@ -542,14 +545,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
     } else if (warp >= TC_EPI_WARP0) {
         const int lq = warp & 3;                         // TMEM lane quarter this warp may access == tile row
-        constexpr int WPG = TC_EPI_WARPS / TC_EPI_GROUPS;            // warps per epilogue group
+        constexpr int WPG = TC_EPI_WARPS / EG;                       // warps per epilogue group
         const int eg = (warp - TC_EPI_WARP0) / WPG;                  // this warp's group: tiles t == eg (mod groups)
         const int half = ((warp - TC_EPI_WARP0) % WPG) >> 2;         // WPG / 4 warps per lane quarter split the columns
         EpiArgs e{bias_s, p.out, p.out_image_stride, p.residual, p.res_image_stride, p.H, p.W, p.Cout, p.act,
                   p.out_mode, p.sig_from, p.subsample, p.dg};
         EpiTile<NT, WPG / 4> ep;
         uint32_t t = (uint32_t)eg;
-        for (int tile = blockIdx.x + eg * gridDim.x; tile < p.num_tiles; tile += TC_EPI_GROUPS * gridDim.x, t += TC_EPI_GROUPS) {
+        for (int tile = blockIdx.x + eg * gridDim.x; tile < p.num_tiles; tile += EG * gridDim.x, t += EG) {
             const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, n = tile / (p.tiles_x * p.tiles_y);
             const uint32_t buf = t % NB;
             const int y = ty * TC_ROWS + lq, x = tx * VALID + lane;
