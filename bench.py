@@ -49,7 +49,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(dev)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20", "-i", str(dev)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -202,7 +202,6 @@ def main():
         barrier()
         ms = e0.elapsed_time(e1)
         launches = eng.last_launch_count() * K
-        clocks = sampler.stop() if sampler else None
 
         # ---- end to end through the public host-buffer call (H2D + forward + D2H every step)
         hosts = [c.cpu().pin_memory() for c in clips]
@@ -215,6 +214,7 @@ def main():
             eng.forward_host(hosts[i % n_clips], out_host)
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
+        clocks = sampler.stop() if sampler else None  # sampled across the device-timed and the e2e regions
         barrier()
 
     # ---- single-window latency (B = 1), device time

@@ -791,7 +791,7 @@ struct TcDcnParams {
     int N, H, W, cpg, act;
     int tiles_x, tiles_y, num_tiles;
 };
-constexpr int DCN_GATHER_WARPS = 16, DCN_THREADS = 32 * (1 + DCN_GATHER_WARPS + 4), DCN_STAGES = 4;  // more stages cost L1 capacity (measured slower)
+constexpr int DCN_GATHER_WARPS = 16, DCN_THREADS = 32 * (1 + DCN_GATHER_WARPS + 4), DCN_STAGES = 3;  // 2..4 measure the same; 6 is slower (L1 capacity)
 constexpr int DCN_TAP_BYTES = 8 * 128 * 16;  // 8 channel blocks x 128 pixels x 16 B
 
 template <bool BLEND16>
