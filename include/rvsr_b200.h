@@ -141,6 +141,25 @@ int rvsr_engine_forward(rvsr_engine *e, const void *x, int x_dtype, void *out, i
 int rvsr_engine_forward_host(rvsr_engine *e, const void *x_host, int x_dtype, void *out_host,
                              int out_dtype, int B, int H, int W, void *dev_in, void *dev_out,
                              void *workspace, size_t workspace_bytes, void *stream);
+/* Sliding-window video inference with a per-frame feature cache.
+ * The reference slides its window one frame at a time and recomputes everything
+ * (test_RealVSR_wi_GT.py:114-119), but the feature pyramid of a frame (conv_first, front ResBlocks,
+ * fea_L2/L3 convs, EDVR_arch.py:276-283) depends on that frame only: extract it once per frame into a
+ * cache of n_slots frames, then run alignment + fusion + reconstruction on windows given as slot
+ * indices.  Results are bit-identical to rvsr_engine_forward on the same frames.
+ *   cache   : caller-owned device buffer of rvsr_engine_cache_bytes(n_slots, H, W)
+ *   extract : frames [F, nc, H, W] NCHW of `dtype` -> slots [slot0, slot0 + F)
+ *   forward : window_slots = HOST array [B * nframes] (window-major, frame order as in forward's x);
+ *             frames = the LQ frames of ALL slots [n_slots, nc, H, W] (for the base of the output);
+ *             workspace: rvsr_engine_workspace_bytes(B, H, W) is sufficient. */
+size_t rvsr_engine_cache_bytes(const rvsr_engine *e, int n_slots, int H, int W);
+size_t rvsr_engine_extract_workspace_bytes(const rvsr_engine *e, int F, int H, int W);
+int rvsr_engine_extract_features(rvsr_engine *e, const void *frames, int dtype, int F, int H, int W,
+                                 void *cache, int n_slots, int slot0, void *workspace,
+                                 size_t workspace_bytes, void *stream);
+int rvsr_engine_forward_cached(rvsr_engine *e, const void *cache, int n_slots, const int *window_slots,
+                               const void *frames, int x_dtype, void *out, int out_dtype, int B,
+                               int H, int W, void *workspace, size_t workspace_bytes, void *stream);
 /* How many kernels the last rvsr_engine_forward enqueued (bench.py's gpu_launches). */
 int rvsr_engine_last_launch_count(const rvsr_engine *e);
 /* Per-launch profiling: when on, every kernel launch of rvsr_engine_forward is bracketed by

@@ -48,6 +48,12 @@ SIGNATURES = {
                                     c_size_t, c_void_p]),
     "rvsr_engine_forward_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
                                          c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "rvsr_engine_cache_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int]),
+    "rvsr_engine_extract_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int]),
+    "rvsr_engine_extract_features": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
+                                             c_void_p, c_size_t, c_void_p]),
+    "rvsr_engine_forward_cached": (c_int, [c_void_p, c_void_p, c_int, ctypes.POINTER(c_int), c_void_p, c_int, c_void_p,
+                                           c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "rvsr_engine_last_launch_count": (c_int, [c_void_p]),
     "rvsr_engine_set_profiling": (c_int, [c_void_p, c_int]),
     "rvsr_engine_profile_collect": (c_int, [c_void_p]),

@@ -449,6 +449,22 @@ int rvsr_engine_forward_host(rvsr_engine *e, const void *x_host, int x_dtype, vo
     RVSR_CUDA(cudaMemcpyAsync(out_host, dev_out, out_bytes, cudaMemcpyDeviceToHost, s));
     return RVSR_OK;
 }
+size_t rvsr_engine_cache_bytes(const rvsr_engine *e, int n_slots, int H, int W) { return e ? e->impl.cache_bytes(n_slots, H, W) : 0; }
+size_t rvsr_engine_extract_workspace_bytes(const rvsr_engine *e, int F, int H, int W) {
+    return e ? const_cast<rvsr_engine *>(e)->impl.extract_workspace_bytes(F, H, W) : 0;
+}
+int rvsr_engine_extract_features(rvsr_engine *e, const void *frames, int dtype, int F, int H, int W, void *cache, int n_slots,
+                                 int slot0, void *workspace, size_t workspace_bytes, void *stream) {
+    RVSR_CHECK_ARG(e != nullptr, "null engine");
+    return e->impl.extract_features(frames, dtype, F, H, W, cache, n_slots, slot0, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+int rvsr_engine_forward_cached(rvsr_engine *e, const void *cache, int n_slots, const int *window_slots, const void *frames,
+                               int x_dtype, void *out, int out_dtype, int B, int H, int W, void *workspace,
+                               size_t workspace_bytes, void *stream) {
+    RVSR_CHECK_ARG(e != nullptr, "null engine");
+    return e->impl.forward_cached(cache, n_slots, window_slots, frames, x_dtype, out, out_dtype, B, H, W, workspace,
+                                  workspace_bytes, (cudaStream_t)stream);
+}
 int rvsr_engine_last_launch_count(const rvsr_engine *e) { return e ? e->impl.last_launches() : 0; }
 int rvsr_engine_set_profiling(rvsr_engine *e, int on) {
     RVSR_CHECK_ARG(e != nullptr, "null engine");

@@ -142,6 +142,8 @@ struct Src {
     long long image_stride;  // elements between consecutive images
     int C;                   // channels (multiple of 8 in storage)
     int frames, fixed_frame;
+    const int *map;          // optional device table: image n reads image map[n] (feature-cache slots)
+    int map_images;          // number of images addressable through `map` (for the TMA tensor map)
 };
 #define RVSR_MAX_SRC 7
 
@@ -221,7 +223,7 @@ template <typename T>
 int launch_tsa_final(const T *fea, const T *att, const T *att_add, T *out, long long n, cudaStream_t s);
 template <typename T, typename Tin, typename Tout>
 int launch_final_add(const T *res_c8, const Tin *x, Tout *out, int B, int frames, int center, int nc,
-                     int H, int W, int scale, cudaStream_t s);
+                     int H, int W, int scale, cudaStream_t s, const int *center_map = nullptr);
 int launch_convert_f16_f32(const void *src, float *dst, long long n, cudaStream_t s);
 int launch_fill_f32(float *dst, float v, long long n, cudaStream_t s);
 

@@ -215,12 +215,19 @@ template <typename T> struct Plan {
     static Src src_of(const Act &a) {
         Src r;
         r.ptr = a.p; r.image_stride = a.image_elems(); r.C = a.C; r.frames = 1; r.fixed_frame = -1;
+        r.map = nullptr; r.map_images = 0;
         return r;
     }
     // image n reads the `frame`-th image of its group of `frames` (PCD reference features)
     static Src src_fixed(const Act &a, int frames, int frame) {
         Src r = src_of(a);
         r.frames = frames; r.fixed_frame = frame;
+        return r;
+    }
+    // image n reads slot map[n] of a cache tensor with `a.N` slots (sliding-window feature cache)
+    static Src src_mapped(const Act &a, const int *map) {
+        Src r = src_of(a);
+        r.map = map; r.map_images = a.N;
         return r;
     }
     // B images, image b reads image b*frames + frame of `a` (TSA: per-frame slices of a [B*N] tensor)
@@ -314,7 +321,7 @@ template <typename T> struct Plan {
     }
 
     // ModulatedDeformConvPack with extra_offset_mask=True (deform_conv.py:274-292)
-    Act dcn_pack(const std::string &name, const Act &x, const Act &feat, int dg, int act) {
+    Act dcn_pack(const std::string &name, const Act &x, const Act &feat, int dg, int act, const int *xmap = nullptr) {
         const int K = 9;
         const PackedConv *pc = get(name);
         const PackedConv *pom = get(name + ".conv_offset_mask");
@@ -326,10 +333,10 @@ template <typename T> struct Plan {
                           feat.C == 64 && (x.C / dg) % 8 == 0 && sizeof(T) == 2;
         Act om = conv(name + ".conv_offset_mask", {src_of(feat)}, feat.N, feat.H, feat.W, RVSR_ACT_NONE, 1,
                       om24 ? OUT_OM24 : OUT_PLANAR_F32, nullptr, 2 * dg * K);
-        Act o = make(x.N, pc->Cout, x.H, x.W);
+        Act o = make(feat.N, pc->Cout, x.H, x.W);
         if (dry || rc != RVSR_OK) return o;
         DcnOp op = {};
-        op.x = src_of(x);
+        op.x = xmap != nullptr ? src_mapped(x, xmap) : src_of(x);
         if (om24) {
             op.om24 = om.p;
             op.om24_image_stride = (long long)dg * 24 * x.H * x.W;
@@ -340,10 +347,10 @@ template <typename T> struct Plan {
         }
         op.w_simt = pc->w_simt; op.w_tc = pc->w_tc; op.bias = pc->bias;
         op.out = o.p; op.out_image_stride = o.image_elems();
-        op.N = x.N; op.H = x.H; op.W = x.W; op.Cout = pc->Cout;
+        op.N = feat.N; op.H = x.H; op.W = x.W; op.Cout = pc->Cout;
         op.kh = op.kw = 3; op.stride = 1; op.pad = 1; op.dil = 1; op.dg = dg;
         op.act = act; op.out_mode = OUT_C8;
-        const double px = (double)x.N * x.H * x.W;
+        const double px = (double)feat.N * x.H * x.W;
         const double flops = (2.0 * x.C * pc->Cout * K + 8.0 * x.C * K) * px;  // contraction + gather
         const double bytes = px * (x.C * sizeof(T) + (om24 ? 96.0 * dg : 3.0 * dg * K * 4) + pc->Cout * sizeof(T));
         const bool tc = om24 && tc_dcn_supported(op);
@@ -384,54 +391,108 @@ template <typename T> struct Plan {
 
 template <typename T>
 int Engine::run(Arena &ar, bool dry, const void *x, int x_dtype, void *out, int out_dtype, int B, int H, int W,
-                cudaStream_t s) {
+                cudaStream_t s, const CacheArgs *ca) {
     const int nf = cfg_.nf, N = cfg_.nframes, nc = cfg_.nc, dg = cfg_.groups, ctr = cfg_.center;
-    const int NB = B * N;
     const int LR = RVSR_ACT_LRELU, NONE = RVSR_ACT_NONE;
     // RVSR_DISABLE_TC=1 routes the fp16 engine through the CUDA-core kernels (debug / cross-check)
     static const bool tc_off = getenv("RVSR_DISABLE_TC") != nullptr && getenv("RVSR_DISABLE_TC")[0] == '1';
     Plan<T> P{this, ar, dry, s, packed_, cfg_.precision == RVSR_F16 && !tc_off};
     using PT = Plan<T>;
+    // Three modes share this plan:
+    //   full    (ca == null)        x = [B, N, nc, H, W] windows -> out
+    //   extract (ca->extract)       x = [F, nc, H, W] frames -> pyramid written into cache slots [slot0, slot0+F)
+    //   cached  (ca && !extract)    windows given as slot indices into the cache; x = all cached LQ frames
+    const bool extract = ca != nullptr && ca->extract, cached = ca != nullptr && !ca->extract;
+    const int NB = extract ? B : B * N;   // images in the feature / alignment stages (extract: B = frame count)
 
-    // ---- LQ frames -> channel-blocked
-    const int nc_store = (cfg_.precision == RVSR_F16 && nc < 16) ? 16 : nc;  // see finalize(): K granularity
-    Act xin = P.make(NB, nc_store, H, W);
-    if (!dry && P.rc == RVSR_OK)
-        P.launch("glue:pack_input:", 0, (double)xin.elems() * sizeof(T) * 1.4, [&] {
-            return x_dtype == RVSR_F32
-                       ? launch_pack_nchw<T, float>((const float *)x, (T *)xin.p, NB, nc, H, W, s, nc_store)
-                       : launch_pack_nchw<T, __half>((const __half *)x, (T *)xin.p, NB, nc, H, W, s, nc_store); });
-    // ---- per-frame feature pyramid (EDVR_arch.py:276-283)
-    Act L1 = P.conv("conv_first", {PT::src_of(xin)}, NB, H, W, LR);
-    L1 = P.resblocks("feature_extraction", cfg_.front_RBs, L1);
-    Act L2 = P.conv("fea_L2_conv1", {PT::src_of(L1)}, NB, H, W, LR, 2);
-    L2 = P.conv("fea_L2_conv2", {PT::src_of(L2)}, NB, L2.H, L2.W, LR);
-    Act L3 = P.conv("fea_L3_conv1", {PT::src_of(L2)}, NB, L2.H, L2.W, LR, 2);
-    L3 = P.conv("fea_L3_conv2", {PT::src_of(L3)}, NB, L3.H, L3.W, LR);
+    Act L1, L2, L3;
+    const int *map_nbr = nullptr, *map_ref = nullptr, *map_ctr = nullptr;
+    if (!cached) {
+        // ---- LQ frames -> channel-blocked
+        const int nc_store = (cfg_.precision == RVSR_F16 && nc < 16) ? 16 : nc;  // see finalize(): K granularity
+        Act xin = P.make(NB, nc_store, H, W);
+        if (!dry && P.rc == RVSR_OK)
+            P.launch("glue:pack_input:", 0, (double)xin.elems() * sizeof(T) * 1.4, [&] {
+                return x_dtype == RVSR_F32
+                           ? launch_pack_nchw<T, float>((const float *)x, (T *)xin.p, NB, nc, H, W, s, nc_store)
+                           : launch_pack_nchw<T, __half>((const __half *)x, (T *)xin.p, NB, nc, H, W, s, nc_store); });
+        // ---- per-frame feature pyramid (EDVR_arch.py:276-283)
+        L1 = P.conv("conv_first", {PT::src_of(xin)}, NB, H, W, LR);
+        L1 = P.resblocks("feature_extraction", cfg_.front_RBs, L1);
+        L2 = P.conv("fea_L2_conv1", {PT::src_of(L1)}, NB, H, W, LR, 2);
+        L2 = P.conv("fea_L2_conv2", {PT::src_of(L2)}, NB, L2.H, L2.W, LR);
+        L3 = P.conv("fea_L3_conv1", {PT::src_of(L2)}, NB, L2.H, L2.W, LR, 2);
+        L3 = P.conv("fea_L3_conv2", {PT::src_of(L3)}, NB, L3.H, L3.W, LR);
+        if (extract) {
+            if (!dry && P.rc == RVSR_OK) {  // copy the pyramid of the F frames into their (contiguous) cache slots
+                const Act *lv[3] = {&L1, &L2, &L3};
+                char *dst = reinterpret_cast<char *>(ca->cache);
+                for (int k = 0; k < 3; ++k) {
+                    const size_t img = (size_t)lv[k]->image_elems() * sizeof(T);
+                    if (cudaMemcpyAsync(dst + (size_t)ca->slot0 * img, lv[k]->p, img * (size_t)NB, cudaMemcpyDeviceToDevice, s) != cudaSuccess) {
+                        set_error("extract_features: cache copy failed");
+                        return RVSR_E_CUDA;
+                    }
+                    dst += (size_t)ca->n_slots * img;  // level regions are laid out [L1 slots][L2 slots][L3 slots]
+                }
+                launches_ = P.launches;
+            }
+            return P.rc;
+        }
+    } else {
+        // ---- features come from the cache: level regions [L1 x n_slots][L2 x n_slots][L3 x n_slots]
+        char *base = reinterpret_cast<char *>(ca->cache);
+        L1.N = L2.N = L3.N = ca->n_slots; L1.C = L2.C = L3.C = nf;
+        L1.H = H; L1.W = W; L2.H = H / 2; L2.W = W / 2; L3.H = H / 4; L3.W = W / 4;
+        L1.p = base;
+        L2.p = base + (size_t)L1.image_elems() * sizeof(T) * ca->n_slots;
+        L3.p = reinterpret_cast<char *>(L2.p) + (size_t)L2.image_elems() * sizeof(T) * ca->n_slots;
+        // device tables: neighbour slot of image b*N+i, reference (centre) slot of its window, centre slot per window
+        int *maps = reinterpret_cast<int *>(ar.alloc((size_t)(2 * NB + B) * sizeof(int)));
+        if (maps == nullptr && P.rc == RVSR_OK) { set_error("workspace too small"); P.rc = RVSR_E_WORKSPACE; }
+        map_nbr = maps; map_ref = maps + NB; map_ctr = maps + 2 * NB;
+        if (!dry && P.rc == RVSR_OK) {
+            std::vector<int> h((size_t)2 * NB + B);
+            for (int b = 0; b < B; ++b) {
+                for (int i = 0; i < N; ++i) {
+                    h[b * N + i] = ca->window_slots[b * N + i];
+                    h[NB + b * N + i] = ca->window_slots[b * N + ctr];
+                }
+                h[2 * NB + b] = ca->window_slots[b * N + ctr];
+            }
+            host_maps_.push_back(std::move(h));  // keep alive until the async copy has been consumed
+            if (cudaMemcpyAsync(maps, host_maps_.back().data(), host_maps_.back().size() * sizeof(int), cudaMemcpyHostToDevice, s) != cudaSuccess) {
+                set_error("forward_cached: slot table upload failed");
+                return RVSR_E_CUDA;
+            }
+        }
+    }
+    auto nbr = [&](const Act &a) { return cached ? PT::src_mapped(a, map_nbr) : PT::src_of(a); };
+    auto ref = [&](const Act &a) { return cached ? PT::src_mapped(a, map_ref) : PT::src_fixed(a, N, ctr); };
 
     // ---- PCD alignment of all N frames at once (EDVR_arch.py:98-132, :297-303)
     const std::string p = "pcd_align.";
-    Act o3 = P.conv(p + "L3_offset_conv1", {PT::src_of(L3), PT::src_fixed(L3, N, ctr)}, NB, L3.H, L3.W, LR);
+    Act o3 = P.conv(p + "L3_offset_conv1", {nbr(L3), ref(L3)}, NB, L3.H, L3.W, LR);
     o3 = P.conv(p + "L3_offset_conv2", {PT::src_of(o3)}, NB, L3.H, L3.W, LR);
-    Act f3 = P.dcn_pack(p + "L3_dcnpack", L3, o3, dg, LR);
+    Act f3 = P.dcn_pack(p + "L3_dcnpack", L3, o3, dg, LR, map_nbr);
 
-    Act o2 = P.conv(p + "L2_offset_conv1", {PT::src_of(L2), PT::src_fixed(L2, N, ctr)}, NB, L2.H, L2.W, LR);
+    Act o2 = P.conv(p + "L2_offset_conv1", {nbr(L2), ref(L2)}, NB, L2.H, L2.W, LR);
     Act o3u = P.up2(o3, 2.f);
     o2 = P.conv(p + "L2_offset_conv2", {PT::src_of(o2), PT::src_of(o3u)}, NB, L2.H, L2.W, LR);
     o2 = P.conv(p + "L2_offset_conv3", {PT::src_of(o2)}, NB, L2.H, L2.W, LR);
-    Act f2 = P.dcn_pack(p + "L2_dcnpack", L2, o2, dg, NONE);
+    Act f2 = P.dcn_pack(p + "L2_dcnpack", L2, o2, dg, NONE, map_nbr);
     Act f3u = P.up2(f3, 1.f);
     f2 = P.conv(p + "L2_fea_conv", {PT::src_of(f2), PT::src_of(f3u)}, NB, L2.H, L2.W, LR);
 
-    Act o1 = P.conv(p + "L1_offset_conv1", {PT::src_of(L1), PT::src_fixed(L1, N, ctr)}, NB, H, W, LR);
+    Act o1 = P.conv(p + "L1_offset_conv1", {nbr(L1), ref(L1)}, NB, H, W, LR);
     Act o2u = P.up2(o2, 2.f);
     o1 = P.conv(p + "L1_offset_conv2", {PT::src_of(o1), PT::src_of(o2u)}, NB, H, W, LR);
     o1 = P.conv(p + "L1_offset_conv3", {PT::src_of(o1)}, NB, H, W, LR);
-    Act f1 = P.dcn_pack(p + "L1_dcnpack", L1, o1, dg, NONE);
+    Act f1 = P.dcn_pack(p + "L1_dcnpack", L1, o1, dg, NONE, map_nbr);
     Act f2u = P.up2(f2, 1.f);
     f1 = P.conv(p + "L1_fea_conv", {PT::src_of(f1), PT::src_of(f2u)}, NB, H, W, NONE);  // no lrelu (:125)
 
-    Act oc = P.conv(p + "cas_offset_conv1", {PT::src_of(f1), PT::src_fixed(L1, N, ctr)}, NB, H, W, LR);
+    Act oc = P.conv(p + "cas_offset_conv1", {PT::src_of(f1), ref(L1)}, NB, H, W, LR);
     oc = P.conv(p + "cas_offset_conv2", {PT::src_of(oc)}, NB, H, W, LR);
     Act aligned = P.dcn_pack(p + "cas_dcnpack", f1, oc, dg, LR);
 
@@ -504,15 +565,15 @@ int Engine::run(Arena &ar, bool dry, const void *x, int x_dtype, void *out, int 
         const T *lp = (const T *)last.p;
         P.launch("glue:final_add_base:", 0, (double)last.elems() * sizeof(T) + (double)B * nc * last.H * last.W * 4, [&] {
             if (x_dtype == RVSR_F32 && out_dtype == RVSR_F32)
-                return launch_final_add<T, float, float>(lp, (const float *)x, (float *)out, B, N, ctr, nc, H, W, scale, s);
+                return launch_final_add<T, float, float>(lp, (const float *)x, (float *)out, B, N, ctr, nc, H, W, scale, s, map_ctr);
             if (x_dtype == RVSR_F32)
-                return launch_final_add<T, float, __half>(lp, (const float *)x, (__half *)out, B, N, ctr, nc, H, W, scale, s);
+                return launch_final_add<T, float, __half>(lp, (const float *)x, (__half *)out, B, N, ctr, nc, H, W, scale, s, map_ctr);
             if (out_dtype == RVSR_F32)
-                return launch_final_add<T, __half, float>(lp, (const __half *)x, (float *)out, B, N, ctr, nc, H, W, scale, s);
-            return launch_final_add<T, __half, __half>(lp, (const __half *)x, (__half *)out, B, N, ctr, nc, H, W, scale, s);
+                return launch_final_add<T, __half, float>(lp, (const __half *)x, (float *)out, B, N, ctr, nc, H, W, scale, s, map_ctr);
+            return launch_final_add<T, __half, __half>(lp, (const __half *)x, (__half *)out, B, N, ctr, nc, H, W, scale, s, map_ctr);
         });
     }
-    if (!dry) {
+    if (!dry && !cached) {
         taps_.clear();
         taps_["L1"] = L1; taps_["L2"] = L2; taps_["L3"] = L3; taps_["aligned"] = aligned; taps_["fused"] = fused;
         tap_dtype_ = sizeof(T) == 4 ? RVSR_F32 : RVSR_F16;
@@ -562,9 +623,9 @@ size_t Engine::workspace_bytes(int B, int H, int W) {
     if (check_dims(cfg_, B, H, W) != RVSR_OK) return 0;
     Arena ar;
     if (cfg_.precision == RVSR_F16)
-        run<__half>(ar, true, nullptr, RVSR_F32, nullptr, RVSR_F32, B, H, W, nullptr);
+        run<__half>(ar, true, nullptr, RVSR_F32, nullptr, RVSR_F32, B, H, W, nullptr, nullptr);
     else
-        run<float>(ar, true, nullptr, RVSR_F32, nullptr, RVSR_F32, B, H, W, nullptr);
+        run<float>(ar, true, nullptr, RVSR_F32, nullptr, RVSR_F32, B, H, W, nullptr, nullptr);
     return ar.peak + 4096;
 }
 
@@ -586,8 +647,69 @@ int Engine::forward(const void *x, int x_dtype, void *out, int out_dtype, int B,
     ar.cap = ws_bytes;
     const size_t mis = (size_t)(reinterpret_cast<uintptr_t>(ws) % 1024);
     if (mis) { ar.base += 1024 - mis; ar.cap -= 1024 - mis; }
-    if (cfg_.precision == RVSR_F16) return run<__half>(ar, false, x, x_dtype, out, out_dtype, B, H, W, s);
-    return run<float>(ar, false, x, x_dtype, out, out_dtype, B, H, W, s);
+    host_maps_.clear();
+    if (cfg_.precision == RVSR_F16) return run<__half>(ar, false, x, x_dtype, out, out_dtype, B, H, W, s, nullptr);
+    return run<float>(ar, false, x, x_dtype, out, out_dtype, B, H, W, s, nullptr);
+}
+
+// ---------------------------------------------------------------- sliding-window feature cache
+size_t Engine::cache_bytes(int n_slots, int H, int W) const {
+    if (n_slots <= 0 || H <= 0 || W <= 0 || H % 4 || W % 4) return 0;
+    const size_t es = cfg_.precision == RVSR_F16 ? 2 : 4, c8 = (size_t)cdiv(cfg_.nf, 8) * 8;
+    return (size_t)n_slots * c8 * es * ((size_t)H * W + (size_t)(H / 2) * (W / 2) + (size_t)(H / 4) * (W / 4));
+}
+size_t Engine::extract_workspace_bytes(int F, int H, int W) {
+    if (check_dims(cfg_, F, H, W) != RVSR_OK) return 0;
+    Arena ar;
+    CacheArgs ca = {};
+    ca.extract = true;
+    if (cfg_.precision == RVSR_F16)
+        run<__half>(ar, true, nullptr, RVSR_F32, nullptr, RVSR_F32, F, H, W, nullptr, &ca);
+    else
+        run<float>(ar, true, nullptr, RVSR_F32, nullptr, RVSR_F32, F, H, W, nullptr, &ca);
+    return ar.peak + 4096;
+}
+static void arena_over(Arena &ar, void *ws, size_t ws_bytes) {
+    ar.base = reinterpret_cast<char *>(ws);
+    ar.cap = ws_bytes;
+    const size_t mis = (size_t)(reinterpret_cast<uintptr_t>(ws) % 1024);
+    if (mis) { ar.base += 1024 - mis; ar.cap -= 1024 - mis; }
+}
+int Engine::extract_features(const void *frames, int dtype, int F, int H, int W, void *cache, int n_slots, int slot0,
+                             void *ws, size_t ws_bytes, cudaStream_t s) {
+    if (!finalized_) { set_error("engine: weights not finalised"); return RVSR_E_STATE; }
+    RVSR_TRY(check_dims(cfg_, F, H, W));
+    RVSR_CHECK_ARG(dtype == RVSR_F32 || dtype == RVSR_F16, "extract_features: bad dtype %d", dtype);
+    RVSR_CHECK_ARG(slot0 >= 0 && n_slots > 0 && slot0 + F <= n_slots, "extract_features: slots [%d, %d) outside the cache of %d", slot0, slot0 + F, n_slots);
+    if (F == 0) return RVSR_OK;
+    RVSR_CHECK_ARG(frames && cache && ws, "extract_features: null buffer");
+    Arena ar;
+    arena_over(ar, ws, ws_bytes);
+    CacheArgs ca = {};
+    ca.extract = true; ca.cache = cache; ca.n_slots = n_slots; ca.slot0 = slot0;
+    prof_clear();
+    if (cfg_.precision == RVSR_F16) return run<__half>(ar, false, frames, dtype, nullptr, RVSR_F32, F, H, W, s, &ca);
+    return run<float>(ar, false, frames, dtype, nullptr, RVSR_F32, F, H, W, s, &ca);
+}
+int Engine::forward_cached(const void *cache, int n_slots, const int *window_slots, const void *frames, int x_dtype, void *out,
+                           int out_dtype, int B, int H, int W, void *ws, size_t ws_bytes, cudaStream_t s) {
+    if (!finalized_) { set_error("engine: weights not finalised"); return RVSR_E_STATE; }
+    RVSR_TRY(check_dims(cfg_, B, H, W));
+    RVSR_CHECK_ARG(x_dtype == RVSR_F32 || x_dtype == RVSR_F16, "forward_cached: bad x dtype %d", x_dtype);
+    RVSR_CHECK_ARG(out_dtype == RVSR_F32 || out_dtype == RVSR_F16, "forward_cached: bad out dtype %d", out_dtype);
+    if (B == 0) return RVSR_OK;
+    RVSR_CHECK_ARG(cache && window_slots && frames && out && ws && n_slots > 0, "forward_cached: null buffer");
+    for (int i = 0; i < B * cfg_.nframes; ++i)
+        RVSR_CHECK_ARG(window_slots[i] >= 0 && window_slots[i] < n_slots, "forward_cached: slot %d outside the cache of %d", window_slots[i], n_slots);
+    Arena ar;
+    arena_over(ar, ws, ws_bytes);
+    CacheArgs ca = {};
+    ca.cache = const_cast<void *>(cache); ca.n_slots = n_slots; ca.window_slots = window_slots;
+    prof_clear();
+    prof_.reserve(1024);
+    host_maps_.clear();
+    if (cfg_.precision == RVSR_F16) return run<__half>(ar, false, frames, x_dtype, out, out_dtype, B, H, W, s, &ca);
+    return run<float>(ar, false, frames, x_dtype, out, out_dtype, B, H, W, s, &ca);
 }
 
 int Engine::read_tap(const char *name, float *dst, size_t dst_elems, cudaStream_t s) {

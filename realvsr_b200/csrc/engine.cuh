@@ -56,6 +56,14 @@ struct ProfEntry {
     float ms = 0.f;
 };
 
+// Feature-cache modes of Engine::run (see engine.cu)
+struct CacheArgs {
+    bool extract;             // true: write the pyramid of the given frames into the cache and stop
+    void *cache;              // [L1 x n_slots][L2 x n_slots][L3 x n_slots], channel-blocked
+    int n_slots, slot0;
+    const int *window_slots;  // host, [B * nframes] slot index of every frame of every window
+};
+
 class Engine {
   public:
     // per-launch profiling (CUDA events on the launching stream)
@@ -74,6 +82,12 @@ class Engine {
     int forward(const void *x, int x_dtype, void *out, int out_dtype, int B, int H, int W, void *ws,
                 size_t ws_bytes, cudaStream_t s);
     int read_tap(const char *name, float *dst, size_t dst_elems, cudaStream_t s);
+    size_t cache_bytes(int n_slots, int H, int W) const;
+    size_t extract_workspace_bytes(int F, int H, int W);
+    int extract_features(const void *frames, int dtype, int F, int H, int W, void *cache, int n_slots, int slot0, void *ws,
+                         size_t ws_bytes, cudaStream_t s);
+    int forward_cached(const void *cache, int n_slots, const int *window_slots, const void *frames, int x_dtype, void *out,
+                       int out_dtype, int B, int H, int W, void *ws, size_t ws_bytes, cudaStream_t s);
     const std::vector<std::string> &names() const { return names_; }
     int last_launches() const { return launches_; }
     const rvsr_edvr_config &cfg() const { return cfg_; }
@@ -81,7 +95,7 @@ class Engine {
   private:
     template <typename T>
     int run(Arena &ar, bool dry, const void *x, int x_dtype, void *out, int out_dtype, int B, int H, int W,
-            cudaStream_t s);
+            cudaStream_t s, const CacheArgs *ca);
     void expect(const std::string &name, std::vector<int64_t> shape);
     void expect_conv(const std::string &name, int co, int ci, int k);
 
@@ -96,6 +110,7 @@ class Engine {
     std::vector<void *> owned_;  // cudaMalloc'ed buffers
     bool profiling_ = false;
     std::vector<ProfEntry> prof_;
+    std::vector<std::vector<int>> host_maps_;
 };
 
 // tc_kernels.cu: tcgen05 paths (fp16 storage).  Return RVSR_E_UNSUPPORTED when the shape is

@@ -21,7 +21,7 @@ static constexpr int TILE_CO = 64;                         // output channels pe
 static constexpr int NTHREADS = 256;
 
 __device__ __forceinline__ long long src_image(const Src &s, int n) {
-    const int m = s.fixed_frame >= 0 ? (n / s.frames) * s.frames + s.fixed_frame : n;
+    const int m = s.map != nullptr ? __ldg(s.map + n) : (s.fixed_frame >= 0 ? (n / s.frames) * s.frames + s.fixed_frame : n);
     return (long long)m * s.image_stride;
 }
 
@@ -550,7 +550,8 @@ template int launch_tsa_final<__half>(const __half *, const __half *, const __ha
 // base = x4 bilinear (align_corners=False) of the centre LQ frame, or the frame itself (scale 1).
 template <typename T, typename Tin, typename Tout>
 __global__ void final_add_kernel(const T *__restrict__ res, const Tin *__restrict__ x, Tout *__restrict__ out,
-                                 int frames, int center, int nc, int H, int W, int scale, long long total) {
+                                 int frames, int center, int nc, int H, int W, int scale, long long total,
+                                 const int *__restrict__ center_map) {
     const int Ho = H * scale, Wo = W * scale;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -560,7 +561,8 @@ __global__ void final_add_kernel(const T *__restrict__ res, const Tin *__restric
         const long long b = r / Ho;
         float v[8];
         load8<T>(res + i * 8, v);
-        const Tin *xc = x + ((b * frames + center) * nc) * (long long)H * W;
+        const long long cimg = center_map != nullptr ? (long long)__ldg(center_map + b) : b * frames + center;
+        const Tin *xc = x + (cimg * nc) * (long long)H * W;
         if (scale == 1) {
             for (int c = 0; c < nc; ++c)
                 out[((b * nc + c) * Ho + oy) * (long long)Wo + ox] =
@@ -584,17 +586,17 @@ __global__ void final_add_kernel(const T *__restrict__ res, const Tin *__restric
 template <typename Tout> __device__ __forceinline__ Tout cast_out(float v);
 template <typename T, typename Tin, typename Tout>
 int launch_final_add(const T *res_c8, const Tin *x, Tout *out, int B, int frames, int center, int nc, int H,
-                     int W, int scale, cudaStream_t s) {
+                     int W, int scale, cudaStream_t s, const int *center_map) {
     RVSR_CHECK_ARG(nc <= 8, "final_add: nc %d > 8", nc);
     const long long total = (long long)B * H * scale * W * scale;
     if (total == 0) return RVSR_OK;
     final_add_kernel<T, Tin, Tout><<<(int)((total + 255) / 256 < 16384 ? (total + 255) / 256 : 16384), 256, 0, s>>>(
-        res_c8, x, out, frames, center, nc, H, W, scale, total);
+        res_c8, x, out, frames, center, nc, H, W, scale, total, center_map);
     RVSR_LAUNCH_CHECK();
     return RVSR_OK;
 }
 #define INST_FINAL(T, Tin, Tout) \
-    template int launch_final_add<T, Tin, Tout>(const T *, const Tin *, Tout *, int, int, int, int, int, int, int, cudaStream_t);
+    template int launch_final_add<T, Tin, Tout>(const T *, const Tin *, Tout *, int, int, int, int, int, int, int, cudaStream_t, const int *);
 INST_FINAL(float, float, float)
 INST_FINAL(float, __half, float)
 INST_FINAL(float, float, __half)

@@ -351,6 +351,7 @@ struct alignas(64) TcConvParams {
     CUtensorMap tmap[RVSR_MAX_SRC];
     int src_pstride[RVSR_MAX_SRC];  // channel-block planes between consecutive images of a source
     int src_frames[RVSR_MAX_SRC], src_fixed[RVSR_MAX_SRC];
+    const int *src_map[RVSR_MAX_SRC];  // optional image -> slot tables (feature cache)
     int nsrc, C8s, nstages;
     const __half *w;  // [pass][tap][Q][NT][8]
     const float *bias;
@@ -469,7 +470,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     PH(0, 0);
                     if (p.debug & 4) { mbar_arrive(FULL(w, st)); PH(0, 1); continue; }
                     mbar_expect_tx(FULL(w, st), stage_bytes);
-                    const int img = p.src_fixed[s] >= 0 ? (n / p.src_frames[s]) * p.src_frames[s] + p.src_fixed[s] : n;
+                    const int img = p.src_map[s] != nullptr ? __ldg(p.src_map[s] + n)
+                                    : (p.src_fixed[s] >= 0 ? (n / p.src_frames[s]) * p.src_frames[s] + p.src_fixed[s] : n);
                     tma_load_3d(smem_u32(stage_s + (size_t)st * stage_bytes), &p.tmap[s], FULL(w, st),
                                 (tx * VALID - PAD) * 8, ty * TC_ROWS - PAD, img * p.src_pstride[s]);
                     PH(0, 1);
@@ -742,8 +744,10 @@ int launch_conv_tc(const ConvOp &op, cudaStream_t s) {
         p.src_pstride[i] = (int)(sr.image_stride / plane);
         p.src_frames[i] = sr.frames > 0 ? sr.frames : 1;
         p.src_fixed[i] = sr.fixed_frame;
+        p.src_map[i] = sr.map;
+        const int reach = sr.map != nullptr ? sr.map_images : op.N;  // images addressable through this source
         const cuuint64_t dims[3] = {(cuuint64_t)op.W * 8, (cuuint64_t)op.H,
-                                    (cuuint64_t)(op.N - 1) * p.src_pstride[i] + pl.C8s};
+                                    (cuuint64_t)(reach - 1) * p.src_pstride[i] + pl.C8s};
         const cuuint64_t strides[2] = {(cuuint64_t)op.W * 16, (cuuint64_t)op.H * op.W * 16};
         const cuuint32_t box[3] = {(cuuint32_t)TC_TW * 8, (cuuint32_t)halo_rows, (cuuint32_t)pl.C8s};
         const cuuint32_t estr[3] = {1, 1, 1};
@@ -782,6 +786,7 @@ int launch_conv_tc(const ConvOp &op, cudaStream_t s) {
 struct TcDcnParams {
     const __half *x;
     long long x_image_stride;
+    const int *x_map;         // optional image -> slot table (feature cache)
     const uint4 *om;          // OUT_OM24 offsets + mask
     long long om_stride;      // uint4 units per image
     const __half *w;
@@ -866,7 +871,7 @@ __global__ void __launch_bounds__(DCN_THREADS, 1) dcn_tc_kernel(const __grid_con
             const int y = ty * TC_ROWS + (m >> 5), x = tx * TC_TW + (m & 31);
             const bool valid = y < p.H && x < p.W;
             const long long pix = valid ? (long long)y * p.W + x : 0;
-            const __half *xb = p.x + (long long)n * p.x_image_stride;
+            const __half *xb = p.x + (long long)(p.x_map != nullptr ? __ldg(p.x_map + n) : n) * p.x_image_stride;
             // offsets / mask of this pixel's two deformable groups (OUT_OM24): 3 blocks of 32 B per group
             const uint4 *om[2];
             uint32_t cur[2][8], mw[2][5];
@@ -1005,7 +1010,7 @@ bool tc_dcn_supported(const DcnOp &op) {
 int launch_dcn_tc(const DcnOp &op, cudaStream_t s) {
     RVSR_CHECK_ARG(tc_dcn_supported(op), "tc dcn: unsupported configuration");
     TcDcnParams p;
-    p.x = reinterpret_cast<const __half *>(op.x.ptr); p.x_image_stride = op.x.image_stride;
+    p.x = reinterpret_cast<const __half *>(op.x.ptr); p.x_image_stride = op.x.image_stride; p.x_map = op.x.map;
     p.om = reinterpret_cast<const uint4 *>(op.om24); p.om_stride = op.om24_image_stride / 4;
     p.w = reinterpret_cast<const __half *>(op.w_tc); p.bias = op.bias;
     p.out = reinterpret_cast<__half *>(op.out); p.out_image_stride = op.out_image_stride;

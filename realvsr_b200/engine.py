@@ -127,6 +127,48 @@ class EDVREngine:
             torch.cuda.current_stream(self.device).synchronize()
         return out_host
 
+    # ------------------------------------------------------------------ sliding-window feature cache
+    def make_cache(self, n_slots, H, W):
+        """Device buffer for the feature pyramids of n_slots frames (rvsr_engine_cache_bytes)."""
+        nbytes = self.L.rvsr_engine_cache_bytes(self.h, n_slots, H, W)
+        if nbytes == 0:
+            _lib.check(_lib.E_INVALID, "cache_bytes (H and W must be multiples of 4)")
+        return torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+
+    def extract_features(self, frames, cache, n_slots, slot0=0):
+        """frames [F, C, H, W] (CUDA) -> cache slots [slot0, slot0 + F)."""
+        frames = frames.contiguous()
+        F_, _, H, W = frames.shape
+        with torch.cuda.device(self.device):
+            need = self.L.rvsr_engine_extract_workspace_bytes(self.h, F_, H, W)
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = None
+                self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            _lib.check(self.L.rvsr_engine_extract_features(
+                self.h, ctypes.c_void_p(frames.data_ptr()), _dt(frames), F_, H, W, ctypes.c_void_p(cache.data_ptr()),
+                n_slots, slot0, ctypes.c_void_p(self._ws.data_ptr()), self._ws.numel(), self._stream()),
+                "extract_features")
+
+    def forward_cached(self, cache, n_slots, window_slots, frames, out_dtype=None):
+        """window_slots: B lists of nframes slot indices; frames: the LQ frames of all slots
+        [n_slots, C, H, W] (CUDA).  -> [B, C, sH, sW]."""
+        B = len(window_slots)
+        flat = [int(v) for w in window_slots for v in w]
+        if len(flat) != B * self.cfg.nframes:
+            raise RuntimeError("forward_cached: every window needs %d slot indices" % self.cfg.nframes)
+        frames = frames.contiguous()
+        _, _, H, W = frames.shape
+        out = torch.empty(B, self.cfg.nc, H * self.scale, W * self.scale, device=frames.device,
+                          dtype=out_dtype or frames.dtype)
+        arr = (ctypes.c_int * len(flat))(*flat)
+        with torch.cuda.device(self.device):
+            ws = self._workspace(B, H, W)
+            _lib.check(self.L.rvsr_engine_forward_cached(
+                self.h, ctypes.c_void_p(cache.data_ptr()), n_slots, arr, ctypes.c_void_p(frames.data_ptr()), _dt(frames),
+                ctypes.c_void_p(out.data_ptr()), _dt(out), B, H, W, ctypes.c_void_p(ws.data_ptr()), ws.numel(),
+                self._stream()), "forward_cached")
+        return out
+
     def last_launch_count(self):
         return self.L.rvsr_engine_last_launch_count(self.h)
 

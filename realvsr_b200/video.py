@@ -1,0 +1,75 @@
+"""Video-level callers of the hot path: the reference's inference loop pieces.
+
+  index_generation   data/util.py:169-214      temporal window indices with 4 padding modes
+  single_forward     utils/util.py:222-237     no_grad forward, result .float().cpu()
+  flipx4_forward     utils/util.py:240-261     x4 flip self-ensemble
+  sr_sequence        test_RealVSR_wi_GT.py:114-119 (the per-frame loop), re-designed: the per-frame
+                     feature pyramid is extracted ONCE per frame into a cache and windows are batched,
+                     instead of recomputing all N pyramids for every output frame.
+"""
+import torch
+
+
+def index_generation(crt_i, max_n, N, padding='reflection'):
+    """Indices of the N frames read for output frame crt_i of a max_n-frame sequence.
+    crt_i = 0, N = 5:  replicate [0,0,0,1,2]  reflection [2,1,0,1,2]  new_info [4,3,0,1,2]  circle [3,4,0,1,2]"""
+    if padding not in ('replicate', 'reflection', 'new_info', 'circle'):
+        raise ValueError('Wrong padding mode')
+    last, half = max_n - 1, N // 2
+    out = []
+    for i in range(crt_i - half, crt_i + half + 1):
+        if i < 0:
+            j = {'replicate': 0, 'reflection': -i, 'new_info': crt_i + half - i, 'circle': N + i}[padding]
+        elif i > last:
+            j = {'replicate': last, 'reflection': 2 * last - i, 'new_info': crt_i - half - (i - last),
+                 'circle': i - N}[padding]
+        else:
+            j = i
+        out.append(j)
+    return out
+
+
+def single_forward(model, inp):
+    """model(inp) without autograd; first element if the model returns a list/tuple; float, on the CPU."""
+    with torch.no_grad():
+        y = model(inp)
+    if isinstance(y, (list, tuple)):
+        y = y[0]
+    return y.data.float().cpu()
+
+
+def flipx4_forward(model, inp):
+    """Average of the forward on the input and its W-, H- and HW-flipped versions (flipped back)."""
+    acc = single_forward(model, inp)
+    for dims in ((-1,), (-2,), (-2, -1)):
+        acc = acc + torch.flip(single_forward(model, torch.flip(inp, dims)), dims)
+    return acc / 4
+
+
+def sr_sequence(model, frames, padding='replicate', batch=4, cache=True):
+    """Super-resolve every frame of a clip.  frames: [T, C, H, W] CUDA tensor (fp16 or fp32);
+    model: realvsr_b200 EDVR / EDVR_NoUp.  Returns [T, C, sH, sW] on the same device.
+
+    Window for output t = index_generation(t, T, nframes, padding) (as the reference's test loop).
+    cache=True: extract each frame's feature pyramid once (rvsr_engine_extract_features) and run
+    alignment + fusion + reconstruction on batches of `batch` windows given as cache slots
+    (rvsr_engine_forward_cached); cache=False: plain batched forwards on gathered windows.
+    Both produce bit-identical frames."""
+    T = frames.shape[0]
+    N = model._cfg["nframes"]
+    windows = [index_generation(t, T, N, padding) for t in range(T)]
+    outs = []
+    with torch.no_grad():
+        if not cache:
+            for t0 in range(0, T, batch):
+                idx = torch.tensor(windows[t0:t0 + batch], device=frames.device)
+                outs.append(model(frames[idx.view(-1)].view(idx.shape[0], N, *frames.shape[1:])))
+            return torch.cat(outs, 0)
+        eng = model._get_engine(frames[:1].unsqueeze(0).expand(1, N, *frames.shape[1:]))
+        H, W = frames.shape[-2:]
+        buf = eng.make_cache(T, H, W)
+        for t0 in range(0, T, 4 * batch):  # extract in chunks to bound the workspace
+            eng.extract_features(frames[t0:t0 + 4 * batch], buf, T, t0)
+        for t0 in range(0, T, batch):
+            outs.append(eng.forward_cached(buf, T, windows[t0:t0 + batch], frames))
+    return torch.cat(outs, 0)
