@@ -301,7 +301,7 @@ size_t rvsr_conv2d_fwd_workspace_bytes(int B, int C1, int C2, int H, int W, int 
     n += 2 * align_up(px * 4 * (size_t)cdiv(Cout, 8) * 8 * es, 256);            // out (maybe shuffled) + residual
     n += 2 * align_up((size_t)Cout * (Cin + 16) * ks * ks * 4, 256);             // fp32 weight copy + padded copy
     n += align_up((size_t)cdiv(Cin + 16, 8) * ks * ks * 8 * cdiv(Cout, 64) * 64 * 4, 256);  // simt pack
-    n += align_up(tc_conv_weight_bytes(Cout, Cin, ks) + 256, 256) + align_up((size_t)Cout * 4, 256);
+    n += 2 * align_up(tc_conv_weight_bytes(Cout, Cin + 16, ks) + 256, 256) + align_up((size_t)Cout * 4, 256);
     return n + 4096;
 }
 
@@ -330,6 +330,7 @@ static int conv2d_fwd_t(const void *x1, const void *x2, const void *weight, cons
     const int cout_pad = cdiv(Cout, 64) * 64;
     float *wsimt = (float *)cv.take((size_t)cdiv(CinS, 8) * KK * 8 * cout_pad * 4);
     void *wtc = tc ? cv.take(tc_conv_weight_bytes(Cout, CinS, ks) + 16) : nullptr;
+    void *wtc2 = (tc && !shuffle && tc2_weight_bytes(Cout, CinS, ks) > 0) ? cv.take(tc2_weight_bytes(Cout, CinS, ks) + 16) : nullptr;
     if (!cv.ok) { set_error("conv2d: workspace too small"); return RVSR_E_WORKSPACE; }
     RVSR_TRY((launch_pack_nchw<T, T>((const T *)x1, a1, B, C1, H, W, s, C1s)));
     if (C2 > 0) RVSR_TRY((launch_pack_nchw<T, T>((const T *)x2, a2, B, C2, H, W, s)));
@@ -345,11 +346,12 @@ static int conv2d_fwd_t(const void *x1, const void *x2, const void *weight, cons
     RVSR_CHECK_ARG(C1 % 8 == 0 || C2 == 0, "conv2d: first source must have a multiple of 8 channels when concatenating");
     RVSR_TRY(pack_weight_simt(w, wsimt, Cout, CinS, ks, &cins, 1, cout_pad, s));
     if (tc && tc_conv_weight_bytes(Cout, CinS, ks) > 0) RVSR_TRY(pack_weight_tc(w, wtc, Cout, CinS, ks, shuffle, s));
+    if (wtc2 != nullptr) RVSR_TRY(pack_weight_tc2(w, wtc2, Cout, CinS, ks, s));
     ConvOp op = {};
     op.src[0] = Src{a1, (long long)cdiv(C1s, 8) * H * W * 8, C1s, 1, -1};
     op.nsrc = 1;
     if (C2 > 0) { op.src[1] = Src{a2, (long long)cdiv(C2, 8) * H * W * 8, C2, 1, -1}; op.nsrc = 2; }
-    op.w_simt = wsimt; op.w_tc = (tc && tc_conv_weight_bytes(Cout, CinS, ks) > 0) ? wtc : nullptr; op.bias = b;
+    op.w_simt = wsimt; op.w_tc = (tc && tc_conv_weight_bytes(Cout, CinS, ks) > 0) ? wtc : nullptr; op.w_tc2 = wtc2; op.bias = b;
     op.out = o; op.out_image_stride = (long long)(out_elems / B);
     op.residual = r; op.res_image_stride = op.out_image_stride;
     op.N = B; op.H = H; op.W = W; op.Cout = Cout; op.ks = ks; op.stride = stride; op.act = act;

@@ -163,6 +163,7 @@ struct ConvOp {
     int nsrc;
     const float *w_simt;   // packed fp32 [sum chunks][taps][8][CoutPad]
     const void *w_tc;      // packed fp16 UMMA layout (tc kernels) or null
+    const void *w_tc2;     // packed fp16 layout of the CTA-pair kernel (64-wide 3x3 convs) or null
     const float *bias;     // [Cout] fp32 or null
     void *out;
     long long out_image_stride;

@@ -183,6 +183,14 @@ int Engine::finalize(cudaStream_t s) {
                 else
                     RVSR_TRY(pack_weight_tc(wsrc, pc.w_tc, pc.Cout, pc.Cin, pc.ks, mode, s));
             }
+            const size_t tb2 = (!is_dcn && mode == 0) ? tc2_weight_bytes(pc.Cout, pc.Cin, pc.ks) : 0;
+            if (tb2 > 0) {
+                if (pc.w_tc2 == nullptr) {
+                    RVSR_CUDA(cudaMalloc(&pc.w_tc2, tb2));
+                    owned_.push_back(pc.w_tc2);
+                }
+                RVSR_TRY(pack_weight_tc2(wsrc, pc.w_tc2, pc.Cout, pc.Cin, pc.ks, s));
+            }
         }
     }
     finalized_ = true;
@@ -291,7 +299,7 @@ template <typename T> struct Plan {
             rc = RVSR_E_INVALID;
             return o;
         }
-        op.w_simt = pc->w_simt; op.w_tc = pc->w_tc; op.bias = pc->bias;
+        op.w_simt = pc->w_simt; op.w_tc = pc->w_tc; op.w_tc2 = pc->w_tc2; op.bias = pc->bias;
         op.out = o.p;
         op.out_image_stride = out_mode == OUT_PLANAR_F32 ? (long long)pc->Cout * Ho * Wo
                               : out_mode == OUT_OM24     ? (long long)(pc->Cout / 27) * 24 * Ho * Wo

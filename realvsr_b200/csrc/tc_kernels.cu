@@ -590,6 +590,212 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #undef PH_BEGIN
 }
 
+// ---------------------------------------------------------------- convolution, CTA pair (cta_group::2)
+// Same algorithm as conv_tc_kernel<3, 64> on a cluster of two CTAs (two SMs of one TPC): one
+// tcgen05.mma.cta_group::2 covers M = 256 pixels (each CTA's own 128-pixel tile, its own halo in its own
+// shared memory) x N = 64 output channels, and the B operand (weights) is split between the pair -- each
+// CTA keeps and feeds only 32 of the 64 rows.  Per SM and MMA that is 4 KB of A + 1 KB of B from shared
+// memory instead of 4 + 2 KB: 40 instead of 48 cycles, i.e. the N = 64 shape's ceiling moves from 2/3 to 0.8
+// of the tensor peak.  Only the leader CTA (cluster rank 0) issues MMAs.  Synchronisation:
+//   FULL(issuer, stage)  leader's barrier, 2 arrivals (leader: arrive.expect_tx for both tiles' bytes, peer:
+//                        remote arrive) + both CTAs' TMA (cp.async.bulk.tensor ... cta_group::2) complete_tx
+//   EMPTY(stage), TFULL(acc)  tcgen05.commit ... multicast::cluster -> the same barrier in BOTH CTAs
+//   TEMPTY(acc)          leader's barrier, arrivals from the epilogue warps of both CTAs (peer: remote arrive)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank0(uint32_t local_addr) {  // same smem offset in cluster CTA 0
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(0));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap *tmap, uint32_t bar_rank0, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_rank0), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {  // arrives on `bar` in both CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+
+template <int KS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_tc2_kernel(const __grid_constant__ TcConvParams p) {
+    constexpr int NT = 64, NH2 = NT / 2;
+    constexpr int KK = KS * KS, PAD = KS / 2, VALID = TC_TW - (KS - 1), HALO_ROWS = TC_ROWS + KS - 1;
+    constexpr int PLANE_BYTES = HALO_ROWS * TC_TW * 16;
+    constexpr int ACC = 64, MMAW = 3, EG = TC_EPI_GROUPS, NB = 6, TMEM_COLS = 512;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int Q = p.nsrc * p.C8s;
+    const uint32_t w_bytes = (uint32_t)Q * KK * NH2 * 16;  // this CTA's half of the weights
+    const uint32_t stage_bytes = (uint32_t)p.C8s * PLANE_BYTES;
+    uint8_t *w_s = smem;
+    uint8_t *stage_s = smem + w_bytes;
+    float *bias_s = reinterpret_cast<float *>(stage_s + (size_t)p.nstages * stage_bytes + 128);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(bias_s + NT);
+    const int S = p.nstages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + (MMAW + 1) * S + 1 + 2 * NB);
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    auto FULL = [&](int w, int st) { return BAR(w * S + st); };
+    auto EMPTY = [&](int st) { return BAR(MMAW * S + st); };
+    const uint32_t WFULL = BAR((MMAW + 1) * S);
+    auto TFULL = [&](int b) { return BAR((MMAW + 1) * S + 1 + b); };
+    auto TEMPTY = [&](int b) { return BAR((MMAW + 1) * S + 1 + NB + b); };
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cid = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+    const int npairs = (p.num_tiles + 1) / 2;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < MMAW * S; ++i) mbar_init(BAR(i), 2);                       // FULL: leader + peer arrive
+        for (int i = MMAW * S; i < (MMAW + 1) * S + 1 + NB; ++i) mbar_init(BAR(i), 1);  // EMPTY, WFULL, TFULL
+        for (int i = 0; i < NB; ++i) mbar_init(TEMPTY(i), 2 * (TC_EPI_WARPS / EG));   // epilogue warps of both CTAs
+        fence_barrier_init();
+        // this CTA's half of the weights: resident for the CTA's lifetime
+        mbar_expect_tx(WFULL, w_bytes);
+        const uint8_t *wg = reinterpret_cast<const uint8_t *>(p.w) + (size_t)rank * w_bytes;
+        for (uint32_t o = 0; o < w_bytes; o += 32768) {
+            const uint32_t n = w_bytes - o < 32768 ? w_bytes - o : 32768;
+            bulk_load(smem_u32(w_s + o), wg + o, n, WFULL);
+        }
+    }
+    for (int i = threadIdx.x; i < NT; i += TC_THREADS) bias_s[i] = (p.bias != nullptr && i < p.Cout) ? p.bias[i] : 0.f;
+    if (threadIdx.x == 0) mbar_wait(WFULL, 0);  // the leader's MMAs read the PEER's weight half too: both must have landed
+    if (warp == 3) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();   // barriers of both CTAs initialised before any remote arrive / multicast commit
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0, tl = 0;
+            for (int pr = cid; pr < npairs; pr += nclusters, ++tl) {
+                int tile = 2 * pr + (int)rank;
+                if (tile >= p.num_tiles) tile = p.num_tiles - 1;  // odd tile count: the peer recomputes the last tile, never stores it
+                const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, n = tile / (p.tiles_x * p.tiles_y);
+                const int w = (int)(tl % MMAW);
+                for (int s = 0; s < p.nsrc; ++s, ++it) {
+                    const int st = it % S;
+                    mbar_wait(EMPTY(st), ((it / S) & 1) ^ 1);
+                    const uint32_t full0 = mapa_rank0(FULL(w, st));
+                    if (rank == 0)
+                        mbar_expect_tx(FULL(w, st), 2 * stage_bytes);
+                    else
+                        mbar_arrive_cluster(full0);
+                    const int img = p.src_map[s] != nullptr ? __ldg(p.src_map[s] + n)
+                                    : (p.src_fixed[s] >= 0 ? (n / p.src_frames[s]) * p.src_frames[s] + p.src_fixed[s] : n);
+                    tma_load_3d_2sm(smem_u32(stage_s + (size_t)st * stage_bytes), &p.tmap[s], full0,
+                                    (tx * VALID - PAD) * 8, ty * TC_ROWS - PAD, img * p.src_pstride[s]);
+                }
+            }
+        }
+    } else if (warp <= MMAW) {
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((256u >> 4) << 24);  // M = 256 over the pair
+            const uint32_t mw = (uint32_t)(warp - 1);
+            const uint32_t nsrc = (uint32_t)p.nsrc, C8s = (uint32_t)p.C8s;
+            const uint64_t adesc0 = make_desc(smem_u32(stage_s), PLANE_BYTES, 128);
+            const uint64_t bdesc0 = make_desc(smem_u32(w_s), NH2 * 16, 128);
+            const uint32_t a_hi = (uint32_t)(adesc0 >> 32), b_hi = (uint32_t)(bdesc0 >> 32);
+            const uint32_t a_base = (uint32_t)adesc0, b_base = (uint32_t)bdesc0;
+            const uint32_t stage_units = stage_bytes >> 4;
+            const uint32_t b_src_step = C8s * (NH2 * 16 / 16), b_tap_step = (uint32_t)Q * (NH2 * 16 / 16);
+            const int nk = (int)C8s / 2;
+            uint32_t st = (mw * nsrc) % (uint32_t)S, par = 0;
+            uint32_t t = mw;
+            for (int pr = cid + (int)mw * nclusters; pr < npairs; pr += MMAW * nclusters, t += MMAW) {
+                const uint32_t buf = t % NB;
+                mbar_wait(TEMPTY(buf), ((t / NB) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + buf * ACC;
+                uint32_t b_lo0 = b_base;
+                for (uint32_t s = 0; s < nsrc; ++s) {
+                    mbar_wait(FULL(mw, st), (par >> st) & 1);
+                    par ^= 1u << st;
+                    tc_fence_after();
+                    const uint32_t a_lo0 = a_base + st * stage_units;
+#pragma unroll
+                    for (int tap = 0; tap < KK; ++tap) {
+                        const uint32_t a_lo = a_lo0 + (uint32_t)((tap / KS) * TC_TW + (tap % KS));
+                        const uint32_t b_lo = b_lo0 + (uint32_t)tap * b_tap_step;
+                        if (nk == 4) {
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                umma_f16_2sm(d, ((uint64_t)a_hi << 32) | (a_lo + (uint32_t)kk * (2 * PLANE_BYTES / 16)),
+                                             ((uint64_t)b_hi << 32) | (b_lo + (uint32_t)kk * (2 * NH2)), idesc,
+                                             (tap | kk) ? 1u : (s ? 1u : 0u));
+                        } else {
+                            for (int kk = 0; kk < nk; ++kk)
+                                umma_f16_2sm(d, ((uint64_t)a_hi << 32) | (a_lo + (uint32_t)kk * (2 * PLANE_BYTES / 16)),
+                                             ((uint64_t)b_hi << 32) | (b_lo + (uint32_t)kk * (2 * NH2)), idesc,
+                                             (tap | kk) ? 1u : (s ? 1u : 0u));
+                        }
+                    }
+                    umma_commit_2sm(EMPTY(st));
+                    b_lo0 += b_src_step;
+                    if (++st == (uint32_t)S) st = 0;
+                }
+                umma_commit_2sm(TFULL(buf));
+                st += (MMAW - 1) * nsrc;
+                while (st >= (uint32_t)S) st -= (uint32_t)S;
+            }
+        }
+    } else if (warp >= TC_EPI_WARP0) {
+        constexpr int WPG = TC_EPI_WARPS / EG;
+        const int lq = warp & 3;
+        const int eg = (warp - TC_EPI_WARP0) / WPG;
+        const int half = ((warp - TC_EPI_WARP0) % WPG) >> 2;
+        EpiArgs e{bias_s, p.out, p.out_image_stride, p.residual, p.res_image_stride, p.H, p.W, p.Cout, p.act,
+                  p.out_mode, p.sig_from, p.subsample, p.dg};
+        EpiTile<NT, WPG / 4> ep;
+        uint32_t t = (uint32_t)eg;
+        for (int pr = cid + eg * nclusters; pr < npairs; pr += EG * nclusters, t += EG) {
+            const int tile = 2 * pr + (int)rank;
+            const bool real = tile < p.num_tiles;
+            const int tcl = real ? tile : p.num_tiles - 1;
+            const int tx = tcl % p.tiles_x, ty = (tcl / p.tiles_x) % p.tiles_y, n = tcl / (p.tiles_x * p.tiles_y);
+            const uint32_t buf = t % NB;
+            const int y = ty * TC_ROWS + lq, x = tx * VALID + lane;
+            const bool valid = real && lane < VALID && y < p.H && x < p.W;
+            ep.prefetch(e, half, 0, n, y, x, valid);
+            mbar_wait(TFULL(buf), (t / NB) & 1);
+            tc_fence_after();
+            ep.run(e, tmem_base + buf * ACC + ((uint32_t)(lq * 32) << 16), half, 0, n, y, x, valid, true, true, [&] {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(mapa_rank0(TEMPTY(buf)));  // the leader's issuer waits for both CTAs
+            });
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();   // no CTA exits (or frees TMEM) while its partner can still touch its barriers / operands
+    if (warp == 3) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+}
+
 // ---------------------------------------------------------------- host side: tensor maps, packing, launch
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -662,6 +868,30 @@ int pack_weight_tc(const float *w_oihw, void *dst, int Cout, int Cin, int ks, in
 int pack_weight_dcn_tc(const float *w_oihw, void *dst, int Cout, int C, int K, cudaStream_t s) {
     RVSR_CHECK_ARG(K == 9, "tc dcn pack: 3x3 only");
     return pack_weight_tc(w_oihw, dst, Cout, C, 3, 0, s);
+}
+
+// CTA-pair layout: [rank][tap][Q][32][8] -- each CTA of the pair owns 32 of the 64 output channels
+size_t tc2_weight_bytes(int Cout, int Cin, int ks) { return (Cout == 64 && ks == 3 && Cin % 16 == 0) ? (size_t)9 * (Cin / 8) * 64 * 16 : 0; }
+__global__ void pack_weight_tc2_kernel(const float *__restrict__ w, __half *__restrict__ dst, int Cin, int Q, long long total) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int e = (int)(i % 8);
+        long long r = i / 8;
+        const int n = (int)(r % 32);
+        r /= 32;
+        const int q = (int)(r % Q);
+        r /= Q;
+        const int tap = (int)(r % 9);
+        const int rank = (int)(r / 9);
+        dst[i] = __float2half_rn(w[((long long)(rank * 32 + n) * Cin + q * 8 + e) * 9 + tap]);
+    }
+}
+int pack_weight_tc2(const float *w_oihw, void *dst, int Cout, int Cin, int ks, cudaStream_t s) {
+    RVSR_CHECK_ARG(tc2_weight_bytes(Cout, Cin, ks) > 0, "tc2 pack: needs Cout == 64, 3x3, Cin %% 16 == 0");
+    const long long total = (long long)2 * 9 * (Cin / 8) * 32 * 8;
+    pack_weight_tc2_kernel<<<(int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096), 256, 0, s>>>(
+        w_oihw, reinterpret_cast<__half *>(dst), Cin, Cin / 8, total);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
 }
 
 static constexpr size_t TC_SMEM_LIMIT = 232448 - 1024 - 2048;  // 227 KB opt-in maximum minus alignment slack and static smem
@@ -773,6 +1003,29 @@ int launch_conv_tc(const ConvOp &op, cudaStream_t s) {
     static const int dbg = getenv("RVSR_TC_DEBUG") ? atoi(getenv("RVSR_TC_DEBUG")) : 0;
     p.debug = dbg;
     const int sms = sm_count();
+    // CTA-pair kernel for the 64-wide 3x3 convolutions (the bulk of the network)
+    static const bool two_cta = !(getenv("RVSR_TC_2CTA") != nullptr && getenv("RVSR_TC_2CTA")[0] == '0');
+    if (two_cta && op.w_tc2 != nullptr && pl.NT == 64 && op.ks == 3 && op.out_mode == OUT_C8 && op.Cout == 64 && p.num_tiles >= 4) {
+        const size_t wb2 = (size_t)op.nsrc * pl.C8s * 9 * 32 * 16;
+        const size_t stage = (size_t)pl.C8s * (TC_ROWS + 2) * TC_TW * 16;
+        const size_t fixed = wb2 + 128 + 64 * 4 + 512;
+        int st2 = (int)((TC_SMEM_LIMIT - fixed) / stage);
+        if (st2 > 6) st2 = 6;
+        p.nstages = st2;
+        p.w = reinterpret_cast<const __half *>(op.w_tc2);
+        const size_t smem2 = fixed + (size_t)st2 * stage + 1024;
+        static bool attr2 = false;
+        if (!attr2) {
+            RVSR_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT + 1024));
+            attr2 = true;
+        }
+        const int npairs = (p.num_tiles + 1) / 2;
+        int clusters = sms / 2;
+        if (clusters > npairs) clusters = npairs;
+        conv_tc2_kernel<3><<<2 * clusters, TC_THREADS, smem2, s>>>(p);
+        RVSR_LAUNCH_CHECK();
+        return RVSR_OK;
+    }
 #define RVSR_TC_CASE(KS_, NT_) \
     if (op.ks == KS_ && pl.NT == NT_) return launch_conv_tc_t<KS_, NT_>(p, pl, sms, s);
     RVSR_TC_CASE(3, 16) RVSR_TC_CASE(3, 64) RVSR_TC_CASE(3, 128)
