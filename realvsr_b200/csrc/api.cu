@@ -207,7 +207,7 @@ size_t rvsr_mdcn_pack_fwd_workspace_bytes(int B, int C, int H, int W, int Cout, 
     n += align_up(px * (size_t)cdiv(Cout, 8) * 8 * es, 256);          // output channel-blocked
     n += 2 * align_up((size_t)27 * dg * C * 9 * 4, 256) + 2 * align_up((size_t)Cout * C * 9 * 4, 256);  // fp32 copies
     n += align_up((size_t)cdiv(C, 8) * 72 * cdiv(27 * dg, 64) * 64 * 4, 256) + align_up((size_t)cdiv(C, 8) * 72 * cdiv(Cout, 64) * 64 * 4, 256);
-    n += align_up(tc_conv_weight_bytes(27 * dg, C, 3, 2) + 256, 256) + align_up(tc_conv_weight_bytes(Cout, C, 3) + 256, 256);
+    n += 2 * align_up(tc_conv_weight_bytes(27 * dg, C, 3, 2) + 256, 256) + align_up(tc_conv_weight_bytes(Cout, C, 3) + 256, 256);
     n += 2 * align_up((size_t)(27 * dg + Cout) * 4, 256);
     return n + 8192;
 }
@@ -230,6 +230,7 @@ static int mdcn_pack_fwd_t(const void *x, const void *feat, const void *w_om, co
     const bool tc = dtype == RVSR_F16 && C == 64 && Cout == 64 && (C / dg) % 8 == 0 && tc_conv_weight_bytes(Com, C, 3, 2) > 0;
     void *wom_tc = tc ? cv.take(tc_conv_weight_bytes(Com, C, 3, 2) + 16) : nullptr;
     void *w_tc = tc ? cv.take(tc_conv_weight_bytes(Cout, C, 3) + 16) : nullptr;
+    void *wom_tc2 = (tc && tc2_weight_bytes(Com, C, 3, 2) > 0) ? cv.take(tc2_weight_bytes(Com, C, 3, 2) + 16) : nullptr;
     if (!cv.ok) { set_error("mdcn_pack: workspace too small"); return RVSR_E_WORKSPACE; }
     RVSR_TRY((launch_pack_nchw<T, T>((const T *)x, xa, B, C, H, W, s)));
     RVSR_TRY((launch_pack_nchw<T, T>((const T *)feat, fa, B, C, H, W, s)));
@@ -251,7 +252,8 @@ static int mdcn_pack_fwd_t(const void *x, const void *feat, const void *w_om, co
     if (tc) {
         RVSR_TRY(pack_weight_tc(wom, wom_tc, Com, C, 3, 2, s));
         RVSR_TRY(pack_weight_tc(w, w_tc, Cout, C, 3, 0, s));
-        co.w_tc = wom_tc; co.out_mode = OUT_OM24; co.dg = dg; co.out_image_stride = (long long)dg * 24 * H * W;
+        if (wom_tc2 != nullptr) RVSR_TRY(pack_weight_tc2(wom, wom_tc2, Com, C, 3, 2, s));
+        co.w_tc = wom_tc; co.w_tc2 = wom_tc2; co.out_mode = OUT_OM24; co.dg = dg; co.out_image_stride = (long long)dg * 24 * H * W;
         RVSR_CHECK_ARG(tc_conv_supported(co), "mdcn_pack: offset conv not covered by the tcgen05 kernel");
         RVSR_TRY(launch_conv_tc(co, s));
         d.w_tc = w_tc; d.om24 = om; d.om24_image_stride = co.out_image_stride; d.out = oa;
@@ -330,7 +332,7 @@ static int conv2d_fwd_t(const void *x1, const void *x2, const void *weight, cons
     const int cout_pad = cdiv(Cout, 64) * 64;
     float *wsimt = (float *)cv.take((size_t)cdiv(CinS, 8) * KK * 8 * cout_pad * 4);
     void *wtc = tc ? cv.take(tc_conv_weight_bytes(Cout, CinS, ks) + 16) : nullptr;
-    void *wtc2 = (tc && !shuffle && tc2_weight_bytes(Cout, CinS, ks) > 0) ? cv.take(tc2_weight_bytes(Cout, CinS, ks) + 16) : nullptr;
+    void *wtc2 = (tc && tc2_weight_bytes(Cout, CinS, ks, shuffle ? 1 : 0) > 0) ? cv.take(tc2_weight_bytes(Cout, CinS, ks, shuffle ? 1 : 0) + 16) : nullptr;
     if (!cv.ok) { set_error("conv2d: workspace too small"); return RVSR_E_WORKSPACE; }
     RVSR_TRY((launch_pack_nchw<T, T>((const T *)x1, a1, B, C1, H, W, s, C1s)));
     if (C2 > 0) RVSR_TRY((launch_pack_nchw<T, T>((const T *)x2, a2, B, C2, H, W, s)));
@@ -346,7 +348,7 @@ static int conv2d_fwd_t(const void *x1, const void *x2, const void *weight, cons
     RVSR_CHECK_ARG(C1 % 8 == 0 || C2 == 0, "conv2d: first source must have a multiple of 8 channels when concatenating");
     RVSR_TRY(pack_weight_simt(w, wsimt, Cout, CinS, ks, &cins, 1, cout_pad, s));
     if (tc && tc_conv_weight_bytes(Cout, CinS, ks) > 0) RVSR_TRY(pack_weight_tc(w, wtc, Cout, CinS, ks, shuffle, s));
-    if (wtc2 != nullptr) RVSR_TRY(pack_weight_tc2(w, wtc2, Cout, CinS, ks, s));
+    if (wtc2 != nullptr) RVSR_TRY(pack_weight_tc2(w, wtc2, Cout, CinS, ks, shuffle ? 1 : 0, s));
     ConvOp op = {};
     op.src[0] = Src{a1, (long long)cdiv(C1s, 8) * H * W * 8, C1s, 1, -1};
     op.nsrc = 1;

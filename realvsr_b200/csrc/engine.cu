@@ -183,13 +183,13 @@ int Engine::finalize(cudaStream_t s) {
                 else
                     RVSR_TRY(pack_weight_tc(wsrc, pc.w_tc, pc.Cout, pc.Cin, pc.ks, mode, s));
             }
-            const size_t tb2 = (!is_dcn && mode == 0) ? tc2_weight_bytes(pc.Cout, pc.Cin, pc.ks) : 0;
+            const size_t tb2 = (!is_dcn && !(is_om && mode != 2)) ? tc2_weight_bytes(pc.Cout, pc.Cin, pc.ks, mode) : 0;
             if (tb2 > 0) {
                 if (pc.w_tc2 == nullptr) {
                     RVSR_CUDA(cudaMalloc(&pc.w_tc2, tb2));
                     owned_.push_back(pc.w_tc2);
                 }
-                RVSR_TRY(pack_weight_tc2(wsrc, pc.w_tc2, pc.Cout, pc.Cin, pc.ks, s));
+                RVSR_TRY(pack_weight_tc2(wsrc, pc.w_tc2, pc.Cout, pc.Cin, pc.ks, mode, s));
             }
         }
     }

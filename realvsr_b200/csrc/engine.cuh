@@ -121,8 +121,8 @@ int launch_conv_tc(const ConvOp &op, cudaStream_t s);
 size_t tc_conv_weight_bytes(int Cout, int Cin, int ks, int mode = 0);
 // mode: 0 plain, 1 pixel-shuffle column order, 2 OUT_OM24 column order (Cout == 27 * dg)
 int pack_weight_tc(const float *w_oihw, void *dst, int Cout, int Cin, int ks, int mode, cudaStream_t s);
-size_t tc2_weight_bytes(int Cout, int Cin, int ks);
-int pack_weight_tc2(const float *w_oihw, void *dst, int Cout, int Cin, int ks, cudaStream_t s);
+size_t tc2_weight_bytes(int Cout, int Cin, int ks, int mode = 0);
+int pack_weight_tc2(const float *w_oihw, void *dst, int Cout, int Cin, int ks, int mode, cudaStream_t s);
 bool tc_dcn_supported(const DcnOp &op);
 int launch_dcn_tc(const DcnOp &op, cudaStream_t s);
 size_t tc_dcn_weight_bytes(int Cout, int C, int K);

@@ -638,12 +638,17 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {  // arrives on `
                  : "memory");
 }
 
-template <int KS>
+template <int KS, int NT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_tc2_kernel(const __grid_constant__ TcConvParams p) {
-    constexpr int NT = 64, NH2 = NT / 2;
+    constexpr int NH2 = NT / 2;
     constexpr int KK = KS * KS, PAD = KS / 2, VALID = TC_TW - (KS - 1), HALO_ROWS = TC_ROWS + KS - 1;
     constexpr int PLANE_BYTES = HALO_ROWS * TC_TW * 16;
-    constexpr int ACC = 64, MMAW = 3, EG = TC_EPI_GROUPS, NB = 6, TMEM_COLS = 512;
+    // one MMA instruction covers two tiles here, so two issuers suffice for the wide tiles, which leaves room for
+    // 4 accumulators (all 512 TMEM columns) and two epilogue groups (the OM24 / pixel-shuffle epilogues are the
+    // slower side of those kernels)
+    constexpr int ACC = acc_stride(NT), MMAW = ACC <= 64 ? 3 : 2, EG = TC_EPI_GROUPS, NB = ACC <= 64 ? 6 : 4, TMEM_COLS = 512;
+    static_assert(NT == 64 || NT == 128, "pair kernel is built for 64- and 128-wide tiles");
+    static_assert(NB % MMAW == 0 && NB % EG == 0 && NB * ACC <= 512, "accumulator plan");
     extern __shared__ __align__(1024) uint8_t smem[];
     const int Q = p.nsrc * p.C8s;
     const uint32_t w_bytes = (uint32_t)Q * KK * NH2 * 16;  // this CTA's half of the weights
@@ -665,6 +670,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
     const uint32_t rank = cluster_ctarank();
     const int cid = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
     const int npairs = (p.num_tiles + 1) / 2;
+    const int pss = blockIdx.y;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < MMAW * S; ++i) mbar_init(BAR(i), 2);                       // FULL: leader + peer arrive
@@ -673,13 +679,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
         fence_barrier_init();
         // this CTA's half of the weights: resident for the CTA's lifetime
         mbar_expect_tx(WFULL, w_bytes);
-        const uint8_t *wg = reinterpret_cast<const uint8_t *>(p.w) + (size_t)rank * w_bytes;
+        const uint8_t *wg = reinterpret_cast<const uint8_t *>(p.w) + ((size_t)pss * 2 + rank) * w_bytes;
         for (uint32_t o = 0; o < w_bytes; o += 32768) {
             const uint32_t n = w_bytes - o < 32768 ? w_bytes - o : 32768;
             bulk_load(smem_u32(w_s + o), wg + o, n, WFULL);
         }
     }
-    for (int i = threadIdx.x; i < NT; i += TC_THREADS) bias_s[i] = (p.bias != nullptr && i < p.Cout) ? p.bias[i] : 0.f;
+    for (int i = threadIdx.x; i < NT; i += TC_THREADS) {  // same column -> channel maps as conv_tc_kernel
+        const int co = pss * NT + i;
+        float b = 0.f;
+        if (p.bias != nullptr) {
+            if (p.out_mode == OUT_C8_SHUFFLE2) {
+                const int c = pss * (NT / 4) + i % (NT / 4), ij = i / (NT / 4);
+                b = (4 * c + ij) < p.Cout ? p.bias[4 * c + ij] : 0.f;
+            } else if (p.out_mode == OUT_OM24) {
+                const int g = pss * 4 + i / 32, j = i % 32;
+                if (g < p.dg && j < 27) b = p.bias[j < 18 ? g * 18 + j : 18 * p.dg + g * 9 + (j - 18)];
+            } else if (co < p.Cout) {
+                b = p.bias[co];
+            }
+        }
+        bias_s[i] = b;
+    }
     if (threadIdx.x == 0) mbar_wait(WFULL, 0);  // the leader's MMAs read the PEER's weight half too: both must have landed
     if (warp == 3) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
@@ -781,10 +802,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
             const uint32_t buf = t % NB;
             const int y = ty * TC_ROWS + lq, x = tx * VALID + lane;
             const bool valid = real && lane < VALID && y < p.H && x < p.W;
-            ep.prefetch(e, half, 0, n, y, x, valid);
+            ep.prefetch(e, half, pss, n, y, x, valid);
             mbar_wait(TFULL(buf), (t / NB) & 1);
             tc_fence_after();
-            ep.run(e, tmem_base + buf * ACC + ((uint32_t)(lq * 32) << 16), half, 0, n, y, x, valid, true, true, [&] {
+            ep.run(e, tmem_base + buf * ACC + ((uint32_t)(lq * 32) << 16), half, pss, n, y, x, valid, true, true, [&] {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(mapa_rank0(TEMPTY(buf)));  // the leader's issuer waits for both CTAs
@@ -870,26 +891,45 @@ int pack_weight_dcn_tc(const float *w_oihw, void *dst, int Cout, int C, int K, c
     return pack_weight_tc(w_oihw, dst, Cout, C, 3, 0, s);
 }
 
-// CTA-pair layout: [rank][tap][Q][32][8] -- each CTA of the pair owns 32 of the 64 output channels
-size_t tc2_weight_bytes(int Cout, int Cin, int ks) { return (Cout == 64 && ks == 3 && Cin % 16 == 0) ? (size_t)9 * (Cin / 8) * 64 * 16 : 0; }
-__global__ void pack_weight_tc2_kernel(const float *__restrict__ w, __half *__restrict__ dst, int Cin, int Q, long long total) {
+// CTA-pair layout: [pass][rank][tap][Q][NT/2][8] -- each CTA of the pair owns half of the pass's columns
+size_t tc2_weight_bytes(int Cout, int Cin, int ks, int mode) {
+    const int NT = tc_pick_nt(Cout, mode);
+    if (ks != 3 || (NT != 64 && NT != 128) || Cin % 16 != 0) return 0;
+    return tc_conv_weight_bytes(Cout, Cin, ks, mode);
+}
+__global__ void pack_weight_tc2_kernel(const float *__restrict__ w, __half *__restrict__ dst, int Cout, int Cin, int Q, int NT,
+                                       int mode, long long total) {
+    const int dg = Cout / 27, NH = NT / 2;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int e = (int)(i % 8);
         long long r = i / 8;
-        const int n = (int)(r % 32);
-        r /= 32;
+        const int nrow = (int)(r % NH);
+        r /= NH;
         const int q = (int)(r % Q);
         r /= Q;
         const int tap = (int)(r % 9);
-        const int rank = (int)(r / 9);
-        dst[i] = __float2half_rn(w[((long long)(rank * 32 + n) * Cin + q * 8 + e) * 9 + tap]);
+        r /= 9;
+        const int rank = (int)(r % 2);
+        const int pss = (int)(r / 2);
+        const int n = rank * NH + nrow, cin = q * 8 + e;
+        int co;
+        if (mode == 1) {
+            co = 4 * (pss * (NT / 4) + n % (NT / 4)) + n / (NT / 4);
+        } else if (mode == 2) {
+            const int g = pss * 4 + n / 32, j = n % 32;
+            co = (g < dg && j < 27) ? (j < 18 ? g * 18 + j : 18 * dg + g * 9 + (j - 18)) : Cout;
+        } else {
+            co = pss * NT + n;
+        }
+        dst[i] = __float2half_rn(co < Cout ? w[((long long)co * Cin + cin) * 9 + tap] : 0.f);
     }
 }
-int pack_weight_tc2(const float *w_oihw, void *dst, int Cout, int Cin, int ks, cudaStream_t s) {
-    RVSR_CHECK_ARG(tc2_weight_bytes(Cout, Cin, ks) > 0, "tc2 pack: needs Cout == 64, 3x3, Cin %% 16 == 0");
-    const long long total = (long long)2 * 9 * (Cin / 8) * 32 * 8;
+int pack_weight_tc2(const float *w_oihw, void *dst, int Cout, int Cin, int ks, int mode, cudaStream_t s) {
+    RVSR_CHECK_ARG(tc2_weight_bytes(Cout, Cin, ks, mode) > 0, "tc2 pack: unsupported shape");
+    const int NT = tc_pick_nt(Cout, mode);
+    const long long total = (long long)tc_passes(Cout, NT, mode) * 2 * 9 * (Cin / 8) * (NT / 2) * 8;
     pack_weight_tc2_kernel<<<(int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096), 256, 0, s>>>(
-        w_oihw, reinterpret_cast<__half *>(dst), Cin, Cin / 8, total);
+        w_oihw, reinterpret_cast<__half *>(dst), Cout, Cin, Cin / 8, NT, mode, total);
     RVSR_LAUNCH_CHECK();
     return RVSR_OK;
 }
@@ -1003,26 +1043,31 @@ int launch_conv_tc(const ConvOp &op, cudaStream_t s) {
     static const int dbg = getenv("RVSR_TC_DEBUG") ? atoi(getenv("RVSR_TC_DEBUG")) : 0;
     p.debug = dbg;
     const int sms = sm_count();
-    // CTA-pair kernel for the 64-wide 3x3 convolutions (the bulk of the network)
+    // CTA-pair kernels (cta_group::2) for the 3x3 convolutions with 64- and 128-wide tiles (the bulk of the network)
     static const bool two_cta = !(getenv("RVSR_TC_2CTA") != nullptr && getenv("RVSR_TC_2CTA")[0] == '0');
-    if (two_cta && op.w_tc2 != nullptr && pl.NT == 64 && op.ks == 3 && op.out_mode == OUT_C8 && op.Cout == 64 && p.num_tiles >= 4) {
-        const size_t wb2 = (size_t)op.nsrc * pl.C8s * 9 * 32 * 16;
+    if (two_cta && op.w_tc2 != nullptr && (pl.NT == 64 || pl.NT == 128) && op.ks == 3 && p.num_tiles >= 4 &&
+        (pl.NT == 128 || op.out_mode == OUT_C8)) {
+        const size_t wb2 = (size_t)op.nsrc * pl.C8s * 9 * (pl.NT / 2) * 16;
         const size_t stage = (size_t)pl.C8s * (TC_ROWS + 2) * TC_TW * 16;
-        const size_t fixed = wb2 + 128 + 64 * 4 + 512;
+        const size_t fixed = wb2 + 128 + pl.NT * 4 + 512;
         int st2 = (int)((TC_SMEM_LIMIT - fixed) / stage);
         if (st2 > 6) st2 = 6;
         p.nstages = st2;
         p.w = reinterpret_cast<const __half *>(op.w_tc2);
         const size_t smem2 = fixed + (size_t)st2 * stage + 1024;
-        static bool attr2 = false;
-        if (!attr2) {
-            RVSR_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT + 1024));
-            attr2 = true;
-        }
         const int npairs = (p.num_tiles + 1) / 2;
-        int clusters = sms / 2;
+        int clusters = (sms / 2) / pl.passes;
+        if (clusters < 1) clusters = 1;
         if (clusters > npairs) clusters = npairs;
-        conv_tc2_kernel<3><<<2 * clusters, TC_THREADS, smem2, s>>>(p);
+        if (pl.NT == 64) {
+            static bool a64 = false;
+            if (!a64) { RVSR_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<3, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT + 1024)); a64 = true; }
+            conv_tc2_kernel<3, 64><<<dim3(2 * clusters, pl.passes), TC_THREADS, smem2, s>>>(p);
+        } else {
+            static bool a128 = false;
+            if (!a128) { RVSR_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<3, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT + 1024)); a128 = true; }
+            conv_tc2_kernel<3, 128><<<dim3(2 * clusters, pl.passes), TC_THREADS, smem2, s>>>(p);
+        }
         RVSR_LAUNCH_CHECK();
         return RVSR_OK;
     }
