@@ -75,6 +75,8 @@ __device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity) {
     __trap();
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -1133,143 +1135,173 @@ __global__ void __launch_bounds__(DCN_THREADS, 1) dcn_tc_kernel(const __grid_con
                 bulk_load(smem_u32(w_s + o), reinterpret_cast<const uint8_t *>(p.w) + o, 24576, BAR(2 * S));
             constexpr uint32_t idesc = make_idesc(NT);
             mbar_wait(BAR(2 * S), 0);
-            uint32_t it = 0, t = 0;
+            uint32_t t = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++t) {
                 const uint32_t buf = t & 1;
                 mbar_wait(BAR(2 * S + 3 + buf), ((t >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d = tmem_base + buf * ACC;
-                for (int tap = 0; tap < K; ++tap, ++it) {
-                    const int st = it % S;
-                    mbar_wait_idle(BAR(st), (it / S) & 1);
-                    tc_fence_after();
-                    const uint32_t a0 = smem_u32(tap_s + st * DCN_TAP_BYTES);
-                    const uint32_t b0 = smem_u32(w_s) + (uint32_t)(tap * Q) * (NT * 16);
+                // 18 gather steps per tile (2 channel halves x 9 taps), two steps per ring stage
 #pragma unroll
-                    for (int kk = 0; kk < Q / 2; ++kk)
-                        umma_f16(d, make_desc(a0 + (uint32_t)(2 * kk) * 2048, 2048, 128),
-                                 make_desc(b0 + (uint32_t)(2 * kk) * (NT * 16), NT * 16, 128), idesc, (tap | kk) ? 1u : 0u);
+                for (int j = 0; j < 9; ++j) {
+                    constexpr int dummy = 0; (void)dummy;
+                    const int st = j % S;
+                    mbar_wait_idle(BAR(st), (t * 3 + j / S) & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int part = 0; part < 2; ++part) {
+                        const int s18 = 2 * j + part, h = s18 / 9, tap = s18 % 9;
+                        const uint32_t a0 = smem_u32(tap_s + st * DCN_TAP_BYTES + part * (DCN_TAP_BYTES / 2));
+                        const uint32_t b0 = smem_u32(w_s) + (uint32_t)(tap * Q + 4 * h) * (NT * 16);
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk)
+                            umma_f16(d, make_desc(a0 + (uint32_t)(2 * kk) * 2048, 2048, 128),
+                                     make_desc(b0 + (uint32_t)(2 * kk) * (NT * 16), NT * 16, 128), idesc, (s18 | kk) ? 1u : 0u);
+                    }
                     umma_commit(BAR(S + st));
                 }
                 umma_commit(BAR(2 * S + 1 + buf));
             }
         }
     } else if (warp <= DCN_GATHER_WARPS) {
-        // ---- gather: thread -> pixel m of the tile and 2 of the 8 channel blocks (q = qq, qq + 4).
-        // Branch-free: corner addresses are clamped into the image and out-of-range corners get a zero
-        // weight, so all 8 corner loads (2 blocks x 4 corners, 128 bit each) are issued back to back;
-        // the next tap's offsets/mask are fetched before the current tap is blended.
+        // ---- gather: thread -> pixel m of the tile and channel block qq of the current half (4 blocks).
+        // A tile is 18 steps (half 0 taps 0..8, half 1 taps 0..8), one bilinear sample per thread and step.
+        // Software pipeline: the four corner loads of step s+1 (also across halves and tiles) are issued
+        // before step s is blended, so the loads of a warp are never drained.  Branch-free: corner addresses
+        // are clamped into the image and out-of-range corners get a zero weight.  The loop is fully unrolled
+        // so the offset / mask registers (three 32 B blocks per pixel and group) are indexed statically.
+        static_assert(S == 3, "stage schedule below assumes 9 two-step stages over a ring of 3");
         const int gt = threadIdx.x - 32;
         const int m = gt & 127, qq = gt >> 7;
         const long long plane = (long long)p.H * p.W;
         const float Hf = (float)p.H, Wf = (float)p.W;
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int Hm1 = p.H - 1, Wm1 = p.W - 1;
+        struct Unit { const uint4 *pl; const uint4 *om; float by, bx; bool valid; };
+        struct Samp { uint4 c[4]; uint32_t w[4]; };
+        auto unit_of = [&](int tile, int half, bool pf) {
+            Unit u;
+            if (tile >= p.num_tiles) tile = p.num_tiles - 1;  // prefetch past the end: a harmless re-read
             const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, n = tile / (p.tiles_x * p.tiles_y);
             const int y = ty * TC_ROWS + (m >> 5), x = tx * TC_TW + (m & 31);
-            const bool valid = y < p.H && x < p.W;
-            const long long pix = valid ? (long long)y * p.W + x : 0;
-            const __half *xb = p.x + (long long)(p.x_map != nullptr ? __ldg(p.x_map + n) : n) * p.x_image_stride;
-            // offsets / mask of this pixel's two deformable groups (OUT_OM24): 3 blocks of 32 B per group
-            const uint4 *om[2];
-            uint32_t cur[2][8], mw[2][5];
-            float dy8[2], dx8[2];
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int g = ((qq + 4 * i) * 8) / p.cpg;
-                om[i] = p.om + (long long)n * p.om_stride + ((long long)(g * 3) * plane + pix) * 2;
-                const uint4 a = __ldg(om[i]), b = __ldg(om[i] + 1);                       // taps 0..3
-                const uint4 c2 = __ldg(om[i] + 4 * plane), d2 = __ldg(om[i] + 4 * plane + 1);  // dy8 dx8 + masks
-                cur[i][0] = a.x; cur[i][1] = a.y; cur[i][2] = a.z; cur[i][3] = a.w;
-                cur[i][4] = b.x; cur[i][5] = b.y; cur[i][6] = b.z; cur[i][7] = b.w;
-                dy8[i] = __uint_as_float(c2.x); dx8[i] = __uint_as_float(c2.y);
-                mw[i][0] = c2.z; mw[i][1] = c2.w; mw[i][2] = d2.x; mw[i][3] = d2.y; mw[i][4] = d2.z;
+            u.valid = y < p.H && x < p.W;
+            const long long pix = u.valid ? (long long)y * p.W + x : 0;
+            const int blk = half * 4 + qq, g = (blk * 8) / p.cpg;
+            const long long img = p.x_map != nullptr ? __ldg(p.x_map + n) : n;
+            u.pl = reinterpret_cast<const uint4 *>(p.x + img * p.x_image_stride + (long long)blk * plane * 8);
+            u.om = p.om + (long long)n * p.om_stride + ((long long)(g * 3) * plane + pix) * 2;
+            u.by = (float)(y - 1); u.bx = (float)(x - 1);
+            if (pf) {
+                // several steps ahead of the first use: the unit's offset/mask blocks into L2 (streamed from
+                // DRAM) and the undeformed 3x3 neighbourhood of its feature planes into L1
+                prefetch_l2(u.om); prefetch_l2(u.om + 2 * plane); prefetch_l2(u.om + 4 * plane);
+                const int xc = min(x, Wm1), yc = min(y, Hm1);
+                prefetch_l1(u.pl + (max(yc - 1, 0) * p.W + xc));
+                prefetch_l1(u.pl + (yc * p.W + xc));
+                prefetch_l1(u.pl + (min(yc + 1, Hm1) * p.W + xc));
             }
+            return u;
+        };
+        auto issue = [&](Samp &sm, const Unit &u, int tap, float dy, float dx, float mk) {
+            const float py = u.by + (float)(tap / 3) + dy, px = u.bx + (float)(tap % 3) + dx;
+            const bool inside = u.valid && py > -1.f && px > -1.f && py < Hf && px < Wf;
+            const float fy = floorf(inside ? py : 0.f), fx = floorf(inside ? px : 0.f);
+            const int y0 = (int)fy, x0 = (int)fx;
+            const float ly = py - fy, lx = px - fx, hy = 1.f - ly, hx = 1.f - lx;
+            const float m_in = inside ? mk : 0.f;  // mask folded into the weights
+            const float wy0 = y0 >= 0 ? hy * m_in : 0.f, wy1 = y0 + 1 <= Hm1 ? ly * m_in : 0.f;
+            const float wx0 = x0 >= 0 ? hx : 0.f, wx1 = x0 + 1 <= Wm1 ? lx : 0.f;
+            const float w0 = wy0 * wx0, w1 = wy0 * wx1, w2 = wy1 * wx0, w3 = wy1 * wx1;
+            const int r0 = max(y0, 0) * p.W, r1 = min(y0 + 1, Hm1) * p.W, x0c = max(x0, 0), x1c = min(x0 + 1, Wm1);
+            sm.c[0] = __ldg(u.pl + (r0 + x0c)); sm.c[1] = __ldg(u.pl + (r0 + x1c));
+            sm.c[2] = __ldg(u.pl + (r1 + x0c)); sm.c[3] = __ldg(u.pl + (r1 + x1c));
+            if (BLEND16) {
+                // corner weights (computed in fp32) rounded to fp16x2 for the HFMA2 blend
+                __half2 h0 = __float2half2_rn(w0), h1 = __float2half2_rn(w1), h2 = __float2half2_rn(w2), h3 = __float2half2_rn(w3);
+                sm.w[0] = *reinterpret_cast<uint32_t *>(&h0); sm.w[1] = *reinterpret_cast<uint32_t *>(&h1);
+                sm.w[2] = *reinterpret_cast<uint32_t *>(&h2); sm.w[3] = *reinterpret_cast<uint32_t *>(&h3);
+            } else {
+                sm.w[0] = __float_as_uint(w0); sm.w[1] = __float_as_uint(w1);
+                sm.w[2] = __float_as_uint(w2); sm.w[3] = __float_as_uint(w3);
+            }
+        };
+        auto blend = [&](const Samp &sm) {
+            uint4 pk;
+            if (BLEND16) {
+                // fp16x2 blend: 16 HFMA2 instead of 32 conversions + 32 FFMA; adds <= 3 fp16 roundings to a
+                // value that is stored as fp16 anyway.
+                __half2 *o = reinterpret_cast<__half2 *>(&pk);
+                const __half2 *wk = reinterpret_cast<const __half2 *>(sm.w);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    __half2 a = __hmul2(wk[0], reinterpret_cast<const __half2 *>(&sm.c[0])[j]);
+                    a = __hfma2(wk[1], reinterpret_cast<const __half2 *>(&sm.c[1])[j], a);
+                    a = __hfma2(wk[2], reinterpret_cast<const __half2 *>(&sm.c[2])[j], a);
+                    o[j] = __hfma2(wk[3], reinterpret_cast<const __half2 *>(&sm.c[3])[j], a);
+                }
+            } else {
+                float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const __half2 *h = reinterpret_cast<const __half2 *>(&sm.c[k]);
+                    const float wk = __uint_as_float(sm.w[k]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 f = __half22float2(h[j]);
+                        v[2 * j] = fmaf(wk, f.x, v[2 * j]);
+                        v[2 * j + 1] = fmaf(wk, f.y, v[2 * j + 1]);
+                    }
+                }
+                __half2 *h = reinterpret_cast<__half2 *>(&pk);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+            }
+            return pk;
+        };
+        // offsets / mask registers: A = taps 0..3, B = taps 4..7, C = [dy8 dx8 m01 m23][m45 m67 m8_ 0]
+        uint4 A[2][2], B[2], C[2][2];
+        Unit U[2];
+        Samp SM[2];
+        auto off_y = [&](int h, int t) -> float {
+            const uint4 &r = t < 4 ? A[h][t >> 1] : (t < 8 ? B[(t - 4) >> 1] : C[h][0]);
+            return __uint_as_float(t == 8 ? r.x : ((t & 1) ? r.z : r.x));
+        };
+        auto off_x = [&](int h, int t) -> float {
+            const uint4 &r = t < 4 ? A[h][t >> 1] : (t < 8 ? B[(t - 4) >> 1] : C[h][0]);
+            return __uint_as_float(t == 8 ? r.y : ((t & 1) ? r.w : r.y));
+        };
+        auto mask_of = [&](int h, int t) -> float {
+            const int wi = t >> 1;
+            const uint32_t word = wi == 0 ? C[h][0].z : wi == 1 ? C[h][0].w : wi == 2 ? C[h][1].x : wi == 3 ? C[h][1].y : C[h][1].z;
+            const __half2 mh = *reinterpret_cast<const __half2 *>(&word);
+            return (t & 1) ? __high2float(mh) : __low2float(mh);
+        };
+        auto load_AC = [&](int h) {
+            A[h][0] = __ldg(U[h].om); A[h][1] = __ldg(U[h].om + 1);
+            C[h][0] = __ldg(U[h].om + 4 * plane); C[h][1] = __ldg(U[h].om + 4 * plane + 1);
+        };
+        U[0] = unit_of(blockIdx.x, 0, false);
+        load_AC(0);
+        issue(SM[0], U[0], 0, off_y(0, 0), off_x(0, 0), mask_of(0, 0));
+        uint32_t t = 0;
 #pragma unroll 1
-            for (int tap = 0; tap < K; ++tap, ++it) {
-                const int st = it % S;
-                const float by = (float)(y - 1 + tap / 3), bx = (float)(x - 1 + tap % 3);
-                uint4 c[2][4];
-                float w[2][4];
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++t) {
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const float dy = __uint_as_float(cur[i][0]), dx = __uint_as_float(cur[i][1]);
-                    const __half2 mh = *reinterpret_cast<const __half2 *>(&mw[i][0]);
-                    const float mk = (tap & 1) ? __high2float(mh) : __low2float(mh);
-                    const float py = by + dy, px = bx + dx;
-                    const bool inside = valid && py > -1.f && px > -1.f && py < Hf && px < Wf;
-                    const float fy = floorf(inside ? py : 0.f), fx = floorf(inside ? px : 0.f);
-                    const int y0 = (int)fy, x0 = (int)fx;
-                    const float ly = py - fy, lx = px - fx, hy = 1.f - ly, hx = 1.f - lx;
-                    const float m_in = inside ? mk : 0.f;                 // mask folded into the weights
-                    const float wy0 = y0 >= 0 ? hy * m_in : 0.f, wy1 = y0 + 1 <= p.H - 1 ? ly * m_in : 0.f;
-                    const float wx0 = x0 >= 0 ? hx : 0.f, wx1 = x0 + 1 <= p.W - 1 ? lx : 0.f;
-                    w[i][0] = wy0 * wx0; w[i][1] = wy0 * wx1; w[i][2] = wy1 * wx0; w[i][3] = wy1 * wx1;
-                    const int y0c = max(y0, 0), y1c = min(y0 + 1, p.H - 1), x0c = max(x0, 0), x1c = min(x0 + 1, p.W - 1);
-                    const uint4 *pl = reinterpret_cast<const uint4 *>(xb + (long long)(qq + 4 * i) * plane * 8);
-                    c[i][0] = __ldg(pl + y0c * p.W + x0c); c[i][1] = __ldg(pl + y0c * p.W + x1c);
-                    c[i][2] = __ldg(pl + y1c * p.W + x0c); c[i][3] = __ldg(pl + y1c * p.W + x1c);
+            for (int s18 = 0; s18 < 18; ++s18) {
+                const int h = s18 / 9, tap = s18 % 9, st = (s18 >> 1) % S, part = s18 & 1;
+                if (tap == 0) { B[0] = __ldg(U[h].om + 2 * plane); B[1] = __ldg(U[h].om + 2 * plane + 1); }
+                if (tap == 1)  // set up the next unit (other half of this tile, or the first half of the next tile)
+                    U[h ^ 1] = h == 0 ? unit_of(tile, 1, true) : unit_of(tile + gridDim.x, 0, true);
+                if (tap == 6) load_AC(h ^ 1);
+                if (tap < 8) issue(SM[(s18 + 1) & 1], U[h], tap + 1, off_y(h, tap + 1), off_x(h, tap + 1), mask_of(h, tap + 1));
+                else issue(SM[(s18 + 1) & 1], U[h ^ 1], 0, off_y(h ^ 1, 0), off_x(h ^ 1, 0), mask_of(h ^ 1, 0));
+                const uint4 pk = blend(SM[s18 & 1]);
+                if (part == 0) mbar_wait(BAR(S + st), ((t * 3 + (s18 >> 1) / S) & 1) ^ 1);  // stage free (its MMAs completed)
+                *reinterpret_cast<uint4 *>(tap_s + st * DCN_TAP_BYTES + part * (DCN_TAP_BYTES / 2) + qq * 2048 + m * 16) = pk;
+                if (part == 1) {
+                    fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(BAR(st));
                 }
-                // advance the per-group offset / mask shift registers to the next tap
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    if (tap == 3) {  // taps 4..7 live in the second 32 B block
-                        const uint4 a = __ldg(om[i] + 2 * plane), b = __ldg(om[i] + 2 * plane + 1);
-                        cur[i][0] = a.x; cur[i][1] = a.y; cur[i][2] = a.z; cur[i][3] = a.w;
-                        cur[i][4] = b.x; cur[i][5] = b.y; cur[i][6] = b.z; cur[i][7] = b.w;
-                    } else if (tap == 7) {
-                        cur[i][0] = __float_as_uint(dy8[i]); cur[i][1] = __float_as_uint(dx8[i]);
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 6; ++k) cur[i][k] = cur[i][k + 2];
-                    }
-                    if (tap & 1) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) mw[i][k] = mw[i][k + 1];
-                    }
-                }
-                uint4 pk[2];
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    if (BLEND16) {
-                        // fp16x2 blend: corner weights (mask folded in, computed in fp32) are rounded to fp16 and
-                        // the four corners are combined with HFMA2 -- 16 instructions instead of 32 conversions
-                        // + 32 FFMA; adds <= 3 fp16 roundings to a value that is stored as fp16 anyway.
-                        __half2 wk[4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) wk[k] = __float2half2_rn(w[i][k]);
-                        __half2 *o = reinterpret_cast<__half2 *>(&pk[i]);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            __half2 a = __hmul2(wk[0], reinterpret_cast<const __half2 *>(&c[i][0])[j]);
-                            a = __hfma2(wk[1], reinterpret_cast<const __half2 *>(&c[i][1])[j], a);
-                            a = __hfma2(wk[2], reinterpret_cast<const __half2 *>(&c[i][2])[j], a);
-                            o[j] = __hfma2(wk[3], reinterpret_cast<const __half2 *>(&c[i][3])[j], a);
-                        }
-                    } else {
-                        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const __half2 *h = reinterpret_cast<const __half2 *>(&c[i][k]);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float2 f = __half22float2(h[j]);
-                                v[2 * j] = fmaf(w[i][k], f.x, v[2 * j]);
-                                v[2 * j + 1] = fmaf(w[i][k], f.y, v[2 * j + 1]);
-                            }
-                        }
-                        __half2 *h = reinterpret_cast<__half2 *>(&pk[i]);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-                    }
-                }
-                mbar_wait(BAR(S + st), ((it / S) & 1) ^ 1);  // stage free (its MMAs have completed)
-                uint8_t *dst = tap_s + st * DCN_TAP_BYTES + m * 16;
-#pragma unroll
-                for (int i = 0; i < 2; ++i) *reinterpret_cast<uint4 *>(dst + (qq + 4 * i) * 2048) = pk[i];
-                fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-                __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(st));
             }
         }
     } else {
