@@ -44,6 +44,33 @@ const char *get_error();
         }                                                                                 \
     } while (0)
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the engine path is launched with programmatic stream serialization: its CTAs may become
+// resident while the previous kernel of the stream is still draining, run their prologue (barrier init, TMEM
+// allocation, weight staging -- nothing produced by the previous kernel) and then block in pdl_wait() until the
+// previous grid has completed and its writes are visible.  pdl_trigger() lets the NEXT kernel do the same.
+// A kernel launched through launch_k() MUST execute pdl_wait() in every CTA before touching activations.
+// RVSR_PDL=0 launches the same kernels fully serialized (the two griddepcontrol instructions become no-ops).
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Only launches made inside a PdlScope (the engine's forward plan, whose weights were packed long before) use it;
+// the operator-level entry points pack weights right before their kernel and stay fully serialized.
+bool pdl_enabled();  // engine.cu
+struct PdlScope {
+    PdlScope();
+    ~PdlScope();
+};
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 #define RVSR_TRY(expr)            \
     do {                          \
         int _rc = (expr);         \

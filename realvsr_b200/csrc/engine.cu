@@ -28,6 +28,13 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 const char *get_error() { return g_err; }
+static thread_local int g_pdl_scope = 0;
+PdlScope::PdlScope() { ++g_pdl_scope; }
+PdlScope::~PdlScope() { --g_pdl_scope; }
+bool pdl_enabled() {
+    static const bool on = !(getenv("RVSR_PDL") != nullptr && getenv("RVSR_PDL")[0] == '0');
+    return on && g_pdl_scope > 0;
+}
 
 // ---------------------------------------------------------------- state_dict contract
 void Engine::expect(const std::string &name, std::vector<int64_t> shape) {
@@ -406,6 +413,7 @@ int Engine::run(Arena &ar, bool dry, const void *x, int x_dtype, void *out, int 
     static const bool tc_off = getenv("RVSR_DISABLE_TC") != nullptr && getenv("RVSR_DISABLE_TC")[0] == '1';
     Plan<T> P{this, ar, dry, s, packed_, cfg_.precision == RVSR_F16 && !tc_off};
     using PT = Plan<T>;
+    PdlScope pdl_scope;  // programmatic dependent launch for every kernel of the plan (common.cuh)
     // Three modes share this plan:
     //   full    (ca == null)        x = [B, N, nc, H, W] windows -> out
     //   extract (ca->extract)       x = [F, nc, H, W] frames -> pyramid written into cache slots [slot0, slot0+F)

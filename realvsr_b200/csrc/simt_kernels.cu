@@ -303,6 +303,8 @@ int pack_weight_simt(const float *w_oihw, float *dst, int Cout, int Cin_total, i
 template <typename T, typename Tin>
 __global__ void pack_nchw_kernel(const Tin *__restrict__ src, T *__restrict__ dst, int C, int Cdst, int H, int W,
                                  long long total) {
+    pdl_trigger();
+    pdl_wait();
     const int C8 = (Cdst + 7) / 8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -326,8 +328,7 @@ int launch_pack_nchw(const Tin *src, T *dst, int N, int C, int H, int W, cudaStr
     if (Cdst < C) Cdst = C;
     const long long total = (long long)N * ((Cdst + 7) / 8) * H * W;
     if (total == 0) return RVSR_OK;
-    pack_nchw_kernel<T, Tin><<<(int)((total + 255) / 256 < 8192 ? (total + 255) / 256 : 8192), 256, 0, s>>>(
-        src, dst, C, Cdst, H, W, total);
+    launch_k(pack_nchw_kernel<T, Tin>, dim3((int)((total + 255) / 256 < 8192 ? (total + 255) / 256 : 8192)), dim3(256), 0, s, src, dst, C, Cdst, H, W, total);
     RVSR_LAUNCH_CHECK();
     return RVSR_OK;
 }
@@ -394,6 +395,8 @@ int launch_fill_f32(float *dst, float v, long long n, cudaStream_t s) {
 template <typename T>
 __global__ void upsample2x_kernel(const T *__restrict__ src, T *__restrict__ dst, int H, int W, float scale,
                                   long long total) {
+    pdl_trigger();
+    pdl_wait();
     const int Ho = 2 * H, Wo = 2 * W;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -421,8 +424,7 @@ template <typename T>
 int launch_upsample2x(const T *src, T *dst, int N, int C, int H, int W, float scale, cudaStream_t s) {
     const long long total = (long long)N * ((C + 7) / 8) * (2 * H) * (2 * W);
     if (total == 0) return RVSR_OK;
-    upsample2x_kernel<T><<<(int)((total + 255) / 256 < 16384 ? (total + 255) / 256 : 16384), 256, 0, s>>>(
-        src, dst, H, W, scale, total);
+    launch_k(upsample2x_kernel<T>, dim3((int)((total + 255) / 256 < 16384 ? (total + 255) / 256 : 16384)), dim3(256), 0, s, src, dst, H, W, scale, total);
     RVSR_LAUNCH_CHECK();
     return RVSR_OK;
 }
@@ -434,6 +436,8 @@ template int launch_upsample2x<__half>(const __half *, __half *, int, int, int, 
 template <typename T>
 __global__ void pool_maxavg_kernel(const T *__restrict__ src, T *__restrict__ dmax, T *__restrict__ davg, int H,
                                    int W, long long total) {
+    pdl_trigger();
+    pdl_wait();
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -463,8 +467,7 @@ template <typename T>
 int launch_pool_maxavg(const T *src, T *dst_max, T *dst_avg, int N, int C, int H, int W, cudaStream_t s) {
     const long long total = (long long)N * ((C + 7) / 8) * ((H - 1) / 2 + 1) * ((W - 1) / 2 + 1);
     if (total == 0) return RVSR_OK;
-    pool_maxavg_kernel<T><<<(int)((total + 255) / 256 < 16384 ? (total + 255) / 256 : 16384), 256, 0, s>>>(
-        src, dst_max, dst_avg, H, W, total);
+    launch_k(pool_maxavg_kernel<T>, dim3((int)((total + 255) / 256 < 16384 ? (total + 255) / 256 : 16384)), dim3(256), 0, s, src, dst_max, dst_avg, H, W, total);
     RVSR_LAUNCH_CHECK();
     return RVSR_OK;
 }
@@ -478,6 +481,8 @@ template <typename T>
 __global__ void tsa_temporal_kernel(const T *__restrict__ emb, const T *__restrict__ emb_ref,
                                     const T *__restrict__ aligned, T *__restrict__ out, int frames, int C8,
                                     long long HW, long long total) {
+    pdl_trigger();
+    pdl_wait();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         const long long pix = i % HW;
@@ -507,8 +512,7 @@ int launch_tsa_temporal(const T *emb, const T *emb_ref, const T *aligned, T *out
                         int H, int W, cudaStream_t s) {
     const long long HW = (long long)H * W, total = (long long)B * frames * HW;
     if (total == 0) return RVSR_OK;
-    tsa_temporal_kernel<T><<<(int)((total + 127) / 128 < 16384 ? (total + 127) / 128 : 16384), 128, 0, s>>>(
-        emb, emb_ref, aligned, out, frames, (C + 7) / 8, HW, total);
+    launch_k(tsa_temporal_kernel<T>, dim3((int)((total + 127) / 128 < 16384 ? (total + 127) / 128 : 16384)), dim3(128), 0, s, emb, emb_ref, aligned, out, frames, (C + 7) / 8, HW, total);
     RVSR_LAUNCH_CHECK();
     return RVSR_OK;
 }
@@ -521,6 +525,8 @@ template int launch_tsa_temporal<__half>(const __half *, const __half *, const _
 template <typename T>
 __global__ void tsa_final_kernel(const T *__restrict__ fea, const T *__restrict__ att,
                                  const T *__restrict__ att_add, T *__restrict__ out, long long n8) {
+    pdl_trigger();
+    pdl_wait();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
          i += (long long)gridDim.x * blockDim.x) {
         float f[8], a[8], d[8];
@@ -536,8 +542,7 @@ template <typename T>
 int launch_tsa_final(const T *fea, const T *att, const T *att_add, T *out, long long n, cudaStream_t s) {
     const long long n8 = n / 8;
     if (n8 == 0) return RVSR_OK;
-    tsa_final_kernel<T><<<(int)((n8 + 255) / 256 < 16384 ? (n8 + 255) / 256 : 16384), 256, 0, s>>>(
-        fea, att, att_add, out, n8);
+    launch_k(tsa_final_kernel<T>, dim3((int)((n8 + 255) / 256 < 16384 ? (n8 + 255) / 256 : 16384)), dim3(256), 0, s, fea, att, att_add, out, n8);
     RVSR_LAUNCH_CHECK();
     return RVSR_OK;
 }
@@ -552,6 +557,8 @@ template <typename T, typename Tin, typename Tout>
 __global__ void final_add_kernel(const T *__restrict__ res, const Tin *__restrict__ x, Tout *__restrict__ out,
                                  int frames, int center, int nc, int H, int W, int scale, long long total,
                                  const int *__restrict__ center_map) {
+    pdl_trigger();
+    pdl_wait();
     const int Ho = H * scale, Wo = W * scale;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -590,8 +597,7 @@ int launch_final_add(const T *res_c8, const Tin *x, Tout *out, int B, int frames
     RVSR_CHECK_ARG(nc <= 8, "final_add: nc %d > 8", nc);
     const long long total = (long long)B * H * scale * W * scale;
     if (total == 0) return RVSR_OK;
-    final_add_kernel<T, Tin, Tout><<<(int)((total + 255) / 256 < 16384 ? (total + 255) / 256 : 16384), 256, 0, s>>>(
-        res_c8, x, out, frames, center, nc, H, W, scale, total, center_map);
+    launch_k(final_add_kernel<T, Tin, Tout>, dim3((int)((total + 255) / 256 < 16384 ? (total + 255) / 256 : 16384)), dim3(256), 0, s, res_c8, x, out, frames, center, nc, H, W, scale, total, center_map);
     RVSR_LAUNCH_CHECK();
     return RVSR_OK;
 }

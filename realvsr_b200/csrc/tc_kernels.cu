@@ -74,6 +74,17 @@ __device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity) {
     }
     __trap();
 }
+// tcgen05.mma / commit / TMA take their operands from uniform registers.  If the compiler cannot prove an
+// operand warp-uniform it wraps every instruction in a "waterfall" loop (ELECT + 5x R2UR.BROADCAST + BRA.U.ANY,
+// ~70 cycles per MMA).  So the issuing roles run their loops with the WHOLE warp on provably uniform values
+// (kernel parameters, blockIdx, values broadcast by shfl) and only the instruction itself is predicated on one
+// elected lane.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xFFFFFFFF;\n\tselp.b32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
@@ -414,16 +425,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const uint32_t WFULL = BAR((MMAW + 1) * S);
     auto TFULL = [&](int b) { return BAR((MMAW + 1) * S + 1 + b); };
     auto TEMPTY = [&](int b) { return BAR((MMAW + 1) * S + 1 + NB + b); };
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
     const int pss = blockIdx.y;
     // RVSR_TC_DEBUG & 16: per-role phase timing (clock64 sums over all tiles of CTA 0), printed at exit
     __shared__ long long ph_acc[3][8];
     const bool stamp = (p.debug & 16) && blockIdx.x == 0 && blockIdx.y == 0;
     if (threadIdx.x < 24) ph_acc[threadIdx.x / 8][threadIdx.x % 8] = 0;
     long long tprev = 0;
-#define PH_BEGIN() do { if (stamp) tprev = clock64(); } while (0)
-#define PH(role, k) do { if (stamp) { const long long tn = clock64(); ph_acc[role][k] += tn - tprev; tprev = tn; } } while (0)
+#define PH_BEGIN() do { if (stamp && lane == 0) tprev = clock64(); } while (0)
+#define PH(role, k) do { if (stamp && lane == 0) { const long long tn = clock64(); ph_acc[role][k] += tn - tprev; tprev = tn; } } while (0)
 
+    pdl_trigger();
     if (threadIdx.x == 0) {
         for (int i = 0; i < (MMAW + 1) * S + 1 + NB; ++i) mbar_init(BAR(i), 1);
         for (int i = 0; i < NB; ++i) mbar_init(TEMPTY(i), TC_EPI_WARPS / EG);
@@ -449,7 +461,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -460,6 +472,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 const uint32_t n = w_bytes - o < 32768 ? w_bytes - o : 32768;
                 bulk_load(smem_u32(w_s + o), wg + o, n, WFULL);
             }
+            pdl_wait();  // weights are static; everything below reads the previous kernel's output
             // ---- halo tiles
             uint32_t it = 0, tl = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
@@ -481,10 +494,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             }
         }
     } else if (warp <= MMAW) {
-        if (lane == 0) {
-            // ---- MMA issuer(s).  This single thread's instruction stream is the critical path of the
-            // whole kernel (the tensor pipe needs a new N=64 MMA every 48 cycles), so: no divisions, no
-            // 64-bit descriptor rebuilds, running counters instead of modulo, everything unrolled.
+        {
+            // ---- MMA issuer(s).  The issue stream is the critical path of the whole kernel (the tensor pipe
+            // needs a new N=64 MMA every 48 cycles), so: whole warp on uniform values (see elect_one()), no
+            // divisions, no 64-bit descriptor rebuilds, running counters instead of modulo, everything unrolled.
             constexpr uint32_t idesc = make_idesc(NT);
             const uint32_t mw = (uint32_t)(warp - 1);
             const uint32_t nsrc = (uint32_t)p.nsrc, C8s = (uint32_t)p.C8s;
@@ -516,31 +529,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     tc_fence_after();
                     if (mw == 0) PH(1, 3);
                     const uint32_t a_lo0 = a_base + st * stage_units;
+                    if (elect_one()) {
 #pragma unroll
-                    for (int tap = 0; tap < KK; ++tap) {
-                        const uint32_t a_lo = a_lo0 + (uint32_t)((tap / KS) * TC_TW + (tap % KS));
-                        const uint32_t b_lo = b_lo0 + (uint32_t)tap * b_tap_step;
-                        if (nk == 4) {
+                        for (int tap = 0; tap < KK; ++tap) {
+                            const uint32_t a_lo = a_lo0 + (uint32_t)((tap / KS) * TC_TW + (tap % KS));
+                            const uint32_t b_lo = b_lo0 + (uint32_t)tap * b_tap_step;
+                            if (nk == 4) {
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk)
-                                umma_f16(d, ((uint64_t)a_hi << 32) | (a_lo + (uint32_t)kk * (2 * PLANE_BYTES / 16)),
-                                         ((uint64_t)b_hi << 32) | (b_lo + (uint32_t)kk * (2 * NT)), idesc,
-                                         (tap | kk) ? 1u : (s ? 1u : 0u));
-                        } else {
-                            for (int kk = 0; kk < nk; ++kk)
-                                umma_f16(d, ((uint64_t)a_hi << 32) | (a_lo + (uint32_t)kk * (2 * PLANE_BYTES / 16)),
-                                         ((uint64_t)b_hi << 32) | (b_lo + (uint32_t)kk * (2 * NT)), idesc,
-                                         (tap | kk) ? 1u : (s ? 1u : 0u));
+                                for (int kk = 0; kk < 4; ++kk)
+                                    umma_f16(d, ((uint64_t)a_hi << 32) | (a_lo + (uint32_t)kk * (2 * PLANE_BYTES / 16)),
+                                             ((uint64_t)b_hi << 32) | (b_lo + (uint32_t)kk * (2 * NT)), idesc,
+                                             (tap | kk) ? 1u : (s ? 1u : 0u));
+                            } else {
+                                for (int kk = 0; kk < nk; ++kk)
+                                    umma_f16(d, ((uint64_t)a_hi << 32) | (a_lo + (uint32_t)kk * (2 * PLANE_BYTES / 16)),
+                                             ((uint64_t)b_hi << 32) | (b_lo + (uint32_t)kk * (2 * NT)), idesc,
+                                             (tap | kk) ? 1u : (s ? 1u : 0u));
+                            }
                         }
+                        umma_commit(EMPTY(st));  // stage reusable once these MMAs have read it
+                        if (s + 1 == nsrc) umma_commit(TFULL(buf));  // accumulator complete
                     }
+                    __syncwarp();
                     if (mw == 0) PH(1, 4);
-                    umma_commit(EMPTY(st));  // stage reusable once these MMAs have read it
-                    if (mw == 0) PH(1, 5);
                     b_lo0 += b_src_step;
                     if (++st == (uint32_t)S) st = 0;
                 }
-                umma_commit(TFULL(buf));  // accumulator complete
-                if (mw == 0) PH(1, 6);
                 if (MMAW > 1) {  // skip the stages of the tiles the other issuer(s) own
                     st += (MMAW - 1) * nsrc;
                     while (st >= (uint32_t)S) st -= (uint32_t)S;
@@ -548,6 +562,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             }
         }
     } else if (warp >= TC_EPI_WARP0) {
+        pdl_wait();  // residual reads / output writes (the issuers only consume what the producer loaded after its wait)
         const int lq = warp & 3;                         // TMEM lane quarter this warp may access == tile row
         constexpr int WPG = TC_EPI_WARPS / EG;                       // warps per epilogue group
         const int eg = (warp - TC_EPI_WARP0) / WPG;                  // this warp's group: tiles t == eg (mod groups)
@@ -668,12 +683,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
     const uint32_t WFULL = BAR((MMAW + 1) * S);
     auto TFULL = [&](int b) { return BAR((MMAW + 1) * S + 1 + b); };
     auto TEMPTY = [&](int b) { return BAR((MMAW + 1) * S + 1 + NB + b); };
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
+    const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const uint32_t rank = blockIdx.x & 1u;  // == %cluster_ctarank for __cluster_dims__(2, 1, 1); provably uniform
     const int cid = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
     const int npairs = (p.num_tiles + 1) / 2;
     const int pss = blockIdx.y;
 
+    pdl_trigger();
     if (threadIdx.x == 0) {
         for (int i = 0; i < MMAW * S; ++i) mbar_init(BAR(i), 2);                       // FULL: leader + peer arrive
         for (int i = MMAW * S; i < (MMAW + 1) * S + 1 + NB; ++i) mbar_init(BAR(i), 1);  // EMPTY, WFULL, TFULL
@@ -711,7 +727,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
     tc_fence_before();
     cluster_sync_all();   // barriers of both CTAs initialised before any remote arrive / multicast commit
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = uniform_u32(*tmem_slot);
+    pdl_wait();  // prologue (barriers, weights, TMEM) overlapped the previous kernel's tail; activations from here on
 
     if (warp == 0) {
         if (lane == 0) {
@@ -725,6 +742,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
                     const int st = it % S;
                     mbar_wait(EMPTY(st), ((it / S) & 1) ^ 1);
                     const uint32_t full0 = mapa_rank0(FULL(w, st));
+                    if (p.debug & 4) { mbar_arrive_cluster(full0); continue; }  // timing experiment: no halo loads
                     if (rank == 0)
                         mbar_expect_tx(FULL(w, st), 2 * stage_bytes);
                     else
@@ -737,7 +755,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
             }
         }
     } else if (warp <= MMAW) {
-        if (lane == 0 && rank == 0) {
+        if (rank == 0) {  // whole warp, uniform values; only the tcgen05 instructions are predicated on one lane
             constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((256u >> 4) << 24);  // M = 256 over the pair
             const uint32_t mw = (uint32_t)(warp - 1);
             const uint32_t nsrc = (uint32_t)p.nsrc, C8s = (uint32_t)p.C8s;
@@ -747,7 +765,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
             const uint32_t a_base = (uint32_t)adesc0, b_base = (uint32_t)bdesc0;
             const uint32_t stage_units = stage_bytes >> 4;
             const uint32_t b_src_step = C8s * (NH2 * 16 / 16), b_tap_step = (uint32_t)Q * (NH2 * 16 / 16);
-            const int nk = (int)C8s / 2;
+            const int nk = (p.debug & 1) ? 0 : (int)C8s / 2;
             uint32_t st = (mw * nsrc) % (uint32_t)S, par = 0;
             uint32_t t = mw;
             for (int pr = cid + (int)mw * nclusters; pr < npairs; pr += MMAW * nclusters, t += MMAW) {
@@ -761,28 +779,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
                     par ^= 1u << st;
                     tc_fence_after();
                     const uint32_t a_lo0 = a_base + st * stage_units;
+                    if (elect_one()) {
 #pragma unroll
-                    for (int tap = 0; tap < KK; ++tap) {
-                        const uint32_t a_lo = a_lo0 + (uint32_t)((tap / KS) * TC_TW + (tap % KS));
-                        const uint32_t b_lo = b_lo0 + (uint32_t)tap * b_tap_step;
-                        if (nk == 4) {
+                        for (int tap = 0; tap < KK; ++tap) {
+                            const uint32_t a_lo = a_lo0 + (uint32_t)((tap / KS) * TC_TW + (tap % KS));
+                            const uint32_t b_lo = b_lo0 + (uint32_t)tap * b_tap_step;
+                            if (nk == 4) {
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk)
-                                umma_f16_2sm(d, ((uint64_t)a_hi << 32) | (a_lo + (uint32_t)kk * (2 * PLANE_BYTES / 16)),
-                                             ((uint64_t)b_hi << 32) | (b_lo + (uint32_t)kk * (2 * NH2)), idesc,
-                                             (tap | kk) ? 1u : (s ? 1u : 0u));
-                        } else {
-                            for (int kk = 0; kk < nk; ++kk)
-                                umma_f16_2sm(d, ((uint64_t)a_hi << 32) | (a_lo + (uint32_t)kk * (2 * PLANE_BYTES / 16)),
-                                             ((uint64_t)b_hi << 32) | (b_lo + (uint32_t)kk * (2 * NH2)), idesc,
-                                             (tap | kk) ? 1u : (s ? 1u : 0u));
+                                for (int kk = 0; kk < 4; ++kk)
+                                    umma_f16_2sm(d, ((uint64_t)a_hi << 32) | (a_lo + (uint32_t)kk * (2 * PLANE_BYTES / 16)),
+                                                 ((uint64_t)b_hi << 32) | (b_lo + (uint32_t)kk * (2 * NH2)), idesc,
+                                                 (tap | kk) ? 1u : (s ? 1u : 0u));
+                            } else {
+                                for (int kk = 0; kk < nk; ++kk)
+                                    umma_f16_2sm(d, ((uint64_t)a_hi << 32) | (a_lo + (uint32_t)kk * (2 * PLANE_BYTES / 16)),
+                                                 ((uint64_t)b_hi << 32) | (b_lo + (uint32_t)kk * (2 * NH2)), idesc,
+                                                 (tap | kk) ? 1u : (s ? 1u : 0u));
+                            }
                         }
+                        umma_commit_2sm(EMPTY(st));
+                        if (s + 1 == nsrc) umma_commit_2sm(TFULL(buf));
                     }
-                    umma_commit_2sm(EMPTY(st));
+                    __syncwarp();
                     b_lo0 += b_src_step;
                     if (++st == (uint32_t)S) st = 0;
                 }
-                umma_commit_2sm(TFULL(buf));
                 st += (MMAW - 1) * nsrc;
                 while (st >= (uint32_t)S) st -= (uint32_t)S;
             }
@@ -807,7 +828,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
             ep.prefetch(e, half, pss, n, y, x, valid);
             mbar_wait(TFULL(buf), (t / NB) & 1);
             tc_fence_after();
-            ep.run(e, tmem_base + buf * ACC + ((uint32_t)(lq * 32) << 16), half, pss, n, y, x, valid, true, true, [&] {
+            ep.run(e, tmem_base + buf * ACC + ((uint32_t)(lq * 32) << 16), half, pss, n, y, x, valid, !(p.debug & 8), !(p.debug & 2), [&] {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(mapa_rank0(TEMPTY(buf)));  // the leader's issuer waits for both CTAs
@@ -985,7 +1006,7 @@ template <int KS, int NT> static int launch_conv_tc_t(const TcConvParams &p, con
     int gx = sms / pl.passes;
     if (gx < 1) gx = 1;
     if (gx > p.num_tiles) gx = p.num_tiles;
-    conv_tc_kernel<KS, NT><<<dim3(gx, pl.passes), TC_THREADS, pl.smem, s>>>(p);
+    launch_k(conv_tc_kernel<KS, NT>, dim3(gx, pl.passes), dim3(TC_THREADS), pl.smem, s, p);
     RVSR_LAUNCH_CHECK();
     return RVSR_OK;
 }
@@ -1064,11 +1085,11 @@ int launch_conv_tc(const ConvOp &op, cudaStream_t s) {
         if (pl.NT == 64) {
             static bool a64 = false;
             if (!a64) { RVSR_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<3, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT + 1024)); a64 = true; }
-            conv_tc2_kernel<3, 64><<<dim3(2 * clusters, pl.passes), TC_THREADS, smem2, s>>>(p);
+            launch_k(conv_tc2_kernel<3, 64>, dim3(2 * clusters, pl.passes), dim3(TC_THREADS), smem2, s, p);
         } else {
             static bool a128 = false;
             if (!a128) { RVSR_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<3, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT + 1024)); a128 = true; }
-            conv_tc2_kernel<3, 128><<<dim3(2 * clusters, pl.passes), TC_THREADS, smem2, s>>>(p);
+            launch_k(conv_tc2_kernel<3, 128>, dim3(2 * clusters, pl.passes), dim3(TC_THREADS), smem2, s, p);
         }
         RVSR_LAUNCH_CHECK();
         return RVSR_OK;
@@ -1112,8 +1133,9 @@ __global__ void __launch_bounds__(DCN_THREADS, 1) dcn_tc_kernel(const __grid_con
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * S + 5);
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
 
+    pdl_trigger();
     if (threadIdx.x == 0) {
         for (int i = 0; i < S; ++i) mbar_init(BAR(i), DCN_GATHER_WARPS);  // full: one arrive per gather warp
         for (int i = S; i < 2 * S + 3; ++i) mbar_init(BAR(i), 1);
@@ -1126,13 +1148,16 @@ __global__ void __launch_bounds__(DCN_THREADS, 1) dcn_tc_kernel(const __grid_con
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
     if (warp == 0) {
-        if (lane == 0) {
-            mbar_expect_tx(BAR(2 * S), w_bytes);
-            for (uint32_t o = 0; o < w_bytes; o += 24576)
-                bulk_load(smem_u32(w_s + o), reinterpret_cast<const uint8_t *>(p.w) + o, 24576, BAR(2 * S));
+        {   // whole warp on uniform values; the tcgen05 / bulk-copy instructions are predicated on one elected lane
+            if (elect_one()) {
+                mbar_expect_tx(BAR(2 * S), w_bytes);
+                for (uint32_t o = 0; o < w_bytes; o += 24576)
+                    bulk_load(smem_u32(w_s + o), reinterpret_cast<const uint8_t *>(p.w) + o, 24576, BAR(2 * S));
+            }
+            __syncwarp();
             constexpr uint32_t idesc = make_idesc(NT);
             mbar_wait(BAR(2 * S), 0);
             uint32_t t = 0;
@@ -1148,19 +1173,22 @@ __global__ void __launch_bounds__(DCN_THREADS, 1) dcn_tc_kernel(const __grid_con
                     const int st = j % S;
                     mbar_wait_idle(BAR(st), (t * 3 + j / S) & 1);
                     tc_fence_after();
+                    if (elect_one()) {
 #pragma unroll
-                    for (int part = 0; part < 2; ++part) {
-                        const int s18 = 2 * j + part, h = s18 / 9, tap = s18 % 9;
-                        const uint32_t a0 = smem_u32(tap_s + st * DCN_TAP_BYTES + part * (DCN_TAP_BYTES / 2));
-                        const uint32_t b0 = smem_u32(w_s) + (uint32_t)(tap * Q + 4 * h) * (NT * 16);
+                        for (int part = 0; part < 2; ++part) {
+                            const int s18 = 2 * j + part, h = s18 / 9, tap = s18 % 9;
+                            const uint32_t a0 = smem_u32(tap_s + st * DCN_TAP_BYTES + part * (DCN_TAP_BYTES / 2));
+                            const uint32_t b0 = smem_u32(w_s) + (uint32_t)(tap * Q + 4 * h) * (NT * 16);
 #pragma unroll
-                        for (int kk = 0; kk < 2; ++kk)
-                            umma_f16(d, make_desc(a0 + (uint32_t)(2 * kk) * 2048, 2048, 128),
-                                     make_desc(b0 + (uint32_t)(2 * kk) * (NT * 16), NT * 16, 128), idesc, (s18 | kk) ? 1u : 0u);
+                            for (int kk = 0; kk < 2; ++kk)
+                                umma_f16(d, make_desc(a0 + (uint32_t)(2 * kk) * 2048, 2048, 128),
+                                         make_desc(b0 + (uint32_t)(2 * kk) * (NT * 16), NT * 16, 128), idesc, (s18 | kk) ? 1u : 0u);
+                        }
+                        umma_commit(BAR(S + st));
+                        if (j == 8) umma_commit(BAR(2 * S + 1 + buf));
                     }
-                    umma_commit(BAR(S + st));
+                    __syncwarp();
                 }
-                umma_commit(BAR(2 * S + 1 + buf));
             }
         }
     } else if (warp <= DCN_GATHER_WARPS) {
@@ -1171,6 +1199,7 @@ __global__ void __launch_bounds__(DCN_THREADS, 1) dcn_tc_kernel(const __grid_con
         // are clamped into the image and out-of-range corners get a zero weight.  The loop is fully unrolled
         // so the offset / mask registers (three 32 B blocks per pixel and group) are indexed statically.
         static_assert(S == 3, "stage schedule below assumes 9 two-step stages over a ring of 3");
+        pdl_wait();  // features and offsets / mask come from the previous kernels
         const int gt = threadIdx.x - 32;
         const int m = gt & 127, qq = gt >> 7;
         const long long plane = (long long)p.H * p.W;
@@ -1305,6 +1334,7 @@ __global__ void __launch_bounds__(DCN_THREADS, 1) dcn_tc_kernel(const __grid_con
             }
         }
     } else {
+        pdl_wait();
         const int lq = warp & 3;
         EpiArgs e{bias_s, p.out, p.out_image_stride, nullptr, 0, p.H, p.W, NT, p.act, OUT_C8, 0, 0, 0};
         EpiTile<NT, 1> ep;
@@ -1359,9 +1389,9 @@ int launch_dcn_tc(const DcnOp &op, cudaStream_t s) {
     int gx = sm_count();
     if (gx > p.num_tiles) gx = p.num_tiles;
     if (blend32)
-        dcn_tc_kernel<false><<<gx, DCN_THREADS, smem, s>>>(p);
+        launch_k(dcn_tc_kernel<false>, dim3(gx), dim3(DCN_THREADS), smem, s, p);
     else
-        dcn_tc_kernel<true><<<gx, DCN_THREADS, smem, s>>>(p);
+        launch_k(dcn_tc_kernel<true>, dim3(gx), dim3(DCN_THREADS), smem, s, p);
     RVSR_LAUNCH_CHECK();
     return RVSR_OK;
 }
