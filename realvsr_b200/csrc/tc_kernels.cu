@@ -26,6 +26,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "engine.cuh"
 
 namespace rvsr {
@@ -45,6 +47,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // Bounded wait: a protocol bug traps (reported as a launch failure) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
+#pragma unroll 1
     for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -61,6 +64,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // the spinning warps do not take issue slots from the warps doing the work.
 __device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
+#pragma unroll 1
     for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -359,6 +363,91 @@ template <int NT, int NH> struct EpiTile {
     }
 };
 
+// Lean epilogue for the dominant case: 64-wide tile, OUT_C8, stride 1 (every 64 -> 64 / 128 -> 64 convolution of the
+// network).  The epilogue's instruction stream is ~1/6 of the step's energy (the step is power-capped), so: activation
+// as a template parameter, one 64-bit output pointer advanced by a constant plane stride, residual blocks fetched
+// before the accumulator wait, all 32 columns of the warp in registers with ONE tcgen05.wait::ld, and the TMEM
+// buffer handed back before any arithmetic.  Exact integer division of the tile index by precomputed magic
+// numbers (host: magic_div) replaces three hardware divisions per tile and warp.
+struct TileDiv { uint32_t m_tpi, tpi, m_tx, tx; };  // tiles per image, tiles per row + their magic multipliers
+// m = floor(2^32 / d) + 1 divides exactly while n_max * d < 2^32; otherwise 0 = "use the hardware division"
+__host__ inline uint32_t magic_div(uint32_t d, uint32_t n_max) {
+    return (d <= 1 || (unsigned long long)n_max * d >= 0xFFFFFFFFull) ? 0u : (uint32_t)(0x100000000ull / d) + 1u;
+}
+__device__ __forceinline__ uint32_t div_magic(uint32_t n, uint32_t m, uint32_t d) { return m == 0 ? n / d : __umulhi(n, m); }
+__device__ __forceinline__ void tile_coords(const TileDiv &td, int tile, int &tx, int &ty, int &n) {
+    const uint32_t img = div_magic((uint32_t)tile, td.m_tpi, td.tpi), r = (uint32_t)tile - img * td.tpi;
+    const uint32_t row = div_magic(r, td.m_tx, td.tx);
+    n = (int)img; ty = (int)row; tx = (int)(r - row * td.tx);
+}
+
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)));
+    return *reinterpret_cast<float2 *>(&r);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)));
+    return *reinterpret_cast<float2 *>(&r);
+}
+
+template <int ACT, typename Release>
+__device__ __forceinline__ void epi_c8_fast(const float *bias_s, __half *out, long long out_image_stride, const __half *residual,
+                                            long long res_image_stride, int H, int W, int Co8, uint32_t taddr, int half,
+                                            int qbase, int n, int y, int x, bool valid, uint32_t full_bar, uint32_t full_par,
+                                            Release &&release) {
+    constexpr int NBLK = 4;  // this warp's 32 columns = 4 channel blocks
+    const long long plane = (long long)H * W, pix = (long long)y * W + x;
+    const int q0 = qbase + half * NBLK;  // first output channel block of this warp (qbase: blocks of earlier N-passes)
+    uint4 res[NBLK];
+    const bool has_res = residual != nullptr && valid;
+    if (has_res) {
+        const uint4 *r = reinterpret_cast<const uint4 *>(residual + (long long)n * res_image_stride) + q0 * plane + pix;
+#pragma unroll
+        for (int j = 0; j < NBLK; ++j) res[j] = q0 + j < Co8 ? __ldg(r + j * plane) : make_uint4(0, 0, 0, 0);
+    }
+    mbar_wait(full_bar, full_par);
+    tc_fence_after();
+    uint32_t a0[16], a1[16];
+    tmem_ld16_nowait(taddr + half * 32, a0);
+    tmem_ld16_nowait(taddr + half * 32 + 16, a1);
+    tmem_ld_wait();
+    release();
+    if (!valid) return;
+    uint4 *o = reinterpret_cast<uint4 *>(out + (long long)n * out_image_stride) + q0 * plane + pix;
+    const float *b = bias_s + half * 32;
+#pragma unroll
+    for (int j = 0; j < NBLK; ++j) {
+        if (q0 + j >= Co8) break;
+        const float4 b0 = *reinterpret_cast<const float4 *>(b + j * 8), b1 = *reinterpret_cast<const float4 *>(b + j * 8 + 4);
+        const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+        const uint32_t *a = (j < 2 ? a0 : a1) + (j & 1) * 8;
+        float2 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {  // packed fp32 pairs (FADD2 / FMUL2): same IEEE results, half the instructions
+            v[i] = add2(make_float2(__uint_as_float(a[2 * i]), __uint_as_float(a[2 * i + 1])), bb[i]);
+            if (ACT == RVSR_ACT_LRELU) {
+                const float2 t = mul2(v[i], make_float2(0.1f, 0.1f));
+                v[i] = make_float2(fmaxf(v[i].x, t.x), fmaxf(v[i].y, t.y));
+            } else if (ACT == RVSR_ACT_RELU) {
+                v[i] = make_float2(fmaxf(v[i].x, 0.f), fmaxf(v[i].y, 0.f));
+            }
+        }
+        if (has_res) {
+            const __half2 *h = reinterpret_cast<const __half2 *>(&res[j]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = add2(v[i], __half22float2(h[i]));
+        }
+        uint4 pk;
+        __half2 *h = reinterpret_cast<__half2 *>(&pk);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[i].x, v[i].y);
+        *o = pk;
+        o += plane;
+    }
+}
+
 // ---------------------------------------------------------------- convolution
 struct alignas(64) TcConvParams {
     CUtensorMap tmap[RVSR_MAX_SRC];
@@ -374,6 +463,7 @@ struct alignas(64) TcConvParams {
     long long res_image_stride;
     int N, H, W, Cout, act, out_mode, sig_from, subsample, dg;
     int tiles_x, tiles_y, num_tiles;
+    TileDiv td;
     int debug;  // RVSR_TC_DEBUG bit mask for timing experiments only (results become garbage):
                 // 1 = issue no MMAs, 2 = no epilogue stores, 4 = no TMA halo loads, 8 = no TMEM loads
 };
@@ -817,6 +907,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
                   p.out_mode, p.sig_from, p.subsample, p.dg};
         EpiTile<NT, WPG / 4> ep;
         uint32_t t = (uint32_t)eg;
+        if (NT == 64 && WPG == 8 && p.out_mode == OUT_C8 && !p.subsample && p.debug == 0) {
+            // lean path (see epi_c8_fast): every 64-wide stride-1 convolution of the network
+            auto tiles = [&](auto act_tag) {
+                constexpr int ACT = decltype(act_tag)::value;
+                const int Co8 = (p.Cout + 7) / 8;
+                uint32_t buf = (uint32_t)eg, par = 0;  // buf = t % NB, par = (t / NB) & 1 without divisions
+                for (int pr = cid + eg * nclusters; pr < npairs; pr += EG * nclusters) {
+                    const int tile = 2 * pr + (int)rank;
+                    const bool real = tile < p.num_tiles;
+                    int tx, ty, n;
+                    tile_coords(p.td, real ? tile : p.num_tiles - 1, tx, ty, n);
+                    const int y = ty * TC_ROWS + lq, x = tx * VALID + lane;
+                    const bool valid = real && lane < VALID && y < p.H && x < p.W;
+                    const uint32_t tempty0 = mapa_rank0(TEMPTY(buf));
+                    epi_c8_fast<ACT>(bias_s, reinterpret_cast<__half *>(p.out), p.out_image_stride, p.residual, p.res_image_stride,
+                                     p.H, p.W, Co8, tmem_base + buf * ACC + ((uint32_t)(lq * 32) << 16), half, pss * (NT / 8), n, y, x,
+                                     valid, TFULL(buf), par, [&] {
+                                         tc_fence_before();
+                                         __syncwarp();
+                                         if (lane == 0) mbar_arrive_cluster(tempty0);
+                                     });
+                    buf += EG;
+                    if (buf >= (uint32_t)NB) { buf -= NB; par ^= 1u; }
+                }
+            };
+            if (p.act == RVSR_ACT_LRELU) tiles(std::integral_constant<int, RVSR_ACT_LRELU>{});
+            else if (p.act == RVSR_ACT_RELU) tiles(std::integral_constant<int, RVSR_ACT_RELU>{});
+            else tiles(std::integral_constant<int, RVSR_ACT_NONE>{});
+        } else
         for (int pr = cid + eg * nclusters; pr < npairs; pr += EG * nclusters, t += EG) {
             const int tile = 2 * pr + (int)rank;
             const bool real = tile < p.num_tiles;
@@ -1063,6 +1182,8 @@ int launch_conv_tc(const ConvOp &op, cudaStream_t s) {
     p.tiles_x = cdiv(op.W, valid); p.tiles_y = cdiv(op.H, TC_ROWS);
     p.num_tiles = p.tiles_x * p.tiles_y * op.N;
     if (p.num_tiles == 0) return RVSR_OK;
+    p.td.tpi = (uint32_t)(p.tiles_x * p.tiles_y); p.td.m_tpi = magic_div(p.td.tpi, (uint32_t)p.num_tiles);
+    p.td.tx = (uint32_t)p.tiles_x; p.td.m_tx = magic_div(p.td.tx, p.td.tpi);
     static const int dbg = getenv("RVSR_TC_DEBUG") ? atoi(getenv("RVSR_TC_DEBUG")) : 0;
     p.debug = dbg;
     const int sms = sm_count();
