@@ -183,6 +183,16 @@ enum OutMode {
                           // 24 words = 3 blocks of 32 B: [dy0 dx0 .. dy3 dx3][dy4 dx4 .. dy7 dx7]
                           // [dy8 dx8 m01 m23 m45 m67 m8_ 0], offsets fp32, sigmoid(mask) as fp16 pairs;
                           // memory [n][dg*3][H][W][8 words]
+    OUT_FINAL = 5,        // network output (tcgen05 conv_last only): NCHW of fin.out_dtype, plus the bilinear x`scale`
+                          // upsample of the centre LQ frame (EDVR_arch.py:315-319) -- no conv_last tensor, no extra pass
+};
+
+// OUT_FINAL: where the base frame comes from (same arithmetic as final_add_kernel)
+struct FinalAdd {
+    const void *x;           // LQ clip, NCHW [B * frames (or all cached frames)][nc][H / scale][W / scale]
+    const int *center_map;   // optional: image b -> index of its centre frame in x (feature-cache mode)
+    int x_dtype, out_dtype;  // RVSR_F32 / RVSR_F16
+    int frames, center, nc, scale;
 };
 
 struct ConvOp {
@@ -200,6 +210,7 @@ struct ConvOp {
     int Cout, ks, stride;  // pad = ks / 2
     int act, out_mode, sig_from;
     int dg;                // OUT_OM24: deformable groups (Cout == 27 * dg)
+    FinalAdd fin;          // OUT_FINAL
 };
 
 struct DcnOp {

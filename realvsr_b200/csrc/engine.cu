@@ -576,8 +576,38 @@ int Engine::run(Arena &ar, bool dry, const void *x, int x_dtype, void *out, int 
         scale = 4;
     }
     r = P.conv("HRconv", {PT::src_of(r)}, B, r.H, r.W, LR);
-    Act last = P.conv("conv_last", {PT::src_of(r)}, B, r.H, r.W, NONE);
-    if (!dry && P.rc == RVSR_OK) {
+    // conv_last + base frame: one tcgen05 launch that writes the NCHW result (OUT_FINAL) when the shape allows it
+    bool fused_final = false;
+    if (P.use_tc && sizeof(T) == 2 && nc <= 8) {
+        const PackedConv *pc = P.get("conv_last");
+        if (pc != nullptr && pc->w_tc != nullptr && r.C % 16 == 0 && r.C <= 64) {
+            fused_final = true;
+            if (!dry && P.rc == RVSR_OK) {
+                ConvOp op = {};
+                op.src[0] = PT::src_of(r); op.nsrc = 1;
+                op.w_simt = pc->w_simt; op.w_tc = pc->w_tc; op.w_tc2 = nullptr; op.bias = pc->bias;
+                op.out = out; op.out_image_stride = 0;
+                op.N = B; op.H = r.H; op.W = r.W; op.Cout = pc->Cout; op.ks = pc->ks; op.stride = 1;
+                op.act = NONE; op.out_mode = OUT_FINAL; op.sig_from = 1 << 30;
+                op.fin.x = x; op.fin.center_map = map_ctr; op.fin.x_dtype = x_dtype; op.fin.out_dtype = out_dtype;
+                op.fin.frames = N; op.fin.center = ctr; op.fin.nc = nc; op.fin.scale = scale;
+                if (!tc_conv_supported(op)) {
+                    fused_final = false;
+                } else {
+                    const double px = (double)B * r.H * r.W;
+                    P.launch("tc:conv3x3_final_co" + std::to_string(pc->Cout) + ":conv_last", 2.0 * r.C * pc->Cout * 9 * px,
+                             px * r.C * sizeof(T) + px * nc * (out_dtype == RVSR_F32 ? 4 : 2) + (double)B * nc * H * W * (x_dtype == RVSR_F32 ? 4 : 2),
+                             [&] { return launch_conv_tc(op, s); });
+                }
+            }
+        }
+    }
+    if (dry && fused_final) {
+        // the dry run cannot ask tc_conv_supported (no pointers yet): reserve the unfused tensor so both plans agree
+        fused_final = false;
+    }
+    Act last = fused_final ? Act() : P.conv("conv_last", {PT::src_of(r)}, B, r.H, r.W, NONE);
+    if (!fused_final && !dry && P.rc == RVSR_OK) {
         const T *lp = (const T *)last.p;
         P.launch("glue:final_add_base:", 0, (double)last.elems() * sizeof(T) + (double)B * nc * last.H * last.W * 4, [&] {
             if (x_dtype == RVSR_F32 && out_dtype == RVSR_F32)

@@ -392,39 +392,58 @@ int launch_fill_f32(float *dst, float v, long long n, cudaStream_t s) {
 // ---------------------------------------------------------------- x2 bilinear upsample (align_corners=False)
 // F.interpolate(scale_factor=2, mode='bilinear') optionally times `scale`
 // (EDVR_arch.py:111-112: upsampled offsets are multiplied by 2 after interpolation).
+// One thread per SOURCE pixel of one channel block: it produces the 2x2 output quad from the 3x3 source
+// neighbourhood (9 x 16 B loads for 4 x 16 B stores instead of 16 loads; the two outputs of a row are one
+// contiguous 32 B).  F.interpolate(scale_factor=2, bilinear, align_corners=False): output 2k reads sources
+// (k-1, k) with weights (0.25, 0.75), output 2k+1 reads (k, k+1) with (0.75, 0.25); indices clamp at the borders
+// (EDVR_arch.py:111-112, :120-121 multiply the upsampled OFFSETS by 2 -- `scale`).  grid.y = (image, block) plane.
 template <typename T>
-__global__ void upsample2x_kernel(const T *__restrict__ src, T *__restrict__ dst, int H, int W, float scale,
-                                  long long total) {
+__global__ void upsample2x_kernel(const T *__restrict__ src, T *__restrict__ dst, int H, int W, float scale) {
     pdl_trigger();
     pdl_wait();
-    const int Ho = 2 * H, Wo = 2 * W;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int ox = (int)(i % Wo);
-        long long r = i / Wo;
-        const int oy = (int)(r % Ho);
-        const long long pl = r / Ho;  // (image, channel block)
-        const float sy = fmaxf(0.5f * (oy + 0.5f) - 0.5f, 0.f), sx = fmaxf(0.5f * (ox + 0.5f) - 0.5f, 0.f);
-        const int y0 = (int)sy, x0 = (int)sx;
-        const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
-        const float ly = sy - y0, lx = sx - x0;
-        const T *p = src + pl * H * W * 8;
-        float a[8], b[8], c[8], d[8], o[8];
-        load8<T>(p + ((long long)y0 * W + x0) * 8, a);
-        load8<T>(p + ((long long)y0 * W + x1) * 8, b);
-        load8<T>(p + ((long long)y1 * W + x0) * 8, c);
-        load8<T>(p + ((long long)y1 * W + x1) * 8, d);
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= H * W) return;
+    const int y = idx / W, x = idx - y * W;
+    const long long pl = blockIdx.y;
+    const T *p = src + pl * H * W * 8;
+    const int ym = max(y - 1, 0), yp = min(y + 1, H - 1), xm = max(x - 1, 0), xp = min(x + 1, W - 1);
+    const int rows[3] = {ym, y, yp};
+    float hl[3][8], hr[3][8];  // horizontally blended rows: left output (2x) and right output (2x + 1)
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-            o[k] = scale * ((1.f - ly) * ((1.f - lx) * a[k] + lx * b[k]) + ly * ((1.f - lx) * c[k] + lx * d[k]));
-        store8<T>(dst + i * 8, o);
+    for (int r = 0; r < 3; ++r) {
+        float a[8], b[8], c[8];
+        const T *row = p + (long long)rows[r] * W * 8;
+        load8<T>(row + xm * 8, a);
+        load8<T>(row + x * 8, b);
+        load8<T>(row + xp * 8, c);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            hl[r][k] = 0.25f * a[k] + 0.75f * b[k];
+            hr[r][k] = 0.75f * b[k] + 0.25f * c[k];
+        }
     }
+    T *o = dst + (pl * (2 * H) + 2 * y) * (long long)(2 * W) * 8 + (long long)(2 * x) * 8;
+    float t[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t[k] = scale * (0.25f * hl[0][k] + 0.75f * hl[1][k]);
+    store8<T>(o, t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t[k] = scale * (0.25f * hr[0][k] + 0.75f * hr[1][k]);
+    store8<T>(o + 8, t);
+    o += (long long)(2 * W) * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t[k] = scale * (0.75f * hl[1][k] + 0.25f * hl[2][k]);
+    store8<T>(o, t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t[k] = scale * (0.75f * hr[1][k] + 0.25f * hr[2][k]);
+    store8<T>(o + 8, t);
 }
 template <typename T>
 int launch_upsample2x(const T *src, T *dst, int N, int C, int H, int W, float scale, cudaStream_t s) {
-    const long long total = (long long)N * ((C + 7) / 8) * (2 * H) * (2 * W);
-    if (total == 0) return RVSR_OK;
-    launch_k(upsample2x_kernel<T>, dim3((int)((total + 255) / 256 < 16384 ? (total + 255) / 256 : 16384)), dim3(256), 0, s, src, dst, H, W, scale, total);
+    const int planes = N * ((C + 7) / 8);
+    if (planes == 0 || H == 0 || W == 0) return RVSR_OK;
+    RVSR_CHECK_ARG(planes <= 65535, "upsample2x: too many (image, channel block) planes: %d", planes);
+    launch_k(upsample2x_kernel<T>, dim3((H * W + 127) / 128, planes), dim3(128), 0, s, src, dst, H, W, scale);
     RVSR_LAUNCH_CHECK();
     return RVSR_OK;
 }

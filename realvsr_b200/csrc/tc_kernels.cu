@@ -156,6 +156,7 @@ struct EpiArgs {
     const __half *residual;
     long long res_image_stride;
     int H, W, Cout, act, out_mode, sig_from, subsample, dg;
+    const FinalAdd *fin;  // OUT_FINAL
 };
 
 // Epilogue of one pixel (= TMEM lane) of one tile.  With NH = 2 two warps share a TMEM lane
@@ -330,8 +331,47 @@ template <int NT, int NH> struct EpiTile {
         }
     }
 
+    // OUT_FINAL: out[n, c, y, x] = conv_last + bias + bilinear(center LQ frame) -- the reference's last two lines
+    // (EDVR_arch.py:315-319) without materialising conv_last's output; base arithmetic as in final_add_kernel.
+    __device__ __forceinline__ void store_final(const EpiArgs &e, int half, int ch, int n, int y, int x) {
+        if (half != 0 || ch != 0) return;
+        const FinalAdd &f = *e.fin;
+        const int Hl = e.H / f.scale, Wl = e.W / f.scale;
+        const long long cimg = f.center_map != nullptr ? (long long)__ldg(f.center_map + n) : (long long)n * f.frames + f.center;
+        const long long lplane = (long long)Hl * Wl, hplane = (long long)e.H * e.W;
+        int y0 = y, x0 = x, y1 = y, x1 = x;
+        float ly = 0.f, lx = 0.f;
+        if (f.scale != 1) {
+            const float inv = 1.f / f.scale;
+            const float sy = fmaxf(inv * (y + 0.5f) - 0.5f, 0.f), sx = fmaxf(inv * (x + 0.5f) - 0.5f, 0.f);
+            y0 = (int)sy; x0 = (int)sx;
+            y1 = y0 + (y0 < Hl - 1 ? 1 : 0); x1 = x0 + (x0 < Wl - 1 ? 1 : 0);
+            ly = sy - y0; lx = sx - x0;
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            if (c >= f.nc) break;
+            const long long pc = (cimg * f.nc + c) * lplane;
+            float p00, p01, p10, p11;
+            if (f.x_dtype == RVSR_F32) {
+                const float *xp = reinterpret_cast<const float *>(f.x) + pc;
+                p00 = __ldg(xp + y0 * Wl + x0); p01 = __ldg(xp + y0 * Wl + x1); p10 = __ldg(xp + y1 * Wl + x0); p11 = __ldg(xp + y1 * Wl + x1);
+            } else {
+                const __half *xp = reinterpret_cast<const __half *>(f.x) + pc;
+                p00 = __half2float(__ldg(xp + y0 * Wl + x0)); p01 = __half2float(__ldg(xp + y0 * Wl + x1));
+                p10 = __half2float(__ldg(xp + y1 * Wl + x0)); p11 = __half2float(__ldg(xp + y1 * Wl + x1));
+            }
+            const float base = f.scale == 1 ? p00 : (1.f - ly) * ((1.f - lx) * p00 + lx * p01) + ly * ((1.f - lx) * p10 + lx * p11);
+            const float v = apply_act(__uint_as_float(acc[0][c]) + e.bias_s[c], e.act) + base;
+            const long long oi = ((long long)n * f.nc + c) * hplane + (long long)y * e.W + x;
+            if (f.out_dtype == RVSR_F32) reinterpret_cast<float *>(e.out)[oi] = v;
+            else reinterpret_cast<__half *>(e.out)[oi] = __float2half_rn(v);
+        }
+    }
+
     __device__ __forceinline__ void store(const EpiArgs &e, int half, int ch, int pss, int n, int y, int x, bool valid) {
         if (!valid) return;
+        if (e.out_mode == OUT_FINAL) { store_final(e, half, ch, n, y, x); return; }
         if (e.out_mode == OUT_C8) {
             if (e.act == RVSR_ACT_LRELU) store_c8<RVSR_ACT_LRELU>(e, half, ch, pss, n, y, x);
             else if (e.act == RVSR_ACT_RELU) store_c8<RVSR_ACT_RELU>(e, half, ch, pss, n, y, x);
@@ -464,6 +504,7 @@ struct alignas(64) TcConvParams {
     int N, H, W, Cout, act, out_mode, sig_from, subsample, dg;
     int tiles_x, tiles_y, num_tiles;
     TileDiv td;
+    FinalAdd fin;
     int debug;  // RVSR_TC_DEBUG bit mask for timing experiments only (results become garbage):
                 // 1 = issue no MMAs, 2 = no epilogue stores, 4 = no TMA halo loads, 8 = no TMEM loads
 };
@@ -658,7 +699,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int eg = (warp - TC_EPI_WARP0) / WPG;                  // this warp's group: tiles t == eg (mod groups)
         const int half = ((warp - TC_EPI_WARP0) % WPG) >> 2;         // WPG / 4 warps per lane quarter split the columns
         EpiArgs e{bias_s, p.out, p.out_image_stride, p.residual, p.res_image_stride, p.H, p.W, p.Cout, p.act,
-                  p.out_mode, p.sig_from, p.subsample, p.dg};
+                  p.out_mode, p.sig_from, p.subsample, p.dg, &p.fin};
         EpiTile<NT, WPG / 4> ep;
         uint32_t t = (uint32_t)eg;
         for (int tile = blockIdx.x + eg * gridDim.x; tile < p.num_tiles; tile += EG * gridDim.x, t += EG) {
@@ -904,7 +945,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
         const int eg = (warp - TC_EPI_WARP0) / WPG;
         const int half = ((warp - TC_EPI_WARP0) % WPG) >> 2;
         EpiArgs e{bias_s, p.out, p.out_image_stride, p.residual, p.res_image_stride, p.H, p.W, p.Cout, p.act,
-                  p.out_mode, p.sig_from, p.subsample, p.dg};
+                  p.out_mode, p.sig_from, p.subsample, p.dg, &p.fin};
         EpiTile<NT, WPG / 4> ep;
         uint32_t t = (uint32_t)eg;
         if (NT == 64 && WPG == 8 && p.out_mode == OUT_C8 && !p.subsample && p.debug == 0) {
@@ -1087,7 +1128,10 @@ static bool tc_conv_plan(const ConvOp &op, TcConvPlan &pl) {
     if (!(op.stride == 1 || (op.stride == 2 && op.ks == 3 && op.out_mode == OUT_C8 && op.H % 2 == 0 && op.W % 2 == 0)))
         return false;
     if (op.out_mode != OUT_C8 && op.out_mode != OUT_C8_SHUFFLE2 && op.out_mode != OUT_PLANAR_F32 &&
-        op.out_mode != OUT_OM24)
+        op.out_mode != OUT_OM24 && op.out_mode != OUT_FINAL)
+        return false;
+    if (op.out_mode == OUT_FINAL && (op.Cout > 8 || op.Cout != op.fin.nc || op.stride != 1 || op.fin.x == nullptr ||
+                                     op.fin.scale < 1 || op.H % op.fin.scale != 0 || op.W % op.fin.scale != 0))
         return false;
     const int mode = op.out_mode == OUT_OM24 ? 2 : 0;
     if (mode == 2 && (op.ks != 3 || op.stride != 1 || op.dg <= 0 || op.Cout != 27 * op.dg)) return false;
@@ -1177,7 +1221,7 @@ int launch_conv_tc(const ConvOp &op, cudaStream_t s) {
     p.out = op.out; p.out_image_stride = op.out_image_stride;
     p.residual = reinterpret_cast<const __half *>(op.residual); p.res_image_stride = op.res_image_stride;
     p.N = op.N; p.H = op.H; p.W = op.W; p.Cout = op.Cout; p.act = op.act; p.out_mode = op.out_mode;
-    p.sig_from = op.sig_from; p.subsample = op.stride == 2 ? 1 : 0; p.dg = op.dg;
+    p.sig_from = op.sig_from; p.subsample = op.stride == 2 ? 1 : 0; p.dg = op.dg; p.fin = op.fin;
     const int valid = TC_TW - (op.ks - 1);
     p.tiles_x = cdiv(op.W, valid); p.tiles_y = cdiv(op.H, TC_ROWS);
     p.num_tiles = p.tiles_x * p.tiles_y * op.N;
@@ -1457,7 +1501,7 @@ __global__ void __launch_bounds__(DCN_THREADS, 1) dcn_tc_kernel(const __grid_con
     } else {
         pdl_wait();
         const int lq = warp & 3;
-        EpiArgs e{bias_s, p.out, p.out_image_stride, nullptr, 0, p.H, p.W, NT, p.act, OUT_C8, 0, 0, 0};
+        EpiArgs e{bias_s, p.out, p.out_image_stride, nullptr, 0, p.H, p.W, NT, p.act, OUT_C8, 0, 0, 0, nullptr};
         EpiTile<NT, 1> ep;
         ep.has_res = false;
         uint32_t t = 0;
