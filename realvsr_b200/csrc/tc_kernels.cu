@@ -96,6 +96,17 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// 256-bit global accesses (sm_100: STG.E.ENL2.256 / LDG.E.ENL2.256): one full 32 B sector per lane and instruction
+__device__ __forceinline__ void st_global_256(void *p, const uint4 &a, const uint4 &b) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+                 "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
+}
+__device__ __forceinline__ void ld_global_nc_256(const void *p, uint4 &a, uint4 &b) {
+    asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p));
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tmap, uint32_t bar, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -147,6 +158,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
 }
 // Instruction descriptor for kind::f16: fp16 A/B (K-major both), fp32 D, M=128, N.
 __host__ __device__ constexpr uint32_t make_idesc(int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24); }
+
+// Pixel-shuffle column order of one N-pass (NT columns = NT/4 channels x 4 sub-pixels ij = 2i + j):
+// column n = i * (NT/2) + kblk * 16 + j * 8 + e  <->  conv channel 4 * (pss * NT/4 + kblk * 8 + e) + 2i + j
+__host__ __device__ __forceinline__ int shuffle_col_to_channel(int n, int pss, int NT) {
+    const int i = n / (NT / 2), r = n % (NT / 2), kblk = r / 16, j = (r % 16) / 8, e = r % 8;
+    return 4 * (pss * (NT / 4) + kblk * 8 + e) + 2 * i + j;
+}
 
 // ---------------------------------------------------------------- shared epilogue
 struct EpiArgs {
@@ -252,31 +270,33 @@ template <int NT, int NH> struct EpiTile {
         }
     }
 
-    // nn.PixelShuffle(2) fused into the store.  Columns were permuted at pack time:
-    // col = ij * (NT/4) + c_local, output channel c = pss*(NT/4) + c_local, out[n, c, 2y + (ij>>1), 2x + (ij&1)].
+    // nn.PixelShuffle(2) fused into the store: out[n, c, 2y + i, 2x + j] = conv[n, 4c + 2i + j, y, x].  Columns were
+    // permuted at pack time (shuffle_col_to_channel) so that 16 consecutive columns are the j = 0 and j = 1 sub-pixels
+    // of one 8-channel block: they are adjacent in memory and go out as ONE 256-bit store (full sectors).
     template <int ACT>
     __device__ __forceinline__ void store_shuffle(const EpiArgs &e, int half, int ch, int pss, int n, int y, int x) {
-        constexpr int CP = NT / 4 > 8 ? NT / 4 : 8;  // channels per (i, j) sub-pixel in one N-pass
+        constexpr int CP = NT / 4;  // channels per sub-pixel in one N-pass
         const int C2 = e.Cout / 4;
         const long long plane2 = (long long)(2 * e.H) * (2 * e.W);  // (pixel, block) cells per output channel block
+        const int c0 = half * HALFC + ch * CW;
+        if (c0 >= NT) return;
+        const int i = c0 / (NT / 2), kb0 = (c0 % (NT / 2)) / 16;
         uint4 *ob = reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(e.out) + (long long)n * e.out_image_stride) +
-                    (long long)(pss * (CP / 8)) * plane2 + (long long)(2 * y) * (2 * e.W) + 2 * x;
+                    (long long)(pss * (CP / 8) + kb0) * plane2 + (long long)(2 * y + i) * (2 * e.W) + 2 * x;
 #pragma unroll
-        for (int j = 0; j < CW / 8; ++j) {
-            const int c0 = half * HALFC + ch * CW + j * 8;
-            if (c0 >= NT) continue;
-            const int ij = c0 / CP, k = (c0 % CP) / 8;  // sub-pixel and channel block within the pass
-            if ((pss * (CP / 8) + k) * 8 >= C2) continue;
-            const float4 b0 = *reinterpret_cast<const float4 *>(e.bias_s + c0);
-            const float4 b1 = *reinterpret_cast<const float4 *>(e.bias_s + c0 + 4);
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            uint4 pk;
-            __half2 *h = reinterpret_cast<__half2 *>(&pk);
+        for (int g = 0; g < CW / 16; ++g) {
+            if ((pss * (CP / 8) + kb0 + g) * 8 >= C2) break;
+            const float *b = e.bias_s + c0 + g * 16;
+            uint4 pk[2];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                h[i] = __floats2half2_rn(act_t<ACT>(__uint_as_float(acc[j >> 1][(j & 1) * 8 + 2 * i]) + bb[2 * i], e.act),
-                                         act_t<ACT>(__uint_as_float(acc[j >> 1][(j & 1) * 8 + 2 * i + 1]) + bb[2 * i + 1], e.act));
-            ob[(long long)k * plane2 + (ij >> 1) * (2 * e.W) + (ij & 1)] = pk;
+            for (int j = 0; j < 2; ++j) {
+                __half2 *h = reinterpret_cast<__half2 *>(&pk[j]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    h[k] = __floats2half2_rn(act_t<ACT>(__uint_as_float(acc[g][j * 8 + 2 * k]) + b[j * 8 + 2 * k], e.act),
+                                             act_t<ACT>(__uint_as_float(acc[g][j * 8 + 2 * k + 1]) + b[j * 8 + 2 * k + 1], e.act));
+            }
+            st_global_256(ob + (long long)g * plane2, pk[0], pk[1]);
         }
     }
 
@@ -314,11 +334,11 @@ template <int NT, int NH> struct EpiTile {
             for (int j = 18; j < 27; ++j) v[j] = __fdividef(1.f, 1.f + __expf(-v[j]));
             uint4 *og = reinterpret_cast<uint4 *>(e.out) + ((long long)n * e.out_image_stride) / 4 +
                         ((long long)(g * 3) * plane + (long long)y * e.W + x) * 2;
-            og[0] = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
-            og[1] = make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7]));
+            st_global_256(og, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])),
+                          make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7])));
             og += plane * 2;
-            og[0] = make_uint4(__float_as_uint(v[8]), __float_as_uint(v[9]), __float_as_uint(v[10]), __float_as_uint(v[11]));
-            og[1] = make_uint4(__float_as_uint(v[12]), __float_as_uint(v[13]), __float_as_uint(v[14]), __float_as_uint(v[15]));
+            st_global_256(og, make_uint4(__float_as_uint(v[8]), __float_as_uint(v[9]), __float_as_uint(v[10]), __float_as_uint(v[11])),
+                          make_uint4(__float_as_uint(v[12]), __float_as_uint(v[13]), __float_as_uint(v[14]), __float_as_uint(v[15])));
             og += plane * 2;
             uint32_t m[5];
 #pragma unroll
@@ -326,8 +346,7 @@ template <int NT, int NH> struct EpiTile {
                 const __half2 h = __floats2half2_rn(v[18 + 2 * k], k < 4 ? v[19 + 2 * k] : 0.f);
                 m[k] = *reinterpret_cast<const uint32_t *>(&h);
             }
-            og[0] = make_uint4(__float_as_uint(v[16]), __float_as_uint(v[17]), m[0], m[1]);
-            og[1] = make_uint4(m[2], m[3], m[4], 0u);
+            st_global_256(og, make_uint4(__float_as_uint(v[16]), __float_as_uint(v[17]), m[0], m[1]), make_uint4(m[2], m[3], m[4], 0u));
         }
     }
 
@@ -577,8 +596,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         float b = 0.f;
         if (p.bias != nullptr) {
             if (p.out_mode == OUT_C8_SHUFFLE2) {
-                const int c = pss * (NT / 4) + i % (NT / 4), ij = i / (NT / 4);
-                b = (4 * c + ij) < p.Cout ? p.bias[4 * c + ij] : 0.f;
+                const int cc = shuffle_col_to_channel(i, pss, NT);
+                b = cc < p.Cout ? p.bias[cc] : 0.f;
             } else if (p.out_mode == OUT_OM24) {
                 const int g = pss * 4 + i / 32, j = i % 32;
                 if (g < p.dg && j < 27) b = p.bias[j < 18 ? g * 18 + j : 18 * p.dg + g * 9 + (j - 18)];
@@ -839,8 +858,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
         float b = 0.f;
         if (p.bias != nullptr) {
             if (p.out_mode == OUT_C8_SHUFFLE2) {
-                const int c = pss * (NT / 4) + i % (NT / 4), ij = i / (NT / 4);
-                b = (4 * c + ij) < p.Cout ? p.bias[4 * c + ij] : 0.f;
+                const int cc = shuffle_col_to_channel(i, pss, NT);
+                b = cc < p.Cout ? p.bias[cc] : 0.f;
             } else if (p.out_mode == OUT_OM24) {
                 const int g = pss * 4 + i / 32, j = i % 32;
                 if (g < p.dg && j < 27) b = p.bias[j < 18 ? g * 18 + j : 18 * p.dg + g * 9 + (j - 18)];
@@ -1048,8 +1067,8 @@ __global__ void pack_weight_tc_kernel(const float *__restrict__ w, __half *__res
         const int pss = (int)(r / KK);
         const int cin = q * 8 + e;
         int co;
-        if (mode == 1) {  // pixel shuffle: column = ij * (NT/4) + c_local  <->  conv channel 4c + ij
-            co = 4 * (pss * (NT / 4) + n % (NT / 4)) + n / (NT / 4);
+        if (mode == 1) {  // pixel shuffle column order
+            co = shuffle_col_to_channel(n, pss, NT);
         } else if (mode == 2) {  // OUT_OM24: column = local group * 32 + [dy0 dx0 .. dy8 dx8 m0 .. m8]
             const int g = pss * 4 + n / 32, j = n % 32;
             co = (g < dg && j < 27) ? (j < 18 ? g * 18 + j : 18 * dg + g * 9 + (j - 18)) : Cout;
@@ -1097,7 +1116,7 @@ __global__ void pack_weight_tc2_kernel(const float *__restrict__ w, __half *__re
         const int n = rank * NH + nrow, cin = q * 8 + e;
         int co;
         if (mode == 1) {
-            co = 4 * (pss * (NT / 4) + n % (NT / 4)) + n / (NT / 4);
+            co = shuffle_col_to_channel(n, pss, NT);
         } else if (mode == 2) {
             const int g = pss * 4 + n / 32, j = n % 32;
             co = (g < dg && j < 27) ? (j < 18 ? g * 18 + j : 18 * dg + g * 9 + (j - 18)) : Cout;
@@ -1470,8 +1489,8 @@ __global__ void __launch_bounds__(DCN_THREADS, 1) dcn_tc_kernel(const __grid_con
             return (t & 1) ? __high2float(mh) : __low2float(mh);
         };
         auto load_AC = [&](int h) {
-            A[h][0] = __ldg(U[h].om); A[h][1] = __ldg(U[h].om + 1);
-            C[h][0] = __ldg(U[h].om + 4 * plane); C[h][1] = __ldg(U[h].om + 4 * plane + 1);
+            ld_global_nc_256(U[h].om, A[h][0], A[h][1]);
+            ld_global_nc_256(U[h].om + 4 * plane, C[h][0], C[h][1]);
         };
         U[0] = unit_of(blockIdx.x, 0, false);
         load_AC(0);
@@ -1482,7 +1501,7 @@ __global__ void __launch_bounds__(DCN_THREADS, 1) dcn_tc_kernel(const __grid_con
 #pragma unroll
             for (int s18 = 0; s18 < 18; ++s18) {
                 const int h = s18 / 9, tap = s18 % 9, st = (s18 >> 1) % S, part = s18 & 1;
-                if (tap == 0) { B[0] = __ldg(U[h].om + 2 * plane); B[1] = __ldg(U[h].om + 2 * plane + 1); }
+                if (tap == 0) ld_global_nc_256(U[h].om + 2 * plane, B[0], B[1]);
                 if (tap == 1)  // set up the next unit (other half of this tile, or the first half of the next tile)
                     U[h ^ 1] = h == 0 ? unit_of(tile, 1, true) : unit_of(tile + gridDim.x, 0, true);
                 if (tap == 6) load_AC(h ^ 1);
