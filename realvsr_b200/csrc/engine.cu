@@ -694,8 +694,10 @@ int Engine::forward(const void *x, int x_dtype, void *out, int out_dtype, int B,
     const size_t mis = (size_t)(reinterpret_cast<uintptr_t>(ws) % 1024);
     if (mis) { ar.base += 1024 - mis; ar.cap -= 1024 - mis; }
     host_maps_.clear();
-    if (cfg_.precision == RVSR_F16) return run<__half>(ar, false, x, x_dtype, out, out_dtype, B, H, W, s, nullptr);
-    return run<float>(ar, false, x, x_dtype, out, out_dtype, B, H, W, s, nullptr);
+    const int rc = cfg_.precision == RVSR_F16 ? run<__half>(ar, false, x, x_dtype, out, out_dtype, B, H, W, s, nullptr)
+                                              : run<float>(ar, false, x, x_dtype, out, out_dtype, B, H, W, s, nullptr);
+    tc_stamps_dump();  // debug only (RVSR_TC_STAMPS): synchronises
+    return rc;
 }
 
 // ---------------------------------------------------------------- sliding-window feature cache

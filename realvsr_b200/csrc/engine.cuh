@@ -116,6 +116,7 @@ class Engine {
 
 // tc_kernels.cu: tcgen05 paths (fp16 storage).  Return RVSR_E_UNSUPPORTED when the shape is
 // not covered so the caller can route the op to the CUDA-core kernel instead.
+void tc_stamps_dump();  // RVSR_TC_STAMPS=1: print the kernel-boundary timeline of the launches since the last dump
 bool tc_conv_supported(const ConvOp &op);
 int launch_conv_tc(const ConvOp &op, cudaStream_t s);
 size_t tc_conv_weight_bytes(int Cout, int Cin, int ks, int mode = 0);

@@ -32,6 +32,39 @@
 
 namespace rvsr {
 
+// ---------------------------------------------------------------- debug: kernel-boundary timeline (RVSR_TC_STAMPS=1)
+// %globaltimer stamps of CTA 0 of every pair-kernel launch: 0 entry, 1 prologue done (cluster sync), 2 pdl_wait
+// returned, 3 first stage full (issuer 0), 4 first accumulator full (epilogue), 5 last epilogue tile done, 6 exit.
+constexpr int STAMP_SLOTS = 512;
+__device__ unsigned long long g_stamps[STAMP_SLOTS][8];
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+static int g_stamp_next = 0;
+static char g_stamp_label[STAMP_SLOTS][48];
+static bool stamps_on() {
+    static const bool on = getenv("RVSR_TC_STAMPS") != nullptr;
+    return on;
+}
+void tc_stamps_dump() {
+    if (!stamps_on() || g_stamp_next == 0) return;
+    cudaDeviceSynchronize();
+    static unsigned long long h[STAMP_SLOTS][8];
+    cudaMemcpyFromSymbol(h, g_stamps, sizeof(h));
+    const int n = g_stamp_next < STAMP_SLOTS ? g_stamp_next : STAMP_SLOTS;
+    printf("[stamps] launch  gap-from-prev-exit | prologue  pdl-wait  first-full  first-acc  ...last-epi  exit | total (us)\n");
+    for (int i = 0; i < n; ++i) {
+        const unsigned long long *t = h[i];
+        const double gap = i > 0 ? ((double)t[0] - (double)h[i - 1][6]) * 1e-3 : 0.0;
+        printf("[stamps] %2d %-40s %7.2f | %6.2f %6.2f %6.2f %6.2f %8.2f %6.2f | %8.2f\n", i, g_stamp_label[i], gap,
+               (t[1] - t[0]) * 1e-3, (t[2] - t[1]) * 1e-3, (double)((long long)(t[3] - t[2])) * 1e-3, (double)((long long)(t[4] - t[3])) * 1e-3,
+               (double)((long long)(t[5] - t[4])) * 1e-3, (double)((long long)(t[6] - t[5])) * 1e-3, (t[6] - t[0]) * 1e-3);
+    }
+    g_stamp_next = 0;
+}
+
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -66,15 +99,16 @@ __device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
 #pragma unroll 1
     for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+        // suspend-time hint: the warp sleeps in hardware until the phase completes (or ~20 us pass) instead of
+        // polling -- the idle roles executed 15 % of the gather kernel's instructions with a 128 ns software back-off
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(bar), "r"(parity)
+            : "r"(bar), "r"(parity), "r"(20000u)
             : "memory");
         if (done) return;
-        __nanosleep(128);
     }
     __trap();
 }
@@ -524,6 +558,7 @@ struct alignas(64) TcConvParams {
     int tiles_x, tiles_y, num_tiles;
     TileDiv td;
     FinalAdd fin;
+    int stamp;  // slot in g_stamps or -1
     int debug;  // RVSR_TC_DEBUG bit mask for timing experiments only (results become garbage):
                 // 1 = issue no MMAs, 2 = no epilogue stores, 4 = no TMA halo loads, 8 = no TMEM loads
 };
@@ -825,7 +860,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
     float *bias_s = reinterpret_cast<float *>(stage_s + (size_t)p.nstages * stage_bytes + 128);
     uint64_t *bars = reinterpret_cast<uint64_t *>(bias_s + NT);
     const int S = p.nstages;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + (MMAW + 1) * S + 1 + 2 * NB);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + (MMAW + 1) * S + 2 + 2 * NB);
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
     auto FULL = [&](int w, int st) { return BAR(w * S + st); };
@@ -833,17 +868,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
     const uint32_t WFULL = BAR((MMAW + 1) * S);
     auto TFULL = [&](int b) { return BAR((MMAW + 1) * S + 1 + b); };
     auto TEMPTY = [&](int b) { return BAR((MMAW + 1) * S + 1 + NB + b); };
+    const uint32_t WPEER = BAR((MMAW + 1) * S + 1 + 2 * NB);  // leader only: the peer's weight half has landed
     const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
     const uint32_t rank = blockIdx.x & 1u;  // == %cluster_ctarank for __cluster_dims__(2, 1, 1); provably uniform
     const int cid = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
     const int npairs = (p.num_tiles + 1) / 2;
     const int pss = blockIdx.y;
 
+    const bool stamp = p.stamp >= 0 && blockIdx.x == 0 && blockIdx.y == 0;
+#define STAMP(k) do { if (stamp) g_stamps[p.stamp][k] = globaltimer_ns(); } while (0)
+    if (threadIdx.x == 0) STAMP(0);
     pdl_trigger();
     if (threadIdx.x == 0) {
         for (int i = 0; i < MMAW * S; ++i) mbar_init(BAR(i), 2);                       // FULL: leader + peer arrive
         for (int i = MMAW * S; i < (MMAW + 1) * S + 1 + NB; ++i) mbar_init(BAR(i), 1);  // EMPTY, WFULL, TFULL
         for (int i = 0; i < NB; ++i) mbar_init(TEMPTY(i), 2 * (TC_EPI_WARPS / EG));   // epilogue warps of both CTAs
+        mbar_init(WPEER, 1);
         fence_barrier_init();
         // this CTA's half of the weights: resident for the CTA's lifetime
         mbar_expect_tx(WFULL, w_bytes);
@@ -853,23 +893,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
             bulk_load(smem_u32(w_s + o), wg + o, n, WFULL);
         }
     }
-    for (int i = threadIdx.x; i < NT; i += TC_THREADS) {  // same column -> channel maps as conv_tc_kernel
-        const int co = pss * NT + i;
-        float b = 0.f;
-        if (p.bias != nullptr) {
-            if (p.out_mode == OUT_C8_SHUFFLE2) {
-                const int cc = shuffle_col_to_channel(i, pss, NT);
-                b = cc < p.Cout ? p.bias[cc] : 0.f;
-            } else if (p.out_mode == OUT_OM24) {
-                const int g = pss * 4 + i / 32, j = i % 32;
-                if (g < p.dg && j < 27) b = p.bias[j < 18 ? g * 18 + j : 18 * p.dg + g * 9 + (j - 18)];
-            } else if (co < p.Cout) {
-                b = p.bias[co];
-            }
-        }
-        bias_s[i] = b;
-    }
-    if (threadIdx.x == 0) mbar_wait(WFULL, 0);  // the leader's MMAs read the PEER's weight half too: both must have landed
+    // Kept OFF the prologue's critical path (every launch pays it): the bias is staged by the epilogue warps while
+    // the first halo tiles are in flight, and the weights are awaited by the issuers -- the leader needs both halves:
+    // the peer forwards "my half has landed" to the leader's WPEER barrier.
     if (warp == 3) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -878,7 +904,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
     cluster_sync_all();   // barriers of both CTAs initialised before any remote arrive / multicast commit
     tc_fence_after();
     const uint32_t tmem_base = uniform_u32(*tmem_slot);
+    if (threadIdx.x == 0) STAMP(1);
     pdl_wait();  // prologue (barriers, weights, TMEM) overlapped the previous kernel's tail; activations from here on
+    if (threadIdx.x == 0) STAMP(2);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -905,7 +933,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
             }
         }
     } else if (warp <= MMAW) {
-        if (rank == 0) {  // whole warp, uniform values; only the tcgen05 instructions are predicated on one lane
+        if (rank != 0) {
+            if (warp == 1 && lane == 0) {
+                mbar_wait(WFULL, 0);
+                mbar_arrive_cluster(mapa_rank0(WPEER));
+            }
+        } else {  // whole warp, uniform values; only the tcgen05 instructions are predicated on one lane
             constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((256u >> 4) << 24);  // M = 256 over the pair
             const uint32_t mw = (uint32_t)(warp - 1);
             const uint32_t nsrc = (uint32_t)p.nsrc, C8s = (uint32_t)p.C8s;
@@ -918,6 +951,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
             const int nk = (p.debug & 1) ? 0 : (int)C8s / 2;
             uint32_t st = (mw * nsrc) % (uint32_t)S, par = 0;
             uint32_t t = mw;
+            mbar_wait(WFULL, 0);  // both weight halves resident (phase 0 of these two barriers completes exactly once)
+            mbar_wait(WPEER, 0);
             for (int pr = cid + (int)mw * nclusters; pr < npairs; pr += MMAW * nclusters, t += MMAW) {
                 const uint32_t buf = t % NB;
                 mbar_wait(TEMPTY(buf), ((t / NB) & 1) ^ 1);
@@ -928,6 +963,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
                     mbar_wait(FULL(mw, st), (par >> st) & 1);
                     par ^= 1u << st;
                     tc_fence_after();
+                    if (mw == 0 && t == 0 && s == 0 && lane == 0) STAMP(3);
                     const uint32_t a_lo0 = a_base + st * stage_units;
                     if (elect_one()) {
 #pragma unroll
@@ -959,6 +995,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
             }
         }
     } else if (warp >= TC_EPI_WARP0) {
+        for (int i = threadIdx.x - 32 * TC_EPI_WARP0; i < NT; i += 32 * TC_EPI_WARPS) {  // column -> channel maps as in conv_tc_kernel
+            const int co = pss * NT + i;
+            float b = 0.f;
+            if (p.bias != nullptr) {
+                if (p.out_mode == OUT_C8_SHUFFLE2) {
+                    const int cc = shuffle_col_to_channel(i, pss, NT);
+                    b = cc < p.Cout ? p.bias[cc] : 0.f;
+                } else if (p.out_mode == OUT_OM24) {
+                    const int g = pss * 4 + i / 32, j = i % 32;
+                    if (g < p.dg && j < 27) b = p.bias[j < 18 ? g * 18 + j : 18 * p.dg + g * 9 + (j - 18)];
+                } else if (co < p.Cout) {
+                    b = p.bias[co];
+                }
+            }
+            bias_s[i] = b;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");  // epilogue warps only
         constexpr int WPG = TC_EPI_WARPS / EG;
         const int lq = warp & 3;
         const int eg = (warp - TC_EPI_WARP0) / WPG;
@@ -988,6 +1041,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
                                          __syncwarp();
                                          if (lane == 0) mbar_arrive_cluster(tempty0);
                                      });
+                    if (pr == cid + eg * nclusters && eg == 0 && warp == TC_EPI_WARP0 && lane == 0) STAMP(4);
                     buf += EG;
                     if (buf >= (uint32_t)NB) { buf -= NB; par ^= 1u; }
                 }
@@ -1014,8 +1068,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
             });
         }
     }
+    if (warp == TC_EPI_WARP0 && lane == 0) STAMP(5);
     tc_fence_before();
     cluster_sync_all();   // no CTA exits (or frees TMEM) while its partner can still touch its barriers / operands
+    if (threadIdx.x == 0) STAMP(6);
+#undef STAMP
     if (warp == 3) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
 }
 
@@ -1249,6 +1306,7 @@ int launch_conv_tc(const ConvOp &op, cudaStream_t s) {
     p.td.tx = (uint32_t)p.tiles_x; p.td.m_tx = magic_div(p.td.tx, p.td.tpi);
     static const int dbg = getenv("RVSR_TC_DEBUG") ? atoi(getenv("RVSR_TC_DEBUG")) : 0;
     p.debug = dbg;
+    p.stamp = -1;
     const int sms = sm_count();
     // CTA-pair kernels (cta_group::2) for the 3x3 convolutions with 64- and 128-wide tiles (the bulk of the network)
     static const bool two_cta = !(getenv("RVSR_TC_2CTA") != nullptr && getenv("RVSR_TC_2CTA")[0] == '0');
@@ -1262,6 +1320,12 @@ int launch_conv_tc(const ConvOp &op, cudaStream_t s) {
         p.nstages = st2;
         p.w = reinterpret_cast<const __half *>(op.w_tc2);
         const size_t smem2 = fixed + (size_t)st2 * stage + 1024;
+        if (stamps_on() && g_stamp_next < STAMP_SLOTS) {
+            p.stamp = g_stamp_next;
+            snprintf(g_stamp_label[g_stamp_next], sizeof(g_stamp_label[0]), "N%d %dx%d src%d co%d m%d tiles%d", op.N, op.H, op.W, op.nsrc,
+                     op.Cout, op.out_mode, p.num_tiles);
+            ++g_stamp_next;
+        }
         const int npairs = (p.num_tiles + 1) / 2;
         int clusters = (sms / 2) / pl.passes;
         if (clusters < 1) clusters = 1;
