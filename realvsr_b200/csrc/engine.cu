@@ -190,6 +190,13 @@ int Engine::finalize(cudaStream_t s) {
                 else
                     RVSR_TRY(pack_weight_tc(wsrc, pc.w_tc, pc.Cout, pc.Cin, pc.ks, mode, s));
             }
+            if (base == "conv_last" && tc_tapn_weight_bytes(pc.Cout, pc.Cin, pc.ks) > 0) {
+                if (pc.w_tapn == nullptr) {
+                    RVSR_CUDA(cudaMalloc(&pc.w_tapn, tc_tapn_weight_bytes(pc.Cout, pc.Cin, pc.ks)));
+                    owned_.push_back(pc.w_tapn);
+                }
+                RVSR_TRY(pack_weight_tapn(wsrc, pc.w_tapn, pc.Cout, pc.Cin, s));
+            }
             const size_t tb2 = (!is_dcn && !(is_om && mode != 2)) ? tc2_weight_bytes(pc.Cout, pc.Cin, pc.ks, mode) : 0;
             if (tb2 > 0) {
                 if (pc.w_tc2 == nullptr) {
@@ -591,7 +598,14 @@ int Engine::run(Arena &ar, bool dry, const void *x, int x_dtype, void *out, int 
                 op.act = NONE; op.out_mode = OUT_FINAL; op.sig_from = 1 << 30;
                 op.fin.x = x; op.fin.center_map = map_ctr; op.fin.x_dtype = x_dtype; op.fin.out_dtype = out_dtype;
                 op.fin.frames = N; op.fin.center = ctr; op.fin.nc = nc; op.fin.scale = scale;
-                if (!tc_conv_supported(op)) {
+                // RVSR_TAPN=0 keeps the ordinary implicit GEMM (36 MMAs per tile) for A/B timing
+                static const bool tapn_on = !(getenv("RVSR_TAPN") != nullptr && getenv("RVSR_TAPN")[0] == '0');
+                if (tapn_on && pc->w_tapn != nullptr) {
+                    const double px = (double)B * r.H * r.W;
+                    P.launch("tc:conv3x3_tapn_co" + std::to_string(pc->Cout) + ":conv_last", 2.0 * r.C * pc->Cout * 9 * px,
+                             px * r.C * sizeof(T) + px * nc * (out_dtype == RVSR_F32 ? 4 : 2) + (double)B * nc * H * W * (x_dtype == RVSR_F32 ? 4 : 2),
+                             [&] { return launch_conv_tapn(op, pc->w_tapn, s); });
+                } else if (!tc_conv_supported(op)) {
                     fused_final = false;
                 } else {
                     const double px = (double)B * r.H * r.W;

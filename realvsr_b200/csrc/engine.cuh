@@ -40,6 +40,7 @@ struct PackedConv {
     float *w_simt = nullptr;  // [chunks][taps][8][cout_pad] fp32
     void *w_tc = nullptr;     // fp16 UMMA layout (tc_kernels.cu) or null
     void *w_tc2 = nullptr;    // fp16 CTA-pair layout or null
+    void *w_tapn = nullptr;   // fp16 taps-in-N layout (conv_last) or null
     float *bias = nullptr;    // fp32 [Cout]
     int Cout = 0, Cin = 0, ks = 0;
 };
@@ -124,6 +125,9 @@ size_t tc_conv_weight_bytes(int Cout, int Cin, int ks, int mode = 0);
 int pack_weight_tc(const float *w_oihw, void *dst, int Cout, int Cin, int ks, int mode, cudaStream_t s);
 size_t tc2_weight_bytes(int Cout, int Cin, int ks, int mode = 0);
 int pack_weight_tc2(const float *w_oihw, void *dst, int Cout, int Cin, int ks, int mode, cudaStream_t s);
+size_t tc_tapn_weight_bytes(int Cout, int Cin, int ks);   // conv_last "taps in N" kernel (Cout <= 3)
+int pack_weight_tapn(const float *w_oihw, void *dst, int Cout, int Cin, cudaStream_t s);
+int launch_conv_tapn(const ConvOp &op, const void *w_tapn, cudaStream_t s);
 bool tc_dcn_supported(const DcnOp &op);
 int launch_dcn_tc(const DcnOp &op, cudaStream_t s);
 size_t tc_dcn_weight_bytes(int Cout, int C, int K);

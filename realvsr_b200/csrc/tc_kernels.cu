@@ -1644,4 +1644,295 @@ int launch_dcn_tc(const DcnOp &op, cudaStream_t s) {
     return RVSR_OK;
 }
 
+
+// ---------------------------------------------------------------- conv_last, "taps in N" (+ base frame)
+// The last convolution has nc (<= 3) output channels: as an ordinary implicit GEMM it needs 36 MMAs per tile that
+// each read a full 4 KB A operand for 16 (3 useful) output columns -- bound by the A-operand shared-memory reads.
+// Here the nine taps move into the N dimension instead:
+//     P[pixel][tap * nc + co] = sum_c in[pixel][c] * W[co][c][tap]          ONE unshifted view, K = 64: 4 MMAs (N = 32)
+//     out[co][y][x]           = sum_tap P[(y + dy - 1, x + dx - 1)][tap * nc + co]   shift-and-add in the epilogue
+// A 6 x 32 halo tile is covered by two M = 128 views (rows 0-3 and rows 2-5): 8 MMAs per 4 x 30 output tile instead
+// of 36.  The epilogue moves the partial sums TMEM -> registers -> shared memory ([column][row][x] fp32, conflict
+// free), synchronises its 8 warps, and every thread then gathers the 9 * nc partials of its output pixel, adds bias
+// and the bilinearly upsampled centre LQ frame (EDVR_arch.py:315-319) and writes the NCHW result.
+struct alignas(64) TcTapnParams {
+    CUtensorMap tmap;
+    const __half *w;     // [C8s][32][8]: row n = tap * nc + co
+    const float *bias;   // [nc]
+    void *out;           // NCHW, fin.out_dtype
+    FinalAdd fin;
+    int N, H, W, nc, C8s, nstages;
+    int tiles_x, tiles_y, num_tiles;
+    TileDiv td;
+    int debug;  // RVSR_TC_DEBUG timing experiments: 1 no MMAs, 2 no output phase, 4 no halo loads, 8 no TMEM drain
+};
+// three epilogue groups of 8 warps take tiles round-robin: one tile's epilogue is a ~2.4k-cycle latency chain
+// (accumulator wait, TMEM drain, two group barriers, shared-memory gather, stores)
+constexpr int TAPN_EPI_WARP0 = 4, TAPN_EG = 3, TAPN_EPI_WARPS = 8 * TAPN_EG, TAPN_THREADS = 32 * (TAPN_EPI_WARP0 + TAPN_EPI_WARPS);
+constexpr int TAPN_NB = 2 * TAPN_EG, TAPN_XCH = 27 * 6 * 32;  // accumulator pairs in flight; floats of one exchange buffer
+constexpr int TAPN_TMEM_COLS = TAPN_NB * 64 <= 256 ? 256 : 512;
+
+__global__ void __launch_bounds__(TAPN_THREADS, 1) conv_tapn_kernel(const __grid_constant__ TcTapnParams p) {
+    constexpr int HALO_ROWS = 6, PLANE_BYTES = HALO_ROWS * TC_TW * 16, VALID = TC_TW - 2, NB = TAPN_NB, EG = TAPN_EG, WPG = TAPN_EPI_WARPS / EG;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int S = p.nstages;
+    const uint32_t w_bytes = (uint32_t)p.C8s * 32 * 16, stage_bytes = (uint32_t)p.C8s * PLANE_BYTES;
+    uint8_t *w_s = smem;
+    uint8_t *stage_s = smem + w_bytes;
+    float *xch = reinterpret_cast<float *>(stage_s + (size_t)S * stage_bytes + 128);
+    float *bias_s = xch + EG * TAPN_XCH;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(bias_s + 8);
+    // bars: S full, S empty, weights-full, NB accumulator-full, NB accumulator-empty
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * S + 1 + 2 * NB);
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    auto FULL = [&](int st) { return BAR(st); };
+    auto EMPTY = [&](int st) { return BAR(S + st); };
+    const uint32_t WFULL = BAR(2 * S);
+    auto TFULL = [&](int b) { return BAR(2 * S + 1 + b); };
+    auto TEMPTY = [&](int b) { return BAR(2 * S + 1 + NB + b); };
+    const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
+
+    pdl_trigger();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2 * S + 1 + NB; ++i) mbar_init(BAR(i), 1);
+        for (int i = 0; i < NB; ++i) mbar_init(TEMPTY(i), WPG);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(smem_u32(tmem_slot), TAPN_TMEM_COLS);  // NB x (2 views x 32 columns)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = uniform_u32(*tmem_slot);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(WFULL, w_bytes);
+            bulk_load(smem_u32(w_s), p.w, w_bytes, WFULL);
+            pdl_wait();
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                int tx, ty, n;
+                tile_coords(p.td, tile, tx, ty, n);
+                const int st = it % S;
+                mbar_wait(EMPTY(st), ((it / S) & 1) ^ 1);
+                if (p.debug & 4) { mbar_arrive(FULL(st)); continue; }
+                mbar_expect_tx(FULL(st), stage_bytes);
+                tma_load_3d(smem_u32(stage_s + (size_t)st * stage_bytes), &p.tmap, FULL(st), (tx * VALID - 1) * 8, ty * TC_ROWS - 1,
+                            n * p.C8s);
+            }
+        }
+    } else if (warp == 1) {
+        // ---- issuer: whole warp on uniform values (see elect_one)
+        constexpr uint32_t idesc = make_idesc(32);
+        const uint64_t adesc0 = make_desc(smem_u32(stage_s), PLANE_BYTES, 128);
+        const uint64_t bdesc0 = make_desc(smem_u32(w_s), 32 * 16, 128);
+        const uint32_t a_hi = (uint32_t)(adesc0 >> 32), b_hi = (uint32_t)(bdesc0 >> 32);
+        const uint32_t a_base = (uint32_t)adesc0, b_base = (uint32_t)bdesc0;
+        const uint32_t stage_units = stage_bytes >> 4;
+        const int nk = (p.debug & 1) ? 0 : p.C8s / 2;
+        mbar_wait(WFULL, 0);
+        uint32_t t = 0, st = 0, sph = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++t) {
+            const uint32_t buf = t % NB;
+            mbar_wait(TEMPTY(buf), ((t / NB) & 1) ^ 1);
+            mbar_wait(FULL(st), sph);
+            tc_fence_after();
+            const uint32_t d = tmem_base + buf * 64;
+            const uint32_t a_lo0 = a_base + st * stage_units;
+            if (elect_one()) {
+#pragma unroll
+                for (int v = 0; v < 2; ++v)  // view v: tile rows 2v .. 2v + 3
+                    for (int kk = 0; kk < nk; ++kk)
+                        umma_f16(d + (uint32_t)v * 32, ((uint64_t)a_hi << 32) | (a_lo0 + (uint32_t)v * (2 * TC_TW) + (uint32_t)kk * (2 * PLANE_BYTES / 16)),
+                                 ((uint64_t)b_hi << 32) | (b_base + (uint32_t)kk * (2 * 32)), idesc, kk ? 1u : 0u);
+                umma_commit(EMPTY(st));
+                umma_commit(TFULL(buf));
+            }
+            __syncwarp();
+            if (++st == (uint32_t)S) { st = 0; sph ^= 1u; }
+        }
+    } else if (warp >= TAPN_EPI_WARP0) {
+        pdl_wait();
+        const int wi = (warp - TAPN_EPI_WARP0) % WPG, eg = (warp - TAPN_EPI_WARP0) / WPG;
+        const int lq = warp & 3, hv = wi >> 2;       // TMEM lane quarter; view this warp drains (phase 1) / channel set (phase 2)
+        const int nc = p.nc, ncol = 9 * nc;
+        if (threadIdx.x - 32 * TAPN_EPI_WARP0 < 8) bias_s[threadIdx.x - 32 * TAPN_EPI_WARP0] =
+            (p.bias != nullptr && (int)(threadIdx.x - 32 * TAPN_EPI_WARP0) < nc) ? p.bias[threadIdx.x - 32 * TAPN_EPI_WARP0] : 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * TAPN_EPI_WARPS) : "memory");
+        float *xg = xch + eg * TAPN_XCH;
+        const FinalAdd &f = p.fin;
+        const int Hl = p.H / f.scale, Wl = p.W / f.scale;
+        const long long lplane = (long long)Hl * Wl, hplane = (long long)p.H * p.W;
+        const bool reader = hv == 0 || lq >= 2;      // view 1's lanes 0..63 repeat tile rows 2, 3
+        const int row = hv == 0 ? lq : lq + 2;       // tile row this warp's TMEM lanes hold
+        // ---- base frame pixels of this thread's output pixel: the 4 bilinear corners per channel are fetched one tile
+        // AHEAD (raw values in registers), so their global-memory latency is hidden behind the previous tile's work;
+        // 8 warps per tile: channels 0, 1 on the view-0 warps, channel 2 on the view-1 warps
+        const int co0 = hv == 0 ? 0 : 2, co1 = min(nc, hv == 0 ? 2 : 3);
+        struct Pix { uint32_t c[2][4]; float ly, lx; int n, y, x; bool valid; };  // c: RAW loaded bits (converting here would wait for the load)
+        auto fetch = [&](int tile, Pix &q) {
+            int tx, ty;
+            tile_coords(p.td, tile, tx, ty, q.n);
+            q.y = ty * TC_ROWS + lq; q.x = tx * VALID + lane;
+            q.valid = lane < VALID && q.y < p.H && q.x < p.W;
+            q.ly = q.lx = 0.f;
+            if (!q.valid) return;
+            const long long cimg = f.center_map != nullptr ? (long long)__ldg(f.center_map + q.n) : (long long)q.n * f.frames + f.center;
+            int y0 = q.y, x0 = q.x, y1 = q.y, x1 = q.x;
+            if (f.scale != 1) {
+                const float inv = 1.f / f.scale;
+                const float sy = fmaxf(inv * (q.y + 0.5f) - 0.5f, 0.f), sx = fmaxf(inv * (q.x + 0.5f) - 0.5f, 0.f);
+                y0 = (int)sy; x0 = (int)sx;
+                y1 = y0 + (y0 < Hl - 1 ? 1 : 0); x1 = x0 + (x0 < Wl - 1 ? 1 : 0);
+                q.ly = sy - y0; q.lx = sx - x0;
+            }
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int co = co0 + k;
+                if (co >= co1) break;
+                const long long pc = (cimg * nc + co) * lplane;
+                if (f.x_dtype == RVSR_F32) {
+                    const uint32_t *xp = reinterpret_cast<const uint32_t *>(f.x) + pc;
+                    q.c[k][0] = __ldg(xp + y0 * Wl + x0); q.c[k][1] = __ldg(xp + y0 * Wl + x1);
+                    q.c[k][2] = __ldg(xp + y1 * Wl + x0); q.c[k][3] = __ldg(xp + y1 * Wl + x1);
+                } else {
+                    const unsigned short *xp = reinterpret_cast<const unsigned short *>(f.x) + pc;
+                    q.c[k][0] = __ldg(xp + y0 * Wl + x0); q.c[k][1] = __ldg(xp + y0 * Wl + x1);
+                    q.c[k][2] = __ldg(xp + y1 * Wl + x0); q.c[k][3] = __ldg(xp + y1 * Wl + x1);
+                }
+            }
+        };
+        // per tile: `cur` was fetched an iteration ago, `nxt` is fetched for the following tile; the two buffers swap
+        // roles by unrolling -- copying nxt into cur would wait for the loads that were just issued.
+        Pix px[2];
+        const int stride = EG * (int)gridDim.x;
+        int tile0 = blockIdx.x + eg * gridDim.x;
+        uint32_t t0 = (uint32_t)eg;
+        if (tile0 < p.num_tiles) fetch(tile0, px[0]);
+        for (; tile0 < p.num_tiles; tile0 += 2 * stride, t0 += 2 * EG) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {  // fully unrolled: px[u] / px[u ^ 1] stay in registers
+            const int tile = tile0 + u * stride;
+            if (tile >= p.num_tiles) break;
+            const uint32_t t = t0 + (uint32_t)u * EG;
+            Pix &cur = px[u], &nxt = px[u ^ 1];
+            const uint32_t buf = t % NB;
+            mbar_wait(TFULL(buf), (t / NB) & 1);
+            tc_fence_after();
+            if (reader && !(p.debug & 8)) {
+                uint32_t r0[16], r1[16];
+                const uint32_t taddr = tmem_base + buf * 64 + (uint32_t)hv * 32 + ((uint32_t)(lq * 32) << 16);
+                tmem_ld16_nowait(taddr, r0);
+                tmem_ld16_nowait(taddr + 16, r1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 27; ++c)
+                    if (c < ncol) xg[(c * 6 + row) * 32 + lane] = __uint_as_float(c < 16 ? r0[c & 15] : r1[c & 15]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(TEMPTY(buf));
+            asm volatile("bar.sync %0, %1;" ::"r"(2 + eg), "n"(32 * WPG) : "memory");  // partial sums of the tile are in xg
+            if (cur.valid && !(p.debug & 2)) {
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const int co = co0 + k;
+                    if (co >= co1) break;
+                    float acc = bias_s[co];
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap)
+                        acc += xg[((tap * nc + co) * 6 + lq + tap / 3) * 32 + lane + tap % 3];
+                    float c4[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        c4[i] = f.x_dtype == RVSR_F32 ? __uint_as_float(cur.c[k][i]) : __half2float(__ushort_as_half((unsigned short)cur.c[k][i]));
+                    const float base = f.scale == 1 ? c4[0] : (1.f - cur.ly) * ((1.f - cur.lx) * c4[0] + cur.lx * c4[1]) +
+                                                                  cur.ly * ((1.f - cur.lx) * c4[2] + cur.lx * c4[3]);
+                    const long long oi = ((long long)cur.n * nc + co) * hplane + (long long)cur.y * p.W + cur.x;
+                    if (f.out_dtype == RVSR_F32) reinterpret_cast<float *>(p.out)[oi] = acc + base;
+                    else reinterpret_cast<__half *>(p.out)[oi] = __float2half_rn(acc + base);
+                }
+            }
+            const int next = tile + EG * gridDim.x;
+            if (next < p.num_tiles) fetch(next, nxt);
+            asm volatile("bar.sync %0, %1;" ::"r"(2 + eg), "n"(32 * WPG) : "memory");  // xg may be overwritten by the next tile
+          }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, TAPN_TMEM_COLS);
+}
+
+size_t tc_tapn_weight_bytes(int Cout, int Cin, int ks) {
+    return (ks == 3 && Cout >= 1 && Cout <= 3 && Cin % 16 == 0 && Cin >= 16 && Cin <= 64) ? (size_t)(Cin / 8) * 32 * 16 : 0;
+}
+__global__ void pack_weight_tapn_kernel(const float *__restrict__ w, __half *__restrict__ dst, int Cout, int Cin, int total) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int e = i % 8, n = (i / 8) % 32, q = i / 256;
+        const int tap = n / Cout, co = n % Cout, cin = q * 8 + e;
+        dst[i] = __float2half_rn(n < 9 * Cout ? w[((long long)co * Cin + cin) * 9 + tap] : 0.f);
+    }
+}
+int pack_weight_tapn(const float *w_oihw, void *dst, int Cout, int Cin, cudaStream_t s) {
+    RVSR_CHECK_ARG(tc_tapn_weight_bytes(Cout, Cin, 3) > 0, "tapn pack: unsupported shape %d <- %d", Cout, Cin);
+    const int total = (Cin / 8) * 32 * 8;
+    pack_weight_tapn_kernel<<<(total + 255) / 256, 256, 0, s>>>(w_oihw, reinterpret_cast<__half *>(dst), Cout, Cin, total);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+
+// op: the conv_last ConvOp (one source, OUT_FINAL, fin filled in); w_tapn from pack_weight_tapn
+int launch_conv_tapn(const ConvOp &op, const void *w_tapn, cudaStream_t s) {
+    const Src &sr = op.src[0];
+    RVSR_CHECK_ARG(op.nsrc == 1 && op.ks == 3 && op.stride == 1 && op.out_mode == OUT_FINAL && w_tapn != nullptr &&
+                       tc_tapn_weight_bytes(op.Cout, sr.C, 3) > 0 && op.fin.nc == op.Cout && op.fin.x != nullptr && op.fin.scale >= 1 &&
+                       op.H % op.fin.scale == 0 && op.W % op.fin.scale == 0 && sr.map == nullptr && sr.fixed_frame < 0,
+                   "tapn conv: unsupported configuration");
+    EncodeTiledFn enc = get_encode();
+    RVSR_CHECK_ARG(enc != nullptr, "tapn conv: cuTensorMapEncodeTiled unavailable");
+    TcTapnParams p;
+    memset(&p, 0, sizeof(p));
+    p.C8s = sr.C / 8;
+    const long long plane = (long long)op.H * op.W * 8;
+    RVSR_CHECK_ARG(sr.image_stride == plane * p.C8s, "tapn conv: source must be densely packed");
+    const cuuint64_t dims[3] = {(cuuint64_t)op.W * 8, (cuuint64_t)op.H, (cuuint64_t)op.N * p.C8s};
+    const cuuint64_t strides[2] = {(cuuint64_t)op.W * 16, (cuuint64_t)op.H * op.W * 16};
+    const cuuint32_t box[3] = {(cuuint32_t)TC_TW * 8, 6, (cuuint32_t)p.C8s};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&p.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(sr.ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("tapn conv: cuTensorMapEncodeTiled failed (%d)", (int)r);
+        return RVSR_E_CUDA;
+    }
+    p.w = reinterpret_cast<const __half *>(w_tapn); p.bias = op.bias; p.out = op.out; p.fin = op.fin;
+    p.N = op.N; p.H = op.H; p.W = op.W; p.nc = op.Cout;
+    static const int dbg = getenv("RVSR_TC_DEBUG") ? atoi(getenv("RVSR_TC_DEBUG")) : 0;
+    p.debug = dbg;
+    p.tiles_x = cdiv(op.W, TC_TW - 2); p.tiles_y = cdiv(op.H, TC_ROWS); p.num_tiles = p.tiles_x * p.tiles_y * op.N;
+    if (p.num_tiles == 0) return RVSR_OK;
+    p.td.tpi = (uint32_t)(p.tiles_x * p.tiles_y); p.td.m_tpi = magic_div(p.td.tpi, (uint32_t)p.num_tiles);
+    p.td.tx = (uint32_t)p.tiles_x; p.td.m_tx = magic_div(p.td.tx, p.td.tpi);
+    const size_t stage = (size_t)p.C8s * 6 * TC_TW * 16;
+    const size_t fixed = (size_t)p.C8s * 32 * 16 + 128 + TAPN_EG * TAPN_XCH * sizeof(float) + 8 * sizeof(float) + 512;
+    int st = (int)((TC_SMEM_LIMIT - fixed) / stage);
+    if (st > 6) st = 6;
+    RVSR_CHECK_ARG(st >= 2, "tapn conv: not enough shared memory");
+    p.nstages = st;
+    const size_t smem = fixed + (size_t)st * stage + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        RVSR_CUDA(cudaFuncSetAttribute(conv_tapn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT + 1024));
+        attr_set = true;
+    }
+    int gx = sm_count();
+    if (gx > p.num_tiles) gx = p.num_tiles;
+    launch_k(conv_tapn_kernel, dim3(gx), dim3(TAPN_THREADS), smem, s, p);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+
 }  // namespace rvsr
