@@ -83,8 +83,9 @@ class EDVREngine:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._ws
 
-    def forward(self, x, out_dtype=None):
-        """x: [B, N, C, H, W] CUDA tensor (fp32 or fp16) -> [B, C, sH, sW] of out_dtype (default x.dtype)."""
+    def forward(self, x, out_dtype=None, out=None):
+        """x: [B, N, C, H, W] CUDA tensor (fp32 or fp16) -> [B, C, sH, sW] of out_dtype (default x.dtype);
+        `out`: optional preallocated result tensor."""
         if not x.is_cuda:
             raise NotImplementedError("realvsr_b200 engine runs on CUDA tensors only (no CPU fallback)")
         if x.dim() != 5 or x.shape[1] != self.cfg.nframes or x.shape[2] != self.cfg.nc:
@@ -92,8 +93,12 @@ class EDVREngine:
                                                                                tuple(x.shape)))
         x = x.contiguous()
         B, _, _, H, W = x.shape
-        out = torch.empty(B, self.cfg.nc, H * self.scale, W * self.scale, device=x.device,
-                          dtype=out_dtype or x.dtype)
+        if out is None:
+            out = torch.empty(B, self.cfg.nc, H * self.scale, W * self.scale, device=x.device,
+                              dtype=out_dtype or x.dtype)
+        elif tuple(out.shape) != (B, self.cfg.nc, H * self.scale, W * self.scale) or not out.is_cuda or not out.is_contiguous():
+            raise RuntimeError("forward: `out` must be a contiguous CUDA tensor of shape %s" %
+                               ((B, self.cfg.nc, H * self.scale, W * self.scale),))
         with torch.cuda.device(self.device):
             ws = self._workspace(B, H, W)
             _lib.check(self.L.rvsr_engine_forward(self.h, ctypes.c_void_p(x.data_ptr()), _dt(x),
@@ -126,6 +131,10 @@ class EDVREngine:
                 ctypes.c_void_p(ws.data_ptr()), ws.numel(), self._stream()), "engine_forward_host")
             torch.cuda.current_stream(self.device).synchronize()
         return out_host
+
+    def host_pipeline(self, depth=2):
+        """Pipelined variant of forward_host for streams of windows: see HostPipeline."""
+        return HostPipeline(self, depth)
 
     # ------------------------------------------------------------------ sliding-window feature cache
     def make_cache(self, n_slots, H, W):
@@ -207,3 +216,61 @@ class EDVREngine:
             _lib.check(self.L.rvsr_engine_read_tap(self.h, name.encode(), ctypes.c_void_p(dst.data_ptr()),
                                                    dst.numel(), self._stream()), "read_tap")
         return dst
+
+
+class HostPipeline:
+    """Host tensors in, host tensors out, for a STREAM of window batches: the H2D copy of batch i + 1 and the D2H
+    copy of batch i - 1 run on their own CUDA streams while batch i is computed (the reference's test loop,
+    test_RealVSR_wi_GT.py:114-119 + utils/util.py:222-237, copies, computes and reads back strictly in turn).
+
+        pipe = engine.host_pipeline()
+        for x_host, out_host in batches:      # pinned host tensors
+            pipe.submit(x_host, out_host)     # returns at once; out_host is valid after wait()/drain()
+        pipe.drain()
+
+    `depth` device staging buffers per direction; submit() blocks the host only when all of them are in flight."""
+
+    def __init__(self, engine, depth=2):
+        self.e, self.depth, self.i = engine, max(2, int(depth)), 0
+        dev = engine.device
+        self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.slots = None
+        self.key = None
+
+    def _alloc(self, x_host):
+        e = self.e
+        B, _, _, H, W = x_host.shape
+        self.key = (tuple(x_host.shape), x_host.dtype)
+        self.slots = [dict(din=torch.empty(x_host.shape, dtype=x_host.dtype, device=e.device),
+                           dout=torch.empty(B, e.cfg.nc, H * e.scale, W * e.scale, dtype=x_host.dtype, device=e.device),
+                           ev_in=torch.cuda.Event(), ev_done=torch.cuda.Event(), ev_out=torch.cuda.Event(), busy=False)
+                      for _ in range(self.depth)]
+
+    def submit(self, x_host, out_host):
+        if self.key != (tuple(x_host.shape), x_host.dtype):
+            self.drain()
+            self._alloc(x_host)
+        sl = self.slots[self.i % self.depth]
+        self.i += 1
+        compute = torch.cuda.current_stream(self.e.device)
+        if sl["busy"]:
+            sl["ev_out"].synchronize()      # the slot's previous result has left the device
+        with torch.cuda.stream(self.s_in):
+            sl["din"].copy_(x_host, non_blocking=True)
+            sl["ev_in"].record(self.s_in)
+        compute.wait_event(sl["ev_in"])
+        self.e.forward(sl["din"], out=sl["dout"])
+        sl["ev_done"].record(compute)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(sl["ev_done"])
+            out_host.copy_(sl["dout"], non_blocking=True)
+            sl["ev_out"].record(self.s_out)
+        sl["busy"] = True
+        return out_host
+
+    def drain(self):
+        if self.slots:
+            for sl in self.slots:
+                if sl["busy"]:
+                    sl["ev_out"].synchronize()
+                    sl["busy"] = False

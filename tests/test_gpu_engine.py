@@ -111,6 +111,27 @@ def test_engine_host_buffers_roundtrip():
     assert torch.equal(out, y.cpu())
 
 
+def test_engine_host_pipeline_matches_forward_host():
+    """HostPipeline (H2D / forward / D2H on three streams, double-buffered) returns bit-identical frames to the
+    one-at-a-time forward_host, for a stream of different inputs and with staging slots being reused."""
+    c = load_case("edvr_tiny")
+    net = _net(c, "engine")
+    x = c["x"].to(DEV)
+    with torch.no_grad():
+        net(x)
+    eng = net._get_engine(x)
+    g = torch.Generator().manual_seed(5)
+    xs = [c["x"].pin_memory()] + [torch.rand(c["x"].shape, generator=g).pin_memory() for _ in range(4)]
+    want = [eng.forward_host(xh).clone() for xh in xs]
+    outs = [torch.empty_like(want[0]).pin_memory() for _ in xs]
+    pipe = eng.host_pipeline(depth=2)
+    for xh, oh in zip(xs, outs):
+        pipe.submit(xh, oh)
+    pipe.drain()
+    for w, o in zip(want, outs):
+        assert torch.equal(w, o)
+
+
 def test_cfg2_full_size_fp16_properties():
     """BASELINE cfg2 size (5x3x180x320 -> 720x1280, nf=64, TSA): too slow for the CPU oracle,
     so check size-independent properties: finite, deterministic, zero-initialised offset
