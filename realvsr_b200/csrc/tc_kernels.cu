@@ -141,6 +141,10 @@ __device__ __forceinline__ void ld_global_nc_256(const void *p, uint4 &a, uint4 
                  : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
                  : "l"(p));
 }
+// the first TMA through a descriptor pays a descriptor fetch: warm it while the previous kernel still drains
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tmap, uint32_t bar, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -657,6 +661,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 const uint32_t n = w_bytes - o < 32768 ? w_bytes - o : 32768;
                 bulk_load(smem_u32(w_s + o), wg + o, n, WFULL);
             }
+            for (int s = 0; s < p.nsrc; ++s) prefetch_tensormap(&p.tmap[s]);
             pdl_wait();  // weights are static; everything below reads the previous kernel's output
             // ---- halo tiles
             uint32_t it = 0, tl = 0;
@@ -892,6 +897,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
             const uint32_t n = w_bytes - o < 32768 ? w_bytes - o : 32768;
             bulk_load(smem_u32(w_s + o), wg + o, n, WFULL);
         }
+        for (int s = 0; s < p.nsrc; ++s) prefetch_tensormap(&p.tmap[s]);
     }
     // Kept OFF the prologue's critical path (every launch pays it): the bias is staged by the epilogue warps while
     // the first halo tiles are in flight, and the weights are awaited by the issuers -- the leader needs both halves:
@@ -1709,6 +1715,7 @@ __global__ void __launch_bounds__(TAPN_THREADS, 1) conv_tapn_kernel(const __grid
         if (lane == 0) {
             mbar_expect_tx(WFULL, w_bytes);
             bulk_load(smem_u32(w_s), p.w, w_bytes, WFULL);
+            prefetch_tensormap(&p.tmap);
             pdl_wait();
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
