@@ -175,6 +175,21 @@ int rvsr_engine_profile_entry(const rvsr_engine *e, int i, char *label, int labe
 int rvsr_engine_read_tap(rvsr_engine *e, const char *name, float *dst_dev, size_t dst_elems,
                          void *stream);
 
+/* ---- image I/O around the model, on the device ------------------------------------
+ * rvsr_frames_from_u8 replaces, for T frames at once, data/util.py::read_img (:87-101: uint8 -> float32 / 255) and
+ * ::read_img_seq (:104-122: channel reversal [2, 1, 0] when reverse_channels != 0, HWC -> CHW, stack):
+ *   u8_thwc [T, H, W, C] uint8 (file order, as cv2.imread returns it)  ->  out_tchw [T, C, H, W] of out_dtype.
+ * rvsr_frames_to_u8 replaces the reference test loop's egress (test_RealVSR_wi_GT.py:121-128):
+ *   color_mode 0: utils/util.py::tensor2img(out_type=uint8, reverse_channel=True) (:151-181)
+ *   color_mode 1: tensor2img(out_type=float32, reverse_channel=False) + data/util.py::ycbcr2bgr (:397-416)
+ *                 + (np.clip(., 0, 1) * 255.).round().astype(uint8)
+ *   in_bchw [B, 3, H, W] (fp32 / fp16)  ->  u8_bhwc_bgr [B, H, W, 3] uint8, ready for cv2.imwrite.  Bit-exact with
+ *   the numpy arithmetic (float32 / float64 steps and round-half-to-even reproduced). */
+int rvsr_frames_from_u8(const void *u8_thwc, void *out_tchw, int T, int C, int H, int W, int reverse_channels,
+                        int out_dtype, void *stream);
+int rvsr_frames_to_u8(const void *in_bchw, int in_dtype, void *u8_bhwc_bgr, int B, int C, int H, int W,
+                      int color_mode, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

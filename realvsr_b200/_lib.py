@@ -36,6 +36,8 @@ SIGNATURES = {
     "rvsr_mdcn_pack_fwd": (c_int, [c_void_p] * 7 + [c_int] * 8 + [c_void_p, c_size_t, c_void_p]),
     "rvsr_conv2d_fwd_workspace_bytes": (c_size_t, [c_int] * 8),
     "rvsr_conv2d_fwd": (c_int, [c_void_p] * 6 + [c_int] * 12 + [c_void_p, c_size_t, c_void_p]),
+    "rvsr_frames_from_u8": (c_int, [c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),
+    "rvsr_frames_to_u8": (c_int, [c_void_p, c_int, c_void_p] + [c_int] * 5 + [c_void_p]),
     "rvsr_engine_create": (c_int, [ctypes.POINTER(EdvrConfig), ctypes.POINTER(c_void_p)]),
     "rvsr_engine_destroy": (None, [c_void_p]),
     "rvsr_engine_set_weight": (c_int, [c_void_p, c_char_p, c_void_p, ctypes.POINTER(ctypes.c_int64), c_int,

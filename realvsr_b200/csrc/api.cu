@@ -489,6 +489,26 @@ int rvsr_engine_profile_entry(const rvsr_engine *e, int i, char *label, int labe
     if (bytes) *bytes = p.bytes;
     return RVSR_OK;
 }
+int rvsr_frames_from_u8(const void *u8_thwc, void *out_tchw, int T, int C, int H, int W, int reverse_channels, int out_dtype,
+                        void *stream) {
+    RVSR_CHECK_ARG(T >= 0 && C >= 1 && C <= 4 && H > 0 && W > 0, "frames_from_u8: bad shape T=%d C=%d H=%d W=%d", T, C, H, W);
+    RVSR_CHECK_ARG(out_dtype == RVSR_F32 || out_dtype == RVSR_F16, "frames_from_u8: bad dtype %d", out_dtype);
+    if (T == 0) return RVSR_OK;
+    RVSR_CHECK_ARG(u8_thwc != nullptr && out_tchw != nullptr, "frames_from_u8: null buffer");
+    if (out_dtype == RVSR_F32)
+        return launch_frames_from_u8<float>((const uint8_t *)u8_thwc, (float *)out_tchw, T, C, H, W, reverse_channels, (cudaStream_t)stream);
+    return launch_frames_from_u8<__half>((const uint8_t *)u8_thwc, (__half *)out_tchw, T, C, H, W, reverse_channels, (cudaStream_t)stream);
+}
+int rvsr_frames_to_u8(const void *in_bchw, int in_dtype, void *u8_bhwc_bgr, int B, int C, int H, int W, int color_mode, void *stream) {
+    RVSR_CHECK_ARG(B >= 0 && C == 3 && H > 0 && W > 0, "frames_to_u8: expected [B, 3, H, W], got C=%d", C);
+    RVSR_CHECK_ARG(in_dtype == RVSR_F32 || in_dtype == RVSR_F16, "frames_to_u8: bad dtype %d", in_dtype);
+    RVSR_CHECK_ARG(color_mode == 0 || color_mode == 1, "frames_to_u8: color_mode must be 0 (RGB) or 1 (YCbCr), got %d", color_mode);
+    if (B == 0) return RVSR_OK;
+    RVSR_CHECK_ARG(in_bchw != nullptr && u8_bhwc_bgr != nullptr, "frames_to_u8: null buffer");
+    if (in_dtype == RVSR_F32)
+        return launch_frames_to_u8<float>((const float *)in_bchw, (uint8_t *)u8_bhwc_bgr, B, H, W, color_mode, (cudaStream_t)stream);
+    return launch_frames_to_u8<__half>((const __half *)in_bchw, (uint8_t *)u8_bhwc_bgr, B, H, W, color_mode, (cudaStream_t)stream);
+}
 int rvsr_engine_read_tap(rvsr_engine *e, const char *name, float *dst_dev, size_t dst_elems, void *stream) {
     RVSR_CHECK_ARG(e != nullptr, "null engine");
     return e->impl.read_tap(name, dst_dev, dst_elems, (cudaStream_t)stream);

@@ -251,6 +251,10 @@ int launch_pack_nchw(const Tin *src, T *dst, int N, int C, int H, int W, cudaStr
 int pad_weight_cin(const float *w, float *dst, int Cout, int Cin, int Cpad, int KK, cudaStream_t s);
 template <typename T, typename Tout>
 int launch_unpack_nchw(const T *src, Tout *dst, int N, int C, int H, int W, cudaStream_t s);
+template <typename Tout>
+int launch_frames_from_u8(const uint8_t *src, Tout *dst, int T, int C, int H, int W, int reverse, cudaStream_t s);
+template <typename Tin>
+int launch_frames_to_u8(const Tin *src, uint8_t *dst, int B, int H, int W, int mode, cudaStream_t s);
 template <typename T>
 int launch_upsample2x(const T *src, T *dst, int N, int C, int H, int W, float scale, cudaStream_t s);
 template <typename T>

@@ -882,4 +882,84 @@ int fold_grouped_weight(const float *gd, float *gw, int Cout, int C, int K, int 
     RVSR_LAUNCH_CHECK();
     return RVSR_OK;
 }
+
+// ---------------------------------------------------------------- image I/O around the model
+// Ingest: what data/util.py::read_img (:87-101, uint8 -> float32 / 255) + read_img_seq (:104-122, channel reversal
+// [2, 1, 0], HWC -> CHW, stack) do on the host, for T frames at once.
+template <typename Tout>
+__global__ void frames_from_u8_kernel(const uint8_t *__restrict__ src, Tout *__restrict__ dst, int C, int H, int W,
+                                      int reverse, long long total) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W);
+        long long r = i / W;
+        const int y = (int)(r % H);
+        r /= H;
+        const int c = (int)(r % C);
+        const long long t = r / C;
+        const int cs = reverse ? C - 1 - c : c;
+        const float v = (float)src[((t * H + y) * W + x) * C + cs] / 255.f;  // float32 division, like numpy
+        dst[i] = from_f<Tout>(v);
+    }
+}
+template <typename Tout>
+int launch_frames_from_u8(const uint8_t *src, Tout *dst, int T, int C, int H, int W, int reverse, cudaStream_t s) {
+    const long long total = (long long)T * C * H * W;
+    if (total == 0) return RVSR_OK;
+    frames_from_u8_kernel<Tout><<<(int)((total + 255) / 256 < 16384 ? (total + 255) / 256 : 16384), 256, 0, s>>>(src, dst, C, H, W, reverse, total);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+template int launch_frames_from_u8<float>(const uint8_t *, float *, int, int, int, int, int, cudaStream_t);
+template int launch_frames_from_u8<__half>(const uint8_t *, __half *, int, int, int, int, int, cudaStream_t);
+
+// Egress: network output [B, 3, H, W] -> uint8 BGR images [B, H, W, 3], the arithmetic of the reference's test loop:
+//   mode 0 (RGB model)   utils/util.py::tensor2img(out_type=uint8, reverse_channel=True) (:151-181):
+//                        clamp to [0, 1], RGB -> BGR, (x * 255.0).round() in float32
+//   mode 1 (YCbCr model) tensor2img(out_type=float32, reverse_channel=False), then data/util.py::ycbcr2bgr (:397-416)
+//                        and (np.clip(., 0, 1) * 255.).round() (test_RealVSR_wi_GT.py:122-123).  ycbcr2bgr multiplies
+//                        the float32 image by a float64 matrix: that part runs in double here as well.
+// np.round / ndarray.round are round-half-to-even: rintf / rint.
+template <typename Tin>
+__global__ void frames_to_u8_kernel(const Tin *__restrict__ src, uint8_t *__restrict__ dst, int H, int W, int mode, long long total) {
+    const long long plane = (long long)H * W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / plane, pix = i % plane;
+        const Tin *p = src + b * 3 * plane + pix;
+        float v[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c] = fminf(fmaxf(to_f<Tin>(p[c * plane]), 0.f), 1.f);  // clamp_(0, 1); (x - 0) / (1 - 0)
+        uint8_t *o = dst + i * 3;
+        if (mode == 0) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) o[2 - c] = (uint8_t)rintf(v[c] * 255.0f);
+        } else {
+            const double M[3][3] = {{0.00456621, 0.00456621, 0.00456621}, {0.00791071, -0.00153632, 0}, {0, -0.00318811, 0.00625893}};
+            const double off[3] = {-276.836, 135.576, -222.921};
+            float img[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) img[c] = v[c] * 255.f;  // img *= 255. on the float32 array
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                // numpy matmul (float32 promoted to float64), K = 3: plain multiply-adds in index order, no fma contraction
+                double acc = __dmul_rn((double)img[0], M[0][k]);
+                acc = __dadd_rn(acc, __dmul_rn((double)img[1], M[1][k]));
+                acc = __dadd_rn(acc, __dmul_rn((double)img[2], M[2][k]));
+                const double rlt = __ddiv_rn(__dadd_rn(__dmul_rn(acc, 255.0), off[k]), 255.0);
+                const float f = fminf(fmaxf((float)rlt, 0.f), 1.f);  // astype(float32); np.clip(., 0, 1)
+                o[k] = (uint8_t)rintf(f * 255.f);
+            }
+        }
+    }
+}
+template <typename Tin>
+int launch_frames_to_u8(const Tin *src, uint8_t *dst, int B, int H, int W, int mode, cudaStream_t s) {
+    const long long total = (long long)B * H * W;
+    if (total == 0) return RVSR_OK;
+    frames_to_u8_kernel<Tin><<<(int)((total + 255) / 256 < 16384 ? (total + 255) / 256 : 16384), 256, 0, s>>>(src, dst, H, W, mode, total);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+template int launch_frames_to_u8<float>(const float *, uint8_t *, int, int, int, int, cudaStream_t);
+template int launch_frames_to_u8<__half>(const __half *, uint8_t *, int, int, int, int, cudaStream_t);
+
 }  // namespace rvsr
