@@ -92,13 +92,19 @@ CASES = {
                                               back_RBs=10, w_TSA=False), (1, 3, 3, 20, 16), 51, 52),
     "edvr_predeblur": ("EDVR", dict(nf=16, nc=3, nframes=3, groups=4, front_RBs=1, back_RBs=1,
                                     predeblur=True, w_TSA=True), (1, 3, 3, 16, 16), 61, 62),
+    # BASELINE cfg4's architecture (7 frames, 128 channels, 16 channels per deformable group) on a small crop
+    "edvr_nf128_7f": ("EDVR", dict(nf=128, nc=3, nframes=7, groups=8, front_RBs=5, back_RBs=10,
+                                   w_TSA=True), (1, 7, 3, 16, 24), 71, 72),
 }
 
 
 def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     E, tvo = import_reference()
+    only = sys.argv[1:]  # optional: regenerate just these cases
     for name, (cls, kw, shape, wseed, xseed) in CASES.items():
+        if only and name not in only:
+            continue
         net = getattr(E, cls)(**kw).eval()
         sd = synth_state_dict({k: v.shape for k, v in net.state_dict().items()}, wseed)
         net.load_state_dict(sd, strict=True)
@@ -118,6 +124,8 @@ def main():
             keys=np.array(list(sd.keys())), torch_version=torch.__version__)
         print(name, tuple(y.shape), float(y.abs().mean()), "aligned0", float(taps["aligned0"].abs().mean()))
 
+    if only and "dcn_unit" not in only:
+        return
     # unit-level DCN fixture: large offsets (many taps leave the image), fp64 + grads
     B, C, H, W, Cout, dg = 2, 16, 11, 13, 12, 4
     x = synth_normal((B, C, H, W), 71).double().requires_grad_()
