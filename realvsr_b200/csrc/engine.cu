@@ -400,6 +400,42 @@ template <typename T> struct Plan {
                 return launch_pool_maxavg<T>((const T *)a.p, (T *)mx.p, (T *)av.p, a.N, a.C, a.H, a.W, s); });
     }
     Act resblocks(const std::string &prefix, int count, Act cur) {
+        // fp16 / 64 channels / enough tiles: the whole run (2 * count convolutions) is ONE persistent launch with
+        // tile-level dataflow between the layers (conv_chain_kernel); otherwise one launch per convolution
+        if (use_tc && sizeof(T) == 2 && cur.C == 64 && count >= 1 && conv_chain_supported(2 * count, cur.N, cur.H, cur.W)) {
+            bool ok = true;
+            for (int i = 0; i < count && ok; ++i)
+                for (const char *c : {".conv1", ".conv2"}) {
+                    const PackedConv *pc = get(prefix + "." + std::to_string(i) + c);
+                    ok = ok && pc != nullptr && pc->w_tc2 != nullptr && pc->Cout == 64 && pc->Cin == 64 && pc->ks == 3;
+                }
+            if (ok) {
+                std::vector<ChainLayerDesc> ls;
+                const Act in0 = cur;
+                double flops = 0, bytes = 0;
+                for (int i = 0; i < count; ++i) {
+                    const std::string b = prefix + "." + std::to_string(i);
+                    const PackedConv *p1 = get(b + ".conv1"), *p2 = get(b + ".conv2");
+                    Act t = make(cur.N, 64, cur.H, cur.W);
+                    Act o = make(cur.N, 64, cur.H, cur.W);
+                    ls.push_back(ChainLayerDesc{cur.p, p1->w_tc2, p1->bias, t.p, nullptr, RVSR_ACT_RELU});
+                    ls.push_back(ChainLayerDesc{t.p, p2->w_tc2, p2->bias, o.p, cur.p, RVSR_ACT_NONE});
+                    const double px = (double)cur.N * cur.H * cur.W;
+                    flops += 2 * 2.0 * 64 * 64 * 9 * px;
+                    bytes += px * 64 * sizeof(T) * 5;  // conv1: in + out; conv2: in + residual + out
+                    cur = o;
+                }
+                void *scratch = ar.alloc(conv_chain_scratch_bytes(2 * count, in0.N, in0.H));
+                if (scratch == nullptr && rc == RVSR_OK) { set_error("workspace too small"); rc = RVSR_E_WORKSPACE; }
+                if (!dry && rc == RVSR_OK) {
+                    eng->host_chain_.emplace_back();
+                    std::vector<char> &staging = eng->host_chain_.back();
+                    launch("tc:chain3x3_co64:" + prefix + " x" + std::to_string(2 * count), flops, bytes,
+                           [&] { return launch_conv_chain(ls.data(), (int)ls.size(), in0.N, in0.H, in0.W, scratch, staging, s); });
+                }
+                return cur;
+            }
+        }
         for (int i = 0; i < count; ++i) {
             const std::string b = prefix + "." + std::to_string(i);
             Act t = conv(b + ".conv1", {src_of(cur)}, cur.N, cur.H, cur.W, RVSR_ACT_RELU);
@@ -708,6 +744,7 @@ int Engine::forward(const void *x, int x_dtype, void *out, int out_dtype, int B,
     const size_t mis = (size_t)(reinterpret_cast<uintptr_t>(ws) % 1024);
     if (mis) { ar.base += 1024 - mis; ar.cap -= 1024 - mis; }
     host_maps_.clear();
+    host_chain_.clear();
     const int rc = cfg_.precision == RVSR_F16 ? run<__half>(ar, false, x, x_dtype, out, out_dtype, B, H, W, s, nullptr)
                                               : run<float>(ar, false, x, x_dtype, out, out_dtype, B, H, W, s, nullptr);
     tc_stamps_dump();  // debug only (RVSR_TC_STAMPS): synchronises
@@ -750,6 +787,7 @@ int Engine::extract_features(const void *frames, int dtype, int F, int H, int W,
     CacheArgs ca = {};
     ca.extract = true; ca.cache = cache; ca.n_slots = n_slots; ca.slot0 = slot0;
     prof_clear();
+    host_chain_.clear();
     if (cfg_.precision == RVSR_F16) return run<__half>(ar, false, frames, dtype, nullptr, RVSR_F32, F, H, W, s, &ca);
     return run<float>(ar, false, frames, dtype, nullptr, RVSR_F32, F, H, W, s, &ca);
 }
@@ -770,6 +808,7 @@ int Engine::forward_cached(const void *cache, int n_slots, const int *window_slo
     prof_clear();
     prof_.reserve(1024);
     host_maps_.clear();
+    host_chain_.clear();
     if (cfg_.precision == RVSR_F16) return run<__half>(ar, false, frames, x_dtype, out, out_dtype, B, H, W, s, &ca);
     return run<float>(ar, false, frames, x_dtype, out, out_dtype, B, H, W, s, &ca);
 }

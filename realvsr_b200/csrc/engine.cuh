@@ -113,6 +113,8 @@ class Engine {
     bool profiling_ = false;
     std::vector<ProfEntry> prof_;
     std::vector<std::vector<int>> host_maps_;
+  public:
+    std::vector<std::vector<char>> host_chain_;  // layer tables of the chain launches of the current forward (async H2D sources)
 };
 
 // tc_kernels.cu: tcgen05 paths (fp16 storage).  Return RVSR_E_UNSUPPORTED when the shape is
@@ -125,6 +127,18 @@ size_t tc_conv_weight_bytes(int Cout, int Cin, int ks, int mode = 0);
 int pack_weight_tc(const float *w_oihw, void *dst, int Cout, int Cin, int ks, int mode, cudaStream_t s);
 size_t tc2_weight_bytes(int Cout, int Cin, int ks, int mode = 0);
 int pack_weight_tc2(const float *w_oihw, void *dst, int Cout, int Cin, int ks, int mode, cudaStream_t s);
+// one persistent launch for a run of same-shape 64 -> 64 3x3 convolutions (tile-level dataflow between layers)
+struct ChainLayerDesc {
+    const void *src;        // [N][8][H][W][8] fp16, densely packed
+    const void *w_tc2;      // pack_weight_tc2 layout
+    const float *bias;
+    void *out;
+    const void *residual;   // or null
+    int act;
+};
+size_t conv_chain_scratch_bytes(int L, int N, int H);
+bool conv_chain_supported(int L, int N, int H, int W);
+int launch_conv_chain(const ChainLayerDesc *layers, int L, int N, int H, int W, void *scratch, std::vector<char> &staging, cudaStream_t s);
 size_t tc_tapn_weight_bytes(int Cout, int Cin, int ks);   // conv_last "taps in N" kernel (Cout <= 3)
 int pack_weight_tapn(const float *w_oihw, void *dst, int Cout, int Cin, cudaStream_t s);
 int launch_conv_tapn(const ConvOp &op, const void *w_tapn, cudaStream_t s);

@@ -27,6 +27,7 @@
 #include <stdlib.h>
 
 #include <type_traits>
+#include <vector>
 
 #include "engine.cuh"
 
@@ -489,7 +490,7 @@ __device__ __forceinline__ float2 mul2(float2 a, float2 b) {
     return *reinterpret_cast<float2 *>(&r);
 }
 
-template <int ACT, typename Release>
+template <int ACT, bool RES_CG = false, typename Release>
 __device__ __forceinline__ void epi_c8_fast(const float *bias_s, __half *out, long long out_image_stride, const __half *residual,
                                             long long res_image_stride, int H, int W, int Co8, uint32_t taddr, int half,
                                             int qbase, int n, int y, int x, bool valid, uint32_t full_bar, uint32_t full_par,
@@ -502,7 +503,8 @@ __device__ __forceinline__ void epi_c8_fast(const float *bias_s, __half *out, lo
     if (has_res) {
         const uint4 *r = reinterpret_cast<const uint4 *>(residual + (long long)n * res_image_stride) + q0 * plane + pix;
 #pragma unroll
-        for (int j = 0; j < NBLK; ++j) res[j] = q0 + j < Co8 ? __ldg(r + j * plane) : make_uint4(0, 0, 0, 0);
+        for (int j = 0; j < NBLK; ++j)  // RES_CG: the residual was written earlier in the SAME kernel (chain): L2-coherent load
+            res[j] = q0 + j < Co8 ? (RES_CG ? __ldcg(r + j * plane) : __ldg(r + j * plane)) : make_uint4(0, 0, 0, 0);
     }
     mbar_wait(full_bar, full_par);
     tc_fence_after();
@@ -1082,6 +1084,317 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
     if (warp == 3) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
 }
 
+// ---------------------------------------------------------------- chain of 64 -> 64 3x3 convolutions, ONE launch
+// A run of same-shape convolutions (the residual trunks: conv - ReLU - conv + skip, 10 and 20 layers deep) pays
+// ~7 us per kernel boundary (drain, launch, prologue, first halo load, first tile: RVSR_TC_STAMPS) for 12 us of
+// work at 4 images.  conv_chain_kernel runs the whole run in one persistent CTA-pair kernel:
+//   * layers are executed in order by every cluster over the same static tile assignment; barriers, TMEM and the
+//     pipeline stay alive across layers (all phase counters run on the cluster-local tile sequence k);
+//   * tile-level dataflow instead of a grid barrier: the epilogue publishes "tile done" on a per (layer, image,
+//     tile row) counter (stores -> __threadfence -> red.release.gpu); the producer of layer l acquires the three rows
+//     it needs from layer l - 1 (ld.acquire.gpu -> fence.proxy.async -> TMA).  Every cluster finishes layer l - 1
+//     without waiting on layer l, all CTAs are co-resident (grid = SM count), so the waits cannot deadlock;
+//   * weights are double buffered (2 x 36 KB per CTA): layer l + 1 is staged into the buffer of layer l - 1 as
+//     soon as the issuers have committed that layer (LDONE), tested without blocking between halo loads.
+struct alignas(128) TcChainLayer {
+    CUtensorMap tmap;        // input of this layer
+    const __half *w;         // CTA-pair layout [rank][tap][8][32][8]
+    const float *bias;       // [64] or null
+    __half *out;
+    const __half *residual;  // null, or a tensor produced earlier (added after the activation)
+    int act, pad[3];
+};
+struct alignas(64) TcChainParams {
+    CUtensorMap tmaps[20];       // input of every layer (kernel-parameter space, like the single-layer kernels)
+    const TcChainLayer *layers;  // device
+    unsigned *flags;             // [nlayers][N][tiles_y], zeroed before the launch
+    long long image_stride;      // halfs per image (every tensor of the chain: 64 channels, H x W)
+    int nlayers, N, H, W, nstages;
+    int tiles_x, tiles_y, num_tiles;
+    TileDiv td;
+    int debug;  // RVSR_CHAIN_DEBUG timing experiments (results may be wrong): 1 no producer fence, 2 no epilogue fence, 4 no counter wait
+};
+constexpr int CHAIN_MAX_LAYERS = 20;  // bias table in shared memory: 20 x 256 B leaves room for six halo stages
+
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_relaxed_gpu_add(unsigned *p, unsigned v) {  // release = the fence.acq_rel.gpu before it
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_chain_kernel(const __grid_constant__ TcChainParams p) {
+    constexpr int NT = 64, NH2 = 32, KS = 3, KK = 9, PAD = 1, VALID = TC_TW - 2, HALO_ROWS = TC_ROWS + 2;
+    constexpr int PLANE_BYTES = HALO_ROWS * TC_TW * 16, C8S = 8;
+    constexpr int ACC = 64, MMAW = 3, EG = TC_EPI_GROUPS, NB = 6, TMEM_COLS = 512, WPG = TC_EPI_WARPS / EG;
+    constexpr uint32_t w_bytes = C8S * KK * NH2 * 16, stage_bytes = C8S * PLANE_BYTES;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int S = p.nstages, L = p.nlayers;
+    uint8_t *w_s = smem;                              // two weight buffers
+    uint8_t *stage_s = smem + 2 * w_bytes;
+    float *bias_all = reinterpret_cast<float *>(stage_s + (size_t)S * stage_bytes + 128);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(bias_all + CHAIN_MAX_LAYERS * NT);
+    const int base2 = (MMAW + 1) * S;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + base2 + 6 + 2 * NB);
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    auto FULL = [&](int w, int st) { return BAR(w * S + st); };
+    auto EMPTY = [&](int st) { return BAR(MMAW * S + st); };
+    auto WFULL = [&](int b) { return BAR(base2 + b); };
+    auto WPEER = [&](int b) { return BAR(base2 + 2 + b); };
+    auto LDONE = [&](int b) { return BAR(base2 + 4 + b); };
+    auto TFULL = [&](int b) { return BAR(base2 + 6 + b); };
+    auto TEMPTY = [&](int b) { return BAR(base2 + 6 + NB + b); };
+    const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const uint32_t rank = blockIdx.x & 1u;
+    const int cid = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+    const int npairs = (p.num_tiles + 1) / 2;
+    const int K = cid < npairs ? (npairs - cid + nclusters - 1) / nclusters : 0;  // tile pairs of this cluster per layer
+
+    auto load_w = [&](int l) {  // this CTA's half of layer l's weights -> buffer l & 1
+        const int b = l & 1;
+        mbar_expect_tx(WFULL(b), w_bytes);
+        const uint8_t *wg = reinterpret_cast<const uint8_t *>(p.layers[l].w) + (size_t)rank * w_bytes;
+        for (uint32_t o = 0; o < w_bytes; o += 18432) bulk_load(smem_u32(w_s + b * w_bytes + o), wg + o, 18432, WFULL(b));
+    };
+
+    pdl_trigger();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < MMAW * S; ++i) mbar_init(BAR(i), 2);
+        for (int i = MMAW * S; i < base2 + 4; ++i) mbar_init(BAR(i), 1);      // EMPTY, WFULL x2, WPEER x2
+        mbar_init(LDONE(0), MMAW); mbar_init(LDONE(1), MMAW);
+        for (int i = 0; i < NB; ++i) mbar_init(TFULL(i), 1);
+        for (int i = 0; i < NB; ++i) mbar_init(TEMPTY(i), 2 * WPG);
+        fence_barrier_init();
+        load_w(0);
+        if (L > 1) load_w(1);
+    }
+    if (warp == 3) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = uniform_u32(*tmem_slot);
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t k = 0;
+            int next_w = 2;  // next layer whose weights are still to be requested
+            const unsigned target = (unsigned)p.tiles_x * (unsigned)WPG;  // a tile row is done when all its tiles' epilogue warps reported
+            for (int l = 0; l < L; ++l) {
+                const unsigned *fl = l > 0 ? p.flags + (size_t)(l - 1) * p.N * p.tiles_y : nullptr;
+                for (int kl = 0; kl < K; ++kl, ++k) {
+                    if (next_w < L && next_w <= l + 1 && mbar_test(LDONE(next_w & 1), (uint32_t)(((next_w - 2) >> 1) & 1))) {
+                        load_w(next_w);
+                        ++next_w;
+                    }
+                    const int pr = cid + kl * nclusters;
+                    int tile = 2 * pr + (int)rank;
+                    if (tile >= p.num_tiles) tile = p.num_tiles - 1;
+                    int tx, ty, n;
+                    tile_coords(p.td, tile, tx, ty, n);
+                    // The halo of this tile reads tile rows ty - 1 .. ty + 1 of the previous layer's output.  Every finished
+                    // tile is counted on the counters of the three rows that read it, so ONE counter covers the halo: a relaxed
+                    // load before the wait for a free stage (it normally already shows the target -- the rows were finished
+                    // a layer ago), then one acquire load (a single L2 round trip; a fence.acq_rel.gpu here costs > 1 us).
+                    const unsigned *fr = fl != nullptr ? fl + (size_t)n * p.tiles_y + ty : nullptr;
+                    if (p.debug & 4) fr = nullptr;
+                    const unsigned want = target * (unsigned)(1 + (ty > 0) + (ty + 1 < p.tiles_y));
+                    unsigned v0 = want;
+                    if (fr != nullptr) v0 = (p.debug & 1) ? ld_relaxed_gpu(fr) : ld_acquire_gpu(fr);  // before the stage wait: latency hidden
+                    const int st = (int)(k % (uint32_t)S), w = (int)(k % MMAW);
+                    mbar_wait(EMPTY(st), ((k / (uint32_t)S) & 1) ^ 1);
+                    if (fr != nullptr) {
+                        if (v0 < want) {  // rare: the previous layer has not reached these rows yet
+                            uint32_t spin = 0;
+                            do {
+                                if (++spin > (1u << 24)) __trap();  // protocol bug: fail the launch instead of hanging the GPU
+                                v0 = ld_relaxed_gpu(fr);
+                            } while (v0 < want);
+                            v0 = ld_acquire_gpu(fr);                      // acquire: the producers' stores are visible
+                        }
+                        asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes -> the TMA read below
+                    }
+                    const uint32_t full0 = mapa_rank0(FULL(w, st));
+                    if (rank == 0)
+                        mbar_expect_tx(FULL(w, st), 2 * stage_bytes);
+                    else
+                        mbar_arrive_cluster(full0);
+                    tma_load_3d_2sm(smem_u32(stage_s + (size_t)st * stage_bytes), &p.tmaps[l], full0, (tx * VALID - PAD) * 8,
+                                    ty * TC_ROWS - PAD, n * C8S);
+                }
+                if (next_w == l + 1 && next_w < L) {  // not requested yet (short layer): now it must be
+                    mbar_wait(LDONE(next_w & 1), (uint32_t)(((next_w - 2) >> 1) & 1));
+                    load_w(next_w);
+                    ++next_w;
+                }
+            }
+        }
+    } else if (warp <= MMAW) {
+        if (rank != 0) {
+            if (warp == 1 && lane == 0)
+                for (int l = 0; l < L; ++l) {  // "my half of layer l has landed" -> leader
+                    mbar_wait(WFULL(l & 1), (uint32_t)((l >> 1) & 1));
+                    mbar_arrive_cluster(mapa_rank0(WPEER(l & 1)));
+                }
+        } else {
+            constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((256u >> 4) << 24);
+            const uint32_t mw = (uint32_t)(warp - 1);
+            const uint64_t adesc0 = make_desc(smem_u32(stage_s), PLANE_BYTES, 128);
+            const uint64_t bdesc0 = make_desc(smem_u32(w_s), NH2 * 16, 128);
+            const uint32_t a_hi = (uint32_t)(adesc0 >> 32), b_hi = (uint32_t)(bdesc0 >> 32);
+            const uint32_t a_base = (uint32_t)adesc0, b_base = (uint32_t)bdesc0;
+            constexpr uint32_t stage_units = stage_bytes >> 4, b_tap_step = C8S * NH2;
+            uint32_t k = 0, par = 0;
+            const bool ph = (p.debug & 16) && blockIdx.x == 0 && mw == 0 && lane == 0;
+            long long pa[5] = {0, 0, 0, 0, 0}, tp = 0;
+            uint32_t pn = 0;
+#define CPH(i) do { if (ph) { const long long tn = clock64(); pa[i] += tn - tp; tp = tn; } } while (0)
+            for (int l = 0; l < L; ++l) {
+                const int b = l & 1;
+                if (ph) tp = clock64();
+                mbar_wait(WFULL(b), (uint32_t)((l >> 1) & 1));
+                mbar_wait(WPEER(b), (uint32_t)((l >> 1) & 1));
+                CPH(4);
+                const uint32_t b_lo0 = b_base + (uint32_t)b * (w_bytes >> 4);
+                for (int kl = 0; kl < K; ++kl, ++k) {
+                    if (k % MMAW != mw) continue;
+                    const uint32_t buf = k % NB, st = k % (uint32_t)S;
+                    if (ph) { tp = clock64(); ++pn; }
+                    mbar_wait(TEMPTY(buf), ((k / NB) & 1) ^ 1);
+                    CPH(0);
+                    mbar_wait(FULL(mw, st), (par >> st) & 1);
+                    par ^= 1u << st;
+                    tc_fence_after();
+                    CPH(1);
+                    const uint32_t d = tmem_base + buf * ACC;
+                    const uint32_t a_lo0 = a_base + st * stage_units;
+                    if (elect_one()) {
+#pragma unroll
+                        for (int tap = 0; tap < KK; ++tap) {
+                            const uint32_t a_lo = a_lo0 + (uint32_t)((tap / KS) * TC_TW + (tap % KS));
+                            const uint32_t b_lo = b_lo0 + (uint32_t)tap * b_tap_step;
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                umma_f16_2sm(d, ((uint64_t)a_hi << 32) | (a_lo + (uint32_t)kk * (2 * PLANE_BYTES / 16)),
+                                             ((uint64_t)b_hi << 32) | (b_lo + (uint32_t)kk * (2 * NH2)), idesc, (tap | kk) ? 1u : 0u);
+                        }
+                        umma_commit_2sm(EMPTY(st));
+                        umma_commit_2sm(TFULL(buf));
+                    }
+                    __syncwarp();
+                    CPH(2);
+                }
+                if (elect_one()) umma_commit_2sm(LDONE(b));  // every MMA this issuer made for layer l has completed
+                __syncwarp();
+            }
+            if (ph && pn > 0)
+                printf("[chain issuer0] %u own tiles, %d layers | per own tile: wait-tempty %lld wait-full %lld issue %lld | per layer: wait-weights %lld\n", pn, L,
+                       pa[0] / pn, pa[1] / pn, pa[2] / pn, pa[4] / L);
+#undef CPH
+        }
+    } else if (warp >= TC_EPI_WARP0) {
+        for (int i = threadIdx.x - 32 * TC_EPI_WARP0; i < L * NT; i += 32 * TC_EPI_WARPS) {
+            const float *bp = p.layers[i / NT].bias;
+            bias_all[i] = bp != nullptr ? bp[i % NT] : 0.f;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+        const int lq = warp & 3;
+        const int eg = (warp - TC_EPI_WARP0) / WPG;
+        const int half = ((warp - TC_EPI_WARP0) % WPG) >> 2;
+        uint32_t k = 0;
+        bool pend_valid = false;      // previous tile of this group: stored, not yet published
+        unsigned *pend_base = nullptr;
+        int pend_row = 0;
+        for (int l = 0; l < L; ++l) {
+            const TcChainLayer *ly = p.layers + l;
+            __half *out = ly->out;
+            const __half *res = ly->residual;
+            const int act = ly->act;
+            unsigned *fl = p.flags + (size_t)l * p.N * p.tiles_y;
+            for (int kl = 0; kl < K; ++kl, ++k) {
+                if ((int)(k % EG) != eg) continue;
+                const int pr = cid + kl * nclusters;
+                const int tile = 2 * pr + (int)rank;
+                const bool real = tile < p.num_tiles;
+                int tx, ty, n;
+                tile_coords(p.td, real ? tile : p.num_tiles - 1, tx, ty, n);
+                const int y = ty * TC_ROWS + lq, x = tx * VALID + lane;
+                const bool valid = real && lane < VALID && y < p.H && x < p.W;
+                const uint32_t buf = k % NB, par = (k / NB) & 1;
+                const uint32_t tempty0 = mapa_rank0(TEMPTY(buf));
+                const uint32_t taddr = tmem_base + buf * ACC + ((uint32_t)(lq * 32) << 16);
+                // `release` runs after this tile's accumulator wait + TMEM drain and before its stores: the point where the
+                // PREVIOUS tile of this warp is published ("my part is in memory").  A fence right behind the stores would
+                // wait a full L2 round trip per tile; one accumulator wait later they have long completed.
+                auto release = [&] {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(tempty0);
+                    if (pend_valid) {
+                        // all 8 warps of the group have stored their part of the previous tile (they are all past it):
+                        // group barrier (CTA-scope ordering), then ONE warp fences at GPU scope and publishes for all
+                        // (the release is cumulative) -- a fence per warp and tile costs > 1 us each
+                        asm volatile("bar.sync %0, %1;" ::"r"(2 + eg), "n"(32 * WPG) : "memory");
+                        if ((warp - TC_EPI_WARP0) % WPG == 0) {
+                            if (!(p.debug & 2)) __threadfence();
+                            if (lane < 3) {
+                                const int r = pend_row + lane - 1;
+                                if (r >= 0 && r < p.tiles_y) red_relaxed_gpu_add(pend_base + r, (unsigned)WPG);
+                            }
+                        }
+                    }
+                };
+                if (act == RVSR_ACT_RELU)
+                    epi_c8_fast<RVSR_ACT_RELU, true>(bias_all + l * NT, out, p.image_stride, res, p.image_stride, p.H, p.W, 8, taddr, half, 0, n,
+                                                     y, x, valid, TFULL(buf), par, release);
+                else if (act == RVSR_ACT_LRELU)
+                    epi_c8_fast<RVSR_ACT_LRELU, true>(bias_all + l * NT, out, p.image_stride, res, p.image_stride, p.H, p.W, 8, taddr, half, 0, n,
+                                                      y, x, valid, TFULL(buf), par, release);
+                else
+                    epi_c8_fast<RVSR_ACT_NONE, true>(bias_all + l * NT, out, p.image_stride, res, p.image_stride, p.H, p.W, 8, taddr, half, 0, n,
+                                                     y, x, valid, TFULL(buf), par, release);
+                pend_valid = real; pend_base = fl + (size_t)n * p.tiles_y; pend_row = ty;
+            }
+            if (pend_valid) {  // end of the layer: the next layer's producers need this one now
+                asm volatile("bar.sync %0, %1;" ::"r"(2 + eg), "n"(32 * WPG) : "memory");
+                if ((warp - TC_EPI_WARP0) % WPG == 0) {
+                    __threadfence();
+                    if (lane < 3) {
+                        const int r = pend_row + lane - 1;
+                        if (r >= 0 && r < p.tiles_y) red_relaxed_gpu_add(pend_base + r, (unsigned)WPG);
+                    }
+                }
+                pend_valid = false;
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 3) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+}
+
 // ---------------------------------------------------------------- host side: tensor maps, packing, launch
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -1355,6 +1668,85 @@ int launch_conv_tc(const ConvOp &op, cudaStream_t s) {
 #undef RVSR_TC_CASE
     set_error("tc conv: no kernel instance for ks=%d NT=%d", op.ks, pl.NT);
     return RVSR_E_UNSUPPORTED;
+}
+
+// ---- chain launch: `layers` (host) describes L same-shape 64 -> 64 3x3 convolutions; scratch = device memory for the
+// layer table and the dataflow counters (conv_chain_scratch_bytes), staging = host bytes that must stay alive until the
+// stream has consumed the table copy (the engine keeps it until the next forward).
+size_t conv_chain_scratch_bytes(int L, int N, int H) {
+    return align_up((size_t)L * sizeof(TcChainLayer), 256) + align_up((size_t)L * N * cdiv(H, TC_ROWS) * sizeof(unsigned), 256);
+}
+bool conv_chain_supported(int L, int N, int H, int W) {
+    // OPT-IN (RVSR_CHAIN=1, read at every call so tests can toggle it).  Measured on B200: correct (bit-identical frames),
+    // but not faster than the per-layer launches once those use programmatic dependent launch -- the per-tile dataflow
+    // handshake (one ld.acquire.gpu per halo load, one group barrier + fence.acq_rel.gpu + 3 reds per finished tile; a
+    // gpu-scope fence costs > 1 us here) eats the ~5 us per boundary it saves: recon trunk 20 x 22 us vs 440 us chained.
+    const char *env = getenv("RVSR_CHAIN");
+    const bool on = env != nullptr && env[0] == '1';
+    const long long tiles = (long long)cdiv(W, TC_TW - 2) * cdiv(H, TC_ROWS) * N;
+    // worth it where kernel boundaries dominate: few tile rounds per layer (RVSR_CHAIN_MAX_ROUNDS, default 24; at 67 rounds --
+    // the 20-image front trunk -- the per-tile dataflow check costs more than the nine boundaries it removes)
+    const int max_rounds = getenv("RVSR_CHAIN_MAX_ROUNDS") ? atoi(getenv("RVSR_CHAIN_MAX_ROUNDS")) : 24;
+    return on && get_encode() != nullptr && L >= 2 && L <= CHAIN_MAX_LAYERS && tiles >= 2LL * sm_count() &&
+           tiles <= (long long)max_rounds * sm_count();
+}
+int launch_conv_chain(const ChainLayerDesc *layers, int L, int N, int H, int W, void *scratch, std::vector<char> &staging, cudaStream_t s) {
+    RVSR_CHECK_ARG(conv_chain_supported(L, N, H, W) && scratch != nullptr, "conv chain: unsupported configuration");
+    EncodeTiledFn enc = get_encode();
+    staging.assign((size_t)L * sizeof(TcChainLayer) + 128, 0);
+    TcChainLayer *hl = reinterpret_cast<TcChainLayer *>((reinterpret_cast<uintptr_t>(staging.data()) + 127) / 128 * 128);
+    for (int l = 0; l < L; ++l) {
+        const ChainLayerDesc &d = layers[l];
+        RVSR_CHECK_ARG(d.src && d.w_tc2 && d.out, "conv chain: null pointer in layer %d", l);
+        const cuuint64_t dims[3] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)N * 8};
+        const cuuint64_t strides[2] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
+        const cuuint32_t box[3] = {(cuuint32_t)TC_TW * 8, (cuuint32_t)(TC_ROWS + 2), 8};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&hl[l].tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(d.src), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("conv chain: cuTensorMapEncodeTiled failed (%d)", (int)r);
+            return RVSR_E_CUDA;
+        }
+        hl[l].w = reinterpret_cast<const __half *>(d.w_tc2); hl[l].bias = d.bias;
+        hl[l].out = reinterpret_cast<__half *>(d.out); hl[l].residual = reinterpret_cast<const __half *>(d.residual);
+        hl[l].act = d.act;
+    }
+    static_assert(CHAIN_MAX_LAYERS <= 20, "TcChainParams::tmaps");
+    TcChainParams p;
+    memset(&p, 0, sizeof(p));
+    for (int l = 0; l < L; ++l) p.tmaps[l] = hl[l].tmap;
+    p.layers = reinterpret_cast<const TcChainLayer *>(scratch);
+    p.flags = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(scratch) + align_up((size_t)L * sizeof(TcChainLayer), 256));
+    p.image_stride = (long long)64 * H * W;
+    p.nlayers = L; p.N = N; p.H = H; p.W = W;
+    p.tiles_x = cdiv(W, TC_TW - 2); p.tiles_y = cdiv(H, TC_ROWS); p.num_tiles = p.tiles_x * p.tiles_y * N;
+    p.td.tpi = (uint32_t)(p.tiles_x * p.tiles_y); p.td.m_tpi = magic_div(p.td.tpi, (uint32_t)p.num_tiles);
+    p.td.tx = (uint32_t)p.tiles_x; p.td.m_tx = magic_div(p.td.tx, p.td.tpi);
+    const size_t wb = 2 * (size_t)8 * 9 * 32 * 16, stage = (size_t)8 * (TC_ROWS + 2) * TC_TW * 16;
+    const size_t fixed = wb + 128 + CHAIN_MAX_LAYERS * 64 * sizeof(float) + 512;
+    int st = (int)((TC_SMEM_LIMIT - fixed) / stage);
+    if (st > 6) st = 6;
+    RVSR_CHECK_ARG(st >= 2, "conv chain: not enough shared memory");
+    p.nstages = st;
+    static const int cdbg = getenv("RVSR_CHAIN_DEBUG") ? atoi(getenv("RVSR_CHAIN_DEBUG")) : 0;
+    p.debug = cdbg;
+    const size_t smem = fixed + (size_t)st * stage + 1024;
+    RVSR_CUDA(cudaMemcpyAsync(scratch, hl, (size_t)L * sizeof(TcChainLayer), cudaMemcpyHostToDevice, s));
+    RVSR_CUDA(cudaMemsetAsync(p.flags, 0, (size_t)L * N * p.tiles_y * sizeof(unsigned), s));
+    static bool attr_set = false;
+    if (!attr_set) {
+        RVSR_CUDA(cudaFuncSetAttribute(conv_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT + 1024));
+        attr_set = true;
+    }
+    const int npairs = (p.num_tiles + 1) / 2;
+    int clusters = sm_count() / 2;
+    if (clusters > npairs) clusters = npairs;
+    // every CTA must be resident at once (tile-level dataflow between clusters): grid <= SM count, one CTA per SM
+    launch_k(conv_chain_kernel, dim3(2 * clusters), dim3(TC_THREADS), smem, s, p);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
 }
 
 // ---------------------------------------------------------------- modulated deformable conv (gather -> UMMA)

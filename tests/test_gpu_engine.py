@@ -132,6 +132,30 @@ def test_engine_host_pipeline_matches_forward_host():
         assert torch.equal(w, o)
 
 
+def test_chain_kernel_is_bit_identical_to_per_layer_launches(monkeypatch):
+    """RVSR_CHAIN=1 runs each residual trunk as ONE persistent launch with tile-level dataflow between the layers
+    (conv_chain_kernel): same MMA order and epilogue arithmetic, so the frames must be bit-identical -- any stale halo
+    read (a broken release / acquire between clusters) shows up as a difference.  cfg2 size, B = 2, three repeats."""
+    from helpers import edvr_state_shapes
+    from synth import synth_input, synth_state_dict
+    kw = dict(nf=64, nc=3, nframes=5, groups=8, front_RBs=5, back_RBs=10, w_TSA=True)
+    net = E.EDVR(**kw).eval()
+    net.load_state_dict(synth_state_dict(edvr_state_shapes("EDVR", **kw), 7), strict=True)
+    net = net.to(DEV).half()
+    net.exec_path = "engine"
+    x = synth_input((2, 5, 3, 180, 320), 9).to(DEV).half()
+    with torch.no_grad():
+        monkeypatch.delenv("RVSR_CHAIN", raising=False)
+        ref = net(x).clone()
+        launches_ref = net._get_engine(x).last_launch_count()
+        monkeypatch.setenv("RVSR_CHAIN", "1")
+        monkeypatch.setenv("RVSR_CHAIN_MAX_ROUNDS", "1000")
+        for _ in range(3):
+            y = net(x)
+            assert torch.equal(y, ref)
+        assert net._get_engine(x).last_launch_count() == launches_ref - 28   # 10 + 20 convolutions became 2 launches
+
+
 def test_cfg2_full_size_fp16_properties():
     """BASELINE cfg2 size (5x3x180x320 -> 720x1280, nf=64, TSA): too slow for the CPU oracle,
     so check size-independent properties: finite, deterministic, zero-initialised offset
