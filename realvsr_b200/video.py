@@ -6,6 +6,8 @@
   sr_sequence        test_RealVSR_wi_GT.py:114-119 (the per-frame loop), re-designed: the per-frame
                      feature pyramid is extracted ONCE per frame into a cache and windows are batched,
                      instead of recomputing all N pyramids for every output frame.
+  tiled_forward      (no reference counterpart: the reference's test scripts run whole frames) spatial tiling
+                     with a halo for frames whose activations would not fit, e.g. BASELINE cfg4's 540x960 -> 4K.
 """
 import torch
 
@@ -73,3 +75,32 @@ def sr_sequence(model, frames, padding='replicate', batch=4, cache=True):
         for t0 in range(0, T, batch):
             outs.append(eng.forward_cached(buf, T, windows[t0:t0 + batch], frames))
     return torch.cat(outs, 0)
+
+
+def tiled_forward(model, x, tile=(180, 320), halo=16, scale=None):
+    """model(x) computed on overlapping spatial tiles.  x: [B, N, C, H, W] CUDA tensor; tile = LQ tile size (h, w),
+    halo = LQ pixels of context on every side (cropped from the result).  Tile origins, sizes and halos are kept
+    multiples of 4 (the pyramid halves the resolution twice).  The network's receptive field is larger than any
+    practical halo, so pixels near tile seams differ slightly from a whole-frame forward (they are exact when one
+    tile covers the frame); with halo = 16 the seam error is of the order of the fp16 storage error.
+    Returns [B, C, s*H, s*W] on x's device."""
+    B, N, C, H, W = x.shape
+    th, tw = (min(tile[0], H) // 4 * 4, min(tile[1], W) // 4 * 4)
+    halo = max(0, int(halo)) // 4 * 4
+    if H % 4 or W % 4 or th <= 0 or tw <= 0:
+        raise RuntimeError("tiled_forward: H, W and the tile must be multiples of 4 (got %dx%d, tile %s)" % (H, W, tile))
+    out = None
+    with torch.no_grad():
+        for y0 in range(0, H, th):
+            for x0 in range(0, W, tw):
+                y1, x1 = min(y0 + th, H), min(x0 + tw, W)
+                ya, xa = max(y0 - halo, 0), max(x0 - halo, 0)
+                yb, xb = min(y1 + halo, H), min(x1 + halo, W)
+                yt = model(x[..., ya:yb, xa:xb].contiguous())
+                if isinstance(yt, (list, tuple)):
+                    yt = yt[0]
+                s = scale or yt.shape[-1] // (xb - xa)
+                if out is None:
+                    out = torch.empty(B, yt.shape[1], s * H, s * W, dtype=yt.dtype, device=yt.device)
+                out[..., s * y0:s * y1, s * x0:s * x1] = yt[..., s * (y0 - ya):s * (y1 - ya), s * (x0 - xa):s * (x1 - xa)]
+    return out

@@ -55,3 +55,32 @@ def test_sr_sequence_cache_is_bit_identical_to_plain_forward(name, half):
     with torch.no_grad():
         y = net(frames[idx].unsqueeze(0))
     assert torch.equal(V.sr_sequence(net, frames, batch=3)[4:5], y)
+
+
+@pytest.mark.gpu
+def test_tiled_forward_matches_whole_frame():
+    """One tile covering the frame is exact; 2 x 2 tiles with a 16-pixel halo differ from the whole-frame forward only by
+    the truncated receptive field at the seams (bounded), and every pixel farther than the halo from a seam... is still
+    only approximately equal (the pyramid's receptive field exceeds the halo), so the bound is global."""
+    import torch
+    from helpers import edvr_state_shapes, rel_err
+    from realvsr_b200 import video
+    from realvsr_b200.archs import EDVR_arch as E
+    from synth import synth_input, synth_state_dict
+    kw = dict(nf=64, nc=3, nframes=3, groups=8, front_RBs=2, back_RBs=2, w_TSA=True)
+    net = E.EDVR(**kw).eval()
+    net.load_state_dict(synth_state_dict(edvr_state_shapes("EDVR", **kw), 17), strict=True)
+    net = net.to("cuda:0")
+    net.exec_path = "engine"
+    x = synth_input((1, 3, 3, 96, 128), 18).to("cuda:0")
+    with torch.no_grad():
+        full = net(x)
+    assert torch.equal(video.tiled_forward(net, x, tile=(96, 128), halo=16), full)
+    tiled = video.tiled_forward(net, x, tile=(48, 64), halo=16)
+    assert tiled.shape == full.shape
+    base = torch.nn.functional.interpolate(x[:, 1], scale_factor=4, mode="bilinear", align_corners=False)
+    assert rel_err((tiled - base).cpu(), (full - base).cpu()) < 0.2       # seams: truncated context
+    inner = (slice(None), slice(None), slice(4 * 8, 4 * 40), slice(4 * 8, 4 * 56))   # interior of the first tile
+    assert rel_err((tiled - base)[inner].cpu(), (full - base)[inner].cpu()) < 5e-2
+    with pytest.raises(RuntimeError):
+        video.tiled_forward(net, x[..., :94, :], tile=(48, 64))
