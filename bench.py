@@ -29,6 +29,7 @@ CFG = dict(nf=64, nc=3, nframes=5, groups=8, front_RBs=5, back_RBs=10, w_TSA=Tru
 H, W = 180, 320
 GFLOP_PER_WINDOW = 976.70  # forward-hook count on the reference modules
 METRIC = "SR frames/sec (5-frame window, 180x320->720x1280)"
+WORKLOAD = "cfg2: 5x3x180x320 LQ window, EDVR nf=64 5 frames groups=8 PCD+TSA+5/10 RB -> 3x720x1280"
 
 
 def peaks():
@@ -133,15 +134,40 @@ def run_reference(args):
     line = dict(metric=METRIC, value=cb["value"], unit="frames/s", n_gpus=args.gpus, steps=steps, warmup=warm,
                 ms_per_step=t * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic", impl="reference",
-                config=dict(workload="cfg2: 5x3x180x320 LQ window, EDVR nf=64 5 frames PCD+TSA+10RB -> 3x720x1280",
+                config=dict(workload=WORKLOAD,
                             note="reference has no CPU DCN (deform_conv.py:109-110 raises); this arm is the oracle "
                                  "port on host cores, bounded to a quarter-size window per step"),
                 cpu_baseline=cb, e2e=dict(value=cb["value"], unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line))
+    _emit(line)
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """stdout must carry exactly ONE JSON line, but native libraries write to fd 1 as well (NCCL prints its version
+    banner there whatever NCCL_DEBUG says on some builds): keep a private copy of fd 1 for the result and point fd 1
+    at stderr for everything else."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -277,7 +303,7 @@ def main():
         line = dict(metric=METRIC, value=value, unit="frames/s", n_gpus=world, steps=K, warmup=args.warmup,
                     ms_per_step=ms_max / K, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="f16" if args.precision == "fp16" else "f32", data="synthetic",
-                    config=dict(workload="cfg2: 5x3x180x320 LQ window, EDVR nf=64 5 frames groups=8 PCD+TSA+5/10 RB -> 3x720x1280",
+                    config=dict(workload=WORKLOAD,
                                 windows_per_gpu_per_step=B, accumulate="f32",
                                 l2="8 rotating input clips; per-step activation working set >> 126 MB L2",
                                 gflop_per_window=GFLOP_PER_WINDOW,
@@ -292,7 +318,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = cpu_sample(steps=2, warmup=1)
             line["cpu_baseline"] = cb
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
