@@ -204,8 +204,10 @@ struct ConvOp {
     const float *bias;     // [Cout] fp32 or null
     void *out;
     long long out_image_stride;
-    const void *residual;  // same layout as out (OUT_C8 only), added after the activation
+    const void *residual;  // same layout as out (OUT_C8 only), added after the activation (res_pre: before bias + activation)
     long long res_image_stride;
+    int res_pre;           // 1: out = act(conv + residual + bias) -- the other half of a split torch.cat convolution
+    int res_div;           // image n reads residual image n / res_div (0 = 1): one residual per window of res_div frames
     int N, H, W;           // images, input height/width
     int Cout, ks, stride;  // pad = ks / 2
     int act, out_mode, sig_from;

@@ -207,6 +207,34 @@ int Engine::finalize(cudaStream_t s) {
             }
         }
     }
+    // Split packs for the convolutions over torch.cat([neighbour, reference]) (PCD *_offset_conv1, EDVR_arch.py:99,:109,
+    // :118,:127): conv(cat[a, b]) = conv_a(a) + conv_b(b), and b -- the reference (centre) frame's features -- is the same
+    // for all N frames of a window.  The engine computes conv_b once per window and adds it to conv_a's accumulator
+    // before bias + activation (ConvOp::res_pre), instead of recomputing it N times inside a 128-channel convolution.
+    if (cfg_.precision == RVSR_F16 && cfg_.nf == 64) {
+        for (const char *n : {"pcd_align.L3_offset_conv1", "pcd_align.L2_offset_conv1", "pcd_align.L1_offset_conv1", "pcd_align.cas_offset_conv1"}) {
+            const std::string base = n;
+            const RawWeight &w = raw_[base + ".weight"];
+            if (w.shape.size() != 4 || w.shape[0] != 64 || w.shape[1] != 128 || w.shape[2] != 3) continue;
+            for (int h = 0; h < 2; ++h) {
+                PackedConv &pc = packed_[base + (h == 0 ? "#a" : "#b")];
+                pc.Cout = 64; pc.Cin = 64; pc.ks = 3;
+                pc.bias = h == 0 ? raw_[base + ".bias"].dev : nullptr;
+                if (pc.w_simt == nullptr) {  // fp32 OIHW half [64][64][3][3], the source of the two tcgen05 packs (not a simt pack)
+                    RVSR_CUDA(cudaMalloc(&pc.w_simt, (size_t)64 * 64 * 9 * sizeof(float)));
+                    owned_.push_back(pc.w_simt);
+                    RVSR_CUDA(cudaMalloc(&pc.w_tc, tc_conv_weight_bytes(64, 64, 3, 0)));
+                    owned_.push_back(pc.w_tc);
+                    RVSR_CUDA(cudaMalloc(&pc.w_tc2, tc2_weight_bytes(64, 64, 3, 0)));
+                    owned_.push_back(pc.w_tc2);
+                }
+                RVSR_CUDA(cudaMemcpy2DAsync(pc.w_simt, (size_t)64 * 9 * sizeof(float), w.dev + (size_t)h * 64 * 9, (size_t)128 * 9 * sizeof(float),
+                                            (size_t)64 * 9 * sizeof(float), 64, cudaMemcpyDeviceToDevice, s));
+                RVSR_TRY(pack_weight_tc(pc.w_simt, pc.w_tc, 64, 64, 3, 0, s));
+                RVSR_TRY(pack_weight_tc2(pc.w_simt, pc.w_tc2, 64, 64, 3, 0, s));
+            }
+        }
+    }
     finalized_ = true;
     return RVSR_OK;
 }
@@ -289,7 +317,8 @@ template <typename T> struct Plan {
 
     // generic convolution with fused epilogue; out allocated here
     Act conv(const std::string &name, std::initializer_list<Src> srcs, int N, int H, int W, int act,
-             int stride = 1, int out_mode = OUT_C8, const Act *residual = nullptr, int sig_from = 1 << 30) {
+             int stride = 1, int out_mode = OUT_C8, const Act *residual = nullptr, int sig_from = 1 << 30,
+             int res_pre = 0, int res_div = 1, bool tc_only = false) {
         const PackedConv *pc = get(name);
         if (pc == nullptr) return Act();
         const int Ho = stride == 1 ? H : (H - 1) / 2 + 1, Wo = stride == 1 ? W : (W - 1) / 2 + 1;
@@ -320,6 +349,7 @@ template <typename T> struct Plan {
                                                          : o.image_elems();
         op.dg = out_mode == OUT_OM24 ? pc->Cout / 27 : 0;
         if (residual != nullptr) { op.residual = residual->p; op.res_image_stride = residual->image_elems(); }
+        op.res_pre = res_pre; op.res_div = res_div;
         op.N = N; op.H = H; op.W = W; op.Cout = pc->Cout; op.ks = pc->ks; op.stride = stride;
         op.act = act; op.out_mode = out_mode; op.sig_from = sig_from;
         const double px = (double)N * Ho * Wo;
@@ -329,6 +359,11 @@ template <typename T> struct Plan {
                                                          : px * pc->Cout * sizeof(T);
         const double bytes = (double)N * H * W * cin * sizeof(T) + obytes + (residual ? obytes : 0);
         const bool tc = use_tc && tc_conv_supported(op);
+        if (tc_only && !tc) {
+            set_error("engine: %s needs the tcgen05 conv kernel", name.c_str());
+            rc = RVSR_E_STATE;
+            return o;
+        }
         if (out_mode == OUT_OM24 && !tc) {
             set_error("engine: %s: OUT_OM24 needs the tcgen05 conv kernel", name.c_str());
             rc = RVSR_E_STATE;
@@ -398,6 +433,16 @@ template <typename T> struct Plan {
         if (!dry && rc == RVSR_OK)
             launch("glue:pool_maxavg:", 0, (double)a.elems() * sizeof(T) * 1.5, [&] {
                 return launch_pool_maxavg<T>((const T *)a.p, (T *)mx.p, (T *)av.p, a.N, a.C, a.H, a.W, s); });
+    }
+    // conv(cat([a, ref])) with `ref` constant over the `frames` images of a window (see Engine::finalize): split packs
+    // when they exist (fp16, nf = 64), otherwise the two-source convolution.  refB: the reference features of the B windows.
+    Act conv_cat_ref(const std::string &name, const Src &a, const Src &ref_all, const Src &refB, int NB_, int B_, int frames, int H, int W, int act) {
+        static const bool split_on = !(getenv("RVSR_SPLIT_CAT") != nullptr && getenv("RVSR_SPLIT_CAT")[0] == '0');
+        if (split_on && use_tc && sizeof(T) == 2 && packed.count(name + "#a") && packed.count(name + "#b") && NB_ == B_ * frames) {
+            Act r = conv(name + "#b", {refB}, B_, H, W, RVSR_ACT_NONE, 1, OUT_C8, nullptr, 1 << 30, 0, 1, true);
+            return conv(name + "#a", {a}, NB_, H, W, act, 1, OUT_C8, &r, 1 << 30, 1, frames, true);
+        }
+        return conv(name, {a, ref_all}, NB_, H, W, act);
     }
     Act resblocks(const std::string &prefix, int count, Act cur) {
         // fp16 / 64 channels / enough tiles: the whole run (2 * count convolutions) is ONE persistent launch with
@@ -528,14 +573,15 @@ int Engine::run(Arena &ar, bool dry, const void *x, int x_dtype, void *out, int 
     }
     auto nbr = [&](const Act &a) { return cached ? PT::src_mapped(a, map_nbr) : PT::src_of(a); };
     auto ref = [&](const Act &a) { return cached ? PT::src_mapped(a, map_ref) : PT::src_fixed(a, N, ctr); };
+    auto refB = [&](const Act &a) { return cached ? PT::src_mapped(a, map_ctr) : PT::src_slice(a, N, ctr); };  // one per window
 
     // ---- PCD alignment of all N frames at once (EDVR_arch.py:98-132, :297-303)
     const std::string p = "pcd_align.";
-    Act o3 = P.conv(p + "L3_offset_conv1", {nbr(L3), ref(L3)}, NB, L3.H, L3.W, LR);
+    Act o3 = P.conv_cat_ref(p + "L3_offset_conv1", nbr(L3), ref(L3), refB(L3), NB, B, N, L3.H, L3.W, LR);
     o3 = P.conv(p + "L3_offset_conv2", {PT::src_of(o3)}, NB, L3.H, L3.W, LR);
     Act f3 = P.dcn_pack(p + "L3_dcnpack", L3, o3, dg, LR, map_nbr);
 
-    Act o2 = P.conv(p + "L2_offset_conv1", {nbr(L2), ref(L2)}, NB, L2.H, L2.W, LR);
+    Act o2 = P.conv_cat_ref(p + "L2_offset_conv1", nbr(L2), ref(L2), refB(L2), NB, B, N, L2.H, L2.W, LR);
     Act o3u = P.up2(o3, 2.f);
     o2 = P.conv(p + "L2_offset_conv2", {PT::src_of(o2), PT::src_of(o3u)}, NB, L2.H, L2.W, LR);
     o2 = P.conv(p + "L2_offset_conv3", {PT::src_of(o2)}, NB, L2.H, L2.W, LR);
@@ -543,7 +589,7 @@ int Engine::run(Arena &ar, bool dry, const void *x, int x_dtype, void *out, int 
     Act f3u = P.up2(f3, 1.f);
     f2 = P.conv(p + "L2_fea_conv", {PT::src_of(f2), PT::src_of(f3u)}, NB, L2.H, L2.W, LR);
 
-    Act o1 = P.conv(p + "L1_offset_conv1", {nbr(L1), ref(L1)}, NB, H, W, LR);
+    Act o1 = P.conv_cat_ref(p + "L1_offset_conv1", nbr(L1), ref(L1), refB(L1), NB, B, N, H, W, LR);
     Act o2u = P.up2(o2, 2.f);
     o1 = P.conv(p + "L1_offset_conv2", {PT::src_of(o1), PT::src_of(o2u)}, NB, H, W, LR);
     o1 = P.conv(p + "L1_offset_conv3", {PT::src_of(o1)}, NB, H, W, LR);
@@ -551,7 +597,7 @@ int Engine::run(Arena &ar, bool dry, const void *x, int x_dtype, void *out, int 
     Act f2u = P.up2(f2, 1.f);
     f1 = P.conv(p + "L1_fea_conv", {PT::src_of(f1), PT::src_of(f2u)}, NB, H, W, NONE);  // no lrelu (:125)
 
-    Act oc = P.conv(p + "cas_offset_conv1", {PT::src_of(f1), ref(L1)}, NB, H, W, LR);
+    Act oc = P.conv_cat_ref(p + "cas_offset_conv1", PT::src_of(f1), ref(L1), refB(L1), NB, B, N, H, W, LR);
     oc = P.conv(p + "cas_offset_conv2", {PT::src_of(oc)}, NB, H, W, LR);
     Act aligned = P.dcn_pack(p + "cas_dcnpack", f1, oc, dg, LR);
 

@@ -214,6 +214,7 @@ struct EpiArgs {
     long long res_image_stride;
     int H, W, Cout, act, out_mode, sig_from, subsample, dg;
     const FinalAdd *fin;  // OUT_FINAL
+    int res_pre, res_div;
 };
 
 // Epilogue of one pixel (= TMEM lane) of one tile.  With NH = 2 two warps share a TMEM lane
@@ -254,7 +255,7 @@ template <int NT, int NH> struct EpiTile {
         has_res = true;
         if constexpr (RES) {
             const int Co8 = (e.Cout + 7) / 8;
-            const uint4 *r = reinterpret_cast<const uint4 *>(e.residual + (long long)n * e.res_image_stride) + (long long)y * e.W + x;
+            const uint4 *r = reinterpret_cast<const uint4 *>(e.residual + (long long)(n / e.res_div) * e.res_image_stride) + (long long)y * e.W + x;
             const long long plane = (long long)e.H * e.W;
 #pragma unroll
             for (int j = 0; j < HALFC / 8; ++j) {
@@ -290,16 +291,20 @@ template <int NT, int NH> struct EpiTile {
             const float4 b0 = *reinterpret_cast<const float4 *>(e.bias_s + c0);
             const float4 b1 = *reinterpret_cast<const float4 *>(e.bias_s + c0 + 4);
             const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            float v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = act_t<ACT>(__uint_as_float(acc[j >> 1][(j & 1) * 8 + i]) + bb[i], e.act);
+            float v[8], rr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (RES && has_res) {
                 const __half2 *h = reinterpret_cast<const __half2 *>(&res[RES ? ch * (CW / 8) + j : 0]);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float2 f = __half22float2(h[i]);
-                    v[2 * i] += f.x; v[2 * i + 1] += f.y;
+                    rr[2 * i] = f.x; rr[2 * i + 1] = f.y;
                 }
+            }
+            const bool pre = e.res_pre != 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float a = __uint_as_float(acc[j >> 1][(j & 1) * 8 + i]) + bb[i];
+                v[i] = pre ? act_t<ACT>(a + rr[i], e.act) : act_t<ACT>(a, e.act) + rr[i];
             }
             uint4 pk;
             __half2 *h = reinterpret_cast<__half2 *>(&pk);
@@ -494,14 +499,14 @@ template <int ACT, bool RES_CG = false, typename Release>
 __device__ __forceinline__ void epi_c8_fast(const float *bias_s, __half *out, long long out_image_stride, const __half *residual,
                                             long long res_image_stride, int H, int W, int Co8, uint32_t taddr, int half,
                                             int qbase, int n, int y, int x, bool valid, uint32_t full_bar, uint32_t full_par,
-                                            Release &&release) {
+                                            Release &&release, int n_res = -1, bool res_pre = false) {
     constexpr int NBLK = 4;  // this warp's 32 columns = 4 channel blocks
     const long long plane = (long long)H * W, pix = (long long)y * W + x;
     const int q0 = qbase + half * NBLK;  // first output channel block of this warp (qbase: blocks of earlier N-passes)
     uint4 res[NBLK];
     const bool has_res = residual != nullptr && valid;
     if (has_res) {
-        const uint4 *r = reinterpret_cast<const uint4 *>(residual + (long long)n * res_image_stride) + q0 * plane + pix;
+        const uint4 *r = reinterpret_cast<const uint4 *>(residual + (long long)(n_res < 0 ? n : n_res) * res_image_stride) + q0 * plane + pix;
 #pragma unroll
         for (int j = 0; j < NBLK; ++j)  // RES_CG: the residual was written earlier in the SAME kernel (chain): L2-coherent load
             res[j] = q0 + j < Co8 ? (RES_CG ? __ldcg(r + j * plane) : __ldg(r + j * plane)) : make_uint4(0, 0, 0, 0);
@@ -523,9 +528,11 @@ __device__ __forceinline__ void epi_c8_fast(const float *bias_s, __half *out, lo
         const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
         const uint32_t *a = (j < 2 ? a0 : a1) + (j & 1) * 8;
         float2 v[4];
+        const bool pre = has_res && res_pre;  // split-cat convolution: the other half's partial sums join before bias + activation
 #pragma unroll
         for (int i = 0; i < 4; ++i) {  // packed fp32 pairs (FADD2 / FMUL2): same IEEE results, half the instructions
             v[i] = add2(make_float2(__uint_as_float(a[2 * i]), __uint_as_float(a[2 * i + 1])), bb[i]);
+            if (pre) v[i] = add2(v[i], __half22float2(reinterpret_cast<const __half2 *>(&res[j])[i]));
             if (ACT == RVSR_ACT_LRELU) {
                 const float2 t = mul2(v[i], make_float2(0.1f, 0.1f));
                 v[i] = make_float2(fmaxf(v[i].x, t.x), fmaxf(v[i].y, t.y));
@@ -533,7 +540,7 @@ __device__ __forceinline__ void epi_c8_fast(const float *bias_s, __half *out, lo
                 v[i] = make_float2(fmaxf(v[i].x, 0.f), fmaxf(v[i].y, 0.f));
             }
         }
-        if (has_res) {
+        if (has_res && !pre) {
             const __half2 *h = reinterpret_cast<const __half2 *>(&res[j]);
 #pragma unroll
             for (int i = 0; i < 4; ++i) v[i] = add2(v[i], __half22float2(h[i]));
@@ -560,6 +567,7 @@ struct alignas(64) TcConvParams {
     long long out_image_stride;
     const __half *residual;
     long long res_image_stride;
+    int res_pre, res_div;
     int N, H, W, Cout, act, out_mode, sig_from, subsample, dg;
     int tiles_x, tiles_y, num_tiles;
     TileDiv td;
@@ -760,7 +768,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int eg = (warp - TC_EPI_WARP0) / WPG;                  // this warp's group: tiles t == eg (mod groups)
         const int half = ((warp - TC_EPI_WARP0) % WPG) >> 2;         // WPG / 4 warps per lane quarter split the columns
         EpiArgs e{bias_s, p.out, p.out_image_stride, p.residual, p.res_image_stride, p.H, p.W, p.Cout, p.act,
-                  p.out_mode, p.sig_from, p.subsample, p.dg, &p.fin};
+                  p.out_mode, p.sig_from, p.subsample, p.dg, &p.fin, p.res_pre, p.res_div};
         EpiTile<NT, WPG / 4> ep;
         uint32_t t = (uint32_t)eg;
         for (int tile = blockIdx.x + eg * gridDim.x; tile < p.num_tiles; tile += EG * gridDim.x, t += EG) {
@@ -1025,7 +1033,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
         const int eg = (warp - TC_EPI_WARP0) / WPG;
         const int half = ((warp - TC_EPI_WARP0) % WPG) >> 2;
         EpiArgs e{bias_s, p.out, p.out_image_stride, p.residual, p.res_image_stride, p.H, p.W, p.Cout, p.act,
-                  p.out_mode, p.sig_from, p.subsample, p.dg, &p.fin};
+                  p.out_mode, p.sig_from, p.subsample, p.dg, &p.fin, p.res_pre, p.res_div};
         EpiTile<NT, WPG / 4> ep;
         uint32_t t = (uint32_t)eg;
         if (NT == 64 && WPG == 8 && p.out_mode == OUT_C8 && !p.subsample && p.debug == 0) {
@@ -1048,7 +1056,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
                                          tc_fence_before();
                                          __syncwarp();
                                          if (lane == 0) mbar_arrive_cluster(tempty0);
-                                     });
+                                     }, n / p.res_div, p.res_pre != 0);
                     if (pr == cid + eg * nclusters && eg == 0 && warp == TC_EPI_WARP0 && lane == 0) STAMP(4);
                     buf += EG;
                     if (buf >= (uint32_t)NB) { buf -= NB; par ^= 1u; }
@@ -1615,6 +1623,7 @@ int launch_conv_tc(const ConvOp &op, cudaStream_t s) {
     p.w = reinterpret_cast<const __half *>(op.w_tc); p.bias = op.bias;
     p.out = op.out; p.out_image_stride = op.out_image_stride;
     p.residual = reinterpret_cast<const __half *>(op.residual); p.res_image_stride = op.res_image_stride;
+    p.res_pre = op.res_pre; p.res_div = op.res_div > 0 ? op.res_div : 1;
     p.N = op.N; p.H = op.H; p.W = op.W; p.Cout = op.Cout; p.act = op.act; p.out_mode = op.out_mode;
     p.sig_from = op.sig_from; p.subsample = op.stride == 2 ? 1 : 0; p.dg = op.dg; p.fin = op.fin;
     const int valid = TC_TW - (op.ks - 1);
@@ -1982,7 +1991,7 @@ __global__ void __launch_bounds__(DCN_THREADS, 1) dcn_tc_kernel(const __grid_con
     } else {
         pdl_wait();
         const int lq = warp & 3;
-        EpiArgs e{bias_s, p.out, p.out_image_stride, nullptr, 0, p.H, p.W, NT, p.act, OUT_C8, 0, 0, 0, nullptr};
+        EpiArgs e{bias_s, p.out, p.out_image_stride, nullptr, 0, p.H, p.W, NT, p.act, OUT_C8, 0, 0, 0, nullptr, 0, 1};
         EpiTile<NT, 1> ep;
         ep.has_res = false;
         uint32_t t = 0;
