@@ -71,6 +71,10 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per (function, device): remember which pairs were set (a process may
+// drive several devices, e.g. the reference's nn.DataParallel wrapper, VideoSR_AllPair_model_YCbCr_Split.py:33-36)
+int ensure_max_dynamic_smem(const void *func, int bytes);  // engine.cu
+
 #define RVSR_TRY(expr)            \
     do {                          \
         int _rc = (expr);         \

@@ -17,6 +17,10 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <mutex>
+#include <set>
+#include <utility>
+
 namespace rvsr {
 
 // ---------------------------------------------------------------- error string
@@ -28,6 +32,17 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 const char *get_error() { return g_err; }
+int ensure_max_dynamic_smem(const void *func, int bytes) {
+    static std::mutex mu;
+    static std::set<std::pair<const void *, int>> done;
+    int dev = 0;
+    RVSR_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    if (done.count({func, dev})) return RVSR_OK;
+    RVSR_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done.insert({func, dev});
+    return RVSR_OK;
+}
 static thread_local int g_pdl_scope = 0;
 PdlScope::PdlScope() { ++g_pdl_scope; }
 PdlScope::~PdlScope() { --g_pdl_scope; }
@@ -318,7 +333,7 @@ template <typename T> struct Plan {
     // generic convolution with fused epilogue; out allocated here
     Act conv(const std::string &name, std::initializer_list<Src> srcs, int N, int H, int W, int act,
              int stride = 1, int out_mode = OUT_C8, const Act *residual = nullptr, int sig_from = 1 << 30,
-             int res_pre = 0, int res_div = 1, bool tc_only = false) {
+             int res_pre = 0, int res_div = 1, bool tc_only = false, double flops_alg = -1.0) {
         const PackedConv *pc = get(name);
         if (pc == nullptr) return Act();
         const int Ho = stride == 1 ? H : (H - 1) / 2 + 1, Wo = stride == 1 ? W : (W - 1) / 2 + 1;
@@ -353,7 +368,8 @@ template <typename T> struct Plan {
         op.N = N; op.H = H; op.W = W; op.Cout = pc->Cout; op.ks = pc->ks; op.stride = stride;
         op.act = act; op.out_mode = out_mode; op.sig_from = sig_from;
         const double px = (double)N * Ho * Wo;
-        const double flops = 2.0 * cin * pc->Cout * pc->ks * pc->ks * px;
+        // algorithmic work of the REFERENCE's layer; flops_alg overrides it where the plan splits a layer
+        const double flops = flops_alg >= 0 ? flops_alg : 2.0 * cin * pc->Cout * pc->ks * pc->ks * px;
         const double obytes = out_mode == OUT_PLANAR_F32 ? px * pc->Cout * 4
                               : out_mode == OUT_OM24     ? px * (pc->Cout / 27) * 96.0
                                                          : px * pc->Cout * sizeof(T);
@@ -439,8 +455,11 @@ template <typename T> struct Plan {
     Act conv_cat_ref(const std::string &name, const Src &a, const Src &ref_all, const Src &refB, int NB_, int B_, int frames, int H, int W, int act) {
         static const bool split_on = !(getenv("RVSR_SPLIT_CAT") != nullptr && getenv("RVSR_SPLIT_CAT")[0] == '0');
         if (split_on && use_tc && sizeof(T) == 2 && packed.count(name + "#a") && packed.count(name + "#b") && NB_ == B_ * frames) {
-            Act r = conv(name + "#b", {refB}, B_, H, W, RVSR_ACT_NONE, 1, OUT_C8, nullptr, 1 << 30, 0, 1, true);
-            return conv(name + "#a", {a}, NB_, H, W, act, 1, OUT_C8, &r, 1 << 30, 1, frames, true);
+            // profile accounting: the pair together is the reference's 128 -> 64 convolution over NB_ images -- its
+            // algorithmic FLOPs are booked on the #a launch, none on #b (the roofline counts the reference's work)
+            Act r = conv(name + "#b", {refB}, B_, H, W, RVSR_ACT_NONE, 1, OUT_C8, nullptr, 1 << 30, 0, 1, true, 0.0);
+            return conv(name + "#a", {a}, NB_, H, W, act, 1, OUT_C8, &r, 1 << 30, 1, frames, true,
+                        2.0 * 128 * 64 * 9 * (double)NB_ * H * W);
         }
         return conv(name, {a, ref_all}, NB_, H, W, act);
     }

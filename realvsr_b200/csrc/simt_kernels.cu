@@ -867,8 +867,7 @@ int launch_dcn_bwd_simt(const DcnBwdOp &op, cudaStream_t s) {
     const int ROWS = K * 8;
     const size_t smem = ((size_t)(2 * ROWS + 64) * (TILE_P + 1) + (size_t)64 * (ROWS + 1)) * sizeof(float);
     if (K == 9) {
-        static bool set9 = false;
-        if (!set9) { RVSR_CUDA(cudaFuncSetAttribute(dcn_bwd_simt_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set9 = true; }
+        RVSR_TRY(ensure_max_dynamic_smem(reinterpret_cast<const void *>(&dcn_bwd_simt_kernel<9>), (int)smem));
         dcn_bwd_simt_kernel<9><<<grid, NTHREADS, smem, s>>>(op);
     } else {
         dcn_bwd_simt_kernel<1><<<grid, NTHREADS, smem, s>>>(op);

@@ -1564,11 +1564,7 @@ bool tc_conv_supported(const ConvOp &op) {
 }
 
 template <int KS, int NT> static int launch_conv_tc_t(const TcConvParams &p, const TcConvPlan &pl, int sms, cudaStream_t s) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        RVSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT + 1024));
-        attr_set = true;
-    }
+    RVSR_TRY(ensure_max_dynamic_smem(reinterpret_cast<const void *>(&conv_tc_kernel<KS, NT>), (int)TC_SMEM_LIMIT + 1024));
     int gx = sms / pl.passes;
     if (gx < 1) gx = 1;
     if (gx > p.num_tiles) gx = p.num_tiles;
@@ -1577,13 +1573,16 @@ template <int KS, int NT> static int launch_conv_tc_t(const TcConvParams &p, con
     return RVSR_OK;
 }
 
-static int sm_count() {
-    static int n = 0;
+static int sm_count() {  // of the CURRENT device (cached per device: a process may drive several)
+    static int cache[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    int n = cache[dev];
     if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (n <= 0) n = 148;
+        cache[dev] = n;
     }
     return n;
 }
@@ -1659,12 +1658,10 @@ int launch_conv_tc(const ConvOp &op, cudaStream_t s) {
         if (clusters < 1) clusters = 1;
         if (clusters > npairs) clusters = npairs;
         if (pl.NT == 64) {
-            static bool a64 = false;
-            if (!a64) { RVSR_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<3, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT + 1024)); a64 = true; }
+            RVSR_TRY(ensure_max_dynamic_smem(reinterpret_cast<const void *>(&conv_tc2_kernel<3, 64>), (int)TC_SMEM_LIMIT + 1024));
             launch_k(conv_tc2_kernel<3, 64>, dim3(2 * clusters, pl.passes), dim3(TC_THREADS), smem2, s, p);
         } else {
-            static bool a128 = false;
-            if (!a128) { RVSR_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<3, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT + 1024)); a128 = true; }
+            RVSR_TRY(ensure_max_dynamic_smem(reinterpret_cast<const void *>(&conv_tc2_kernel<3, 128>), (int)TC_SMEM_LIMIT + 1024));
             launch_k(conv_tc2_kernel<3, 128>, dim3(2 * clusters, pl.passes), dim3(TC_THREADS), smem2, s, p);
         }
         RVSR_LAUNCH_CHECK();
@@ -1744,11 +1741,7 @@ int launch_conv_chain(const ChainLayerDesc *layers, int L, int N, int H, int W, 
     const size_t smem = fixed + (size_t)st * stage + 1024;
     RVSR_CUDA(cudaMemcpyAsync(scratch, hl, (size_t)L * sizeof(TcChainLayer), cudaMemcpyHostToDevice, s));
     RVSR_CUDA(cudaMemsetAsync(p.flags, 0, (size_t)L * N * p.tiles_y * sizeof(unsigned), s));
-    static bool attr_set = false;
-    if (!attr_set) {
-        RVSR_CUDA(cudaFuncSetAttribute(conv_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT + 1024));
-        attr_set = true;
-    }
+    RVSR_TRY(ensure_max_dynamic_smem(reinterpret_cast<const void *>(&conv_chain_kernel), (int)TC_SMEM_LIMIT + 1024));
     const int npairs = (p.num_tiles + 1) / 2;
     int clusters = sm_count() / 2;
     if (clusters > npairs) clusters = npairs;
@@ -2033,12 +2026,8 @@ int launch_dcn_tc(const DcnOp &op, cudaStream_t s) {
     p.tiles_x = cdiv(op.W, TC_TW); p.tiles_y = cdiv(op.H, TC_ROWS); p.num_tiles = p.tiles_x * p.tiles_y * op.N;
     if (p.num_tiles == 0) return RVSR_OK;
     const size_t smem = 8 * 9 * 64 * 16 + DCN_STAGES * DCN_TAP_BYTES + 64 * 4 + 256 + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-        RVSR_CUDA(cudaFuncSetAttribute(dcn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RVSR_CUDA(cudaFuncSetAttribute(dcn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    RVSR_TRY(ensure_max_dynamic_smem(reinterpret_cast<const void *>(&dcn_tc_kernel<true>), (int)smem));
+    RVSR_TRY(ensure_max_dynamic_smem(reinterpret_cast<const void *>(&dcn_tc_kernel<false>), (int)smem));
     // RVSR_DCN_BLEND=fp32 keeps the bilinear blend in fp32 (one rounding per sample instead of four)
     static const bool blend32 = getenv("RVSR_DCN_BLEND") != nullptr && strcmp(getenv("RVSR_DCN_BLEND"), "fp32") == 0;
     int gx = sm_count();
@@ -2331,11 +2320,7 @@ int launch_conv_tapn(const ConvOp &op, const void *w_tapn, cudaStream_t s) {
     RVSR_CHECK_ARG(st >= 2, "tapn conv: not enough shared memory");
     p.nstages = st;
     const size_t smem = fixed + (size_t)st * stage + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-        RVSR_CUDA(cudaFuncSetAttribute(conv_tapn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT + 1024));
-        attr_set = true;
-    }
+    RVSR_TRY(ensure_max_dynamic_smem(reinterpret_cast<const void *>(&conv_tapn_kernel), (int)TC_SMEM_LIMIT + 1024));
     int gx = sm_count();
     if (gx > p.num_tiles) gx = p.num_tiles;
     launch_k(conv_tapn_kernel, dim3(gx), dim3(TAPN_THREADS), smem, s, p);

@@ -156,6 +156,22 @@ def test_chain_kernel_is_bit_identical_to_per_layer_launches(monkeypatch):
         assert net._get_engine(x).last_launch_count() == launches_ref - 28   # 10 + 20 convolutions became 2 launches
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_devices_in_one_process():
+    """The reference wraps the model in nn.DataParallel (VideoSR_AllPair_model_YCbCr_Split.py:33-36): one process, several
+    devices.  Per-device state of the library (opt-in shared-memory attribute, SM count) must follow the current device."""
+    c = load_case("edvr_nf64_crop")
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        net = getattr(E, c["cls"])(**c["kwargs"]).eval()
+        net.load_state_dict(c["sd"], strict=True)
+        net = net.to(dev).half()
+        net.exec_path = "engine"
+        with torch.no_grad():
+            outs.append(net(c["x"].to(dev).half()).cpu())
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_cfg2_full_size_fp16_properties():
     """BASELINE cfg2 size (5x3x180x320 -> 720x1280, nf=64, TSA): too slow for the CPU oracle,
     so check size-independent properties: finite, deterministic, zero-initialised offset
