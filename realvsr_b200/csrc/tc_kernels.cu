@@ -1192,6 +1192,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
         for (int i = 0; i < NB; ++i) mbar_init(TFULL(i), 1);
         for (int i = 0; i < NB; ++i) mbar_init(TEMPTY(i), 2 * WPG);
         fence_barrier_init();
+        tmem_slot[2] = 0; tmem_slot[3] = 0;  // per epilogue group: (tile, warp) parts stored so far
         load_w(0);
         if (L > 1) load_w(1);
     }
@@ -1207,56 +1208,66 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
 
     if (warp == 0) {
         if (lane == 0) {
+            // Flat loop over (layer, tile) with a one-tile look-ahead: the dataflow counter of the NEXT tile is requested
+            // (relaxed, L2) before this tile's stage wait, so its round trip never sits on the critical path.
+            // No acquire is used on purpose: ld.acquire.gpu and fence.acq_rel.gpu both cost ~1 us here, more than a whole
+            // tile.  What makes this sound on this hardware: the halo is read by the TMA unit, i.e. from L2 (the coherence
+            // point), never through an SM's L1; the writers fence (gpu scope) between their stores and the counter update,
+            // so a counter value seen in L2 implies the stores are in L2; and the TMA is issued after the counter load has
+            // returned (data dependence) and after fence.proxy.async (generic -> async proxy ordering in this thread).
+            const unsigned target = (unsigned)p.tiles_x * (unsigned)WPG;  // per tile row: every tile's 8 epilogue warps
+            struct Tile { int tx, ty, n; const unsigned *fr; unsigned want; };
+            auto tile_at = [&](int l, int kl) {
+                Tile t;
+                int tile = 2 * (cid + kl * nclusters) + (int)rank;
+                if (tile >= p.num_tiles) tile = p.num_tiles - 1;
+                tile_coords(p.td, tile, t.tx, t.ty, t.n);
+                t.fr = (l > 0 && !(p.debug & 4)) ? p.flags + ((size_t)(l - 1) * p.N + t.n) * p.tiles_y + t.ty : nullptr;
+                t.want = target * (unsigned)(1 + (t.ty > 0) + (t.ty + 1 < p.tiles_y));
+                return t;
+            };
             uint32_t k = 0;
             int next_w = 2;  // next layer whose weights are still to be requested
-            const unsigned target = (unsigned)p.tiles_x * (unsigned)WPG;  // a tile row is done when all its tiles' epilogue warps reported
-            for (int l = 0; l < L; ++l) {
-                const unsigned *fl = l > 0 ? p.flags + (size_t)(l - 1) * p.N * p.tiles_y : nullptr;
-                for (int kl = 0; kl < K; ++kl, ++k) {
-                    if (next_w < L && next_w <= l + 1 && mbar_test(LDONE(next_w & 1), (uint32_t)(((next_w - 2) >> 1) & 1))) {
-                        load_w(next_w);
-                        ++next_w;
-                    }
-                    const int pr = cid + kl * nclusters;
-                    int tile = 2 * pr + (int)rank;
-                    if (tile >= p.num_tiles) tile = p.num_tiles - 1;
-                    int tx, ty, n;
-                    tile_coords(p.td, tile, tx, ty, n);
-                    // The halo of this tile reads tile rows ty - 1 .. ty + 1 of the previous layer's output.  Every finished
-                    // tile is counted on the counters of the three rows that read it, so ONE counter covers the halo: a relaxed
-                    // load before the wait for a free stage (it normally already shows the target -- the rows were finished
-                    // a layer ago), then one acquire load (a single L2 round trip; a fence.acq_rel.gpu here costs > 1 us).
-                    const unsigned *fr = fl != nullptr ? fl + (size_t)n * p.tiles_y + ty : nullptr;
-                    if (p.debug & 4) fr = nullptr;
-                    const unsigned want = target * (unsigned)(1 + (ty > 0) + (ty + 1 < p.tiles_y));
-                    unsigned v0 = want;
-                    if (fr != nullptr) v0 = (p.debug & 1) ? ld_relaxed_gpu(fr) : ld_acquire_gpu(fr);  // before the stage wait: latency hidden
-                    const int st = (int)(k % (uint32_t)S), w = (int)(k % MMAW);
-                    mbar_wait(EMPTY(st), ((k / (uint32_t)S) & 1) ^ 1);
-                    if (fr != nullptr) {
-                        if (v0 < want) {  // rare: the previous layer has not reached these rows yet
-                            uint32_t spin = 0;
-                            do {
-                                if (++spin > (1u << 24)) __trap();  // protocol bug: fail the launch instead of hanging the GPU
-                                v0 = ld_relaxed_gpu(fr);
-                            } while (v0 < want);
-                            v0 = ld_acquire_gpu(fr);                      // acquire: the producers' stores are visible
-                        }
-                        asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes -> the TMA read below
-                    }
-                    const uint32_t full0 = mapa_rank0(FULL(w, st));
-                    if (rank == 0)
-                        mbar_expect_tx(FULL(w, st), 2 * stage_bytes);
-                    else
-                        mbar_arrive_cluster(full0);
-                    tma_load_3d_2sm(smem_u32(stage_s + (size_t)st * stage_bytes), &p.tmaps[l], full0, (tx * VALID - PAD) * 8,
-                                    ty * TC_ROWS - PAD, n * C8S);
+            int l = 0, kl = 0;
+            Tile cur = tile_at(0, 0);
+            unsigned vcur = cur.want;
+            const uint32_t total = (uint32_t)L * (uint32_t)K;
+            for (; k < total; ++k) {
+                int nl = l, nkl = kl + 1;
+                if (nkl == K) { nkl = 0; ++nl; }
+                Tile nxt = cur;
+                unsigned vnxt = 0;
+                if (nl < L) {
+                    nxt = tile_at(nl, nkl);
+                    vnxt = nxt.fr != nullptr ? ld_relaxed_gpu(nxt.fr) : nxt.want;
                 }
-                if (next_w == l + 1 && next_w < L) {  // not requested yet (short layer): now it must be
+                if (next_w < L && next_w <= l + 1 && mbar_test(LDONE(next_w & 1), (uint32_t)(((next_w - 2) >> 1) & 1))) {
+                    load_w(next_w);
+                    ++next_w;
+                }
+                const int st = (int)(k % (uint32_t)S), w = (int)(k % MMAW);
+                mbar_wait(EMPTY(st), ((k / (uint32_t)S) & 1) ^ 1);
+                if (cur.fr != nullptr) {
+                    uint32_t spin = 0;
+                    while (vcur < cur.want) {  // rare: the previous layer has not finished these rows yet
+                        if (++spin > (1u << 24)) __trap();  // protocol bug: fail the launch instead of hanging the GPU
+                        vcur = ld_relaxed_gpu(cur.fr);
+                    }
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                }
+                const uint32_t full0 = mapa_rank0(FULL(w, st));
+                if (rank == 0)
+                    mbar_expect_tx(FULL(w, st), 2 * stage_bytes);
+                else
+                    mbar_arrive_cluster(full0);
+                tma_load_3d_2sm(smem_u32(stage_s + (size_t)st * stage_bytes), &p.tmaps[l], full0, (cur.tx * VALID - PAD) * 8,
+                                cur.ty * TC_ROWS - PAD, cur.n * C8S);
+                if (kl == K - 1 && next_w == l + 1 && next_w < L) {  // end of a (short) layer and the next weights not requested yet
                     mbar_wait(LDONE(next_w & 1), (uint32_t)(((next_w - 2) >> 1) & 1));
                     load_w(next_w);
                     ++next_w;
                 }
+                cur = nxt; vcur = vnxt; l = nl; kl = nkl;
             }
         }
     } else if (warp <= MMAW) {
@@ -1275,27 +1286,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
             const uint32_t a_base = (uint32_t)adesc0, b_base = (uint32_t)bdesc0;
             constexpr uint32_t stage_units = stage_bytes >> 4, b_tap_step = C8S * NH2;
             uint32_t k = 0, par = 0;
-            const bool ph = (p.debug & 16) && blockIdx.x == 0 && mw == 0 && lane == 0;
-            long long pa[5] = {0, 0, 0, 0, 0}, tp = 0;
-            uint32_t pn = 0;
-#define CPH(i) do { if (ph) { const long long tn = clock64(); pa[i] += tn - tp; tp = tn; } } while (0)
             for (int l = 0; l < L; ++l) {
                 const int b = l & 1;
-                if (ph) tp = clock64();
                 mbar_wait(WFULL(b), (uint32_t)((l >> 1) & 1));
                 mbar_wait(WPEER(b), (uint32_t)((l >> 1) & 1));
-                CPH(4);
                 const uint32_t b_lo0 = b_base + (uint32_t)b * (w_bytes >> 4);
                 for (int kl = 0; kl < K; ++kl, ++k) {
                     if (k % MMAW != mw) continue;
                     const uint32_t buf = k % NB, st = k % (uint32_t)S;
-                    if (ph) { tp = clock64(); ++pn; }
                     mbar_wait(TEMPTY(buf), ((k / NB) & 1) ^ 1);
-                    CPH(0);
                     mbar_wait(FULL(mw, st), (par >> st) & 1);
                     par ^= 1u << st;
                     tc_fence_after();
-                    CPH(1);
                     const uint32_t d = tmem_base + buf * ACC;
                     const uint32_t a_lo0 = a_base + st * stage_units;
                     if (elect_one()) {
@@ -1312,15 +1314,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
                         umma_commit_2sm(TFULL(buf));
                     }
                     __syncwarp();
-                    CPH(2);
                 }
                 if (elect_one()) umma_commit_2sm(LDONE(b));  // every MMA this issuer made for layer l has completed
                 __syncwarp();
             }
-            if (ph && pn > 0)
-                printf("[chain issuer0] %u own tiles, %d layers | per own tile: wait-tempty %lld wait-full %lld issue %lld | per layer: wait-weights %lld\n", pn, L,
-                       pa[0] / pn, pa[1] / pn, pa[2] / pn, pa[4] / L);
-#undef CPH
         }
     } else if (warp >= TC_EPI_WARP0) {
         for (int i = threadIdx.x - 32 * TC_EPI_WARP0; i < L * NT; i += 32 * TC_EPI_WARPS) {
@@ -1332,9 +1329,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
         const int eg = (warp - TC_EPI_WARP0) / WPG;
         const int half = ((warp - TC_EPI_WARP0) % WPG) >> 2;
         uint32_t k = 0;
-        bool pend_valid = false;      // previous tile of this group: stored, not yet published
-        unsigned *pend_base = nullptr;
-        int pend_row = 0;
+        unsigned *stored = reinterpret_cast<unsigned *>(tmem_slot + 2) + eg;  // tiles x warps of this group stored so far
         for (int l = 0; l < L; ++l) {
             const TcChainLayer *ly = p.layers + l;
             __half *out = ly->out;
@@ -1353,26 +1348,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
                 const uint32_t buf = k % NB, par = (k / NB) & 1;
                 const uint32_t tempty0 = mapa_rank0(TEMPTY(buf));
                 const uint32_t taddr = tmem_base + buf * ACC + ((uint32_t)(lq * 32) << 16);
-                // `release` runs after this tile's accumulator wait + TMEM drain and before its stores: the point where the
-                // PREVIOUS tile of this warp is published ("my part is in memory").  A fence right behind the stores would
-                // wait a full L2 round trip per tile; one accumulator wait later they have long completed.
                 auto release = [&] {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(tempty0);
-                    if (pend_valid) {
-                        // all 8 warps of the group have stored their part of the previous tile (they are all past it):
-                        // group barrier (CTA-scope ordering), then ONE warp fences at GPU scope and publishes for all
-                        // (the release is cumulative) -- a fence per warp and tile costs > 1 us each
-                        asm volatile("bar.sync %0, %1;" ::"r"(2 + eg), "n"(32 * WPG) : "memory");
-                        if ((warp - TC_EPI_WARP0) % WPG == 0) {
-                            if (!(p.debug & 2)) __threadfence();
-                            if (lane < 3) {
-                                const int r = pend_row + lane - 1;
-                                if (r >= 0 && r < p.tiles_y) red_relaxed_gpu_add(pend_base + r, (unsigned)WPG);
-                            }
-                        }
-                    }
                 };
                 if (act == RVSR_ACT_RELU)
                     epi_c8_fast<RVSR_ACT_RELU, true>(bias_all + l * NT, out, p.image_stride, res, p.image_stride, p.H, p.W, 8, taddr, half, 0, n,
@@ -1383,18 +1362,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
                 else
                     epi_c8_fast<RVSR_ACT_NONE, true>(bias_all + l * NT, out, p.image_stride, res, p.image_stride, p.H, p.W, 8, taddr, half, 0, n,
                                                      y, x, valid, TFULL(buf), par, release);
-                pend_valid = real; pend_base = fl + (size_t)n * p.tiles_y; pend_row = ty;
-            }
-            if (pend_valid) {  // end of the layer: the next layer's producers need this one now
-                asm volatile("bar.sync %0, %1;" ::"r"(2 + eg), "n"(32 * WPG) : "memory");
-                if ((warp - TC_EPI_WARP0) % WPG == 0) {
-                    __threadfence();
-                    if (lane < 3) {
-                        const int r = pend_row + lane - 1;
-                        if (r >= 0 && r < p.tiles_y) red_relaxed_gpu_add(pend_base + r, (unsigned)WPG);
+                // ---- publish.  Every warp reports "my part of the tile is stored" on a shared-memory counter of its group
+                // (CTA scope, cheap); ONE warp per tile -- they take turns -- waits until all 8 have reported, fences at GPU
+                // scope (cumulative: it covers the other warps' stores, ordered before it by the CTA-scope handshake) and
+                // bumps the global counters of the three tile rows that read this tile.  A gpu-scope fence costs ~1 us: done
+                // by every warp for every tile it made the epilogue the bottleneck, now each warp pays it every 8th tile.
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) atomicAdd_block(stored, 1u);
+                const uint32_t j = k / EG;  // group-local tile sequence number
+                if ((int)(j % WPG) == (warp - TC_EPI_WARP0) % WPG) {
+                    const unsigned need = (unsigned)WPG * (j + 1);
+                    uint32_t spin = 0;
+                    while (*reinterpret_cast<volatile unsigned *>(stored) < need)
+                        if (++spin > (1u << 26)) __trap();
+                    __threadfence_block();
+                    if (real) {
+                        if (!(p.debug & 2)) __threadfence();
+                        if (lane < 3) {
+                            const int r = ty + lane - 1;
+                            if (r >= 0 && r < p.tiles_y) red_relaxed_gpu_add(fl + (size_t)n * p.tiles_y + r, (unsigned)WPG);
+                        }
                     }
                 }
-                pend_valid = false;
             }
         }
     }
@@ -1683,10 +1673,9 @@ size_t conv_chain_scratch_bytes(int L, int N, int H) {
     return align_up((size_t)L * sizeof(TcChainLayer), 256) + align_up((size_t)L * N * cdiv(H, TC_ROWS) * sizeof(unsigned), 256);
 }
 bool conv_chain_supported(int L, int N, int H, int W) {
-    // OPT-IN (RVSR_CHAIN=1, read at every call so tests can toggle it).  Measured on B200: correct (bit-identical frames),
-    // but not faster than the per-layer launches once those use programmatic dependent launch -- the per-tile dataflow
-    // handshake (one ld.acquire.gpu per halo load, one group barrier + fence.acq_rel.gpu + 3 reds per finished tile; a
-    // gpu-scope fence costs > 1 us here) eats the ~5 us per boundary it saves: recon trunk 20 x 22 us vs 440 us chained.
+    // OPT-IN (RVSR_CHAIN=1, read at every call so tests can toggle it).  Measured on B200: correct (bit-identical frames)
+    // and, with the dataflow handshake off the critical path, level with -- not faster than -- the per-layer launches
+    // under programmatic dependent launch (recon trunk 0.41 vs 0.44 ms, 20-image front trunk 1.0 vs 0.83 ms): DESIGN.md 3.1.
     const char *env = getenv("RVSR_CHAIN");
     const bool on = env != nullptr && env[0] == '1';
     const long long tiles = (long long)cdiv(W, TC_TW - 2) * cdiv(H, TC_ROWS) * N;
