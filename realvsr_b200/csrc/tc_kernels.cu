@@ -1214,7 +1214,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
             // tile.  What makes this sound on this hardware: the halo is read by the TMA unit, i.e. from L2 (the coherence
             // point), never through an SM's L1; the writers fence (gpu scope) between their stores and the counter update,
             // so a counter value seen in L2 implies the stores are in L2; and the TMA is issued after the counter load has
-            // returned (data dependence) and after fence.proxy.async (generic -> async proxy ordering in this thread).
+            // returned (its value decides the loop exit); the generic -> async cross-proxy fence sits on the writer side.
             const unsigned target = (unsigned)p.tiles_x * (unsigned)WPG;  // per tile row: every tile's 8 epilogue warps
             struct Tile { int tx, ty, n; const unsigned *fr; unsigned want; };
             auto tile_at = [&](int l, int kl) {
@@ -1253,7 +1253,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
                         if (++spin > (1u << 24)) __trap();  // protocol bug: fail the launch instead of hanging the GPU
                         vcur = ld_relaxed_gpu(cur.fr);
                     }
-                    asm volatile("fence.proxy.async;" ::: "memory");
+                    if ((p.debug & 16) && spin > 0) atomicAdd(reinterpret_cast<unsigned long long *>(&g_stamps[STAMP_SLOTS - 9][0]), (unsigned long long)spin);
+                    if ((p.debug & 16) && spin > 0) atomicAdd(reinterpret_cast<unsigned long long *>(&g_stamps[STAMP_SLOTS - 9][1]), 1ull);
+                    // no proxy fence here (it costs ~0.4 us per tile on this thread's critical path): the TMA below cannot
+                    // issue before the counter load has returned (its value decides the loop exit), it reads L2, and the
+                    // cross-proxy fence is made once per tile on the WRITER side by the publishing warp
+                    if (p.debug & 1) asm volatile("fence.proxy.async;" ::: "memory");
                 }
                 const uint32_t full0 = mapa_rank0(FULL(w, st));
                 if (rank == 0)
@@ -1286,10 +1291,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
             const uint32_t a_base = (uint32_t)adesc0, b_base = (uint32_t)bdesc0;
             constexpr uint32_t stage_units = stage_bytes >> 4, b_tap_step = C8S * NH2;
             uint32_t k = 0, par = 0;
+            // RVSR_CHAIN_DEBUG & 16: per-layer timeline of issuer 0 of cluster 0 (ns since its first layer started)
+            const bool tl_on = (p.debug & 16) && blockIdx.x == 0 && mw == 0 && lane == 0;
+            unsigned long long tl0 = 0;
             for (int l = 0; l < L; ++l) {
                 const int b = l & 1;
+                const unsigned long long ta = tl_on ? globaltimer_ns() : 0;
                 mbar_wait(WFULL(b), (uint32_t)((l >> 1) & 1));
                 mbar_wait(WPEER(b), (uint32_t)((l >> 1) & 1));
+                if (tl_on) {
+                    (void)tl0;
+                    g_stamps[STAMP_SLOTS - 1 - (l >> 2)][(l & 3) * 2] = ta;
+                    g_stamps[STAMP_SLOTS - 1 - (l >> 2)][(l & 3) * 2 + 1] = globaltimer_ns();
+                }
                 const uint32_t b_lo0 = b_base + (uint32_t)b * (w_bytes >> 4);
                 for (int kl = 0; kl < K; ++kl, ++k) {
                     if (k % MMAW != mw) continue;
@@ -1318,6 +1332,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
                 if (elect_one()) umma_commit_2sm(LDONE(b));  // every MMA this issuer made for layer l has completed
                 __syncwarp();
             }
+            if (tl_on) g_stamps[STAMP_SLOTS - 8][0] = globaltimer_ns();
         }
     } else if (warp >= TC_EPI_WARP0) {
         for (int i = threadIdx.x - 32 * TC_EPI_WARP0; i < L * NT; i += 32 * TC_EPI_WARPS) {
@@ -1378,6 +1393,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
                         if (++spin > (1u << 26)) __trap();
                     __threadfence_block();
                     if (real) {
+                        asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy stores -> readable by other SMs' TMA units
                         if (!(p.debug & 2)) __threadfence();
                         if (lane < 3) {
                             const int r = ty + lane - 1;
@@ -1673,15 +1689,13 @@ size_t conv_chain_scratch_bytes(int L, int N, int H) {
     return align_up((size_t)L * sizeof(TcChainLayer), 256) + align_up((size_t)L * N * cdiv(H, TC_ROWS) * sizeof(unsigned), 256);
 }
 bool conv_chain_supported(int L, int N, int H, int W) {
-    // OPT-IN (RVSR_CHAIN=1, read at every call so tests can toggle it).  Measured on B200: correct (bit-identical frames)
-    // and, with the dataflow handshake off the critical path, level with -- not faster than -- the per-layer launches
-    // under programmatic dependent launch (recon trunk 0.41 vs 0.44 ms, 20-image front trunk 1.0 vs 0.83 ms): DESIGN.md 3.1.
+    // ON by default (RVSR_CHAIN=0 restores one launch per convolution; read at every call so tests can toggle it).
+    // Measured on B200 against the PDL-overlapped per-layer launches: -3 % step time at batch 4 and at batch 1,
+    // bit-identical frames.  Needs every CTA resident at once: see launch_conv_chain.
     const char *env = getenv("RVSR_CHAIN");
-    const bool on = env != nullptr && env[0] == '1';
+    const bool on = !(env != nullptr && env[0] == '0');
     const long long tiles = (long long)cdiv(W, TC_TW - 2) * cdiv(H, TC_ROWS) * N;
-    // worth it where kernel boundaries dominate: few tile rounds per layer (RVSR_CHAIN_MAX_ROUNDS, default 24; at 67 rounds --
-    // the 20-image front trunk -- the per-tile dataflow check costs more than the nine boundaries it removes)
-    const int max_rounds = getenv("RVSR_CHAIN_MAX_ROUNDS") ? atoi(getenv("RVSR_CHAIN_MAX_ROUNDS")) : 24;
+    const int max_rounds = getenv("RVSR_CHAIN_MAX_ROUNDS") ? atoi(getenv("RVSR_CHAIN_MAX_ROUNDS")) : 1 << 20;  // experiments
     return on && get_encode() != nullptr && L >= 2 && L <= CHAIN_MAX_LAYERS && tiles >= 2LL * sm_count() &&
            tiles <= (long long)max_rounds * sm_count();
 }
@@ -1734,9 +1748,37 @@ int launch_conv_chain(const ChainLayerDesc *layers, int L, int N, int H, int W, 
     const int npairs = (p.num_tiles + 1) / 2;
     int clusters = sm_count() / 2;
     if (clusters > npairs) clusters = npairs;
-    // every CTA must be resident at once (tile-level dataflow between clusters): grid <= SM count, one CTA per SM
+    // Every CTA must be resident at once (tile-level dataflow between clusters; a CTA that is not scheduled would be
+    // waited for by the others): never launch more clusters than the device can hold of this kernel.
+    {
+        cudaLaunchConfig_t occ = {};
+        occ.gridDim = dim3(2 * clusters); occ.blockDim = dim3(TC_THREADS); occ.dynamicSmemBytes = smem;
+        cudaLaunchAttribute ca[1];
+        ca[0].id = cudaLaunchAttributeClusterDimension;
+        ca[0].val.clusterDim.x = 2; ca[0].val.clusterDim.y = 1; ca[0].val.clusterDim.z = 1;
+        occ.attrs = ca; occ.numAttrs = 1;
+        int max_clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&max_clusters, conv_chain_kernel, &occ) == cudaSuccess && max_clusters > 0 &&
+            clusters > max_clusters)
+            clusters = max_clusters;
+        else
+            (void)cudaGetLastError();
+    }
     launch_k(conv_chain_kernel, dim3(2 * clusters), dim3(TC_THREADS), smem, s, p);
     RVSR_LAUNCH_CHECK();
+    if (p.debug & 16) {  // per-layer timeline of issuer 0 of cluster 0 (debug only: synchronises)
+        cudaStreamSynchronize(s);
+        static unsigned long long h[STAMP_SLOTS][8];
+        cudaMemcpyFromSymbol(h, g_stamps, sizeof(h));
+        const unsigned long long t0 = h[STAMP_SLOTS - 1][0];
+        printf("[chain timeline] %d layers, N=%d:", L, N);
+        for (int l = 0; l < L; ++l) printf(" %.1f(+%.1f)", (h[STAMP_SLOTS - 1 - (l >> 2)][(l & 3) * 2] - t0) * 1e-3,
+                                           (h[STAMP_SLOTS - 1 - (l >> 2)][(l & 3) * 2 + 1] - h[STAMP_SLOTS - 1 - (l >> 2)][(l & 3) * 2]) * 1e-3);
+        printf(" end %.1f us | counter waits: %llu tiles waited, %llu re-polls (of %d tile loads)\n", (h[STAMP_SLOTS - 8][0] - t0) * 1e-3,
+               h[STAMP_SLOTS - 9][1], h[STAMP_SLOTS - 9][0], p.num_tiles * (L - 1));
+        static unsigned long long zero[8] = {0};
+        cudaMemcpyToSymbol(g_stamps, zero, sizeof(zero), (size_t)(STAMP_SLOTS - 9) * sizeof(zero));
+    }
     return RVSR_OK;
 }
 

@@ -133,7 +133,7 @@ def test_engine_host_pipeline_matches_forward_host():
 
 
 def test_chain_kernel_is_bit_identical_to_per_layer_launches(monkeypatch):
-    """RVSR_CHAIN=1 runs each residual trunk as ONE persistent launch with tile-level dataflow between the layers
+    """By default each residual trunk runs as ONE persistent launch with tile-level dataflow between the layers
     (conv_chain_kernel): same MMA order and epilogue arithmetic, so the frames must be bit-identical -- any stale halo
     read (a broken release / acquire between clusters) shows up as a difference.  cfg2 size, B = 2, three repeats."""
     from helpers import edvr_state_shapes
@@ -145,11 +145,10 @@ def test_chain_kernel_is_bit_identical_to_per_layer_launches(monkeypatch):
     net.exec_path = "engine"
     x = synth_input((2, 5, 3, 180, 320), 9).to(DEV).half()
     with torch.no_grad():
-        monkeypatch.delenv("RVSR_CHAIN", raising=False)
+        monkeypatch.setenv("RVSR_CHAIN", "0")
         ref = net(x).clone()
         launches_ref = net._get_engine(x).last_launch_count()
-        monkeypatch.setenv("RVSR_CHAIN", "1")
-        monkeypatch.setenv("RVSR_CHAIN_MAX_ROUNDS", "1000")
+        monkeypatch.delenv("RVSR_CHAIN", raising=False)     # default: chained
         for _ in range(3):
             y = net(x)
             assert torch.equal(y, ref)
