@@ -60,7 +60,8 @@ def main(tag):
     open(os.path.join(pr, "%s_launches.txt" % tag), "w").write(out.getvalue())
     json.dump(traffic, open(os.path.join(pr, "ncu_traffic.json"), "w"), indent=1)
     print(out.getvalue())
-    for rep, name in (("prof_conv.ncu-rep", "ncu_conv3x3"), ("prof_dcn.ncu-rep", "ncu_dcn"), ("prof_tapn.ncu-rep", "ncu_conv_last_tapn")):
+    for rep, name in (("prof_conv.ncu-rep", "ncu_conv3x3"), ("prof_dcn.ncu-rep", "ncu_dcn"), ("prof_tapn.ncu-rep", "ncu_conv_last_tapn"),
+                      ("prof_chain.ncu-rep", "ncu_conv_chain")):
         path = os.path.join(go, rep)
         if os.path.exists(path):
             buf = io.StringIO()
