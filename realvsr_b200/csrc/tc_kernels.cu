@@ -1122,6 +1122,7 @@ struct alignas(64) TcChainParams {
     TileDiv td;
     int debug;  // RVSR_CHAIN_DEBUG timing experiments (results may be wrong): 1 no producer fence, 2 no epilogue fence, 4 no counter wait
 };
+constexpr bool CHAIN_RES_CG = true;  // residuals were written earlier in the same kernel: L2-coherent loads (measured: no cost vs ld.global.nc)
 constexpr int CHAIN_MAX_LAYERS = 20;  // bias table in shared memory: 20 x 256 B leaves room for six halo stages
 
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
@@ -1369,13 +1370,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
                     if (lane == 0) mbar_arrive_cluster(tempty0);
                 };
                 if (act == RVSR_ACT_RELU)
-                    epi_c8_fast<RVSR_ACT_RELU, true>(bias_all + l * NT, out, p.image_stride, res, p.image_stride, p.H, p.W, 8, taddr, half, 0, n,
+                    epi_c8_fast<RVSR_ACT_RELU, CHAIN_RES_CG>(bias_all + l * NT, out, p.image_stride, res, p.image_stride, p.H, p.W, 8, taddr, half, 0, n,
                                                      y, x, valid, TFULL(buf), par, release);
                 else if (act == RVSR_ACT_LRELU)
-                    epi_c8_fast<RVSR_ACT_LRELU, true>(bias_all + l * NT, out, p.image_stride, res, p.image_stride, p.H, p.W, 8, taddr, half, 0, n,
+                    epi_c8_fast<RVSR_ACT_LRELU, CHAIN_RES_CG>(bias_all + l * NT, out, p.image_stride, res, p.image_stride, p.H, p.W, 8, taddr, half, 0, n,
                                                       y, x, valid, TFULL(buf), par, release);
                 else
-                    epi_c8_fast<RVSR_ACT_NONE, true>(bias_all + l * NT, out, p.image_stride, res, p.image_stride, p.H, p.W, 8, taddr, half, 0, n,
+                    epi_c8_fast<RVSR_ACT_NONE, CHAIN_RES_CG>(bias_all + l * NT, out, p.image_stride, res, p.image_stride, p.H, p.W, 8, taddr, half, 0, n,
                                                      y, x, valid, TFULL(buf), par, release);
                 // ---- publish.  Every warp reports "my part of the tile is stored" on a shared-memory counter of its group
                 // (CTA scope, cheap); ONE warp per tile -- they take turns -- waits until all 8 have reported, fences at GPU
