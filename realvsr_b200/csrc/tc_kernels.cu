@@ -1796,6 +1796,7 @@ struct TcDcnParams {
     long long out_image_stride;
     int N, H, W, cpg, act;
     int tiles_x, tiles_y, num_tiles;
+    int debug;  // RVSR_DCN_DEBUG timing experiments (results wrong): 1 = no fence.proxy.async after the gather stores
 };
 constexpr int DCN_GATHER_WARPS = 16, DCN_THREADS = 32 * (1 + DCN_GATHER_WARPS + 4), DCN_STAGES = 3;  // 2..4 measure the same; 6 is slower (L1 capacity)
 constexpr int DCN_TAP_BYTES = 8 * 128 * 16;  // 8 channel blocks x 128 pixels x 16 B
@@ -2007,7 +2008,7 @@ __global__ void __launch_bounds__(DCN_THREADS, 1) dcn_tc_kernel(const __grid_con
                 if (part == 0) mbar_wait(BAR(S + st), ((t * 3 + (s18 >> 1) / S) & 1) ^ 1);  // stage free (its MMAs completed)
                 *reinterpret_cast<uint4 *>(tap_s + st * DCN_TAP_BYTES + part * (DCN_TAP_BYTES / 2) + qq * 2048 + m * 16) = pk;
                 if (part == 1) {
-                    fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+                    if (!(p.debug & 1)) fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
                     __syncwarp();
                     if (lane == 0) mbar_arrive(BAR(st));
                 }
@@ -2057,6 +2058,8 @@ int launch_dcn_tc(const DcnOp &op, cudaStream_t s) {
     p.N = op.N; p.H = op.H; p.W = op.W; p.cpg = op.x.C / op.dg; p.act = op.act;
     p.tiles_x = cdiv(op.W, TC_TW); p.tiles_y = cdiv(op.H, TC_ROWS); p.num_tiles = p.tiles_x * p.tiles_y * op.N;
     if (p.num_tiles == 0) return RVSR_OK;
+    static const int ddbg = getenv("RVSR_DCN_DEBUG") ? atoi(getenv("RVSR_DCN_DEBUG")) : 0;
+    p.debug = ddbg;
     const size_t smem = 8 * 9 * 64 * 16 + DCN_STAGES * DCN_TAP_BYTES + 64 * 4 + 256 + 1024;
     RVSR_TRY(ensure_max_dynamic_smem(reinterpret_cast<const void *>(&dcn_tc_kernel<true>), (int)smem));
     RVSR_TRY(ensure_max_dynamic_smem(reinterpret_cast<const void *>(&dcn_tc_kernel<false>), (int)smem));
