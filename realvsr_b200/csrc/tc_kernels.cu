@@ -1211,11 +1211,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
         if (lane == 0) {
             // Flat loop over (layer, tile) with a one-tile look-ahead: the dataflow counter of the NEXT tile is requested
             // (relaxed, L2) before this tile's stage wait, so its round trip never sits on the critical path.
-            // No acquire is used on purpose: ld.acquire.gpu and fence.acq_rel.gpu both cost ~1 us here, more than a whole
-            // tile.  What makes this sound on this hardware: the halo is read by the TMA unit, i.e. from L2 (the coherence
-            // point), never through an SM's L1; the writers fence (gpu scope) between their stores and the counter update,
-            // so a counter value seen in L2 implies the stores are in L2; and the TMA is issued after the counter load has
-            // returned (its value decides the loop exit); the generic -> async cross-proxy fence sits on the writer side.
+            // The writers fence (gpu scope) between their stores and the counter update; the reader orders its TMA behind
+            // the counter load with fence.proxy.async (required, see below).
             const unsigned target = (unsigned)p.tiles_x * (unsigned)WPG;  // per tile row: every tile's 8 epilogue warps
             struct Tile { int tx, ty, n; const unsigned *fr; unsigned want; };
             auto tile_at = [&](int l, int kl) {
@@ -1256,10 +1253,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
                     }
                     if ((p.debug & 16) && spin > 0) atomicAdd(reinterpret_cast<unsigned long long *>(&g_stamps[STAMP_SLOTS - 9][0]), (unsigned long long)spin);
                     if ((p.debug & 16) && spin > 0) atomicAdd(reinterpret_cast<unsigned long long *>(&g_stamps[STAMP_SLOTS - 9][1]), 1ull);
-                    // no proxy fence here (it costs ~0.4 us per tile on this thread's critical path): the TMA below cannot
-                    // issue before the counter load has returned (its value decides the loop exit), it reads L2, and the
-                    // cross-proxy fence is made once per tile on the WRITER side by the publishing warp
-                    if (p.debug & 1) asm volatile("fence.proxy.async;" ::: "memory");
+                    // The cross-proxy fence on THIS side is required: with a relaxed counter load and only the control
+                    // dependency in front of the TMA, 10 of 24 fresh engines produced a few hundred wrong pixels (a halo read
+                    // before its producer's stores; tools/chain_race2.py).  Either fence.proxy.async or ld.acquire.gpu here
+                    // removes it (0 of 30); the fence is the cheaper one (~0.4 us per tile, on this thread's critical path).
+                    if (p.debug & 8) vcur = ld_acquire_gpu(cur.fr);
+                    if (!(p.debug & 1)) asm volatile("fence.proxy.async;" ::: "memory");
                 }
                 const uint32_t full0 = mapa_rank0(FULL(w, st));
                 if (rank == 0)
@@ -1383,7 +1382,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
                 // scope (cumulative: it covers the other warps' stores, ordered before it by the CTA-scope handshake) and
                 // bumps the global counters of the three tile rows that read this tile.  A gpu-scope fence costs ~1 us: done
                 // by every warp for every tile it made the epilogue the bottleneck, now each warp pays it every 8th tile.
-                __threadfence_block();
+                if (p.debug & 32) __threadfence(); else __threadfence_block();
                 __syncwarp();
                 if (lane == 0) atomicAdd_block(stored, 1u);
                 const uint32_t j = k / EG;  // group-local tile sequence number
@@ -1690,11 +1689,12 @@ size_t conv_chain_scratch_bytes(int L, int N, int H) {
     return align_up((size_t)L * sizeof(TcChainLayer), 256) + align_up((size_t)L * N * cdiv(H, TC_ROWS) * sizeof(unsigned), 256);
 }
 bool conv_chain_supported(int L, int N, int H, int W) {
-    // ON by default (RVSR_CHAIN=0 restores one launch per convolution; read at every call so tests can toggle it).
-    // Measured on B200 against the PDL-overlapped per-layer launches: -3 % step time at batch 4 and at batch 1,
-    // bit-identical frames.  Needs every CTA resident at once: see launch_conv_chain.
+    // OPT-IN (RVSR_CHAIN=1; read at every call so tests can toggle it).  Correct (bit-identical frames, also right after
+    // the workspace held other data) once the producer orders its TMA behind the counter load with fence.proxy.async --
+    // and with that fence on the producer's critical path it is level with, not faster than, the PDL-overlapped
+    // per-layer launches.  Needs every CTA resident at once: see launch_conv_chain.
     const char *env = getenv("RVSR_CHAIN");
-    const bool on = !(env != nullptr && env[0] == '0');
+    const bool on = env != nullptr && env[0] == '1';
     const long long tiles = (long long)cdiv(W, TC_TW - 2) * cdiv(H, TC_ROWS) * N;
     const int max_rounds = getenv("RVSR_CHAIN_MAX_ROUNDS") ? atoi(getenv("RVSR_CHAIN_MAX_ROUNDS")) : 1 << 20;  // experiments
     return on && get_encode() != nullptr && L >= 2 && L <= CHAIN_MAX_LAYERS && tiles >= 2LL * sm_count() &&
