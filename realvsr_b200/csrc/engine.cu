@@ -46,9 +46,9 @@ int ensure_max_dynamic_smem(const void *func, int bytes) {
 static thread_local int g_pdl_scope = 0;
 PdlScope::PdlScope() { ++g_pdl_scope; }
 PdlScope::~PdlScope() { --g_pdl_scope; }
-bool pdl_enabled() {
-    static const bool on = !(getenv("RVSR_PDL") != nullptr && getenv("RVSR_PDL")[0] == '0');
-    return on && g_pdl_scope > 0;
+bool pdl_enabled() {  // RVSR_PDL is read at every launch so that tests can compare both modes in one process
+    const char *env = getenv("RVSR_PDL");
+    return !(env != nullptr && env[0] == '0') && g_pdl_scope > 0;
 }
 
 // ---------------------------------------------------------------- state_dict contract

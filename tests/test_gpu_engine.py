@@ -156,6 +156,26 @@ def test_chain_kernel_is_bit_identical_to_per_layer_launches(monkeypatch, B):
         assert net._get_engine(xs[0]).last_launch_count() == launches_ref - 28   # 10 + 20 convolutions became 2 launches
 
 
+def test_overlapped_launches_match_serialized_launches(monkeypatch):
+    """Programmatic dependent launch lets every kernel's prologue overlap the previous kernel's tail; a kernel that touched
+    activations before its griddepcontrol.wait would read the PREVIOUS forward's data.  Alternating inputs makes that
+    visible: frames with overlapped launches must equal the fully serialized ones (RVSR_PDL=0) bit for bit."""
+    from helpers import edvr_state_shapes
+    from synth import synth_input, synth_state_dict
+    kw = dict(nf=64, nc=3, nframes=5, groups=8, front_RBs=5, back_RBs=10, w_TSA=True)
+    net = E.EDVR(**kw).eval()
+    net.load_state_dict(synth_state_dict(edvr_state_shapes("EDVR", **kw), 7), strict=True)
+    net = net.to(DEV).half()
+    net.exec_path = "engine"
+    xs = [synth_input((1, 5, 3, 180, 320), 29 + i).to(DEV).half() for i in range(2)]
+    with torch.no_grad():
+        monkeypatch.setenv("RVSR_PDL", "0")
+        refs = [net(x).clone() for x in xs]
+        monkeypatch.delenv("RVSR_PDL", raising=False)
+        for i in range(10):
+            assert torch.equal(net(xs[i % 2]), refs[i % 2]), "overlapped launches differ from serialized ones in repeat %d" % i
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
 def test_two_devices_in_one_process():
     """The reference wraps the model in nn.DataParallel (VideoSR_AllPair_model_YCbCr_Split.py:33-36): one process, several
