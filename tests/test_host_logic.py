@@ -72,3 +72,45 @@ def test_engine_path_refuses_cpu_tensors():
     with pytest.raises(RuntimeError):
         with torch.no_grad():
             net(torch.zeros(1, 5, 3, 16, 16))
+
+
+def test_tiled_forward_stitches_exactly_for_a_local_model():
+    """video.tiled_forward on the CPU with a stand-in model whose receptive field is smaller than the halo (x4 bilinear
+    of the centre frame + a 3x3 box filter): the stitched result must equal the whole-frame result everywhere, for tile
+    grids that divide the frame and for ragged last tiles."""
+    import torch
+    import torch.nn.functional as F
+    from realvsr_b200 import video
+
+    def model(x):                                   # [B, N, C, H, W] -> [B, C, 4H, 4W]
+        c = x[:, x.shape[1] // 2]
+        c = F.avg_pool2d(F.pad(c, (1, 1, 1, 1), mode="replicate"), 3, 1)
+        return F.interpolate(c, scale_factor=4, mode="bilinear", align_corners=False)
+
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(2, 3, 3, 40, 56, generator=g)
+    full = model(x)
+    for tile in ((40, 56), (20, 28), (16, 24), (12, 20)):
+        out = video.tiled_forward(model, x, tile=tile, halo=8)
+        assert out.shape == full.shape
+        # replicate padding at the true image border is the only place a tile can differ: tiles see the same border
+        assert torch.allclose(out, full, atol=1e-6), tile
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """The driver parses ONE JSON line from bench.py's stdout; native libraries may print to fd 1 (NCCL banner), so
+    bench.py keeps a private copy of stdout for the result.  The reference arm runs on the CPU (the oracle port)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout[:500]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
