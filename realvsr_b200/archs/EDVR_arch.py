@@ -22,6 +22,7 @@ There is no CPU path (the reference's DCN is CUDA-only as well, deform_conv.py:1
 """
 import functools
 import os
+import threading
 
 import torch
 import torch.nn as nn
@@ -30,6 +31,8 @@ import torch.nn.functional as F
 from . import arch_util
 from .dcn.deform_conv import ModulatedDeformConvPack as DCN
 from .. import engine as _engine
+
+_ENGINE_LOCK = threading.Lock()  # DataParallel runs the replicas' forwards in threads
 
 
 def _conv3(cin, cout, stride=1):
@@ -204,35 +207,100 @@ class _EDVRBase(nn.Module):
         # engine arithmetic: None = follow the input dtype (fp32 in -> fp32 SIMT kernels,
         # fp16 in -> tensor-core kernels); 'fp16' runs fp32 inputs through the fp16 engine.
         self.engine_precision = os.environ.get("RVSR_ENGINE_PRECISION") or None
-        self.__dict__['_engines'] = {}  # (device index, precision) -> [EDVREngine, weight stamp]
+        # how a weight change is detected before an engine forward: 'stamp' (data_ptr + version of every weight),
+        # 'checksum' (stamp + a device-side sum, catches p.data.xxx_() edits) or 'always' (see invalidate_engine)
+        self.engine_weight_check = os.environ.get("RVSR_WEIGHT_CHECK", "stamp")
+        # (device index, precision) -> [EDVREngine, (weight stamp, checksum)].  Shared BY REFERENCE with nn.DataParallel
+        # replicas (replicate() shallow-copies __dict__): replica d finds the engine of device d built by an earlier
+        # iteration instead of creating one per forward.
+        self.__dict__['_engines'] = {}
 
     # ------------------------------------------------------------------ engine path
+    def _named_weights(self):
+        """(name, tensor) of every weight, in state_dict order.  Works on nn.DataParallel replicas too: torch's
+        replicate() leaves a replica's ``_parameters`` empty and sets the broadcast copies as plain attributes
+        (kept in ``_former_parameters``), so ``parameters()`` / ``state_dict()`` are empty there."""
+        for prefix, m in self.named_modules():
+            former = m.__dict__.get('_former_parameters') or {}
+            for k, v in m._parameters.items():
+                t = v if v is not None else former.get(k)
+                if t is not None:
+                    yield (prefix + '.' + k if prefix else k), t
+            for k, v in former.items():
+                if k not in m._parameters and v is not None:
+                    yield (prefix + '.' + k if prefix else k), v
+
+    def _on_replica(self):
+        return bool(self.__dict__.get('_is_replica', False)) or '_former_parameters' in self.__dict__
+
     def _engine_ok(self, x):
         if self.exec_path == "module":
             return False
+        # the grad check looks at the actual weight tensors (a DataParallel replica has no parameters())
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(t.requires_grad for _, t in self._named_weights()))
         ok = (x.is_cuda and not self.is_predeblur and not self.HR_in and self.nf % 8 == 0
-              and x.dtype in (torch.float32, torch.float16)
-              and not (torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))))
+              and x.dtype in (torch.float32, torch.float16) and not needs_grad)
         if not ok and self.exec_path == "engine":
             raise RuntimeError("realvsr_b200: exec_path='engine' but this call needs the module path "
                                "(autograd enabled, non-CUDA input, or predeblur/HR_in)")
         return ok
 
     def _weight_stamp(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        return tuple((t.data_ptr(), t._version) for _, t in self._named_weights())
+
+    def invalidate_engine(self):
+        """Force the engine to re-read the weights at the next forward.  The automatic check compares
+        (data_ptr, version) of every weight, which sees ``load_state_dict``, ``.to()``, optimizer steps and any
+        in-place op on the parameter -- but NOT in-place writes through ``p.data`` (``p.data.mul_(s)``,
+        ``p.data.copy_(ema)``): torch does not bump ``p._version`` for those.  Call this after such an edit, or set
+        ``engine_weight_check = 'always'`` (re-hand the weights on every call, a few ms) /
+        ``'checksum'`` (a device-side sum of all weights is compared on every call: one small D2H sync)."""
+        for slot in self._engines.values():
+            slot[1] = None
+
+    def _weights_changed(self, slot, stamp):
+        mode = self.engine_weight_check
+        if mode == "always" or self._on_replica():
+            return True   # replicas: broadcast copies are fresh tensors every iteration; a recycled address proves nothing
+        if slot[1] is None or slot[1][0] != stamp:
+            return True
+        if mode == "checksum":
+            return slot[1][1] != self._weight_checksum()
+        return False
+
+    def _weight_checksum(self):
+        ws = [t.detach() for _, t in self._named_weights()]
+        return float(torch.stack(torch._foreach_norm([w.float() for w in ws])).double().sum())
 
     def _get_engine(self, x):
         prec = self.engine_precision or ("fp16" if x.dtype == torch.float16 else "fp32")
         key = (x.device.index, prec)
-        slot = self._engines.get(key)
-        if slot is None:
-            slot = [_engine.EDVREngine(precision=prec, device=x.device, **self._cfg), None]
-            self._engines[key] = slot
+        with _ENGINE_LOCK:
+            slot = self._engines.get(key)
+            if slot is None:
+                slot = [_engine.EDVREngine(precision=prec, device=x.device, **self._cfg), None]
+                self._engines[key] = slot
         stamp = self._weight_stamp()
-        if slot[1] != stamp:
-            slot[0].load_state_dict(self.state_dict(), strict=True)
-            slot[1] = stamp
+        if self._weights_changed(slot, stamp):
+            slot[0].load_state_dict({k: t for k, t in self._named_weights()}, strict=True)
+            slot[1] = (stamp, self._weight_checksum() if self.engine_weight_check == "checksum" else None)
         return slot[0]
+
+    def load_state_dict(self, *args, **kwargs):
+        r = super(_EDVRBase, self).load_state_dict(*args, **kwargs)
+        self.invalidate_engine()
+        return r
+
+    def _apply(self, fn, *args, **kwargs):
+        r = super(_EDVRBase, self)._apply(fn, *args, **kwargs)
+        self.invalidate_engine()
+        return r
+
+    def __getstate__(self):
+        # the engine cache holds ctypes handles (not picklable / deep-copyable): a copy starts with an empty cache
+        d = self.__dict__.copy()
+        d['_engines'] = {}
+        return d
 
     def forward(self, x):
         if self._engine_ok(x):

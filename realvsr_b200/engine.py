@@ -58,17 +58,16 @@ class EDVREngine:
         """Strict like the reference's test scripts (test_RealVSR_wi_GT.py:77): unexpected or
         missing keys raise RuntimeError.  A leading 'module.' (DataParallel) is stripped like
         base_model.load_network does (base_model.py:104-114)."""
+        known = set(self.weight_names())
         with torch.cuda.device(self.device):
             for k, v in sd.items():
                 name = k[7:] if k.startswith("module.") else k
+                if not strict and name not in known:
+                    continue  # strict=False skips unknown keys only; size mismatches and CUDA errors still raise
                 t = v.detach().to(device=self.device, dtype=torch.float32).contiguous()
                 shape = (ctypes.c_int64 * t.dim())(*t.shape)
-                try:
-                    _lib.check(self.L.rvsr_engine_set_weight(self.h, name.encode(), ctypes.c_void_p(t.data_ptr()),
-                                                             shape, t.dim(), self._stream()), "load_state_dict")
-                except RuntimeError:
-                    if strict:
-                        raise
+                _lib.check(self.L.rvsr_engine_set_weight(self.h, name.encode(), ctypes.c_void_p(t.data_ptr()),
+                                                         shape, t.dim(), self._stream()), "load_state_dict")
             _lib.check(self.L.rvsr_engine_finalize(self.h, self._stream()), "load_state_dict")
             torch.cuda.current_stream(self.device).synchronize()  # source tensors may be temporaries
         self.loaded = True
@@ -113,7 +112,13 @@ class EDVREngine:
         """Host tensors in, host tensors out (pinned for async copies): H2D + forward + D2H on
         the current stream, then a stream synchronise -- what the reference's
         util.single_forward (utils/util.py:222-237) does around the model."""
+        if x_host.is_cuda or x_host.dim() != 5 or not x_host.is_contiguous():
+            raise RuntimeError("forward_host: x_host must be a contiguous host tensor [B, N, C, H, W]")
         B, _, _, H, W = x_host.shape
+        if out_host is not None and (out_host.is_cuda or not out_host.is_contiguous() or out_host.dtype != x_host.dtype or
+                                     tuple(out_host.shape) != (B, self.cfg.nc, H * self.scale, W * self.scale)):
+            raise RuntimeError("forward_host: out_host must be a contiguous host tensor of x_host's dtype and shape %s" %
+                               ((B, self.cfg.nc, H * self.scale, W * self.scale),))
         key = (tuple(x_host.shape), x_host.dtype)
         if key not in self._staging:
             self._staging.clear()
@@ -225,7 +230,7 @@ class HostPipeline:
 
         pipe = engine.host_pipeline()
         for x_host, out_host in batches:      # pinned host tensors
-            pipe.submit(x_host, out_host)     # returns at once; out_host is valid after wait()/drain()
+            pipe.submit(x_host, out_host)     # returns a ticket at once; wait_input(t): x_host reusable, wait(t): out_host valid
         pipe.drain()
 
     `depth` device staging buffers per direction; submit() blocks the host only when all of them are in flight."""
@@ -246,7 +251,24 @@ class HostPipeline:
                            ev_in=torch.cuda.Event(), ev_done=torch.cuda.Event(), ev_out=torch.cuda.Event(), busy=False)
                       for _ in range(self.depth)]
 
+    @staticmethod
+    def _check_host(t, what, dtype=None, shape=None):
+        if t.is_cuda or not t.is_contiguous() or not t.is_pinned():
+            raise RuntimeError("HostPipeline: %s must be a contiguous pinned host tensor" % what)
+        if dtype is not None and t.dtype != dtype:
+            raise RuntimeError("HostPipeline: %s must be %s (got %s)" % (what, dtype, t.dtype))
+        if shape is not None and tuple(t.shape) != tuple(shape):
+            raise RuntimeError("HostPipeline: %s must have shape %s (got %s)" % (what, tuple(shape), tuple(t.shape)))
+
     def submit(self, x_host, out_host):
+        """Queue one batch.  Returns a ticket for wait_input(): x_host may be refilled once wait_input(ticket)
+        has returned (its H2D copy has left the host buffer); out_host is valid after wait(ticket) / drain()."""
+        e = self.e
+        if x_host.dim() != 5:
+            raise RuntimeError("HostPipeline: x_host must be [B, N, C, H, W]")
+        B, _, _, H, W = x_host.shape
+        self._check_host(x_host, "x_host")
+        self._check_host(out_host, "out_host", x_host.dtype, (B, e.cfg.nc, H * e.scale, W * e.scale))
         if self.key != (tuple(x_host.shape), x_host.dtype):
             self.drain()
             self._alloc(x_host)
@@ -266,7 +288,17 @@ class HostPipeline:
             out_host.copy_(sl["dout"], non_blocking=True)
             sl["ev_out"].record(self.s_out)
         sl["busy"] = True
-        return out_host
+        return self.i - 1
+
+    def wait_input(self, ticket):
+        """Block until the H2D copy of submit() number `ticket` has read its x_host (safe to refill it)."""
+        if self.slots and self.i - ticket <= self.depth:
+            self.slots[ticket % self.depth]["ev_in"].synchronize()
+
+    def wait(self, ticket):
+        """Block until the result of submit() number `ticket` has landed in its out_host."""
+        if self.slots and self.i - ticket <= self.depth:
+            self.slots[ticket % self.depth]["ev_out"].synchronize()
 
     def drain(self):
         if self.slots:

@@ -31,6 +31,20 @@ def index_generation(crt_i, max_n, N, padding='reflection'):
     return out
 
 
+def pad_to_multiple(x, m=4):
+    """Replicate-pad the last two dims of x up to multiples of m (bottom / right).  The network halves the resolution
+    twice and doubles it back (EDVR_arch.py:279-287, :111-124), so H and W must be multiples of 4 -- the reference fails
+    on e.g. 270x480 (-> 1080p); pad, run, and crop the result to [..., :s*H, :s*W].  Returns (padded, (H, W))."""
+    import torch.nn.functional as F
+    H, W = x.shape[-2:]
+    ph, pw = (-H) % m, (-W) % m
+    if ph == 0 and pw == 0:
+        return x, (H, W)
+    lead = x.shape[:-3]
+    y = F.pad(x.reshape((-1,) + tuple(x.shape[-3:])), (0, pw, 0, ph), mode="replicate")
+    return y.reshape(tuple(lead) + tuple(y.shape[-3:])), (H, W)
+
+
 def single_forward(model, inp):
     """model(inp) without autograd; first element if the model returns a list/tuple; float, on the CPU."""
     with torch.no_grad():

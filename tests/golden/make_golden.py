@@ -92,6 +92,12 @@ CASES = {
                                               back_RBs=10, w_TSA=False), (1, 3, 3, 20, 16), 51, 52),
     "edvr_predeblur": ("EDVR", dict(nf=16, nc=3, nframes=3, groups=4, front_RBs=1, back_RBs=1,
                                     predeblur=True, w_TSA=True), (1, 3, 3, 16, 16), 61, 62),
+    # HR_in=True (EDVR_arch.py:228-231, :267-274, :315-316): full-resolution input, two stride-2 convs in the stem,
+    # output at the INPUT resolution, base = the centre frame itself; alone and together with predeblur (:15-59 HR_in stem)
+    "edvr_hr_in": ("EDVR", dict(nf=16, nc=3, nframes=3, groups=4, front_RBs=1, back_RBs=1,
+                                HR_in=True, w_TSA=True), (1, 3, 3, 32, 48), 81, 82),
+    "edvr_predeblur_hr_in": ("EDVR", dict(nf=16, nc=3, nframes=3, groups=4, front_RBs=1, back_RBs=1,
+                                          predeblur=True, HR_in=True, w_TSA=False), (1, 3, 3, 32, 32), 83, 84),
     # BASELINE cfg4's architecture (7 frames, 128 channels, 16 channels per deformable group) on a small crop
     "edvr_nf128_7f": ("EDVR", dict(nf=128, nc=3, nframes=7, groups=8, front_RBs=5, back_RBs=10,
                                    w_TSA=True), (1, 7, 3, 16, 24), 71, 72),
@@ -123,6 +129,22 @@ def main():
             wseed=wseed, xseed=xseed, out=y.numpy(), aligned0=taps["aligned0"].numpy(),
             keys=np.array(list(sd.keys())), torch_version=torch.__version__)
         print(name, tuple(y.shape), float(y.abs().mean()), "aligned0", float(taps["aligned0"].abs().mean()))
+
+    if not only or "edvr_tiny_grads" in only:
+        # whole-network backward golden (BASELINE cfg5's step on a tiny architecture): the reference network in float64,
+        # L1 loss against a seeded target, gradient of EVERY parameter (torchvision's deform_conv2d has autograd)
+        kw = dict(nf=8, nc=3, nframes=5, groups=8, front_RBs=1, back_RBs=1, w_TSA=True)
+        net = E.EDVR(**kw).double().train()
+        sd = synth_state_dict({k: v.shape for k, v in net.state_dict().items()}, 91)
+        net.load_state_dict(sd, strict=True)
+        x = synth_input((2, 5, 3, 24, 24), 92).double()
+        gt = synth_normal((2, 3, 96, 96), 93, std=0.3).double() + 0.5
+        loss = torch.nn.functional.l1_loss(net(x), gt)
+        loss.backward()
+        grads = {"g:" + k: p.grad.float().numpy() for k, p in net.named_parameters()}
+        np.savez_compressed(os.path.join(HERE, "edvr_tiny_grads.npz"), kwargs=repr(kw), wseed=91, xseed=92, gtseed=93,
+                            shape=np.array([2, 5, 3, 24, 24]), loss=float(loss), **grads)
+        print("edvr_tiny_grads loss", float(loss), len(grads), "gradients")
 
     if only and "dcn_unit" not in only:
         return

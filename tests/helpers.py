@@ -7,7 +7,7 @@ import torch
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 EDVR_CASES = ["edvr_tiny", "edvr_tiny_b2_g2", "edvr_noup_3f", "edvr_nf64_crop",
-              "edvr_noup_nf64_ship", "edvr_predeblur", "edvr_nf128_7f"]
+              "edvr_noup_nf64_ship", "edvr_predeblur", "edvr_nf128_7f", "edvr_hr_in", "edvr_predeblur_hr_in"]
 
 
 def load_case(name):

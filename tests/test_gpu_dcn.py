@@ -253,3 +253,31 @@ def test_training_step_through_module_path():
         wparam[idx] += eps
     fd = (lp - lm) / (2 * eps)
     assert abs(fd - g) < 0.15 * max(abs(g), 1e-4) + 2e-5, (fd, g)
+
+
+def test_whole_network_gradients_match_reference_golden():
+    """BASELINE cfg5's step (forward + L1 loss + backward) on a tiny architecture: EVERY parameter's gradient against
+    the golden produced by the reference's own EDVR_arch.py in float64 (tests/golden/make_golden.py, edvr_tiny_grads:
+    torchvision's deform_conv2d supplies the DCN autograd there).  Module path here: torch convs + rvsr_mdcn_fwd /
+    rvsr_mdcn_bwd.  Tolerance 1e-3 of each gradient tensor's max (fp32 vs float64, atomics-free summation order)."""
+    import ast
+    from helpers import edvr_state_shapes
+    from realvsr_b200.archs import EDVR_arch as E
+    from synth import synth_input, synth_state_dict
+    z = np.load(os.path.join(GOLDEN, "edvr_tiny_grads.npz"))
+    kw = ast.literal_eval(str(z["kwargs"]))
+    net = E.EDVR(**kw).train()
+    net.load_state_dict(synth_state_dict(edvr_state_shapes("EDVR", **kw), int(z["wseed"])), strict=True)
+    net = net.to(DEV)
+    x = synth_input(tuple(z["shape"]), int(z["xseed"])).to(DEV)
+    gt = (synth_normal((2, 3, 96, 96), int(z["gtseed"]), std=0.3) + 0.5).to(DEV)
+    loss = torch.nn.functional.l1_loss(net(x), gt)
+    loss.backward()
+    assert abs(float(loss) - float(z["loss"])) < 1e-5
+    worst = ("", 0.0)
+    for name, p_ in net.named_parameters():
+        e = rel_err(p_.grad.cpu(), torch.from_numpy(z["g:" + name]))
+        if e > worst[1]:
+            worst = (name, e)
+    print("whole-network gradients: worst %s %.2e" % worst)
+    assert worst[1] < 1e-3, worst

@@ -4,7 +4,7 @@ Errors are measured on the network's own contribution  out - base  (base = bilin
 centre frame, or the centre frame for EDVR_NoUp) so the comparison is not flattered by the
 image-sized base term, as max|diff| / max|reference residual|.
   fp32 engine vs reference-generated golden : < 1e-3  (north_star tolerance)
-  fp16 engine vs the same golden            : < 3e-2  (fp16 storage of ~100 chained layers;
+  fp16 engine vs the same golden            : < 1e-2  (fp16 storage of ~100 chained layers;
                                                fp32 coordinates, blend and accumulation)
 """
 import pytest
@@ -55,7 +55,7 @@ def test_engine_fp16_matches_golden(name):
         y = net(c["x"].to(DEV).half())
     assert y.dtype == torch.float16
     base = _base(c)
-    assert rel_err(y.float().cpu() - base, c["out"] - base) < 3e-2
+    assert rel_err(y.float().cpu() - base, c["out"] - base) < 1e-2
 
 
 @pytest.mark.parametrize("name", ["edvr_tiny", "edvr_noup_3f", "edvr_predeblur"])
@@ -192,6 +192,53 @@ def test_two_devices_in_one_process():
     assert torch.equal(outs[0], outs[1])
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_dataparallel_wrapper_train_and_eval():
+    """The wrapper the reference's training models use (nn.DataParallel over gpu_ids, VideoSR_AllPair_model_YCbCr_Split.py:36;
+    the shipped YAMLs select it).  Replicas have no parameters() / state_dict() (replicate() sets the broadcast weights as
+    plain attributes): with autograd they must take the module path and deliver gradients to the wrapped module's
+    parameters; under no_grad (model.test()) they run the engine with the replica's weights."""
+    c = load_case("edvr_tiny_b2_g2")
+    net = getattr(E, c["cls"])(**c["kwargs"])
+    net.load_state_dict(c["sd"], strict=True)
+    net = net.to(DEV)
+    dp = torch.nn.DataParallel(net, device_ids=[0, 1])
+    x = c["x"].to(DEV)
+    base = _base(c)
+    dp.eval()
+    with torch.no_grad():
+        y = dp(x)
+    assert rel_err(y.cpu() - base, c["out"] - base) < 1e-3
+    dp.train()
+    out = dp(x)
+    out.mean().backward()
+    assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in net.parameters())
+    assert rel_err(out.detach().cpu() - base, c["out"] - base) < 1e-3
+
+
+def test_engine_sees_data_writes_after_invalidate():
+    """In-place writes through p.data do not bump p._version (torch semantics): invalidate_engine() / the 'checksum' weight
+    check make the engine re-read the weights."""
+    c = load_case("edvr_tiny")
+    net = _net(c, "engine")
+    x = c["x"].to(DEV)
+    with torch.no_grad():
+        y1 = net(x)
+        net.conv_last.bias.data.add_(0.25)
+        net.invalidate_engine()
+        y2 = net(x)
+        assert rel_err(y2 - y1, torch.full_like(y1, 0.25)) < 1e-5
+        net.engine_weight_check = "checksum"
+        net(x)
+        net.conv_last.bias.data.add_(0.25)
+        y3 = net(x)
+        assert rel_err(y3 - y1, torch.full_like(y1, 0.5)) < 1e-5
+    import copy
+    net2 = copy.deepcopy(net)                      # engine cache holds ctypes handles: the copy starts without one
+    with torch.no_grad():
+        assert torch.equal(net2(x), y3)
+
+
 def test_cfg2_full_size_fp16_properties():
     """BASELINE cfg2 size (5x3x180x320 -> 720x1280, nf=64, TSA): too slow for the CPU oracle,
     so check size-independent properties: finite, deterministic, zero-initialised offset
@@ -218,7 +265,7 @@ def test_cfg2_full_size_fp16_properties():
     with torch.no_grad():
         y32 = net32(x.float())
     base = F.interpolate(x[:, 2].float(), scale_factor=4, mode="bilinear", align_corners=False)
-    assert rel_err(y.float() - base, y32 - base) < 3e-2
+    assert rel_err(y.float() - base, y32 - base) < 1e-2
 
 
 def test_shipped_realvsr_config_full_frame():
@@ -245,5 +292,5 @@ def test_shipped_realvsr_config_full_frame():
     net16.exec_path = "engine"
     y16 = V.single_forward(net16, x.half())
     base = x[:, 1].cpu()
-    assert rel_err(y16 - base, y32 - base) < 3e-2
+    assert rel_err(y16 - base, y32 - base) < 1e-2
     assert torch.equal(y16, V.single_forward(net16, x.half()))

@@ -50,7 +50,8 @@ def test_resblock_init_scale():
     assert len(arch_util.make_layer(arch_util.ResidualBlock_noBN, 3, nf=8)) == 3
 
 
-@pytest.mark.parametrize("name", ["edvr_tiny", "edvr_tiny_b2_g2", "edvr_noup_3f", "edvr_predeblur"])
+@pytest.mark.parametrize("name", ["edvr_tiny", "edvr_tiny_b2_g2", "edvr_noup_3f", "edvr_predeblur", "edvr_hr_in",
+                                  "edvr_predeblur_hr_in"])
 def test_module_path_graph_matches_reference_golden(name, monkeypatch):
     c = load_case(name)
     net = getattr(E, c["cls"])(**c["kwargs"]).eval()
@@ -114,3 +115,77 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
     assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+# ---------------------------------------------------------------- engine-cache bookkeeping (no GPU needed)
+def _fake_replica(net):
+    """What torch.nn.parallel.replicate() produces (replicate.py:167-197): no _parameters, the broadcast copies as
+    plain tensor attributes + _former_parameters, sub-modules replaced by their replicas, __dict__ shallow-copied."""
+    memo = {}
+    for m in net.modules():
+        r = m._replicate_for_data_parallel()
+        r._former_parameters = {}
+        memo[m] = r
+    for m, r in memo.items():
+        for k, child in m._modules.items():
+            if child is not None:
+                r._modules[k] = memo[child]
+        for k, p in m._parameters.items():
+            if p is not None:
+                cp = p.detach().clone().requires_grad_(p.requires_grad) * 1.0  # non-leaf, like Broadcast.apply's output
+                setattr(r, k, cp)
+                r._former_parameters[k] = cp
+    return memo[net]
+
+
+def test_named_weights_on_dataparallel_replica():
+    net = E.EDVR(nf=8, groups=2, front_RBs=1, back_RBs=1)
+    rep = _fake_replica(net)
+    assert len(list(rep.parameters())) == 0 and len(rep.state_dict()) == 0   # why state_dict() cannot feed the engine
+    names = [k for k, _ in rep._named_weights()]
+    assert names == list(net.state_dict().keys())
+    assert rep._on_replica() and not net._on_replica()
+    # replica weights require grad (non-leaf copies): with autograd on, the engine must not be chosen
+    x = torch.zeros(1, 5, 3, 8, 8)
+    rep.exec_path = "auto"
+    assert rep._engine_ok(x) is False
+    assert rep._engines is net._engines      # shared on purpose: replica d reuses device d's engine across iterations
+    assert rep._weights_changed([None, ("anything", None)], "anything") is True   # replicas always re-hand weights
+
+
+def test_engine_cache_survives_deepcopy_and_pickle():
+    import copy
+    import ctypes
+    import pickle
+    net = E.EDVR(nf=8, groups=2, front_RBs=1, back_RBs=1)
+    net._engines[(0, "fp16")] = [ctypes.c_void_p(1234), None]   # stands for an EDVREngine (ctypes handles inside)
+    c = copy.deepcopy(net)
+    assert c._engines == {} and len(net._engines) == 1
+    assert list(c.state_dict().keys()) == list(net.state_dict().keys())
+    c2 = pickle.loads(pickle.dumps(net))
+    assert c2._engines == {}
+
+
+def test_weight_stamp_and_invalidate():
+    net = E.EDVR(nf=8, groups=2, front_RBs=1, back_RBs=1)
+    slot = [None, None]
+    st = net._weight_stamp()
+    assert net._weights_changed(slot, st)
+    slot[1] = (st, None)
+    assert not net._weights_changed(slot, net._weight_stamp())
+    with torch.no_grad():
+        net.conv_last.bias.add_(1.0)                       # in-place on the parameter: version bump -> seen
+    assert net._weights_changed(slot, net._weight_stamp())
+    slot[1] = (net._weight_stamp(), None)
+    net.conv_last.bias.data.add_(1.0)                      # through .data: NOT seen by the stamp (torch semantics) ...
+    assert not net._weights_changed(slot, net._weight_stamp())
+    net._engines[(0, "fp32")] = slot
+    net.invalidate_engine()                                # ... hence the explicit call
+    assert net._weights_changed(slot, net._weight_stamp())
+    net.engine_weight_check = "checksum"                   # ... or the checksum mode
+    slot[1] = (net._weight_stamp(), net._weight_checksum())
+    assert not net._weights_changed(slot, net._weight_stamp())
+    net.conv_last.bias.data.add_(1.0)
+    assert net._weights_changed(slot, net._weight_stamp())
+    net.load_state_dict(net.state_dict())                  # hooks: load_state_dict / .to() invalidate
+    assert net._engines[(0, "fp32")][1] is None

@@ -58,29 +58,43 @@ def test_sr_sequence_cache_is_bit_identical_to_plain_forward(name, half):
 
 
 @pytest.mark.gpu
-def test_tiled_forward_matches_whole_frame():
-    """One tile covering the frame is exact; 2 x 2 tiles with a 16-pixel halo differ from the whole-frame forward only by
-    the truncated receptive field at the seams (bounded), and every pixel farther than the halo from a seam... is still
-    only approximately equal (the pyramid's receptive field exceeds the halo), so the bound is global."""
-    import torch
-    from helpers import edvr_state_shapes, rel_err
-    from realvsr_b200 import video
+@pytest.mark.parametrize("half", [False, True])
+def test_tiled_forward_matches_oracle_with_identical_tiling(half):
+    """BASELINE cfg4's architecture (7 frames, nf = 128, 16 channels per deformable group) on a 2 x 2-tile crop.  The
+    network's receptive field exceeds any practical halo, so tiles + halo != whole frame near the seams (SURVEY.md 7,
+    "hard parts"): parity for tiled inference is therefore defined PER TILING -- the CPU oracle is run through the same
+    video.tiled_forward (same tile origins, halos and crop) and must agree everywhere: fp32 engine < 1e-3, fp16 < 1e-2.
+    One tile covering the frame is bit-identical to the plain forward."""
+    import torch.nn.functional as F
+    from helpers import rel_err
+    from oracle import edvr_oracle as O
     from realvsr_b200.archs import EDVR_arch as E
-    from synth import synth_input, synth_state_dict
-    kw = dict(nf=64, nc=3, nframes=3, groups=8, front_RBs=2, back_RBs=2, w_TSA=True)
+    from synth import synth_input
+    c = load_case("edvr_nf128_7f")
+    kw = c["kwargs"]
     net = E.EDVR(**kw).eval()
-    net.load_state_dict(synth_state_dict(edvr_state_shapes("EDVR", **kw), 17), strict=True)
+    net.load_state_dict(c["sd"], strict=True)
     net = net.to("cuda:0")
     net.exec_path = "engine"
-    x = synth_input((1, 3, 3, 96, 128), 18).to("cuda:0")
+    x = synth_input((1, 7, 3, 40, 56), 118)
+    xd = x.to("cuda:0")
+    if half:
+        net, xd = net.half(), xd.half()
+
+    def oracle_model(t):
+        with torch.no_grad():
+            return O.edvr_forward(c["sd"], t, groups=kw["groups"], w_TSA=True, upsample=True)
+
+    tile, halo = (20, 28), 8
+    ref = V.tiled_forward(oracle_model, x, tile=tile, halo=halo)
+    got = V.tiled_forward(net, xd, tile=tile, halo=halo).float().cpu()
+    base = F.interpolate(x[:, 3], scale_factor=4, mode="bilinear", align_corners=False)
+    err = rel_err(got - base, ref - base)
+    print("tiled nf128/7f %s engine vs identically tiled oracle: %.2e" % ("fp16" if half else "fp32", err))
+    assert got.shape == ref.shape == (1, 3, 160, 224)
+    assert err < (1e-2 if half else 1e-3)
     with torch.no_grad():
-        full = net(x)
-    assert torch.equal(video.tiled_forward(net, x, tile=(96, 128), halo=16), full)
-    tiled = video.tiled_forward(net, x, tile=(48, 64), halo=16)
-    assert tiled.shape == full.shape
-    base = torch.nn.functional.interpolate(x[:, 1], scale_factor=4, mode="bilinear", align_corners=False)
-    assert rel_err((tiled - base).cpu(), (full - base).cpu()) < 0.2       # seams: truncated context
-    inner = (slice(None), slice(None), slice(4 * 8, 4 * 40), slice(4 * 8, 4 * 56))   # interior of the first tile
-    assert rel_err((tiled - base)[inner].cpu(), (full - base)[inner].cpu()) < 5e-2
+        full = net(xd)
+    assert torch.equal(V.tiled_forward(net, xd, tile=(40, 56), halo=8), full)
     with pytest.raises(RuntimeError):
-        video.tiled_forward(net, x[..., :94, :], tile=(48, 64))
+        V.tiled_forward(net, xd[..., :38, :], tile=tile)
