@@ -249,6 +249,20 @@ static int mdcn_pack_fwd_t(const void *x, const void *feat, const void *w_om, co
     DcnOp d = {};
     d.x = Src{xa, img, C, 1, -1}; d.bias = b; d.N = B; d.H = H; d.W = W; d.Cout = Cout; d.kh = d.kw = 3; d.stride = 1;
     d.pad = 1; d.dil = 1; d.dg = dg; d.act = act;
+    if (tc && dg == 8 && bom != nullptr && tc_pack_om_weight_bytes(Com, C, dg) > 0) {
+        // ONE kernel: offset/mask conv -> TMEM -> gather -> contraction (dcn_fused.cu); the OM tensor never exists.
+        // The workspace slots of the two-kernel path's weight layouts hold this kernel's (same sizes).
+        PackFusedOp f = {};
+        f.x = Src{xa, img, C, 1, -1}; f.feat = fa; f.w_om = wom_tc; f.bias_om = bom; f.w_dcn2 = w_tc; f.bias = b;
+        f.out = oa; f.out_image_stride = (long long)cdiv(Cout, 8) * H * W * 8;
+        f.N = B; f.H = H; f.W = W; f.Cout = Cout; f.dg = dg; f.act = act;
+        if (tc_pack_fused_supported(f)) {
+            RVSR_TRY(pack_weight_om_stream(wom, wom_tc, Com, C, dg, s));
+            RVSR_TRY(pack_weight_tc2(w, w_tc, Cout, C, 3, 0, s));
+            RVSR_TRY(launch_pack_fused(f, s));
+            return launch_unpack_nchw<T, T>(oa, (T *)y, B, Cout, H, W, s);
+        }
+    }
     if (tc) {
         RVSR_TRY(pack_weight_tc(wom, wom_tc, Com, C, 3, 2, s));
         RVSR_TRY(pack_weight_tc(w, w_tc, Cout, C, 3, 0, s));

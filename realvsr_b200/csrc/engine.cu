@@ -212,13 +212,22 @@ int Engine::finalize(cudaStream_t s) {
                 }
                 RVSR_TRY(pack_weight_tapn(wsrc, pc.w_tapn, pc.Cout, pc.Cin, s));
             }
-            const size_t tb2 = (!is_dcn && !(is_om && mode != 2)) ? tc2_weight_bytes(pc.Cout, pc.Cin, pc.ks, mode) : 0;
+            const bool dcn64 = is_dcn && pc.Cout == 64 && pc.Cin == 64 && pc.ks == 3;  // fused pack: contraction weights, pair layout
+            const size_t tb2 = dcn64 ? tc2_weight_bytes(64, 64, 3, 0)
+                                     : ((!is_dcn && !(is_om && mode != 2)) ? tc2_weight_bytes(pc.Cout, pc.Cin, pc.ks, mode) : 0);
             if (tb2 > 0) {
                 if (pc.w_tc2 == nullptr) {
                     RVSR_CUDA(cudaMalloc(&pc.w_tc2, tb2));
                     owned_.push_back(pc.w_tc2);
                 }
-                RVSR_TRY(pack_weight_tc2(wsrc, pc.w_tc2, pc.Cout, pc.Cin, pc.ks, mode, s));
+                RVSR_TRY(pack_weight_tc2(wsrc, pc.w_tc2, pc.Cout, pc.Cin, pc.ks, dcn64 ? 0 : mode, s));
+            }
+            if (is_om && tc_pack_om_weight_bytes(pc.Cout, pc.Cin, cfg_.groups) > 0) {
+                if (pc.w_om_stream == nullptr) {
+                    RVSR_CUDA(cudaMalloc(&pc.w_om_stream, tc_pack_om_weight_bytes(pc.Cout, pc.Cin, cfg_.groups)));
+                    owned_.push_back(pc.w_om_stream);
+                }
+                RVSR_TRY(pack_weight_om_stream(wsrc, pc.w_om_stream, pc.Cout, pc.Cin, cfg_.groups, s));
             }
         }
     }
@@ -404,6 +413,24 @@ template <typename T> struct Plan {
         // thirds), last 9*dg = sigmoid(mask).
         const bool om24 = use_tc && pc->w_tc != nullptr && pom->w_tc != nullptr && x.C == 64 && pc->Cout == 64 &&
                           feat.C == 64 && (x.C / dg) % 8 == 0 && sizeof(T) == 2;
+        // ONE kernel for the whole pack (dcn_fused.cu): offsets / mask go from the offset conv's TMEM accumulator straight into
+        // the gather threads' registers.  RVSR_DCN_FUSED=0 keeps the round-1 kernel pair (OUT_OM24 tensor in HBM) for A/B runs.
+        if (om24 && pom->w_om_stream != nullptr && pc->w_tc2 != nullptr && pom->bias != nullptr) {
+            PackFusedOp f = {};
+            f.x = xmap != nullptr ? src_mapped(x, xmap) : src_of(x);
+            f.feat = feat.p; f.w_om = pom->w_om_stream; f.bias_om = pom->bias; f.w_dcn2 = pc->w_tc2; f.bias = pc->bias;
+            f.N = feat.N; f.H = x.H; f.W = x.W; f.Cout = pc->Cout; f.dg = dg; f.act = act;
+            if (tc_pack_fused_supported(f)) {
+                Act o = make(feat.N, pc->Cout, x.H, x.W);
+                if (dry || rc != RVSR_OK) return o;
+                f.out = o.p; f.out_image_stride = o.image_elems();
+                const double px = (double)feat.N * x.H * x.W;
+                const double flops = (2.0 * feat.C * pom->Cout * K + 2.0 * x.C * pc->Cout * K + 8.0 * x.C * K) * px;
+                const double bytes = px * (feat.C + x.C + pc->Cout) * sizeof(T);  // 22.1 MB per L1 image
+                launch("tc:dcn_pack_fused:" + name, flops, bytes, [&] { return launch_pack_fused(f, s); });
+                return o;
+            }
+        }
         Act om = conv(name + ".conv_offset_mask", {src_of(feat)}, feat.N, feat.H, feat.W, RVSR_ACT_NONE, 1,
                       om24 ? OUT_OM24 : OUT_PLANAR_F32, nullptr, 2 * dg * K);
         Act o = make(feat.N, pc->Cout, x.H, x.W);

@@ -41,6 +41,7 @@ struct PackedConv {
     void *w_tc = nullptr;     // fp16 UMMA layout (tc_kernels.cu) or null
     void *w_tc2 = nullptr;    // fp16 CTA-pair layout or null
     void *w_tapn = nullptr;   // fp16 taps-in-N layout (conv_last) or null
+    void *w_om_stream = nullptr;  // conv_offset_mask only: streamed layout of the fused pack kernel (dcn_fused.cu) or null
     float *bias = nullptr;    // fp32 [Cout]
     int Cout = 0, Cin = 0, ks = 0;
 };
@@ -142,6 +143,22 @@ int launch_conv_chain(const ChainLayerDesc *layers, int L, int N, int H, int W, 
 size_t tc_tapn_weight_bytes(int Cout, int Cin, int ks);   // conv_last "taps in N" kernel (Cout <= 3)
 int pack_weight_tapn(const float *w_oihw, void *dst, int Cout, int Cin, cudaStream_t s);
 int launch_conv_tapn(const ConvOp &op, const void *w_tapn, cudaStream_t s);
+// dcn_fused.cu: ModulatedDeformConvPack as ONE kernel (offset/mask conv -> TMEM -> gather -> contraction)
+struct PackFusedOp {
+    Src x;                 // sampled features [N][8][H][W][8] fp16 (optionally through an image -> slot map)
+    const void *feat;      // offset features, densely packed [N][8][H][W][8] fp16
+    const void *w_om;      // pack_weight_om_stream layout
+    const float *bias_om;  // [27 * dg] fp32, reference channel order
+    const void *w_dcn2;    // pack_weight_tc2 layout (CTA pair) of the 64 x 64 x 3 x 3 contraction weights
+    const float *bias;     // [64] or null
+    void *out;
+    long long out_image_stride;
+    int N, H, W, Cout, dg, act;
+};
+size_t tc_pack_om_weight_bytes(int Cout, int Cin, int dg);
+int pack_weight_om_stream(const float *w_oihw, void *dst, int Cout, int Cin, int dg, cudaStream_t s);
+bool tc_pack_fused_supported(const PackFusedOp &op);
+int launch_pack_fused(const PackFusedOp &op, cudaStream_t s);
 bool tc_dcn_supported(const DcnOp &op);
 int launch_dcn_tc(const DcnOp &op, cudaStream_t s);
 size_t tc_dcn_weight_bytes(int Cout, int C, int K);

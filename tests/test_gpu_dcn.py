@@ -271,9 +271,16 @@ def test_whole_network_gradients_match_reference_golden():
     net = net.to(DEV)
     x = synth_input(tuple(z["shape"]), int(z["xseed"])).to(DEV)
     gt = (synth_normal((2, 3, 96, 96), int(z["gtseed"]), std=0.3) + 0.5).to(DEV)
-    loss = torch.nn.functional.l1_loss(net(x), gt)
-    loss.backward()
-    assert abs(float(loss) - float(z["loss"])) < 1e-5
+    # the plain convolutions of the module path are cuDNN: TF32 (torch's default for convolutions, 10-bit mantissa) would
+    # put ~1e-2 on the small gradients of the offset branches -- strict fp32 for a 1e-3 comparison
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        loss = torch.nn.functional.l1_loss(net(x), gt)
+        loss.backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    assert abs(float(loss.detach()) - float(z["loss"])) < 1e-5
     worst = ("", 0.0)
     for name, p_ in net.named_parameters():
         e = rel_err(p_.grad.cpu(), torch.from_numpy(z["g:" + name]))

@@ -16,7 +16,7 @@ from realvsr_b200.archs import EDVR_arch as E
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-ENGINE_CASES = [c for c in EDVR_CASES if c != "edvr_predeblur"]
+ENGINE_CASES = [c for c in EDVR_CASES if c not in ("edvr_predeblur", "edvr_hr_in", "edvr_predeblur_hr_in")]  # stems: module path (tested below)
 
 
 def _base(c):
@@ -58,7 +58,7 @@ def test_engine_fp16_matches_golden(name):
     assert rel_err(y.float().cpu() - base, c["out"] - base) < 1e-2
 
 
-@pytest.mark.parametrize("name", ["edvr_tiny", "edvr_noup_3f", "edvr_predeblur"])
+@pytest.mark.parametrize("name", ["edvr_tiny", "edvr_noup_3f", "edvr_predeblur", "edvr_hr_in", "edvr_predeblur_hr_in"])
 def test_module_path_matches_golden(name):
     """nn.Conv2d modules + our DCN operator (the autograd-capable path)."""
     c = load_case(name)

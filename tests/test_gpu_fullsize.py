@@ -90,7 +90,12 @@ def test_fp16_engine_no_worse_than_reference_fp16_gpu_path(cfg2):
     taps = {}
     y_ref16 = ref_gpu.edvr_forward(cfg2["sd"], x.to(DEV).half(), groups=8, w_TSA=True, upsample=True, taps=taps).float().cpu()
     al_ref16 = taps["aligned"].reshape(nb * 5, 64, H, W).float().cpu()
-    y_ref32 = ref_gpu.edvr_forward(cfg2["sd"], x.to(DEV), groups=8, w_TSA=True, upsample=True).cpu()
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False   # strict fp32 convolutions for the reference's fp32 line
+    try:
+        y_ref32 = ref_gpu.edvr_forward(cfg2["sd"], x.to(DEV), groups=8, w_TSA=True, upsample=True).cpu()
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
     net = _engine_net(cfg2["sd"], half=True)
     y, al = _run(net, x, half=True)
     e_ours = rel_err(y - base, ref - base)
