@@ -105,8 +105,9 @@ int rvsr_conv2d_fwd(const void *x1, const void *x2, const void *weight, const vo
 typedef struct rvsr_edvr_config {
     int nf, nc, nframes, groups, front_RBs, back_RBs;
     int center;    /* -1 => nframes / 2 (EDVR_arch.py:217) */
-    int predeblur; /* must be 0 (RVSR_E_UNSUPPORTED otherwise; not used by any shipped YAML) */
-    int HR_in;     /* must be 0 */
+    int predeblur; /* 1: Predeblur_ResNet_Pyramid + conv_1x1 in front of the feature extraction (EDVR_arch.py:15-59, :226-227, :262-266) */
+    int HR_in;     /* 1: frames arrive at the OUTPUT resolution; stem conv_first_1 -> _2 (stride 2) -> _3 (stride 2), base = the
+                      centre frame itself (EDVR_arch.py:228-231, :267-274, :315-316).  Both are ignored when upsample = 0 (EDVR_NoUp) */
     int w_TSA;
     int upsample;  /* 1 = EDVR (x4 pixel-shuffle tail), 0 = EDVR_NoUp */
     int precision; /* RVSR_F32: fp32 storage, SIMT kernels (strict parity);
@@ -130,7 +131,7 @@ const char *rvsr_engine_weight_name(const rvsr_engine *e, int i);
 
 size_t rvsr_engine_workspace_bytes(const rvsr_engine *e, int B, int H, int W);
 /* x: [B, nframes, nc, H, W] NCHW DEVICE tensor of x_dtype; out: [B, nc, sH, sW] of out_dtype
- * (s = 4 for EDVR, 1 for EDVR_NoUp).  H and W must be multiples of 4. */
+ * (s = 4 for EDVR, 1 for EDVR_NoUp and for EDVR with HR_in).  H and W must be multiples of 4 (16 with HR_in). */
 int rvsr_engine_forward(rvsr_engine *e, const void *x, int x_dtype, void *out, int out_dtype,
                         int B, int H, int W, void *workspace, size_t workspace_bytes,
                         void *stream);

@@ -14,7 +14,7 @@ Two execution paths, both on this package's own CUDA kernels for the deformable 
 * engine path  -- inference (no autograd) on CUDA tensors: the whole forward is ONE call into
   the C++ engine (rvsr_engine_forward); weights are re-handed to the engine whenever a
   parameter changes.  This is the B200 hot path.
-* module path  -- training / autograd, or the rarely used predeblur / HR_in options: the same
+* module path  -- training / autograd: the same
   graph expressed with nn.Conv2d modules plus ``ModulatedDeformConvPack`` (our DCN operator
   with its own backward), structured like the reference so autograd works unchanged.
 
@@ -238,11 +238,10 @@ class _EDVRBase(nn.Module):
             return False
         # the grad check looks at the actual weight tensors (a DataParallel replica has no parameters())
         needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(t.requires_grad for _, t in self._named_weights()))
-        ok = (x.is_cuda and not self.is_predeblur and not self.HR_in and self.nf % 8 == 0
-              and x.dtype in (torch.float32, torch.float16) and not needs_grad)
+        ok = (x.is_cuda and self.nf % 8 == 0 and x.dtype in (torch.float32, torch.float16) and not needs_grad)
         if not ok and self.exec_path == "engine":
             raise RuntimeError("realvsr_b200: exec_path='engine' but this call needs the module path "
-                               "(autograd enabled, non-CUDA input, or predeblur/HR_in)")
+                               "(autograd enabled, non-CUDA input, or nf not a multiple of 8)")
         return ok
 
     def _weight_stamp(self):

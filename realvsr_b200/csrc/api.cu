@@ -411,10 +411,7 @@ int rvsr_engine_create(const rvsr_edvr_config *cfg, rvsr_engine **out) {
                    "engine_create: bad config");
     RVSR_CHECK_ARG(cfg->front_RBs >= 0 && cfg->back_RBs >= 0, "engine_create: bad block counts");
     RVSR_CHECK_ARG(cfg->precision == RVSR_F32 || cfg->precision == RVSR_F16, "engine_create: bad precision");
-    if (cfg->predeblur || cfg->HR_in) {
-        set_error("engine_create: predeblur / HR_in are not built (use the module path)");
-        return RVSR_E_UNSUPPORTED;
-    }
+    // predeblur / HR_in only exist in EDVR (upsample = 1); EDVR_NoUp stores and ignores them (EDVR_arch.py:335-339)
     if (cfg->nf % 8 != 0 || cfg->nf % cfg->groups != 0 || cfg->nframes > RVSR_MAX_SRC) {
         set_error("engine_create: needs nf %% 8 == 0, nf %% groups == 0, nframes <= %d", RVSR_MAX_SRC);
         return RVSR_E_UNSUPPORTED;

@@ -176,7 +176,8 @@ struct Src {
     const int *map;          // optional device table: image n reads image map[n] (feature-cache slots)
     int map_images;          // number of images addressable through `map` (for the TMA tensor map)
 };
-#define RVSR_MAX_SRC 7
+#define RVSR_MAX_SRC 7        // CUDA-core kernels; EDVR's widest concat is nframes <= 7 frames
+#define RVSR_MAX_SRC_TC 14    // tcgen05 kernels: a 128-channel source (nf = 128) is fed as two 64-channel sources
 
 enum OutMode {
     OUT_C8 = 0,           // channel-blocked, same resolution
@@ -200,7 +201,7 @@ struct FinalAdd {
 };
 
 struct ConvOp {
-    Src src[RVSR_MAX_SRC];
+    Src src[RVSR_MAX_SRC_TC];
     int nsrc;
     const float *w_simt;   // packed fp32 [sum chunks][taps][8][CoutPad]
     const void *w_tc;      // packed fp16 UMMA layout (tc kernels) or null
@@ -228,6 +229,7 @@ struct DcnOp {
     long long om24_image_stride;  // in 4-byte words
     const float *w_simt;   // packed like ConvOp
     const void *w_tc;
+    const void *w_tc_hi;   // nf = 128: contraction weights of input channels [64, 128) (w_tc: [0, 64)), pack_weight_dcn_tc_half
     const float *bias;
     void *out;
     long long out_image_stride;
@@ -262,7 +264,7 @@ int launch_frames_from_u8(const uint8_t *src, Tout *dst, int T, int C, int H, in
 template <typename Tin>
 int launch_frames_to_u8(const Tin *src, uint8_t *dst, int B, int H, int W, int mode, cudaStream_t s);
 template <typename T>
-int launch_upsample2x(const T *src, T *dst, int N, int C, int H, int W, float scale, cudaStream_t s);
+int launch_upsample2x(const T *src, T *dst, int N, int C, int H, int W, float scale, cudaStream_t s, const T *add = nullptr);
 template <typename T>
 int launch_pool_maxavg(const T *src, T *dst_max, T *dst_avg, int N, int C, int H, int W, cudaStream_t s);
 template <typename T>

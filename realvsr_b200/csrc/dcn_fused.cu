@@ -59,7 +59,7 @@ struct alignas(64) TcPackParams {
     int N, H, W, act;
     int tiles_x, tiles_y, num_tiles;
     TileDiv td;
-    int debug;               // RVSR_DCN_DEBUG timing experiments (results wrong): 1 no gather loads, 2 no offset-conv MMAs
+    int debug;               // RVSR_DCN_DEBUG timing experiments (results wrong): 1 no gather loads, 2 no offset-conv MMAs, 8 no MMA issue throttle
 };
 
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap *tmap, uint32_t bar_rank0, int c0, int c1) {
@@ -221,7 +221,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FP_THREADS, 1) dcn_p
                     for (int tap = 0; tap < 9; ++tap) {
                         // at most two taps (8 MMAs, ~0.5k cycles) queued: the contraction's MMAs share the tensor pipe in issue
                         // order, and the gather ring only buffers ~3k cycles of them
-                        if (wc >= 2) mbar_wait(BAR(B_WEMPTY + (wc - 2) % FP_SW), ((wc - 2) / FP_SW) & 1);
+                        if (wc >= 2 && !(p.debug & 8)) mbar_wait(BAR(B_WEMPTY + (wc - 2) % FP_SW), ((wc - 2) / FP_SW) & 1);
                         mbar_wait(BAR(B_WFULL + wst), wpar);
                         tc_fence_after();
                         const uint32_t a_lo = a_base + (uint32_t)(tap % 3) * (FP_COPY_BYTES >> 4) + (uint32_t)((tap / 3) * TC_TW);
@@ -304,11 +304,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FP_THREADS, 1) dcn_p
             const long long img = p.x_map != nullptr ? __ldg(p.x_map + n) : n;
             u.pl = reinterpret_cast<const uint4 *>(p.x + img * p.x_image_stride + (long long)(half * 4 + qq) * plane * 8);
             u.by = (float)(y - 1); u.bx = (float)(x - 1);
-            if (u.valid) {  // the undeformed 3x3 neighbourhood of this unit's feature plane into L1, several steps ahead
-                prefetch_l1(u.pl + (max(y - 1, 0) * p.W + x));
-                prefetch_l1(u.pl + (y * p.W + x));
-                prefetch_l1(u.pl + (min(y + 1, Hm1) * p.W + x));
-            }
+            // (an L1 prefetch of the undeformed neighbourhood here cost 4.5 %: the L1TEX pipe is the co-bottleneck of the gather)
             return u;
         };
         // this thread's 32 OM columns of half hf -> registers (+ bias, sigmoid on the mask columns); releases the columns.

@@ -67,7 +67,30 @@ Engine::Engine(const rvsr_edvr_config &cfg) : cfg_(cfg) {
     if (cfg_.center < 0) cfg_.center = cfg_.nframes / 2;
     const int nf = cfg_.nf, N = cfg_.nframes;
     // Same order as the reference modules register their parameters.
-    expect_conv("conv_first", nf, cfg_.nc, 3);
+    if (!cfg_.upsample) cfg_.predeblur = cfg_.HR_in = 0;  // EDVR_NoUp ignores both (EDVR_arch.py:335-339, :358-404)
+    if (cfg_.predeblur) {  // Predeblur_ResNet_Pyramid (EDVR_arch.py:15-59) + conv_1x1 (:226-227)
+        const std::string d = "pre_deblur.";
+        if (cfg_.HR_in) {
+            expect_conv(d + "conv_first_1", nf, 3, 3);
+            expect_conv(d + "conv_first_2", nf, nf, 3);
+            expect_conv(d + "conv_first_3", nf, nf, 3);
+        } else {
+            expect_conv(d + "conv_first", nf, 3, 3);
+        }
+        for (const char *n : {"RB_L1_1", "RB_L1_2", "RB_L1_3", "RB_L1_4", "RB_L1_5", "RB_L2_1", "RB_L2_2", "RB_L3_1"}) {
+            expect_conv(d + n + ".conv1", nf, nf, 3);
+            expect_conv(d + n + ".conv2", nf, nf, 3);
+        }
+        expect_conv(d + "deblur_L2_conv", nf, nf, 3);
+        expect_conv(d + "deblur_L3_conv", nf, nf, 3);
+        expect_conv("conv_1x1", nf, nf, 1);
+    } else if (cfg_.HR_in) {  // EDVR_arch.py:228-231
+        expect_conv("conv_first_1", nf, cfg_.nc, 3);
+        expect_conv("conv_first_2", nf, nf, 3);
+        expect_conv("conv_first_3", nf, nf, 3);
+    } else {
+        expect_conv("conv_first", nf, cfg_.nc, 3);
+    }
     for (int i = 0; i < cfg_.front_RBs; ++i) {
         expect_conv("feature_extraction." + std::to_string(i) + ".conv1", nf, nf, 3);
         expect_conv("feature_extraction." + std::to_string(i) + ".conv2", nf, nf, 3);
@@ -167,7 +190,8 @@ int Engine::finalize(cudaStream_t s) {
         pc.ks = (int)w.shape[2];
         pc.bias = raw_[base + ".bias"].dev;
         const float *wsrc = w.dev;
-        if (cfg_.precision == RVSR_F16 && base == "conv_first" && pc.Cin < 16) {
+        const bool first = base == "conv_first" || base == "conv_first_1" || base == "pre_deblur.conv_first" || base == "pre_deblur.conv_first_1";
+        if (cfg_.precision == RVSR_F16 && first && pc.Cin < 16) {
             // tensor-core K granularity is 16 channels: the LQ frames are stored zero-padded to 16
             // channels and conv_first's weight gets matching zero input channels
             float *padded = nullptr;
@@ -189,9 +213,9 @@ int Engine::finalize(cudaStream_t s) {
             const bool is_dcn = base.size() > 8 && base.compare(base.size() - 8, 8, "_dcnpack") == 0;
             const bool shuffle = (base == "upconv1" || base == "upconv2");
             const bool is_om = base.size() > 17 && base.compare(base.size() - 17, 17, ".conv_offset_mask") == 0;
-            // the tcgen05 DCN kernel wants offsets/mask in OUT_OM24 order (needs nf == 64, whole 8-channel
+            // the tcgen05 DCN kernels want offsets/mask in OUT_OM24 order (nf == 64 or 128, whole 8-channel
             // blocks per deformable group); otherwise the offset conv stays planar on the CUDA-core kernel
-            const int mode = shuffle ? 1 : ((is_om && tc_dcn_weight_bytes(cfg_.nf, cfg_.nf, 9) > 0 &&
+            const int mode = shuffle ? 1 : ((is_om && (cfg_.nf == 64 || cfg_.nf == 128) &&
                                              (cfg_.nf / cfg_.groups) % 8 == 0) ? 2 : 0);
             const size_t tb = is_dcn ? tc_dcn_weight_bytes(pc.Cout, pc.Cin, pc.ks * pc.ks)
                                      : ((is_om && mode != 2) ? 0 : tc_conv_weight_bytes(pc.Cout, pc.Cin, pc.ks, mode));
@@ -228,6 +252,59 @@ int Engine::finalize(cudaStream_t s) {
                     owned_.push_back(pc.w_om_stream);
                 }
                 RVSR_TRY(pack_weight_om_stream(wsrc, pc.w_om_stream, pc.Cout, pc.Cin, cfg_.groups, s));
+            }
+        }
+    }
+    // nf = 128 (BASELINE cfg4): the weights-resident tcgen05 kernels hold at most a 64-wide output tile of a 256-channel
+    // contraction per CTA pair, so a 128-output convolution runs as two launches over the two halves of its output
+    // channels ("#o0" / "#o1": rows [0, 64) / [64, 128) of the OIHW weight, contiguous), each reading its 128-channel
+    // sources as pairs of 64-channel sources (Plan::conv).
+    if (cfg_.precision == RVSR_F16) {
+        for (const auto &n : names_) {
+            const size_t pos = n.rfind(".weight");
+            if (pos == std::string::npos || pos + 7 != n.size()) continue;
+            const std::string base = n.substr(0, pos);
+            const RawWeight &w = raw_[n];
+            const bool is_dcn = base.size() > 8 && base.compare(base.size() - 8, 8, "_dcnpack") == 0;
+            if (w.shape.size() != 4 || w.shape[0] != 128 || base == "upconv1" || base == "upconv2") continue;
+            const PackedConv &full = packed_[base];   // Cin as packed (conv_first: padded to 16)
+            const int Cin = full.Cin, ks = full.ks, KK = ks * ks;
+            if (Cin % 16 != 0) continue;
+            if (is_dcn) {
+                if (Cin != 128 || ks != 3) continue;
+                for (int h = 0; h < 2; ++h) {  // "#i0" / "#i1": input channels [0, 64) / [64, 128), all 128 outputs
+                    PackedConv &pc = packed_[base + (h == 0 ? "#i0" : "#i1")];
+                    pc.Cout = 128; pc.Cin = 64; pc.ks = 3; pc.bias = full.bias;
+                    if (pc.w_tc == nullptr) {
+                        RVSR_CUDA(cudaMalloc(&pc.w_tc, tc_dcn_half_weight_bytes()));
+                        owned_.push_back(pc.w_tc);
+                    }
+                    RVSR_TRY(pack_weight_dcn_tc_half(w.dev, pc.w_tc, h, s));
+                }
+                continue;
+            }
+            const float *wsrc = w.dev;
+            if (Cin != (int)w.shape[1]) {  // conv_first: the zero-padded copy made above is not kept; rebuild it
+                float *padded = nullptr;
+                RVSR_CUDA(cudaMalloc(&padded, (size_t)128 * Cin * KK * sizeof(float)));
+                owned_.push_back(padded);
+                RVSR_TRY(pad_weight_cin(w.dev, padded, 128, (int)w.shape[1], Cin, KK, s));
+                wsrc = padded;
+            }
+            for (int h = 0; h < 2; ++h) {
+                PackedConv &pc = packed_[base + (h == 0 ? "#o0" : "#o1")];
+                pc.Cout = 64; pc.Cin = Cin; pc.ks = ks;
+                pc.bias = full.bias != nullptr ? full.bias + h * 64 : nullptr;
+                const float *wh = wsrc + (size_t)h * 64 * Cin * KK;
+                const size_t tb = tc_conv_weight_bytes(64, Cin, ks, 0), tb2 = tc2_weight_bytes(64, Cin, ks, 0);
+                if (tb > 0) {
+                    if (pc.w_tc == nullptr) { RVSR_CUDA(cudaMalloc(&pc.w_tc, tb)); owned_.push_back(pc.w_tc); }
+                    RVSR_TRY(pack_weight_tc(wh, pc.w_tc, 64, Cin, ks, 0, s));
+                }
+                if (tb2 > 0) {
+                    if (pc.w_tc2 == nullptr) { RVSR_CUDA(cudaMalloc(&pc.w_tc2, tb2)); owned_.push_back(pc.w_tc2); }
+                    RVSR_TRY(pack_weight_tc2(wh, pc.w_tc2, 64, Cin, ks, 0, s));
+                }
             }
         }
     }
@@ -360,7 +437,18 @@ template <typename T> struct Plan {
         if (dry || rc != RVSR_OK) return o;
         ConvOp op = {};
         int cin = 0;
-        for (const Src &sr : srcs) { op.src[op.nsrc++] = sr; cin += sr.C; }
+        for (const Src &sr : srcs) {
+            cin += sr.C;
+            if (use_tc && sizeof(T) == 2 && sr.C == 128 && op.nsrc + 2 <= RVSR_MAX_SRC_TC) {
+                // tcgen05 kernels stage at most 64 channels per source: a 128-channel tensor = two sources, the second 8 planes in
+                Src a = sr, b = sr;
+                a.C = b.C = 64;
+                b.ptr = reinterpret_cast<const T *>(sr.ptr) + (long long)64 * H * W;
+                op.src[op.nsrc++] = a; op.src[op.nsrc++] = b;
+            } else if (op.nsrc < RVSR_MAX_SRC_TC) {
+                op.src[op.nsrc++] = sr;
+            }
+        }
         if (cin != pc->Cin) {
             set_error("engine: %s expects %d input channels, got %d", name.c_str(), pc->Cin, cin);
             rc = RVSR_E_INVALID;
@@ -383,7 +471,34 @@ template <typename T> struct Plan {
                               : out_mode == OUT_OM24     ? px * (pc->Cout / 27) * 96.0
                                                          : px * pc->Cout * sizeof(T);
         const double bytes = (double)N * H * W * cin * sizeof(T) + obytes + (residual ? obytes : 0);
-        const bool tc = use_tc && tc_conv_supported(op);
+        // 128 output channels: two 64-wide launches on the "#o0" / "#o1" half packs (see finalize)
+        if (use_tc && sizeof(T) == 2 && pc->Cout == 128 && out_mode == OUT_C8 && packed.count(name + "#o0") && packed.count(name + "#o1")) {
+            bool ok = true;
+            ConvOp hv[2];
+            for (int h = 0; h < 2 && ok; ++h) {
+                const PackedConv &ph = packed.find(name + (h == 0 ? "#o0" : "#o1"))->second;
+                hv[h] = op;
+                hv[h].w_simt = nullptr; hv[h].w_tc = ph.w_tc; hv[h].w_tc2 = ph.w_tc2; hv[h].bias = ph.bias;
+                hv[h].Cout = 64;
+                hv[h].out = reinterpret_cast<T *>(o.p) + (long long)h * 64 * Ho * Wo;
+                if (residual != nullptr) hv[h].residual = reinterpret_cast<const T *>(residual->p) + (long long)h * 64 * Ho * Wo;
+                ok = tc_conv_supported(hv[h]);
+            }
+            if (ok) {
+                const double px2 = (double)N * Ho * Wo;
+                for (int h = 0; h < 2; ++h)
+                    launch(std::string("tc:conv") + std::to_string(pc->ks) + "x" + std::to_string(pc->ks) + "_co128h:" + name,
+                           (flops_alg >= 0 ? flops_alg : 2.0 * cin * pc->Cout * pc->ks * pc->ks * px2) / 2,
+                           ((double)N * H * W * cin * sizeof(T)) + (px2 * 64 * sizeof(T)) * (residual ? 2 : 1),
+                           [&] { return launch_conv_tc(hv[h], s); });
+                return o;
+            }
+        }
+        const bool tc = use_tc && op.nsrc <= RVSR_MAX_SRC_TC && tc_conv_supported(op);
+        if (!tc) {  // the CUDA-core kernel takes whole sources (<= 7): undo the 64-channel split
+            op.nsrc = 0;
+            for (const Src &sr : srcs) op.src[op.nsrc++] = sr;
+        }
         if (tc_only && !tc) {
             set_error("engine: %s needs the tcgen05 conv kernel", name.c_str());
             rc = RVSR_E_STATE;
@@ -411,8 +526,11 @@ template <typename T> struct Plan {
         // tcgen05 pair: offset conv writes OUT_OM24, gather kernel consumes it.  Otherwise planar fp32
         // [N][27*dg][H][W]: first 18*dg = offsets (o1|o2 of chunk(3) concatenated back = the first two
         // thirds), last 9*dg = sigmoid(mask).
-        const bool om24 = use_tc && pc->w_tc != nullptr && pom->w_tc != nullptr && x.C == 64 && pc->Cout == 64 &&
-                          feat.C == 64 && (x.C / dg) % 8 == 0 && sizeof(T) == 2;
+        const PackedConv *pi0 = packed.count(name + "#i0") ? &packed.find(name + "#i0")->second : nullptr;   // nf = 128 half packs
+        const PackedConv *pi1 = packed.count(name + "#i1") ? &packed.find(name + "#i1")->second : nullptr;
+        const bool c128 = x.C == 128 && pc->Cout == 128 && feat.C == 128 && pi0 != nullptr && pi1 != nullptr;
+        const bool om24 = use_tc && pom->w_tc != nullptr && sizeof(T) == 2 && (x.C / dg) % 8 == 0 &&
+                          ((pc->w_tc != nullptr && x.C == 64 && pc->Cout == 64 && feat.C == 64) || c128);
         // ONE kernel for the whole pack (dcn_fused.cu): offsets / mask go from the offset conv's TMEM accumulator straight into
         // the gather threads' registers.  RVSR_DCN_FUSED=0 keeps the round-1 kernel pair (OUT_OM24 tensor in HBM) for A/B runs.
         if (om24 && pom->w_om_stream != nullptr && pc->w_tc2 != nullptr && pom->bias != nullptr) {
@@ -445,7 +563,7 @@ template <typename T> struct Plan {
             op.mask = op.offset + (long long)2 * dg * K * x.H * x.W;
             op.offset_image_stride = op.mask_image_stride = (long long)3 * dg * K * x.H * x.W;
         }
-        op.w_simt = pc->w_simt; op.w_tc = pc->w_tc; op.bias = pc->bias;
+        op.w_simt = pc->w_simt; op.w_tc = c128 ? pi0->w_tc : pc->w_tc; op.w_tc_hi = c128 ? pi1->w_tc : nullptr; op.bias = pc->bias;
         op.out = o.p; op.out_image_stride = o.image_elems();
         op.N = feat.N; op.H = x.H; op.W = x.W; op.Cout = pc->Cout;
         op.kh = op.kw = 3; op.stride = 1; op.pad = 1; op.dil = 1; op.dg = dg;
@@ -489,6 +607,19 @@ template <typename T> struct Plan {
                         2.0 * 128 * 64 * 9 * (double)NB_ * H * W);
         }
         return conv(name, {a, ref_all}, NB_, H, W, act);
+    }
+    // one ResidualBlock_noBN by its full prefix (Predeblur pyramid): x + conv2(relu(conv1(x)))
+    Act resblock1(const std::string &b, const Act &cur) {
+        Act t = conv(b + ".conv1", {src_of(cur)}, cur.N, cur.H, cur.W, RVSR_ACT_RELU);
+        return conv(b + ".conv2", {src_of(t)}, cur.N, cur.H, cur.W, RVSR_ACT_NONE, 1, OUT_C8, &cur);
+    }
+    // a + up2(b)  (bilinear x2, align_corners=False), one pass
+    Act up2_add(const Act &b, const Act &a) {
+        Act o = make(b.N, b.C, 2 * b.H, 2 * b.W);
+        if (!dry && rc == RVSR_OK)
+            launch("glue:upsample2x_add:", 0, (double)b.elems() * sizeof(T) * 9, [&] {
+                return launch_upsample2x<T>((const T *)b.p, (T *)o.p, b.N, b.C, b.H, b.W, 1.f, s, (const T *)a.p); });
+        return o;
     }
     Act resblocks(const std::string &prefix, int count, Act cur) {
         // fp16 / 64 channels / enough tiles: the whole run (2 * count convolutions) is ONE persistent launch with
@@ -539,9 +670,12 @@ template <typename T> struct Plan {
 }  // namespace
 
 template <typename T>
-int Engine::run(Arena &ar, bool dry, const void *x, int x_dtype, void *out, int out_dtype, int B, int H, int W,
+int Engine::run(Arena &ar, bool dry, const void *x, int x_dtype, void *out, int out_dtype, int B, int Hin, int Win,
                 cudaStream_t s, const CacheArgs *ca) {
     const int nf = cfg_.nf, N = cfg_.nframes, nc = cfg_.nc, dg = cfg_.groups, ctr = cfg_.center;
+    // HR_in: frames arrive at the OUTPUT resolution, two stride-2 convolutions bring the features to 1/4 (EDVR_arch.py:267-274)
+    const bool hr = cfg_.HR_in != 0;
+    const int H = hr ? Hin / 4 : Hin, W = hr ? Win / 4 : Win;
     const int LR = RVSR_ACT_LRELU, NONE = RVSR_ACT_NONE;
     // RVSR_DISABLE_TC=1 routes the fp16 engine through the CUDA-core kernels (debug / cross-check)
     static const bool tc_off = getenv("RVSR_DISABLE_TC") != nullptr && getenv("RVSR_DISABLE_TC")[0] == '1';
@@ -560,14 +694,33 @@ int Engine::run(Arena &ar, bool dry, const void *x, int x_dtype, void *out, int 
     if (!cached) {
         // ---- LQ frames -> channel-blocked
         const int nc_store = (cfg_.precision == RVSR_F16 && nc < 16) ? 16 : nc;  // see finalize(): K granularity
-        Act xin = P.make(NB, nc_store, H, W);
+        Act xin = P.make(NB, nc_store, Hin, Win);
         if (!dry && P.rc == RVSR_OK)
             P.launch("glue:pack_input:", 0, (double)xin.elems() * sizeof(T) * 1.4, [&] {
                 return x_dtype == RVSR_F32
-                           ? launch_pack_nchw<T, float>((const float *)x, (T *)xin.p, NB, nc, H, W, s, nc_store)
-                           : launch_pack_nchw<T, __half>((const __half *)x, (T *)xin.p, NB, nc, H, W, s, nc_store); });
-        // ---- per-frame feature pyramid (EDVR_arch.py:276-283)
-        L1 = P.conv("conv_first", {PT::src_of(xin)}, NB, H, W, LR);
+                           ? launch_pack_nchw<T, float>((const float *)x, (T *)xin.p, NB, nc, Hin, Win, s, nc_store)
+                           : launch_pack_nchw<T, __half>((const __half *)x, (T *)xin.p, NB, nc, Hin, Win, s, nc_store); });
+        // ---- per-frame feature pyramid (EDVR_arch.py:262-283)
+        auto stem = [&](const std::string &pre) {  // conv_first, or the HR_in stem conv_first_1 -> _2 (s2) -> _3 (s2)
+            if (!hr) return P.conv(pre + "conv_first", {PT::src_of(xin)}, NB, Hin, Win, LR);
+            Act a = P.conv(pre + "conv_first_1", {PT::src_of(xin)}, NB, Hin, Win, LR);
+            a = P.conv(pre + "conv_first_2", {PT::src_of(a)}, NB, Hin, Win, LR, 2);
+            return P.conv(pre + "conv_first_3", {PT::src_of(a)}, NB, a.H, a.W, LR, 2);
+        };
+        if (cfg_.predeblur) {  // Predeblur_ResNet_Pyramid.forward (EDVR_arch.py:43-59), then conv_1x1 without activation (:265)
+            const std::string d = "pre_deblur.";
+            Act l1 = stem(d);
+            Act l2 = P.conv(d + "deblur_L2_conv", {PT::src_of(l1)}, NB, H, W, LR, 2);
+            Act l3 = P.conv(d + "deblur_L3_conv", {PT::src_of(l2)}, NB, l2.H, l2.W, LR, 2);
+            l3 = P.resblock1(d + "RB_L3_1", l3);
+            l2 = P.up2_add(l3, P.resblock1(d + "RB_L2_1", l2));
+            l2 = P.resblock1(d + "RB_L2_2", l2);
+            l1 = P.up2_add(l2, P.resblock1(d + "RB_L1_2", P.resblock1(d + "RB_L1_1", l1)));
+            for (const char *n : {"RB_L1_3", "RB_L1_4", "RB_L1_5"}) l1 = P.resblock1(d + n, l1);
+            L1 = P.conv("conv_1x1", {PT::src_of(l1)}, NB, H, W, NONE);
+        } else {
+            L1 = stem("");
+        }
         L1 = P.resblocks("feature_extraction", cfg_.front_RBs, L1);
         L2 = P.conv("fea_L2_conv1", {PT::src_of(L1)}, NB, H, W, LR, 2);
         L2 = P.conv("fea_L2_conv2", {PT::src_of(L2)}, NB, L2.H, L2.W, LR);
@@ -704,11 +857,11 @@ int Engine::run(Arena &ar, bool dry, const void *x, int x_dtype, void *out, int 
 
     // ---- reconstruction (EDVR_arch.py:310-319 / :398-403)
     Act r = P.resblocks("recon_trunk", cfg_.back_RBs, fused);
-    int scale = 1;
+    int scale = 1;  // output resolution / resolution of the frames the base is taken from
     if (cfg_.upsample) {
         r = P.conv("upconv1", {PT::src_of(r)}, B, H, W, LR, 1, OUT_C8_SHUFFLE2);
         r = P.conv("upconv2", {PT::src_of(r)}, B, r.H, r.W, LR, 1, OUT_C8_SHUFFLE2);
-        scale = 4;
+        scale = hr ? 1 : 4;  // HR_in: base = the centre frame itself (EDVR_arch.py:315-316)
     }
     r = P.conv("HRconv", {PT::src_of(r)}, B, r.H, r.W, LR);
     // conv_last + base frame: one tcgen05 launch that writes the NCHW result (OUT_FINAL) when the shape allows it
@@ -731,14 +884,14 @@ int Engine::run(Arena &ar, bool dry, const void *x, int x_dtype, void *out, int 
                 if (tapn_on && pc->w_tapn != nullptr) {
                     const double px = (double)B * r.H * r.W;
                     P.launch("tc:conv3x3_tapn_co" + std::to_string(pc->Cout) + ":conv_last", 2.0 * r.C * pc->Cout * 9 * px,
-                             px * r.C * sizeof(T) + px * nc * (out_dtype == RVSR_F32 ? 4 : 2) + (double)B * nc * H * W * (x_dtype == RVSR_F32 ? 4 : 2),
+                             px * r.C * sizeof(T) + px * nc * (out_dtype == RVSR_F32 ? 4 : 2) + (double)B * nc * Hin * Win * (x_dtype == RVSR_F32 ? 4 : 2),
                              [&] { return launch_conv_tapn(op, pc->w_tapn, s); });
                 } else if (!tc_conv_supported(op)) {
                     fused_final = false;
                 } else {
                     const double px = (double)B * r.H * r.W;
                     P.launch("tc:conv3x3_final_co" + std::to_string(pc->Cout) + ":conv_last", 2.0 * r.C * pc->Cout * 9 * px,
-                             px * r.C * sizeof(T) + px * nc * (out_dtype == RVSR_F32 ? 4 : 2) + (double)B * nc * H * W * (x_dtype == RVSR_F32 ? 4 : 2),
+                             px * r.C * sizeof(T) + px * nc * (out_dtype == RVSR_F32 ? 4 : 2) + (double)B * nc * Hin * Win * (x_dtype == RVSR_F32 ? 4 : 2),
                              [&] { return launch_conv_tc(op, s); });
                 }
             }
@@ -753,12 +906,12 @@ int Engine::run(Arena &ar, bool dry, const void *x, int x_dtype, void *out, int 
         const T *lp = (const T *)last.p;
         P.launch("glue:final_add_base:", 0, (double)last.elems() * sizeof(T) + (double)B * nc * last.H * last.W * 4, [&] {
             if (x_dtype == RVSR_F32 && out_dtype == RVSR_F32)
-                return launch_final_add<T, float, float>(lp, (const float *)x, (float *)out, B, N, ctr, nc, H, W, scale, s, map_ctr);
+                return launch_final_add<T, float, float>(lp, (const float *)x, (float *)out, B, N, ctr, nc, Hin, Win, scale, s, map_ctr);
             if (x_dtype == RVSR_F32)
-                return launch_final_add<T, float, __half>(lp, (const float *)x, (__half *)out, B, N, ctr, nc, H, W, scale, s, map_ctr);
+                return launch_final_add<T, float, __half>(lp, (const float *)x, (__half *)out, B, N, ctr, nc, Hin, Win, scale, s, map_ctr);
             if (out_dtype == RVSR_F32)
-                return launch_final_add<T, __half, float>(lp, (const __half *)x, (float *)out, B, N, ctr, nc, H, W, scale, s, map_ctr);
-            return launch_final_add<T, __half, __half>(lp, (const __half *)x, (__half *)out, B, N, ctr, nc, H, W, scale, s, map_ctr);
+                return launch_final_add<T, __half, float>(lp, (const __half *)x, (float *)out, B, N, ctr, nc, Hin, Win, scale, s, map_ctr);
+            return launch_final_add<T, __half, __half>(lp, (const __half *)x, (__half *)out, B, N, ctr, nc, Hin, Win, scale, s, map_ctr);
         });
     }
     if (!dry && !cached) {
@@ -802,8 +955,8 @@ int Engine::prof_collect() {
 
 static int check_dims(const rvsr_edvr_config &c, int B, int H, int W) {
     RVSR_CHECK_ARG(B >= 0 && H > 0 && W > 0, "engine: bad input size B=%d H=%d W=%d", B, H, W);
-    RVSR_CHECK_ARG(H % 4 == 0 && W % 4 == 0, "engine: H and W must be multiples of 4 (got %dx%d)", H, W);
-    (void)c;
+    const int m = c.HR_in && c.upsample ? 16 : 4;  // two stride-2 levels (+ two more in the HR_in stem)
+    RVSR_CHECK_ARG(H % m == 0 && W % m == 0, "engine: H and W must be multiples of %d (got %dx%d)", m, H, W);
     return RVSR_OK;
 }
 
@@ -845,7 +998,8 @@ int Engine::forward(const void *x, int x_dtype, void *out, int out_dtype, int B,
 
 // ---------------------------------------------------------------- sliding-window feature cache
 size_t Engine::cache_bytes(int n_slots, int H, int W) const {
-    if (n_slots <= 0 || H <= 0 || W <= 0 || H % 4 || W % 4) return 0;
+    if (n_slots <= 0 || check_dims(cfg_, 0, H, W) != RVSR_OK) return 0;
+    if (cfg_.HR_in && cfg_.upsample) { H /= 4; W /= 4; }  // the cache holds features: 1/4 of the HR_in frame size
     const size_t es = cfg_.precision == RVSR_F16 ? 2 : 4, c8 = (size_t)cdiv(cfg_.nf, 8) * 8;
     return (size_t)n_slots * c8 * es * ((size_t)H * W + (size_t)(H / 2) * (W / 2) + (size_t)(H / 4) * (W / 4));
 }

@@ -163,5 +163,7 @@ bool tc_dcn_supported(const DcnOp &op);
 int launch_dcn_tc(const DcnOp &op, cudaStream_t s);
 size_t tc_dcn_weight_bytes(int Cout, int C, int K);
 int pack_weight_dcn_tc(const float *w_oihw, void *dst, int Cout, int C, int K, cudaStream_t s);
+size_t tc_dcn_half_weight_bytes();  // nf = 128: one input-channel half of the 128 x 128 x 3 x 3 contraction weights
+int pack_weight_dcn_tc_half(const float *w_oihw, void *dst, int h, cudaStream_t s);
 
 }  // namespace rvsr

@@ -392,7 +392,7 @@ int launch_fill_f32(float *dst, float v, long long n, cudaStream_t s) {
 // (k-1, k) with weights (0.25, 0.75), output 2k+1 reads (k, k+1) with (0.75, 0.25); indices clamp at the borders
 // (EDVR_arch.py:111-112, :120-121 multiply the upsampled OFFSETS by 2 -- `scale`).  grid.y = (image, block) plane.
 template <typename T>
-__global__ void upsample2x_kernel(const T *__restrict__ src, T *__restrict__ dst, int H, int W, float scale) {
+__global__ void upsample2x_kernel(const T *__restrict__ src, T *__restrict__ dst, int H, int W, float scale, const T *__restrict__ add) {
     pdl_trigger();
     pdl_wait();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -416,33 +416,44 @@ __global__ void upsample2x_kernel(const T *__restrict__ src, T *__restrict__ dst
             hr[r][k] = 0.75f * b[k] + 0.25f * c[k];
         }
     }
-    T *o = dst + (pl * (2 * H) + 2 * y) * (long long)(2 * W) * 8 + (long long)(2 * x) * 8;
-    float t[8];
+    const long long o0 = (pl * (2 * H) + 2 * y) * (long long)(2 * W) * 8 + (long long)(2 * x) * 8;
+    T *o = dst + o0;
+    const T *ad = add != nullptr ? add + o0 : nullptr;  // optional: dst = scale * up(src) + add (Predeblur pyramid, EDVR_arch.py:53-57)
+    float t[8], u[8];
+    auto put = [&](long long off) {
+        if (ad != nullptr) {
+            load8<T>(ad + off, u);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t[k] += u[k];
+        }
+        store8<T>(o + off, t);
+    };
 #pragma unroll
     for (int k = 0; k < 8; ++k) t[k] = scale * (0.25f * hl[0][k] + 0.75f * hl[1][k]);
-    store8<T>(o, t);
+    put(0);
 #pragma unroll
     for (int k = 0; k < 8; ++k) t[k] = scale * (0.25f * hr[0][k] + 0.75f * hr[1][k]);
-    store8<T>(o + 8, t);
-    o += (long long)(2 * W) * 8;
+    put(8);
+    const long long row = (long long)(2 * W) * 8;
 #pragma unroll
     for (int k = 0; k < 8; ++k) t[k] = scale * (0.75f * hl[1][k] + 0.25f * hl[2][k]);
-    store8<T>(o, t);
+    put(row);
 #pragma unroll
     for (int k = 0; k < 8; ++k) t[k] = scale * (0.75f * hr[1][k] + 0.25f * hr[2][k]);
-    store8<T>(o + 8, t);
+    put(row + 8);
 }
+
 template <typename T>
-int launch_upsample2x(const T *src, T *dst, int N, int C, int H, int W, float scale, cudaStream_t s) {
+int launch_upsample2x(const T *src, T *dst, int N, int C, int H, int W, float scale, cudaStream_t s, const T *add) {
     const int planes = N * ((C + 7) / 8);
     if (planes == 0 || H == 0 || W == 0) return RVSR_OK;
     RVSR_CHECK_ARG(planes <= 65535, "upsample2x: too many (image, channel block) planes: %d", planes);
-    launch_k(upsample2x_kernel<T>, dim3((H * W + 127) / 128, planes), dim3(128), 0, s, src, dst, H, W, scale);
+    launch_k(upsample2x_kernel<T>, dim3((H * W + 127) / 128, planes), dim3(128), 0, s, src, dst, H, W, scale, add);
     RVSR_LAUNCH_CHECK();
     return RVSR_OK;
 }
-template int launch_upsample2x<float>(const float *, float *, int, int, int, int, float, cudaStream_t);
-template int launch_upsample2x<__half>(const __half *, __half *, int, int, int, int, float, cudaStream_t);
+template int launch_upsample2x<float>(const float *, float *, int, int, int, int, float, cudaStream_t, const float *);
+template int launch_upsample2x<__half>(const __half *, __half *, int, int, int, int, float, cudaStream_t, const __half *);
 
 // ---------------------------------------------------------------- MaxPool2d(3,2,1) + AvgPool2d(3,2,1) in one pass
 // max pads with -inf; avg divides by 9 always (count_include_pad=True) -- EDVR_arch.py:154-155.

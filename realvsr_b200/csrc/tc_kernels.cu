@@ -392,10 +392,10 @@ __device__ __forceinline__ void epi_c8_fast(const float *bias_s, __half *out, lo
 
 // ---------------------------------------------------------------- convolution
 struct alignas(64) TcConvParams {
-    CUtensorMap tmap[RVSR_MAX_SRC];
-    int src_pstride[RVSR_MAX_SRC];  // channel-block planes between consecutive images of a source
-    int src_frames[RVSR_MAX_SRC], src_fixed[RVSR_MAX_SRC];
-    const int *src_map[RVSR_MAX_SRC];  // optional image -> slot tables (feature cache)
+    CUtensorMap tmap[RVSR_MAX_SRC_TC];
+    int src_pstride[RVSR_MAX_SRC_TC];  // channel-block planes between consecutive images of a source
+    int src_frames[RVSR_MAX_SRC_TC], src_fixed[RVSR_MAX_SRC_TC];
+    const int *src_map[RVSR_MAX_SRC_TC];  // optional image -> slot tables (feature cache)
     int nsrc, C8s, nstages;
     const __half *w;  // [pass][tap][Q][NT][8]
     const float *bias;
@@ -653,11 +653,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 //                        remote arrive) + both CTAs' TMA (cp.async.bulk.tensor ... cta_group::2) complete_tx
 //   EMPTY(stage), TFULL(acc)  tcgen05.commit ... multicast::cluster -> the same barrier in BOTH CTAs
 //   TEMPTY(acc)          leader's barrier, arrivals from the epilogue warps of both CTAs (peer: remote arrive)
-template <int KS, int NT>
+// S2 = true: stride-2 convolution as a REAL implicit GEMM (fea_L2/L3_conv1, the HR_in stem, the predeblur pyramid:
+// EDVR_arch.py:279,:282,:229-231,:31-32).  out(y, x) = sum in(2y + dy - 1, 2x + dx - 1): split the input into its four
+// (row parity p, column parity q) phase images; tap dy reads phase p = 1, 0, 1 at phase row y - 1, y, y, and the same for dx.
+// The four phase tiles (5 rows x 32 pixels each) come straight from the un-split tensor through a 4-D tensor map with
+// element strides {1, 2, 2, 1}; each tap is then a view of one phase tile shifted by (0 | 1, 0 | 1), exactly like the
+// stride-1 taps.  Kernel geometry (H, W, tiles) is that of the OUTPUT.  (Round 1 computed these layers at full resolution
+// and stored every other pixel: 4x the MMAs.)
+template <int KS, int NT, bool S2 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_tc2_kernel(const __grid_constant__ TcConvParams p) {
     constexpr int NH2 = NT / 2;
-    constexpr int KK = KS * KS, PAD = KS / 2, VALID = TC_TW - (KS - 1), HALO_ROWS = TC_ROWS + KS - 1;
+    constexpr int KK = KS * KS, PAD = KS / 2, VALID = TC_TW - (KS - 1), HALO_ROWS = S2 ? TC_ROWS + 1 : TC_ROWS + KS - 1;
     constexpr int PLANE_BYTES = HALO_ROWS * TC_TW * 16;
+    static_assert(!S2 || (KS == 3 && NT == 64), "stride-2 path: 3x3, 64-wide tiles");
     // one MMA instruction covers two tiles here, so two issuers suffice for the wide tiles, which leaves room for
     // 4 accumulators (all 512 TMEM columns) and two epilogue groups (the OM24 / pixel-shuffle epilogues are the
     // slower side of those kernels)
@@ -667,7 +675,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
     extern __shared__ __align__(1024) uint8_t smem[];
     const int Q = p.nsrc * p.C8s;
     const uint32_t w_bytes = (uint32_t)Q * KK * NH2 * 16;  // this CTA's half of the weights
-    const uint32_t stage_bytes = (uint32_t)p.C8s * PLANE_BYTES;
+    const uint32_t phase_bytes = (uint32_t)p.C8s * PLANE_BYTES;                // S2: one phase tile (all channel blocks)
+    const uint32_t stage_bytes = S2 ? 4 * phase_bytes : phase_bytes;
     uint8_t *w_s = smem;
     uint8_t *stage_s = smem + w_bytes;
     float *bias_s = reinterpret_cast<float *>(stage_s + (size_t)p.nstages * stage_bytes + 128);
@@ -741,8 +750,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
                         mbar_arrive_cluster(full0);
                     const int img = p.src_map[s] != nullptr ? __ldg(p.src_map[s] + n)
                                     : (p.src_fixed[s] >= 0 ? (n / p.src_frames[s]) * p.src_frames[s] + p.src_fixed[s] : n);
-                    tma_load_3d_2sm(smem_u32(stage_s + (size_t)st * stage_bytes), &p.tmap[s], full0,
-                                    (tx * VALID - PAD) * 8, ty * TC_ROWS - PAD, img * p.src_pstride[s]);
+                    if (S2) {
+#pragma unroll
+                        for (int ph = 0; ph < 4; ++ph)  // phase (row parity ph >> 1, column parity ph & 1), origin one phase pixel up / left
+                            tma_load_4d_2sm(smem_u32(stage_s + (size_t)st * stage_bytes + ph * phase_bytes), &p.tmap[s], full0, 0,
+                                            2 * (tx * VALID - 1) + (ph & 1), 2 * (ty * TC_ROWS - 1) + (ph >> 1), img * p.src_pstride[s]);
+                    } else {
+                        tma_load_3d_2sm(smem_u32(stage_s + (size_t)st * stage_bytes), &p.tmap[s], full0,
+                                        (tx * VALID - PAD) * 8, ty * TC_ROWS - PAD, img * p.src_pstride[s]);
+                    }
                 }
             }
         }
@@ -760,7 +776,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
             const uint64_t bdesc0 = make_desc(smem_u32(w_s), NH2 * 16, 128);
             const uint32_t a_hi = (uint32_t)(adesc0 >> 32), b_hi = (uint32_t)(bdesc0 >> 32);
             const uint32_t a_base = (uint32_t)adesc0, b_base = (uint32_t)bdesc0;
-            const uint32_t stage_units = stage_bytes >> 4;
+            const uint32_t stage_units = stage_bytes >> 4, phase_units = phase_bytes >> 4;
             const uint32_t b_src_step = C8s * (NH2 * 16 / 16), b_tap_step = (uint32_t)Q * (NH2 * 16 / 16);
             const int nk = (p.debug & 1) ? 0 : (int)C8s / 2;
             uint32_t st = (mw * nsrc) % (uint32_t)S, par = 0;
@@ -782,7 +798,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
                     if (elect_one()) {
 #pragma unroll
                         for (int tap = 0; tap < KK; ++tap) {
-                            const uint32_t a_lo = a_lo0 + (uint32_t)((tap / KS) * TC_TW + (tap % KS));
+                            // stride 1: tap (dy, dx) = the halo tile advanced by dy rows and dx pixels.  stride 2: phase tile
+                            // (dy != 1, dx != 1) advanced by (dy != 0) rows and (dx != 0) pixels (see the kernel's header)
+                            const uint32_t a_lo = S2 ? a_lo0 + (uint32_t)(((tap / KS) != 1 ? 2 : 0) + ((tap % KS) != 1 ? 1 : 0)) * phase_units +
+                                                           (uint32_t)(((tap / KS) != 0 ? TC_TW : 0) + ((tap % KS) != 0 ? 1 : 0))
+                                                     : a_lo0 + (uint32_t)((tap / KS) * TC_TW + (tap % KS));
                             const uint32_t b_lo = b_lo0 + (uint32_t)tap * b_tap_step;
                             if (nk == 4) {
 #pragma unroll
@@ -1400,13 +1420,38 @@ int launch_conv_tc(const ConvOp &op, cudaStream_t s) {
     const int sms = sm_count();
     // CTA-pair kernels (cta_group::2) for the 3x3 convolutions with 64- and 128-wide tiles (the bulk of the network)
     static const bool two_cta = !(getenv("RVSR_TC_2CTA") != nullptr && getenv("RVSR_TC_2CTA")[0] == '0');
+    // stride 2 as a real implicit GEMM over the four phase images (RVSR_S2=0: compute at full resolution and subsample)
+    static const bool s2_on = !(getenv("RVSR_S2") != nullptr && getenv("RVSR_S2")[0] == '0');
+    const bool s2 = s2_on && two_cta && op.stride == 2 && op.w_tc2 != nullptr && pl.NT == 64 && op.ks == 3 && op.out_mode == OUT_C8 &&
+                    op.residual == nullptr && op.H % 2 == 0 && op.W % 2 == 0;
+    if (s2) {
+        const int Ho = op.H / 2, Wo = op.W / 2;
+        for (int i = 0; i < op.nsrc; ++i) {  // 4-D maps {8 channels, W, H, planes}, every other pixel of every other row
+            const Src &sr = op.src[i];
+            const int reach = sr.map != nullptr ? sr.map_images : op.N;
+            const cuuint64_t dims[4] = {8, (cuuint64_t)op.W, (cuuint64_t)op.H, (cuuint64_t)(reach - 1) * p.src_pstride[i] + pl.C8s};
+            const cuuint64_t strides[3] = {16, (cuuint64_t)op.W * 16, (cuuint64_t)op.H * op.W * 16};
+            const cuuint32_t box[4] = {8, 2 * TC_TW, 2 * (TC_ROWS + 1), (cuuint32_t)pl.C8s};
+            const cuuint32_t estr[4] = {1, 2, 2, 1};
+            CUresult r = enc(&p.tmap[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(sr.ptr), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { set_error("tc conv: cuTensorMapEncodeTiled (stride 2) failed (%d)", (int)r); return RVSR_E_CUDA; }
+        }
+        p.H = Ho; p.W = Wo; p.subsample = 0;
+        p.tiles_x = cdiv(Wo, valid); p.tiles_y = cdiv(Ho, TC_ROWS);
+        p.num_tiles = p.tiles_x * p.tiles_y * op.N;
+        p.td.tpi = (uint32_t)(p.tiles_x * p.tiles_y); p.td.m_tpi = magic_div(p.td.tpi, (uint32_t)p.num_tiles);
+        p.td.tx = (uint32_t)p.tiles_x; p.td.m_tx = magic_div(p.td.tx, p.td.tpi);
+    }
     if (two_cta && op.w_tc2 != nullptr && (pl.NT == 64 || pl.NT == 128) && op.ks == 3 && p.num_tiles >= 4 &&
-        (pl.NT == 128 || op.out_mode == OUT_C8)) {
+        (pl.NT == 128 || op.out_mode == OUT_C8) && (op.stride == 1 || s2)) {
         const size_t wb2 = (size_t)op.nsrc * pl.C8s * 9 * (pl.NT / 2) * 16;
-        const size_t stage = (size_t)pl.C8s * (TC_ROWS + 2) * TC_TW * 16;
+        const size_t stage = s2 ? (size_t)4 * pl.C8s * (TC_ROWS + 1) * TC_TW * 16 : (size_t)pl.C8s * (TC_ROWS + 2) * TC_TW * 16;
         const size_t fixed = wb2 + 128 + pl.NT * 4 + 512;
         int st2 = (int)((TC_SMEM_LIMIT - fixed) / stage);
         if (st2 > 6) st2 = 6;
+        RVSR_CHECK_ARG(st2 >= 2, "tc conv: not enough shared memory for two stages");
         p.nstages = st2;
         p.w = reinterpret_cast<const __half *>(op.w_tc2);
         const size_t smem2 = fixed + (size_t)st2 * stage + 1024;
@@ -1420,7 +1465,10 @@ int launch_conv_tc(const ConvOp &op, cudaStream_t s) {
         int clusters = (sms / 2) / pl.passes;
         if (clusters < 1) clusters = 1;
         if (clusters > npairs) clusters = npairs;
-        if (pl.NT == 64) {
+        if (s2) {
+            RVSR_TRY(ensure_max_dynamic_smem(reinterpret_cast<const void *>(&conv_tc2_kernel<3, 64, true>), (int)TC_SMEM_LIMIT + 1024));
+            launch_k(conv_tc2_kernel<3, 64, true>, dim3(2 * clusters, pl.passes), dim3(TC_THREADS), smem2, s, p);
+        } else if (pl.NT == 64) {
             RVSR_TRY(ensure_max_dynamic_smem(reinterpret_cast<const void *>(&conv_tc2_kernel<3, 64>), (int)TC_SMEM_LIMIT + 1024));
             launch_k(conv_tc2_kernel<3, 64>, dim3(2 * clusters, pl.passes), dim3(TC_THREADS), smem2, s, p);
         } else {
@@ -1554,13 +1602,17 @@ struct TcDcnParams {
     int N, H, W, cpg, act;
     int tiles_x, tiles_y, num_tiles;
     int debug;  // RVSR_DCN_DEBUG timing experiments (results wrong): 1 = no fence.proxy.async after the gather stores
+    // nf = 128 (NT = 128): one launch contracts 64 input channels (8 blocks starting at blk0) into all 128 outputs; the
+    // second launch adds its result to the first one's partial sums (fp16, no bias) and finishes with bias + activation
+    int blk0, accum, finish;
 };
 constexpr int DCN_GATHER_WARPS = 16, DCN_THREADS = 32 * (1 + DCN_GATHER_WARPS + 4), DCN_STAGES = 3;  // 2..4 measure the same; 6 is slower (L1 capacity)
 constexpr int DCN_TAP_BYTES = 8 * 128 * 16;  // 8 channel blocks x 128 pixels x 16 B
 
-template <bool BLEND16>
+template <bool BLEND16, int NT>
 __global__ void __launch_bounds__(DCN_THREADS, 1) dcn_tc_kernel(const __grid_constant__ TcDcnParams p) {
-    constexpr int NT = 64, K = 9, Q = 8, ACC = 64, TMEM_COLS = 128;
+    constexpr int K = 9, Q = 8, ACC = NT, TMEM_COLS = 2 * NT;
+    static_assert(NT == 64 || NT == 128, "DCN contraction tile: 64 or 128 output channels");
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr uint32_t w_bytes = Q * K * NT * 16;
     uint8_t *w_s = smem;
@@ -1652,7 +1704,7 @@ __global__ void __launch_bounds__(DCN_THREADS, 1) dcn_tc_kernel(const __grid_con
             const int y = ty * TC_ROWS + (m >> 5), x = tx * TC_TW + (m & 31);
             u.valid = y < p.H && x < p.W;
             const long long pix = u.valid ? (long long)y * p.W + x : 0;
-            const int blk = half * 4 + qq, g = (blk * 8) / p.cpg;
+            const int blk = p.blk0 + half * 4 + qq, g = (blk * 8) / p.cpg;
             const long long img = p.x_map != nullptr ? __ldg(p.x_map + n) : n;
             u.pl = reinterpret_cast<const uint4 *>(p.x + img * p.x_image_stride + (long long)blk * plane * 8);
             u.om = p.om + (long long)n * p.om_stride + ((long long)(g * 3) * plane + pix) * 2;
@@ -1775,7 +1827,7 @@ __global__ void __launch_bounds__(DCN_THREADS, 1) dcn_tc_kernel(const __grid_con
         pdl_wait();
         const int lq = warp & 3;
         EpiArgs e{bias_s, p.out, p.out_image_stride, nullptr, 0, p.H, p.W, NT, p.act, OUT_C8, 0, 0, 0, nullptr, 0, 1};
-        EpiTile<NT, 1> ep;
+        EpiTile<64, 1> ep;
         ep.has_res = false;
         uint32_t t = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++t) {
@@ -1784,11 +1836,54 @@ __global__ void __launch_bounds__(DCN_THREADS, 1) dcn_tc_kernel(const __grid_con
             mbar_wait_idle(BAR(2 * S + 1 + buf), (t >> 1) & 1);  // a tile takes ~10k cycles to gather
             tc_fence_after();
             const int y = ty * TC_ROWS + lq, x = tx * TC_TW + lane;
-            ep.run(e, tmem_base + buf * ACC + ((uint32_t)(lq * 32) << 16), 0, 0, n, y, x, y < p.H && x < p.W, true, true, [&] {
+            const uint32_t taddr = tmem_base + buf * ACC + ((uint32_t)(lq * 32) << 16);
+            auto release = [&] {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR(2 * S + 3 + buf));
-            });
+            };
+            if constexpr (NT == 64) {
+                ep.run(e, taddr, 0, 0, n, y, x, y < p.H && x < p.W, true, true, release);
+            } else {
+                // 128 columns, 32 at a time; partial sums of the first input half are read back from `out` (same thread, in place)
+                const bool valid = y < p.H && x < p.W;
+                uint4 *o = reinterpret_cast<uint4 *>(p.out + (long long)n * p.out_image_stride) + (long long)y * p.W + x;
+                const long long plane = (long long)p.H * p.W;
+#pragma unroll 1
+                for (int hc = 0; hc < NT / 32; ++hc) {
+                    uint32_t a[2][16];
+                    tmem_ld16_nowait(taddr + hc * 32, a[0]);
+                    tmem_ld16_nowait(taddr + hc * 32 + 16, a[1]);
+                    tmem_ld_wait();
+                    if (hc == NT / 32 - 1) release();
+                    if (!valid) continue;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float v[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(a[q >> 1][(q & 1) * 8 + i]);
+                        uint4 *dst = o + (long long)(hc * 4 + q) * plane;
+                        if (p.accum) {
+                            const uint4 prev = *dst;
+                            const __half2 *h = reinterpret_cast<const __half2 *>(&prev);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float2 f = __half22float2(h[i]);
+                                v[2 * i] += f.x; v[2 * i + 1] += f.y;
+                            }
+                        }
+                        if (p.finish) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[i] = apply_act(v[i] + bias_s[hc * 32 + q * 8 + i], p.act);
+                        }
+                        uint4 pk;
+                        __half2 *h = reinterpret_cast<__half2 *>(&pk);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+                        *dst = pk;
+                    }
+                }
+            }
         }
     }
     tc_fence_before();
@@ -1797,10 +1892,11 @@ __global__ void __launch_bounds__(DCN_THREADS, 1) dcn_tc_kernel(const __grid_con
 }
 
 bool tc_dcn_supported(const DcnOp &op) {
-    if (op.w_tc == nullptr || op.x.C != 64 || op.Cout != 64 || op.kh != 3 || op.kw != 3) return false;
+    const bool c64 = op.x.C == 64 && op.Cout == 64, c128 = op.x.C == 128 && op.Cout == 128 && op.w_tc_hi != nullptr;
+    if (op.w_tc == nullptr || !(c64 || c128) || op.kh != 3 || op.kw != 3) return false;
     if (op.stride != 1 || op.pad != 1 || op.dil != 1 || op.out_mode != OUT_C8) return false;
     const int cpg = op.x.C / op.dg;
-    if (cpg * op.dg != 64 || cpg % 8 != 0) return false;
+    if (cpg * op.dg != op.x.C || cpg % 8 != 0) return false;
     if (op.x.fixed_frame >= 0 || op.om24 == nullptr) return false;
     return true;
 }
@@ -1817,17 +1913,49 @@ int launch_dcn_tc(const DcnOp &op, cudaStream_t s) {
     if (p.num_tiles == 0) return RVSR_OK;
     static const int ddbg = getenv("RVSR_DCN_DEBUG") ? atoi(getenv("RVSR_DCN_DEBUG")) : 0;
     p.debug = ddbg;
-    const size_t smem = 8 * 9 * 64 * 16 + DCN_STAGES * DCN_TAP_BYTES + 64 * 4 + 256 + 1024;
-    RVSR_TRY(ensure_max_dynamic_smem(reinterpret_cast<const void *>(&dcn_tc_kernel<true>), (int)smem));
-    RVSR_TRY(ensure_max_dynamic_smem(reinterpret_cast<const void *>(&dcn_tc_kernel<false>), (int)smem));
-    // RVSR_DCN_BLEND=fp32 keeps the bilinear blend in fp32 (one rounding per sample instead of four)
     static const bool blend32 = getenv("RVSR_DCN_BLEND") != nullptr && strcmp(getenv("RVSR_DCN_BLEND"), "fp32") == 0;
     int gx = sm_count();
     if (gx > p.num_tiles) gx = p.num_tiles;
-    if (blend32)
-        launch_k(dcn_tc_kernel<false>, dim3(gx), dim3(DCN_THREADS), smem, s, p);
-    else
-        launch_k(dcn_tc_kernel<true>, dim3(gx), dim3(DCN_THREADS), smem, s, p);
+    p.blk0 = 0; p.accum = 0; p.finish = 1;
+    if (op.x.C == 64) {
+        const size_t smem = 8 * 9 * 64 * 16 + DCN_STAGES * DCN_TAP_BYTES + 64 * 4 + 256 + 1024;
+        RVSR_TRY(ensure_max_dynamic_smem(reinterpret_cast<const void *>(&dcn_tc_kernel<true, 64>), (int)smem));
+        RVSR_TRY(ensure_max_dynamic_smem(reinterpret_cast<const void *>(&dcn_tc_kernel<false, 64>), (int)smem));
+        // RVSR_DCN_BLEND=fp32 keeps the bilinear blend in fp32 (one rounding per sample instead of four)
+        if (blend32)
+            launch_k(dcn_tc_kernel<false, 64>, dim3(gx), dim3(DCN_THREADS), smem, s, p);
+        else
+            launch_k(dcn_tc_kernel<true, 64>, dim3(gx), dim3(DCN_THREADS), smem, s, p);
+        RVSR_LAUNCH_CHECK();
+        return RVSR_OK;
+    }
+    // nf = 128: the 128 x 128 x 9 weights (295 KB) do not fit: two launches over the input-channel halves
+    const size_t smem = 8 * 9 * 128 * 16 + DCN_STAGES * DCN_TAP_BYTES + 128 * 4 + 256 + 1024;
+    RVSR_TRY(ensure_max_dynamic_smem(reinterpret_cast<const void *>(&dcn_tc_kernel<true, 128>), (int)smem));
+    RVSR_TRY(ensure_max_dynamic_smem(reinterpret_cast<const void *>(&dcn_tc_kernel<false, 128>), (int)smem));
+    for (int h = 0; h < 2; ++h) {
+        p.w = reinterpret_cast<const __half *>(h == 0 ? op.w_tc : op.w_tc_hi);
+        p.blk0 = 8 * h; p.accum = h; p.finish = h;
+        if (blend32)
+            launch_k(dcn_tc_kernel<false, 128>, dim3(gx), dim3(DCN_THREADS), smem, s, p);
+        else
+            launch_k(dcn_tc_kernel<true, 128>, dim3(gx), dim3(DCN_THREADS), smem, s, p);
+        RVSR_LAUNCH_CHECK();
+    }
+    return RVSR_OK;
+}
+
+// contraction weights of one input-channel half (nf = 128): [tap][8 blocks][128 rows][8], value = w[n][h * 64 + q * 8 + e][tap]
+size_t tc_dcn_half_weight_bytes() { return (size_t)9 * 8 * 128 * 16; }
+__global__ void pack_weight_dcn_half_kernel(const float *__restrict__ w, __half *__restrict__ dst, int h, int total) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int e = i % 8, n = (i / 8) % 128, q = (i / 1024) % 8, tap = i / 8192;
+        dst[i] = __float2half_rn(w[((long long)n * 128 + h * 64 + q * 8 + e) * 9 + tap]);
+    }
+}
+int pack_weight_dcn_tc_half(const float *w_oihw, void *dst, int h, cudaStream_t s) {
+    const int total = 9 * 8 * 128 * 8;
+    pack_weight_dcn_half_kernel<<<(total + 255) / 256, 256, 0, s>>>(w_oihw, reinterpret_cast<__half *>(dst), h, total);
     RVSR_LAUNCH_CHECK();
     return RVSR_OK;
 }

@@ -30,7 +30,7 @@ class EDVREngine:
                                    int(bool(predeblur)), int(bool(HR_in)), int(bool(w_TSA)), int(bool(upsample)),
                                    _PRECISION[precision])
         self.precision = precision
-        self.scale = 4 if upsample else 1
+        self.scale = 4 if (upsample and not HR_in) else 1   # HR_in: frames arrive at the output resolution
         h = ctypes.c_void_p()
         _lib.check(self.L.rvsr_engine_create(ctypes.byref(self.cfg), ctypes.byref(h)), "engine_create")
         self.h = h

@@ -2,7 +2,7 @@
 
   index_generation   data/util.py:169-214      temporal window indices with 4 padding modes
   single_forward     utils/util.py:222-237     no_grad forward, result .float().cpu()
-  flipx4_forward     utils/util.py:240-261     x4 flip self-ensemble
+  flipx4_forward     utils/util.py:240-261     x4 flip self-ensemble (flipx4_forward_batched: the same as one batch-4 call)
   sr_sequence        test_RealVSR_wi_GT.py:114-119 (the per-frame loop), re-designed: the per-frame
                      feature pyramid is extracted ONCE per frame into a cache and windows are batched,
                      instead of recomputing all N pyramids for every output frame.
@@ -59,6 +59,19 @@ def flipx4_forward(model, inp):
     acc = single_forward(model, inp)
     for dims in ((-1,), (-2,), (-2, -1)):
         acc = acc + torch.flip(single_forward(model, torch.flip(inp, dims)), dims)
+    return acc / 4
+
+
+def flipx4_forward_batched(model, inp):
+    """flipx4_forward as ONE batch-4 call: the four flipped copies of every window go through the model together (the
+    reference runs four forwards, utils/util.py:240-261).  Same result: the engine is batch-invariant."""
+    B = inp.shape[0]
+    dims = (None, (-1,), (-2,), (-2, -1))
+    x = torch.cat([inp if d is None else torch.flip(inp, d) for d in dims], 0)
+    y = single_forward(model, x)
+    acc = y[:B]
+    for k, d in enumerate(dims[1:], 1):
+        acc = acc + torch.flip(y[k * B:(k + 1) * B], d)
     return acc / 4
 
 

@@ -30,9 +30,9 @@ def test_header_symbols_all_exported_and_bound():
 def test_engine_config_validation_without_gpu():
     L = _lib.lib()
     h = ctypes.c_void_p()
-    bad = _lib.EdvrConfig(64, 3, 5, 8, 5, 10, -1, 1, 0, 1, 1, _lib.F16)  # predeblur: not built
+    bad = _lib.EdvrConfig(60, 3, 5, 8, 5, 10, -1, 0, 0, 1, 1, _lib.F16)  # nf must be a multiple of 8
     assert L.rvsr_engine_create(ctypes.byref(bad), ctypes.byref(h)) == _lib.E_UNSUPPORTED
-    assert b"predeblur" in L.rvsr_last_error()
+    assert b"nf" in L.rvsr_last_error()
     bad = _lib.EdvrConfig(16, 3, 5, 8, 5, 10, -1, 0, 0, 1, 0, _lib.F16)  # NoUp needs nf == 64
     assert L.rvsr_engine_create(ctypes.byref(bad), ctypes.byref(h)) == _lib.E_INVALID
     with pytest.raises(NotImplementedError):
@@ -45,15 +45,20 @@ def test_engine_state_dict_contract_names():
     from helpers import edvr_state_shapes
     L = _lib.lib()
     for up, kw in ((1, dict(nf=64, nframes=5, groups=8, front_RBs=5, back_RBs=10, w_TSA=True)),
-                   (0, dict(nf=64, nframes=3, groups=8, front_RBs=5, back_RBs=10, w_TSA=False))):
-        cfg = _lib.EdvrConfig(kw["nf"], 3, kw["nframes"], kw["groups"], kw["front_RBs"], kw["back_RBs"], -1, 0, 0,
-                              int(kw["w_TSA"]), up, _lib.F32)
+                   (0, dict(nf=64, nframes=3, groups=8, front_RBs=5, back_RBs=10, w_TSA=False)),
+                   (1, dict(nf=16, nframes=3, groups=4, front_RBs=1, back_RBs=1, w_TSA=True, predeblur=True, HR_in=True)),
+                   (1, dict(nf=16, nframes=3, groups=4, front_RBs=1, back_RBs=1, w_TSA=True, predeblur=True)),
+                   (1, dict(nf=16, nframes=3, groups=4, front_RBs=1, back_RBs=1, w_TSA=False, HR_in=True))):
+        cfg = _lib.EdvrConfig(kw["nf"], 3, kw["nframes"], kw["groups"], kw["front_RBs"], kw["back_RBs"], -1,
+                              int(kw.get("predeblur", False)), int(kw.get("HR_in", False)), int(kw["w_TSA"]), up, _lib.F32)
         h = ctypes.c_void_p()
         assert L.rvsr_engine_create(ctypes.byref(cfg), ctypes.byref(h)) == 0
         names = [L.rvsr_engine_weight_name(h, i).decode() for i in range(L.rvsr_engine_num_weights(h))]
         assert names == list(edvr_state_shapes("EDVR" if up else "EDVR_NoUp", **kw).keys())
         # workspace sizing is host-only arithmetic: 0 for bad dims, >0 and monotone otherwise
         assert L.rvsr_engine_workspace_bytes(h, 1, 30, 32) == 0
+        if kw.get("HR_in"):
+            assert L.rvsr_engine_workspace_bytes(h, 1, 36, 32) == 0     # HR_in: multiples of 16
         a, b = L.rvsr_engine_workspace_bytes(h, 1, 32, 32), L.rvsr_engine_workspace_bytes(h, 2, 32, 32)
         assert 0 < a < b
         L.rvsr_engine_destroy(h)

@@ -16,12 +16,13 @@ from realvsr_b200.archs import EDVR_arch as E
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-ENGINE_CASES = [c for c in EDVR_CASES if c not in ("edvr_predeblur", "edvr_hr_in", "edvr_predeblur_hr_in")]  # stems: module path (tested below)
+ENGINE_CASES = list(EDVR_CASES)   # incl. the predeblur / HR_in stems (EDVR_arch.py:15-59, :228-231)
 
 
 def _base(c):
     xc = c["x"][:, c["kwargs"]["nframes"] // 2]
-    return F.interpolate(xc, scale_factor=4, mode="bilinear", align_corners=False) if c["cls"] == "EDVR" else xc
+    up = c["cls"] == "EDVR" and not c["kwargs"].get("HR_in", False)   # HR_in: base = the centre frame itself (:315-316)
+    return F.interpolate(xc, scale_factor=4, mode="bilinear", align_corners=False) if up else xc
 
 
 def _net(c, path):
@@ -41,7 +42,7 @@ def test_engine_fp32_matches_golden(name):
     base = _base(c)
     assert rel_err(y.cpu() - base, c["out"] - base) < 1e-3
     eng = net._get_engine(c["x"].to(DEV))
-    al = eng.read_tap("aligned", (c["x"].shape[0] * c["x"].shape[1],) + tuple(c["aligned0"].shape[1:]))
+    al = eng.read_tap("aligned", (c["x"].shape[0] * c["x"].shape[1],) + tuple(c["aligned0"].shape[1:]))   # feature resolution
     B, N = c["x"].shape[:2]
     al0 = al.view(B, N, *al.shape[1:])[:, 0].cpu()
     assert rel_err(al0, c["aligned0"]) < 1e-3

@@ -58,6 +58,30 @@ def test_sr_sequence_cache_is_bit_identical_to_plain_forward(name, half):
 
 
 @pytest.mark.gpu
+def test_flipx4_on_the_engine_matches_reference_semantics():
+    """utils/util.py:240-261 on the real model: four forwards on flipped inputs, flipped back and averaged -- against the
+    CPU oracle doing the same, and the batch-4 variant against the four separate calls (bit-identical)."""
+    from helpers import rel_err
+    from oracle import edvr_oracle as O
+    from realvsr_b200.archs import EDVR_arch as E
+    c = load_case("edvr_tiny")
+    kw = c["kwargs"]
+    net = E.EDVR(**kw).eval()
+    net.load_state_dict(c["sd"], strict=True)
+    net = net.to("cuda:0")
+    net.exec_path = "engine"
+    x = c["x"]
+
+    def oracle_model(t):
+        return O.edvr_forward(c["sd"], t, groups=kw["groups"], w_TSA=kw["w_TSA"], upsample=True)
+
+    ref = V.flipx4_forward(oracle_model, x)
+    got = V.flipx4_forward(net, x.to("cuda:0"))
+    assert rel_err(got, ref) < 1e-4
+    assert torch.equal(V.flipx4_forward_batched(net, x.to("cuda:0")), got)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("half", [False, True])
 def test_tiled_forward_matches_oracle_with_identical_tiling(half):
     """BASELINE cfg4's architecture (7 frames, nf = 128, 16 channels per deformable group) on a 2 x 2-tile crop.  The
