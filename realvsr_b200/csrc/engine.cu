@@ -363,6 +363,12 @@ template <typename T> struct Plan {
         }
         return a;
     }
+    // the plan is done with this activation: its memory may be handed to a later layer (see Arena)
+    void drop(Act &a) {
+        static const bool keep = getenv("RVSR_ARENA_REUSE") != nullptr && getenv("RVSR_ARENA_REUSE")[0] == '0';
+        if (!keep && a.p != nullptr) ar.free(a.p);
+        a.p = nullptr;
+    }
     static Src src_of(const Act &a) {
         Src r;
         r.ptr = a.p; r.image_stride = a.image_elems(); r.C = a.C; r.frames = 1; r.fixed_frame = -1;
@@ -552,7 +558,7 @@ template <typename T> struct Plan {
         Act om = conv(name + ".conv_offset_mask", {src_of(feat)}, feat.N, feat.H, feat.W, RVSR_ACT_NONE, 1,
                       om24 ? OUT_OM24 : OUT_PLANAR_F32, nullptr, 2 * dg * K);
         Act o = make(feat.N, pc->Cout, x.H, x.W);
-        if (dry || rc != RVSR_OK) return o;
+        if (dry || rc != RVSR_OK) { drop(om); return o; }
         DcnOp op = {};
         op.x = xmap != nullptr ? src_mapped(x, xmap) : src_of(x);
         if (om24) {
@@ -579,6 +585,7 @@ template <typename T> struct Plan {
         }
         launch(std::string(tc ? "tc:" : "simt:") + "dcn_gather_mma:" + name, flops, bytes,
                [&] { return tc ? launch_dcn_tc(op, s) : launch_dcn_simt<T>(op, s); });
+        drop(om);
         return o;
     }
     Act up2(const Act &a, float scale) {
@@ -603,65 +610,39 @@ template <typename T> struct Plan {
             // profile accounting: the pair together is the reference's 128 -> 64 convolution over NB_ images -- its
             // algorithmic FLOPs are booked on the #a launch, none on #b (the roofline counts the reference's work)
             Act r = conv(name + "#b", {refB}, B_, H, W, RVSR_ACT_NONE, 1, OUT_C8, nullptr, 1 << 30, 0, 1, true, 0.0);
-            return conv(name + "#a", {a}, NB_, H, W, act, 1, OUT_C8, &r, 1 << 30, 1, frames, true,
-                        2.0 * 128 * 64 * 9 * (double)NB_ * H * W);
+            Act o = conv(name + "#a", {a}, NB_, H, W, act, 1, OUT_C8, &r, 1 << 30, 1, frames, true,
+                         2.0 * 128 * 64 * 9 * (double)NB_ * H * W);
+            drop(r);
+            return o;
         }
         return conv(name, {a, ref_all}, NB_, H, W, act);
     }
     // one ResidualBlock_noBN by its full prefix (Predeblur pyramid): x + conv2(relu(conv1(x)))
-    Act resblock1(const std::string &b, const Act &cur) {
+    // (consumes `cur`: its memory is released once the block's output exists)
+    Act resblock1(const std::string &b, Act cur) {
         Act t = conv(b + ".conv1", {src_of(cur)}, cur.N, cur.H, cur.W, RVSR_ACT_RELU);
-        return conv(b + ".conv2", {src_of(t)}, cur.N, cur.H, cur.W, RVSR_ACT_NONE, 1, OUT_C8, &cur);
+        Act o = conv(b + ".conv2", {src_of(t)}, cur.N, cur.H, cur.W, RVSR_ACT_NONE, 1, OUT_C8, &cur);
+        drop(t); drop(cur);
+        return o;
     }
     // a + up2(b)  (bilinear x2, align_corners=False), one pass
-    Act up2_add(const Act &b, const Act &a) {
+    Act up2_add(Act b, Act a) {  // consumes both
         Act o = make(b.N, b.C, 2 * b.H, 2 * b.W);
         if (!dry && rc == RVSR_OK)
             launch("glue:upsample2x_add:", 0, (double)b.elems() * sizeof(T) * 9, [&] {
                 return launch_upsample2x<T>((const T *)b.p, (T *)o.p, b.N, b.C, b.H, b.W, 1.f, s, (const T *)a.p); });
+        drop(a); drop(b);
         return o;
     }
-    Act resblocks(const std::string &prefix, int count, Act cur) {
-        // fp16 / 64 channels / enough tiles: the whole run (2 * count convolutions) is ONE persistent launch with
-        // tile-level dataflow between the layers (conv_chain_kernel); otherwise one launch per convolution
-        if (use_tc && sizeof(T) == 2 && cur.C == 64 && count >= 1 && conv_chain_supported(2 * count, cur.N, cur.H, cur.W)) {
-            bool ok = true;
-            for (int i = 0; i < count && ok; ++i)
-                for (const char *c : {".conv1", ".conv2"}) {
-                    const PackedConv *pc = get(prefix + "." + std::to_string(i) + c);
-                    ok = ok && pc != nullptr && pc->w_tc2 != nullptr && pc->Cout == 64 && pc->Cin == 64 && pc->ks == 3;
-                }
-            if (ok) {
-                std::vector<ChainLayerDesc> ls;
-                const Act in0 = cur;
-                double flops = 0, bytes = 0;
-                for (int i = 0; i < count; ++i) {
-                    const std::string b = prefix + "." + std::to_string(i);
-                    const PackedConv *p1 = get(b + ".conv1"), *p2 = get(b + ".conv2");
-                    Act t = make(cur.N, 64, cur.H, cur.W);
-                    Act o = make(cur.N, 64, cur.H, cur.W);
-                    ls.push_back(ChainLayerDesc{cur.p, p1->w_tc2, p1->bias, t.p, nullptr, RVSR_ACT_RELU});
-                    ls.push_back(ChainLayerDesc{t.p, p2->w_tc2, p2->bias, o.p, cur.p, RVSR_ACT_NONE});
-                    const double px = (double)cur.N * cur.H * cur.W;
-                    flops += 2 * 2.0 * 64 * 64 * 9 * px;
-                    bytes += px * 64 * sizeof(T) * 5;  // conv1: in + out; conv2: in + residual + out
-                    cur = o;
-                }
-                void *scratch = ar.alloc(conv_chain_scratch_bytes(2 * count, in0.N, in0.H));
-                if (scratch == nullptr && rc == RVSR_OK) { set_error("workspace too small"); rc = RVSR_E_WORKSPACE; }
-                if (!dry && rc == RVSR_OK) {
-                    eng->host_chain_.emplace_back();
-                    std::vector<char> &staging = eng->host_chain_.back();
-                    launch("tc:chain3x3_co64:" + prefix + " x" + std::to_string(2 * count), flops, bytes,
-                           [&] { return launch_conv_chain(ls.data(), (int)ls.size(), in0.N, in0.H, in0.W, scratch, staging, s); });
-                }
-                return cur;
-            }
-        }
+    // `keep_input`: the caller still needs `cur` (a tap); every intermediate of the run is released as soon as it is dead
+    Act resblocks(const std::string &prefix, int count, Act cur, bool keep_input = false) {
         for (int i = 0; i < count; ++i) {
             const std::string b = prefix + "." + std::to_string(i);
             Act t = conv(b + ".conv1", {src_of(cur)}, cur.N, cur.H, cur.W, RVSR_ACT_RELU);
-            cur = conv(b + ".conv2", {src_of(t)}, cur.N, cur.H, cur.W, RVSR_ACT_NONE, 1, OUT_C8, &cur);
+            Act o = conv(b + ".conv2", {src_of(t)}, cur.N, cur.H, cur.W, RVSR_ACT_NONE, 1, OUT_C8, &cur);
+            drop(t);
+            if (!(keep_input && i == 0)) drop(cur);
+            cur = o;
         }
         return cur;
     }
@@ -691,6 +672,8 @@ int Engine::run(Arena &ar, bool dry, const void *x, int x_dtype, void *out, int 
 
     Act L1, L2, L3;
     const int *map_nbr = nullptr, *map_ref = nullptr, *map_ctr = nullptr;
+    // dst = v, releasing what dst held (v was computed FROM the old dst: arguments are evaluated before the call)
+    auto replace = [&](Act &dst, Act v) { P.drop(dst); dst = v; };
     if (!cached) {
         // ---- LQ frames -> channel-blocked
         const int nc_store = (cfg_.precision == RVSR_F16 && nc < 16) ? 16 : nc;  // see finalize(): K granularity
@@ -702,10 +685,16 @@ int Engine::run(Arena &ar, bool dry, const void *x, int x_dtype, void *out, int 
                            : launch_pack_nchw<T, __half>((const __half *)x, (T *)xin.p, NB, nc, Hin, Win, s, nc_store); });
         // ---- per-frame feature pyramid (EDVR_arch.py:262-283)
         auto stem = [&](const std::string &pre) {  // conv_first, or the HR_in stem conv_first_1 -> _2 (s2) -> _3 (s2)
-            if (!hr) return P.conv(pre + "conv_first", {PT::src_of(xin)}, NB, Hin, Win, LR);
+            if (!hr) {
+                Act o = P.conv(pre + "conv_first", {PT::src_of(xin)}, NB, Hin, Win, LR);
+                P.drop(xin);
+                return o;
+            }
             Act a = P.conv(pre + "conv_first_1", {PT::src_of(xin)}, NB, Hin, Win, LR);
-            a = P.conv(pre + "conv_first_2", {PT::src_of(a)}, NB, Hin, Win, LR, 2);
-            return P.conv(pre + "conv_first_3", {PT::src_of(a)}, NB, a.H, a.W, LR, 2);
+            P.drop(xin);
+            replace(a, P.conv(pre + "conv_first_2", {PT::src_of(a)}, NB, Hin, Win, LR, 2));
+            replace(a, P.conv(pre + "conv_first_3", {PT::src_of(a)}, NB, a.H, a.W, LR, 2));
+            return a;
         };
         if (cfg_.predeblur) {  // Predeblur_ResNet_Pyramid.forward (EDVR_arch.py:43-59), then conv_1x1 without activation (:265)
             const std::string d = "pre_deblur.";
@@ -718,14 +707,15 @@ int Engine::run(Arena &ar, bool dry, const void *x, int x_dtype, void *out, int 
             l1 = P.up2_add(l2, P.resblock1(d + "RB_L1_2", P.resblock1(d + "RB_L1_1", l1)));
             for (const char *n : {"RB_L1_3", "RB_L1_4", "RB_L1_5"}) l1 = P.resblock1(d + n, l1);
             L1 = P.conv("conv_1x1", {PT::src_of(l1)}, NB, H, W, NONE);
+            P.drop(l1);
         } else {
             L1 = stem("");
         }
         L1 = P.resblocks("feature_extraction", cfg_.front_RBs, L1);
         L2 = P.conv("fea_L2_conv1", {PT::src_of(L1)}, NB, H, W, LR, 2);
-        L2 = P.conv("fea_L2_conv2", {PT::src_of(L2)}, NB, L2.H, L2.W, LR);
+        replace(L2, P.conv("fea_L2_conv2", {PT::src_of(L2)}, NB, L2.H, L2.W, LR));
         L3 = P.conv("fea_L3_conv1", {PT::src_of(L2)}, NB, L2.H, L2.W, LR, 2);
-        L3 = P.conv("fea_L3_conv2", {PT::src_of(L3)}, NB, L3.H, L3.W, LR);
+        replace(L3, P.conv("fea_L3_conv2", {PT::src_of(L3)}, NB, L3.H, L3.W, LR));
         if (extract) {
             if (!dry && P.rc == RVSR_OK) {  // copy the pyramid of the F frames into their (contiguous) cache slots
                 const Act *lv[3] = {&L1, &L2, &L3};
@@ -776,29 +766,41 @@ int Engine::run(Arena &ar, bool dry, const void *x, int x_dtype, void *out, int 
 
     // ---- PCD alignment of all N frames at once (EDVR_arch.py:98-132, :297-303)
     const std::string p = "pcd_align.";
+    // (L1 / L2 / L3, `aligned` and `fused` stay allocated: they are the parity taps of rvsr_engine_read_tap)
     Act o3 = P.conv_cat_ref(p + "L3_offset_conv1", nbr(L3), ref(L3), refB(L3), NB, B, N, L3.H, L3.W, LR);
-    o3 = P.conv(p + "L3_offset_conv2", {PT::src_of(o3)}, NB, L3.H, L3.W, LR);
+    replace(o3, P.conv(p + "L3_offset_conv2", {PT::src_of(o3)}, NB, L3.H, L3.W, LR));
     Act f3 = P.dcn_pack(p + "L3_dcnpack", L3, o3, dg, LR, map_nbr);
 
     Act o2 = P.conv_cat_ref(p + "L2_offset_conv1", nbr(L2), ref(L2), refB(L2), NB, B, N, L2.H, L2.W, LR);
     Act o3u = P.up2(o3, 2.f);
-    o2 = P.conv(p + "L2_offset_conv2", {PT::src_of(o2), PT::src_of(o3u)}, NB, L2.H, L2.W, LR);
-    o2 = P.conv(p + "L2_offset_conv3", {PT::src_of(o2)}, NB, L2.H, L2.W, LR);
+    P.drop(o3);
+    replace(o2, P.conv(p + "L2_offset_conv2", {PT::src_of(o2), PT::src_of(o3u)}, NB, L2.H, L2.W, LR));
+    P.drop(o3u);
+    replace(o2, P.conv(p + "L2_offset_conv3", {PT::src_of(o2)}, NB, L2.H, L2.W, LR));
     Act f2 = P.dcn_pack(p + "L2_dcnpack", L2, o2, dg, NONE, map_nbr);
     Act f3u = P.up2(f3, 1.f);
-    f2 = P.conv(p + "L2_fea_conv", {PT::src_of(f2), PT::src_of(f3u)}, NB, L2.H, L2.W, LR);
+    P.drop(f3);
+    replace(f2, P.conv(p + "L2_fea_conv", {PT::src_of(f2), PT::src_of(f3u)}, NB, L2.H, L2.W, LR));
+    P.drop(f3u);
 
     Act o1 = P.conv_cat_ref(p + "L1_offset_conv1", nbr(L1), ref(L1), refB(L1), NB, B, N, H, W, LR);
     Act o2u = P.up2(o2, 2.f);
-    o1 = P.conv(p + "L1_offset_conv2", {PT::src_of(o1), PT::src_of(o2u)}, NB, H, W, LR);
-    o1 = P.conv(p + "L1_offset_conv3", {PT::src_of(o1)}, NB, H, W, LR);
+    P.drop(o2);
+    replace(o1, P.conv(p + "L1_offset_conv2", {PT::src_of(o1), PT::src_of(o2u)}, NB, H, W, LR));
+    P.drop(o2u);
+    replace(o1, P.conv(p + "L1_offset_conv3", {PT::src_of(o1)}, NB, H, W, LR));
     Act f1 = P.dcn_pack(p + "L1_dcnpack", L1, o1, dg, NONE, map_nbr);
+    P.drop(o1);
     Act f2u = P.up2(f2, 1.f);
-    f1 = P.conv(p + "L1_fea_conv", {PT::src_of(f1), PT::src_of(f2u)}, NB, H, W, NONE);  // no lrelu (:125)
+    P.drop(f2);
+    replace(f1, P.conv(p + "L1_fea_conv", {PT::src_of(f1), PT::src_of(f2u)}, NB, H, W, NONE));  // no lrelu (:125)
+    P.drop(f2u);
 
     Act oc = P.conv_cat_ref(p + "cas_offset_conv1", PT::src_of(f1), ref(L1), refB(L1), NB, B, N, H, W, LR);
-    oc = P.conv(p + "cas_offset_conv2", {PT::src_of(oc)}, NB, H, W, LR);
+    replace(oc, P.conv(p + "cas_offset_conv2", {PT::src_of(oc)}, NB, H, W, LR));
     Act aligned = P.dcn_pack(p + "cas_dcnpack", f1, oc, dg, LR);
+    P.drop(oc);
+    P.drop(f1);
 
     // ---- fusion
     Act fused;
@@ -829,41 +831,53 @@ int Engine::run(Arena &ar, bool dry, const void *x, int x_dtype, void *out, int 
             P.launch("glue:tsa_temporal:", 4.0 * ali.elems(), (double)ali.elems() * sizeof(T) * 4, [&] {
                 return launch_tsa_temporal<T>((const T *)emb.p, (const T *)emb_ref.p, (const T *)aligned.p,
                                               (T *)ali.p, B, N, nf, H, W, s); });
+        P.drop(emb); P.drop(emb_ref);
         Act fea = conv_frames(t + "fea_fusion", ali, LR);
         Act att = conv_frames(t + "sAtt_1", ali, LR);
+        P.drop(ali);
         Act mx, av;
         P.pools(att, mx, av);
-        att = P.conv(t + "sAtt_2", {PT::src_of(mx), PT::src_of(av)}, B, mx.H, mx.W, LR);
+        replace(att, P.conv(t + "sAtt_2", {PT::src_of(mx), PT::src_of(av)}, B, mx.H, mx.W, LR));
+        P.drop(mx); P.drop(av);
         Act attL = P.conv(t + "sAtt_L1", {PT::src_of(att)}, B, att.H, att.W, LR);
         Act mx2, av2;
         P.pools(attL, mx2, av2);
-        attL = P.conv(t + "sAtt_L2", {PT::src_of(mx2), PT::src_of(av2)}, B, mx2.H, mx2.W, LR);
-        attL = P.conv(t + "sAtt_L3", {PT::src_of(attL)}, B, attL.H, attL.W, LR);
+        replace(attL, P.conv(t + "sAtt_L2", {PT::src_of(mx2), PT::src_of(av2)}, B, mx2.H, mx2.W, LR));
+        P.drop(mx2); P.drop(av2);
+        replace(attL, P.conv(t + "sAtt_L3", {PT::src_of(attL)}, B, attL.H, attL.W, LR));
         Act attLu = P.up2(attL, 1.f);
-        att = P.conv(t + "sAtt_3", {PT::src_of(att)}, B, att.H, att.W, LR, 1, OUT_C8, &attLu);  // lrelu, then + att_L
-        att = P.conv(t + "sAtt_4", {PT::src_of(att)}, B, att.H, att.W, LR);
+        P.drop(attL);
+        replace(att, P.conv(t + "sAtt_3", {PT::src_of(att)}, B, att.H, att.W, LR, 1, OUT_C8, &attLu));  // lrelu, then + att_L
+        P.drop(attLu);
+        replace(att, P.conv(t + "sAtt_4", {PT::src_of(att)}, B, att.H, att.W, LR));
         Act attu = P.up2(att, 1.f);
-        att = P.conv(t + "sAtt_5", {PT::src_of(attu)}, B, H, W, NONE);
+        replace(att, P.conv(t + "sAtt_5", {PT::src_of(attu)}, B, H, W, NONE));
+        P.drop(attu);
         Act add = P.conv(t + "sAtt_add_1", {PT::src_of(att)}, B, H, W, LR);
-        add = P.conv(t + "sAtt_add_2", {PT::src_of(add)}, B, H, W, NONE);
+        replace(add, P.conv(t + "sAtt_add_2", {PT::src_of(add)}, B, H, W, NONE));
         fused = P.make(B, nf, H, W);
         if (!dry && P.rc == RVSR_OK)
             P.launch("glue:tsa_final:", 0, (double)fused.elems() * sizeof(T) * 4, [&] {
                 return launch_tsa_final<T>((const T *)fea.p, (const T *)att.p, (const T *)add.p, (T *)fused.p,
                                            fused.elems(), s); });
+        P.drop(fea); P.drop(att); P.drop(add);
     } else {
         fused = conv_frames("tsa_fusion", aligned, NONE);
     }
 
     // ---- reconstruction (EDVR_arch.py:310-319 / :398-403)
-    Act r = P.resblocks("recon_trunk", cfg_.back_RBs, fused);
+    Act r = P.resblocks("recon_trunk", cfg_.back_RBs, fused, true);
+    auto next_r = [&](Act v) {  // r = v; the old r is released unless it is still the `fused` tap (back_RBs == 0)
+        if (r.p != fused.p) P.drop(r);
+        r = v;
+    };
     int scale = 1;  // output resolution / resolution of the frames the base is taken from
     if (cfg_.upsample) {
-        r = P.conv("upconv1", {PT::src_of(r)}, B, H, W, LR, 1, OUT_C8_SHUFFLE2);
-        r = P.conv("upconv2", {PT::src_of(r)}, B, r.H, r.W, LR, 1, OUT_C8_SHUFFLE2);
+        next_r(P.conv("upconv1", {PT::src_of(r)}, B, H, W, LR, 1, OUT_C8_SHUFFLE2));
+        next_r(P.conv("upconv2", {PT::src_of(r)}, B, r.H, r.W, LR, 1, OUT_C8_SHUFFLE2));
         scale = hr ? 1 : 4;  // HR_in: base = the centre frame itself (EDVR_arch.py:315-316)
     }
-    r = P.conv("HRconv", {PT::src_of(r)}, B, r.H, r.W, LR);
+    next_r(P.conv("HRconv", {PT::src_of(r)}, B, r.H, r.W, LR));
     // conv_last + base frame: one tcgen05 launch that writes the NCHW result (OUT_FINAL) when the shape allows it
     bool fused_final = false;
     if (P.use_tc && sizeof(T) == 2 && nc <= 8) {
@@ -989,7 +1003,6 @@ int Engine::forward(const void *x, int x_dtype, void *out, int out_dtype, int B,
     const size_t mis = (size_t)(reinterpret_cast<uintptr_t>(ws) % 1024);
     if (mis) { ar.base += 1024 - mis; ar.cap -= 1024 - mis; }
     host_maps_.clear();
-    host_chain_.clear();
     const int rc = cfg_.precision == RVSR_F16 ? run<__half>(ar, false, x, x_dtype, out, out_dtype, B, H, W, s, nullptr)
                                               : run<float>(ar, false, x, x_dtype, out, out_dtype, B, H, W, s, nullptr);
     tc_stamps_dump();  // debug only (RVSR_TC_STAMPS): synchronises
@@ -1033,7 +1046,6 @@ int Engine::extract_features(const void *frames, int dtype, int F, int H, int W,
     CacheArgs ca = {};
     ca.extract = true; ca.cache = cache; ca.n_slots = n_slots; ca.slot0 = slot0;
     prof_clear();
-    host_chain_.clear();
     if (cfg_.precision == RVSR_F16) return run<__half>(ar, false, frames, dtype, nullptr, RVSR_F32, F, H, W, s, &ca);
     return run<float>(ar, false, frames, dtype, nullptr, RVSR_F32, F, H, W, s, &ca);
 }
@@ -1054,7 +1066,6 @@ int Engine::forward_cached(const void *cache, int n_slots, const int *window_slo
     prof_clear();
     prof_.reserve(1024);
     host_maps_.clear();
-    host_chain_.clear();
     if (cfg_.precision == RVSR_F16) return run<__half>(ar, false, frames, x_dtype, out, out_dtype, B, H, W, s, &ca);
     return run<float>(ar, false, frames, x_dtype, out, out_dtype, B, H, W, s, &ca);
 }

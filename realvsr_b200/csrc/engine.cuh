@@ -8,23 +8,59 @@
 
 namespace rvsr {
 
-// Bump allocator over the caller-provided workspace.  With base == nullptr it only counts,
-// which is how rvsr_engine_workspace_bytes() sizes the workspace from the same code path
-// that later runs the forward.
+// Allocator over the caller-provided workspace: best-fit free list with coalescing, so that an activation's memory is
+// reused as soon as the plan says it is dead (Plan::drop) -- the peak, not the sum, of the live tensors sizes the
+// workspace (round 1's bump allocator needed ~6 GB for a batch of 4 cfg2 windows).  With base == nullptr it only does the
+// bookkeeping, which is how rvsr_engine_workspace_bytes() sizes the workspace from the same code path that later runs
+// the forward: both runs see the same sequence of alloc / free calls and therefore the same offsets.
+// Reuse is safe without extra synchronisation: every kernel of a forward is enqueued on ONE stream, and a kernel only
+// touches activations after griddepcontrol.wait, i.e. after every earlier kernel of the stream has completed.
 struct Arena {
+    struct Block { size_t off, size; bool free; };
     char *base = nullptr;
-    size_t cap = 0, off = 0, peak = 0;
+    size_t cap = 0, peak = 0;
     bool overflow = false;
+    std::vector<Block> blocks;  // sorted by offset, contiguous from 0
     void *alloc(size_t bytes) {
-        const size_t a = align_up(off, 1024);
-        off = a + align_up(bytes, 1024);
-        if (off > peak) peak = off;
-        if (base == nullptr) return reinterpret_cast<void *>(size_t(1024));  // dry run: non-null dummy
-        if (off > cap) { overflow = true; return nullptr; }
-        return base + a;
+        const size_t need = align_up(bytes == 0 ? 1 : bytes, 1024);
+        int best = -1;
+        for (int i = 0; i < (int)blocks.size(); ++i)
+            if (blocks[i].free && blocks[i].size >= need && (best < 0 || blocks[i].size < blocks[best].size)) best = i;
+        size_t off;
+        if (best >= 0) {
+            off = blocks[best].off;
+            if (blocks[best].size > need) {
+                const Block rest{off + need, blocks[best].size - need, true};
+                blocks[best].size = need;
+                blocks.insert(blocks.begin() + best + 1, rest);
+            }
+            blocks[best].free = false;
+        } else {
+            if (!blocks.empty() && blocks.back().free) {  // grow the free tail instead of leaving a hole
+                off = blocks.back().off;
+                blocks.back().size = need;
+                blocks.back().free = false;
+            } else {
+                off = blocks.empty() ? 0 : blocks.back().off + blocks.back().size;
+                blocks.push_back(Block{off, need, false});
+            }
+            if (off + need > peak) peak = off + need;
+        }
+        if (base == nullptr) return reinterpret_cast<void *>(size_t(1024) + off);  // dry run: non-null, offset recoverable
+        if (off + need > cap) { overflow = true; return nullptr; }
+        return base + off;
     }
-    size_t mark() const { return off; }
-    void release(size_t m) { off = m; }
+    void free(const void *p) {
+        if (p == nullptr) return;
+        const size_t off = base == nullptr ? reinterpret_cast<size_t>(p) - 1024 : (size_t)(reinterpret_cast<const char *>(p) - base);
+        for (int i = 0; i < (int)blocks.size(); ++i) {
+            if (blocks[i].off != off || blocks[i].free) continue;
+            blocks[i].free = true;
+            if (i + 1 < (int)blocks.size() && blocks[i + 1].free) { blocks[i].size += blocks[i + 1].size; blocks.erase(blocks.begin() + i + 1); }
+            if (i > 0 && blocks[i - 1].free) { blocks[i - 1].size += blocks[i].size; blocks.erase(blocks.begin() + i); }
+            return;
+        }
+    }
 };
 
 // Channel-blocked activation [N][C8][H][W][8].
@@ -114,8 +150,6 @@ class Engine {
     bool profiling_ = false;
     std::vector<ProfEntry> prof_;
     std::vector<std::vector<int>> host_maps_;
-  public:
-    std::vector<std::vector<char>> host_chain_;  // layer tables of the chain launches of the current forward (async H2D sources)
 };
 
 // tc_kernels.cu: tcgen05 paths (fp16 storage).  Return RVSR_E_UNSUPPORTED when the shape is
@@ -128,18 +162,6 @@ size_t tc_conv_weight_bytes(int Cout, int Cin, int ks, int mode = 0);
 int pack_weight_tc(const float *w_oihw, void *dst, int Cout, int Cin, int ks, int mode, cudaStream_t s);
 size_t tc2_weight_bytes(int Cout, int Cin, int ks, int mode = 0);
 int pack_weight_tc2(const float *w_oihw, void *dst, int Cout, int Cin, int ks, int mode, cudaStream_t s);
-// one persistent launch for a run of same-shape 64 -> 64 3x3 convolutions (tile-level dataflow between layers)
-struct ChainLayerDesc {
-    const void *src;        // [N][8][H][W][8] fp16, densely packed
-    const void *w_tc2;      // pack_weight_tc2 layout
-    const float *bias;
-    void *out;
-    const void *residual;   // or null
-    int act;
-};
-size_t conv_chain_scratch_bytes(int L, int N, int H);
-bool conv_chain_supported(int L, int N, int H, int W);
-int launch_conv_chain(const ChainLayerDesc *layers, int L, int N, int H, int W, void *scratch, std::vector<char> &staging, cudaStream_t s);
 size_t tc_tapn_weight_bytes(int Cout, int Cin, int ks);   // conv_last "taps in N" kernel (Cout <= 3)
 int pack_weight_tapn(const float *w_oihw, void *dst, int Cout, int Cin, cudaStream_t s);
 int launch_conv_tapn(const ConvOp &op, const void *w_tapn, cudaStream_t s);

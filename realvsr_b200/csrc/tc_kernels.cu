@@ -910,312 +910,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
     if (warp == 3) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
 }
 
-// ---------------------------------------------------------------- chain of 64 -> 64 3x3 convolutions, ONE launch
-// A run of same-shape convolutions (the residual trunks: conv - ReLU - conv + skip, 10 and 20 layers deep) pays
-// ~7 us per kernel boundary (drain, launch, prologue, first halo load, first tile: RVSR_TC_STAMPS) for 12 us of
-// work at 4 images.  conv_chain_kernel runs the whole run in one persistent CTA-pair kernel:
-//   * layers are executed in order by every cluster over the same static tile assignment; barriers, TMEM and the
-//     pipeline stay alive across layers (all phase counters run on the cluster-local tile sequence k);
-//   * tile-level dataflow instead of a grid barrier: the epilogue publishes "tile done" on a per (layer, image,
-//     tile row) counter (stores -> __threadfence -> red.release.gpu); the producer of layer l acquires the three rows
-//     it needs from layer l - 1 (ld.acquire.gpu -> fence.proxy.async -> TMA).  Every cluster finishes layer l - 1
-//     without waiting on layer l, all CTAs are co-resident (grid = SM count), so the waits cannot deadlock;
-//   * weights are double buffered (2 x 36 KB per CTA): layer l + 1 is staged into the buffer of layer l - 1 as
-//     soon as the issuers have committed that layer (LDONE), tested without blocking between halo loads.
-struct alignas(128) TcChainLayer {
-    CUtensorMap tmap;        // input of this layer
-    const __half *w;         // CTA-pair layout [rank][tap][8][32][8]
-    const float *bias;       // [64] or null
-    __half *out;
-    const __half *residual;  // null, or a tensor produced earlier (added after the activation)
-    int act, pad[3];
-};
-struct alignas(64) TcChainParams {
-    CUtensorMap tmaps[20];       // input of every layer (kernel-parameter space, like the single-layer kernels)
-    const TcChainLayer *layers;  // device
-    unsigned *flags;             // [nlayers][N][tiles_y], zeroed before the launch
-    long long image_stride;      // halfs per image (every tensor of the chain: 64 channels, H x W)
-    int nlayers, N, H, W, nstages;
-    int tiles_x, tiles_y, num_tiles;
-    TileDiv td;
-    int debug;  // RVSR_CHAIN_DEBUG timing experiments (results may be wrong): 1 no producer fence, 2 no epilogue fence, 4 no counter wait
-};
-constexpr bool CHAIN_RES_CG = true;  // residuals were written earlier in the same kernel: L2-coherent loads (measured: no cost vs ld.global.nc)
-constexpr int CHAIN_MAX_LAYERS = 20;  // bias table in shared memory: 20 x 256 B leaves room for six halo stages
-
-__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned *p) {
-    unsigned v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void red_relaxed_gpu_add(unsigned *p, unsigned v) {  // release = the fence.acq_rel.gpu before it
-    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_chain_kernel(const __grid_constant__ TcChainParams p) {
-    constexpr int NT = 64, NH2 = 32, KS = 3, KK = 9, PAD = 1, VALID = TC_TW - 2, HALO_ROWS = TC_ROWS + 2;
-    constexpr int PLANE_BYTES = HALO_ROWS * TC_TW * 16, C8S = 8;
-    constexpr int ACC = 64, MMAW = 3, EG = TC_EPI_GROUPS, NB = 6, TMEM_COLS = 512, WPG = TC_EPI_WARPS / EG;
-    constexpr uint32_t w_bytes = C8S * KK * NH2 * 16, stage_bytes = C8S * PLANE_BYTES;
-    extern __shared__ __align__(1024) uint8_t smem[];
-    const int S = p.nstages, L = p.nlayers;
-    uint8_t *w_s = smem;                              // two weight buffers
-    uint8_t *stage_s = smem + 2 * w_bytes;
-    float *bias_all = reinterpret_cast<float *>(stage_s + (size_t)S * stage_bytes + 128);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(bias_all + CHAIN_MAX_LAYERS * NT);
-    const int base2 = (MMAW + 1) * S;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + base2 + 6 + 2 * NB);
-    const uint32_t bar0 = smem_u32(bars);
-    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-    auto FULL = [&](int w, int st) { return BAR(w * S + st); };
-    auto EMPTY = [&](int st) { return BAR(MMAW * S + st); };
-    auto WFULL = [&](int b) { return BAR(base2 + b); };
-    auto WPEER = [&](int b) { return BAR(base2 + 2 + b); };
-    auto LDONE = [&](int b) { return BAR(base2 + 4 + b); };
-    auto TFULL = [&](int b) { return BAR(base2 + 6 + b); };
-    auto TEMPTY = [&](int b) { return BAR(base2 + 6 + NB + b); };
-    const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
-    const uint32_t rank = blockIdx.x & 1u;
-    const int cid = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
-    const int npairs = (p.num_tiles + 1) / 2;
-    const int K = cid < npairs ? (npairs - cid + nclusters - 1) / nclusters : 0;  // tile pairs of this cluster per layer
-
-    auto load_w = [&](int l) {  // this CTA's half of layer l's weights -> buffer l & 1
-        const int b = l & 1;
-        mbar_expect_tx(WFULL(b), w_bytes);
-        const uint8_t *wg = reinterpret_cast<const uint8_t *>(p.layers[l].w) + (size_t)rank * w_bytes;
-        for (uint32_t o = 0; o < w_bytes; o += 18432) bulk_load(smem_u32(w_s + b * w_bytes + o), wg + o, 18432, WFULL(b));
-    };
-
-    pdl_trigger();
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < MMAW * S; ++i) mbar_init(BAR(i), 2);
-        for (int i = MMAW * S; i < base2 + 4; ++i) mbar_init(BAR(i), 1);      // EMPTY, WFULL x2, WPEER x2
-        mbar_init(LDONE(0), MMAW); mbar_init(LDONE(1), MMAW);
-        for (int i = 0; i < NB; ++i) mbar_init(TFULL(i), 1);
-        for (int i = 0; i < NB; ++i) mbar_init(TEMPTY(i), 2 * WPG);
-        fence_barrier_init();
-        tmem_slot[2] = 0; tmem_slot[3] = 0;  // per epilogue group: (tile, warp) parts stored so far
-        load_w(0);
-        if (L > 1) load_w(1);
-    }
-    if (warp == 3) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    cluster_sync_all();
-    tc_fence_after();
-    const uint32_t tmem_base = uniform_u32(*tmem_slot);
-    pdl_wait();
-
-    if (warp == 0) {
-        if (lane == 0) {
-            // Flat loop over (layer, tile) with a one-tile look-ahead: the dataflow counter of the NEXT tile is requested
-            // (relaxed, L2) before this tile's stage wait, so its round trip never sits on the critical path.
-            // The writers fence (gpu scope) between their stores and the counter update; the reader orders its TMA behind
-            // the counter load with fence.proxy.async (required, see below).
-            const unsigned target = (unsigned)p.tiles_x * (unsigned)WPG;  // per tile row: every tile's 8 epilogue warps
-            struct Tile { int tx, ty, n; const unsigned *fr; unsigned want; };
-            auto tile_at = [&](int l, int kl) {
-                Tile t;
-                int tile = 2 * (cid + kl * nclusters) + (int)rank;
-                if (tile >= p.num_tiles) tile = p.num_tiles - 1;
-                tile_coords(p.td, tile, t.tx, t.ty, t.n);
-                t.fr = (l > 0 && !(p.debug & 4)) ? p.flags + ((size_t)(l - 1) * p.N + t.n) * p.tiles_y + t.ty : nullptr;
-                t.want = target * (unsigned)(1 + (t.ty > 0) + (t.ty + 1 < p.tiles_y));
-                return t;
-            };
-            uint32_t k = 0;
-            int next_w = 2;  // next layer whose weights are still to be requested
-            int l = 0, kl = 0;
-            Tile cur = tile_at(0, 0);
-            unsigned vcur = cur.want;
-            const uint32_t total = (uint32_t)L * (uint32_t)K;
-            for (; k < total; ++k) {
-                int nl = l, nkl = kl + 1;
-                if (nkl == K) { nkl = 0; ++nl; }
-                Tile nxt = cur;
-                unsigned vnxt = 0;
-                if (nl < L) {
-                    nxt = tile_at(nl, nkl);
-                    vnxt = nxt.fr != nullptr ? ld_relaxed_gpu(nxt.fr) : nxt.want;
-                }
-                if (next_w < L && next_w <= l + 1 && mbar_test(LDONE(next_w & 1), (uint32_t)(((next_w - 2) >> 1) & 1))) {
-                    load_w(next_w);
-                    ++next_w;
-                }
-                const int st = (int)(k % (uint32_t)S), w = (int)(k % MMAW);
-                mbar_wait(EMPTY(st), ((k / (uint32_t)S) & 1) ^ 1);
-                if (cur.fr != nullptr) {
-                    uint32_t spin = 0;
-                    while (vcur < cur.want) {  // rare: the previous layer has not finished these rows yet
-                        if (++spin > (1u << 24)) __trap();  // protocol bug: fail the launch instead of hanging the GPU
-                        vcur = ld_relaxed_gpu(cur.fr);
-                    }
-                    if ((p.debug & 16) && spin > 0) atomicAdd(reinterpret_cast<unsigned long long *>(&g_stamps[STAMP_SLOTS - 9][0]), (unsigned long long)spin);
-                    if ((p.debug & 16) && spin > 0) atomicAdd(reinterpret_cast<unsigned long long *>(&g_stamps[STAMP_SLOTS - 9][1]), 1ull);
-                    // The cross-proxy fence on THIS side is required: with a relaxed counter load and only the control
-                    // dependency in front of the TMA, 10 of 24 fresh engines produced a few hundred wrong pixels (a halo read
-                    // before its producer's stores; tools/chain_race2.py).  Either fence.proxy.async or ld.acquire.gpu here
-                    // removes it (0 of 30); the fence is the cheaper one (~0.4 us per tile, on this thread's critical path).
-                    if (p.debug & 8) vcur = ld_acquire_gpu(cur.fr);
-                    if (!(p.debug & 1)) asm volatile("fence.proxy.async;" ::: "memory");
-                }
-                const uint32_t full0 = mapa_rank0(FULL(w, st));
-                if (rank == 0)
-                    mbar_expect_tx(FULL(w, st), 2 * stage_bytes);
-                else
-                    mbar_arrive_cluster(full0);
-                tma_load_3d_2sm(smem_u32(stage_s + (size_t)st * stage_bytes), &p.tmaps[l], full0, (cur.tx * VALID - PAD) * 8,
-                                cur.ty * TC_ROWS - PAD, cur.n * C8S);
-                if (kl == K - 1 && next_w == l + 1 && next_w < L) {  // end of a (short) layer and the next weights not requested yet
-                    mbar_wait(LDONE(next_w & 1), (uint32_t)(((next_w - 2) >> 1) & 1));
-                    load_w(next_w);
-                    ++next_w;
-                }
-                cur = nxt; vcur = vnxt; l = nl; kl = nkl;
-            }
-        }
-    } else if (warp <= MMAW) {
-        if (rank != 0) {
-            if (warp == 1 && lane == 0)
-                for (int l = 0; l < L; ++l) {  // "my half of layer l has landed" -> leader
-                    mbar_wait(WFULL(l & 1), (uint32_t)((l >> 1) & 1));
-                    mbar_arrive_cluster(mapa_rank0(WPEER(l & 1)));
-                }
-        } else {
-            constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((256u >> 4) << 24);
-            const uint32_t mw = (uint32_t)(warp - 1);
-            const uint64_t adesc0 = make_desc(smem_u32(stage_s), PLANE_BYTES, 128);
-            const uint64_t bdesc0 = make_desc(smem_u32(w_s), NH2 * 16, 128);
-            const uint32_t a_hi = (uint32_t)(adesc0 >> 32), b_hi = (uint32_t)(bdesc0 >> 32);
-            const uint32_t a_base = (uint32_t)adesc0, b_base = (uint32_t)bdesc0;
-            constexpr uint32_t stage_units = stage_bytes >> 4, b_tap_step = C8S * NH2;
-            uint32_t k = 0, par = 0;
-            // RVSR_CHAIN_DEBUG & 16: per-layer timeline of issuer 0 of cluster 0 (ns since its first layer started)
-            const bool tl_on = (p.debug & 16) && blockIdx.x == 0 && mw == 0 && lane == 0;
-            unsigned long long tl0 = 0;
-            for (int l = 0; l < L; ++l) {
-                const int b = l & 1;
-                const unsigned long long ta = tl_on ? globaltimer_ns() : 0;
-                mbar_wait(WFULL(b), (uint32_t)((l >> 1) & 1));
-                mbar_wait(WPEER(b), (uint32_t)((l >> 1) & 1));
-                if (tl_on) {
-                    (void)tl0;
-                    g_stamps[STAMP_SLOTS - 1 - (l >> 2)][(l & 3) * 2] = ta;
-                    g_stamps[STAMP_SLOTS - 1 - (l >> 2)][(l & 3) * 2 + 1] = globaltimer_ns();
-                }
-                const uint32_t b_lo0 = b_base + (uint32_t)b * (w_bytes >> 4);
-                for (int kl = 0; kl < K; ++kl, ++k) {
-                    if (k % MMAW != mw) continue;
-                    const uint32_t buf = k % NB, st = k % (uint32_t)S;
-                    mbar_wait(TEMPTY(buf), ((k / NB) & 1) ^ 1);
-                    mbar_wait(FULL(mw, st), (par >> st) & 1);
-                    par ^= 1u << st;
-                    tc_fence_after();
-                    const uint32_t d = tmem_base + buf * ACC;
-                    const uint32_t a_lo0 = a_base + st * stage_units;
-                    if (elect_one()) {
-#pragma unroll
-                        for (int tap = 0; tap < KK; ++tap) {
-                            const uint32_t a_lo = a_lo0 + (uint32_t)((tap / KS) * TC_TW + (tap % KS));
-                            const uint32_t b_lo = b_lo0 + (uint32_t)tap * b_tap_step;
-#pragma unroll
-                            for (int kk = 0; kk < 4; ++kk)
-                                umma_f16_2sm(d, ((uint64_t)a_hi << 32) | (a_lo + (uint32_t)kk * (2 * PLANE_BYTES / 16)),
-                                             ((uint64_t)b_hi << 32) | (b_lo + (uint32_t)kk * (2 * NH2)), idesc, (tap | kk) ? 1u : 0u);
-                        }
-                        umma_commit_2sm(EMPTY(st));
-                        umma_commit_2sm(TFULL(buf));
-                    }
-                    __syncwarp();
-                }
-                if (elect_one()) umma_commit_2sm(LDONE(b));  // every MMA this issuer made for layer l has completed
-                __syncwarp();
-            }
-            if (tl_on) g_stamps[STAMP_SLOTS - 8][0] = globaltimer_ns();
-        }
-    } else if (warp >= TC_EPI_WARP0) {
-        for (int i = threadIdx.x - 32 * TC_EPI_WARP0; i < L * NT; i += 32 * TC_EPI_WARPS) {
-            const float *bp = p.layers[i / NT].bias;
-            bias_all[i] = bp != nullptr ? bp[i % NT] : 0.f;
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
-        const int lq = warp & 3;
-        const int eg = (warp - TC_EPI_WARP0) / WPG;
-        const int half = ((warp - TC_EPI_WARP0) % WPG) >> 2;
-        uint32_t k = 0;
-        unsigned *stored = reinterpret_cast<unsigned *>(tmem_slot + 2) + eg;  // tiles x warps of this group stored so far
-        for (int l = 0; l < L; ++l) {
-            const TcChainLayer *ly = p.layers + l;
-            __half *out = ly->out;
-            const __half *res = ly->residual;
-            const int act = ly->act;
-            unsigned *fl = p.flags + (size_t)l * p.N * p.tiles_y;
-            for (int kl = 0; kl < K; ++kl, ++k) {
-                if ((int)(k % EG) != eg) continue;
-                const int pr = cid + kl * nclusters;
-                const int tile = 2 * pr + (int)rank;
-                const bool real = tile < p.num_tiles;
-                int tx, ty, n;
-                tile_coords(p.td, real ? tile : p.num_tiles - 1, tx, ty, n);
-                const int y = ty * TC_ROWS + lq, x = tx * VALID + lane;
-                const bool valid = real && lane < VALID && y < p.H && x < p.W;
-                const uint32_t buf = k % NB, par = (k / NB) & 1;
-                const uint32_t tempty0 = mapa_rank0(TEMPTY(buf));
-                const uint32_t taddr = tmem_base + buf * ACC + ((uint32_t)(lq * 32) << 16);
-                auto release = [&] {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(tempty0);
-                };
-                if (act == RVSR_ACT_RELU)
-                    epi_c8_fast<RVSR_ACT_RELU, CHAIN_RES_CG>(bias_all + l * NT, out, p.image_stride, res, p.image_stride, p.H, p.W, 8, taddr, half, 0, n,
-                                                     y, x, valid, TFULL(buf), par, release);
-                else if (act == RVSR_ACT_LRELU)
-                    epi_c8_fast<RVSR_ACT_LRELU, CHAIN_RES_CG>(bias_all + l * NT, out, p.image_stride, res, p.image_stride, p.H, p.W, 8, taddr, half, 0, n,
-                                                      y, x, valid, TFULL(buf), par, release);
-                else
-                    epi_c8_fast<RVSR_ACT_NONE, CHAIN_RES_CG>(bias_all + l * NT, out, p.image_stride, res, p.image_stride, p.H, p.W, 8, taddr, half, 0, n,
-                                                     y, x, valid, TFULL(buf), par, release);
-                // ---- publish.  Every warp reports "my part of the tile is stored" on a shared-memory counter of its group
-                // (CTA scope, cheap); ONE warp per tile -- they take turns -- waits until all 8 have reported, fences at GPU
-                // scope (cumulative: it covers the other warps' stores, ordered before it by the CTA-scope handshake) and
-                // bumps the global counters of the three tile rows that read this tile.  A gpu-scope fence costs ~1 us: done
-                // by every warp for every tile it made the epilogue the bottleneck, now each warp pays it every 8th tile.
-                if (p.debug & 32) __threadfence(); else __threadfence_block();
-                __syncwarp();
-                if (lane == 0) atomicAdd_block(stored, 1u);
-                const uint32_t j = k / EG;  // group-local tile sequence number
-                if ((int)(j % WPG) == (warp - TC_EPI_WARP0) % WPG) {
-                    const unsigned need = (unsigned)WPG * (j + 1);
-                    uint32_t spin = 0;
-                    while (*reinterpret_cast<volatile unsigned *>(stored) < need)
-                        if (++spin > (1u << 26)) __trap();
-                    __threadfence_block();
-                    if (real) {
-                        asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy stores -> readable by other SMs' TMA units
-                        if (!(p.debug & 2)) __threadfence();
-                        if (lane < 3) {
-                            const int r = ty + lane - 1;
-                            if (r >= 0 && r < p.tiles_y) red_relaxed_gpu_add(fl + (size_t)n * p.tiles_y + r, (unsigned)WPG);
-                        }
-                    }
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    cluster_sync_all();
-    if (warp == 3) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
-}
-
 // ---------------------------------------------------------------- host side: tensor maps, packing, launch
 static int tc_pick_nt(int Cout, int mode = 0) {
     if (mode == 2) return (Cout % 27 == 0) ? 128 : 0;  // OUT_OM24: 4 deformable groups x 32 columns per pass
@@ -1423,7 +1117,9 @@ int launch_conv_tc(const ConvOp &op, cudaStream_t s) {
     // stride 2 as a real implicit GEMM over the four phase images (RVSR_S2=0: compute at full resolution and subsample)
     static const bool s2_on = !(getenv("RVSR_S2") != nullptr && getenv("RVSR_S2")[0] == '0');
     const bool s2 = s2_on && two_cta && op.stride == 2 && op.w_tc2 != nullptr && pl.NT == 64 && op.ks == 3 && op.out_mode == OUT_C8 &&
-                    op.residual == nullptr && op.H % 2 == 0 && op.W % 2 == 0;
+                    op.residual == nullptr && op.H % 2 == 0 && op.W % 2 == 0 &&
+                    // two stages of four phase tiles next to this CTA's weight half (else: full resolution + subsampled store)
+                    (size_t)op.nsrc * pl.C8s * 9 * 32 * 16 + 128 + 64 * 4 + 512 + 2 * (size_t)4 * pl.C8s * (TC_ROWS + 1) * TC_TW * 16 <= TC_SMEM_LIMIT;
     if (s2) {
         const int Ho = op.H / 2, Wo = op.W / 2;
         for (int i = 0; i < op.nsrc; ++i) {  // 4-D maps {8 channels, W, H, planes}, every other pixel of every other row
@@ -1485,107 +1181,6 @@ int launch_conv_tc(const ConvOp &op, cudaStream_t s) {
 #undef RVSR_TC_CASE
     set_error("tc conv: no kernel instance for ks=%d NT=%d", op.ks, pl.NT);
     return RVSR_E_UNSUPPORTED;
-}
-
-// ---- chain launch: `layers` (host) describes L same-shape 64 -> 64 3x3 convolutions; scratch = device memory for the
-// layer table and the dataflow counters (conv_chain_scratch_bytes), staging = host bytes that must stay alive until the
-// stream has consumed the table copy (the engine keeps it until the next forward).
-size_t conv_chain_scratch_bytes(int L, int N, int H) {
-    return align_up((size_t)L * sizeof(TcChainLayer), 256) + align_up((size_t)L * N * cdiv(H, TC_ROWS) * sizeof(unsigned), 256);
-}
-bool conv_chain_supported(int L, int N, int H, int W) {
-    // OPT-IN (RVSR_CHAIN=1; read at every call so tests can toggle it).  Correct (bit-identical frames, also right after
-    // the workspace held other data) once the producer orders its TMA behind the counter load with fence.proxy.async --
-    // and with that fence on the producer's critical path it is level with, not faster than, the PDL-overlapped
-    // per-layer launches.  Needs every CTA resident at once: see launch_conv_chain.
-    const char *env = getenv("RVSR_CHAIN");
-    const bool on = env != nullptr && env[0] == '1';
-    const long long tiles = (long long)cdiv(W, TC_TW - 2) * cdiv(H, TC_ROWS) * N;
-    const int max_rounds = getenv("RVSR_CHAIN_MAX_ROUNDS") ? atoi(getenv("RVSR_CHAIN_MAX_ROUNDS")) : 1 << 20;  // experiments
-    return on && get_encode() != nullptr && L >= 2 && L <= CHAIN_MAX_LAYERS && tiles >= 2LL * sm_count() &&
-           tiles <= (long long)max_rounds * sm_count();
-}
-int launch_conv_chain(const ChainLayerDesc *layers, int L, int N, int H, int W, void *scratch, std::vector<char> &staging, cudaStream_t s) {
-    RVSR_CHECK_ARG(conv_chain_supported(L, N, H, W) && scratch != nullptr, "conv chain: unsupported configuration");
-    EncodeTiledFn enc = get_encode();
-    staging.assign((size_t)L * sizeof(TcChainLayer) + 128, 0);
-    TcChainLayer *hl = reinterpret_cast<TcChainLayer *>((reinterpret_cast<uintptr_t>(staging.data()) + 127) / 128 * 128);
-    for (int l = 0; l < L; ++l) {
-        const ChainLayerDesc &d = layers[l];
-        RVSR_CHECK_ARG(d.src && d.w_tc2 && d.out, "conv chain: null pointer in layer %d", l);
-        const cuuint64_t dims[3] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)N * 8};
-        const cuuint64_t strides[2] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
-        const cuuint32_t box[3] = {(cuuint32_t)TC_TW * 8, (cuuint32_t)(TC_ROWS + 2), 8};
-        const cuuint32_t estr[3] = {1, 1, 1};
-        CUresult r = enc(&hl[l].tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(d.src), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) {
-            set_error("conv chain: cuTensorMapEncodeTiled failed (%d)", (int)r);
-            return RVSR_E_CUDA;
-        }
-        hl[l].w = reinterpret_cast<const __half *>(d.w_tc2); hl[l].bias = d.bias;
-        hl[l].out = reinterpret_cast<__half *>(d.out); hl[l].residual = reinterpret_cast<const __half *>(d.residual);
-        hl[l].act = d.act;
-    }
-    static_assert(CHAIN_MAX_LAYERS <= 20, "TcChainParams::tmaps");
-    TcChainParams p;
-    memset(&p, 0, sizeof(p));
-    for (int l = 0; l < L; ++l) p.tmaps[l] = hl[l].tmap;
-    p.layers = reinterpret_cast<const TcChainLayer *>(scratch);
-    p.flags = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(scratch) + align_up((size_t)L * sizeof(TcChainLayer), 256));
-    p.image_stride = (long long)64 * H * W;
-    p.nlayers = L; p.N = N; p.H = H; p.W = W;
-    p.tiles_x = cdiv(W, TC_TW - 2); p.tiles_y = cdiv(H, TC_ROWS); p.num_tiles = p.tiles_x * p.tiles_y * N;
-    p.td.tpi = (uint32_t)(p.tiles_x * p.tiles_y); p.td.m_tpi = magic_div(p.td.tpi, (uint32_t)p.num_tiles);
-    p.td.tx = (uint32_t)p.tiles_x; p.td.m_tx = magic_div(p.td.tx, p.td.tpi);
-    const size_t wb = 2 * (size_t)8 * 9 * 32 * 16, stage = (size_t)8 * (TC_ROWS + 2) * TC_TW * 16;
-    const size_t fixed = wb + 128 + CHAIN_MAX_LAYERS * 64 * sizeof(float) + 512;
-    int st = (int)((TC_SMEM_LIMIT - fixed) / stage);
-    if (st > 6) st = 6;
-    RVSR_CHECK_ARG(st >= 2, "conv chain: not enough shared memory");
-    p.nstages = st;
-    static const int cdbg = getenv("RVSR_CHAIN_DEBUG") ? atoi(getenv("RVSR_CHAIN_DEBUG")) : 0;
-    p.debug = cdbg;
-    const size_t smem = fixed + (size_t)st * stage + 1024;
-    RVSR_CUDA(cudaMemcpyAsync(scratch, hl, (size_t)L * sizeof(TcChainLayer), cudaMemcpyHostToDevice, s));
-    RVSR_CUDA(cudaMemsetAsync(p.flags, 0, (size_t)L * N * p.tiles_y * sizeof(unsigned), s));
-    RVSR_TRY(ensure_max_dynamic_smem(reinterpret_cast<const void *>(&conv_chain_kernel), (int)TC_SMEM_LIMIT + 1024));
-    const int npairs = (p.num_tiles + 1) / 2;
-    int clusters = sm_count() / 2;
-    if (clusters > npairs) clusters = npairs;
-    // Every CTA must be resident at once (tile-level dataflow between clusters; a CTA that is not scheduled would be
-    // waited for by the others): never launch more clusters than the device can hold of this kernel.
-    {
-        cudaLaunchConfig_t occ = {};
-        occ.gridDim = dim3(2 * clusters); occ.blockDim = dim3(TC_THREADS); occ.dynamicSmemBytes = smem;
-        cudaLaunchAttribute ca[1];
-        ca[0].id = cudaLaunchAttributeClusterDimension;
-        ca[0].val.clusterDim.x = 2; ca[0].val.clusterDim.y = 1; ca[0].val.clusterDim.z = 1;
-        occ.attrs = ca; occ.numAttrs = 1;
-        int max_clusters = 0;
-        if (cudaOccupancyMaxActiveClusters(&max_clusters, conv_chain_kernel, &occ) == cudaSuccess && max_clusters > 0 &&
-            clusters > max_clusters)
-            clusters = max_clusters;
-        else
-            (void)cudaGetLastError();
-    }
-    launch_k(conv_chain_kernel, dim3(2 * clusters), dim3(TC_THREADS), smem, s, p);
-    RVSR_LAUNCH_CHECK();
-    if (p.debug & 16) {  // per-layer timeline of issuer 0 of cluster 0 (debug only: synchronises)
-        cudaStreamSynchronize(s);
-        static unsigned long long h[STAMP_SLOTS][8];
-        cudaMemcpyFromSymbol(h, g_stamps, sizeof(h));
-        const unsigned long long t0 = h[STAMP_SLOTS - 1][0];
-        printf("[chain timeline] %d layers, N=%d:", L, N);
-        for (int l = 0; l < L; ++l) printf(" %.1f(+%.1f)", (h[STAMP_SLOTS - 1 - (l >> 2)][(l & 3) * 2] - t0) * 1e-3,
-                                           (h[STAMP_SLOTS - 1 - (l >> 2)][(l & 3) * 2 + 1] - h[STAMP_SLOTS - 1 - (l >> 2)][(l & 3) * 2]) * 1e-3);
-        printf(" end %.1f us | counter waits: %llu tiles waited, %llu re-polls (of %d tile loads)\n", (h[STAMP_SLOTS - 8][0] - t0) * 1e-3,
-               h[STAMP_SLOTS - 9][1], h[STAMP_SLOTS - 9][0], p.num_tiles * (L - 1));
-        static unsigned long long zero[8] = {0};
-        cudaMemcpyToSymbol(g_stamps, zero, sizeof(zero), (size_t)(STAMP_SLOTS - 9) * sizeof(zero));
-    }
-    return RVSR_OK;
 }
 
 // ---------------------------------------------------------------- modulated deformable conv (gather -> UMMA)

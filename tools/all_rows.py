@@ -18,6 +18,7 @@ x = synth_input((B, 5, 3, H, W), 8).to("cuda:0").half()
 with torch.no_grad():
     for _ in range(3): net(x)
     rows = net._get_engine(x).profile(x, steps=5)
+print("workspace %.3f GB (RVSR_ARENA_REUSE=%s)" % (net._get_engine(x)._ws.numel() / 1e9, os.environ.get("RVSR_ARENA_REUSE", "1")))
 tot = sum(r["ms"] for r in rows)
 print("B=%d %dx%d: %d launches, sum %.3f ms" % (B, H, W, len(rows), tot))
 for r in rows:
