@@ -122,6 +122,43 @@ def cpu_sample(steps, warmup):
                        (steps, H, W, t, cores)), t
 
 
+def cfg4_time(dev):
+    """BASELINE cfg4: 7-frame window, nf = 128 variant, 540x960 -> 2160x3840 (4K) on one GPU, tiled (9 tiles of 180x320 LQ
+    pixels + 16 pixels of halo, realvsr_b200.video.tiled_forward), fp16 engine on the tcgen05 kernels.  Device time of
+    whole frames (CUDA events), after the main timed regions."""
+    import torch
+    from helpers import edvr_state_shapes
+    from realvsr_b200 import video
+    from realvsr_b200.archs import EDVR_arch as E
+    from synth import synth_input, synth_state_dict
+    try:
+        kw = dict(nf=128, nc=3, nframes=7, groups=8, front_RBs=5, back_RBs=10, w_TSA=True)
+        net = E.EDVR(**kw).eval()
+        net.load_state_dict(synth_state_dict(edvr_state_shapes("EDVR", **kw), 7), strict=True)
+        net = net.to(dev).half()
+        net.exec_path = "engine"
+        x = synth_input((1, 7, 3, 540, 960), 8).to(dev).half()
+        for _ in range(2):
+            y = video.tiled_forward(net, x, tile=(180, 320), halo=16)
+        n = 3
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            y = video.tiled_forward(net, x, tile=(180, 320), halo=16)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        ok = bool(torch.isfinite(y).all())
+        del net, x, y
+        torch.cuda.empty_cache()
+        tf = 38.16e3 / ms  # SURVEY 8d: 38.16 TFLOP per 4K frame (no halo) -> TFLOP/s
+        return dict(ms_per_frame=ms, frames_per_s=1e3 / ms, finite=ok, tflops=tf,
+                    workload="7x3x540x960 -> 3x2160x3840, EDVR nf=128 7 frames groups=8 (16 ch / deformable group), 9 tiles of "
+                             "180x320 + 16 halo; SURVEY 8d floor 23.2 ms (38.16 TFLOP at the measured bf16 peak)")
+    except Exception as e:
+        return dict(unavailable=repr(e)[:200])
+
+
 def gpu_reference_times(dev):
     """SURVEY.md 8(d) "existing GPU kernel" line: the reference network's op sequence with cuDNN convolutions and the
     reference's OWN deform_conv_cuda extension (compiled unmodified into oracle/_ref), on this GPU, fp32 and fp16,
@@ -441,6 +478,7 @@ def main():
         if sustained is not None:
             line["sustained"] = sustained
         if world == 1:
+            line["cfg4"] = cfg4_time(dev)
             line["gpu_reference"] = gpu_reference_times(dev)
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = cpu_sample(steps=2, warmup=1)

@@ -11,7 +11,7 @@
  *   - all device work is enqueued on the cudaStream_t passed as `stream` (void*),
  *     no host synchronisation, no allocation inside per-call entry points; the caller
  *     owns every buffer including the workspace.
- *   - dtype codes: RVSR_F32 = 0, RVSR_F16 = 1.
+ *   - dtype codes: RVSR_F32 = 0, RVSR_F16 = 1, RVSR_BF16 = 2 (DCN operator only).
  *   - "NCHW" tensors are contiguous like the reference's; the engine's private
  *     activation layout (channel-blocked [N][C/8][H][W][8]) never crosses this ABI.
  */
@@ -27,6 +27,9 @@ extern "C" {
 
 #define RVSR_F32 0
 #define RVSR_F16 1
+#define RVSR_BF16 2 /* DCN operator (rvsr_mdcn_fwd / rvsr_mdcn_bwd) only: bfloat16 tensors in and out, fp32 arithmetic inside --
+                       the dtype of a torch.autocast(bfloat16) training step (BASELINE cfg5); the reference's extension has no
+                       bf16 dispatch at all (deform_conv_cuda_kernel.cu:781) */
 
 #define RVSR_OK 0
 #define RVSR_E_INVALID (-1)     /* bad argument / unsupported shape (reference: AT_ERROR / shape_check) */
@@ -66,7 +69,8 @@ int rvsr_mdcn_fwd(const void *input, const void *offset, const void *mask, const
 /* modulated_deform_conv_cuda_backward (deform_conv_cuda.cpp:571-685) + the col2im /
  * col2im_coord kernels (deform_conv_cuda_kernel.cu:635-767).  grad_input, grad_offset,
  * grad_mask are overwritten; grad_weight and grad_bias (may be NULL) must be zeroed by
- * the caller and are accumulated into, like the reference (cpp:659-671). fp32 only. */
+ * the caller and are accumulated into, like the reference (cpp:659-671).  RVSR_F32, or RVSR_BF16 (all ten tensors
+ * bfloat16; gradients are computed and accumulated in fp32 and rounded once on the way out). */
 size_t rvsr_mdcn_bwd_workspace_bytes(int B, int C, int H, int W, int Cout, int kh, int kw,
                                      int stride, int pad, int dil, int groups, int dg, int dtype);
 int rvsr_mdcn_bwd(const void *input, const void *offset, const void *mask, const void *weight,

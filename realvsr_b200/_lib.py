@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librvsr_b200.so")
 
-F32, F16 = 0, 1
+F32, F16, BF16 = 0, 1, 2
 OK, E_INVALID, E_CUDA, E_WORKSPACE, E_STATE, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 ACT_NONE, ACT_LRELU, ACT_RELU = 0, 1, 2
 

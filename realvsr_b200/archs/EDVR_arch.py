@@ -324,9 +324,13 @@ class _EDVRBase(nn.Module):
         l1 = self.feature_extraction(l1)
         l2 = act(self.fea_L2_conv2(act(self.fea_L2_conv1(l1))))
         l3 = act(self.fea_L3_conv2(act(self.fea_L3_conv1(l2))))
-        pyr = [l1.view(B, N, -1, H, W), l2.view(B, N, -1, H // 2, W // 2), l3.view(B, N, -1, H // 4, W // 4)]
-        ref = [lv[:, self.center].contiguous() for lv in pyr]
-        aligned = torch.stack([self.pcd_align([lv[:, i].contiguous() for lv in pyr], ref) for i in range(N)], 1)
+        # The reference aligns the N frames one by one in a Python loop (EDVR_arch.py:297-303); PCD_Align shares its weights
+        # over the frames, so here the loop is folded into the batch: [B*N] neighbours against the centre frame's features
+        # repeated N times -- one set of (larger) kernel launches, identical arithmetic per frame, same autograd graph shape.
+        pyr = [l1, l2, l3]
+        ref = [lv.view(B, N, *lv.shape[1:])[:, self.center:self.center + 1].expand(B, N, *lv.shape[1:]).reshape(lv.shape)
+               for lv in pyr]
+        aligned = self.pcd_align(pyr, ref).view(B, N, -1, H, W)
         fea = self.tsa_fusion(aligned if self.w_TSA else aligned.view(B, -1, H, W))
         out = self.recon_trunk(fea)
         if self._upsample:

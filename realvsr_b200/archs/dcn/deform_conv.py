@@ -29,8 +29,10 @@ def _dtype_code(t):
         return _lib.F32
     if t.dtype == torch.float16:
         return _lib.F16
+    if t.dtype == torch.bfloat16:
+        return _lib.BF16   # bf16 tensors, fp32 arithmetic (torch.autocast(bfloat16) training); the reference has no bf16 dispatch
     # the reference dispatches double/float/half only (AT_DISPATCH_FLOATING_TYPES_AND_HALF)
-    raise RuntimeError("modulated_deform_conv: unsupported dtype %s (float32/float16 only)" % t.dtype)
+    raise RuntimeError("modulated_deform_conv: unsupported dtype %s (float32/float16/bfloat16 only)" % t.dtype)
 
 
 def _stream(t):
@@ -77,20 +79,23 @@ class ModulatedDeformConvFunction(Function):
             raise NotImplementedError
         input, offset, mask, weight, bias = ctx.saved_tensors
         s, p, d, g, dg = ctx.conv
-        f32 = torch.float32
-        # gradients are computed in fp32 (the reference's half path accumulates atomics in half)
-        xi, of, mk, wt, go = [t.detach().to(f32).contiguous() for t in (input, offset, mask, weight, grad_output)]
+        # gradients are computed in fp32 (the reference's half path accumulates atomics in half).  bf16 tensors go through
+        # the ABI as they are (RVSR_BF16: widened and rounded inside the library); fp16 / mixed dtypes are widened here.
+        native_bf16 = all(t.dtype == torch.bfloat16 for t in (input, offset, mask, grad_output))  # weight: fp32 master under autocast
+        wd = torch.bfloat16 if native_bf16 else torch.float32
+        code = _lib.BF16 if native_bf16 else _lib.F32
+        xi, of, mk, wt, go = [t.detach().to(wd).contiguous() for t in (input, offset, mask, weight, grad_output)]
         grad_input, grad_offset, grad_mask = torch.empty_like(xi), torch.empty_like(of), torch.empty_like(mk)
         grad_weight = torch.zeros_like(wt)
-        grad_bias = torch.zeros(weight.shape[0], dtype=f32, device=xi.device) if ctx.with_bias else None
+        grad_bias = torch.zeros(weight.shape[0], dtype=wd, device=xi.device) if ctx.with_bias else None
         B, C, H, W = xi.shape
         Cout, _, kh, kw = wt.shape
         dims = (B, C, H, W, Cout, kh, kw, s, p, d, g, dg)
         L = _lib.lib()
         with torch.cuda.device(xi.device):
-            ws = xi.new_empty(max(1, L.rvsr_mdcn_bwd_workspace_bytes(*dims, _lib.F32)), dtype=torch.uint8)
+            ws = xi.new_empty(max(1, L.rvsr_mdcn_bwd_workspace_bytes(*dims, code)), dtype=torch.uint8)
             _lib.check(L.rvsr_mdcn_bwd(_p(xi), _p(of), _p(mk), _p(wt), _p(go), _p(grad_input), _p(grad_offset),
-                                       _p(grad_mask), _p(grad_weight), _p(grad_bias), *dims, _lib.F32, _p(ws),
+                                       _p(grad_mask), _p(grad_weight), _p(grad_bias), *dims, code, _p(ws),
                                        ws.numel(), _stream(xi)), "modulated_deform_conv backward")
         cast = lambda t, like: None if t is None else t.to(like.dtype)  # noqa: E731
         return (cast(grad_input, input), cast(grad_offset, offset), cast(grad_mask, mask),

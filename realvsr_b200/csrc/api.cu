@@ -121,6 +121,13 @@ size_t rvsr_mdcn_fwd_workspace_bytes(int B, int C, int H, int W, int Cout, int k
     if (dcn_dims(d, B, C, H, W, Cout, kh, kw, stride, pad, dil, groups, dg) != RVSR_OK) return 0;
     Carver cv{nullptr, 0};
     DcnWs ws;
+    if (dtype == RVSR_BF16) {  // fp32 copies of the six tensors (see rvsr_mdcn_fwd)
+        const size_t po = (size_t)d.Ho * d.Wo;
+        for (size_t n : {(size_t)d.B * d.C * d.H * d.W, (size_t)d.B * d.dg * 2 * d.K * po, (size_t)d.B * d.dg * d.K * po,
+                         (size_t)d.Cout * (d.C / d.groups) * d.K, (size_t)d.Cout, (size_t)d.B * d.Cout * po})
+            cv.take(n * 4);
+        dtype = RVSR_F32;
+    }
     carve_dcn(cv, d, dtype, ws);
     return cv.off + 256;
 }
@@ -130,16 +137,33 @@ int rvsr_mdcn_fwd(const void *input, const void *offset, const void *mask, const
                   int groups, int dg, int dtype, void *workspace, size_t workspace_bytes, void *stream) {
     DcnDims d;
     RVSR_TRY(dcn_dims(d, B, C, H, W, Cout, kh, kw, stride, pad, dil, groups, dg));
-    RVSR_CHECK_ARG(dtype == RVSR_F32 || dtype == RVSR_F16, "dcn: bad dtype %d", dtype);
+    RVSR_CHECK_ARG(dtype == RVSR_F32 || dtype == RVSR_F16 || dtype == RVSR_BF16, "dcn: bad dtype %d", dtype);
     if (B == 0) return RVSR_OK;
     RVSR_CHECK_ARG(input && offset && mask && weight && output && workspace, "dcn: null buffer");
     Carver cv{(char *)workspace, workspace_bytes};
     const size_t mis = (size_t)((uintptr_t)workspace % 256);
     if (mis) { cv.base += 256 - mis; cv.cap -= 256 - mis; }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == RVSR_BF16) {  // bfloat16 tensors, fp32 arithmetic: widen, run the fp32 operator, round the result once
+        const size_t po = (size_t)d.Ho * d.Wo;
+        const long long n_in = (long long)d.B * d.C * d.H * d.W, n_off = (long long)d.B * d.dg * 2 * d.K * po, n_msk = n_off / 2,
+                        n_w = (long long)d.Cout * (d.C / d.groups) * d.K, n_out = (long long)d.B * d.Cout * po;
+        float *in32 = (float *)cv.take(n_in * 4), *off32 = (float *)cv.take(n_off * 4), *msk32 = (float *)cv.take(n_msk * 4);
+        float *w32 = (float *)cv.take(n_w * 4), *b32 = (float *)cv.take((size_t)d.Cout * 4), *out32 = (float *)cv.take(n_out * 4);
+        DcnWs ws;
+        carve_dcn(cv, d, RVSR_F32, ws);
+        if (!cv.ok) { set_error("dcn: workspace too small (%zu bytes)", workspace_bytes); return RVSR_E_WORKSPACE; }
+        RVSR_TRY(launch_convert_bf16_f32(input, in32, n_in, s));
+        RVSR_TRY(launch_convert_bf16_f32(offset, off32, n_off, s));
+        RVSR_TRY(launch_convert_bf16_f32(mask, msk32, n_msk, s));
+        RVSR_TRY(launch_convert_bf16_f32(weight, w32, n_w, s));
+        if (bias) RVSR_TRY(launch_convert_bf16_f32(bias, b32, d.Cout, s));
+        RVSR_TRY(mdcn_fwd_t<float>(d, in32, off32, msk32, w32, bias ? b32 : nullptr, out32, RVSR_F32, ws, RVSR_ACT_NONE, s));
+        return launch_convert_f32_bf16(out32, output, n_out, s);
+    }
     DcnWs ws;
     carve_dcn(cv, d, dtype, ws);
     if (!cv.ok) { set_error("dcn: workspace too small (%zu bytes)", workspace_bytes); return RVSR_E_WORKSPACE; }
-    cudaStream_t s = (cudaStream_t)stream;
     if (dtype == RVSR_F16)
         return mdcn_fwd_t<__half>(d, input, offset, mask, weight, bias, output, dtype, ws, RVSR_ACT_NONE, s);
     return mdcn_fwd_t<float>(d, input, offset, mask, weight, bias, output, dtype, ws, RVSR_ACT_NONE, s);
@@ -153,7 +177,14 @@ static size_t mdcn_bwd_ws(const DcnDims &d) {
 size_t rvsr_mdcn_bwd_workspace_bytes(int B, int C, int H, int W, int Cout, int kh, int kw, int stride, int pad, int dil,
                                      int groups, int dg, int dtype) {
     DcnDims d;
-    if (dtype != RVSR_F32 || dcn_dims(d, B, C, H, W, Cout, kh, kw, stride, pad, dil, groups, dg) != RVSR_OK) return 0;
+    if ((dtype != RVSR_F32 && dtype != RVSR_BF16) || dcn_dims(d, B, C, H, W, Cout, kh, kw, stride, pad, dil, groups, dg) != RVSR_OK) return 0;
+    if (dtype == RVSR_BF16) {  // fp32 copies of the five inputs and the five gradients (same carving as rvsr_mdcn_bwd)
+        const size_t po = (size_t)d.Ho * d.Wo;
+        const size_t n_in = (size_t)d.B * d.C * d.H * d.W, n_off = (size_t)d.B * d.dg * 2 * d.K * po, n_w = (size_t)d.Cout * (d.C / d.groups) * d.K;
+        Carver cv{nullptr, 0};
+        for (size_t n : {n_in, n_off, n_off / 2, n_w, (size_t)d.B * d.Cout * po, n_in, n_off, n_off / 2, n_w, (size_t)d.Cout}) cv.take(n * 4);
+        return cv.off + mdcn_bwd_ws(d) + 1024;
+    }
     return mdcn_bwd_ws(d);
 }
 int rvsr_mdcn_bwd(const void *input, const void *offset, const void *mask, const void *weight, const void *grad_output,
@@ -162,13 +193,44 @@ int rvsr_mdcn_bwd(const void *input, const void *offset, const void *mask, const
                   void *workspace, size_t workspace_bytes, void *stream) {
     DcnDims d;
     RVSR_TRY(dcn_dims(d, B, C, H, W, Cout, kh, kw, stride, pad, dil, groups, dg));
-    if (dtype != RVSR_F32) {
-        set_error("rvsr_mdcn_bwd: gradients are computed in fp32 (convert on the host side)");
+    if (dtype != RVSR_F32 && dtype != RVSR_BF16) {
+        set_error("rvsr_mdcn_bwd: fp32 or bf16 tensors (gradients are computed in fp32; convert fp16 on the host side)");
         return RVSR_E_UNSUPPORTED;
     }
     if (B == 0) return RVSR_OK;
     RVSR_CHECK_ARG(input && offset && mask && weight && grad_output && grad_input && grad_offset && grad_mask &&
                        grad_weight && workspace, "dcn bwd: null buffer");
+    if (dtype == RVSR_BF16) {  // widen the inputs, run the fp32 operator on fp32 scratch, round every gradient once
+        Carver cb{(char *)workspace, workspace_bytes};
+        const size_t misb = (size_t)((uintptr_t)workspace % 256);
+        if (misb) { cb.base += 256 - misb; cb.cap -= 256 - misb; }
+        const size_t po = (size_t)d.Ho * d.Wo;
+        const long long n_in = (long long)d.B * d.C * d.H * d.W, n_off = (long long)d.B * d.dg * 2 * d.K * po, n_msk = n_off / 2,
+                        n_w = (long long)d.Cout * (d.C / d.groups) * d.K, n_out = (long long)d.B * d.Cout * po;
+        float *in32 = (float *)cb.take(n_in * 4), *off32 = (float *)cb.take(n_off * 4), *msk32 = (float *)cb.take(n_msk * 4);
+        float *w32 = (float *)cb.take(n_w * 4), *go32 = (float *)cb.take(n_out * 4);
+        float *gin32 = (float *)cb.take(n_in * 4), *goff32 = (float *)cb.take(n_off * 4), *gmsk32 = (float *)cb.take(n_msk * 4);
+        float *gw32 = (float *)cb.take(n_w * 4), *gb32 = (float *)cb.take((size_t)d.Cout * 4);
+        if (!cb.ok || cb.off + mdcn_bwd_ws(d) > cb.cap) { set_error("dcn bwd: workspace too small"); return RVSR_E_WORKSPACE; }
+        cudaStream_t sb = (cudaStream_t)stream;
+        RVSR_TRY(launch_convert_bf16_f32(input, in32, n_in, sb));
+        RVSR_TRY(launch_convert_bf16_f32(offset, off32, n_off, sb));
+        RVSR_TRY(launch_convert_bf16_f32(mask, msk32, n_msk, sb));
+        RVSR_TRY(launch_convert_bf16_f32(weight, w32, n_w, sb));
+        RVSR_TRY(launch_convert_bf16_f32(grad_output, go32, n_out, sb));
+        // grad_weight / grad_bias: summed in fp32 scratch and WRITTEN (a bf16 accumulator would round every partial sum);
+        // for the caller-zeroed tensors the contract asks for, that is the same result
+        RVSR_CUDA(cudaMemsetAsync(gw32, 0, n_w * 4, sb));
+        RVSR_CUDA(cudaMemsetAsync(gb32, 0, (size_t)d.Cout * 4, sb));
+        RVSR_TRY(rvsr_mdcn_bwd(in32, off32, msk32, w32, go32, gin32, goff32, gmsk32, gw32, grad_bias ? gb32 : nullptr, B, C, H, W, Cout, kh, kw,
+                               stride, pad, dil, groups, dg, RVSR_F32, cb.base + cb.off, cb.cap - cb.off, stream));
+        RVSR_TRY(launch_convert_f32_bf16(gin32, grad_input, n_in, sb));
+        RVSR_TRY(launch_convert_f32_bf16(goff32, grad_offset, n_off, sb));
+        RVSR_TRY(launch_convert_f32_bf16(gmsk32, grad_mask, n_msk, sb));
+        RVSR_TRY(launch_convert_f32_bf16(gw32, grad_weight, n_w, sb));
+        if (grad_bias) RVSR_TRY(launch_convert_f32_bf16(gb32, grad_bias, d.Cout, sb));
+        return RVSR_OK;
+    }
     Carver cv{(char *)workspace, workspace_bytes};
     const size_t mis = (size_t)((uintptr_t)workspace % 256);
     if (mis) { cv.base += 256 - mis; cv.cap -= 256 - mis; }

@@ -276,6 +276,8 @@ template <typename T, typename Tin, typename Tout>
 int launch_final_add(const T *res_c8, const Tin *x, Tout *out, int B, int frames, int center, int nc,
                      int H, int W, int scale, cudaStream_t s, const int *center_map = nullptr);
 int launch_convert_f16_f32(const void *src, float *dst, long long n, cudaStream_t s);
+int launch_convert_bf16_f32(const void *src, float *dst, long long n, cudaStream_t s);
+int launch_convert_f32_bf16(const float *src, void *dst, long long n, cudaStream_t s);
 int launch_fill_f32(float *dst, float v, long long n, cudaStream_t s);
 
 // weight packing (host-callable, device work on stream)

@@ -12,6 +12,8 @@
 //   DCN sample/gather  dcn/src/deform_conv_cuda_kernel.cu:467-497, :571-633
 //   DCN contraction    dcn/src/deform_conv_cuda.cpp:539-568
 //   upsample / pools / attention   EDVR_arch.py:111-124, :154-155, :175-207
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace rvsr {
@@ -368,6 +370,28 @@ int launch_convert_f16_f32(const void *src, float *dst, long long n, cudaStream_
     if (n == 0) return RVSR_OK;
     convert_f16_f32_kernel<<<(int)((n + 255) / 256 < 8192 ? (n + 255) / 256 : 8192), 256, 0, s>>>(
         reinterpret_cast<const __half *>(src), dst, n);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+__global__ void convert_bf16_f32_kernel(const __nv_bfloat16 *__restrict__ src, float *__restrict__ dst, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = __bfloat162float(src[i]);
+}
+__global__ void convert_f32_bf16_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = __float2bfloat16_rn(src[i]);
+}
+int launch_convert_bf16_f32(const void *src, float *dst, long long n, cudaStream_t s) {
+    if (n == 0) return RVSR_OK;
+    convert_bf16_f32_kernel<<<(int)((n + 255) / 256 < 8192 ? (n + 255) / 256 : 8192), 256, 0, s>>>(
+        reinterpret_cast<const __nv_bfloat16 *>(src), dst, n);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+int launch_convert_f32_bf16(const float *src, void *dst, long long n, cudaStream_t s) {
+    if (n == 0) return RVSR_OK;
+    convert_f32_bf16_kernel<<<(int)((n + 255) / 256 < 8192 ? (n + 255) / 256 : 8192), 256, 0, s>>>(
+        src, reinterpret_cast<__nv_bfloat16 *>(dst), n);
     RVSR_LAUNCH_CHECK();
     return RVSR_OK;
 }

@@ -1016,6 +1016,7 @@ int pack_weight_tc2(const float *w_oihw, void *dst, int Cout, int Cin, int ks, i
 struct TcConvPlan {
     int NT, passes, KS, C8s, nstages;
     size_t smem;
+    bool pair_only;  // the weights only fit split over a CTA pair (cta_group::2 kernel)
 };
 static bool tc_conv_plan(const ConvOp &op, TcConvPlan &pl) {
     if (op.w_tc == nullptr || (op.ks != 1 && op.ks != 3) || op.nsrc < 1) return false;
@@ -1042,8 +1043,15 @@ static bool tc_conv_plan(const ConvOp &op, TcConvPlan &pl) {
     pl.C8s = C / 8;
     const size_t wb = (size_t)op.nsrc * pl.C8s * op.ks * op.ks * pl.NT * 16;
     const size_t stage = (size_t)pl.C8s * (TC_ROWS + op.ks - 1) * TC_TW * 16;
-    const size_t fixed = wb + 128 + pl.NT * 4 + 512;
-    if (fixed + 2 * stage > TC_SMEM_LIMIT) return false;
+    size_t fixed = wb + 128 + pl.NT * 4 + 512;
+    pl.pair_only = false;
+    if (fixed + 2 * stage > TC_SMEM_LIMIT) {
+        // the CTA-pair kernel keeps half of the weight rows per CTA (nf = 128: 256 -> 64 and 128 -> 216 contractions)
+        const bool pair = op.w_tc2 != nullptr && op.ks == 3 && op.stride == 1 && (pl.NT == 128 || (pl.NT == 64 && op.out_mode == OUT_C8));
+        fixed = wb / 2 + 128 + pl.NT * 4 + 512;
+        if (!pair || fixed + 2 * stage > TC_SMEM_LIMIT) return false;
+        pl.pair_only = true;
+    }
     pl.nstages = (int)((TC_SMEM_LIMIT - fixed) / stage);
     if (pl.nstages > 6) pl.nstages = 6;
     pl.smem = fixed + pl.nstages * stage + 1024;
@@ -1140,7 +1148,7 @@ int launch_conv_tc(const ConvOp &op, cudaStream_t s) {
         p.td.tpi = (uint32_t)(p.tiles_x * p.tiles_y); p.td.m_tpi = magic_div(p.td.tpi, (uint32_t)p.num_tiles);
         p.td.tx = (uint32_t)p.tiles_x; p.td.m_tx = magic_div(p.td.tx, p.td.tpi);
     }
-    if (two_cta && op.w_tc2 != nullptr && (pl.NT == 64 || pl.NT == 128) && op.ks == 3 && p.num_tiles >= 4 &&
+    if ((two_cta || pl.pair_only) && op.w_tc2 != nullptr && (pl.NT == 64 || pl.NT == 128) && op.ks == 3 && (p.num_tiles >= 4 || pl.pair_only) &&
         (pl.NT == 128 || op.out_mode == OUT_C8) && (op.stride == 1 || s2)) {
         const size_t wb2 = (size_t)op.nsrc * pl.C8s * 9 * (pl.NT / 2) * 16;
         const size_t stage = s2 ? (size_t)4 * pl.C8s * (TC_ROWS + 1) * TC_TW * 16 : (size_t)pl.C8s * (TC_ROWS + 2) * TC_TW * 16;
@@ -1174,6 +1182,7 @@ int launch_conv_tc(const ConvOp &op, cudaStream_t s) {
         RVSR_LAUNCH_CHECK();
         return RVSR_OK;
     }
+    RVSR_CHECK_ARG(!pl.pair_only, "tc conv: this shape needs the CTA-pair kernel");
 #define RVSR_TC_CASE(KS_, NT_) \
     if (op.ks == KS_ && pl.NT == NT_) return launch_conv_tc_t<KS_, NT_>(p, pl, sms, s);
     RVSR_TC_CASE(3, 16) RVSR_TC_CASE(3, 64) RVSR_TC_CASE(3, 128)

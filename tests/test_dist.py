@@ -104,3 +104,66 @@ def test_sharded_sr_pipeline_gloo(total, src):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(res)
+
+
+# ---------------------------------------------------------------- NCCL, real model (needs two GPUs)
+def _nccl_worker(rank, world, port, q):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p_ in (root, os.path.join(root, "tests"), os.path.join(root, "tests", "golden")):
+        if p_ not in sys.path:
+            sys.path.insert(0, p_)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from helpers import load_case
+        from realvsr_b200.archs import EDVR_arch as E
+        from synth import synth_input
+        c = load_case("edvr_nf64_crop")
+        net = E.EDVR(**c["kwargs"]).eval()
+        net.load_state_dict(c["sd"], strict=True)
+        net = net.to(dev).half()
+        net.exec_path = "engine"
+        total, (H, W) = 5, c["x"].shape[-2:]
+        clips = synth_input((total, 5, 3, H, W), 77).half()
+        with torch.no_grad():
+            want = net(clips.to(dev)) if rank == 0 else None          # all windows on one GPU
+        # 1. blocking scatter -> model -> gather
+        got = D.sr_windows(net, clips.to(dev) if rank == 0 else None, shape=tuple(clips.shape), dtype=torch.float16, device=dev, src=0)
+        ok = bool(torch.equal(got, want)) if rank == 0 else got is None
+        # 2. the double-buffered host pipeline of bench.py's cfg3 section
+        eng = net._get_engine(clips[:1].to(dev))
+        sh = D.ShardedSR(lambda xc, yc: eng.forward(xc, out=yc), total, (5, 3, H, W), (3, 4 * H, 4 * W), torch.float16, dev, src=0, chunk=2)
+        if rank == 0:
+            jobs = [(clips.pin_memory(), torch.empty(total, 3, 4 * H, 4 * W, dtype=torch.float16).pin_memory()) for _ in range(3)]
+            sh.run(jobs)
+            ok = ok and all(bool(torch.equal(o, want.cpu())) for _, o in jobs) and sh.bytes_scatter > 0 and sh.bytes_gather > 0
+        else:
+            sh.run(3)
+        q.put(ok)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_window_sharding_over_nccl_with_the_real_model():
+    """BASELINE cfg3's plumbing on real hardware: 5 windows scattered from rank 0 over NCCL, super-resolved by the fp16 engine
+    on two GPUs, gathered back -- bit-identical to all windows on one GPU, for the blocking helper (dist.sr_windows) and for
+    the double-buffered host pipeline (dist.ShardedSR) that bench.py's `cfg3` key times."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert all(res)

@@ -225,6 +225,41 @@ def test_mdcn_bwd_no_bias_and_fp16_inputs():
         assert t.grad.dtype == torch.float16 and rel_err(t.grad.float().cpu(), r) < 3e-3
 
 
+def test_mdcn_bf16_forward_and_backward_vs_oracle():
+    """RVSR_BF16 (BASELINE cfg5's dtype): bfloat16 tensors through the ABI, fp32 arithmetic inside.  Against the fp32 C oracle
+    on the same bf16-rounded inputs; the only extra error is the final rounding of each result to bf16 (2^-9 relative)."""
+    x, off, msk, w, b, (s, p, d, g, dg) = _case(B=2, C=16, H=12, W=10, Cout=16, dg=4)
+    r = lambda t: t.bfloat16().float()  # noqa: E731
+    go = synth_normal((2, 16, 12, 10), 79)
+    ref = O.dcn_forward(r(x), r(off), r(msk), r(w), r(b), s, p, d, g, dg)
+    gref = O.dcn_backward(r(x), r(off), r(msk), r(w), r(go), s, p, d, g, dg, with_bias=True)
+    leaves = [t.to(DEV).bfloat16().requires_grad_() for t in (x, off, msk, w, b)]
+    y = D.modulated_deform_conv(*leaves, s, p, d, g, dg)
+    assert y.dtype == torch.bfloat16 and rel_err(y.float().cpu(), ref) < 6e-3
+    y.backward(go.to(DEV).bfloat16())
+    for t, gr, name in zip(leaves, gref, ("x", "offset", "mask", "weight", "bias")):
+        assert t.grad.dtype == torch.bfloat16 and rel_err(t.grad.float().cpu(), gr) < 8e-3, name
+
+
+def test_training_step_bf16_autocast():
+    """cfg5 as BASELINE states it: the training step under torch.autocast(bfloat16) -- torch's convolutions in bf16, the DCN
+    through RVSR_BF16.  Loss close to the fp32 step's, finite gradients on every parameter."""
+    from helpers import load_case
+    from realvsr_b200.archs import EDVR_arch as E
+    c = load_case("edvr_tiny")
+    net = E.EDVR(**c["kwargs"]).train()
+    net.load_state_dict(c["sd"], strict=True)
+    net = net.to(DEV)
+    x = c["x"].to(DEV)
+    gt = synth_normal(tuple(c["out"].shape), 5, std=0.3).to(DEV)
+    l32 = float(torch.nn.functional.l1_loss(net(x), gt).detach())
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        loss = torch.nn.functional.l1_loss(net(x).float(), gt)
+    loss.backward()
+    assert abs(float(loss.detach()) - l32) < 2e-2 * max(l32, 1e-3)
+    assert all(p_.grad is not None and bool(torch.isfinite(p_.grad).all()) for p_ in net.parameters())
+
+
 def test_training_step_through_module_path():
     """cfg5-shaped smoke (tiny): EDVR module path forward + L1 loss + backward through our DCN fwd/bwd;
     gradients reach every parameter and match a finite-difference probe on one DCN weight."""

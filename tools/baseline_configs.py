@@ -22,7 +22,7 @@ def timed(fn, n):
 
 which = sys.argv[1:] or ["cfg4", "cfg5"]
 if "cfg4" in which:
-    # 7-frame window, 128-channel variant, 540x960 -> 2160x3840, tiled (nf = 128 runs on the CUDA-core fp16 kernels)
+    # 7-frame window, 128-channel variant, 540x960 -> 2160x3840, tiled (nf = 128 on the tcgen05 kernels: 64-channel source split, output halves)
     kw = dict(nf=128, nc=3, nframes=7, groups=8, front_RBs=5, back_RBs=10, w_TSA=True)
     net = E.EDVR(**kw).eval()
     net.load_state_dict(synth_state_dict(edvr_state_shapes("EDVR", **kw), 7), strict=True)

@@ -1,0 +1,29 @@
+"""Where the cfg5 training step spends its time (torch profiler, CUDA kernels grouped by name)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")):
+    sys.path.insert(0, p)
+import torch
+import torch.nn.functional as F
+from helpers import edvr_state_shapes
+from realvsr_b200.archs import EDVR_arch as E
+from synth import synth_input, synth_state_dict
+kw = dict(nf=64, nc=3, nframes=5, groups=8, front_RBs=5, back_RBs=10, w_TSA=True)
+net = E.EDVR(**kw)
+net.load_state_dict(synth_state_dict(edvr_state_shapes("EDVR", **kw), 7), strict=True)
+net = net.to("cuda:0").train()
+x = synth_input((16, 5, 3, 64, 64), 9).to("cuda:0")
+gt = synth_input((16, 3, 256, 256), 10).to("cuda:0")
+amp = os.environ.get("AMP", "0") == "1"
+def step():
+    net.zero_grad(set_to_none=True)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+        loss = F.l1_loss(net(x).float(), gt)
+    loss.backward()
+for _ in range(3): step()
+torch.cuda.synchronize()
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for _ in range(3): step()
+    torch.cuda.synchronize()
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=18, max_name_column_width=70))
