@@ -61,7 +61,7 @@ def main(tag):
     json.dump(traffic, open(os.path.join(pr, "ncu_traffic.json"), "w"), indent=1)
     print(out.getvalue())
     for rep, name in (("prof_conv.ncu-rep", "ncu_conv3x3"), ("prof_dcn.ncu-rep", "ncu_dcn"), ("prof_tapn.ncu-rep", "ncu_conv_last_tapn"),
-                      ("prof_chain.ncu-rep", "ncu_conv_chain")):
+                      ("prof_fused.ncu-rep", "ncu_dcn_pack_fused")):
         path = os.path.join(go, rep)
         if os.path.exists(path):
             buf = io.StringIO()
