@@ -24,7 +24,8 @@ def main():
         m = re.search(r"Function : (\S+)", line)
         if m:
             cur = next(names)
-            cur = re.sub(r"\(.*", "", cur).replace("rvsr::", "")
+            cur = cur.replace("(anonymous namespace)::", "").replace("rvsr::", "")
+            cur = re.sub(r"\(.*", "", cur)
             counts[cur] = collections.Counter()
             continue
         m = re.search(r"^\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
