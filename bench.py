@@ -159,6 +159,46 @@ def cfg4_time(dev):
         return dict(unavailable=repr(e)[:200])
 
 
+def cfg5_time(dev):
+    """BASELINE cfg5: one training step -- batch 16 of 5x3x64x64 patches, EDVR nf=64, forward + L1 loss + backward (no
+    optimizer), under torch.autocast(bfloat16) and in fp32.  Module path: torch's convolutions (cuDNN, exactly where the
+    reference uses nn.Conv2d) + this repo's DCN operator forward / backward (bf16: dcn_bwd_tc_kernel on tcgen05)."""
+    import torch
+    import torch.nn.functional as F
+    from helpers import edvr_state_shapes
+    from realvsr_b200.archs import EDVR_arch as E
+    from synth import synth_input, synth_state_dict
+    try:
+        net = E.EDVR(**CFG)
+        net.load_state_dict(synth_state_dict(edvr_state_shapes("EDVR", **CFG), 7), strict=True)
+        net = net.to(dev).train()
+        x = synth_input((16, 5, 3, 64, 64), 9).to(dev)
+        gt = synth_input((16, 3, 256, 256), 10).to(dev)
+        out = dict(workload="B=16, 5x3x64x64 -> 256x256, forward + L1 + backward, no optimizer step; SURVEY 8d floor 2.0 ms",
+                   unit="ms/step")
+        for name, amp in (("bf16_autocast", True), ("fp32", False)):
+            def step():
+                net.zero_grad(set_to_none=True)
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+                    loss = F.l1_loss(net(x).float(), gt)
+                loss.backward()
+                return loss
+            for _ in range(2):
+                step()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                loss = step()
+            e1.record()
+            torch.cuda.synchronize()
+            out[name] = dict(ms=e0.elapsed_time(e1) / 3, loss=float(loss.detach()))
+        del net, x, gt
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:
+        return dict(unavailable=repr(e)[:200])
+
+
 def gpu_reference_times(dev):
     """SURVEY.md 8(d) "existing GPU kernel" line: the reference network's op sequence with cuDNN convolutions and the
     reference's OWN deform_conv_cuda extension (compiled unmodified into oracle/_ref), on this GPU, fp32 and fp16,
@@ -479,6 +519,7 @@ def main():
             line["sustained"] = sustained
         if world == 1:
             line["cfg4"] = cfg4_time(dev)
+            line["cfg5"] = cfg5_time(dev)
             line["gpu_reference"] = gpu_reference_times(dev)
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = cpu_sample(steps=2, warmup=1)

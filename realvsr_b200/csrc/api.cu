@@ -183,7 +183,8 @@ size_t rvsr_mdcn_bwd_workspace_bytes(int B, int C, int H, int W, int Cout, int k
         const size_t n_in = (size_t)d.B * d.C * d.H * d.W, n_off = (size_t)d.B * d.dg * 2 * d.K * po, n_w = (size_t)d.Cout * (d.C / d.groups) * d.K;
         Carver cv{nullptr, 0};
         for (size_t n : {n_in, n_off, n_off / 2, n_w, (size_t)d.B * d.Cout * po, n_in, n_off, n_off / 2, n_w, (size_t)d.Cout}) cv.take(n * 4);
-        return cv.off + mdcn_bwd_ws(d) + 1024;
+        const size_t simt = cv.off + mdcn_bwd_ws(d) + 1024, tc = dcn_bwd_tc_workspace_bytes(d.B, d.H, d.W) + 512;
+        return simt > tc ? simt : tc;
     }
     return mdcn_bwd_ws(d);
 }
@@ -200,7 +201,12 @@ int rvsr_mdcn_bwd(const void *input, const void *offset, const void *mask, const
     if (B == 0) return RVSR_OK;
     RVSR_CHECK_ARG(input && offset && mask && weight && grad_output && grad_input && grad_offset && grad_mask &&
                        grad_weight && workspace, "dcn bwd: null buffer");
-    if (dtype == RVSR_BF16) {  // widen the inputs, run the fp32 operator on fp32 scratch, round every gradient once
+    if (dtype == RVSR_BF16 && dcn_bwd_tc_supported(C, Cout, kh, kw, stride, pad, dil, groups, dg) &&
+        workspace_bytes >= dcn_bwd_tc_workspace_bytes(B, H, W) + 256)
+        // EDVR's shape class: grad_col / grad_weight contractions on tcgen05, bf16 operands (dcn_bwd_tc.cu)
+        return launch_dcn_bwd_tc(input, offset, mask, weight, grad_output, grad_input, grad_offset, grad_mask, grad_weight, grad_bias, B, H, W,
+                                 workspace, workspace_bytes, (cudaStream_t)stream);
+    if (dtype == RVSR_BF16) {  // other shapes: widen the inputs, run the fp32 operator on fp32 scratch, round every gradient once
         Carver cb{(char *)workspace, workspace_bytes};
         const size_t misb = (size_t)((uintptr_t)workspace % 256);
         if (misb) { cb.base += 256 - misb; cb.cap -= 256 - misb; }

@@ -181,6 +181,12 @@ size_t tc_pack_om_weight_bytes(int Cout, int Cin, int dg);
 int pack_weight_om_stream(const float *w_oihw, void *dst, int Cout, int Cin, int dg, cudaStream_t s);
 bool tc_pack_fused_supported(const PackFusedOp &op);
 int launch_pack_fused(const PackFusedOp &op, cudaStream_t s);
+// dcn_bwd_tc.cu: DCN backward on the tensor cores (bf16 tensors, EDVR's nf = 64 shape class)
+bool dcn_bwd_tc_supported(int C, int Cout, int kh, int kw, int stride, int pad, int dil, int groups, int dg);
+size_t dcn_bwd_tc_workspace_bytes(int B, int H, int W);
+int launch_dcn_bwd_tc(const void *input, const void *offset, const void *mask, const void *weight, const void *grad_output,
+                      void *grad_input, void *grad_offset, void *grad_mask, void *grad_weight, void *grad_bias, int B, int H, int W,
+                      void *workspace, size_t workspace_bytes, cudaStream_t s);
 bool tc_dcn_supported(const DcnOp &op);
 int launch_dcn_tc(const DcnOp &op, cudaStream_t s);
 size_t tc_dcn_weight_bytes(int Cout, int C, int K);

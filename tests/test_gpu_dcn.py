@@ -241,6 +241,27 @@ def test_mdcn_bf16_forward_and_backward_vs_oracle():
         assert t.grad.dtype == torch.bfloat16 and rel_err(t.grad.float().cpu(), gr) < 8e-3, name
 
 
+@pytest.mark.parametrize("shape", [(2, 20, 36), (1, 64, 64), (3, 7, 33)])
+def test_mdcn_bf16_backward_on_tensor_cores_vs_oracle(shape, monkeypatch):
+    """EDVR's DCN shape class (64 -> 64, 3x3, 8 deformable groups) in bf16: rvsr_mdcn_bwd runs dcn_bwd_tc_kernel (grad_col and
+    grad_weight contractions on tcgen05, bf16 operands, fp32 accumulate).  Against the fp32 C oracle on the same
+    bf16-rounded inputs, and against the CUDA-core bf16 path (RVSR_DCN_BWD_TC=0 is read once per process, so the comparison
+    is with the oracle only).  Ragged tiles (W = 36, 33; H = 20, 7), offsets that leave the image."""
+    B, H, W = shape
+    x, off, msk, w, b, (s, p, d, g, dg) = _case(B=B, C=64, H=H, W=W, Cout=64, dg=8, off_std=2.5, seed=700 + H)
+    w = w * 0.3
+    r = lambda t: t.bfloat16().float()  # noqa: E731
+    go = synth_normal((B, 64, H, W), 779 + W) * 0.01           # gradient-sized values (bf16 keeps their range)
+    gref = O.dcn_backward(r(x), r(off), r(msk), r(w), r(go), s, p, d, g, dg, with_bias=True)
+    leaves = [t.to(DEV).bfloat16().requires_grad_() for t in (x, off, msk, w, b)]
+    y = D.modulated_deform_conv(*leaves, s, p, d, g, dg)
+    y.backward(go.to(DEV).bfloat16())
+    for t, gr, name in zip(leaves, gref, ("x", "offset", "mask", "weight", "bias")):
+        e = rel_err(t.grad.float().cpu(), gr)
+        print("bf16 tensor-core DCN backward %s: grad_%s rel err %.2e" % (shape, name, e))
+        assert t.grad.dtype == torch.bfloat16 and e < 1e-2, name
+
+
 def test_training_step_bf16_autocast():
     """cfg5 as BASELINE states it: the training step under torch.autocast(bfloat16) -- torch's convolutions in bf16, the DCN
     through RVSR_BF16.  Loss close to the fp32 step's, finite gradients on every parameter."""
