@@ -27,8 +27,10 @@ extern "C" {
 
 #define RVSR_F32 0
 #define RVSR_F16 1
-#define RVSR_BF16 2 /* DCN operator (rvsr_mdcn_fwd / rvsr_mdcn_bwd) only: bfloat16 tensors in and out, fp32 arithmetic inside --
-                       the dtype of a torch.autocast(bfloat16) training step (BASELINE cfg5); the reference's extension has no
+#define RVSR_BF16 2 /* DCN operator (rvsr_mdcn_fwd / rvsr_mdcn_bwd) only: bfloat16 tensors in and out -- the dtype of a
+                       torch.autocast(bfloat16) training step (BASELINE cfg5).  EDVR's shape class (64 -> 64, 3x3, stride 1,
+                       8 deformable groups) runs on tcgen05 in both directions (bf16 / fp16 operands, fp32 accumulate); other
+                       shapes are widened to the fp32 CUDA-core kernels and rounded once.  The reference's extension has no
                        bf16 dispatch at all (deform_conv_cuda_kernel.cu:781) */
 
 #define RVSR_OK 0

@@ -64,6 +64,11 @@ void carve_dcn(Carver &cv, const DcnDims &d, int dtype, DcnWs &ws) {
     ws.wpack = (float *)cv.take((size_t)cdiv(d.C, 8) * d.K * 8 * cdiv(d.Cout, 64) * 64 * 4);
 }
 
+bool mdcn_fwd_tc_enabled() {  // RVSR_MDCN_FWD_TC=0: 16-bit rvsr_mdcn_fwd stays on the CUDA-core kernel (A/B runs)
+    static const bool off = getenv("RVSR_MDCN_FWD_TC") != nullptr && getenv("RVSR_MDCN_FWD_TC")[0] == '0';
+    return !off;
+}
+
 template <typename T>
 int mdcn_fwd_t(const DcnDims &d, const void *input, const void *offset, const void *mask, const void *weight,
                const void *bias, void *output, int dtype, const DcnWs &ws, int act, cudaStream_t s) {
@@ -121,6 +126,13 @@ size_t rvsr_mdcn_fwd_workspace_bytes(int B, int C, int H, int W, int Cout, int k
     if (dcn_dims(d, B, C, H, W, Cout, kh, kw, stride, pad, dil, groups, dg) != RVSR_OK) return 0;
     Carver cv{nullptr, 0};
     DcnWs ws;
+    size_t tc_bytes = 0;
+    if ((dtype == RVSR_F16 || dtype == RVSR_BF16) && C == 64 && Cout == 64 && kh == 3 && kw == 3 && dg == 8) {  // tcgen05 path of rvsr_mdcn_fwd
+        Carver ct{nullptr, 0};
+        const size_t px = (size_t)B * H * W;
+        for (size_t n : {px * 64 * 2, px * 64 * 2, px * 8 * 96, (size_t)64 * 64 * 9 * 4, (size_t)64 * 4, tc_dcn_weight_bytes(64, 64, 9) + 16}) ct.take(n);
+        tc_bytes = ct.off + 256;
+    }
     if (dtype == RVSR_BF16) {  // fp32 copies of the six tensors (see rvsr_mdcn_fwd)
         const size_t po = (size_t)d.Ho * d.Wo;
         for (size_t n : {(size_t)d.B * d.C * d.H * d.W, (size_t)d.B * d.dg * 2 * d.K * po, (size_t)d.B * d.dg * d.K * po,
@@ -129,7 +141,7 @@ size_t rvsr_mdcn_fwd_workspace_bytes(int B, int C, int H, int W, int Cout, int k
         dtype = RVSR_F32;
     }
     carve_dcn(cv, d, dtype, ws);
-    return cv.off + 256;
+    return (cv.off > tc_bytes ? cv.off : tc_bytes) + 256;
 }
 
 int rvsr_mdcn_fwd(const void *input, const void *offset, const void *mask, const void *weight, const void *bias,
@@ -144,6 +156,39 @@ int rvsr_mdcn_fwd(const void *input, const void *offset, const void *mask, const
     const size_t mis = (size_t)((uintptr_t)workspace % 256);
     if (mis) { cv.base += 256 - mis; cv.cap -= 256 - mis; }
     cudaStream_t s = (cudaStream_t)stream;
+    // EDVR's shape class with 16-bit tensors: gather -> UMMA on tcgen05 (dcn_tc_kernel; fp16 operands, fp32 coordinates and
+    // accumulate -- a bf16 caller's values are exactly representable up to fp16's range, which activations do not leave)
+    if ((dtype == RVSR_F16 || dtype == RVSR_BF16) && C == 64 && Cout == 64 && kh == 3 && kw == 3 && stride == 1 && pad == 1 && dil == 1 &&
+        groups == 1 && dg == 8 && mdcn_fwd_tc_enabled()) {
+        const size_t px = (size_t)B * H * W;
+        __half *x8 = (__half *)cv.take(px * 64 * 2), *y8 = (__half *)cv.take(px * 64 * 2);
+        void *om = cv.take(px * 8 * 96);
+        float *w32 = (float *)cv.take((size_t)64 * 64 * 9 * 4), *b32 = (float *)cv.take(64 * 4);
+        void *wtc = cv.take(tc_dcn_weight_bytes(64, 64, 9) + 16);
+        if (!cv.ok) { set_error("dcn: workspace too small (%zu bytes)", workspace_bytes); return RVSR_E_WORKSPACE; }
+        if (dtype == RVSR_F16) {
+            RVSR_TRY((launch_pack_nchw<__half, __half>((const __half *)input, x8, B, 64, H, W, s)));
+            RVSR_TRY(launch_convert_f16_f32(weight, w32, 64 * 64 * 9, s));
+            if (bias) RVSR_TRY(launch_convert_f16_f32(bias, b32, 64, s));
+        } else {
+            RVSR_TRY((launch_pack_nchw<__half, __nv_bfloat16>((const __nv_bfloat16 *)input, x8, B, 64, H, W, s)));
+            RVSR_TRY(launch_convert_bf16_f32(weight, w32, 64 * 64 * 9, s));
+            if (bias) RVSR_TRY(launch_convert_bf16_f32(bias, b32, 64, s));
+        }
+        RVSR_TRY(launch_om24_from_planar(offset, mask, dtype, om, B, 8, H, W, s));
+        RVSR_TRY(pack_weight_dcn_tc(w32, wtc, 64, 64, 9, s));
+        DcnOp op = {};
+        op.x = Src{x8, (long long)64 * H * W, 64, 1, -1}; op.om24 = om; op.om24_image_stride = (long long)8 * 24 * H * W;
+        op.w_tc = wtc; op.bias = bias ? b32 : nullptr; op.out = y8; op.out_image_stride = (long long)64 * H * W;
+        op.N = B; op.H = H; op.W = W; op.Cout = 64; op.kh = op.kw = 3; op.stride = 1; op.pad = 1; op.dil = 1; op.dg = 8;
+        op.act = RVSR_ACT_NONE; op.out_mode = OUT_C8;
+        if (tc_dcn_supported(op)) {
+            RVSR_TRY(launch_dcn_tc(op, s));
+            if (dtype == RVSR_F16) return launch_unpack_nchw<__half, __half>(y8, (__half *)output, B, 64, H, W, s);
+            return launch_unpack_nchw<__half, __nv_bfloat16>(y8, (__nv_bfloat16 *)output, B, 64, H, W, s);
+        }
+        cv.off = 0;  // not covered after all (no tensor-map encoder): fall through to the CUDA-core paths
+    }
     if (dtype == RVSR_BF16) {  // bfloat16 tensors, fp32 arithmetic: widen, run the fp32 operator, round the result once
         const size_t po = (size_t)d.Ho * d.Wo;
         const long long n_in = (long long)d.B * d.C * d.H * d.W, n_off = (long long)d.B * d.dg * 2 * d.K * po, n_msk = n_off / 2,

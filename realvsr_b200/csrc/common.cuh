@@ -1,5 +1,6 @@
 // common.cuh -- shared helpers for the rvsr_b200 kernels (sm_100a only).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -85,6 +86,7 @@ int ensure_max_dynamic_smem(const void *func, int bytes);  // engine.cu
 template <typename T> __device__ __forceinline__ float to_f(T v);
 template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 template <typename T> __device__ __forceinline__ T from_f(float v);
 template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
@@ -276,6 +278,8 @@ template <typename T, typename Tin, typename Tout>
 int launch_final_add(const T *res_c8, const Tin *x, Tout *out, int B, int frames, int center, int nc,
                      int H, int W, int scale, cudaStream_t s, const int *center_map = nullptr);
 int launch_convert_f16_f32(const void *src, float *dst, long long n, cudaStream_t s);
+// planar offsets [n][dg*18][H][W] + sigmoid-ed mask [n][dg*9][H][W] of `dtype` -> OUT_OM24 (see OutMode)
+int launch_om24_from_planar(const void *offset, const void *mask, int dtype, void *om24, int N, int dg, int H, int W, cudaStream_t s);
 int launch_convert_bf16_f32(const void *src, float *dst, long long n, cudaStream_t s);
 int launch_convert_f32_bf16(const float *src, void *dst, long long n, cudaStream_t s);
 int launch_fill_f32(float *dst, float v, long long n, cudaStream_t s);

@@ -332,6 +332,7 @@ template int launch_pack_nchw<float, float>(const float *, float *, int, int, in
 template int launch_pack_nchw<__half, float>(const float *, __half *, int, int, int, int, cudaStream_t, int);
 template int launch_pack_nchw<float, __half>(const __half *, float *, int, int, int, int, cudaStream_t, int);
 template int launch_pack_nchw<__half, __half>(const __half *, __half *, int, int, int, int, cudaStream_t, int);
+template int launch_pack_nchw<__half, __nv_bfloat16>(const __nv_bfloat16 *, __half *, int, int, int, int, cudaStream_t, int);
 
 template <typename T, typename Tout>
 __global__ void unpack_nchw_kernel(const T *__restrict__ src, Tout *__restrict__ dst, int C, int H, int W,
@@ -360,6 +361,7 @@ int launch_unpack_nchw(const T *src, Tout *dst, int N, int C, int H, int W, cuda
 template int launch_unpack_nchw<float, float>(const float *, float *, int, int, int, int, cudaStream_t);
 template int launch_unpack_nchw<__half, float>(const __half *, float *, int, int, int, int, cudaStream_t);
 template int launch_unpack_nchw<__half, __half>(const __half *, __half *, int, int, int, int, cudaStream_t);
+template int launch_unpack_nchw<__half, __nv_bfloat16>(const __half *, __nv_bfloat16 *, int, int, int, int, cudaStream_t);
 
 __global__ void convert_f16_f32_kernel(const __half *__restrict__ src, float *__restrict__ dst, long long n) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
@@ -370,6 +372,48 @@ int launch_convert_f16_f32(const void *src, float *dst, long long n, cudaStream_
     if (n == 0) return RVSR_OK;
     convert_f16_f32_kernel<<<(int)((n + 255) / 256 < 8192 ? (n + 255) / 256 : 8192), 256, 0, s>>>(
         reinterpret_cast<const __half *>(src), dst, n);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+// planar offsets / mask -> OUT_OM24: per pixel and deformable group three 32-byte blocks
+// [dy0 dx0 .. dy3 dx3][dy4 dx4 .. dy7 dx7][dy8 dx8 m01 m23 m45 m67 m8_ 0], offsets fp32, mask as fp16 pairs
+template <typename Tin>
+__global__ void om24_from_planar_kernel(const Tin *__restrict__ off, const Tin *__restrict__ msk, uint4 *__restrict__ om, int dg, int HW) {
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= HW) return;
+    const int g = blockIdx.y;
+    const long long n = blockIdx.z;
+    const Tin *op = off + (n * dg * 18 + g * 18) * (long long)HW + pix;
+    const Tin *mp = msk + (n * dg * 9 + g * 9) * (long long)HW + pix;
+    float o[18], m[10];
+#pragma unroll
+    for (int j = 0; j < 18; ++j) o[j] = to_f<Tin>(op[(long long)j * HW]);
+#pragma unroll
+    for (int j = 0; j < 9; ++j) m[j] = to_f<Tin>(mp[(long long)j * HW]);
+    m[9] = 0.f;
+    uint32_t mw[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const __half2 h = __floats2half2_rn(m[2 * k], m[2 * k + 1]);
+        mw[k] = *reinterpret_cast<const uint32_t *>(&h);
+    }
+    uint4 *d = om + ((n * dg * 3 + g * 3) * (long long)HW + pix) * 2;
+    auto f = [](float v) { return __float_as_uint(v); };
+    d[0] = make_uint4(f(o[0]), f(o[1]), f(o[2]), f(o[3])); d[1] = make_uint4(f(o[4]), f(o[5]), f(o[6]), f(o[7]));
+    d += (long long)HW * 2;
+    d[0] = make_uint4(f(o[8]), f(o[9]), f(o[10]), f(o[11])); d[1] = make_uint4(f(o[12]), f(o[13]), f(o[14]), f(o[15]));
+    d += (long long)HW * 2;
+    d[0] = make_uint4(f(o[16]), f(o[17]), mw[0], mw[1]); d[1] = make_uint4(mw[2], mw[3], mw[4], 0u);
+}
+int launch_om24_from_planar(const void *offset, const void *mask, int dtype, void *om24, int N, int dg, int H, int W, cudaStream_t s) {
+    if ((long long)N * dg * H * W == 0) return RVSR_OK;
+    const dim3 grid((H * W + 127) / 128, dg, N);
+    if (dtype == RVSR_F16)
+        om24_from_planar_kernel<__half><<<grid, 128, 0, s>>>((const __half *)offset, (const __half *)mask, (uint4 *)om24, dg, H * W);
+    else if (dtype == RVSR_BF16)
+        om24_from_planar_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>((const __nv_bfloat16 *)offset, (const __nv_bfloat16 *)mask, (uint4 *)om24, dg, H * W);
+    else
+        om24_from_planar_kernel<float><<<grid, 128, 0, s>>>((const float *)offset, (const float *)mask, (uint4 *)om24, dg, H * W);
     RVSR_LAUNCH_CHECK();
     return RVSR_OK;
 }

@@ -61,7 +61,9 @@ def test_mdcn_fwd_fp16_vs_oracle(cfg):
     y = D.modulated_deform_conv(x.to(DEV).half(), off.to(DEV).half(), msk.to(DEV).half(), w.to(DEV).half(),
                                 b.to(DEV).half(), s, p, d, g, dg)
     assert y.dtype == torch.float16
-    assert rel_err(y.float().cpu(), ref) < 2e-3
+    # EDVR's 64-channel / 8-group shape runs the tcgen05 gather -> UMMA kernel (fp16x2 bilinear blend: up to three more fp16
+    # roundings per sample, same bound as the fused pack); the other shapes the CUDA-core kernel with an fp32 blend
+    assert rel_err(y.float().cpu(), ref) < (4e-3 if cfg["C"] == 64 else 2e-3)
 
 
 def test_mdcn_fwd_matches_reference_generated_golden():
@@ -255,6 +257,9 @@ def test_mdcn_bf16_backward_on_tensor_cores_vs_oracle(shape, monkeypatch):
     gref = O.dcn_backward(r(x), r(off), r(msk), r(w), r(go), s, p, d, g, dg, with_bias=True)
     leaves = [t.to(DEV).bfloat16().requires_grad_() for t in (x, off, msk, w, b)]
     y = D.modulated_deform_conv(*leaves, s, p, d, g, dg)
+    ef = rel_err(y.float().cpu(), O.dcn_forward(r(x), r(off), r(msk), r(w), r(b), s, p, d, g, dg))
+    print("bf16 DCN forward on tcgen05 %s: rel err %.2e" % (shape, ef))
+    assert y.dtype == torch.bfloat16 and ef < 8e-3          # forward: dcn_tc_kernel, fp16 operands inside, bf16 result
     y.backward(go.to(DEV).bfloat16())
     for t, gr, name in zip(leaves, gref, ("x", "offset", "mask", "weight", "bias")):
         e = rel_err(t.grad.float().cpu(), gr)
