@@ -82,6 +82,18 @@ def test_engine_batch_invariance_and_determinism():
     assert torch.equal(y2[0:1], y1) and torch.equal(y2[2:3], y1)   # batch position does not matter
 
 
+def test_engine_nf128_batch_invariance_fp16():
+    """BASELINE cfg4's architecture (nf = 128: 64-channel source split, output halves, two-pass DCN contraction) at batch 3:
+    every window's frame equals the single-window result bit for bit, wherever it sits in the batch."""
+    c = load_case("edvr_nf128_7f")
+    net = _net(c, "engine").half()
+    x = c["x"].to(DEV).half()
+    with torch.no_grad():
+        y1 = net(x)
+        y3 = net(torch.cat([x, x.flip(1), x], 0))
+    assert torch.equal(y3[0:1], y1) and torch.equal(y3[2:3], y1) and not torch.equal(y3[1:2], y1)
+
+
 def test_engine_reloads_weights_when_parameters_change():
     c = load_case("edvr_tiny")
     net = _net(c, "engine")
