@@ -286,6 +286,44 @@ def test_training_step_bf16_autocast():
     assert all(p_.grad is not None and bool(torch.isfinite(p_.grad).all()) for p_ in net.parameters())
 
 
+def test_bf16_training_gradients_agree_with_fp32_on_the_nf64_network():
+    """The tensor-core DCN kernels inside a real network: EDVR nf = 64 (the shape class dcn_tc_kernel / dcn_bwd_tc_kernel
+    cover) on a small crop, one training step under torch.autocast(bfloat16) against the same step in fp32 (CUDA-core DCN
+    kernels, cuDNN TF32 off).  bf16 storage puts ~1e-2 of noise on every activation, so the check is directional: the
+    gradient of every DCN-related parameter points the same way (cosine > 0.97) and has the same size (within 10 %)."""
+    from helpers import load_case
+    from realvsr_b200.archs import EDVR_arch as E
+    c = load_case("edvr_nf64_crop")
+    net = E.EDVR(**c["kwargs"]).train()
+    net.load_state_dict(c["sd"], strict=True)
+    net = net.to(DEV)
+    x = torch.cat([c["x"], c["x"].flip(3)], 0).to(DEV)
+    gt = synth_normal((2,) + tuple(c["out"].shape[1:]), 55, std=0.3).to(DEV) + 0.5
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        torch.nn.functional.l1_loss(net(x), gt).backward()
+        g32 = {n: p_.grad.clone() for n, p_ in net.named_parameters()}
+        net.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = torch.nn.functional.l1_loss(net(x).float(), gt)
+        loss.backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    worst = (1.0, "")
+    for n, p_ in net.named_parameters():
+        if "dcnpack" not in n and "offset_conv" not in n:
+            continue
+        a, b = p_.grad.float().flatten(), g32[n].float().flatten()
+        cos = float(torch.dot(a, b) / (a.norm() * b.norm()).clamp_min(1e-30))
+        ratio = float(a.norm() / b.norm().clamp_min(1e-30))
+        if cos < worst[0]:
+            worst = (cos, n)
+        assert 0.9 < ratio < 1.1, (n, ratio)
+    print("bf16 (tcgen05 DCN fwd + bwd) vs fp32 gradients: worst cosine %.4f (%s)" % worst)
+    assert worst[0] > 0.97, worst
+
+
 def test_training_step_through_module_path():
     """cfg5-shaped smoke (tiny): EDVR module path forward + L1 loss + backward through our DCN fwd/bwd;
     gradients reach every parameter and match a finite-difference probe on one DCN weight."""
