@@ -176,7 +176,9 @@ def cfg5_time(dev):
         gt = synth_input((16, 3, 256, 256), 10).to(dev)
         out = dict(workload="B=16, 5x3x64x64 -> 256x256, forward + L1 + backward, no optimizer step; SURVEY 8d floor 2.0 ms",
                    unit="ms/step")
-        for name, amp in (("bf16_autocast", True), ("fp32", False)):
+        for name, amp in (("bf16_autocast", True), ("fp32", False), ("bf16_autocast_channels_last", True)):
+            if name.endswith("channels_last"):  # user-side cuDNN setting: no NCHW <-> NHWC transposes around every convolution
+                net = net.to(memory_format=torch.channels_last)
             def step():
                 net.zero_grad(set_to_none=True)
                 with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):

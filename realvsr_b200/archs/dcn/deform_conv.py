@@ -180,12 +180,13 @@ class ModulatedDeformConvPack(ModulatedDeformConv):
             from ... import ops
             return ops.mdcn_pack(x, feat, self.conv_offset_mask.weight, self.conv_offset_mask.bias, self.weight,
                                  self.bias, self.deformable_groups)
+        x = x.contiguous()   # channels_last activations (a user-side cuDNN setting) reach the NCHW operator as a copy
         om = self.conv_offset_mask(feat)
         third = om.shape[1] // 3
         # chunk(3) then cat(o1, o2) == the first two thirds; the reference also computes a
         # mean(|offset|) here and throws it away (deform_conv.py:285) -- not reproduced.
         offset, mask = om[:, :2 * third], torch.sigmoid(om[:, 2 * third:])
-        return modulated_deform_conv(x, offset, mask, self.weight, self.bias, self.stride, self.padding,
+        return modulated_deform_conv(x, offset, mask, self.weight.contiguous(), self.bias, self.stride, self.padding,
                                      self.dilation, self.groups, self.deformable_groups)
 
 

@@ -12,6 +12,8 @@ kw = dict(nf=64, nc=3, nframes=5, groups=8, front_RBs=5, back_RBs=10, w_TSA=True
 net = E.EDVR(**kw)
 net.load_state_dict(synth_state_dict(edvr_state_shapes("EDVR", **kw), 7), strict=True)
 net = net.to("cuda:0").train()
+if os.environ.get("CL", "0") == "1":   # experiment: channels_last weights / activations for the cuDNN convolutions
+    net = net.to(memory_format=torch.channels_last)
 x = synth_input((16, 5, 3, 64, 64), 9).to("cuda:0")
 gt = synth_input((16, 3, 256, 256), 10).to("cuda:0")
 amp = os.environ.get("AMP", "0") == "1"
