@@ -54,7 +54,7 @@ def build(force=False, verbose=False):
             print(out.decode(errors="replace"))
         if p.returncode != 0:
             raise RuntimeError("nvcc failed on %s" % src)
-    subprocess.run([_nvcc(), "-shared", "-o", LIB] + objs, check=True)
+    subprocess.run([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs, check=True)
     return LIB
 
 
