@@ -135,3 +135,23 @@ def test_dcn_pack_full_size_vs_c_oracle():
     e16 = rel_err(y16.float().cpu(), ref)
     print("dcn pack 180x320 B=2: fp16 (tcgen05) vs C oracle %.2e" % e16)
     assert e16 < 4e-3
+
+
+def test_1080p_window_fp16_engine_vs_fp32_engine():
+    """The `e2e_1080p` workload (270x480 padded to 272x480 -> 1088x1920): other tile counts than cfg2 (15 x 68 tiles per image,
+    ragged last column tile of the 30-column conv tiles), fp16 tcgen05 engine against the fp32 CUDA-core engine, which the
+    tests above pin to the oracle at 1e-6; replicate padding and the crop back to 1080 rows via video.pad_to_multiple."""
+    from realvsr_b200 import video as V
+    sd = synth_state_dict(edvr_state_shapes("EDVR", **KW), 7)
+    x270 = synth_input((1, 5, 3, 270, 480), 31)
+    x, (h, w) = V.pad_to_multiple(x270, 4)
+    assert tuple(x.shape[-2:]) == (272, 480) and (h, w) == (270, 480)
+    n16, n32 = _engine_net(sd, half=True), _engine_net(sd, half=False)
+    with torch.no_grad():
+        y16 = n16(x.to(DEV).half()).float().cpu()
+        y32 = n32(x.to(DEV)).cpu()
+    base = F.interpolate(x[:, 2], scale_factor=4, mode="bilinear", align_corners=False)
+    e = rel_err(y16 - base, y32 - base)
+    print("1080p window: fp16 engine vs fp32 engine %.2e" % e)
+    assert y16.shape == (1, 3, 1088, 1920) and e < 1e-2
+    assert y16[..., :4 * h, :4 * w].shape == (1, 3, 1080, 1920)
