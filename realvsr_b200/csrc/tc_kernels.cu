@@ -331,7 +331,7 @@ template <int NT, int NH> struct EpiTile {
 // before the accumulator wait, all 32 columns of the warp in registers with ONE tcgen05.wait::ld, and the TMEM
 // buffer handed back before any arithmetic.  Exact integer division of the tile index by precomputed magic
 // numbers (host: magic_div) replaces three hardware divisions per tile and warp.
-template <int ACT, bool RES_CG = false, typename Release>
+template <int ACT, typename Release>
 __device__ __forceinline__ void epi_c8_fast(const float *bias_s, __half *out, long long out_image_stride, const __half *residual,
                                             long long res_image_stride, int H, int W, int Co8, uint32_t taddr, int half,
                                             int qbase, int n, int y, int x, bool valid, uint32_t full_bar, uint32_t full_par,
@@ -344,8 +344,7 @@ __device__ __forceinline__ void epi_c8_fast(const float *bias_s, __half *out, lo
     if (has_res) {
         const uint4 *r = reinterpret_cast<const uint4 *>(residual + (long long)(n_res < 0 ? n : n_res) * res_image_stride) + q0 * plane + pix;
 #pragma unroll
-        for (int j = 0; j < NBLK; ++j)  // RES_CG: the residual was written earlier in the SAME kernel (chain): L2-coherent load
-            res[j] = q0 + j < Co8 ? (RES_CG ? __ldcg(r + j * plane) : __ldg(r + j * plane)) : make_uint4(0, 0, 0, 0);
+        for (int j = 0; j < NBLK; ++j) res[j] = q0 + j < Co8 ? __ldg(r + j * plane) : make_uint4(0, 0, 0, 0);
     }
     mbar_wait(full_bar, full_par);
     tc_fence_after();

@@ -31,4 +31,4 @@ for half in (True, False) if "--fp16-only" not in sys.argv else (True,):
         y = net(xi)
     torch.cuda.synchronize()
     print("forward", "fp16" if half else "fp32", tuple(y.shape), "finite", bool(torch.isfinite(y).all()),
-          "launches", net._get_engine(xi).last_launch_count(), "RVSR_CHAIN", os.environ.get("RVSR_CHAIN", "0"))
+          "launches", net._get_engine(xi).last_launch_count())
