@@ -12,8 +12,9 @@
  *     no host synchronisation, no allocation inside per-call entry points; the caller
  *     owns every buffer including the workspace.
  *   - dtype codes: RVSR_F32 = 0, RVSR_F16 = 1, RVSR_BF16 = 2 (DCN operator only).
- *   - "NCHW" tensors are contiguous like the reference's; the engine's private
- *     activation layout (channel-blocked [N][C/8][H][W][8]) never crosses this ABI.
+ *   - "NCHW" tensors are contiguous like the reference's; the inference engine's
+ *     activation layout (channel-blocked [N][C/8][H][W][8]) stays private to it.  Only the
+ *     training entry points (rvsr_c8_*) take channel-blocked bf16 tensors.
  */
 #ifndef RVSR_B200_H
 #define RVSR_B200_H
@@ -103,6 +104,39 @@ int rvsr_conv2d_fwd(const void *x1, const void *x2, const void *weight, const vo
                     const void *residual, void *y, int B, int C1, int C2, int H, int W, int Cout,
                     int ks, int stride, int act, int shuffle, int dtype, int use_tc, void *workspace,
                     size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------ training path (bf16, channel-blocked tensors)
+ * BASELINE cfg5 (bf16 training step): the plain convolutions of EDVR_arch.py forward AND backward on this library's
+ * tcgen05 kernels, called from torch.autograd.Functions (realvsr_b200/train_c8.py) that replace nn.Conv2d's autograd
+ * (EDVR_arch.py:71-91, :229-253; arch_util.py:121-139), F.interpolate x2 (:109-121) and PixelShuffle(2) + lrelu (:313-314).
+ * "C8" tensors are [N][ceil(C/8)][H][W][8] bfloat16, contiguous per image (x_image_stride in elements lets a source be a
+ * channel slice of a wider tensor); channels beyond C are zero.
+ *   rvsr_c8_conv_pack_weight  fp32 OIHW nn.Parameter -> the kernels' bf16 operand layout.  mode 0: forward convolution over
+ *                             input channels [w_c0, w_c0 + Cin) of rows with w_cin_total channels.  mode 1: the DATA GRADIENT
+ *                             of input channels [w_c0, w_c0 + Cout) as a convolution Cin (= forward Cout) -> Cout with the
+ *                             transposed, flipped weights (dX = conv(dY, W^T flipped); stride 1 only).
+ *   rvsr_c8_conv_fwd          y = act(conv(cat(x[0..nsrc)), w) + bias) [+ residual], optional fused PixelShuffle(2); nsrc sources
+ *                             of C channels each (C % 16 == 0, C <= 64); also runs every data gradient (with mode-1 weights).
+ *   rvsr_c8_conv_wgrad        dw_t[tap][ci][co] += sum_pixels x[pixel + tap][ci] * g[pixel][co] (fp32, [9][64][Cout], zeroed by the
+ *                             caller; the OIHW gradient is its transpose), db[co] += sum_pixels g (may be NULL).  Cin = 64, 3x3.
+ *   rvsr_c8_act_bwd           out = y > 0 ? g : slope * g  (LeakyReLU(0.1) / ReLU given the layer OUTPUT y)
+ *   rvsr_c8_unshuffle2_act_bwd  gradient through lrelu(PixelShuffle(2)(.)): g, y [N][C/4 ch][2H][2W] -> out [N][C ch][H][W]
+ *   rvsr_c8_upsample2x        bilinear x2 (align_corners=False) times `scale`, or (backward = 1) its adjoint. */
+/* NCHW (RVSR_BF16 / RVSR_F32) <-> C8 with `planes` >= ceil(C / 8) channel blocks per image: only blocks [0, ceil(C / 8)) are
+ * written (channels C .. of the last one as zeros) / read */
+int rvsr_c8_from_nchw(const void *src, int src_dtype, void *dst_c8, int N, int C, int H, int W, int planes, void *stream);
+int rvsr_c8_to_nchw(const void *src_c8, void *dst, int dst_dtype, int N, int C, int H, int W, int planes, void *stream);
+size_t rvsr_c8_conv_weight_bytes(int Cout, int Cin, int ks, int shuffle);
+int rvsr_c8_conv_pack_weight(const float *weight, void *dst, int Cout, int Cin, int ks, int shuffle, int mode, int w_cin_total,
+                             int w_c0, void *stream);
+int rvsr_c8_conv_fwd(const void *const *x, const long long *x_image_stride, int nsrc, int C, const void *w_packed, const float *bias,
+                     const void *residual, void *y, int N, int H, int W, int Cout, int ks, int stride, int act, int shuffle,
+                     void *stream);
+int rvsr_c8_conv_wgrad(const void *x, long long x_image_stride, const void *g, float *dw_t, float *db, int N, int H, int W, int Cin,
+                       int Cout, int ks, void *stream);
+int rvsr_c8_act_bwd(const void *g, const void *y, void *out, long long n_elems, int act, void *stream);
+int rvsr_c8_unshuffle2_act_bwd(const void *g, const void *y, void *out, int N, int C, int H, int W, int act, void *stream);
+int rvsr_c8_upsample2x(const void *src, void *dst, long long planes, int H, int W, float scale, int backward, void *stream);
 
 /* ------------------------------------------------------------------ EDVR engine
  * Replaces EDVR.forward / EDVR_NoUp.forward (EDVR_arch.py:258-320, :358-404) and everything

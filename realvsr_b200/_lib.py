@@ -36,6 +36,16 @@ SIGNATURES = {
     "rvsr_mdcn_pack_fwd": (c_int, [c_void_p] * 7 + [c_int] * 8 + [c_void_p, c_size_t, c_void_p]),
     "rvsr_conv2d_fwd_workspace_bytes": (c_size_t, [c_int] * 8),
     "rvsr_conv2d_fwd": (c_int, [c_void_p] * 6 + [c_int] * 12 + [c_void_p, c_size_t, c_void_p]),
+    "rvsr_c8_from_nchw": (c_int, [c_void_p, c_int, c_void_p] + [c_int] * 5 + [c_void_p]),
+    "rvsr_c8_to_nchw": (c_int, [c_void_p, c_void_p, c_int] + [c_int] * 5 + [c_void_p]),
+    "rvsr_c8_conv_weight_bytes": (c_size_t, [c_int] * 4),
+    "rvsr_c8_conv_pack_weight": (c_int, [c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
+    "rvsr_c8_conv_fwd": (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(ctypes.c_longlong), c_int, c_int, c_void_p,
+                                 c_void_p, c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
+    "rvsr_c8_conv_wgrad": (c_int, [c_void_p, ctypes.c_longlong, c_void_p, c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),
+    "rvsr_c8_act_bwd": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p]),
+    "rvsr_c8_unshuffle2_act_bwd": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
+    "rvsr_c8_upsample2x": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, ctypes.c_float, c_int, c_void_p]),
     "rvsr_frames_from_u8": (c_int, [c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),
     "rvsr_frames_to_u8": (c_int, [c_void_p, c_int, c_void_p] + [c_int] * 5 + [c_void_p]),
     "rvsr_engine_create": (c_int, [ctypes.POINTER(EdvrConfig), ctypes.POINTER(c_void_p)]),

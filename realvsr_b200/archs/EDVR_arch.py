@@ -30,6 +30,7 @@ import torch.nn.functional as F
 
 from . import arch_util
 from .dcn.deform_conv import ModulatedDeformConvPack as DCN
+from .dcn.deform_conv import modulated_deform_conv as _dcn_fn
 from .. import engine as _engine
 
 _ENGINE_LOCK = threading.Lock()  # DataParallel runs the replicas' forwards in threads
@@ -304,7 +305,84 @@ class _EDVRBase(nn.Module):
     def forward(self, x):
         if self._engine_ok(x):
             return self._get_engine(x)(x)
+        if self._train_c8_ok(x):
+            return self._forward_c8(x)
         return self._forward_modules(x)
+
+    # ------------------------------------------------------------------ bf16 training path (channel-blocked tensors)
+    def _train_c8_ok(self, x):
+        """bf16 autograd on this library's convolution kernels (realvsr_b200/train_c8.py) instead of cuDNN: taken under
+        torch.autocast(bfloat16) -- BASELINE cfg5's configuration -- or with exec_path = 'train_c8'.  Gradients are bf16
+        quality (like autocast's); the fp32 module path stays the default for fp32 training."""
+        want = self.exec_path == "train_c8" or (self.exec_path == "auto" and torch.is_autocast_enabled() and
+                                                torch.get_autocast_dtype("cuda") == torch.bfloat16 and
+                                                os.environ.get("RVSR_TRAIN_C8", "1") != "0")
+        ok = (x.is_cuda and self.nf == 64 and not (self._upsample and (self.is_predeblur or self.HR_in)))
+        if want and not ok and self.exec_path == "train_c8":
+            raise RuntimeError("realvsr_b200: exec_path='train_c8' needs CUDA input, nf == 64 and the standard stem")
+        return want and ok
+
+    def _forward_c8(self, x):
+        """Same graph as _forward_modules.  Stride-1 3x3 convolutions (117 of the 132 conv sites), residual adds, torch.cat,
+        the x2 upsamples and PixelShuffle + lrelu run as train_c8 Functions on [N, C/8, H, W, 8] bf16 tensors; the rest
+        (3-channel first / last convolution, the two stride-2 convolutions, the DCN operator, TSA's 1x1 convolutions / pools)
+        stays on NCHW bf16 tensors under autocast, with a layout conversion at each boundary."""
+        from .. import train_c8 as T
+        B, N, C, H, W = x.size()
+        bf = torch.bfloat16
+        conv = lambda m, t, act=None, residual=None, shuffle=False: T.conv(t, m.weight, m.bias, act=act, residual=residual,  # noqa: E731
+                                                                           shuffle=shuffle)
+        nchw = lambda t: T.from_c8(t, None, bf)  # noqa: E731
+
+        def trunk(blocks, t):
+            for blk in blocks:  # ResidualBlock_noBN (arch_util.py:135-139): x + conv2(relu(conv1(x)))
+                t = conv(blk.conv2, conv(blk.conv1, t, "relu"), None, residual=t)
+            return t
+
+        def dcn(pack, t, feat, act=None):
+            # ModulatedDeformConvPack.forward (deform_conv.py:274-292): the 64 -> 216 offset / mask convolution runs here with its
+            # weights zero-padded to 256 outputs (whole 64-wide tiles for the data gradient); the operator itself is
+            # rvsr_mdcn_fwd / rvsr_mdcn_bwd on NCHW bf16 tensors
+            k = pack.conv_offset_mask.weight.shape[0]
+            w_om = F.pad(pack.conv_offset_mask.weight, (0, 0, 0, 0, 0, 0, 0, 256 - k))
+            b_om = F.pad(pack.conv_offset_mask.bias, (0, 256 - k))
+            om = T.from_c8(T.conv(feat, w_om, b_om), k, bf)
+            third = k // 3
+            y = _dcn_fn(nchw(t), om[:, :2 * third], torch.sigmoid(om[:, 2 * third:]), pack.weight.contiguous(), pack.bias,
+                        pack.stride, pack.padding, pack.dilation, pack.groups, pack.deformable_groups)
+            return T.to_c8(F.leaky_relu(y, 0.1) if act else y)
+
+        with torch.autocast("cuda", dtype=bf):
+            x_center = x[:, self.center].contiguous()
+            frames = x.reshape(-1, C, H, W)
+            l1 = trunk(self.feature_extraction, T.to_c8(F.leaky_relu(self.conv_first(frames), 0.1)))
+            l2 = conv(self.fea_L2_conv2, T.to_c8(F.leaky_relu(self.fea_L2_conv1(nchw(l1)), 0.1)), "lrelu")
+            l3 = conv(self.fea_L3_conv2, T.to_c8(F.leaky_relu(self.fea_L3_conv1(nchw(l2)), 0.1)), "lrelu")
+            pyr = [l1, l2, l3]
+            ref = [lv.view(B, N, *lv.shape[1:])[:, self.center:self.center + 1].expand(B, N, *lv.shape[1:]).reshape(lv.shape)
+                   for lv in pyr]
+            p = self.pcd_align  # PCD_Align.forward (EDVR_arch.py:98-132), all N frames as one batch
+            off3 = conv(p.L3_offset_conv2, conv(p.L3_offset_conv1, [pyr[2], ref[2]], "lrelu"), "lrelu")
+            fea3 = dcn(p.L3_dcnpack, pyr[2], off3, act=True)
+            off2 = conv(p.L2_offset_conv1, [pyr[1], ref[1]], "lrelu")
+            off2 = conv(p.L2_offset_conv3, conv(p.L2_offset_conv2, [off2, T.upsample2x(off3, 2.0)], "lrelu"), "lrelu")
+            fea2 = conv(p.L2_fea_conv, [dcn(p.L2_dcnpack, pyr[1], off2), T.upsample2x(fea3)], "lrelu")
+            off1 = conv(p.L1_offset_conv1, [pyr[0], ref[0]], "lrelu")
+            off1 = conv(p.L1_offset_conv3, conv(p.L1_offset_conv2, [off1, T.upsample2x(off2, 2.0)], "lrelu"), "lrelu")
+            fea1 = conv(p.L1_fea_conv, [dcn(p.L1_dcnpack, pyr[0], off1), T.upsample2x(fea2)])
+            offc = conv(p.cas_offset_conv2, conv(p.cas_offset_conv1, [fea1, ref[0]], "lrelu"), "lrelu")
+            aligned = nchw(dcn(p.cas_dcnpack, fea1, offc, act=True)).view(B, N, -1, H, W)
+            fea = self.tsa_fusion(aligned if self.w_TSA else aligned.view(B, -1, H, W))
+            out = trunk(self.recon_trunk, T.to_c8(fea))
+            if self._upsample:
+                out = conv(self.upconv1, out, "lrelu", shuffle=True)   # lrelu(PixelShuffle(conv)) == PixelShuffle(lrelu(conv))
+                out = conv(self.upconv2, out, "lrelu", shuffle=True)
+            out = self.conv_last(nchw(conv(self.HRconv, out, "lrelu")))
+        if self._upsample:
+            base = F.interpolate(x_center, scale_factor=4, mode='bilinear', align_corners=False)
+        else:
+            base = x_center
+        return out.float() + base
 
     # ------------------------------------------------------------------ module path (autograd-capable)
     def _forward_modules(self, x):

@@ -1,0 +1,113 @@
+// api_train.cu -- extern "C" surface of the bf16 training path (rvsr_c8_* in include/rvsr_b200.h): thin argument checks
+// around the launchers of train_kernels.cu and the bf16 mode of the tcgen05 convolution kernels (tc_kernels.cu).
+#include "engine.cuh"
+
+namespace rvsr {
+bool conv_wgrad_tc_supported(int Cin, int ks, int stride);
+int launch_conv_wgrad_tc(const void *x_c8, long long x_image_stride, const void *g_c8, float *dw, float *db, int N, int H, int W,
+                         int Cout, cudaStream_t s);
+int launch_act_bwd_c8(const void *g, const void *y, void *out, long long n_elems, int act, cudaStream_t s);
+int launch_unshuffle2_act_bwd_c8(const void *g, const void *y, void *out, int N, int C, int H, int W, int act, cudaStream_t s);
+int launch_upsample2x_c8(const void *src, void *dst, long long planes, int H, int W, float scale, int backward, cudaStream_t s);
+int launch_nchw_to_c8_bf16(const void *src, int src_dtype, void *dst, int N, int C, int H, int W, int planes, cudaStream_t s);
+int launch_c8_to_nchw_bf16(const void *src, void *dst, int dst_dtype, int N, int C, int H, int W, int planes, cudaStream_t s);
+}  // namespace rvsr
+
+using namespace rvsr;
+
+extern "C" {
+
+int rvsr_c8_from_nchw(const void *src, int src_dtype, void *dst_c8, int N, int C, int H, int W, int planes, void *stream) {
+    RVSR_CHECK_ARG(N >= 0 && C > 0 && H > 0 && W > 0, "c8_from_nchw: bad sizes");
+    RVSR_CHECK_ARG(N == 0 || (src && dst_c8), "c8_from_nchw: null buffer");
+    return launch_nchw_to_c8_bf16(src, src_dtype, dst_c8, N, C, H, W, planes, (cudaStream_t)stream);
+}
+int rvsr_c8_to_nchw(const void *src_c8, void *dst, int dst_dtype, int N, int C, int H, int W, int planes, void *stream) {
+    RVSR_CHECK_ARG(N >= 0 && C > 0 && H > 0 && W > 0, "c8_to_nchw: bad sizes");
+    RVSR_CHECK_ARG(N == 0 || (src_c8 && dst), "c8_to_nchw: null buffer");
+    return launch_c8_to_nchw_bf16(src_c8, dst, dst_dtype, N, C, H, W, planes, (cudaStream_t)stream);
+}
+
+size_t rvsr_c8_conv_weight_bytes(int Cout, int Cin, int ks, int shuffle) {
+    const size_t a = tc_conv_weight_bytes(Cout, Cin, ks, shuffle ? 1 : 0);
+    if (a == 0) return 0;
+    return align_up(a, 256) + align_up(tc2_weight_bytes(Cout, Cin, ks, shuffle ? 1 : 0), 256) + 256;
+}
+
+int rvsr_c8_conv_pack_weight(const float *weight, void *dst, int Cout, int Cin, int ks, int shuffle, int mode, int w_cin_total,
+                             int w_c0, void *stream) {
+    RVSR_CHECK_ARG(weight && dst && Cout > 0 && Cin > 0 && (ks == 1 || ks == 3), "c8 pack weight: bad arguments");
+    RVSR_CHECK_ARG(mode == 0 || mode == 1, "c8 pack weight: mode %d", mode);
+    RVSR_CHECK_ARG(((uintptr_t)dst & 255) == 0, "c8 pack weight: destination must be 256-byte aligned");
+    const size_t a = tc_conv_weight_bytes(Cout, Cin, ks, shuffle ? 1 : 0);
+    if (a == 0) { set_error("c8 pack weight: shape %d x %d x %d not covered by the tcgen05 kernels", Cout, Cin, ks); return RVSR_E_UNSUPPORTED; }
+    const long long KK = ks * ks;
+    WeightView wv;
+    if (mode == 0) {  // forward: weight[co][w_c0 + cin][tap], rows of w_cin_total input channels
+        RVSR_CHECK_ARG(w_c0 >= 0 && w_c0 + Cin <= w_cin_total, "c8 pack weight: channel slice");
+        wv = WeightView{w_c0 * KK, w_cin_total * KK, KK, 1, 1};
+    } else {          // data gradient of input channels [w_c0, w_c0 + Cout): weight[cin][w_c0 + co][KK - 1 - tap]
+        RVSR_CHECK_ARG(w_c0 >= 0 && w_c0 + Cout <= w_cin_total, "c8 pack weight: channel slice");
+        wv = WeightView{w_c0 * KK + KK - 1, KK, w_cin_total * KK, -1, 1};
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    RVSR_TRY(pack_weight_tc(weight, dst, Cout, Cin, ks, shuffle ? 1 : 0, s, &wv));
+    if (tc2_weight_bytes(Cout, Cin, ks, shuffle ? 1 : 0) > 0)
+        RVSR_TRY(pack_weight_tc2(weight, (char *)dst + align_up(a, 256), Cout, Cin, ks, shuffle ? 1 : 0, s, &wv));
+    return RVSR_OK;
+}
+
+int rvsr_c8_conv_fwd(const void *const *x, const long long *x_image_stride, int nsrc, int C, const void *w_packed, const float *bias,
+                     const void *residual, void *y, int N, int H, int W, int Cout, int ks, int stride, int act, int shuffle,
+                     void *stream) {
+    RVSR_CHECK_ARG(x && x_image_stride && nsrc >= 1 && nsrc <= RVSR_MAX_SRC_TC, "c8 conv: 1..%d sources", RVSR_MAX_SRC_TC);
+    RVSR_CHECK_ARG(N >= 0 && C > 0 && H > 0 && W > 0 && Cout > 0 && (ks == 1 || ks == 3) && (stride == 1 || stride == 2), "c8 conv: bad sizes");
+    RVSR_CHECK_ARG(!shuffle || (Cout % 4 == 0 && residual == nullptr && stride == 1), "c8 conv: pixel-shuffle needs Cout %% 4 == 0, no residual");
+    if (N == 0) return RVSR_OK;
+    RVSR_CHECK_ARG(w_packed && y, "c8 conv: null buffer");
+    const int mode = shuffle ? 1 : 0;
+    const size_t a = tc_conv_weight_bytes(Cout, nsrc * C, ks, mode);
+    if (a == 0) { set_error("c8 conv: shape not covered by the tcgen05 kernels"); return RVSR_E_UNSUPPORTED; }
+    ConvOp op = {};
+    for (int i = 0; i < nsrc; ++i) {
+        RVSR_CHECK_ARG(x[i] != nullptr, "c8 conv: null source %d", i);
+        op.src[i] = Src{x[i], x_image_stride[i], C, 1, -1};
+    }
+    op.nsrc = nsrc;
+    op.w_tc = w_packed;
+    op.w_tc2 = tc2_weight_bytes(Cout, nsrc * C, ks, mode) > 0 ? (const char *)w_packed + align_up(a, 256) : nullptr;
+    op.bias = bias;
+    const int Ho = stride == 1 ? H : H / 2, Wo = stride == 1 ? W : W / 2;
+    op.out = y;
+    op.out_image_stride = shuffle ? (long long)cdiv(Cout / 4, 8) * 8 * 4 * Ho * Wo : (long long)cdiv(Cout, 8) * 8 * Ho * Wo;
+    op.residual = residual; op.res_image_stride = op.out_image_stride;
+    op.N = N; op.H = H; op.W = W; op.Cout = Cout; op.ks = ks; op.stride = stride; op.act = act;
+    op.out_mode = shuffle ? OUT_C8_SHUFFLE2 : OUT_C8; op.sig_from = 1 << 30;
+    op.bf16 = 1;
+    if (!tc_conv_supported(op)) { set_error("c8 conv: configuration not covered by the tcgen05 kernels"); return RVSR_E_UNSUPPORTED; }
+    return launch_conv_tc(op, (cudaStream_t)stream);
+}
+
+int rvsr_c8_conv_wgrad(const void *x, long long x_image_stride, const void *g, float *dw_t, float *db, int N, int H, int W, int Cin,
+                       int Cout, int ks, void *stream) {
+    RVSR_CHECK_ARG(N >= 0 && H > 0 && W > 0 && Cout > 0, "c8 conv wgrad: bad sizes");
+    if (!conv_wgrad_tc_supported(Cin, ks, 1)) { set_error("c8 conv wgrad: built for 64 input channels, 3x3, stride 1"); return RVSR_E_UNSUPPORTED; }
+    if (N == 0) return RVSR_OK;
+    RVSR_CHECK_ARG(x && g && dw_t, "c8 conv wgrad: null buffer");
+    return launch_conv_wgrad_tc(x, x_image_stride, g, dw_t, db, N, H, W, Cout, (cudaStream_t)stream);
+}
+
+int rvsr_c8_act_bwd(const void *g, const void *y, void *out, long long n_elems, int act, void *stream) {
+    RVSR_CHECK_ARG(n_elems >= 0 && (n_elems == 0 || (g && y && out)), "c8 act bwd: bad arguments");
+    return launch_act_bwd_c8(g, y, out, n_elems, act, (cudaStream_t)stream);
+}
+int rvsr_c8_unshuffle2_act_bwd(const void *g, const void *y, void *out, int N, int C, int H, int W, int act, void *stream) {
+    RVSR_CHECK_ARG(N >= 0 && C > 0 && H > 0 && W > 0 && g && out && (act == RVSR_ACT_NONE || y), "c8 unshuffle: bad arguments");
+    return launch_unshuffle2_act_bwd_c8(g, y, out, N, C, H, W, act, (cudaStream_t)stream);
+}
+int rvsr_c8_upsample2x(const void *src, void *dst, long long planes, int H, int W, float scale, int backward, void *stream) {
+    RVSR_CHECK_ARG(planes >= 0 && H > 0 && W > 0 && (planes == 0 || (src && dst)), "c8 upsample2x: bad arguments");
+    return launch_upsample2x_c8(src, dst, planes, H, W, scale, backward, (cudaStream_t)stream);
+}
+
+}  // extern "C"

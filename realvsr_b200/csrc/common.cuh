@@ -202,6 +202,14 @@ struct FinalAdd {
     int frames, center, nc, scale;
 };
 
+// How a weight-packing kernel addresses its fp32 source: element (co, cin, tap) of the convolution being packed is read at
+// base + co * s_co + cin * s_ci + tap * s_tap.  OIHW: {0, Cin * KK, KK, 1}.  Data gradient of input channels [c0, c0 + C) of a
+// convolution with CinTot inputs (dX = conv(dY, W^T flipped)): {c0 * KK + KK - 1, KK, CinTot * KK, -1}.
+struct WeightView {
+    long long base, s_co, s_ci, s_tap;
+    int bf16;  // destination format: 0 = fp16, 1 = bfloat16
+};
+
 struct ConvOp {
     Src src[RVSR_MAX_SRC_TC];
     int nsrc;
@@ -220,6 +228,7 @@ struct ConvOp {
     int act, out_mode, sig_from;
     int dg;                // OUT_OM24: deformable groups (Cout == 27 * dg)
     FinalAdd fin;          // OUT_FINAL
+    int bf16;              // tcgen05 kernels: sources, residual and output are bfloat16 (w_tc / w_tc2 packed as bfloat16)
 };
 
 struct DcnOp {

@@ -97,6 +97,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FP_THREADS, 1) dcn_p
     const int cid = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
     const int npairs = (p.num_tiles + 1) / 2;
     const int T = cid < npairs ? (npairs - cid + nclusters - 1) / nclusters : 0;  // tile pairs of this cluster
+    const bool slow_poll = !(p.debug & 16);  // RVSR_DCN_DEBUG & 16: the idle roles poll with the suspend-time hint again (A/B)
 
     pdl_trigger();
     if (threadIdx.x == 0) {
@@ -147,7 +148,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FP_THREADS, 1) dcn_p
             uint32_t wk = 0;  // weight chunks issued so far
             auto wchunk = [&](int hf, int tap) {
                 const int st = (int)(wk % FP_SW);
-                mbar_wait(BAR(B_WEMPTY + st), ((wk / FP_SW) & 1) ^ 1);
+                if (slow_poll) mbar_wait_sleep(BAR(B_WEMPTY + st), ((wk / FP_SW) & 1) ^ 1, 100);
+                else mbar_wait(BAR(B_WEMPTY + st), ((wk / FP_SW) & 1) ^ 1);
                 const uint32_t full0 = mapa_rank0(BAR(B_WFULL + st));
                 if (rank == 0) mbar_expect_tx(BAR(B_WFULL + st), 2 * FP_WCHUNK);
                 else mbar_arrive_cluster(full0);
@@ -159,7 +161,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FP_THREADS, 1) dcn_p
                 if (tile >= p.num_tiles) tile = p.num_tiles - 1;  // odd tile count: the peer recomputes the last tile, never stores it
                 int tx, ty, n;
                 tile_coords(p.td, tile, tx, ty, n);
-                mbar_wait(BAR(B_HEMPTY), ((uint32_t)t & 1) ^ 1);  // one stage: the previous tile's offset conv has read it
+                if (slow_poll) mbar_wait_sleep(BAR(B_HEMPTY), ((uint32_t)t & 1) ^ 1, 400);  // one stage: the previous tile's offset conv has read it
+                else mbar_wait(BAR(B_HEMPTY), ((uint32_t)t & 1) ^ 1);
                 const uint32_t full0 = mapa_rank0(BAR(B_HFULL));
                 if (rank == 0) mbar_expect_tx(BAR(B_HFULL), 2 * FP_HALO_BYTES);
                 else mbar_arrive_cluster(full0);
@@ -203,7 +206,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FP_THREADS, 1) dcn_p
                 tc_fence_after();
 #pragma unroll 1
                 for (int hf = 0; hf < 2; ++hf) {
-                    mbar_wait(BAR(B_OMEMPTY + hf), ((uint32_t)t & 1) ^ 1);  // every gather thread has pulled the previous tile's columns
+                    if (slow_poll) mbar_wait_sleep(BAR(B_OMEMPTY + hf), ((uint32_t)t & 1) ^ 1, 400);  // every gather thread has pulled the previous tile's columns
+                    else mbar_wait(BAR(B_OMEMPTY + hf), ((uint32_t)t & 1) ^ 1);
                     tc_fence_after();
                     const uint32_t d = tmem_base + (uint32_t)hf * FP_OM_COLS;
 #pragma unroll
@@ -247,7 +251,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FP_THREADS, 1) dcn_p
 #pragma unroll
                 for (int u = 0; u < 18 / FP_SPS; ++u) {
                     const int st = u % FP_SA;
-                    mbar_wait_idle(BAR(B_AFULL + st), ((uint32_t)t * (18 / FP_SPS / FP_SA) + u / FP_SA) & 1);
+                    if (slow_poll) mbar_wait_sleep(BAR(B_AFULL + st), ((uint32_t)t * (18 / FP_SPS / FP_SA) + u / FP_SA) & 1, 200);
+                    else mbar_wait_idle(BAR(B_AFULL + st), ((uint32_t)t * (18 / FP_SPS / FP_SA) + u / FP_SA) & 1);
                     tc_fence_after();
                     if (elect_one()) {
 #pragma unroll
@@ -439,7 +444,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FP_THREADS, 1) dcn_p
             const uint32_t buf = (uint32_t)t & 1;
             const int y = ty * TC_ROWS + lq, x = tx * TC_TW + lane;
             const bool valid = real && y < p.H && x < p.W;
-            mbar_wait_idle(BAR(B_DFULL + buf), ((uint32_t)t >> 1) & 1);  // a tile takes ~10k cycles to gather
+            if (slow_poll) mbar_wait_sleep(BAR(B_DFULL + buf), ((uint32_t)t >> 1) & 1, 1000);  // a tile takes ~10k cycles to gather
+            else mbar_wait_idle(BAR(B_DFULL + buf), ((uint32_t)t >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + FP_D_COL0 + buf * 64 + ((uint32_t)(lq * 32) << 16);
             uint4 *o = reinterpret_cast<uint4 *>(p.out + (long long)n * p.out_image_stride) + (long long)y * p.W + x;

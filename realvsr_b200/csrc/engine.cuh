@@ -159,9 +159,9 @@ bool tc_conv_supported(const ConvOp &op);
 int launch_conv_tc(const ConvOp &op, cudaStream_t s);
 size_t tc_conv_weight_bytes(int Cout, int Cin, int ks, int mode = 0);
 // mode: 0 plain, 1 pixel-shuffle column order, 2 OUT_OM24 column order (Cout == 27 * dg)
-int pack_weight_tc(const float *w_oihw, void *dst, int Cout, int Cin, int ks, int mode, cudaStream_t s);
+int pack_weight_tc(const float *w_oihw, void *dst, int Cout, int Cin, int ks, int mode, cudaStream_t s, const WeightView *view = nullptr);
 size_t tc2_weight_bytes(int Cout, int Cin, int ks, int mode = 0);
-int pack_weight_tc2(const float *w_oihw, void *dst, int Cout, int Cin, int ks, int mode, cudaStream_t s);
+int pack_weight_tc2(const float *w_oihw, void *dst, int Cout, int Cin, int ks, int mode, cudaStream_t s, const WeightView *view = nullptr);
 size_t tc_tapn_weight_bytes(int Cout, int Cin, int ks);   // conv_last "taps in N" kernel (Cout <= 3)
 int pack_weight_tapn(const float *w_oihw, void *dst, int Cout, int Cin, cudaStream_t s);
 int launch_conv_tapn(const ConvOp &op, const void *w_tapn, cudaStream_t s);

@@ -57,6 +57,26 @@ __device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity) {
     }
     __trap();
 }
+// For roles that wait for MICROSECONDS inside a CTA with heavy mbarrier traffic: poll, then sleep a FIXED time.  (The
+// suspend-time hint above compiles to NANOSLEEP.SYNCS, which any mbarrier event of the CTA ends: in the fused DCN pack kernel
+// the idle warps woke up 14 000 times each per launch and the wake-up / re-check loops were ~20 % of all executed instructions,
+// taken from the gather warps of the same scheduler -- ncu source view, profiles/r02_ncu_dcn_pack_fused.txt.)
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, uint32_t ns) {
+    uint32_t done = 0;
+#pragma unroll 1
+    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        asm volatile("nanosleep.u32 %0;" ::"r"(ns));
+    }
+    __trap();
+}
 // tcgen05.mma / commit / TMA take their operands from uniform registers.  If the compiler cannot prove an
 // operand warp-uniform it wraps every instruction in a "waterfall" loop (ELECT + 5x R2UR.BROADCAST + BRA.U.ANY,
 // ~70 cycles per MMA).  So the issuing roles run their loops with the WHOLE warp on provably uniform values

@@ -83,7 +83,24 @@ struct EpiArgs {
     int H, W, Cout, act, out_mode, sig_from, subsample, dg;
     const FinalAdd *fin;  // OUT_FINAL
     int res_pre, res_div;
+    int bf16;  // 16-bit storage format of out / residual: 0 = fp16, 1 = bfloat16 (training path)
 };
+
+// 16-bit pair <-> fp32 pair in either storage format
+template <bool BF> __device__ __forceinline__ float2 unpack16x2(uint32_t u) {
+    if (BF) return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+    return __half22float2(*reinterpret_cast<const __half2 *>(&u));
+}
+template <bool BF> __device__ __forceinline__ uint32_t pack16x2(float a, float b) {
+    if (BF) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<const uint32_t *>(&h);
+    }
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+__device__ __forceinline__ float2 unpack16x2_rt(uint32_t u, int bf) { return bf ? unpack16x2<true>(u) : unpack16x2<false>(u); }
+__device__ __forceinline__ uint32_t pack16x2_rt(float a, float b, int bf) { return bf ? pack16x2<true>(a, b) : pack16x2<false>(a, b); }
 
 // Epilogue of one pixel (= TMEM lane) of one tile.  With NH = 2 two warps share a TMEM lane
 // quarter and take the lower / upper half of the NT accumulator columns.  Order of events:
@@ -152,10 +169,10 @@ template <int NT, int NH> struct EpiTile {
             const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
             float v[8], rr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (RES && has_res) {
-                const __half2 *h = reinterpret_cast<const __half2 *>(&res[RES ? ch * (CW / 8) + j : 0]);
+                const uint32_t *h = reinterpret_cast<const uint32_t *>(&res[RES ? ch * (CW / 8) + j : 0]);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float2 f = __half22float2(h[i]);
+                    const float2 f = unpack16x2_rt(h[i], e.bf16);
                     rr[2 * i] = f.x; rr[2 * i + 1] = f.y;
                 }
             }
@@ -166,9 +183,9 @@ template <int NT, int NH> struct EpiTile {
                 v[i] = pre ? act_t<ACT>(a + rr[i], e.act) : act_t<ACT>(a, e.act) + rr[i];
             }
             uint4 pk;
-            __half2 *h = reinterpret_cast<__half2 *>(&pk);
+            uint32_t *h = reinterpret_cast<uint32_t *>(&pk);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+            for (int i = 0; i < 4; ++i) h[i] = pack16x2_rt(v[2 * i], v[2 * i + 1], e.bf16);
             o[q * plane] = pk;
         }
     }
@@ -193,11 +210,11 @@ template <int NT, int NH> struct EpiTile {
             uint4 pk[2];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                __half2 *h = reinterpret_cast<__half2 *>(&pk[j]);
+                uint32_t *h = reinterpret_cast<uint32_t *>(&pk[j]);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    h[k] = __floats2half2_rn(act_t<ACT>(__uint_as_float(acc[g][j * 8 + 2 * k]) + b[j * 8 + 2 * k], e.act),
-                                             act_t<ACT>(__uint_as_float(acc[g][j * 8 + 2 * k + 1]) + b[j * 8 + 2 * k + 1], e.act));
+                    h[k] = pack16x2_rt(act_t<ACT>(__uint_as_float(acc[g][j * 8 + 2 * k]) + b[j * 8 + 2 * k], e.act),
+                                       act_t<ACT>(__uint_as_float(acc[g][j * 8 + 2 * k + 1]) + b[j * 8 + 2 * k + 1], e.act), e.bf16);
             }
             st_global_256(ob + (long long)g * plane2, pk[0], pk[1]);
         }
@@ -331,7 +348,7 @@ template <int NT, int NH> struct EpiTile {
 // before the accumulator wait, all 32 columns of the warp in registers with ONE tcgen05.wait::ld, and the TMEM
 // buffer handed back before any arithmetic.  Exact integer division of the tile index by precomputed magic
 // numbers (host: magic_div) replaces three hardware divisions per tile and warp.
-template <int ACT, typename Release>
+template <int ACT, bool BF, typename Release>
 __device__ __forceinline__ void epi_c8_fast(const float *bias_s, __half *out, long long out_image_stride, const __half *residual,
                                             long long res_image_stride, int H, int W, int Co8, uint32_t taddr, int half,
                                             int qbase, int n, int y, int x, bool valid, uint32_t full_bar, uint32_t full_par,
@@ -367,7 +384,7 @@ __device__ __forceinline__ void epi_c8_fast(const float *bias_s, __half *out, lo
 #pragma unroll
         for (int i = 0; i < 4; ++i) {  // packed fp32 pairs (FADD2 / FMUL2): same IEEE results, half the instructions
             v[i] = add2(make_float2(__uint_as_float(a[2 * i]), __uint_as_float(a[2 * i + 1])), bb[i]);
-            if (pre) v[i] = add2(v[i], __half22float2(reinterpret_cast<const __half2 *>(&res[j])[i]));
+            if (pre) v[i] = add2(v[i], unpack16x2<BF>(reinterpret_cast<const uint32_t *>(&res[j])[i]));
             if (ACT == RVSR_ACT_LRELU) {
                 const float2 t = mul2(v[i], make_float2(0.1f, 0.1f));
                 v[i] = make_float2(fmaxf(v[i].x, t.x), fmaxf(v[i].y, t.y));
@@ -376,14 +393,14 @@ __device__ __forceinline__ void epi_c8_fast(const float *bias_s, __half *out, lo
             }
         }
         if (has_res && !pre) {
-            const __half2 *h = reinterpret_cast<const __half2 *>(&res[j]);
+            const uint32_t *h = reinterpret_cast<const uint32_t *>(&res[j]);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] = add2(v[i], __half22float2(h[i]));
+            for (int i = 0; i < 4; ++i) v[i] = add2(v[i], unpack16x2<BF>(h[i]));
         }
         uint4 pk;
-        __half2 *h = reinterpret_cast<__half2 *>(&pk);
+        uint32_t *h = reinterpret_cast<uint32_t *>(&pk);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[i].x, v[i].y);
+        for (int i = 0; i < 4; ++i) h[i] = pack16x2<BF>(v[i].x, v[i].y);
         *o = pk;
         o += plane;
     }
@@ -407,6 +424,7 @@ struct alignas(64) TcConvParams {
     int tiles_x, tiles_y, num_tiles;
     TileDiv td;
     FinalAdd fin;
+    int bf16;   // operands, residual and output are bfloat16 instead of fp16 (training path; same kernels, other instruction-descriptor formats)
     int stamp;  // slot in g_stamps or -1
     int debug;  // RVSR_TC_DEBUG bit mask for timing experiments only (results become garbage):
                 // 1 = issue no MMAs, 2 = no epilogue stores, 4 = no TMA halo loads, 8 = no TMEM loads
@@ -532,7 +550,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             // ---- MMA issuer(s).  The issue stream is the critical path of the whole kernel (the tensor pipe
             // needs a new N=64 MMA every 48 cycles), so: whole warp on uniform values (see elect_one()), no
             // divisions, no 64-bit descriptor rebuilds, running counters instead of modulo, everything unrolled.
-            constexpr uint32_t idesc = make_idesc(NT);
+            const uint32_t idesc = make_idesc(NT) | (p.bf16 ? (1u << 7) | (1u << 10) : 0u);  // a/b format: 0 = F16, 1 = BF16
             const uint32_t mw = (uint32_t)(warp - 1);
             const uint32_t nsrc = (uint32_t)p.nsrc, C8s = (uint32_t)p.C8s;
             const uint64_t adesc0 = make_desc(smem_u32(stage_s), PLANE_BYTES, 128);
@@ -602,7 +620,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int eg = (warp - TC_EPI_WARP0) / WPG;                  // this warp's group: tiles t == eg (mod groups)
         const int half = ((warp - TC_EPI_WARP0) % WPG) >> 2;         // WPG / 4 warps per lane quarter split the columns
         EpiArgs e{bias_s, p.out, p.out_image_stride, p.residual, p.res_image_stride, p.H, p.W, p.Cout, p.act,
-                  p.out_mode, p.sig_from, p.subsample, p.dg, &p.fin, p.res_pre, p.res_div};
+                  p.out_mode, p.sig_from, p.subsample, p.dg, &p.fin, p.res_pre, p.res_div, p.bf16};
         EpiTile<NT, WPG / 4> ep;
         uint32_t t = (uint32_t)eg;
         for (int tile = blockIdx.x + eg * gridDim.x; tile < p.num_tiles; tile += EG * gridDim.x, t += EG) {
@@ -768,7 +786,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
                 mbar_arrive_cluster(mapa_rank0(WPEER));
             }
         } else {  // whole warp, uniform values; only the tcgen05 instructions are predicated on one lane
-            constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((256u >> 4) << 24);  // M = 256 over the pair
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((256u >> 4) << 24) |  // M = 256 over the pair
+                                   (p.bf16 ? (1u << 7) | (1u << 10) : 0u);
             const uint32_t mw = (uint32_t)(warp - 1);
             const uint32_t nsrc = (uint32_t)p.nsrc, C8s = (uint32_t)p.C8s;
             const uint64_t adesc0 = make_desc(smem_u32(stage_s), PLANE_BYTES, 128);
@@ -850,13 +869,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
         const int eg = (warp - TC_EPI_WARP0) / WPG;
         const int half = ((warp - TC_EPI_WARP0) % WPG) >> 2;
         EpiArgs e{bias_s, p.out, p.out_image_stride, p.residual, p.res_image_stride, p.H, p.W, p.Cout, p.act,
-                  p.out_mode, p.sig_from, p.subsample, p.dg, &p.fin, p.res_pre, p.res_div};
+                  p.out_mode, p.sig_from, p.subsample, p.dg, &p.fin, p.res_pre, p.res_div, p.bf16};
         EpiTile<NT, WPG / 4> ep;
         uint32_t t = (uint32_t)eg;
         if (NT == 64 && WPG == 8 && p.out_mode == OUT_C8 && !p.subsample && p.debug == 0) {
             // lean path (see epi_c8_fast): every 64-wide stride-1 convolution of the network
-            auto tiles = [&](auto act_tag) {
+            auto tiles = [&](auto act_tag, auto bf_tag) {
                 constexpr int ACT = decltype(act_tag)::value;
+                constexpr bool BF = decltype(bf_tag)::value;
                 const int Co8 = (p.Cout + 7) / 8;
                 uint32_t buf = (uint32_t)eg, par = 0;  // buf = t % NB, par = (t / NB) & 1 without divisions
                 for (int pr = cid + eg * nclusters; pr < npairs; pr += EG * nclusters) {
@@ -867,7 +887,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
                     const int y = ty * TC_ROWS + lq, x = tx * VALID + lane;
                     const bool valid = real && lane < VALID && y < p.H && x < p.W;
                     const uint32_t tempty0 = mapa_rank0(TEMPTY(buf));
-                    epi_c8_fast<ACT>(bias_s, reinterpret_cast<__half *>(p.out), p.out_image_stride, p.residual, p.res_image_stride,
+                    epi_c8_fast<ACT, BF>(bias_s, reinterpret_cast<__half *>(p.out), p.out_image_stride, p.residual, p.res_image_stride,
                                      p.H, p.W, Co8, tmem_base + buf * ACC + ((uint32_t)(lq * 32) << 16), half, pss * (NT / 8), n, y, x,
                                      valid, TFULL(buf), par, [&] {
                                          tc_fence_before();
@@ -879,9 +899,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
                     if (buf >= (uint32_t)NB) { buf -= NB; par ^= 1u; }
                 }
             };
-            if (p.act == RVSR_ACT_LRELU) tiles(std::integral_constant<int, RVSR_ACT_LRELU>{});
-            else if (p.act == RVSR_ACT_RELU) tiles(std::integral_constant<int, RVSR_ACT_RELU>{});
-            else tiles(std::integral_constant<int, RVSR_ACT_NONE>{});
+            if (p.bf16) {
+                if (p.act == RVSR_ACT_LRELU) tiles(std::integral_constant<int, RVSR_ACT_LRELU>{}, std::true_type{});
+                else if (p.act == RVSR_ACT_RELU) tiles(std::integral_constant<int, RVSR_ACT_RELU>{}, std::true_type{});
+                else tiles(std::integral_constant<int, RVSR_ACT_NONE>{}, std::true_type{});
+            } else if (p.act == RVSR_ACT_LRELU) tiles(std::integral_constant<int, RVSR_ACT_LRELU>{}, std::false_type{});
+            else if (p.act == RVSR_ACT_RELU) tiles(std::integral_constant<int, RVSR_ACT_RELU>{}, std::false_type{});
+            else tiles(std::integral_constant<int, RVSR_ACT_NONE>{}, std::false_type{});
         } else
         for (int pr = cid + eg * nclusters; pr < npairs; pr += EG * nclusters, t += EG) {
             const int tile = 2 * pr + (int)rank;
@@ -928,8 +952,13 @@ size_t tc_conv_weight_bytes(int Cout, int Cin, int ks, int mode) {
 }
 size_t tc_dcn_weight_bytes(int Cout, int C, int K) { return (Cout == 64 && C == 64 && K == 9) ? tc_conv_weight_bytes(64, 64, 3) : 0; }
 
-__global__ void pack_weight_tc_kernel(const float *__restrict__ w, __half *__restrict__ dst, int Cout, int Cin, int KK,
-                                      int Q, int NT, int mode, long long total) {
+// Weight element (co, cin, tap) is read at w[base + co * s_co + cin * s_ci + tap * s_tap]: OIHW is (Cin * KK, KK, 1, 0); the
+// transposed, flipped slice a data-gradient convolution needs is another stride set (WeightView, common.cuh).
+__device__ __forceinline__ uint16_t to_16(float v, int bf) {
+    return bf ? __bfloat16_as_ushort(__float2bfloat16_rn(v)) : __half_as_ushort(__float2half_rn(v));
+}
+__global__ void pack_weight_tc_kernel(const float *__restrict__ w, uint16_t *__restrict__ dst, int Cout, int Cin, int KK,
+                                      int Q, int NT, int mode, long long total, WeightView wv) {
     const int dg = Cout / 27;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int e = (int)(i % 8);
@@ -950,16 +979,17 @@ __global__ void pack_weight_tc_kernel(const float *__restrict__ w, __half *__res
         } else {
             co = pss * NT + n;
         }
-        dst[i] = __float2half_rn((co < Cout && cin < Cin) ? w[((long long)co * Cin + cin) * KK + tap] : 0.f);
+        dst[i] = to_16((co < Cout && cin < Cin) ? w[wv.base + (long long)co * wv.s_co + (long long)cin * wv.s_ci + (long long)tap * wv.s_tap] : 0.f, wv.bf16);
     }
 }
-int pack_weight_tc(const float *w_oihw, void *dst, int Cout, int Cin, int ks, int mode, cudaStream_t s) {
+int pack_weight_tc(const float *w_oihw, void *dst, int Cout, int Cin, int ks, int mode, cudaStream_t s, const WeightView *view) {
+    const WeightView wv = view ? *view : WeightView{0, (long long)Cin * ks * ks, ks * ks, 1, 0};
     const int NT = tc_pick_nt(Cout, mode);
     RVSR_CHECK_ARG(NT != 0, "tc pack: unsupported Cout %d (mode %d)", Cout, mode);
     const int Q = pad16(Cin) / 8;
     const long long total = (long long)tc_passes(Cout, NT, mode) * ks * ks * Q * NT * 8;
     pack_weight_tc_kernel<<<(int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096), 256, 0, s>>>(
-        w_oihw, reinterpret_cast<__half *>(dst), Cout, Cin, ks * ks, Q, NT, mode, total);
+        w_oihw, reinterpret_cast<uint16_t *>(dst), Cout, Cin, ks * ks, Q, NT, mode, total, wv);
     RVSR_LAUNCH_CHECK();
     return RVSR_OK;
 }
@@ -974,8 +1004,8 @@ size_t tc2_weight_bytes(int Cout, int Cin, int ks, int mode) {
     if (ks != 3 || (NT != 64 && NT != 128) || Cin % 16 != 0) return 0;
     return tc_conv_weight_bytes(Cout, Cin, ks, mode);
 }
-__global__ void pack_weight_tc2_kernel(const float *__restrict__ w, __half *__restrict__ dst, int Cout, int Cin, int Q, int NT,
-                                       int mode, long long total) {
+__global__ void pack_weight_tc2_kernel(const float *__restrict__ w, uint16_t *__restrict__ dst, int Cout, int Cin, int Q, int NT,
+                                       int mode, long long total, WeightView wv) {
     const int dg = Cout / 27, NH = NT / 2;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int e = (int)(i % 8);
@@ -998,15 +1028,16 @@ __global__ void pack_weight_tc2_kernel(const float *__restrict__ w, __half *__re
         } else {
             co = pss * NT + n;
         }
-        dst[i] = __float2half_rn(co < Cout ? w[((long long)co * Cin + cin) * 9 + tap] : 0.f);
+        dst[i] = to_16(co < Cout ? w[wv.base + (long long)co * wv.s_co + (long long)cin * wv.s_ci + (long long)tap * wv.s_tap] : 0.f, wv.bf16);
     }
 }
-int pack_weight_tc2(const float *w_oihw, void *dst, int Cout, int Cin, int ks, int mode, cudaStream_t s) {
+int pack_weight_tc2(const float *w_oihw, void *dst, int Cout, int Cin, int ks, int mode, cudaStream_t s, const WeightView *view) {
+    const WeightView wv = view ? *view : WeightView{0, (long long)Cin * 9, 9, 1, 0};
     RVSR_CHECK_ARG(tc2_weight_bytes(Cout, Cin, ks, mode) > 0, "tc2 pack: unsupported shape");
     const int NT = tc_pick_nt(Cout, mode);
     const long long total = (long long)tc_passes(Cout, NT, mode) * 2 * 9 * (Cin / 8) * (NT / 2) * 8;
     pack_weight_tc2_kernel<<<(int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096), 256, 0, s>>>(
-        w_oihw, reinterpret_cast<__half *>(dst), Cout, Cin, Cin / 8, NT, mode, total);
+        w_oihw, reinterpret_cast<uint16_t *>(dst), Cout, Cin, Cin / 8, NT, mode, total, wv);
     RVSR_LAUNCH_CHECK();
     return RVSR_OK;
 }
@@ -1106,7 +1137,7 @@ int launch_conv_tc(const ConvOp &op, cudaStream_t s) {
     p.w = reinterpret_cast<const __half *>(op.w_tc); p.bias = op.bias;
     p.out = op.out; p.out_image_stride = op.out_image_stride;
     p.residual = reinterpret_cast<const __half *>(op.residual); p.res_image_stride = op.res_image_stride;
-    p.res_pre = op.res_pre; p.res_div = op.res_div > 0 ? op.res_div : 1;
+    p.res_pre = op.res_pre; p.res_div = op.res_div > 0 ? op.res_div : 1; p.bf16 = op.bf16;
     p.N = op.N; p.H = op.H; p.W = op.W; p.Cout = op.Cout; p.act = op.act; p.out_mode = op.out_mode;
     p.sig_from = op.sig_from; p.subsample = op.stride == 2 ? 1 : 0; p.dg = op.dg; p.fin = op.fin;
     const int valid = TC_TW - (op.ks - 1);

@@ -1,0 +1,496 @@
+// train_kernels.cu -- the bf16 TRAINING path on channel-blocked tensors (BASELINE cfg5: forward + backward of the plain
+// convolutions of EDVR_arch.py on this library's own kernels instead of cuDNN).
+//
+// Tensors are "C8": [N][C/8][H][W][8] bfloat16, the layout of the inference engine, held by PyTorch as ordinary 5-D tensors
+// (realvsr_b200/train_c8.py) so that torch.autograd orchestrates and every Function below is one launch of:
+//   forward / data gradient   conv_tc2_kernel / conv_tc_kernel (tc_kernels.cu) with bf16 operands; the data gradient of a
+//                             stride-1 convolution IS a convolution with the transposed, flipped weights (WeightView)
+//   weight (+ bias) gradient  conv_wgrad_tc_kernel (here): dW[tap][ci][co] = sum_pixels x[pixel + tap][ci] * g[pixel][co], a GEMM
+//                             whose K dimension is the PIXEL axis, on tcgen05 with both operands MN-major
+//   activation gradient, pixel-unshuffle, x2 bilinear upsample forward / adjoint, NCHW <-> C8: small CUDA-core kernels (HBM-bound)
+// Reference semantics: nn.Conv2d autograd at EDVR_arch.py:71-91, :229-253, arch_util.py:121-139; F.interpolate(scale_factor=2,
+// mode='bilinear', align_corners=False) at EDVR_arch.py:109-121; nn.PixelShuffle(2) at :313-314.
+#include <cuda_bf16.h>
+
+#include "tc_common.cuh"
+
+namespace rvsr {
+
+namespace {
+
+// ---------------------------------------------------------------- weight gradient on tcgen05
+// Per 128-pixel tile (4 rows x 32 columns) and K step (16 consecutive pixels of one row):
+//   B operand  = g tile   [8 co blocks][4 rows][32 px][8]   (TMA, dense box)            N = 64 output channels
+//   A operand  = x halo   [16 blocks][6 rows][34 px][8]: blocks 0-7 the tile's halo from row -1, blocks 8-15 THE SAME halo from
+//                row 0 -- so one M = 128 instruction covers taps (dy, dx) [rows 0-63] and (dy + 1, dx) [rows 64-127] of all 64
+//                input channels.  A tap is a shifted start address, exactly as in the forward kernels.  The halo is 34 pixels
+//                wide (K steps must not wrap at dx = +1), which no dense TMA box delivers (<= 256 elements per dimension), so
+//                eight producer warps assemble it with 16-byte loads (zero fill outside the image) and write both copies.
+//   D          = six 128 x 64 fp32 accumulators in TMEM, resident over ALL tiles of the CTA: (dy -1|0, dx -1), (.., dx 0),
+//                (.., dx +1), then (dy +1|unused, dx -1..+1): 6 instructions per K step for 9 taps (75 % useful rows).
+// One red.global.add.v4.f32 pass per CTA at the end into dW^T [9][64][Cout] fp32 (zeroed by the caller).  The bias gradient
+// (column sums of g) is taken from the g tiles in shared memory by two otherwise idle warps.
+constexpr int WG_PROD_WARPS = 8, WG_WARP_TMA = 8, WG_WARP_MMA = 9, WG_WARP_BIAS0 = 10, WG_BIAS_WARPS = 2;
+constexpr int WG_THREADS = 32 * (WG_WARP_BIAS0 + WG_BIAS_WARPS);
+constexpr int WG_XCOLS = 34, WG_XROWS = 6;
+constexpr int WG_XPLANE = WG_XROWS * WG_XCOLS * 16;  // 3264 B per channel block
+constexpr int WG_XCOPY = 8 * WG_XPLANE;              // 26112
+constexpr int WG_G_BYTES = 8 * 128 * 16;             // 16384
+constexpr int WG_STAGE = WG_G_BYTES + 2 * WG_XCOPY;  // 68608 (a multiple of 128: the TMA destination stays aligned)
+constexpr int WG_STAGES = 3;
+constexpr int WG_HALO_ELEMS = 8 * (WG_XROWS + 1) * WG_XCOLS;  // 16-byte cells loaded per tile: rows -1 .. 5
+constexpr int WG_PER_THREAD = (WG_HALO_ELEMS + 32 * WG_PROD_WARPS - 1) / (32 * WG_PROD_WARPS);
+
+struct alignas(64) WgradParams {
+    CUtensorMap tmap_g;        // [W * 8, H, N * g_planes] bf16, box {256, 4, 8}
+    const uint4 *x;            // C8 bf16: 16-byte cells [N][planes][H][W]
+    long long x_image_stride;  // cells between images
+    int g_planes;              // channel blocks per image of g
+    float *dw;                 // [9][64][Cout] fp32, accumulated into
+    float *db;                 // [Cout] fp32 or null, accumulated into
+    int Cout, N, H, W;
+    int tiles_x, tiles_y, num_tiles;
+    TileDiv td;
+};
+
+__device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// kind::f16 with bf16 A / B, fp32 D, both operands MN-major
+__host__ __device__ constexpr uint32_t wg_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __grid_constant__ WgradParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *stage_s = smem;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(stage_s + WG_STAGES * WG_STAGE);
+    constexpr int B_FULL = 0, B_EMPTY = WG_STAGES, B_DONE = 2 * WG_STAGES, B_COUNT = B_DONE + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + B_COUNT);
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int pass = blockIdx.y;
+    const int T = blockIdx.x < (unsigned)p.num_tiles ? (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < WG_STAGES; ++i) {
+            mbar_init(BAR(B_FULL + i), WG_PROD_WARPS + 1);   // producer warps + the TMA thread's expect_tx arrival
+            mbar_init(BAR(B_EMPTY + i), 1 + WG_BIAS_WARPS);  // tcgen05.commit + the bias warps
+        }
+        mbar_init(BAR(B_DONE), 1);
+        fence_barrier_init();
+        prefetch_tensormap(&p.tmap_g);
+    }
+    if (warp == WG_WARP_MMA) tmem_alloc(smem_u32(tmem_slot), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = uniform_u32(*tmem_slot);
+
+    if (warp < WG_PROD_WARPS) {
+        // ---- x halo producers: rows -1 .. 5 of the tile, 34 columns from -1, all 8 channel blocks; rows 0 .. 4 go to both copies
+        const long long plane = (long long)p.H * p.W;
+        for (int t = 0; t < T; ++t) {
+            const int tile = blockIdx.x + t * gridDim.x, st = t % WG_STAGES;
+            int tx, ty, n;
+            tile_coords(p.td, tile, tx, ty, n);
+            const int y0 = ty * TC_ROWS - 1, x0 = tx * TC_TW - 1;
+            const uint4 *src = p.x + (long long)n * p.x_image_stride;
+            uint4 v[WG_PER_THREAD];
+#pragma unroll
+            for (int i = 0; i < WG_PER_THREAD; ++i) {
+                const int idx = (int)threadIdx.x + i * 32 * WG_PROD_WARPS;
+                const int pl = idx / ((WG_XROWS + 1) * WG_XCOLS), rem = idx - pl * ((WG_XROWS + 1) * WG_XCOLS);
+                const int row = rem / WG_XCOLS, col = rem - row * WG_XCOLS;
+                const int gy = y0 + row, gx = x0 + col;
+                v[i] = make_uint4(0, 0, 0, 0);
+                if (idx < WG_HALO_ELEMS && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) v[i] = __ldg(src + pl * plane + (long long)gy * p.W + gx);
+            }
+            mbar_wait(BAR(B_EMPTY + st), ((t / WG_STAGES) & 1) ^ 1);
+            uint4 *xa = reinterpret_cast<uint4 *>(stage_s + st * WG_STAGE + WG_G_BYTES);
+#pragma unroll
+            for (int i = 0; i < WG_PER_THREAD; ++i) {
+                const int idx = (int)threadIdx.x + i * 32 * WG_PROD_WARPS;
+                const int pl = idx / ((WG_XROWS + 1) * WG_XCOLS), rem = idx - pl * ((WG_XROWS + 1) * WG_XCOLS);
+                const int row = rem / WG_XCOLS, col = rem - row * WG_XCOLS;
+                if (idx < WG_HALO_ELEMS) {
+                    if (row < WG_XROWS) xa[(pl * WG_XROWS + row) * WG_XCOLS + col] = v[i];
+                    if (row >= 1) xa[((8 + pl) * WG_XROWS + row - 1) * WG_XCOLS + col] = v[i];
+                }
+            }
+            fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(B_FULL + st));
+        }
+        // ---- flush: D row m = (tap half, ci), column = co.  Warps 0-7: TMEM lane quarter warp & 3, column half warp >> 2.
+        if (T > 0) {
+            mbar_wait(BAR(B_DONE), 0);
+            tc_fence_after();
+            const int q = warp & 3, hf = warp >> 2;
+            const int m = q * 32 + lane, ci = m & 63, uphalf = m >> 6;
+            const int co0 = pass * 64 + hf * 32;
+#pragma unroll 1
+            for (int b = 0; b < 6; ++b) {
+                if (b >= 3 && q >= 2) break;  // rows 64-127 of the dy = +1 accumulators are not weights
+                const int tap = b < 3 ? uphalf * 3 + b : 6 + (b - 3);
+                uint32_t a0[16], a1[16];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 64 + hf * 32);
+                tmem_ld16_nowait(taddr, a0);
+                tmem_ld16_nowait(taddr + 16, a1);
+                tmem_ld_wait();
+                float *d = p.dw + ((long long)tap * 64 + ci) * p.Cout + co0;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    if (co0 + j < p.Cout)
+                        red_add_v4(d + j, __uint_as_float(a0[j]), __uint_as_float(a0[j + 1]), __uint_as_float(a0[j + 2]), __uint_as_float(a0[j + 3]));
+                    if (co0 + 16 + j < p.Cout)
+                        red_add_v4(d + 16 + j, __uint_as_float(a1[j]), __uint_as_float(a1[j + 1]), __uint_as_float(a1[j + 2]), __uint_as_float(a1[j + 3]));
+                }
+            }
+        }
+    } else if (warp == WG_WARP_TMA) {
+        if (lane == 0) {
+            for (int t = 0; t < T; ++t) {
+                const int tile = blockIdx.x + t * gridDim.x, st = t % WG_STAGES;
+                int tx, ty, n;
+                tile_coords(p.td, tile, tx, ty, n);
+                mbar_wait(BAR(B_EMPTY + st), ((t / WG_STAGES) & 1) ^ 1);
+                mbar_expect_tx(BAR(B_FULL + st), WG_G_BYTES);
+                tma_load_3d(smem_u32(stage_s + st * WG_STAGE), &p.tmap_g, BAR(B_FULL + st), tx * TC_TW * 8, ty * TC_ROWS,
+                            n * p.g_planes + pass * 8);
+            }
+        }
+    } else if (warp == WG_WARP_MMA) {
+        constexpr uint32_t idesc = wg_idesc(128, 64);
+        for (int t = 0; t < T; ++t) {
+            const int st = t % WG_STAGES;
+            mbar_wait(BAR(B_FULL + st), (t / WG_STAGES) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t g0 = smem_u32(stage_s + st * WG_STAGE), x0 = g0 + WG_G_BYTES;
+#pragma unroll
+                for (int r = 0; r < TC_ROWS; ++r)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint64_t bdesc = make_desc(g0 + (uint32_t)(r * TC_TW + h * 16) * 16, 128, 2048);
+#pragma unroll
+                        for (int b = 0; b < 6; ++b) {
+                            const uint32_t a = x0 + (uint32_t)((r + (b >= 3 ? 2 : 0)) * WG_XCOLS + h * 16 + (b % 3)) * 16;
+                            umma_f16(tmem_base + (uint32_t)b * 64, make_desc(a, 128, WG_XPLANE), bdesc, idesc, (t | r | h) ? 1u : 0u);
+                        }
+                    }
+                umma_commit(BAR(B_EMPTY + st));
+            }
+            __syncwarp();
+        }
+        if (T > 0 && elect_one()) umma_commit(BAR(B_DONE));
+        __syncwarp();
+    } else {
+        // ---- bias gradient: column sums of the g tiles (pixels outside the image arrive as zeros)
+        const int j = (warp - WG_WARP_BIAS0) * 32 + lane;  // 0 .. 63: channel block j / 8, pixels (j % 8) * 16 ..
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int t = 0; t < T; ++t) {
+            const int st = t % WG_STAGES;
+            mbar_wait_sleep(BAR(B_FULL + st), (t / WG_STAGES) & 1, 200);
+            if (p.db != nullptr) {
+                const uint4 *g = reinterpret_cast<const uint4 *>(stage_s + st * WG_STAGE) + (j >> 3) * 128 + (j & 7) * 16;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const uint4 u = g[i];
+                    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        acc[2 * k] += __uint_as_float(w[k] << 16);
+                        acc[2 * k + 1] += __uint_as_float(w[k] & 0xffff0000u);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(B_EMPTY + st));
+        }
+        if (p.db != nullptr && T > 0) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float s = acc[k];
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                s += __shfl_xor_sync(0xffffffffu, s, 4);
+                const int co = pass * 64 + (j >> 3) * 8 + k;
+                if ((j & 7) == 0 && co < p.Cout) atomicAdd(p.db + co, s);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == WG_WARP_MMA) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------- small CUDA-core kernels (bf16, 16-byte cells)
+__device__ __forceinline__ void unpack8(const uint4 &u, float (&v)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[2 * i] = __uint_as_float(w[i] << 16);
+        v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+    uint4 u;
+    uint32_t *w = reinterpret_cast<uint32_t *>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        w[i] = *reinterpret_cast<const uint32_t *>(&h);
+    }
+    return u;
+}
+
+// gradient through LeakyReLU(0.1) / ReLU given the layer's OUTPUT y (sign(y) == sign of the pre-activation; at 0 both
+// frameworks take the negative branch): out = y > 0 ? g : slope * g
+__global__ void act_bwd_c8_kernel(const uint4 *__restrict__ g, const uint4 *__restrict__ y, uint4 *__restrict__ out, long long n, float slope) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float gv[8], yv[8];
+        unpack8(__ldg(g + i), gv);
+        unpack8(__ldg(y + i), yv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) gv[k] = yv[k] > 0.f ? gv[k] : slope * gv[k];
+        out[i] = pack8(gv);
+    }
+}
+
+// Gradient through lrelu(PixelShuffle(2)(conv)) (EDVR_arch.py:313-314): g, y are [N][C2/8][2H][2W][8] (C2 = C / 4 channels),
+// out is the gradient of the conv output [N][C/8][H][W][8]: out[n, 4c + 2i + j, h, w] = g[n, c, 2h + i, 2w + j] * act'(y[...]).
+// One thread per (n, output channel block q, h, w): its 8 channels 8q .. 8q+7 = c in {2q, 2q + 1} x (i, j).
+__global__ void unshuffle2_act_bwd_kernel(const __nv_bfloat16 *__restrict__ g, const __nv_bfloat16 *__restrict__ y, uint4 *__restrict__ out,
+                                          int C8, int H, int W, long long total, float slope, int has_act) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int w = (int)(i % W);
+        long long r = i / W;
+        const int h = (int)(r % H);
+        r /= H;
+        const int q = (int)(r % C8);
+        const long long n = r / C8;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int ch = q * 8 + e, c = ch >> 2, ii = (ch >> 1) & 1, jj = ch & 1;
+            const long long src = (((n * (C8 / 4) + (c >> 3)) * (2 * H) + (2 * h + ii)) * (long long)(2 * W) + (2 * w + jj)) * 8 + (c & 7);
+            const float gv = __bfloat162float(g[src]);
+            v[e] = (!has_act || __bfloat162float(y[src]) > 0.f) ? gv : slope * gv;
+        }
+        out[i] = pack8(v);
+    }
+}
+
+// F.interpolate(scale_factor=2, mode='bilinear', align_corners=False) on [planes][H][W][8], times `scale`
+__global__ void upsample2x_c8_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, int H, int W, long long total, float scale) {
+    const int Ho = 2 * H, Wo = 2 * W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % Wo);
+        long long r = i / Wo;
+        const int oy = (int)(r % Ho);
+        const long long pl = r / Ho;
+        const float sy = fmaxf(0.5f * (oy + 0.5f) - 0.5f, 0.f), sx = fmaxf(0.5f * (ox + 0.5f) - 0.5f, 0.f);
+        const int y0 = (int)sy, x0 = (int)sx, y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+        const float ly = sy - y0, lx = sx - x0;
+        const uint4 *p = src + pl * H * W;
+        float a[8], b[8], c[8], d[8], o[8];
+        unpack8(__ldg(p + (long long)y0 * W + x0), a);
+        unpack8(__ldg(p + (long long)y0 * W + x1), b);
+        unpack8(__ldg(p + (long long)y1 * W + x0), c);
+        unpack8(__ldg(p + (long long)y1 * W + x1), d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = scale * ((1.f - ly) * ((1.f - lx) * a[k] + lx * b[k]) + ly * ((1.f - lx) * c[k] + lx * d[k]));
+        dst[i] = pack8(o);
+    }
+}
+// its adjoint: gin[y][x] = scale * sum over the outputs whose two taps per axis include (y, x).  Output rows 2y-1 .. 2y+2 can
+// reference input row y; each candidate recomputes its (y0, y1, ly) exactly as the forward does, so borders are exact.
+__global__ void upsample2x_bwd_c8_kernel(const uint4 *__restrict__ g, uint4 *__restrict__ gin, int H, int W, long long total, float scale) {
+    const int Ho = 2 * H, Wo = 2 * W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W);
+        long long r = i / W;
+        const int y = (int)(r % H);
+        const long long pl = r / H;
+        const uint4 *p = g + pl * Ho * Wo;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float wy[4], wx[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int oy = 2 * y - 1 + k, ox = 2 * x - 1 + k;
+            wy[k] = 0.f; wx[k] = 0.f;
+            if (oy >= 0 && oy < Ho) {
+                const float sy = fmaxf(0.5f * (oy + 0.5f) - 0.5f, 0.f);
+                const int y0 = (int)sy, y1 = y0 + (y0 < H - 1 ? 1 : 0);
+                const float ly = sy - y0;
+                wy[k] = (y0 == y ? 1.f - ly : 0.f) + (y1 == y ? ly : 0.f);
+            }
+            if (ox >= 0 && ox < Wo) {
+                const float sx = fmaxf(0.5f * (ox + 0.5f) - 0.5f, 0.f);
+                const int x0 = (int)sx, x1 = x0 + (x0 < W - 1 ? 1 : 0);
+                const float lx = sx - x0;
+                wx[k] = (x0 == x ? 1.f - lx : 0.f) + (x1 == x ? lx : 0.f);
+            }
+        }
+#pragma unroll
+        for (int ky = 0; ky < 4; ++ky) {
+            if (wy[ky] == 0.f) continue;
+#pragma unroll
+            for (int kx = 0; kx < 4; ++kx) {
+                if (wx[kx] == 0.f) continue;
+                float v[8];
+                unpack8(__ldg(p + (long long)(2 * y - 1 + ky) * Wo + (2 * x - 1 + kx)), v);
+                const float w = wy[ky] * wx[kx];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] += w * v[k];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] *= scale;
+        gin[i] = pack8(acc);
+    }
+}
+
+// NCHW (bf16 or fp32) -> C8 bf16 (channels beyond C are zero) and back; one thread per (pixel, channel block)
+template <typename Tin>
+__global__ void nchw_to_c8_kernel(const Tin *__restrict__ src, uint4 *__restrict__ dst, int C, int HW, int C8) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= HW) return;
+    const int q = blockIdx.y;  // C8: channel blocks per image of the C8 tensor (>= gridDim.y)
+    const long long n = blockIdx.z;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int c = q * 8 + e;
+        v[e] = c < C ? to_f<Tin>(src[(n * C + c) * (long long)HW + i]) : 0.f;
+    }
+    dst[(n * C8 + q) * (long long)HW + i] = pack8(v);
+}
+template <typename Tout>
+__global__ void c8_to_nchw_kernel(const uint4 *__restrict__ src, Tout *__restrict__ dst, int C, int HW, int C8) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= HW) return;
+    const int q = blockIdx.y;
+    const long long n = blockIdx.z;
+    float v[8];
+    unpack8(__ldg(src + (n * C8 + q) * (long long)HW + i), v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int c = q * 8 + e;
+        if (c < C) {
+            if constexpr (sizeof(Tout) == 4) dst[(n * C + c) * (long long)HW + i] = v[e];
+            else dst[(n * C + c) * (long long)HW + i] = __float2bfloat16_rn(v[e]);
+        }
+    }
+}
+
+static int ew_grid(long long n) {
+    long long b = (n + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+bool conv_wgrad_tc_supported(int Cin, int ks, int stride) {
+    return Cin == 64 && ks == 3 && stride == 1 && get_encode() != nullptr;
+}
+
+// dw: [9][64][Cout] fp32 and db: [Cout] fp32 (or null), both ACCUMULATED into (the caller zeroes them).
+int launch_conv_wgrad_tc(const void *x_c8, long long x_image_stride, const void *g_c8, float *dw, float *db, int N, int H, int W,
+                         int Cout, cudaStream_t s) {
+    RVSR_CHECK_ARG(Cout > 0 && Cout % 8 == 0, "conv wgrad: Cout %d is not a multiple of 8", Cout);
+    RVSR_CHECK_ARG(x_image_stride % 8 == 0, "conv wgrad: image stride");
+    if (N == 0) return RVSR_OK;
+    EncodeTiledFn enc = get_encode();
+    RVSR_CHECK_ARG(enc != nullptr, "conv wgrad: cuTensorMapEncodeTiled unavailable");
+    WgradParams p;
+    memset(&p, 0, sizeof(p));
+    const int gpl = Cout / 8;
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)N * gpl};
+        const cuuint64_t strides[2] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
+        const cuuint32_t box[3] = {(cuuint32_t)TC_TW * 8, (cuuint32_t)TC_ROWS, 8};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&p.tmap_g, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(g_c8), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("conv wgrad: cuTensorMapEncodeTiled failed (%d)", (int)r); return RVSR_E_CUDA; }
+    }
+    p.x = reinterpret_cast<const uint4 *>(x_c8); p.x_image_stride = x_image_stride / 8; p.g_planes = gpl;
+    p.dw = dw; p.db = db; p.Cout = Cout; p.N = N; p.H = H; p.W = W;
+    p.tiles_x = cdiv(W, TC_TW); p.tiles_y = cdiv(H, TC_ROWS); p.num_tiles = p.tiles_x * p.tiles_y * N;
+    p.td.tpi = (uint32_t)(p.tiles_x * p.tiles_y); p.td.m_tpi = magic_div(p.td.tpi, (uint32_t)p.num_tiles);
+    p.td.tx = (uint32_t)p.tiles_x; p.td.m_tx = magic_div(p.td.tx, p.td.tpi);
+    const int passes = cdiv(Cout, 64);
+    const size_t smem = (size_t)WG_STAGES * WG_STAGE + 8 * 16 + 1024;
+    RVSR_TRY(ensure_max_dynamic_smem(reinterpret_cast<const void *>(&conv_wgrad_tc_kernel), (int)smem));
+    // every CTA ends with a 36 864-float atomic flush: few tiles -> fewer CTAs
+    int gx = p.num_tiles / 6;
+    const int cap = sm_count() / passes > 0 ? sm_count() / passes : 1;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    conv_wgrad_tc_kernel<<<dim3(gx, passes), WG_THREADS, smem, s>>>(p);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+
+int launch_act_bwd_c8(const void *g, const void *y, void *out, long long n_elems, int act, cudaStream_t s) {
+    RVSR_CHECK_ARG(n_elems % 8 == 0, "act bwd: element count");
+    RVSR_CHECK_ARG(act == RVSR_ACT_LRELU || act == RVSR_ACT_RELU, "act bwd: activation %d", act);
+    if (n_elems == 0) return RVSR_OK;
+    act_bwd_c8_kernel<<<ew_grid(n_elems / 8), 256, 0, s>>>((const uint4 *)g, (const uint4 *)y, (uint4 *)out, n_elems / 8,
+                                                           act == RVSR_ACT_LRELU ? 0.1f : 0.f);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+// g, y: [N][C/32][2H][2W][8] -> out: [N][C/8][H][W][8]; act = RVSR_ACT_NONE: pure pixel-unshuffle (y unused)
+int launch_unshuffle2_act_bwd_c8(const void *g, const void *y, void *out, int N, int C, int H, int W, int act, cudaStream_t s) {
+    RVSR_CHECK_ARG(C % 32 == 0, "unshuffle: C %d is not a multiple of 32", C);
+    const long long total = (long long)N * (C / 8) * H * W;
+    if (total == 0) return RVSR_OK;
+    unshuffle2_act_bwd_kernel<<<ew_grid(total), 256, 0, s>>>((const __nv_bfloat16 *)g, (const __nv_bfloat16 *)y, (uint4 *)out, C / 8, H, W,
+                                                            total, act == RVSR_ACT_LRELU ? 0.1f : 0.f, act != RVSR_ACT_NONE);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+int launch_upsample2x_c8(const void *src, void *dst, long long planes, int H, int W, float scale, int backward, cudaStream_t s) {
+    if (planes == 0 || H == 0 || W == 0) return RVSR_OK;
+    if (!backward) {
+        const long long total = planes * 4 * H * W;
+        upsample2x_c8_kernel<<<ew_grid(total), 256, 0, s>>>((const uint4 *)src, (uint4 *)dst, H, W, total, scale);
+    } else {  // src: gradient of the [2H][2W] output, dst: gradient of the [H][W] input
+        const long long total = planes * H * W;
+        upsample2x_bwd_c8_kernel<<<ew_grid(total), 256, 0, s>>>((const uint4 *)src, (uint4 *)dst, H, W, total, scale);
+    }
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+int launch_nchw_to_c8_bf16(const void *src, int src_dtype, void *dst, int N, int C, int H, int W, int planes, cudaStream_t s) {
+    RVSR_CHECK_ARG(planes >= cdiv(C, 8), "nchw -> c8: %d channel blocks cannot hold %d channels", planes, C);
+    if (N == 0) return RVSR_OK;
+    const int HW = H * W;
+    RVSR_CHECK_ARG(N <= 65535 && cdiv(C, 8) <= 65535, "nchw -> c8: too many images / blocks");
+    const dim3 grid((HW + 255) / 256, cdiv(C, 8), N);
+    if (src_dtype == RVSR_BF16) nchw_to_c8_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16 *)src, (uint4 *)dst, C, HW, planes);
+    else if (src_dtype == RVSR_F32) nchw_to_c8_kernel<float><<<grid, 256, 0, s>>>((const float *)src, (uint4 *)dst, C, HW, planes);
+    else { set_error("nchw -> c8: dtype %d", src_dtype); return RVSR_E_INVALID; }
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+int launch_c8_to_nchw_bf16(const void *src, void *dst, int dst_dtype, int N, int C, int H, int W, int planes, cudaStream_t s) {
+    RVSR_CHECK_ARG(planes >= cdiv(C, 8), "c8 -> nchw: %d channel blocks do not hold %d channels", planes, C);
+    if (N == 0) return RVSR_OK;
+    const int HW = H * W;
+    RVSR_CHECK_ARG(N <= 65535 && cdiv(C, 8) <= 65535, "c8 -> nchw: too many images / blocks");
+    const dim3 grid((HW + 255) / 256, cdiv(C, 8), N);
+    if (dst_dtype == RVSR_BF16) c8_to_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const uint4 *)src, (__nv_bfloat16 *)dst, C, HW, planes);
+    else if (dst_dtype == RVSR_F32) c8_to_nchw_kernel<float><<<grid, 256, 0, s>>>((const uint4 *)src, (float *)dst, C, HW, planes);
+    else { set_error("c8 -> nchw: dtype %d", dst_dtype); return RVSR_E_INVALID; }
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+
+}  // namespace rvsr

@@ -1,0 +1,253 @@
+"""bf16 training path on channel-blocked ("C8") tensors: torch.autograd.Functions over the rvsr_c8_* C ABI.
+
+BASELINE cfg5 is a bf16 training step.  Under torch.autocast every nn.Conv2d of EDVR_arch.py runs on cuDNN, which
+spends more time converting NCHW <-> NHWC, reducing bias gradients and launching elementwise kernels than convolving
+(profiles/r02_cfg5_profile.txt).  Here activations stay in the inference engine's layout -- [N, C/8, H, W, 8] bfloat16,
+an ordinary 5-D torch tensor -- between layers, and each layer is one Function whose forward AND backward are this
+library's tcgen05 kernels:
+
+    forward        rvsr_c8_conv_fwd (bias, activation, residual add, torch.cat of the inputs, PixelShuffle(2) fused)
+    data gradient  the same kernel with the transposed, flipped weights (one launch per concatenated input)
+    weight + bias  rvsr_c8_conv_wgrad (pixel-K GEMM on tcgen05; fp32 accumulate over the whole batch)
+    activation     rvsr_c8_act_bwd / rvsr_c8_unshuffle2_act_bwd on the saved OUTPUT (no pre-activation is stored)
+
+torch.autograd still owns the graph: it sums the gradients of a tensor with several consumers and calls these
+backwards in order.  Parameters stay fp32 OIHW nn.Parameters (the reference's state_dict contract); they are re-packed
+into the kernels' operand layout on every call because an optimizer step changes them.  No CPU or cuDNN fallback inside
+a Function: an unsupported shape raises NotImplementedError (the caller, EDVR._forward_c8, only routes supported layers
+here).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+ACT = {None: _lib.ACT_NONE, "none": _lib.ACT_NONE, "lrelu": _lib.ACT_LRELU, "relu": _lib.ACT_RELU}
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def channels(t):
+    return t.shape[1] * 8
+
+
+def _check_c8(t, what):
+    if t.dim() != 5 or t.shape[-1] != 8 or t.dtype != torch.bfloat16 or not t.is_cuda:
+        raise RuntimeError("%s: expected a CUDA bfloat16 [N, C/8, H, W, 8] tensor, got %s %s" % (what, tuple(t.shape), t.dtype))
+    return t.contiguous()
+
+
+# ---------------------------------------------------------------- layout conversion
+def _to_c8_raw(x, planes=None):
+    if not x.is_cuda:
+        raise NotImplementedError("realvsr_b200.train_c8: CUDA tensors only (no CPU fallback)")
+    if x.dtype not in (torch.bfloat16, torch.float32):
+        x = x.float()
+    x = x.contiguous()
+    N, C, H, W = x.shape
+    planes = (C + 7) // 8 if planes is None else planes
+    y = torch.empty((N, planes, H, W, 8), dtype=torch.bfloat16, device=x.device)
+    if planes > (C + 7) // 8:
+        y[:, (C + 7) // 8:].zero_()
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().rvsr_c8_from_nchw(_p(x), _lib.BF16 if x.dtype == torch.bfloat16 else _lib.F32, _p(y), N, C, H, W,
+                                                planes, _stream(x.device)), "c8_from_nchw")
+    return y
+
+
+def _from_c8_raw(x, C, dtype):
+    N, planes, H, W, _ = x.shape
+    y = torch.empty((N, C, H, W), dtype=dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().rvsr_c8_to_nchw(_p(x), _p(y), _lib.BF16 if dtype == torch.bfloat16 else _lib.F32, N, C, H, W,
+                                              planes, _stream(x.device)), "c8_to_nchw")
+    return y
+
+
+class _ToC8(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.meta = (x.shape[1], x.dtype)
+        return _to_c8_raw(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        C, dtype = ctx.meta
+        return _from_c8_raw(_check_c8(g, "to_c8 backward"), C, dtype)
+
+
+class _FromC8(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, C, dtype):
+        x = _check_c8(x, "from_c8")
+        ctx.planes = x.shape[1]
+        return _from_c8_raw(x, C, dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _to_c8_raw(g, ctx.planes), None, None  # channels beyond C (padding, or planes the caller dropped) get zero gradient
+
+
+def to_c8(x):
+    """NCHW (bf16 / fp32) -> [N, ceil(C/8), H, W, 8] bf16."""
+    return _ToC8.apply(x)
+
+
+def from_c8(x, C=None, dtype=torch.bfloat16):
+    """[N, C/8, H, W, 8] bf16 -> NCHW `dtype` (the first C channels)."""
+    return _FromC8.apply(x, channels(x) if C is None else C, dtype)
+
+
+# ---------------------------------------------------------------- convolution
+def _pack_weight(weight, Cout, Cin, ks, shuffle, mode, cin_total, c0):
+    L = _lib.lib()
+    nbytes = L.rvsr_c8_conv_weight_bytes(Cout, Cin, ks, int(shuffle))
+    if nbytes == 0:
+        raise NotImplementedError("train_c8: convolution %d <- %d (k=%d) is not covered by the tcgen05 kernels" % (Cout, Cin, ks))
+    dst = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
+    _lib.check(L.rvsr_c8_conv_pack_weight(_p(weight), _p(dst), Cout, Cin, ks, int(shuffle), mode, cin_total, c0,
+                                          _stream(weight.device)), "c8_conv_pack_weight")
+    return dst
+
+
+def _conv_launch(xs, w_packed, bias, residual, N, H, W, C, Cout, ks, act, shuffle):
+    dev = xs[0].device
+    n = len(xs)
+    ptrs = (ctypes.c_void_p * n)(*[x.data_ptr() for x in xs])
+    strides = (ctypes.c_longlong * n)(*[x.stride(0) for x in xs])
+    if shuffle:
+        y = torch.empty((N, Cout // 32, 2 * H, 2 * W, 8), dtype=torch.bfloat16, device=dev)
+    else:
+        y = torch.empty((N, (Cout + 7) // 8, H, W, 8), dtype=torch.bfloat16, device=dev)
+    _lib.check(_lib.lib().rvsr_c8_conv_fwd(ptrs, strides, n, C, _p(w_packed), _p(bias), _p(residual), _p(y), N, H, W, Cout, ks, 1,
+                                           act, int(shuffle), _stream(dev)), "c8_conv_fwd")
+    return y
+
+
+def _src_ok(x):
+    """A source may be a channel slice [:, a:b] of a contiguous C8 tensor (image stride > its own size)."""
+    s = x.stride()
+    H, W = x.shape[2], x.shape[3]
+    return s[4] == 1 and s[3] == 8 and s[2] == 8 * W and s[1] == 8 * W * H
+
+
+class _ConvC8(torch.autograd.Function):
+    """y = [PixelShuffle2](act(conv(cat(xs), weight) + bias)) [+ residual]; stride 1, pad ks // 2."""
+
+    @staticmethod
+    def forward(ctx, weight, bias, residual, act, shuffle, *xs):
+        xs = [x if _src_ok(x) else x.contiguous() for x in xs]
+        for x in xs:
+            if x.dim() != 5 or x.dtype != torch.bfloat16 or not x.is_cuda:
+                raise RuntimeError("conv_c8: sources must be CUDA bfloat16 [N, C/8, H, W, 8] tensors")
+        N, C8, H, W, _ = xs[0].shape
+        C = C8 * 8
+        Cout, Cin, ks, _ = weight.shape
+        if Cin != C * len(xs) or any(tuple(x.shape) != tuple(xs[0].shape) for x in xs):
+            raise RuntimeError("conv_c8: weight expects %d input channels, sources give %d x %d" % (Cin, len(xs), C))
+        if weight.dtype != torch.float32 or (bias is not None and bias.dtype != torch.float32):
+            raise RuntimeError("conv_c8: parameters must be fp32 (the reference's state_dict dtype)")
+        weight = weight.contiguous()
+        if residual is not None:
+            residual = _check_c8(residual, "conv_c8 residual")
+        with torch.cuda.device(weight.device):
+            wp = _pack_weight(weight, Cout, Cin, ks, shuffle, 0, Cin, 0)
+            y = _conv_launch(xs, wp, bias, residual, N, H, W, C, Cout, ks, act, shuffle)
+        ctx.meta = (act, shuffle, N, H, W, C, Cout, ks, len(xs), residual is not None)
+        needs = ctx.needs_input_grad
+        ctx.saved_x = bool(needs[0] or needs[1])
+        ctx.save_for_backward(weight, *(xs if ctx.saved_x else []), *([y] if act != _lib.ACT_NONE else []))
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        act, shuffle, N, H, W, C, Cout, ks, nsrc, has_res = ctx.meta
+        saved = ctx.saved_tensors
+        weight = saved[0]
+        xs = saved[1:1 + nsrc] if ctx.saved_x else None
+        y = saved[-1] if act != _lib.ACT_NONE else None
+        L = _lib.lib()
+        dev = weight.device
+        g = _check_c8(g, "conv_c8 backward")
+        needs = ctx.needs_input_grad
+        with torch.cuda.device(dev):
+            s = _stream(dev)
+            g_res = g if has_res and needs[2] else None  # the residual joins after the activation: its gradient is g itself
+            if has_res and act != _lib.ACT_NONE:
+                raise RuntimeError("conv_c8: residual with an activation is not a layer of this network")
+            if shuffle:  # g, y are in the shuffled geometry [N, Cout/4 ch, 2H, 2W] -> gradient of the conv output
+                gp = torch.empty((N, Cout // 8, H, W, 8), dtype=torch.bfloat16, device=dev)
+                _lib.check(L.rvsr_c8_unshuffle2_act_bwd(_p(g), _p(y), _p(gp), N, Cout, H, W, act, s), "c8_unshuffle2_act_bwd")
+            elif act != _lib.ACT_NONE:
+                gp = torch.empty_like(g)
+                _lib.check(L.rvsr_c8_act_bwd(_p(g), _p(y), _p(gp), g.numel(), act, s), "c8_act_bwd")
+            else:
+                gp = g
+            gw = gb = None
+            if needs[0] or needs[1]:
+                if ks != 3 or C != 64:
+                    raise NotImplementedError("conv_c8: the weight gradient is built for 3x3 convolutions of 64-channel sources")
+                gb = torch.zeros(Cout, dtype=torch.float32, device=dev) if needs[1] else None
+                parts = []
+                for x in xs:
+                    dwt = torch.zeros((9, 64, Cout), dtype=torch.float32, device=dev)
+                    _lib.check(L.rvsr_c8_conv_wgrad(_p(x), x.stride(0), _p(gp), _p(dwt), _p(gb if x is xs[0] else None), N, H, W, C,
+                                                    Cout, ks, s), "c8_conv_wgrad")
+                    parts.append(dwt.permute(2, 1, 0))  # [Cout, 64, 9]
+                gw = (parts[0] if nsrc == 1 else torch.cat(parts, 1)).reshape(Cout, nsrc * C, 3, 3)
+                if not needs[0]:
+                    gw = None
+            gxs = [None] * nsrc
+            if any(needs[5:5 + nsrc]):
+                # dX_i = conv(dY, W[:, slice_i]^T flipped): Cout gradient channels enter as 64-channel sources
+                if Cout % 64 != 0:
+                    raise NotImplementedError("conv_c8: the data gradient needs Cout %% 64 == 0 (got %d)" % Cout)
+                gsrc = [gp[:, 8 * k:8 * k + 8] for k in range(Cout // 64)]
+                for i in range(nsrc):
+                    if not needs[5 + i]:
+                        continue
+                    wp = _pack_weight(weight, C, Cout, ks, False, 1, nsrc * C, i * C)
+                    gxs[i] = _conv_launch(gsrc, wp, None, None, N, H, W, 64, C, ks, _lib.ACT_NONE, False)
+        return (gw, gb, g_res, None, None, *gxs)
+
+
+def conv(xs, weight, bias=None, act=None, residual=None, shuffle=False):
+    """One nn.Conv2d site (3x3 / 1x1, stride 1) on C8 tensors; `xs` is a tensor or the list torch.cat would have joined."""
+    if isinstance(xs, torch.Tensor):
+        xs = [xs]
+    return _ConvC8.apply(weight, bias, residual, ACT[act], bool(shuffle), *xs)
+
+
+# ---------------------------------------------------------------- x2 bilinear upsample (optionally scaled)
+class _Up2C8(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, scale):
+        x = _check_c8(x, "upsample2x_c8")
+        N, P, H, W, _ = x.shape
+        ctx.scale = float(scale)
+        y = torch.empty((N, P, 2 * H, 2 * W, 8), dtype=torch.bfloat16, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().rvsr_c8_upsample2x(_p(x), _p(y), N * P, H, W, ctx.scale, 0, _stream(x.device)), "c8_upsample2x")
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _check_c8(g, "upsample2x_c8 backward")
+        N, P, H2, W2, _ = g.shape
+        gx = torch.empty((N, P, H2 // 2, W2 // 2, 8), dtype=torch.bfloat16, device=g.device)
+        with torch.cuda.device(g.device):
+            _lib.check(_lib.lib().rvsr_c8_upsample2x(_p(g), _p(gx), N * P, H2 // 2, W2 // 2, ctx.scale, 1, _stream(g.device)),
+                       "c8_upsample2x (adjoint)")
+        return gx, None
+
+
+def upsample2x(x, scale=1.0):
+    """scale * F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=False) on a C8 tensor."""
+    return _Up2C8.apply(x, scale)

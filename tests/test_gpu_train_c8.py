@@ -1,0 +1,169 @@
+"""bf16 training path (realvsr_b200/train_c8.py) against torch autograd in fp32 on the same bf16-rounded operands.
+
+Reference semantics: nn.Conv2d autograd (EDVR_arch.py:71-91, :229-253, arch_util.py:121-139), F.interpolate x2 bilinear
+(:109-121), PixelShuffle(2) + lrelu (:313-314).  Tolerances: outputs and data gradients are stored in bf16 (8 mantissa
+bits): max |err| <= 1e-2 of the tensor's max magnitude.  Weight / bias gradients are fp32 sums of bf16 products:
+<= 3e-3 of the max magnitude.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _r(t):  # round to bf16, keep fp32
+    return t.to(torch.bfloat16).float()
+
+
+def _rel(a, b):
+    return float((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-20))
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def test_layout_roundtrip_and_gradient():
+    from realvsr_b200 import train_c8 as T
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(3, 19, 7, 11, device="cuda", generator=g, requires_grad=True)
+    c = T.to_c8(x)
+    assert tuple(c.shape) == (3, 3, 7, 11, 8) and c.dtype == torch.bfloat16
+    assert float(c.detach()[:, 2, :, :, 3:].abs().max()) == 0.0  # channels 19..23 are zero padding
+    y = T.from_c8(c, 19, torch.float32)
+    assert torch.equal(y, _r(x.detach()))
+    w = torch.randn_like(y)
+    (y * w).sum().backward()
+    assert torch.equal(x.grad, _r(w))
+
+
+@pytest.mark.parametrize("case", ["lrelu", "relu", "none_residual", "cat2", "shuffle", "shuffle_none"])
+@pytest.mark.parametrize("shape", [(2, 16, 32), (3, 18, 40), (1, 64, 64)])
+def test_conv_forward_backward(case, shape):
+    from realvsr_b200 import train_c8 as T
+    N, H, W = shape
+    g = torch.Generator(device="cuda").manual_seed(len(case) * 131 + N * 17 + H)
+    nsrc = 2 if case == "cat2" else 1
+    Cout = 256 if case.startswith("shuffle") else 64
+    act = {"lrelu": "lrelu", "relu": "relu", "none_residual": None, "cat2": "lrelu", "shuffle": "lrelu", "shuffle_none": None}[case]
+    xs = [_r(torch.randn(N, 64, H, W, device="cuda", generator=g)).requires_grad_() for _ in range(nsrc)]
+    w = _r(torch.randn(Cout, 64 * nsrc, 3, 3, device="cuda", generator=g) * 0.05).requires_grad_()  # a bf16-exact leaf: no cast in the graph
+    b = (torch.randn(Cout, device="cuda", generator=g) * 0.1).requires_grad_()
+    res = _r(torch.randn(N, 64, H, W, device="cuda", generator=g)).requires_grad_() if case == "none_residual" else None
+    # product
+    xs2 = [x.detach().clone().requires_grad_() for x in xs]
+    w2, b2 = w.detach().clone().requires_grad_(), b.detach().clone().requires_grad_()
+    res2 = res.detach().clone().requires_grad_() if res is not None else None
+    y = T.conv([T.to_c8(x) for x in xs2], w2, b2, act=act, residual=None if res2 is None else T.to_c8(res2),
+               shuffle=case.startswith("shuffle"))
+    Cy = Cout // 4 if case.startswith("shuffle") else Cout
+    y_nchw = T.from_c8(y, Cy, torch.float32)
+    # reference: fp32 math on the same bf16-exact operands.  The branch of the activation is taken from the PRODUCT's output
+    # sign: two fp32 summation orders disagree on it for the ~1e-6 of outputs whose pre-activation is ~1e-7 (forward
+    # difference 1e-7, but a different gradient at that element), which is no property of either implementation.
+    pre = F.conv2d(torch.cat(xs, 1), w, b, padding=1)
+    pos = (F.pixel_unshuffle(y_nchw.detach(), 2) if case.startswith("shuffle") else y_nchw.detach()) > 0
+    assert act is None or int((pos != (pre.detach() > 0)).sum()) <= 4
+    if act == "lrelu":
+        y_ref = pre * torch.where(pos, 1.0, 0.1)
+    elif act == "relu":
+        y_ref = pre * pos
+    else:
+        y_ref = pre
+    if res is not None:
+        y_ref = y_ref + res
+    if case.startswith("shuffle"):
+        y_ref = F.pixel_shuffle(y_ref, 2)
+    gy = _r(torch.randn(y_ref.shape, device="cuda", generator=g))
+    leaves = xs + [w, b] + ([res] if res is not None else [])
+    ref_grads = torch.autograd.grad(y_ref, leaves, gy)
+    assert y_nchw.shape == y_ref.shape
+    assert _rel(y_nchw, y_ref.detach()) < 1e-2
+    leaves2 = xs2 + [w2, b2] + ([res2] if res2 is not None else [])
+    grads = torch.autograd.grad(y_nchw, leaves2, gy)
+    names = ["dx%d" % i for i in range(nsrc)] + ["dw", "db"] + (["dres"] if res is not None else [])
+    for name, a, r in zip(names, grads, ref_grads):
+        tol = 3e-3 if name in ("dw", "db") else 1e-2
+        assert a.shape == r.shape, name
+        assert _rel(a, r) < tol, (name, _rel(a, r))
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 5, 7), (3, 16, 16, 16)])
+def test_upsample2x(shape):
+    from realvsr_b200 import train_c8 as T
+    N, C, H, W = shape
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = _r(torch.randn(N, C, H, W, device="cuda", generator=g)).requires_grad_()
+    y_ref = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False) * 2
+    gy = _r(torch.randn(y_ref.shape, device="cuda", generator=g))
+    (gx_ref,) = torch.autograd.grad(y_ref, [x], gy)
+    x2 = x.detach().clone().requires_grad_()
+    y = T.from_c8(T.upsample2x(T.to_c8(x2), 2.0), C, torch.float32)
+    assert _rel(y, y_ref) < 1e-2
+    (gx,) = torch.autograd.grad(y, [x2], gy)
+    assert _rel(gx, gx_ref) < 1e-2
+
+
+def test_network_gradients_c8_path_vs_fp32_and_vs_autocast():
+    """EDVR nf = 64 on a small crop, one training step three ways: fp32 module path (cuDNN TF32 off; its gradients are pinned to
+    the float64 oracle by tests/test_gpu_dcn.py), torch.autocast(bfloat16) on the module path (cuDNN convolutions), and the
+    train_c8 path (this library's convolution kernels).  bf16 storage puts ~1e-2 of noise on every activation, so the check is
+    directional, for EVERY parameter: cosine with the fp32 gradient > 0.95 and not worse than autocast's by more than 0.03,
+    norm within 10 %."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from helpers import load_case
+    from synth import synth_normal
+    from realvsr_b200.archs import EDVR_arch as E
+    c = load_case("edvr_nf64_crop")
+    net = E.EDVR(**c["kwargs"]).train()
+    net.load_state_dict(c["sd"], strict=True)
+    net = net.to("cuda")
+    x = torch.cat([c["x"], c["x"].flip(3)], 0).to("cuda")
+    gt = synth_normal((2,) + tuple(c["out"].shape[1:]), 55, std=0.3).to("cuda") + 0.5
+
+    def grads(path, amp):
+        net.exec_path = path
+        net.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+            loss = F.l1_loss(net(x).float(), gt)
+        loss.backward()
+        return float(loss.detach()), {n: p.grad.detach().float().clone() for n, p in net.named_parameters()}
+
+    l32, g32 = grads("module", False)
+    lac, gac = grads("module", True)
+    lc8, gc8 = grads("train_c8", False)
+    assert abs(lc8 - l32) < 2e-2 * l32 and abs(lc8 - lac) < 2e-2 * l32
+    worst = (1.0, "", 1.0)
+    for n in g32:
+        a, b, r = gc8[n].flatten(), gac[n].flatten(), g32[n].flatten()
+        cos = lambda u, v: float(torch.dot(u, v) / (u.norm() * v.norm()).clamp_min(1e-30))  # noqa: E731
+        c8, ac = cos(a, r), cos(b, r)
+        if c8 < worst[0]:
+            worst = (c8, n, ac)
+        assert c8 > 0.95 and c8 > ac - 0.03, (n, c8, ac)
+        assert 0.9 < float(a.norm() / r.norm().clamp_min(1e-30)) < 1.1, n
+    print("train_c8 vs fp32 gradients: worst cosine %.4f (%s; torch autocast there: %.4f)" % worst)
+
+
+def test_layout_with_spare_channel_blocks():
+    """from_c8 of the first C channels of a wider tensor (the 216 offset / mask channels of a 256-channel convolution output)
+    and its gradient (zeros in the dropped blocks), batch > 1."""
+    from realvsr_b200 import train_c8 as T
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = _r(torch.randn(3, 32, 6, 10, device="cuda", generator=g))
+    c = T.to_c8(x).requires_grad_()
+    y = T.from_c8(c, 20, torch.float32)
+    assert torch.equal(y, x[:, :20])
+    w = _r(torch.randn_like(y))
+    (y * w).sum().backward()
+    back = T.from_c8(c.grad, 32, torch.float32)
+    assert torch.equal(back[:, :20], w) and float(back[:, 20:].abs().max()) == 0.0

@@ -24,8 +24,13 @@ def step():
     loss.backward()
 for _ in range(3): step()
 torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(5): step()
+e1.record(); torch.cuda.synchronize()
+print('cfg5 step: %.2f ms (AMP=%s, RVSR_TRAIN_C8=%s, CL=%s)' % (e0.elapsed_time(e1) / 5, os.environ.get('AMP', '0'), os.environ.get('RVSR_TRAIN_C8', '1'), os.environ.get('CL', '0')))
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     for _ in range(3): step()
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=18, max_name_column_width=70))
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=int(os.environ.get('ROWS', '18')), max_name_column_width=70))

@@ -1,0 +1,29 @@
+"""conv_wgrad_tc_kernel / bf16 conv timing per launch (CUDA events, 20 launches) over image counts and sizes."""
+import ctypes, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from realvsr_b200 import _lib, train_c8 as T
+L = _lib.lib()
+dev = "cuda:0"
+def timeit(fn, n=20):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e3
+s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+for (N, H, W, Cout) in [(80, 64, 64, 64), (40, 64, 64, 64), (16, 64, 64, 64), (4, 64, 64, 64), (80, 32, 32, 64), (80, 16, 16, 64),
+                        (16, 256, 256, 64), (16, 128, 128, 256), (80, 64, 64, 256)]:
+    x = torch.randn(N, 8, H, W, 8, device=dev).bfloat16()
+    g = torch.randn(N, Cout // 8, H, W, 8, device=dev).bfloat16()
+    dw = torch.zeros(9, 64, Cout, device=dev)
+    db = torch.zeros(Cout, device=dev)
+    w = torch.randn(Cout, 64, 3, 3, device=dev) * 0.05
+    t_w = timeit(lambda: _lib.check(L.rvsr_c8_conv_wgrad(x.data_ptr(), x.stride(0), g.data_ptr(), dw.data_ptr(), db.data_ptr(), N, H, W, 64, Cout, 3, s)))
+    wp = T._pack_weight(w, Cout, 64, 3, False, 0, 64, 0)
+    t_f = timeit(lambda: T._conv_launch([x], wp, None, None, N, H, W, 64, Cout, 3, 1, False))
+    fl = 2.0 * N * H * W * 64 * Cout * 9
+    print("N=%3d %3dx%3d Cout=%3d: wgrad %7.1f us (%5.2f PFLOP/s)   fwd conv %7.1f us (%5.2f PFLOP/s)" % (N, H, W, Cout, t_w, fl / t_w * 1e-9, t_f, fl / t_f * 1e-9))
