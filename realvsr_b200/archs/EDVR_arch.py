@@ -323,10 +323,10 @@ class _EDVRBase(nn.Module):
         return want and ok
 
     def _forward_c8(self, x):
-        """Same graph as _forward_modules.  Stride-1 3x3 convolutions (117 of the 132 conv sites), residual adds, torch.cat,
-        the x2 upsamples and PixelShuffle + lrelu run as train_c8 Functions on [N, C/8, H, W, 8] bf16 tensors; the rest
-        (3-channel first / last convolution, the two stride-2 convolutions, the DCN operator, TSA's 1x1 convolutions / pools)
-        stays on NCHW bf16 tensors under autocast, with a layout conversion at each boundary."""
+        """Same graph as _forward_modules.  Every 64-channel convolution (3x3 and 1x1; stride 2 as stride 1 + subsampling), the
+        residual adds, torch.cat, the x2 upsamples and PixelShuffle + lrelu run as train_c8 Functions on [N, C/8, H, W, 8] bf16
+        tensors; TSA's pools / sigmoids / products are torch ops on the same tensors.  Only the two 3-channel convolutions
+        (conv_first, conv_last) and the DCN operator work on NCHW bf16 tensors, with a layout conversion at the boundary."""
         from .. import train_c8 as T
         B, N, C, H, W = x.size()
         bf = torch.bfloat16
@@ -352,12 +352,38 @@ class _EDVRBase(nn.Module):
                         pack.stride, pack.padding, pack.dilation, pack.groups, pack.deformable_groups)
             return T.to_c8(F.leaky_relu(y, 0.1) if act else y)
 
+        def down2(m, t):
+            # stride-2 3x3 convolution = the stride-1 convolution at the even pixels (pad 1 both ways): 4x the MMAs of two small
+            # layers instead of two layout round trips through cuDNN
+            return conv(m, t, "lrelu")[:, :, ::2, ::2].contiguous()
+
+        def tsa(m, aligned):
+            # TSA_Fusion.forward (EDVR_arch.py:168-208) on C8 tensors: convolutions as above, the rest elementwise torch ops
+            # (a C8 tensor is an ordinary 5-D tensor: channel = 8 * dim 1 + dim 4)
+            a6 = aligned.view(B, N, *aligned.shape[1:])                                   # [B, N, 8, H, W, 8]
+            emb_ref = conv(m.tAtt_2, a6[:, self.center].contiguous())                     # [B, 8, H, W, 8]
+            emb = conv(m.tAtt_1, aligned).view(B, N, *aligned.shape[1:])
+            prob = torch.sigmoid((emb.float() * emb_ref.float().unsqueeze(1)).sum((2, 5)))  # [B, N, H, W]
+            weighted = (a6 * prob.to(bf).unsqueeze(2).unsqueeze(-1))
+            srcs = [weighted[:, i].contiguous() for i in range(N)]                        # the N x 64 channels of the 1x1 fusions
+            fea = conv(m.fea_fusion, srcs, "lrelu")
+            att = conv(m.sAtt_1, srcs, "lrelu")
+            pool = lambda t: (F.max_pool3d(t, (3, 3, 1), (2, 2, 1), (1, 1, 0)), F.avg_pool3d(t, (3, 3, 1), (2, 2, 1), (1, 1, 0)))  # noqa: E731
+            att = conv(m.sAtt_2, list(pool(att)), "lrelu")
+            att_l = conv(m.sAtt_L1, att, "lrelu")
+            att_l = conv(m.sAtt_L2, list(pool(att_l)), "lrelu")
+            att_l = T.upsample2x(conv(m.sAtt_L3, att_l, "lrelu"))
+            att = conv(m.sAtt_3, att, "lrelu") + att_l
+            att = conv(m.sAtt_5, T.upsample2x(conv(m.sAtt_4, att, "lrelu")))
+            att_add = conv(m.sAtt_add_2, conv(m.sAtt_add_1, att, "lrelu"))
+            return fea * torch.sigmoid(att) * 2 + att_add
+
         with torch.autocast("cuda", dtype=bf):
             x_center = x[:, self.center].contiguous()
             frames = x.reshape(-1, C, H, W)
             l1 = trunk(self.feature_extraction, T.to_c8(F.leaky_relu(self.conv_first(frames), 0.1)))
-            l2 = conv(self.fea_L2_conv2, T.to_c8(F.leaky_relu(self.fea_L2_conv1(nchw(l1)), 0.1)), "lrelu")
-            l3 = conv(self.fea_L3_conv2, T.to_c8(F.leaky_relu(self.fea_L3_conv1(nchw(l2)), 0.1)), "lrelu")
+            l2 = conv(self.fea_L2_conv2, down2(self.fea_L2_conv1, l1), "lrelu")
+            l3 = conv(self.fea_L3_conv2, down2(self.fea_L3_conv1, l2), "lrelu")
             pyr = [l1, l2, l3]
             ref = [lv.view(B, N, *lv.shape[1:])[:, self.center:self.center + 1].expand(B, N, *lv.shape[1:]).reshape(lv.shape)
                    for lv in pyr]
@@ -371,9 +397,13 @@ class _EDVRBase(nn.Module):
             off1 = conv(p.L1_offset_conv3, conv(p.L1_offset_conv2, [off1, T.upsample2x(off2, 2.0)], "lrelu"), "lrelu")
             fea1 = conv(p.L1_fea_conv, [dcn(p.L1_dcnpack, pyr[0], off1), T.upsample2x(fea2)])
             offc = conv(p.cas_offset_conv2, conv(p.cas_offset_conv1, [fea1, ref[0]], "lrelu"), "lrelu")
-            aligned = nchw(dcn(p.cas_dcnpack, fea1, offc, act=True)).view(B, N, -1, H, W)
-            fea = self.tsa_fusion(aligned if self.w_TSA else aligned.view(B, -1, H, W))
-            out = trunk(self.recon_trunk, T.to_c8(fea))
+            aligned = dcn(p.cas_dcnpack, fea1, offc, act=True)
+            if self.w_TSA:
+                fea = tsa(self.tsa_fusion, aligned)
+            else:
+                a6 = aligned.view(B, N, *aligned.shape[1:])
+                fea = conv(self.tsa_fusion, [a6[:, i].contiguous() for i in range(N)])
+            out = trunk(self.recon_trunk, fea)
             if self._upsample:
                 out = conv(self.upconv1, out, "lrelu", shuffle=True)   # lrelu(PixelShuffle(conv)) == PixelShuffle(lrelu(conv))
                 out = conv(self.upconv2, out, "lrelu", shuffle=True)

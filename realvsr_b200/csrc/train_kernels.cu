@@ -51,6 +51,8 @@ struct alignas(64) WgradParams {
     int Cout, N, H, W;
     int tiles_x, tiles_y, num_tiles;
     TileDiv td;
+    int ks;     // 3, or 1: only the centre tap (rows 64-127 of accumulator 1) is a weight
+    int debug;  // RVSR_WG_DEBUG, timing experiments only (results become garbage): 1 = issue no MMAs, 2 = no halo loads / stores
 };
 
 __device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, float d) {
@@ -89,39 +91,59 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
     const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
     if (warp < WG_PROD_WARPS) {
-        // ---- x halo producers: rows -1 .. 5 of the tile, 34 columns from -1, all 8 channel blocks; rows 0 .. 4 go to both copies
+        // ---- x halo producers: rows -1 .. 5 of the tile, 34 columns from -1, all 8 channel blocks; rows 0 .. 4 go to both copies.
+        // The loads of tile t + 1 are in flight while tile t is written to shared memory (two register sets).
         const long long plane = (long long)p.H * p.W;
-        for (int t = 0; t < T; ++t) {
-            const int tile = blockIdx.x + t * gridDim.x, st = t % WG_STAGES;
+        int cell[WG_PER_THREAD];  // this thread's cells of the halo: (block, row, column) -> offsets, fixed for the whole kernel
+        int off_a[WG_PER_THREAD], off_b[WG_PER_THREAD], rowi[WG_PER_THREAD], coli[WG_PER_THREAD];
+#pragma unroll
+        for (int i = 0; i < WG_PER_THREAD; ++i) {
+            const int idx = (int)threadIdx.x + i * 32 * WG_PROD_WARPS;
+            const int pl = idx / ((WG_XROWS + 1) * WG_XCOLS), rem = idx - pl * ((WG_XROWS + 1) * WG_XCOLS);
+            const int row = rem / WG_XCOLS, col = rem - row * WG_XCOLS;
+            cell[i] = idx < WG_HALO_ELEMS ? pl : -1;
+            rowi[i] = row; coli[i] = col;
+            off_a[i] = row < WG_XROWS ? (pl * WG_XROWS + row) * WG_XCOLS + col : -1;
+            off_b[i] = row >= 1 ? ((8 + pl) * WG_XROWS + row - 1) * WG_XCOLS + col : -1;
+        }
+        auto load_tile = [&](int t, uint4 (&v)[WG_PER_THREAD]) {
+            const int tile = blockIdx.x + t * gridDim.x;
             int tx, ty, n;
             tile_coords(p.td, tile, tx, ty, n);
             const int y0 = ty * TC_ROWS - 1, x0 = tx * TC_TW - 1;
             const uint4 *src = p.x + (long long)n * p.x_image_stride;
-            uint4 v[WG_PER_THREAD];
 #pragma unroll
             for (int i = 0; i < WG_PER_THREAD; ++i) {
-                const int idx = (int)threadIdx.x + i * 32 * WG_PROD_WARPS;
-                const int pl = idx / ((WG_XROWS + 1) * WG_XCOLS), rem = idx - pl * ((WG_XROWS + 1) * WG_XCOLS);
-                const int row = rem / WG_XCOLS, col = rem - row * WG_XCOLS;
-                const int gy = y0 + row, gx = x0 + col;
+                const int gy = y0 + rowi[i], gx = x0 + coli[i];
                 v[i] = make_uint4(0, 0, 0, 0);
-                if (idx < WG_HALO_ELEMS && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) v[i] = __ldg(src + pl * plane + (long long)gy * p.W + gx);
+                if (cell[i] >= 0 && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W && !(p.debug & 2))
+                    v[i] = __ldg(src + cell[i] * plane + (long long)gy * p.W + gx);
             }
+        };
+        auto store_tile = [&](int t, const uint4 (&v)[WG_PER_THREAD]) {
+            const int st = t % WG_STAGES;
             mbar_wait(BAR(B_EMPTY + st), ((t / WG_STAGES) & 1) ^ 1);
             uint4 *xa = reinterpret_cast<uint4 *>(stage_s + st * WG_STAGE + WG_G_BYTES);
 #pragma unroll
             for (int i = 0; i < WG_PER_THREAD; ++i) {
-                const int idx = (int)threadIdx.x + i * 32 * WG_PROD_WARPS;
-                const int pl = idx / ((WG_XROWS + 1) * WG_XCOLS), rem = idx - pl * ((WG_XROWS + 1) * WG_XCOLS);
-                const int row = rem / WG_XCOLS, col = rem - row * WG_XCOLS;
-                if (idx < WG_HALO_ELEMS) {
-                    if (row < WG_XROWS) xa[(pl * WG_XROWS + row) * WG_XCOLS + col] = v[i];
-                    if (row >= 1) xa[((8 + pl) * WG_XROWS + row - 1) * WG_XCOLS + col] = v[i];
+                if (cell[i] >= 0 && !(p.debug & 2)) {
+                    if (off_a[i] >= 0) xa[off_a[i]] = v[i];
+                    if (off_b[i] >= 0) xa[off_b[i]] = v[i];
                 }
             }
             fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(B_FULL + st));
+        };
+        uint4 va[WG_PER_THREAD], vb[WG_PER_THREAD];
+        if (T > 0) load_tile(0, va);
+        for (int t = 0; t < T; t += 2) {
+            if (t + 1 < T) load_tile(t + 1, vb);
+            store_tile(t, va);
+            if (t + 1 < T) {
+                if (t + 2 < T) load_tile(t + 2, va);
+                store_tile(t + 1, vb);
+            }
         }
         // ---- flush: D row m = (tap half, ci), column = co.  Warps 0-7: TMEM lane quarter warp & 3, column half warp >> 2.
         if (T > 0) {
@@ -133,13 +155,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
 #pragma unroll 1
             for (int b = 0; b < 6; ++b) {
                 if (b >= 3 && q >= 2) break;  // rows 64-127 of the dy = +1 accumulators are not weights
-                const int tap = b < 3 ? uphalf * 3 + b : 6 + (b - 3);
+                if (p.ks == 1 && (b != 1 || q < 2)) continue;  // 1x1: the centre tap only
+                const int tap = p.ks == 1 ? 0 : (b < 3 ? uphalf * 3 + b : 6 + (b - 3));
                 uint32_t a0[16], a1[16];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 64 + hf * 32);
                 tmem_ld16_nowait(taddr, a0);
                 tmem_ld16_nowait(taddr + 16, a1);
                 tmem_ld_wait();
-                float *d = p.dw + ((long long)tap * 64 + ci) * p.Cout + co0;
+                float *d = p.dw + ((long long)tap * 64 + ci) * p.Cout + co0;  // [taps][64][Cout]
 #pragma unroll
                 for (int j = 0; j < 16; j += 4) {
                     if (co0 + j < p.Cout)
@@ -176,6 +199,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
                         const uint64_t bdesc = make_desc(g0 + (uint32_t)(r * TC_TW + h * 16) * 16, 128, 2048);
 #pragma unroll
                         for (int b = 0; b < 6; ++b) {
+                            if ((p.ks == 1 && b != 1) || (p.debug & 1)) continue;
                             const uint32_t a = x0 + (uint32_t)((r + (b >= 3 ? 2 : 0)) * WG_XCOLS + h * 16 + (b % 3)) * 16;
                             umma_f16(tmem_base + (uint32_t)b * 64, make_desc(a, 128, WG_XPLANE), bdesc, idesc, (t | r | h) ? 1u : 0u);
                         }
@@ -395,12 +419,12 @@ static int ew_grid(long long n) {
 }  // namespace
 
 bool conv_wgrad_tc_supported(int Cin, int ks, int stride) {
-    return Cin == 64 && ks == 3 && stride == 1 && get_encode() != nullptr;
+    return Cin == 64 && (ks == 3 || ks == 1) && stride == 1 && get_encode() != nullptr;
 }
 
-// dw: [9][64][Cout] fp32 and db: [Cout] fp32 (or null), both ACCUMULATED into (the caller zeroes them).
+// dw: [ks * ks][64][Cout] fp32 and db: [Cout] fp32 (or null), both ACCUMULATED into (the caller zeroes them).
 int launch_conv_wgrad_tc(const void *x_c8, long long x_image_stride, const void *g_c8, float *dw, float *db, int N, int H, int W,
-                         int Cout, cudaStream_t s) {
+                         int Cout, int ks, cudaStream_t s) {
     RVSR_CHECK_ARG(Cout > 0 && Cout % 8 == 0, "conv wgrad: Cout %d is not a multiple of 8", Cout);
     RVSR_CHECK_ARG(x_image_stride % 8 == 0, "conv wgrad: image stride");
     if (N == 0) return RVSR_OK;
@@ -420,7 +444,9 @@ int launch_conv_wgrad_tc(const void *x_c8, long long x_image_stride, const void 
         if (r != CUDA_SUCCESS) { set_error("conv wgrad: cuTensorMapEncodeTiled failed (%d)", (int)r); return RVSR_E_CUDA; }
     }
     p.x = reinterpret_cast<const uint4 *>(x_c8); p.x_image_stride = x_image_stride / 8; p.g_planes = gpl;
-    p.dw = dw; p.db = db; p.Cout = Cout; p.N = N; p.H = H; p.W = W;
+    p.dw = dw; p.db = db; p.Cout = Cout; p.N = N; p.H = H; p.W = W; p.ks = ks;
+    static const int dbg = getenv("RVSR_WG_DEBUG") ? atoi(getenv("RVSR_WG_DEBUG")) : 0;
+    p.debug = dbg;
     p.tiles_x = cdiv(W, TC_TW); p.tiles_y = cdiv(H, TC_ROWS); p.num_tiles = p.tiles_x * p.tiles_y * N;
     p.td.tpi = (uint32_t)(p.tiles_x * p.tiles_y); p.td.m_tpi = magic_div(p.td.tpi, (uint32_t)p.num_tiles);
     p.td.tx = (uint32_t)p.tiles_x; p.td.m_tx = magic_div(p.td.tx, p.td.tpi);

@@ -192,16 +192,14 @@ class _ConvC8(torch.autograd.Function):
                 gp = g
             gw = gb = None
             if needs[0] or needs[1]:
-                if ks != 3 or C != 64:
-                    raise NotImplementedError("conv_c8: the weight gradient is built for 3x3 convolutions of 64-channel sources")
+                if C != 64:
+                    raise NotImplementedError("conv_c8: the weight gradient is built for 64-channel sources")
                 gb = torch.zeros(Cout, dtype=torch.float32, device=dev) if needs[1] else None
-                parts = []
-                for x in xs:
-                    dwt = torch.zeros((9, 64, Cout), dtype=torch.float32, device=dev)
-                    _lib.check(L.rvsr_c8_conv_wgrad(_p(x), x.stride(0), _p(gp), _p(dwt), _p(gb if x is xs[0] else None), N, H, W, C,
+                dwt = torch.zeros((nsrc, ks * ks, 64, Cout), dtype=torch.float32, device=dev)
+                for i, x in enumerate(xs):
+                    _lib.check(L.rvsr_c8_conv_wgrad(_p(x), x.stride(0), _p(gp), _p(dwt[i]), _p(gb if i == 0 else None), N, H, W, C,
                                                     Cout, ks, s), "c8_conv_wgrad")
-                    parts.append(dwt.permute(2, 1, 0))  # [Cout, 64, 9]
-                gw = (parts[0] if nsrc == 1 else torch.cat(parts, 1)).reshape(Cout, nsrc * C, 3, 3)
+                gw = dwt.permute(3, 0, 2, 1).reshape(Cout, nsrc * C, ks, ks)  # [Cout][source][ci][tap]
                 if not needs[0]:
                     gw = None
             gxs = [None] * nsrc
@@ -251,3 +249,50 @@ class _Up2C8(torch.autograd.Function):
 def upsample2x(x, scale=1.0):
     """scale * F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=False) on a C8 tensor."""
     return _Up2C8.apply(x, scale)
+
+
+# ---------------------------------------------------------------- whole-step CUDA graph
+class GraphedStep:
+    """forward + loss + backward of `net` captured ONCE into a CUDA graph and replayed per step.
+
+    A training step of this path is ~1000 small launches issued from Python; eager, the host cannot feed the GPU fast enough
+    (the step is launch-bound).  Everything on the path is capture-safe: kernels go to torch's current stream, no host
+    synchronisation, buffers come from torch's (graph-private) allocator, weights are re-packed INSIDE the graph so a replay
+    sees the optimizer's latest values.  Usage:
+
+        step = GraphedStep(net, torch.nn.functional.l1_loss, x_example, target_example)
+        for x, target in loader:          # fixed shapes
+            loss = step(x, target)        # p.grad of every parameter now holds this step's gradient (overwritten, not summed)
+            optimizer.step()
+
+    The usual whole-network capture rules apply (torch.cuda.graphs): static shapes, optimizer.zero_grad(set_to_none=True) must
+    NOT be called between replays (the graph owns the .grad tensors)."""
+
+    def __init__(self, net, loss_fn, x, target, amp_dtype=torch.bfloat16, warmup=3):
+        if not x.is_cuda:
+            raise NotImplementedError("GraphedStep: CUDA tensors only")
+        self.net, self.loss_fn, self.amp_dtype = net, loss_fn, amp_dtype
+        self.x, self.target = x.detach().clone(), target.detach().clone()
+        side = torch.cuda.Stream(device=x.device)
+        side.wait_stream(torch.cuda.current_stream(x.device))
+        with torch.cuda.stream(side):   # warm-up on a side stream: lazy initialisation (cuDNN plans, smem attributes) happens here
+            for _ in range(warmup):
+                net.zero_grad(set_to_none=True)
+                self._fwd_bwd()
+        torch.cuda.current_stream(x.device).wait_stream(side)
+        net.zero_grad(set_to_none=True)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._fwd_bwd()
+
+    def _fwd_bwd(self):
+        with torch.autocast("cuda", dtype=self.amp_dtype, enabled=self.amp_dtype is not None):
+            loss = self.loss_fn(self.net(self.x).float(), self.target)
+        loss.backward()
+        return loss.detach()
+
+    def __call__(self, x, target):
+        self.x.copy_(x)
+        self.target.copy_(target)
+        self.graph.replay()
+        return self.loss

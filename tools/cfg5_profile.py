@@ -22,13 +22,18 @@ def step():
     with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
         loss = F.l1_loss(net(x).float(), gt)
     loss.backward()
+if os.environ.get('GRAPH', '0') == '1':
+    from realvsr_b200.train_c8 import GraphedStep
+    gs = GraphedStep(net, F.l1_loss, x, gt, amp_dtype=torch.bfloat16 if amp else None)
+    step = lambda: gs(x, gt)
 for _ in range(3): step()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(5): step()
 e1.record(); torch.cuda.synchronize()
-print('cfg5 step: %.2f ms (AMP=%s, RVSR_TRAIN_C8=%s, CL=%s)' % (e0.elapsed_time(e1) / 5, os.environ.get('AMP', '0'), os.environ.get('RVSR_TRAIN_C8', '1'), os.environ.get('CL', '0')))
+print('cfg5 step: %.2f ms (AMP=%s, RVSR_TRAIN_C8=%s, CL=%s, GRAPH=%s)' % (e0.elapsed_time(e1) / 5, os.environ.get('AMP', '0'), os.environ.get('RVSR_TRAIN_C8', '1'), os.environ.get('CL', '0'), os.environ.get('GRAPH', '0')))
+if os.environ.get('NOPROF', '0') == '1': sys.exit(0)
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     for _ in range(3): step()
