@@ -114,7 +114,9 @@ int rvsr_conv2d_fwd(const void *x1, const void *x2, const void *weight, const vo
  *   rvsr_c8_conv_pack_weight  fp32 OIHW nn.Parameter -> the kernels' bf16 operand layout.  mode 0: forward convolution over
  *                             input channels [w_c0, w_c0 + Cin) of rows with w_cin_total channels.  mode 1: the DATA GRADIENT
  *                             of input channels [w_c0, w_c0 + Cout) as a convolution Cin (= forward Cout) -> Cout with the
- *                             transposed, flipped weights (dX = conv(dY, W^T flipped); stride 1 only).
+ *                             transposed, flipped weights (dX = conv(dY, W^T flipped); stride 1 only).  layouts: bit 0 = the
+ *                             single-CTA kernels' operand layout, bit 1 = the CTA-pair kernels' (read by 3x3 launches of >= 4
+ *                             tiles); 3 packs both.
  *   rvsr_c8_conv_fwd          y = act(conv(cat(x[0..nsrc)), w) + bias) [+ residual], optional fused PixelShuffle(2); nsrc sources
  *                             of C channels each (C % 16 == 0, C <= 64); also runs every data gradient (with mode-1 weights).
  *   rvsr_c8_conv_wgrad        dw_t[tap][ci][co] += sum_pixels x[pixel + tap][ci] * g[pixel][co] (fp32, [9][64][Cout], zeroed by the
@@ -128,7 +130,7 @@ int rvsr_c8_from_nchw(const void *src, int src_dtype, void *dst_c8, int N, int C
 int rvsr_c8_to_nchw(const void *src_c8, void *dst, int dst_dtype, int N, int C, int H, int W, int planes, void *stream);
 size_t rvsr_c8_conv_weight_bytes(int Cout, int Cin, int ks, int shuffle);
 int rvsr_c8_conv_pack_weight(const float *weight, void *dst, int Cout, int Cin, int ks, int shuffle, int mode, int w_cin_total,
-                             int w_c0, void *stream);
+                             int w_c0, int layouts, void *stream);
 int rvsr_c8_conv_fwd(const void *const *x, const long long *x_image_stride, int nsrc, int C, const void *w_packed, const float *bias,
                      const void *residual, void *y, int N, int H, int W, int Cout, int ks, int stride, int act, int shuffle,
                      void *stream);

@@ -407,12 +407,15 @@ class _EDVRBase(nn.Module):
             if self._upsample:
                 out = conv(self.upconv1, out, "lrelu", shuffle=True)   # lrelu(PixelShuffle(conv)) == PixelShuffle(lrelu(conv))
                 out = conv(self.upconv2, out, "lrelu", shuffle=True)
-            out = self.conv_last(nchw(conv(self.HRconv, out, "lrelu")))
+            # conv_last (64 -> nc <= 8): the output padded to 16 channels (the narrowest tile of the tcgen05 kernels)
+            w_last = F.pad(self.conv_last.weight, (0, 0, 0, 0, 0, 0, 0, 16 - self.nc))
+            b_last = F.pad(self.conv_last.bias, (0, 16 - self.nc))
+            out = T.from_c8(T.conv(conv(self.HRconv, out, "lrelu"), w_last, b_last), self.nc, torch.float32)
         if self._upsample:
             base = F.interpolate(x_center, scale_factor=4, mode='bilinear', align_corners=False)
         else:
             base = x_center
-        return out.float() + base
+        return out + base
 
     # ------------------------------------------------------------------ module path (autograd-capable)
     def _forward_modules(self, x):

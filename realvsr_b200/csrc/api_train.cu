@@ -35,7 +35,7 @@ size_t rvsr_c8_conv_weight_bytes(int Cout, int Cin, int ks, int shuffle) {
 }
 
 int rvsr_c8_conv_pack_weight(const float *weight, void *dst, int Cout, int Cin, int ks, int shuffle, int mode, int w_cin_total,
-                             int w_c0, void *stream) {
+                             int w_c0, int layouts, void *stream) {
     RVSR_CHECK_ARG(weight && dst && Cout > 0 && Cin > 0 && (ks == 1 || ks == 3), "c8 pack weight: bad arguments");
     RVSR_CHECK_ARG(mode == 0 || mode == 1, "c8 pack weight: mode %d", mode);
     RVSR_CHECK_ARG(((uintptr_t)dst & 255) == 0, "c8 pack weight: destination must be 256-byte aligned");
@@ -51,8 +51,9 @@ int rvsr_c8_conv_pack_weight(const float *weight, void *dst, int Cout, int Cin, 
         wv = WeightView{w_c0 * KK + KK - 1, KK, w_cin_total * KK, -1, 1};
     }
     cudaStream_t s = (cudaStream_t)stream;
-    RVSR_TRY(pack_weight_tc(weight, dst, Cout, Cin, ks, shuffle ? 1 : 0, s, &wv));
-    if (tc2_weight_bytes(Cout, Cin, ks, shuffle ? 1 : 0) > 0)
+    // layouts: bit 0 = single-CTA kernels' layout, bit 1 = CTA-pair layout (the one launches of >= 4 tiles read; 3x3 only)
+    if (layouts & 1) RVSR_TRY(pack_weight_tc(weight, dst, Cout, Cin, ks, shuffle ? 1 : 0, s, &wv));
+    if ((layouts & 2) && tc2_weight_bytes(Cout, Cin, ks, shuffle ? 1 : 0) > 0)
         RVSR_TRY(pack_weight_tc2(weight, (char *)dst + align_up(a, 256), Cout, Cin, ks, shuffle ? 1 : 0, s, &wv));
     return RVSR_OK;
 }

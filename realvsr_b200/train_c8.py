@@ -106,15 +106,21 @@ def from_c8(x, C=None, dtype=torch.bfloat16):
 
 
 # ---------------------------------------------------------------- convolution
-def _pack_weight(weight, Cout, Cin, ks, shuffle, mode, cin_total, c0):
+def _pack_weight(weight, Cout, Cin, ks, shuffle, mode, cin_total, c0, tiles=0):
     L = _lib.lib()
     nbytes = L.rvsr_c8_conv_weight_bytes(Cout, Cin, ks, int(shuffle))
     if nbytes == 0:
         raise NotImplementedError("train_c8: convolution %d <- %d (k=%d) is not covered by the tcgen05 kernels" % (Cout, Cin, ks))
     dst = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
-    _lib.check(L.rvsr_c8_conv_pack_weight(_p(weight), _p(dst), Cout, Cin, ks, int(shuffle), mode, cin_total, c0,
+    # launches of >= 4 tiles of a 3x3 convolution with 64- / 128-wide output tiles run on the CTA-pair kernel: one layout suffices
+    pair_only = ks == 3 and tiles >= 4 and Cin % 16 == 0 and Cout > 16 and Cout % 64 == 0
+    _lib.check(L.rvsr_c8_conv_pack_weight(_p(weight), _p(dst), Cout, Cin, ks, int(shuffle), mode, cin_total, c0, 2 if pair_only else 3,
                                           _stream(weight.device)), "c8_conv_pack_weight")
     return dst
+
+
+def _tiles(N, H, W, ks):
+    return N * ((H + 3) // 4) * ((W + 32 - ks) // (33 - ks))
 
 
 def _conv_launch(xs, w_packed, bias, residual, N, H, W, C, Cout, ks, act, shuffle):
@@ -158,7 +164,7 @@ class _ConvC8(torch.autograd.Function):
         if residual is not None:
             residual = _check_c8(residual, "conv_c8 residual")
         with torch.cuda.device(weight.device):
-            wp = _pack_weight(weight, Cout, Cin, ks, shuffle, 0, Cin, 0)
+            wp = _pack_weight(weight, Cout, Cin, ks, shuffle, 0, Cin, 0, _tiles(N, H, W, ks))
             y = _conv_launch(xs, wp, bias, residual, N, H, W, C, Cout, ks, act, shuffle)
         ctx.meta = (act, shuffle, N, H, W, C, Cout, ks, len(xs), residual is not None)
         needs = ctx.needs_input_grad
@@ -194,8 +200,9 @@ class _ConvC8(torch.autograd.Function):
             if needs[0] or needs[1]:
                 if C != 64:
                     raise NotImplementedError("conv_c8: the weight gradient is built for 64-channel sources")
-                gb = torch.zeros(Cout, dtype=torch.float32, device=dev) if needs[1] else None
-                dwt = torch.zeros((nsrc, ks * ks, 64, Cout), dtype=torch.float32, device=dev)
+                nw = nsrc * ks * ks * 64 * Cout
+                zb = torch.zeros(nw + Cout, dtype=torch.float32, device=dev)   # one fill for both accumulators
+                dwt, gb = zb[:nw].view(nsrc, ks * ks, 64, Cout), (zb[nw:] if needs[1] else None)
                 for i, x in enumerate(xs):
                     _lib.check(L.rvsr_c8_conv_wgrad(_p(x), x.stride(0), _p(gp), _p(dwt[i]), _p(gb if i == 0 else None), N, H, W, C,
                                                     Cout, ks, s), "c8_conv_wgrad")
@@ -205,14 +212,15 @@ class _ConvC8(torch.autograd.Function):
             gxs = [None] * nsrc
             if any(needs[5:5 + nsrc]):
                 # dX_i = conv(dY, W[:, slice_i]^T flipped): Cout gradient channels enter as 64-channel sources
-                if Cout % 64 != 0:
-                    raise NotImplementedError("conv_c8: the data gradient needs Cout %% 64 == 0 (got %d)" % Cout)
-                gsrc = [gp[:, 8 * k:8 * k + 8] for k in range(Cout // 64)]
+                if Cout % 64 != 0 and not (Cout < 64 and Cout % 16 == 0):
+                    raise NotImplementedError("conv_c8: the data gradient needs Cout %% 64 == 0 or Cout in {16, 32, 48} (got %d)" % Cout)
+                gc = min(Cout, 64)
+                gsrc = [gp[:, 8 * k:8 * k + 8] for k in range(Cout // 64)] if Cout >= 64 else [gp]
                 for i in range(nsrc):
                     if not needs[5 + i]:
                         continue
-                    wp = _pack_weight(weight, C, Cout, ks, False, 1, nsrc * C, i * C)
-                    gxs[i] = _conv_launch(gsrc, wp, None, None, N, H, W, 64, C, ks, _lib.ACT_NONE, False)
+                    wp = _pack_weight(weight, C, Cout, ks, False, 1, nsrc * C, i * C, _tiles(N, H, W, ks))
+                    gxs[i] = _conv_launch(gsrc, wp, None, None, N, H, W, gc, C, ks, _lib.ACT_NONE, False)
         return (gw, gb, g_res, None, None, *gxs)
 
 

@@ -43,17 +43,19 @@ def test_layout_roundtrip_and_gradient():
     assert torch.equal(x.grad, _r(w))
 
 
-@pytest.mark.parametrize("case", ["lrelu", "relu", "none_residual", "cat2", "shuffle", "shuffle_none"])
+@pytest.mark.parametrize("case", ["lrelu", "relu", "none_residual", "cat2", "shuffle", "shuffle_none", "k1_lrelu", "k1_cat5", "cout16"])
 @pytest.mark.parametrize("shape", [(2, 16, 32), (3, 18, 40), (1, 64, 64)])
 def test_conv_forward_backward(case, shape):
     from realvsr_b200 import train_c8 as T
     N, H, W = shape
     g = torch.Generator(device="cuda").manual_seed(len(case) * 131 + N * 17 + H)
-    nsrc = 2 if case == "cat2" else 1
-    Cout = 256 if case.startswith("shuffle") else 64
-    act = {"lrelu": "lrelu", "relu": "relu", "none_residual": None, "cat2": "lrelu", "shuffle": "lrelu", "shuffle_none": None}[case]
+    nsrc = {"cat2": 2, "k1_cat5": 5}.get(case, 1)
+    Cout = 256 if case.startswith("shuffle") else (16 if case == "cout16" else 64)
+    ks = 1 if case.startswith("k1") else 3
+    act = {"lrelu": "lrelu", "relu": "relu", "none_residual": None, "cat2": "lrelu", "shuffle": "lrelu", "shuffle_none": None,
+           "k1_lrelu": "lrelu", "k1_cat5": "lrelu", "cout16": None}[case]
     xs = [_r(torch.randn(N, 64, H, W, device="cuda", generator=g)).requires_grad_() for _ in range(nsrc)]
-    w = _r(torch.randn(Cout, 64 * nsrc, 3, 3, device="cuda", generator=g) * 0.05).requires_grad_()  # a bf16-exact leaf: no cast in the graph
+    w = _r(torch.randn(Cout, 64 * nsrc, ks, ks, device="cuda", generator=g) * 0.05).requires_grad_()  # a bf16-exact leaf: no cast in the graph
     b = (torch.randn(Cout, device="cuda", generator=g) * 0.1).requires_grad_()
     res = _r(torch.randn(N, 64, H, W, device="cuda", generator=g)).requires_grad_() if case == "none_residual" else None
     # product
@@ -67,7 +69,7 @@ def test_conv_forward_backward(case, shape):
     # reference: fp32 math on the same bf16-exact operands.  The branch of the activation is taken from the PRODUCT's output
     # sign: two fp32 summation orders disagree on it for the ~1e-6 of outputs whose pre-activation is ~1e-7 (forward
     # difference 1e-7, but a different gradient at that element), which is no property of either implementation.
-    pre = F.conv2d(torch.cat(xs, 1), w, b, padding=1)
+    pre = F.conv2d(torch.cat(xs, 1), w, b, padding=ks // 2)
     pos = (F.pixel_unshuffle(y_nchw.detach(), 2) if case.startswith("shuffle") else y_nchw.detach()) > 0
     assert act is None or int((pos != (pre.detach() > 0)).sum()) <= 4
     if act == "lrelu":
