@@ -139,6 +139,16 @@ int rvsr_c8_conv_wgrad(const void *x, long long x_image_stride, const void *g, f
 int rvsr_c8_act_bwd(const void *g, const void *y, void *out, long long n_elems, int act, void *stream);
 int rvsr_c8_unshuffle2_act_bwd(const void *g, const void *y, void *out, int N, int C, int H, int W, int act, void *stream);
 int rvsr_c8_upsample2x(const void *src, void *dst, long long planes, int H, int W, float scale, int backward, void *stream);
+/* ModulatedDeformConvPack.forward / its autograd (deform_conv.py:274-292, :97-153) on C8 tensors, for EDVR's shape class
+ * (64 -> 64 channels, 3x3, stride 1, pad 1, 8 deformable groups).  `om` is the output of the conv_offset_mask convolution
+ * as a 256-channel C8 tensor (144 offsets, 72 mask logits, 40 zero channels: the 216 outputs padded to whole 64-wide tiles);
+ * the chunk / cat / sigmoid of the reference happen inside.  fwd: y = act(dcn(x, offset, sigmoid(mask)) + bias) on
+ * dcn_tc_kernel.  bwd (dcn_bwd_tc_kernel): gx, gom (C8 bf16), gw [64][64][3][3] and gb [64] (fp32), all written. */
+size_t rvsr_c8_mdcn_workspace_bytes(int N, int H, int W, int backward);
+int rvsr_c8_mdcn_fwd(const void *x, const void *om, const float *weight, const float *bias, void *y, int N, int H, int W, int act,
+                     void *workspace, size_t workspace_bytes, void *stream);
+int rvsr_c8_mdcn_bwd(const void *x, const void *om, const float *weight, const void *g, const void *y, void *gx, void *gom, float *gw,
+                     float *gb, int N, int H, int W, int act, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------ EDVR engine
  * Replaces EDVR.forward / EDVR_NoUp.forward (EDVR_arch.py:258-320, :358-404) and everything

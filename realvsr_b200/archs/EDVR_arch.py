@@ -30,7 +30,6 @@ import torch.nn.functional as F
 
 from . import arch_util
 from .dcn.deform_conv import ModulatedDeformConvPack as DCN
-from .dcn.deform_conv import modulated_deform_conv as _dcn_fn
 from .. import engine as _engine
 
 _ENGINE_LOCK = threading.Lock()  # DataParallel runs the replicas' forwards in threads
@@ -325,8 +324,8 @@ class _EDVRBase(nn.Module):
     def _forward_c8(self, x):
         """Same graph as _forward_modules.  Every 64-channel convolution (3x3 and 1x1; stride 2 as stride 1 + subsampling), the
         residual adds, torch.cat, the x2 upsamples and PixelShuffle + lrelu run as train_c8 Functions on [N, C/8, H, W, 8] bf16
-        tensors; TSA's pools / sigmoids / products are torch ops on the same tensors.  Only the two 3-channel convolutions
-        (conv_first, conv_last) and the DCN operator work on NCHW bf16 tensors, with a layout conversion at the boundary."""
+        tensors, and so does the DCN operator (train_c8.dcn_pack); TSA's pools / sigmoids / products are torch ops on the same
+        tensors.  Only conv_first (3 input channels) is a torch convolution on NCHW tensors."""
         from .. import train_c8 as T
         B, N, C, H, W = x.size()
         bf = torch.bfloat16
@@ -340,17 +339,13 @@ class _EDVRBase(nn.Module):
             return t
 
         def dcn(pack, t, feat, act=None):
-            # ModulatedDeformConvPack.forward (deform_conv.py:274-292): the 64 -> 216 offset / mask convolution runs here with its
-            # weights zero-padded to 256 outputs (whole 64-wide tiles for the data gradient); the operator itself is
-            # rvsr_mdcn_fwd / rvsr_mdcn_bwd on NCHW bf16 tensors
+            # ModulatedDeformConvPack.forward (deform_conv.py:274-292): the 64 -> 216 offset / mask convolution with its weights
+            # zero-padded to 256 outputs (whole 64-wide tiles for the data gradient), then the operator on the same C8 tensors
+            # (rvsr_c8_mdcn_fwd / _bwd: dcn_tc_kernel, dcn_bwd_tc_kernel)
             k = pack.conv_offset_mask.weight.shape[0]
             w_om = F.pad(pack.conv_offset_mask.weight, (0, 0, 0, 0, 0, 0, 0, 256 - k))
             b_om = F.pad(pack.conv_offset_mask.bias, (0, 256 - k))
-            om = T.from_c8(T.conv(feat, w_om, b_om), k, bf)
-            third = k // 3
-            y = _dcn_fn(nchw(t), om[:, :2 * third], torch.sigmoid(om[:, 2 * third:]), pack.weight.contiguous(), pack.bias,
-                        pack.stride, pack.padding, pack.dilation, pack.groups, pack.deformable_groups)
-            return T.to_c8(F.leaky_relu(y, 0.1) if act else y)
+            return T.dcn_pack(t, T.conv(feat, w_om, b_om), pack.weight, pack.bias, "lrelu" if act else None)
 
         def down2(m, t):
             # stride-2 3x3 convolution = the stride-1 convolution at the even pixels (pad 1 both ways): 4x the MMAs of two small

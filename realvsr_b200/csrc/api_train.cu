@@ -11,6 +11,11 @@ int launch_unshuffle2_act_bwd_c8(const void *g, const void *y, void *out, int N,
 int launch_upsample2x_c8(const void *src, void *dst, long long planes, int H, int W, float scale, int backward, cudaStream_t s);
 int launch_nchw_to_c8_bf16(const void *src, int src_dtype, void *dst, int N, int C, int H, int W, int planes, cudaStream_t s);
 int launch_c8_to_nchw_bf16(const void *src, void *dst, int dst_dtype, int N, int C, int H, int W, int planes, cudaStream_t s);
+size_t c8_mdcn_workspace_bytes(int N, int H, int W, int backward);
+int c8_mdcn_fwd(const void *x, const void *om, const float *weight, const float *bias, void *y, int N, int H, int W, int act,
+                void *workspace, size_t workspace_bytes, cudaStream_t s);
+int c8_mdcn_bwd(const void *x, const void *om, const float *weight, const void *g, const void *y, void *gx, void *gom, float *gw,
+                float *gb, int N, int H, int W, int act, void *workspace, size_t workspace_bytes, cudaStream_t s);
 }  // namespace rvsr
 
 using namespace rvsr;
@@ -109,6 +114,20 @@ int rvsr_c8_unshuffle2_act_bwd(const void *g, const void *y, void *out, int N, i
 int rvsr_c8_upsample2x(const void *src, void *dst, long long planes, int H, int W, float scale, int backward, void *stream) {
     RVSR_CHECK_ARG(planes >= 0 && H > 0 && W > 0 && (planes == 0 || (src && dst)), "c8 upsample2x: bad arguments");
     return launch_upsample2x_c8(src, dst, planes, H, W, scale, backward, (cudaStream_t)stream);
+}
+
+size_t rvsr_c8_mdcn_workspace_bytes(int N, int H, int W, int backward) { return c8_mdcn_workspace_bytes(N, H, W, backward); }
+int rvsr_c8_mdcn_fwd(const void *x, const void *om, const float *weight, const float *bias, void *y, int N, int H, int W, int act,
+                     void *workspace, size_t workspace_bytes, void *stream) {
+    RVSR_CHECK_ARG(N >= 0 && H > 0 && W > 0, "c8 mdcn fwd: bad sizes");
+    RVSR_CHECK_ARG(N == 0 || (x && om && weight && y && workspace), "c8 mdcn fwd: null buffer");
+    return c8_mdcn_fwd(x, om, weight, bias, y, N, H, W, act, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+int rvsr_c8_mdcn_bwd(const void *x, const void *om, const float *weight, const void *g, const void *y, void *gx, void *gom, float *gw,
+                     float *gb, int N, int H, int W, int act, void *workspace, size_t workspace_bytes, void *stream) {
+    RVSR_CHECK_ARG(N >= 0 && H > 0 && W > 0, "c8 mdcn bwd: bad sizes");
+    RVSR_CHECK_ARG(gw && (N == 0 || (x && om && weight && g && gx && gom && workspace)), "c8 mdcn bwd: null buffer");
+    return c8_mdcn_bwd(x, om, weight, g, y, gx, gom, gw, gb, N, H, W, act, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

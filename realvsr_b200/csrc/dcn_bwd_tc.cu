@@ -353,6 +353,44 @@ size_t dcn_bwd_tc_workspace_bytes(int B, int H, int W) {
            align_up(px * 64 * 4, 256) + align_up(px * 144 * 4, 256) + align_up(px * 72 * 4, 256) + 2 * align_up((size_t)64 * 64 * 9 * 4, 256) + 4096;
 }
 
+size_t dcn_bwd_tc_wt_bytes() { return BW_WT_BYTES; }
+// weight: bf16 [64][64][3][3] -> the kernel's W^T operand layout (dcn_bwd_tc_wt_bytes())
+int pack_wt_dcn_bwd_tc(const void *weight_bf16, void *wt, cudaStream_t s) {
+    pack_wt_bwd_kernel<<<(BW_WT_BYTES / 2 + 255) / 256, 256, 0, s>>>((const __nv_bfloat16 *)weight_bf16, (__nv_bfloat16 *)wt, BW_WT_BYTES / 2);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+// The kernel itself on its native buffers: x8 / g8 channel-blocked bf16 [B][8][H][W][8], off32 / msk32 planar fp32 ([B][144][H][W],
+// [B][72][H][W], mask already sigmoid-ed), wt from pack_wt_dcn_bwd_tc.  gx8 (fp32 channel-blocked) and gw32 ([64][64][9]) must be
+// ZEROED by the caller; goff32 / gmsk32 (planar fp32) are fully written.
+int launch_dcn_bwd_tc_core(const void *x8, const void *g8, const float *off32, const float *msk32, const void *wt, float *gx8, float *goff32,
+                           float *gmsk32, float *gw32, int B, int H, int W, cudaStream_t s) {
+    TcDcnBwdParams p;
+    memset(&p, 0, sizeof(p));
+    {
+        EncodeTiledFn enc = get_encode();
+        const cuuint64_t dims[3] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)B * 8};
+        const cuuint64_t strides[2] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
+        const cuuint32_t box[3] = {(cuuint32_t)TC_TW * 8, (cuuint32_t)TC_ROWS, 8};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&p.tmap_gout, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(g8), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("dcn bwd (tensor cores): cuTensorMapEncodeTiled failed (%d)", (int)r); return RVSR_E_CUDA; }
+    }
+    p.x = (const __nv_bfloat16 *)x8; p.offset = off32; p.mask = msk32; p.wt = (const __nv_bfloat16 *)wt; p.gx = gx8; p.goffset = goff32; p.gmask = gmsk32; p.gw = gw32;
+    p.N = B; p.H = H; p.W = W;
+    p.tiles_x = cdiv(W, TC_TW); p.tiles_y = cdiv(H, TC_ROWS); p.num_tiles = p.tiles_x * p.tiles_y * B;
+    p.td.tpi = (uint32_t)(p.tiles_x * p.tiles_y); p.td.m_tpi = magic_div(p.td.tpi, (uint32_t)p.num_tiles);
+    p.td.tx = (uint32_t)p.tiles_x; p.td.m_tx = magic_div(p.td.tx, p.td.tpi);
+    const size_t smem = BW_WT_BYTES + BW_GS * BW_G_BYTES + BW_SS * BW_STAGE_BYTES + BW_STEP_BYTES + 256 + 1024;
+    RVSR_TRY(ensure_max_dynamic_smem(reinterpret_cast<const void *>(&dcn_bwd_tc_kernel), (int)smem));
+    int gx = sm_count();
+    if (gx > p.num_tiles) gx = p.num_tiles;
+    dcn_bwd_tc_kernel<<<gx, BW_THREADS, smem, s>>>(p);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+
 // All tensors bf16 NCHW (weight [64][64][3][3]); every gradient is written (grad_weight / grad_bias: this call's sums).
 int launch_dcn_bwd_tc(const void *input, const void *offset, const void *mask, const void *weight, const void *grad_output,
                       void *grad_input, void *grad_offset, void *grad_mask, void *grad_weight, void *grad_bias, int B, int H, int W,
@@ -374,34 +412,11 @@ int launch_dcn_bwd_tc(const void *input, const void *offset, const void *mask, c
     RVSR_LAUNCH_CHECK();
     RVSR_TRY(launch_convert_bf16_f32(offset, off32, (long long)px * 144, s));
     RVSR_TRY(launch_convert_bf16_f32(mask, msk32, (long long)px * 72, s));
-    pack_wt_bwd_kernel<<<(BW_WT_BYTES / 2 + 255) / 256, 256, 0, s>>>((const __nv_bfloat16 *)weight, wt, BW_WT_BYTES / 2);
-    RVSR_LAUNCH_CHECK();
+    RVSR_TRY(pack_wt_dcn_bwd_tc(weight, wt, s));
     RVSR_CUDA(cudaMemsetAsync(gx8, 0, px * 64 * 4, s));
     RVSR_CUDA(cudaMemsetAsync(gw32, 0, (size_t)64 * 64 * 9 * 4, s));
     RVSR_CUDA(cudaMemsetAsync(gb32, 0, 64 * 4, s));
-    TcDcnBwdParams p;
-    memset(&p, 0, sizeof(p));
-    {
-        EncodeTiledFn enc = get_encode();
-        const cuuint64_t dims[3] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)B * 8};
-        const cuuint64_t strides[2] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
-        const cuuint32_t box[3] = {(cuuint32_t)TC_TW * 8, (cuuint32_t)TC_ROWS, 8};
-        const cuuint32_t estr[3] = {1, 1, 1};
-        CUresult r = enc(&p.tmap_gout, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, g8, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) { set_error("dcn bwd (tensor cores): cuTensorMapEncodeTiled failed (%d)", (int)r); return RVSR_E_CUDA; }
-    }
-    p.x = x8; p.offset = off32; p.mask = msk32; p.wt = wt; p.gx = gx8; p.goffset = goff32; p.gmask = gmsk32; p.gw = gw32;
-    p.N = B; p.H = H; p.W = W;
-    p.tiles_x = cdiv(W, TC_TW); p.tiles_y = cdiv(H, TC_ROWS); p.num_tiles = p.tiles_x * p.tiles_y * B;
-    p.td.tpi = (uint32_t)(p.tiles_x * p.tiles_y); p.td.m_tpi = magic_div(p.td.tpi, (uint32_t)p.num_tiles);
-    p.td.tx = (uint32_t)p.tiles_x; p.td.m_tx = magic_div(p.td.tx, p.td.tpi);
-    const size_t smem = BW_WT_BYTES + BW_GS * BW_G_BYTES + BW_SS * BW_STAGE_BYTES + BW_STEP_BYTES + 256 + 1024;
-    RVSR_TRY(ensure_max_dynamic_smem(reinterpret_cast<const void *>(&dcn_bwd_tc_kernel), (int)smem));
-    int gx = sm_count();
-    if (gx > p.num_tiles) gx = p.num_tiles;
-    dcn_bwd_tc_kernel<<<gx, BW_THREADS, smem, s>>>(p);
-    RVSR_LAUNCH_CHECK();
+    RVSR_TRY(launch_dcn_bwd_tc_core(x8, g8, off32, msk32, wt, gx8, goff32, gmsk32, gw32, B, H, W, s));
     if (grad_bias != nullptr) {
         bias_grad_bf16_kernel<<<dim3(64, B < 32 ? B : 32), 256, 0, s>>>((const __nv_bfloat16 *)grad_output, gb32, 64, HW, B);
         RVSR_LAUNCH_CHECK();

@@ -16,6 +16,12 @@
 
 namespace rvsr {
 
+size_t dcn_bwd_tc_wt_bytes();
+int pack_wt_dcn_bwd_tc(const void *weight_bf16, void *wt, cudaStream_t s);
+int launch_dcn_bwd_tc_core(const void *x8, const void *g8, const float *off32, const float *msk32, const void *wt, float *gx8, float *goff32,
+                           float *gmsk32, float *gw32, int B, int H, int W, cudaStream_t s);
+int launch_act_bwd_c8(const void *g, const void *y, void *out, long long n_elems, int act, cudaStream_t s);
+
 namespace {
 
 // ---------------------------------------------------------------- weight gradient on tcgen05
@@ -410,6 +416,123 @@ __global__ void c8_to_nchw_kernel(const uint4 *__restrict__ src, Tout *__restric
     }
 }
 
+// ---- ModulatedDeformConvPack on C8 tensors: layout glue around dcn_tc_kernel / dcn_bwd_tc_kernel
+// om: the 64 -> 216 offset / mask convolution's output as a 256-channel C8 bf16 tensor (channels: 144 offsets g * 18 + 2 * tap +
+// {dy, dx}, 72 mask logits 144 + g * 9 + tap, 40 zeros -- deform_conv.py:279-283).  One thread per (image, group, pixel) writes
+//   om24  the forward kernel's format (see om24_from_planar_kernel), mask = sigmoid(logit), and / or
+//   off32 / msk32  planar fp32 [N][144][HW] / [N][72][HW] for the backward kernel.
+__global__ void om_from_c8_kernel(const __nv_bfloat16 *__restrict__ om, uint4 *__restrict__ om24, float *__restrict__ off32,
+                                  float *__restrict__ msk32, int HW) {
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= HW) return;
+    const int g = blockIdx.y;
+    const long long n = blockIdx.z;
+    const __nv_bfloat16 *src = om + n * 32 * (long long)HW * 8;
+    auto ch = [&](int c) { return __bfloat162float(src[((long long)(c >> 3) * HW + pix) * 8 + (c & 7)]); };
+    float o[18], m[10];
+#pragma unroll
+    for (int j = 0; j < 18; ++j) o[j] = ch(g * 18 + j);
+#pragma unroll
+    for (int j = 0; j < 9; ++j) m[j] = __fdividef(1.f, 1.f + __expf(-ch(144 + g * 9 + j)));
+    m[9] = 0.f;
+    if (om24 != nullptr) {
+        uint32_t mw[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const __half2 h = __floats2half2_rn(m[2 * k], m[2 * k + 1]);
+            mw[k] = *reinterpret_cast<const uint32_t *>(&h);
+        }
+        uint4 *d = om24 + ((n * 24 + g * 3) * (long long)HW + pix) * 2;
+        auto f = [](float v) { return __float_as_uint(v); };
+        d[0] = make_uint4(f(o[0]), f(o[1]), f(o[2]), f(o[3])); d[1] = make_uint4(f(o[4]), f(o[5]), f(o[6]), f(o[7]));
+        d += (long long)HW * 2;
+        d[0] = make_uint4(f(o[8]), f(o[9]), f(o[10]), f(o[11])); d[1] = make_uint4(f(o[12]), f(o[13]), f(o[14]), f(o[15]));
+        d += (long long)HW * 2;
+        d[0] = make_uint4(f(o[16]), f(o[17]), mw[0], mw[1]); d[1] = make_uint4(mw[2], mw[3], mw[4], 0u);
+    }
+    if (off32 != nullptr) {
+        float *po = off32 + (n * 144 + g * 18) * (long long)HW + pix, *pm = msk32 + (n * 72 + g * 9) * (long long)HW + pix;
+#pragma unroll
+        for (int j = 0; j < 18; ++j) po[(long long)j * HW] = o[j];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) pm[(long long)j * HW] = m[j];
+    }
+}
+// gradient of the 256-channel convolution output from the operator's planar fp32 gradients: offsets as they are, mask logits
+// through the sigmoid (s * (1 - s) with s = msk32), padding channels zero.  One thread per (image, channel block, pixel).
+__global__ void om_grad_to_c8_kernel(const float *__restrict__ goff32, const float *__restrict__ gmsk32, const float *__restrict__ msk32,
+                                     uint4 *__restrict__ gom, int HW) {
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= HW) return;
+    const int q = blockIdx.y;
+    const long long n = blockIdx.z;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int c = q * 8 + e;
+        if (c < 144) {
+            v[e] = goff32[(n * 144 + c) * (long long)HW + pix];
+        } else if (c < 216) {
+            const long long i = (n * 72 + (c - 144)) * (long long)HW + pix;
+            const float sg = msk32[i];
+            v[e] = gmsk32[i] * sg * (1.f - sg);
+        } else {
+            v[e] = 0.f;
+        }
+    }
+    gom[(n * 32 + q) * (long long)HW + pix] = pack8(v);
+}
+// db[c] += sum over images and pixels of a 64-channel C8 tensor
+__global__ void bias_grad_c8_kernel(const uint4 *__restrict__ g, float *__restrict__ db, int HW, int N) {
+    const int q = blockIdx.y;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int n = blockIdx.z; n < N; n += gridDim.z)
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+            float v[8];
+            unpack8(__ldg(g + ((long long)n * 8 + q) * HW + i), v);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] += v[k];
+        }
+    __shared__ float part[8][8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        float s_ = acc[k];
+        for (int o = 16; o > 0; o >>= 1) s_ += __shfl_xor_sync(0xffffffffu, s_, o);
+        if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5][k] = s_;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        float t = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += part[w][threadIdx.x];
+        atomicAdd(db + q * 8 + threadIdx.x, t);
+    }
+}
+// bf16 <-> fp16, same layout (dcn_tc_kernel's operands are fp16: more mantissa than bf16, and activations stay far inside its range)
+__global__ void cvt_bf16_to_f16_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float v[8];
+        unpack8(__ldg(src + i), v);
+        uint4 u;
+        __half2 *h = reinterpret_cast<__half2 *>(&u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) h[k] = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+        dst[i] = u;
+    }
+}
+__global__ void cvt_f16_to_bf16_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const uint4 u = __ldg(src + i);
+        const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 f = __half22float2(h[k]);
+            v[2 * k] = f.x; v[2 * k + 1] = f.y;
+        }
+        dst[i] = pack8(v);
+    }
+}
+
 static int ew_grid(long long n) {
     long long b = (n + 255) / 256;
     const long long cap = (long long)sm_count() * 16;
@@ -515,6 +638,79 @@ int launch_c8_to_nchw_bf16(const void *src, void *dst, int dst_dtype, int N, int
     if (dst_dtype == RVSR_BF16) c8_to_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const uint4 *)src, (__nv_bfloat16 *)dst, C, HW, planes);
     else if (dst_dtype == RVSR_F32) c8_to_nchw_kernel<float><<<grid, 256, 0, s>>>((const uint4 *)src, (float *)dst, C, HW, planes);
     else { set_error("c8 -> nchw: dtype %d", dst_dtype); return RVSR_E_INVALID; }
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+
+// ---------------------------------------------------------------- ModulatedDeformConvPack on C8 tensors
+// Shape class of every EDVR DCN with nf = 64: C = Cout = 64, 3x3, stride 1, pad 1, 8 deformable groups.
+size_t c8_mdcn_workspace_bytes(int N, int H, int W, int backward) {
+    const size_t px = (size_t)N * H * W;
+    if (!backward)
+        return 2 * align_up(px * 128, 256) + align_up(px * 768, 256) + align_up(tc_dcn_weight_bytes(64, 64, 9) + 16, 256) + 4096;
+    return align_up(px * 128, 256) + 2 * (align_up(px * 576, 256) + align_up(px * 288, 256)) + align_up(px * 256, 256) +
+           align_up(dcn_bwd_tc_wt_bytes(), 256) + align_up((size_t)64 * 64 * 9 * 2, 256) + 4096;
+}
+int c8_mdcn_fwd(const void *x, const void *om, const float *weight, const float *bias, void *y, int N, int H, int W, int act,
+                void *workspace, size_t workspace_bytes, cudaStream_t s) {
+    RVSR_CHECK_ARG(workspace_bytes >= c8_mdcn_workspace_bytes(N, H, W, 0), "c8 mdcn fwd: workspace too small");
+    if (N == 0) return RVSR_OK;
+    const size_t px = (size_t)N * H * W;
+    char *wsp = reinterpret_cast<char *>(workspace);
+    wsp += (256 - (size_t)((uintptr_t)wsp % 256)) % 256;
+    auto take = [&](size_t bytes) { char *r = wsp; wsp += align_up(bytes, 256); return r; };
+    void *x16 = take(px * 128), *y16 = take(px * 128), *om24 = take(px * 768), *wtc = take(tc_dcn_weight_bytes(64, 64, 9) + 16);
+    const int HW = H * W;
+    cvt_bf16_to_f16_kernel<<<ew_grid((long long)px * 8), 256, 0, s>>>((const uint4 *)x, (uint4 *)x16, (long long)px * 8);
+    om_from_c8_kernel<<<dim3((HW + 127) / 128, 8, N), 128, 0, s>>>((const __nv_bfloat16 *)om, (uint4 *)om24, nullptr, nullptr, HW);
+    RVSR_LAUNCH_CHECK();
+    RVSR_TRY(pack_weight_dcn_tc(weight, wtc, 64, 64, 9, s));
+    DcnOp op = {};
+    op.x = Src{x16, (long long)64 * HW, 64, 1, -1}; op.om24 = om24; op.om24_image_stride = (long long)8 * 24 * HW;
+    op.w_tc = wtc; op.bias = bias; op.out = y16; op.out_image_stride = (long long)64 * HW;
+    op.N = N; op.H = H; op.W = W; op.Cout = 64; op.kh = op.kw = 3; op.stride = 1; op.pad = 1; op.dil = 1; op.dg = 8;
+    op.act = act; op.out_mode = OUT_C8;
+    if (!tc_dcn_supported(op)) { set_error("c8 mdcn fwd: tcgen05 DCN kernel unavailable"); return RVSR_E_UNSUPPORTED; }
+    RVSR_TRY(launch_dcn_tc(op, s));
+    cvt_f16_to_bf16_kernel<<<ew_grid((long long)px * 8), 256, 0, s>>>((const uint4 *)y16, (uint4 *)y, (long long)px * 8);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+// g: gradient of y (after the activation, y = the forward output, needed only when act != none).  gx: [N][8][H][W][8] bf16,
+// gom: [N][32][H][W][8] bf16, gw: [64][64][3][3] fp32 and gb: [64] fp32 -- all WRITTEN (this call's values).
+int c8_mdcn_bwd(const void *x, const void *om, const float *weight, const void *g, const void *y, void *gx, void *gom, float *gw,
+                float *gb, int N, int H, int W, int act, void *workspace, size_t workspace_bytes, cudaStream_t s) {
+    RVSR_CHECK_ARG(workspace_bytes >= c8_mdcn_workspace_bytes(N, H, W, 1), "c8 mdcn bwd: workspace too small");
+    RVSR_CHECK_ARG(act == RVSR_ACT_NONE || y != nullptr, "c8 mdcn bwd: the activation gradient needs the forward output");
+    RVSR_CUDA(cudaMemsetAsync(gw, 0, (size_t)64 * 64 * 9 * 4, s));
+    if (gb != nullptr) RVSR_CUDA(cudaMemsetAsync(gb, 0, 64 * 4, s));
+    if (N == 0) return RVSR_OK;
+    const size_t px = (size_t)N * H * W;
+    char *wsp = reinterpret_cast<char *>(workspace);
+    wsp += (256 - (size_t)((uintptr_t)wsp % 256)) % 256;
+    auto take = [&](size_t bytes) { char *r = wsp; wsp += align_up(bytes, 256); return r; };
+    void *gact = take(px * 128);
+    float *off32 = (float *)take(px * 576), *msk32 = (float *)take(px * 288), *goff32 = (float *)take(px * 576), *gmsk32 = (float *)take(px * 288);
+    float *gx32 = (float *)take(px * 256);
+    void *wt = take(dcn_bwd_tc_wt_bytes()), *wbf = take((size_t)64 * 64 * 9 * 2);
+    const int HW = H * W;
+    const void *gp = g;
+    if (act != RVSR_ACT_NONE) {
+        RVSR_TRY(launch_act_bwd_c8(g, y, gact, (long long)px * 64, act, s));
+        gp = gact;
+    }
+    om_from_c8_kernel<<<dim3((HW + 127) / 128, 8, N), 128, 0, s>>>((const __nv_bfloat16 *)om, nullptr, off32, msk32, HW);
+    RVSR_LAUNCH_CHECK();
+    RVSR_TRY(launch_convert_f32_bf16(weight, wbf, 64 * 64 * 9, s));
+    RVSR_TRY(pack_wt_dcn_bwd_tc(wbf, wt, s));
+    RVSR_CUDA(cudaMemsetAsync(gx32, 0, px * 256, s));
+    RVSR_TRY(launch_dcn_bwd_tc_core(x, gp, off32, msk32, wt, gx32, goff32, gmsk32, gw, N, H, W, s));
+    if (gb != nullptr) {
+        bias_grad_c8_kernel<<<dim3(HW >= 4096 ? 16 : 1, 8, N < 8 ? N : 8), 256, 0, s>>>((const uint4 *)gp, gb, HW, N);
+        RVSR_LAUNCH_CHECK();
+    }
+    RVSR_TRY(launch_convert_f32_bf16(gx32, gx, (long long)px * 64, s));
+    om_grad_to_c8_kernel<<<dim3((HW + 127) / 128, 32, N), 128, 0, s>>>(goff32, gmsk32, msk32, (uint4 *)gom, HW);
     RVSR_LAUNCH_CHECK();
     return RVSR_OK;
 }

@@ -231,6 +231,49 @@ def conv(xs, weight, bias=None, act=None, residual=None, shuffle=False):
     return _ConvC8.apply(weight, bias, residual, ACT[act], bool(shuffle), *xs)
 
 
+# ---------------------------------------------------------------- modulated deformable convolution pack
+class _DcnPackC8(torch.autograd.Function):
+    """y = act(dcn(x, offset, sigmoid(mask)) + bias) with offset / mask taken from `om`, the 256-channel C8 output of the
+    conv_offset_mask convolution (ModulatedDeformConvPack.forward, deform_conv.py:274-292)."""
+
+    @staticmethod
+    def forward(ctx, x, om, weight, bias, act):
+        x, om = _check_c8(x, "dcn_pack_c8 x"), _check_c8(om, "dcn_pack_c8 om")
+        N, P, H, W, _ = x.shape
+        if P != 8 or om.shape[1] != 32 or tuple(weight.shape) != (64, 64, 3, 3) or weight.dtype != torch.float32:
+            raise NotImplementedError("dcn_pack_c8: built for 64 -> 64 channels, 3x3, 8 deformable groups, fp32 parameters")
+        weight = weight.contiguous()
+        y = torch.empty_like(x)
+        L = _lib.lib()
+        with torch.cuda.device(x.device):
+            ws = torch.empty(L.rvsr_c8_mdcn_workspace_bytes(N, H, W, 0), dtype=torch.uint8, device=x.device)
+            _lib.check(L.rvsr_c8_mdcn_fwd(_p(x), _p(om), _p(weight), _p(bias), _p(y), N, H, W, act, _p(ws), ws.numel(), _stream(x.device)),
+                       "c8_mdcn_fwd")
+        ctx.act, ctx.with_bias = act, bias is not None
+        ctx.save_for_backward(x, om, weight, *([y] if act != _lib.ACT_NONE else []))
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, om, weight = ctx.saved_tensors[:3]
+        y = ctx.saved_tensors[3] if ctx.act != _lib.ACT_NONE else None
+        g = _check_c8(g, "dcn_pack_c8 backward")
+        N, _, H, W, _ = x.shape
+        gx, gom = torch.empty_like(x), torch.empty_like(om)
+        gw = torch.empty_like(weight)
+        gb = torch.empty(64, dtype=torch.float32, device=x.device) if ctx.with_bias else None
+        L = _lib.lib()
+        with torch.cuda.device(x.device):
+            ws = torch.empty(L.rvsr_c8_mdcn_workspace_bytes(N, H, W, 1), dtype=torch.uint8, device=x.device)
+            _lib.check(L.rvsr_c8_mdcn_bwd(_p(x), _p(om), _p(weight), _p(g), _p(y), _p(gx), _p(gom), _p(gw), _p(gb), N, H, W, ctx.act,
+                                          _p(ws), ws.numel(), _stream(x.device)), "c8_mdcn_bwd")
+        return gx, gom, gw, gb, None
+
+
+def dcn_pack(x, om, weight, bias=None, act=None):
+    return _DcnPackC8.apply(x, om, weight, bias, ACT[act])
+
+
 # ---------------------------------------------------------------- x2 bilinear upsample (optionally scaled)
 class _Up2C8(torch.autograd.Function):
     @staticmethod

@@ -169,3 +169,39 @@ def test_layout_with_spare_channel_blocks():
     (y * w).sum().backward()
     back = T.from_c8(c.grad, 32, torch.float32)
     assert torch.equal(back[:, :20], w) and float(back[:, 20:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("act", [None, "lrelu"])
+def test_dcn_pack_c8_against_the_nchw_operator(act):
+    """train_c8.dcn_pack (C8 tensors, sigmoid / chunk inside) against ModulatedDeformConvFunction on NCHW bf16 tensors -- the
+    operator tests/test_gpu_dcn.py pins to the C oracle and the float64 gradients -- forward and all five gradients."""
+    from realvsr_b200 import train_c8 as T
+    from realvsr_b200.archs.dcn.deform_conv import modulated_deform_conv
+    g = torch.Generator(device="cuda").manual_seed(11)
+    N, H, W = 3, 20, 40
+    x = _r(torch.randn(N, 64, H, W, device="cuda", generator=g)).requires_grad_()
+    om = torch.zeros(N, 256, H, W, device="cuda")
+    om[:, :144] = torch.randn(N, 144, H, W, device="cuda", generator=g) * 2.0
+    om[:, 144:216] = torch.randn(N, 72, H, W, device="cuda", generator=g)
+    om = _r(om).requires_grad_()
+    w = _r(torch.randn(64, 64, 3, 3, device="cuda", generator=g) * 0.05).requires_grad_()
+    b = _r(torch.randn(64, device="cuda", generator=g) * 0.1).requires_grad_()  # bf16-exact: the NCHW operator rounds its bias to bf16
+    gy = _r(torch.randn(N, 64, H, W, device="cuda", generator=g))
+    # reference: the NCHW operator in bf16 (tensor-core kernels, fp32 master weights as under autocast)
+    y_ref = modulated_deform_conv(x.bfloat16(), om[:, :144].bfloat16(), torch.sigmoid(om[:, 144:216]).bfloat16(), w, b, 1, 1, 1, 1, 8).float()
+    x2, om2, w2, b2 = [t.detach().clone().requires_grad_() for t in (x, om, w, b)]
+    y = T.from_c8(T.dcn_pack(T.to_c8(x2), T.to_c8(om2), w2, b2, act), 64, torch.float32)
+    if act:
+        # the NCHW operator receives the mask rounded to bf16, the C8 operator computes the sigmoid itself: outputs differ by
+        # ~1e-3, which flips the LeakyReLU branch of the ~1e-3 of outputs that close to zero.  Same branch for both (see
+        # test_conv_forward_backward).
+        pos = y.detach() > 0
+        assert float((pos != (y_ref.detach() > 0)).float().mean()) < 5e-3
+        y_ref = y_ref * torch.where(pos, 1.0, 0.1)
+    ref = torch.autograd.grad(y_ref, [x, om, w, b], gy)
+    assert _rel(y, y_ref.detach()) < 1e-2
+    got = torch.autograd.grad(y, [x2, om2, w2, b2], gy)
+    for name, a, r in zip(("dx", "dom", "dw", "db"), got, ref):
+        assert a.shape == r.shape
+        assert _rel(a, r) < 2e-2, (name, _rel(a, r))
+    assert float(got[1][:, 216:].abs().max()) == 0.0
