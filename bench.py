@@ -161,11 +161,15 @@ def cfg4_time(dev):
 
 def cfg5_time(dev):
     """BASELINE cfg5: one training step -- batch 16 of 5x3x64x64 patches, EDVR nf=64, forward + L1 loss + backward (no
-    optimizer), under torch.autocast(bfloat16) and in fp32.  Module path: torch's convolutions (cuDNN, exactly where the
-    reference uses nn.Conv2d) + this repo's DCN operator forward / backward (bf16: dcn_bwd_tc_kernel on tcgen05)."""
+    optimizer).  bf16_c8_*: under torch.autocast(bfloat16) the module routes through realvsr_b200/train_c8.py -- every
+    convolution forward / data gradient / weight gradient and the DCN operator on this library's tcgen05 kernels
+    (channel-blocked bf16 tensors); `graph` replays the whole step as one CUDA graph (train_c8.GraphedStep), `eager` issues
+    its ~1000 launches from Python.  bf16_cudnn_*: the same step on the nn.Module graph (torch's cuDNN convolutions + this
+    repo's DCN operator), the round-1/2 path, for comparison.  fp32: module path, CUDA-core DCN kernels (gradient parity)."""
     import torch
     import torch.nn.functional as F
     from helpers import edvr_state_shapes
+    from realvsr_b200 import train_c8
     from realvsr_b200.archs import EDVR_arch as E
     from synth import synth_input, synth_state_dict
     try:
@@ -176,24 +180,38 @@ def cfg5_time(dev):
         gt = synth_input((16, 3, 256, 256), 10).to(dev)
         out = dict(workload="B=16, 5x3x64x64 -> 256x256, forward + L1 + backward, no optimizer step; SURVEY 8d floor 2.0 ms",
                    unit="ms/step")
-        for name, amp in (("bf16_autocast", True), ("fp32", False), ("bf16_autocast_channels_last", True)):
-            if name.endswith("channels_last"):  # user-side cuDNN setting: no NCHW <-> NHWC transposes around every convolution
-                net = net.to(memory_format=torch.channels_last)
+
+        def timed(step, n=5):
+            for _ in range(2):
+                step()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                loss = step()
+            e1.record()
+            torch.cuda.synchronize()
+            return dict(ms=e0.elapsed_time(e1) / n, loss=float(loss.detach()))
+
+        def eager(amp):
             def step():
                 net.zero_grad(set_to_none=True)
                 with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
                     loss = F.l1_loss(net(x).float(), gt)
                 loss.backward()
                 return loss
-            for _ in range(2):
-                step()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(3):
-                loss = step()
-            e1.record()
-            torch.cuda.synchronize()
-            out[name] = dict(ms=e0.elapsed_time(e1) / 3, loss=float(loss.detach()))
+            return step
+
+        net.exec_path = "auto"
+        gs = train_c8.GraphedStep(net, F.l1_loss, x, gt)
+        out["bf16_c8_graph"] = timed(lambda: gs(x, gt))
+        del gs
+        net.zero_grad(set_to_none=True)
+        out["bf16_c8_eager"] = timed(eager(True))
+        net.exec_path = "module"
+        out["bf16_cudnn_autocast"] = timed(eager(True), 3)
+        out["fp32"] = timed(eager(False), 3)
+        net = net.to(memory_format=torch.channels_last)  # user-side cuDNN setting: no NCHW <-> NHWC transposes around every convolution
+        out["bf16_cudnn_autocast_channels_last"] = timed(eager(True), 3)
         del net, x, gt
         torch.cuda.empty_cache()
         return out

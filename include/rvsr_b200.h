@@ -119,8 +119,9 @@ int rvsr_conv2d_fwd(const void *x1, const void *x2, const void *weight, const vo
  *                             tiles); 3 packs both.
  *   rvsr_c8_conv_fwd          y = act(conv(cat(x[0..nsrc)), w) + bias) [+ residual], optional fused PixelShuffle(2); nsrc sources
  *                             of C channels each (C % 16 == 0, C <= 64); also runs every data gradient (with mode-1 weights).
- *   rvsr_c8_conv_wgrad        dw_t[tap][ci][co] += sum_pixels x[pixel + tap][ci] * g[pixel][co] (fp32, [9][64][Cout], zeroed by the
- *                             caller; the OIHW gradient is its transpose), db[co] += sum_pixels g (may be NULL).  Cin = 64, 3x3.
+ *   rvsr_c8_conv_wgrad        gw[co][c0 + ci][ky][kx] = sum_pixels x[pixel + (ky, kx) - pad][ci] * g[pixel][co] for the 64 input
+ *                             channels of source x (OIHW fp32 [Cout][cin_total][ks][ks]; written, fixed summation order),
+ *                             db[co] = sum_pixels g (may be NULL).  Cin = 64 per call, ks in {1, 3}.
  *   rvsr_c8_act_bwd           out = y > 0 ? g : slope * g  (LeakyReLU(0.1) / ReLU given the layer OUTPUT y)
  *   rvsr_c8_unshuffle2_act_bwd  gradient through lrelu(PixelShuffle(2)(.)): g, y [N][C/4 ch][2H][2W] -> out [N][C ch][H][W]
  *   rvsr_c8_upsample2x        bilinear x2 (align_corners=False) times `scale`, or (backward = 1) its adjoint. */
@@ -134,8 +135,9 @@ int rvsr_c8_conv_pack_weight(const float *weight, void *dst, int Cout, int Cin, 
 int rvsr_c8_conv_fwd(const void *const *x, const long long *x_image_stride, int nsrc, int C, const void *w_packed, const float *bias,
                      const void *residual, void *y, int N, int H, int W, int Cout, int ks, int stride, int act, int shuffle,
                      void *stream);
-int rvsr_c8_conv_wgrad(const void *x, long long x_image_stride, const void *g, float *dw_t, float *db, int N, int H, int W, int Cin,
-                       int Cout, int ks, void *stream);
+size_t rvsr_c8_conv_wgrad_workspace_bytes(int N, int H, int W, int Cout);
+int rvsr_c8_conv_wgrad(const void *x, long long x_image_stride, const void *g, float *gw, float *db, int N, int H, int W, int Cin,
+                       int Cout, int ks, int cin_total, int c0, void *workspace, size_t workspace_bytes, void *stream);
 int rvsr_c8_act_bwd(const void *g, const void *y, void *out, long long n_elems, int act, void *stream);
 int rvsr_c8_unshuffle2_act_bwd(const void *g, const void *y, void *out, int N, int C, int H, int W, int act, void *stream);
 int rvsr_c8_upsample2x(const void *src, void *dst, long long planes, int H, int W, float scale, int backward, void *stream);

@@ -52,8 +52,8 @@ struct alignas(64) WgradParams {
     const uint4 *x;            // C8 bf16: 16-byte cells [N][planes][H][W]
     long long x_image_stride;  // cells between images
     int g_planes;              // channel blocks per image of g
-    float *dw;                 // [9][64][Cout] fp32, accumulated into
-    float *db;                 // [Cout] fp32 or null, accumulated into
+    float *partial;            // [passes][CTAs][6][128][64] fp32: every CTA's accumulators (summed by wgrad_reduce_kernel)
+    float *bias_partial;       // [passes][CTAs][64] fp32 or null
     int Cout, N, H, W;
     int tiles_x, tiles_y, num_tiles;
     TileDiv td;
@@ -61,9 +61,6 @@ struct alignas(64) WgradParams {
     int debug;  // RVSR_WG_DEBUG, timing experiments only (results become garbage): 1 = issue no MMAs, 2 = no halo loads / stores
 };
 
-__device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
 // kind::f16 with bf16 A / B, fp32 D, both operands MN-major
 __host__ __device__ constexpr uint32_t wg_idesc(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -75,6 +72,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
     uint64_t *bars = reinterpret_cast<uint64_t *>(stage_s + WG_STAGES * WG_STAGE);
     constexpr int B_FULL = 0, B_EMPTY = WG_STAGES, B_DONE = 2 * WG_STAGES, B_COUNT = B_DONE + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + B_COUNT);
+    float *bias_s = reinterpret_cast<float *>(tmem_slot + 4);  // 2 x 64 floats
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
     const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -151,30 +149,28 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
                 store_tile(t + 1, vb);
             }
         }
-        // ---- flush: D row m = (tap half, ci), column = co.  Warps 0-7: TMEM lane quarter warp & 3, column half warp >> 2.
+        // ---- flush: D row m = (tap half, ci), column = co, to this CTA's slice of `partial` (plain stores: 148 CTAs adding into the
+        // same 36 864 addresses with red.global cost ~25 us per launch).  Warps 0-7: TMEM lane quarter warp & 3, column half warp >> 2.
         if (T > 0) {
             mbar_wait(BAR(B_DONE), 0);
             tc_fence_after();
             const int q = warp & 3, hf = warp >> 2;
-            const int m = q * 32 + lane, ci = m & 63, uphalf = m >> 6;
-            const int co0 = pass * 64 + hf * 32;
+            const int m = q * 32 + lane;
+            float *part = p.partial + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 6 * 128 + m) * 64 + hf * 32;
 #pragma unroll 1
             for (int b = 0; b < 6; ++b) {
                 if (b >= 3 && q >= 2) break;  // rows 64-127 of the dy = +1 accumulators are not weights
                 if (p.ks == 1 && (b != 1 || q < 2)) continue;  // 1x1: the centre tap only
-                const int tap = p.ks == 1 ? 0 : (b < 3 ? uphalf * 3 + b : 6 + (b - 3));
                 uint32_t a0[16], a1[16];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 64 + hf * 32);
                 tmem_ld16_nowait(taddr, a0);
                 tmem_ld16_nowait(taddr + 16, a1);
                 tmem_ld_wait();
-                float *d = p.dw + ((long long)tap * 64 + ci) * p.Cout + co0;  // [taps][64][Cout]
+                float4 *d = reinterpret_cast<float4 *>(part + (size_t)b * 128 * 64);
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    if (co0 + j < p.Cout)
-                        red_add_v4(d + j, __uint_as_float(a0[j]), __uint_as_float(a0[j + 1]), __uint_as_float(a0[j + 2]), __uint_as_float(a0[j + 3]));
-                    if (co0 + 16 + j < p.Cout)
-                        red_add_v4(d + 16 + j, __uint_as_float(a1[j]), __uint_as_float(a1[j + 1]), __uint_as_float(a1[j + 2]), __uint_as_float(a1[j + 3]));
+                for (int j = 0; j < 4; ++j) {
+                    d[j] = make_float4(__uint_as_float(a0[4 * j]), __uint_as_float(a0[4 * j + 1]), __uint_as_float(a0[4 * j + 2]), __uint_as_float(a0[4 * j + 3]));
+                    d[4 + j] = make_float4(__uint_as_float(a1[4 * j]), __uint_as_float(a1[4 * j + 1]), __uint_as_float(a1[4 * j + 2]), __uint_as_float(a1[4 * j + 3]));
                 }
             }
         }
@@ -217,43 +213,82 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
         if (T > 0 && elect_one()) umma_commit(BAR(B_DONE));
         __syncwarp();
     } else {
-        // ---- bias gradient: column sums of the g tiles (pixels outside the image arrive as zeros)
-        const int j = (warp - WG_WARP_BIAS0) * 32 + lane;  // 0 .. 63: channel block j / 8, pixels (j % 8) * 16 ..
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        // ---- bias gradient: column sums of the g tiles (pixels outside the image arrive as zeros).  64 threads walk the tile's
+        // 1024 16-byte cells with consecutive lanes on consecutive cells (a strided walk made these loads 32-way bank
+        // conflicts that saturated the LSU pipe the halo producers share -- ncu, profiles/r02_ncu_conv_wgrad.txt).
+        const int j = (warp - WG_WARP_BIAS0) * 32 + lane;  // 0 .. 63
+        float acc[8][8];                                    // [channel block][channel]
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[q][k] = 0.f;
         for (int t = 0; t < T; ++t) {
             const int st = t % WG_STAGES;
             mbar_wait_sleep(BAR(B_FULL + st), (t / WG_STAGES) & 1, 200);
-            if (p.db != nullptr) {
-                const uint4 *g = reinterpret_cast<const uint4 *>(stage_s + st * WG_STAGE) + (j >> 3) * 128 + (j & 7) * 16;
+            if (p.bias_partial != nullptr) {
+                const uint4 *g = reinterpret_cast<const uint4 *>(stage_s + st * WG_STAGE) + j;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const uint4 u = g[i];
+                for (int i = 0; i < 16; ++i) {  // cell i * 64 + j: channel block i / 2
+                    const uint4 u = g[i * 64];
                     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        acc[2 * k] += __uint_as_float(w[k] << 16);
-                        acc[2 * k + 1] += __uint_as_float(w[k] & 0xffff0000u);
+                        acc[i >> 1][2 * k] += __uint_as_float(w[k] << 16);
+                        acc[i >> 1][2 * k + 1] += __uint_as_float(w[k] & 0xffff0000u);
                     }
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(B_EMPTY + st));
         }
-        if (p.db != nullptr && T > 0) {
+        if (p.bias_partial != nullptr) {
+            float *bp = p.bias_partial + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 64;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                float s = acc[k];
-                s += __shfl_xor_sync(0xffffffffu, s, 1);
-                s += __shfl_xor_sync(0xffffffffu, s, 2);
-                s += __shfl_xor_sync(0xffffffffu, s, 4);
-                const int co = pass * 64 + (j >> 3) * 8 + k;
-                if ((j & 7) == 0 && co < p.Cout) atomicAdd(p.db + co, s);
-            }
+            for (int q = 0; q < 8; ++q)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    float s = acc[q][k];
+                    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                    if (lane == 0) bias_s[(warp - WG_WARP_BIAS0) * 64 + q * 8 + k] = s;
+                }
+            asm volatile("bar.sync 1, 64;" ::: "memory");  // the two bias warps
+            bp[j] = bias_s[j] + bias_s[64 + j];
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == WG_WARP_MMA) tmem_dealloc(tmem_base, 512);
+}
+
+// Sum of the CTAs' accumulators -> the OIHW weight gradient gw[co][c0 + ci][ky][kx] (written, fp32) and db[co].  One thread per
+// (tap, ci, co) with co fastest: the reads of every partial are coalesced, the sum order is fixed (bit-reproducible gradients,
+// which atomics would not give).
+__global__ void wgrad_reduce_kernel(const float *__restrict__ partial, const float *__restrict__ bias_partial, float *__restrict__ gw,
+                                    float *__restrict__ db, int ctas, int Cout, int cin_total, int c0, int ks) {
+    const int KK = ks * ks;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < KK * 64 * Cout) {
+        const int co = idx % Cout, ci = (idx / Cout) % 64, tap = idx / (Cout * 64);
+        int b, m;
+        if (ks == 1) { b = 1; m = 64 + ci; }
+        else if (tap < 6) { b = tap % 3; m = (tap / 3) * 64 + ci; }
+        else { b = 3 + tap % 3; m = ci; }
+        const float *src = partial + ((size_t)(co >> 6) * ctas * 6 * 128 + (size_t)b * 128 + m) * 64 + (co & 63);
+        float s0 = 0.f, s1 = 0.f;
+        int c = 0;
+        for (; c + 1 < ctas; c += 2) {
+            s0 += src[(size_t)c * 6 * 128 * 64];
+            s1 += src[(size_t)(c + 1) * 6 * 128 * 64];
+        }
+        if (c < ctas) s0 += src[(size_t)c * 6 * 128 * 64];
+        gw[((size_t)co * cin_total + c0 + ci) * KK + tap] = s0 + s1;
+    }
+    if (db != nullptr && idx < Cout) {
+        const float *src = bias_partial + (size_t)(idx >> 6) * ctas * 64 + (idx & 63);
+        float s_ = 0.f;
+        for (int c = 0; c < ctas; ++c) s_ += src[(size_t)c * 64];
+        db[idx] = s_;
+    }
 }
 
 // ---------------------------------------------------------------- small CUDA-core kernels (bf16, 16-byte cells)
@@ -545,12 +580,31 @@ bool conv_wgrad_tc_supported(int Cin, int ks, int stride) {
     return Cin == 64 && (ks == 3 || ks == 1) && stride == 1 && get_encode() != nullptr;
 }
 
-// dw: [ks * ks][64][Cout] fp32 and db: [Cout] fp32 (or null), both ACCUMULATED into (the caller zeroes them).
-int launch_conv_wgrad_tc(const void *x_c8, long long x_image_stride, const void *g_c8, float *dw, float *db, int N, int H, int W,
-                         int Cout, int ks, cudaStream_t s) {
+static int wgrad_ctas(int num_tiles, int passes) {
+    static const int tpc = getenv("RVSR_WG_TPC") ? atoi(getenv("RVSR_WG_TPC")) : 6;
+    int gx = num_tiles / (tpc > 0 ? tpc : 1);  // tiles per CTA below which more CTAs stop paying (prologue + flush + reduce)
+    const int cap = sm_count() / passes > 0 ? sm_count() / passes : 1;
+    if (gx > cap) gx = cap;
+    return gx < 1 ? 1 : gx;
+}
+size_t conv_wgrad_tc_workspace_bytes(int N, int H, int W, int Cout) {
+    const int passes = cdiv(Cout, 64), tiles = cdiv(W, TC_TW) * cdiv(H, TC_ROWS) * N;
+    const size_t ctas = (size_t)wgrad_ctas(tiles, passes) * passes;
+    return align_up(ctas * 6 * 128 * 64 * 4, 256) + align_up(ctas * 64 * 4, 256) + 512;
+}
+// gw: OIHW fp32 [Cout][cin_total][ks][ks], the slice of input channels [c0, c0 + 64) is WRITTEN; db: [Cout] fp32 or null, written.
+int launch_conv_wgrad_tc(const void *x_c8, long long x_image_stride, const void *g_c8, float *gw, float *db, int N, int H, int W,
+                         int Cout, int ks, int cin_total, int c0, void *workspace, size_t workspace_bytes, cudaStream_t s) {
     RVSR_CHECK_ARG(Cout > 0 && Cout % 8 == 0, "conv wgrad: Cout %d is not a multiple of 8", Cout);
     RVSR_CHECK_ARG(x_image_stride % 8 == 0, "conv wgrad: image stride");
-    if (N == 0) return RVSR_OK;
+    RVSR_CHECK_ARG(c0 >= 0 && c0 + 64 <= cin_total, "conv wgrad: channel slice");
+    RVSR_CHECK_ARG(workspace_bytes >= conv_wgrad_tc_workspace_bytes(N, H, W, Cout), "conv wgrad: workspace too small");
+    if (N == 0) {
+        RVSR_CHECK_ARG(c0 == 0 && cin_total == 64, "conv wgrad: empty batch with a channel slice");
+        RVSR_CUDA(cudaMemsetAsync(gw, 0, (size_t)Cout * 64 * ks * ks * 4, s));
+        if (db) RVSR_CUDA(cudaMemsetAsync(db, 0, (size_t)Cout * 4, s));
+        return RVSR_OK;
+    }
     EncodeTiledFn enc = get_encode();
     RVSR_CHECK_ARG(enc != nullptr, "conv wgrad: cuTensorMapEncodeTiled unavailable");
     WgradParams p;
@@ -566,22 +620,24 @@ int launch_conv_wgrad_tc(const void *x_c8, long long x_image_stride, const void 
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("conv wgrad: cuTensorMapEncodeTiled failed (%d)", (int)r); return RVSR_E_CUDA; }
     }
+    p.tiles_x = cdiv(W, TC_TW); p.tiles_y = cdiv(H, TC_ROWS); p.num_tiles = p.tiles_x * p.tiles_y * N;
+    const int passes = cdiv(Cout, 64), gx = wgrad_ctas(p.num_tiles, passes);
+    char *wsp = reinterpret_cast<char *>(workspace);
+    wsp += (256 - (size_t)((uintptr_t)wsp % 256)) % 256;
+    p.partial = reinterpret_cast<float *>(wsp);
+    p.bias_partial = db != nullptr ? reinterpret_cast<float *>(wsp + align_up((size_t)gx * passes * 6 * 128 * 64 * 4, 256)) : nullptr;
     p.x = reinterpret_cast<const uint4 *>(x_c8); p.x_image_stride = x_image_stride / 8; p.g_planes = gpl;
-    p.dw = dw; p.db = db; p.Cout = Cout; p.N = N; p.H = H; p.W = W; p.ks = ks;
+    p.Cout = Cout; p.N = N; p.H = H; p.W = W; p.ks = ks;
     static const int dbg = getenv("RVSR_WG_DEBUG") ? atoi(getenv("RVSR_WG_DEBUG")) : 0;
     p.debug = dbg;
-    p.tiles_x = cdiv(W, TC_TW); p.tiles_y = cdiv(H, TC_ROWS); p.num_tiles = p.tiles_x * p.tiles_y * N;
     p.td.tpi = (uint32_t)(p.tiles_x * p.tiles_y); p.td.m_tpi = magic_div(p.td.tpi, (uint32_t)p.num_tiles);
     p.td.tx = (uint32_t)p.tiles_x; p.td.m_tx = magic_div(p.td.tx, p.td.tpi);
-    const int passes = cdiv(Cout, 64);
-    const size_t smem = (size_t)WG_STAGES * WG_STAGE + 8 * 16 + 1024;
+    const size_t smem = (size_t)WG_STAGES * WG_STAGE + 8 * 16 + 2 * 64 * 4 + 1024;
     RVSR_TRY(ensure_max_dynamic_smem(reinterpret_cast<const void *>(&conv_wgrad_tc_kernel), (int)smem));
-    // every CTA ends with a 36 864-float atomic flush: few tiles -> fewer CTAs
-    int gx = p.num_tiles / 6;
-    const int cap = sm_count() / passes > 0 ? sm_count() / passes : 1;
-    if (gx > cap) gx = cap;
-    if (gx < 1) gx = 1;
     conv_wgrad_tc_kernel<<<dim3(gx, passes), WG_THREADS, smem, s>>>(p);
+    RVSR_LAUNCH_CHECK();
+    const int total = ks * ks * 64 * Cout;
+    wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, s>>>(p.partial, p.bias_partial, gw, db, gx, Cout, cin_total, c0, ks);
     RVSR_LAUNCH_CHECK();
     return RVSR_OK;
 }

@@ -200,13 +200,12 @@ class _ConvC8(torch.autograd.Function):
             if needs[0] or needs[1]:
                 if C != 64:
                     raise NotImplementedError("conv_c8: the weight gradient is built for 64-channel sources")
-                nw = nsrc * ks * ks * 64 * Cout
-                zb = torch.zeros(nw + Cout, dtype=torch.float32, device=dev)   # one fill for both accumulators
-                dwt, gb = zb[:nw].view(nsrc, ks * ks, 64, Cout), (zb[nw:] if needs[1] else None)
+                gw = torch.empty((Cout, nsrc * C, ks, ks), dtype=torch.float32, device=dev)
+                gb = torch.empty(Cout, dtype=torch.float32, device=dev) if needs[1] else None
+                ws = torch.empty(L.rvsr_c8_conv_wgrad_workspace_bytes(N, H, W, Cout), dtype=torch.uint8, device=dev)
                 for i, x in enumerate(xs):
-                    _lib.check(L.rvsr_c8_conv_wgrad(_p(x), x.stride(0), _p(gp), _p(dwt[i]), _p(gb if i == 0 else None), N, H, W, C,
-                                                    Cout, ks, s), "c8_conv_wgrad")
-                gw = dwt.permute(3, 0, 2, 1).reshape(Cout, nsrc * C, ks, ks)  # [Cout][source][ci][tap]
+                    _lib.check(L.rvsr_c8_conv_wgrad(_p(x), x.stride(0), _p(gp), _p(gw), _p(gb if i == 0 else None), N, H, W, C, Cout, ks,
+                                                    nsrc * C, i * C, _p(ws), ws.numel(), s), "c8_conv_wgrad")
                 if not needs[0]:
                     gw = None
             gxs = [None] * nsrc
