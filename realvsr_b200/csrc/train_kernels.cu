@@ -31,12 +31,13 @@ namespace {
 //                row 0 -- so one M = 128 instruction covers taps (dy, dx) [rows 0-63] and (dy + 1, dx) [rows 64-127] of all 64
 //                input channels.  A tap is a shifted start address, exactly as in the forward kernels.  The halo is 34 pixels
 //                wide (K steps must not wrap at dx = +1), which no dense TMA box delivers (<= 256 elements per dimension), so
-//                eight producer warps assemble it with 16-byte loads (zero fill outside the image) and write both copies.
+//                sixteen producer warps assemble it with 16-byte loads (zero fill outside the image) and write both copies.
 //   D          = six 128 x 64 fp32 accumulators in TMEM, resident over ALL tiles of the CTA: (dy -1|0, dx -1), (.., dx 0),
 //                (.., dx +1), then (dy +1|unused, dx -1..+1): 6 instructions per K step for 9 taps (75 % useful rows).
 // One red.global.add.v4.f32 pass per CTA at the end into dW^T [9][64][Cout] fp32 (zeroed by the caller).  The bias gradient
 // (column sums of g) is taken from the g tiles in shared memory by two otherwise idle warps.
-constexpr int WG_PROD_WARPS = 8, WG_WARP_TMA = 8, WG_WARP_MMA = 9, WG_WARP_BIAS0 = 10, WG_BIAS_WARPS = 2;
+constexpr int WG_PROD_WARPS = 16, WG_WARP_TMA = 16, WG_WARP_MMA = 17, WG_WARP_BIAS0 = 18, WG_BIAS_WARPS = 2;
+constexpr int WG_AHEAD = 4;  // register sets of a producer thread = halo tiles whose loads are in flight ahead of the shared-memory ring
 constexpr int WG_THREADS = 32 * (WG_WARP_BIAS0 + WG_BIAS_WARPS);
 constexpr int WG_XCOLS = 34, WG_XROWS = 6;
 constexpr int WG_XPLANE = WG_XROWS * WG_XCOLS * 16;  // 3264 B per channel block
@@ -139,19 +140,25 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(B_FULL + st));
         };
-        uint4 va[WG_PER_THREAD], vb[WG_PER_THREAD];
-        if (T > 0) load_tile(0, va);
-        for (int t = 0; t < T; t += 2) {
-            if (t + 1 < T) load_tile(t + 1, vb);
-            store_tile(t, va);
-            if (t + 1 < T) {
-                if (t + 2 < T) load_tile(t + 2, va);
-                store_tile(t + 1, vb);
+        // WG_AHEAD tiles of loads in flight per thread: with few tiles per CTA (the 16-image layers) the kernel is bound by
+        // the latency of these loads, not by their bandwidth
+        uint4 v[WG_AHEAD][WG_PER_THREAD];
+#pragma unroll
+        for (int k = 0; k < WG_AHEAD - 1; ++k)
+            if (k < T) load_tile(k, v[k]);
+        for (int t0 = 0; t0 < T; t0 += WG_AHEAD) {
+#pragma unroll
+            for (int k = 0; k < WG_AHEAD; ++k) {
+                const int t = t0 + k;
+                if (t < T) {
+                    if (t + WG_AHEAD - 1 < T) load_tile(t + WG_AHEAD - 1, v[(k + WG_AHEAD - 1) % WG_AHEAD]);
+                    store_tile(t, v[k]);
+                }
             }
         }
         // ---- flush: D row m = (tap half, ci), column = co, to this CTA's slice of `partial` (plain stores: 148 CTAs adding into the
         // same 36 864 addresses with red.global cost ~25 us per launch).  Warps 0-7: TMEM lane quarter warp & 3, column half warp >> 2.
-        if (T > 0) {
+        if (T > 0 && warp < 8) {
             mbar_wait(BAR(B_DONE), 0);
             tc_fence_after();
             const int q = warp & 3, hf = warp >> 2;
@@ -260,29 +267,49 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
     if (warp == WG_WARP_MMA) tmem_dealloc(tmem_base, 512);
 }
 
-// Sum of the CTAs' accumulators -> the OIHW weight gradient gw[co][c0 + ci][ky][kx] (written, fp32) and db[co].  One thread per
-// (tap, ci, co) with co fastest: the reads of every partial are coalesced, the sum order is fixed (bit-reproducible gradients,
-// which atomics would not give).
-__global__ void wgrad_reduce_kernel(const float *__restrict__ partial, const float *__restrict__ bias_partial, float *__restrict__ gw,
-                                    float *__restrict__ db, int ctas, int Cout, int cin_total, int c0, int ks) {
-    const int KK = ks * ks;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < KK * 64 * Cout) {
-        const int co = idx % Cout, ci = (idx / Cout) % 64, tap = idx / (Cout * 64);
+// Sum of the CTAs' accumulators -> the OIHW weight gradient gw[co][c0 + ci][ky][kx] (written, fp32) and db[co].  A block = 64
+// groups of 4 consecutive output channels x 4 slices of the CTA range: 16-byte loads, 4 in flight per thread (the partials are
+// up to 29 MB, mostly L2-resident: memory-level parallelism is what this kernel needs), then a fixed-order sum of the 4 slices
+// (bit-reproducible gradients, which atomics would not give).
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float *__restrict__ partial, const float *__restrict__ bias_partial,
+                                                           float *__restrict__ gw, float *__restrict__ db, int ctas, int Cout, int cin_total,
+                                                           int c0, int ks) {
+    const int KK = ks * ks, Cq = Cout / 4;
+    const int grp = blockIdx.x * 64 + (threadIdx.x & 63), slice = threadIdx.x >> 6;
+    __shared__ float4 sm[4][64];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool live = grp < KK * 64 * Cq;
+    int co = 0, ci = 0, tap = 0;
+    if (live) {
+        co = (grp % Cq) * 4; ci = (grp / Cq) % 64; tap = grp / (Cq * 64);
         int b, m;
         if (ks == 1) { b = 1; m = 64 + ci; }
         else if (tap < 6) { b = tap % 3; m = (tap / 3) * 64 + ci; }
         else { b = 3 + tap % 3; m = ci; }
-        const float *src = partial + ((size_t)(co >> 6) * ctas * 6 * 128 + (size_t)b * 128 + m) * 64 + (co & 63);
-        float s0 = 0.f, s1 = 0.f;
-        int c = 0;
-        for (; c + 1 < ctas; c += 2) {
-            s0 += src[(size_t)c * 6 * 128 * 64];
-            s1 += src[(size_t)(c + 1) * 6 * 128 * 64];
+        const float4 *src = reinterpret_cast<const float4 *>(partial + ((size_t)(co >> 6) * ctas * 6 * 128 + (size_t)b * 128 + m) * 64 + (co & 63));
+        const size_t stride = (size_t)6 * 128 * 64 / 4;  // float4s between consecutive CTAs' slices
+        const int per = (ctas + 3) / 4, lo = slice * per, hi = min(ctas, lo + per);
+        int c = lo;
+        for (; c + 3 < hi; c += 4) {
+            const float4 v0 = __ldg(src + (size_t)c * stride), v1 = __ldg(src + (size_t)(c + 1) * stride);
+            const float4 v2 = __ldg(src + (size_t)(c + 2) * stride), v3 = __ldg(src + (size_t)(c + 3) * stride);
+            acc.x += (v0.x + v1.x) + (v2.x + v3.x); acc.y += (v0.y + v1.y) + (v2.y + v3.y);
+            acc.z += (v0.z + v1.z) + (v2.z + v3.z); acc.w += (v0.w + v1.w) + (v2.w + v3.w);
         }
-        if (c < ctas) s0 += src[(size_t)c * 6 * 128 * 64];
-        gw[((size_t)co * cin_total + c0 + ci) * KK + tap] = s0 + s1;
+        for (; c < hi; ++c) {
+            const float4 v = __ldg(src + (size_t)c * stride);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
     }
+    sm[slice][threadIdx.x & 63] = acc;
+    __syncthreads();
+    if (live && slice == 0) {
+        const float4 a1 = sm[1][threadIdx.x], a2 = sm[2][threadIdx.x], a3 = sm[3][threadIdx.x];
+        const float r[4] = {(acc.x + a1.x) + (a2.x + a3.x), (acc.y + a1.y) + (a2.y + a3.y), (acc.z + a1.z) + (a2.z + a3.z), (acc.w + a1.w) + (a2.w + a3.w)};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gw[((size_t)(co + k) * cin_total + c0 + ci) * KK + tap] = r[k];
+    }
+    const int idx = blockIdx.x * 256 + threadIdx.x;
     if (db != nullptr && idx < Cout) {
         const float *src = bias_partial + (size_t)(idx >> 6) * ctas * 64 + (idx & 63);
         float s_ = 0.f;
@@ -580,11 +607,13 @@ bool conv_wgrad_tc_supported(int Cin, int ks, int stride) {
     return Cin == 64 && (ks == 3 || ks == 1) && stride == 1 && get_encode() != nullptr;
 }
 
+// CTAs per pass.  Measured cost model of one launch (us): 8 + 0.08 * CTAs (each CTA writes 147 KB of partial sums that the
+// reduce kernel reads back) + 2 * tiles / CTAs  ->  minimum at CTAs = 5 * sqrt(tiles)
 static int wgrad_ctas(int num_tiles, int passes) {
-    static const int tpc = getenv("RVSR_WG_TPC") ? atoi(getenv("RVSR_WG_TPC")) : 6;
-    int gx = num_tiles / (tpc > 0 ? tpc : 1);  // tiles per CTA below which more CTAs stop paying (prologue + flush + reduce)
+    int gx = (int)(5.0 * sqrt((double)num_tiles));
     const int cap = sm_count() / passes > 0 ? sm_count() / passes : 1;
     if (gx > cap) gx = cap;
+    if (gx > num_tiles) gx = num_tiles;
     return gx < 1 ? 1 : gx;
 }
 size_t conv_wgrad_tc_workspace_bytes(int N, int H, int W, int Cout) {
@@ -636,8 +665,10 @@ int launch_conv_wgrad_tc(const void *x_c8, long long x_image_stride, const void 
     RVSR_TRY(ensure_max_dynamic_smem(reinterpret_cast<const void *>(&conv_wgrad_tc_kernel), (int)smem));
     conv_wgrad_tc_kernel<<<dim3(gx, passes), WG_THREADS, smem, s>>>(p);
     RVSR_LAUNCH_CHECK();
-    const int total = ks * ks * 64 * Cout;
-    wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, s>>>(p.partial, p.bias_partial, gw, db, gx, Cout, cin_total, c0, ks);
+    const int groups = ks * ks * 64 * (Cout / 4);  // Cout % 8 == 0
+    int rb = (groups + 63) / 64;
+    if (rb * 256 < Cout) rb = (Cout + 255) / 256;  // the bias sums ride on the first threads
+    wgrad_reduce_kernel<<<rb, 256, 0, s>>>(p.partial, p.bias_partial, gw, db, gx, Cout, cin_total, c0, ks);
     RVSR_LAUNCH_CHECK();
     return RVSR_OK;
 }
