@@ -325,7 +325,7 @@ class _EDVRBase(nn.Module):
         """Same graph as _forward_modules.  Every 64-channel convolution (3x3 and 1x1; stride 2 as stride 1 + subsampling), the
         residual adds, torch.cat, the x2 upsamples and PixelShuffle + lrelu run as train_c8 Functions on [N, C/8, H, W, 8] bf16
         tensors, and so does the DCN operator (train_c8.dcn_pack); TSA's pools / sigmoids / products are torch ops on the same
-        tensors.  Only conv_first (3 input channels) is a torch convolution on NCHW tensors."""
+        tensors.  conv_first packs the NCHW frames itself (train_c8.conv_first); the x4 bilinear base is torch's."""
         from .. import train_c8 as T
         B, N, C, H, W = x.size()
         bf = torch.bfloat16
@@ -376,7 +376,7 @@ class _EDVRBase(nn.Module):
         with torch.autocast("cuda", dtype=bf):
             x_center = x[:, self.center].contiguous()
             frames = x.reshape(-1, C, H, W)
-            l1 = trunk(self.feature_extraction, T.to_c8(F.leaky_relu(self.conv_first(frames), 0.1)))
+            l1 = trunk(self.feature_extraction, T.conv_first(frames, self.conv_first.weight, self.conv_first.bias, "lrelu"))
             l2 = conv(self.fea_L2_conv2, down2(self.fea_L2_conv1, l1), "lrelu")
             l3 = conv(self.fea_L3_conv2, down2(self.fea_L3_conv1, l2), "lrelu")
             pyr = [l1, l2, l3]

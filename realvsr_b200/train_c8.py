@@ -223,6 +223,61 @@ class _ConvC8(torch.autograd.Function):
         return (gw, gb, g_res, None, None, *gxs)
 
 
+class _ConvFirstC8(torch.autograd.Function):
+    """conv_first (EDVR_arch.py:233, :276): 3x3 convolution of an NCHW image with <= 16 channels + LeakyReLU, C8 output.
+    The image is packed to 16 channels (the tensor-core K granularity), the weight's input channels zero-padded to match.
+    Weight gradient on conv_wgrad_tc_kernel, which reads 64-channel sources: the packed image is allocated with three images
+    of zero slack behind it and handed over as "8 channel blocks per image, image stride 2 blocks" -- blocks 2..7 of an
+    image alias the following images (finite values), their rows of the gradient are discarded.  The input gets no gradient
+    (frames are data)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act):
+        if not x.is_cuda:
+            raise NotImplementedError("realvsr_b200.train_c8: CUDA tensors only (no CPU fallback)")
+        N, C, H, W = x.shape
+        Cout, Cin, ks, _ = weight.shape
+        if Cin != C or C > 16 or ks != 3 or Cout % 64 != 0 or weight.dtype != torch.float32:
+            raise NotImplementedError("conv_first_c8: 3x3, <= 16 input channels, Cout %% 64 == 0, fp32 parameters")
+        xp = torch.zeros((N + 3, 2, H, W, 8), dtype=torch.bfloat16, device=x.device)
+        xin = x if x.dtype in (torch.bfloat16, torch.float32) else x.float()
+        xin = xin.contiguous()
+        w16 = torch.nn.functional.pad(weight.detach(), (0, 0, 0, 0, 0, 16 - C)).contiguous()
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().rvsr_c8_from_nchw(_p(xin), _lib.BF16 if xin.dtype == torch.bfloat16 else _lib.F32, _p(xp), N, C, H, W, 2,
+                                                    _stream(x.device)), "c8_from_nchw")
+            wp = _pack_weight(w16, Cout, 16, 3, False, 0, 16, 0, _tiles(N, H, W, 3))
+            y = _conv_launch([xp[:N]], wp, bias, None, N, H, W, 16, Cout, 3, act, False)
+        ctx.meta = (act, N, C, H, W, Cout)
+        ctx.save_for_backward(xp, *([y] if act != _lib.ACT_NONE else []))
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        act, N, C, H, W, Cout = ctx.meta
+        xp = ctx.saved_tensors[0]
+        g = _check_c8(g, "conv_first_c8 backward")
+        L, dev = _lib.lib(), g.device
+        with torch.cuda.device(dev):
+            s = _stream(dev)
+            if act != _lib.ACT_NONE:
+                gp = torch.empty_like(g)
+                _lib.check(L.rvsr_c8_act_bwd(_p(g), _p(ctx.saved_tensors[1]), _p(gp), g.numel(), act, s), "c8_act_bwd")
+            else:
+                gp = g
+            gw = torch.empty((Cout, 64, 3, 3), dtype=torch.float32, device=dev)
+            gb = torch.empty(Cout, dtype=torch.float32, device=dev) if ctx.needs_input_grad[2] else None
+            ws = torch.empty(L.rvsr_c8_conv_wgrad_workspace_bytes(N, H, W, Cout), dtype=torch.uint8, device=dev)
+            _lib.check(L.rvsr_c8_conv_wgrad(_p(xp), xp.stride(0), _p(gp), _p(gw), _p(gb), N, H, W, 64, Cout, 3, 64, 0, _p(ws), ws.numel(), s),
+                       "c8_conv_wgrad")
+        return None, gw[:, :C].contiguous(), gb, None
+
+
+def conv_first(x, weight, bias=None, act=None):
+    """First convolution of the network on an NCHW image (<= 16 channels): C8 bf16 output, weight / bias gradients."""
+    return _ConvFirstC8.apply(x, weight, bias, ACT[act])
+
+
 def conv(xs, weight, bias=None, act=None, residual=None, shuffle=False):
     """One nn.Conv2d site (3x3 / 1x1, stride 1) on C8 tensors; `xs` is a tensor or the list torch.cat would have joined."""
     if isinstance(xs, torch.Tensor):

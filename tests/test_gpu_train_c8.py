@@ -205,3 +205,23 @@ def test_dcn_pack_c8_against_the_nchw_operator(act):
         assert a.shape == r.shape
         assert _rel(a, r) < 2e-2, (name, _rel(a, r))
     assert float(got[1][:, 216:].abs().max()) == 0.0
+
+
+def test_conv_first_c8():
+    """3 -> 64 channels from an NCHW fp32 image: forward, weight and bias gradients against torch autograd."""
+    from realvsr_b200 import train_c8 as T
+    g = torch.Generator(device="cuda").manual_seed(21)
+    N, H, W = 5, 20, 40
+    x = _r(torch.rand(N, 3, H, W, device="cuda", generator=g))
+    w = _r(torch.randn(64, 3, 3, 3, device="cuda", generator=g) * 0.2).requires_grad_()
+    b = (torch.randn(64, device="cuda", generator=g) * 0.1).requires_grad_()
+    w2, b2 = w.detach().clone().requires_grad_(), b.detach().clone().requires_grad_()
+    y = T.from_c8(T.conv_first(x, w2, b2, "lrelu"), 64, torch.float32)
+    pre = F.conv2d(x, w, b, padding=1)
+    y_ref = pre * torch.where(y.detach() > 0, 1.0, 0.1)
+    assert _rel(y, y_ref.detach()) < 1e-2
+    gy = _r(torch.randn(y.shape, device="cuda", generator=g))
+    ref = torch.autograd.grad(y_ref, [w, b], gy)
+    got = torch.autograd.grad(y, [w2, b2], gy)
+    for name, a, r in zip(("dw", "db"), got, ref):
+        assert a.shape == r.shape and _rel(a, r) < 3e-3, (name, _rel(a, r))
