@@ -141,6 +141,14 @@ int rvsr_c8_conv_wgrad(const void *x, long long x_image_stride, const void *g, f
 int rvsr_c8_act_bwd(const void *g, const void *y, void *out, long long n_elems, int act, void *stream);
 int rvsr_c8_unshuffle2_act_bwd(const void *g, const void *y, void *out, int N, int C, int H, int W, int act, void *stream);
 int rvsr_c8_upsample2x(const void *src, void *dst, long long planes, int H, int W, float scale, int backward, void *stream);
+/* TSA_Fusion's temporal attention (EDVR_arch.py:170-181) and its gradient on 64-channel C8 tensors: aligned, emb [B * N][8][H][W][8],
+ * emb_ref [B][8][H][W][8]; prob[b][n][pixel] = sigmoid(<emb[b, n], emb_ref[b]>) (fp32, kept for the backward);
+ * out[n] ([B][8][H][W][8], one tensor per frame = the N sources of the 1x1 fusion convolutions) = aligned[b, n] * prob.
+ * bwd: gout[n] may be NULL (no gradient for that frame); g_aligned, g_emb, g_emb_ref are written. */
+int rvsr_c8_tsa_temporal(const void *aligned, const void *emb, const void *emb_ref, void *const *out, float *prob, int B, int N, int C,
+                         int H, int W, void *stream);
+int rvsr_c8_tsa_temporal_bwd(const void *const *gout, const void *aligned, const void *emb, const void *emb_ref, const float *prob,
+                             void *g_aligned, void *g_emb, void *g_emb_ref, int B, int N, int C, int H, int W, void *stream);
 /* ModulatedDeformConvPack.forward / its autograd (deform_conv.py:274-292, :97-153) on C8 tensors, for EDVR's shape class
  * (64 -> 64 channels, 3x3, stride 1, pad 1, 8 deformable groups).  `om` is the output of the conv_offset_mask convolution
  * as a 256-channel C8 tensor (144 offsets, 72 mask logits, 40 zero channels: the 216 outputs padded to whole 64-wide tiles);

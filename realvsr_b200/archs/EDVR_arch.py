@@ -357,10 +357,7 @@ class _EDVRBase(nn.Module):
             # (a C8 tensor is an ordinary 5-D tensor: channel = 8 * dim 1 + dim 4)
             a6 = aligned.view(B, N, *aligned.shape[1:])                                   # [B, N, 8, H, W, 8]
             emb_ref = conv(m.tAtt_2, a6[:, self.center].contiguous())                     # [B, 8, H, W, 8]
-            emb = conv(m.tAtt_1, aligned).view(B, N, *aligned.shape[1:])
-            prob = torch.sigmoid((emb.float() * emb_ref.float().unsqueeze(1)).sum((2, 5)))  # [B, N, H, W]
-            weighted = (a6 * prob.to(bf).unsqueeze(2).unsqueeze(-1))
-            srcs = [weighted[:, i].contiguous() for i in range(N)]                        # the N x 64 channels of the 1x1 fusions
+            srcs = T.tsa_temporal(aligned, conv(m.tAtt_1, aligned), emb_ref, N)           # the N x 64 channels of the 1x1 fusions
             fea = conv(m.fea_fusion, srcs, "lrelu")
             att = conv(m.sAtt_1, srcs, "lrelu")
             pool = lambda t: (F.max_pool3d(t, (3, 3, 1), (2, 2, 1), (1, 1, 0)), F.avg_pool3d(t, (3, 3, 1), (2, 2, 1), (1, 1, 0)))  # noqa: E731

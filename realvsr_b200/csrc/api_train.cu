@@ -17,6 +17,10 @@ int c8_mdcn_fwd(const void *x, const void *om, const float *weight, const float 
                 void *workspace, size_t workspace_bytes, cudaStream_t s);
 int c8_mdcn_bwd(const void *x, const void *om, const float *weight, const void *g, const void *y, void *gx, void *gom, float *gw,
                 float *gb, int N, int H, int W, int act, void *workspace, size_t workspace_bytes, cudaStream_t s);
+int launch_tsa_temporal_c8(const void *aligned, const void *emb, const void *emb_ref, void *const *out, float *prob, int B, int N, int H,
+                           int W, cudaStream_t s);
+int launch_tsa_temporal_bwd_c8(const void *const *gout, const void *aligned, const void *emb, const void *emb_ref, const float *prob,
+                               void *g_aligned, void *g_emb, void *g_emb_ref, int B, int N, int H, int W, cudaStream_t s);
 }  // namespace rvsr
 
 using namespace rvsr;
@@ -131,6 +135,21 @@ int rvsr_c8_mdcn_bwd(const void *x, const void *om, const float *weight, const v
     RVSR_CHECK_ARG(N >= 0 && H > 0 && W > 0, "c8 mdcn bwd: bad sizes");
     RVSR_CHECK_ARG(gw && (N == 0 || (x && om && weight && g && gx && gom && workspace)), "c8 mdcn bwd: null buffer");
     return c8_mdcn_bwd(x, om, weight, g, y, gx, gom, gw, gb, N, H, W, act, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int rvsr_c8_tsa_temporal(const void *aligned, const void *emb, const void *emb_ref, void *const *out, float *prob, int B, int N, int C,
+                         int H, int W, void *stream) {
+    RVSR_CHECK_ARG(B >= 0 && N > 0 && H > 0 && W > 0, "c8 tsa temporal: bad sizes");
+    if (C != 64) { set_error("c8 tsa temporal: built for 64 channels"); return RVSR_E_UNSUPPORTED; }
+    RVSR_CHECK_ARG(B == 0 || (aligned && emb && emb_ref && out && prob), "c8 tsa temporal: null buffer");
+    return launch_tsa_temporal_c8(aligned, emb, emb_ref, out, prob, B, N, H, W, (cudaStream_t)stream);
+}
+int rvsr_c8_tsa_temporal_bwd(const void *const *gout, const void *aligned, const void *emb, const void *emb_ref, const float *prob,
+                             void *g_aligned, void *g_emb, void *g_emb_ref, int B, int N, int C, int H, int W, void *stream) {
+    RVSR_CHECK_ARG(B >= 0 && N > 0 && H > 0 && W > 0, "c8 tsa temporal bwd: bad sizes");
+    if (C != 64) { set_error("c8 tsa temporal: built for 64 channels"); return RVSR_E_UNSUPPORTED; }
+    RVSR_CHECK_ARG(B == 0 || (gout && aligned && emb && emb_ref && prob && g_aligned && g_emb && g_emb_ref), "c8 tsa temporal bwd: null buffer");
+    return launch_tsa_temporal_bwd_c8(gout, aligned, emb, emb_ref, prob, g_aligned, g_emb, g_emb_ref, B, N, H, W, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -595,6 +595,84 @@ __global__ void cvt_f16_to_bf16_kernel(const uint4 *__restrict__ src, uint4 *__r
     }
 }
 
+// ---- TSA temporal attention (EDVR_arch.py:170-181) on C8 tensors, 64 channels.  One thread per (batch, frame, pixel):
+// prob = sigmoid(sum_c emb[b, n, c] * emb_ref[b, c]); out_n = aligned[b, n] * prob.  `out` is N separate [B][8][HW][8] tensors
+// (the N sources of the 1x1 fusion convolutions), prob [B][N][HW] fp32 is kept for the backward.
+struct TsaPtrs { void *p[RVSR_MAX_SRC_TC]; };
+__global__ void tsa_temporal_c8_kernel(const uint4 *__restrict__ aligned, const uint4 *__restrict__ emb, const uint4 *__restrict__ emb_ref,
+                                       TsaPtrs out, float *__restrict__ prob, int N, int HW, long long total) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int px = (int)(i % HW);
+        const int n = (int)((i / HW) % N);
+        const long long b = i / ((long long)HW * N);
+        const uint4 *e = emb + ((b * N + n) * 8) * (long long)HW + px, *r = emb_ref + (b * 8) * (long long)HW + px;
+        float dot = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            float ev[8], rv[8];
+            unpack8(__ldg(e + (long long)q * HW), ev);
+            unpack8(__ldg(r + (long long)q * HW), rv);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) dot += ev[k] * rv[k];
+        }
+        const float pr = __fdividef(1.f, 1.f + __expf(-dot));
+        prob[i] = pr;
+        const uint4 *a = aligned + ((b * N + n) * 8) * (long long)HW + px;
+        uint4 *o = reinterpret_cast<uint4 *>(out.p[n]) + (b * 8) * (long long)HW + px;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            float av[8];
+            unpack8(__ldg(a + (long long)q * HW), av);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) av[k] *= pr;
+            o[(long long)q * HW] = pack8(av);
+        }
+    }
+}
+// backward: one thread per (batch, pixel) walks the N frames.  g_aligned = g_out * prob; g_dot = (sum_c g_out * aligned) * p (1 - p);
+// g_emb = g_dot * emb_ref; g_emb_ref = sum_n g_dot * emb[n]  (no atomics: the frame loop is inside the thread)
+__global__ void tsa_temporal_bwd_c8_kernel(TsaPtrs gout, const uint4 *__restrict__ aligned, const uint4 *__restrict__ emb,
+                                           const uint4 *__restrict__ emb_ref, const float *__restrict__ prob, uint4 *__restrict__ g_aligned,
+                                           uint4 *__restrict__ g_emb, uint4 *__restrict__ g_emb_ref, int N, int HW, long long total) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int px = (int)(i % HW);
+        const long long b = i / HW;
+        const uint4 *r = emb_ref + (b * 8) * (long long)HW + px;
+        float acc[8][8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[q][k] = 0.f;
+        for (int n = 0; n < N; ++n) {
+            const long long base = ((b * N + n) * 8) * (long long)HW + px;
+            const float pr = prob[(b * N + n) * (long long)HW + px];
+            const uint4 *go = reinterpret_cast<const uint4 *>(gout.p[n]);
+            float gdot = 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float gv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, av[8];
+                if (go != nullptr) unpack8(__ldg(go + (b * 8 + q) * (long long)HW + px), gv);
+                unpack8(__ldg(aligned + base + (long long)q * HW), av);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { gdot += gv[k] * av[k]; gv[k] *= pr; }
+                g_aligned[base + (long long)q * HW] = pack8(gv);
+            }
+            gdot *= pr * (1.f - pr);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float ev[8], rv[8];
+                unpack8(__ldg(emb + base + (long long)q * HW), ev);
+                unpack8(__ldg(r + (long long)q * HW), rv);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { acc[q][k] += gdot * ev[k]; rv[k] *= gdot; }
+                g_emb[base + (long long)q * HW] = pack8(rv);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) g_emb_ref[(b * 8 + q) * (long long)HW + px] = pack8(acc[q]);
+    }
+}
+
 static int ew_grid(long long n) {
     long long b = (n + 255) / 256;
     const long long cap = (long long)sm_count() * 16;
@@ -725,6 +803,30 @@ int launch_c8_to_nchw_bf16(const void *src, void *dst, int dst_dtype, int N, int
     if (dst_dtype == RVSR_BF16) c8_to_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const uint4 *)src, (__nv_bfloat16 *)dst, C, HW, planes);
     else if (dst_dtype == RVSR_F32) c8_to_nchw_kernel<float><<<grid, 256, 0, s>>>((const uint4 *)src, (float *)dst, C, HW, planes);
     else { set_error("c8 -> nchw: dtype %d", dst_dtype); return RVSR_E_INVALID; }
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+
+int launch_tsa_temporal_c8(const void *aligned, const void *emb, const void *emb_ref, void *const *out, float *prob, int B, int N, int H,
+                           int W, cudaStream_t s) {
+    RVSR_CHECK_ARG(N >= 1 && N <= RVSR_MAX_SRC_TC, "tsa temporal: 1..%d frames", RVSR_MAX_SRC_TC);
+    const long long total = (long long)B * N * H * W;
+    if (total == 0) return RVSR_OK;
+    TsaPtrs o;
+    for (int i = 0; i < N; ++i) o.p[i] = out[i];
+    tsa_temporal_c8_kernel<<<ew_grid(total), 256, 0, s>>>((const uint4 *)aligned, (const uint4 *)emb, (const uint4 *)emb_ref, o, prob, N, H * W, total);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+int launch_tsa_temporal_bwd_c8(const void *const *gout, const void *aligned, const void *emb, const void *emb_ref, const float *prob,
+                               void *g_aligned, void *g_emb, void *g_emb_ref, int B, int N, int H, int W, cudaStream_t s) {
+    RVSR_CHECK_ARG(N >= 1 && N <= RVSR_MAX_SRC_TC, "tsa temporal: 1..%d frames", RVSR_MAX_SRC_TC);
+    const long long total = (long long)B * H * W;
+    if (total == 0) return RVSR_OK;
+    TsaPtrs g;
+    for (int i = 0; i < N; ++i) g.p[i] = const_cast<void *>(gout[i]);
+    tsa_temporal_bwd_c8_kernel<<<(int)((total + 127) / 128), 128, 0, s>>>(g, (const uint4 *)aligned, (const uint4 *)emb, (const uint4 *)emb_ref, prob,
+                                                                         (uint4 *)g_aligned, (uint4 *)g_emb, (uint4 *)g_emb_ref, N, H * W, total);
     RVSR_LAUNCH_CHECK();
     return RVSR_OK;
 }

@@ -328,6 +328,45 @@ def dcn_pack(x, om, weight, bias=None, act=None):
     return _DcnPackC8.apply(x, om, weight, bias, ACT[act])
 
 
+# ---------------------------------------------------------------- TSA temporal attention
+class _TsaTemporalC8(torch.autograd.Function):
+    """(aligned, emb: [B * N, 8, H, W, 8]; emb_ref: [B, 8, H, W, 8]) -> N tensors aligned[b, n] * sigmoid(<emb[b, n], emb_ref[b]>)
+    (TSA_Fusion.forward, EDVR_arch.py:170-181): the N inputs of the 1x1 fusion convolutions, each [B, 8, H, W, 8]."""
+
+    @staticmethod
+    def forward(ctx, aligned, emb, emb_ref, N):
+        aligned, emb, emb_ref = _check_c8(aligned, "tsa aligned"), _check_c8(emb, "tsa emb"), _check_c8(emb_ref, "tsa emb_ref")
+        B, P, H, W, _ = emb_ref.shape
+        if P != 8 or tuple(aligned.shape) != (B * N, 8, H, W, 8) or aligned.shape != emb.shape:
+            raise NotImplementedError("tsa_temporal_c8: 64 channels, aligned / emb [B * N, 8, H, W, 8], emb_ref [B, 8, H, W, 8]")
+        outs = [torch.empty_like(emb_ref) for _ in range(N)]
+        prob = torch.empty((B, N, H, W), dtype=torch.float32, device=emb.device)
+        ptrs = (ctypes.c_void_p * N)(*[o.data_ptr() for o in outs])
+        with torch.cuda.device(emb.device):
+            _lib.check(_lib.lib().rvsr_c8_tsa_temporal(_p(aligned), _p(emb), _p(emb_ref), ptrs, _p(prob), B, N, 64, H, W, _stream(emb.device)),
+                       "c8_tsa_temporal")
+        ctx.N = N
+        ctx.save_for_backward(aligned, emb, emb_ref, prob)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        aligned, emb, emb_ref, prob = ctx.saved_tensors
+        N = ctx.N
+        B, _, H, W, _ = emb_ref.shape
+        gouts = [None if g is None else _check_c8(g, "tsa backward") for g in gouts]
+        ptrs = (ctypes.c_void_p * N)(*[0 if g is None else g.data_ptr() for g in gouts])
+        g_aligned, g_emb, g_emb_ref = torch.empty_like(aligned), torch.empty_like(emb), torch.empty_like(emb_ref)
+        with torch.cuda.device(emb.device):
+            _lib.check(_lib.lib().rvsr_c8_tsa_temporal_bwd(ptrs, _p(aligned), _p(emb), _p(emb_ref), _p(prob), _p(g_aligned), _p(g_emb),
+                                                           _p(g_emb_ref), B, N, 64, H, W, _stream(emb.device)), "c8_tsa_temporal_bwd")
+        return g_aligned, g_emb, g_emb_ref, None
+
+
+def tsa_temporal(aligned, emb, emb_ref, N):
+    return list(_TsaTemporalC8.apply(aligned, emb, emb_ref, N))
+
+
 # ---------------------------------------------------------------- x2 bilinear upsample (optionally scaled)
 class _Up2C8(torch.autograd.Function):
     @staticmethod

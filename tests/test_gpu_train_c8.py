@@ -225,3 +225,25 @@ def test_conv_first_c8():
     got = torch.autograd.grad(y, [w2, b2], gy)
     for name, a, r in zip(("dw", "db"), got, ref):
         assert a.shape == r.shape and _rel(a, r) < 3e-3, (name, _rel(a, r))
+
+
+def test_tsa_temporal_c8():
+    """Temporal attention (EDVR_arch.py:170-181) forward and the three gradients against torch autograd in fp32."""
+    from realvsr_b200 import train_c8 as T
+    g = torch.Generator(device="cuda").manual_seed(31)
+    B, N, H, W = 2, 5, 12, 20
+    al = _r(torch.randn(B * N, 64, H, W, device="cuda", generator=g)).requires_grad_()
+    em = _r(torch.randn(B * N, 64, H, W, device="cuda", generator=g) * 0.3).requires_grad_()
+    er = _r(torch.randn(B, 64, H, W, device="cuda", generator=g) * 0.3).requires_grad_()
+    prob = torch.sigmoid((em.view(B, N, 64, H, W) * er.unsqueeze(1)).sum(2, keepdim=True))
+    ref = (al.view(B, N, 64, H, W) * prob)
+    gy = _r(torch.randn(ref.shape, device="cuda", generator=g))
+    gy[:, 3] = 0
+    gref = torch.autograd.grad(ref, [al, em, er], gy)
+    al2, em2, er2 = [t.detach().clone().requires_grad_() for t in (al, em, er)]
+    outs = T.tsa_temporal(T.to_c8(al2), T.to_c8(em2), T.to_c8(er2), N)
+    y = torch.stack([T.from_c8(o, 64, torch.float32) for o in outs], 1)
+    assert _rel(y, ref.detach()) < 1e-2
+    got = torch.autograd.grad(y, [al2, em2, er2], gy)
+    for name, a, r in zip(("d_aligned", "d_emb", "d_emb_ref"), got, gref):
+        assert a.shape == r.shape and _rel(a, r) < 1e-2, (name, _rel(a, r))
