@@ -167,3 +167,73 @@ def test_window_sharding_over_nccl_with_the_real_model():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert all(res)
+
+
+# ---------------------------------------------------------------- DDP training step on the bf16 training path (needs two GPUs)
+def _ddp_worker(rank, world, port, q):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p_ in (root, os.path.join(root, "tests"), os.path.join(root, "tests", "golden")):
+        if p_ not in sys.path:
+            sys.path.insert(0, p_)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import torch.nn.functional as F
+        from helpers import load_case
+        from realvsr_b200.archs import EDVR_arch as E
+        from synth import synth_input
+        c = load_case("edvr_nf64_crop")
+        net = E.EDVR(**c["kwargs"]).train()
+        net.load_state_dict(c["sd"], strict=True)
+        net = net.to(dev)
+        H, W = c["x"].shape[-2:]
+        x = synth_input((2, 5, 3, H, W), 100 + rank).to(dev)       # a different batch on every rank
+        gt = synth_input((2, 3, 4 * H, 4 * W), 200 + rank).to(dev)
+
+        def step(model):
+            model.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):     # -> EDVR._forward_c8 (train_c8 path)
+                loss = F.l1_loss(model(x).float(), gt)
+            loss.backward()
+
+        step(net)                                                  # local gradients, then their average over the ranks by hand
+        want = []
+        for p_ in net.parameters():
+            g = p_.grad.detach().clone()
+            dist.all_reduce(g)
+            want.append(g / world)
+        ddp = torch.nn.parallel.DistributedDataParallel(net, device_ids=[rank])  # VideoSR_AllPair_model_YCbCr_Split.py:33-34
+        step(ddp)
+        worst = 0.0
+        for p_, w in zip(net.parameters(), want):
+            worst = max(worst, float((p_.grad - w).abs().max() / w.abs().max().clamp_min(1e-12)))
+        # the same kernels ran on the same data; what differs is the order of the fp32 atomics inside dcn_bwd_tc_kernel (its
+        # grad_input is then rounded to bf16, and a flipped last bit travels on through the data gradients) and NCCL's sum order
+        print("rank %d: DDP vs hand-averaged gradients, worst relative difference %.2e" % (rank, worst), flush=True)
+        q.put(worst < 2e-2)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_ddp_training_step_on_the_c8_path():
+    """SURVEY 8(e) training row: replicas + gradient all-reduce.  DistributedDataParallel around the module, bf16 autocast step on
+    the train_c8 path on two GPUs with different batches: DDP's gradients equal the hand-averaged local gradients."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert all(res)

@@ -247,3 +247,41 @@ def test_tsa_temporal_c8():
     got = torch.autograd.grad(y, [al2, em2, er2], gy)
     for name, a, r in zip(("d_aligned", "d_emb", "d_emb_ref"), got, gref):
         assert a.shape == r.shape and _rel(a, r) < 1e-2, (name, _rel(a, r))
+
+
+@pytest.mark.parametrize("cls,kw", [("EDVR_NoUp", dict(nf=64, nframes=3, groups=8, front_RBs=2, back_RBs=2, w_TSA=False)),
+                                    ("EDVR", dict(nf=64, nframes=7, groups=8, front_RBs=1, back_RBs=1, w_TSA=True)),
+                                    ("EDVR", dict(nf=64, nframes=3, groups=8, front_RBs=1, back_RBs=1, w_TSA=False))])
+def test_other_architectures_on_the_c8_path(cls, kw):
+    """The shipped RealVSR configuration (EDVR_NoUp, 3 frames, no TSA: train_EDVR_woTSA_RealVSR_YCbCr_Split.yml:38-50) and other
+    frame counts: train_c8 gradients against the fp32 module path, every parameter (same criterion as the cfg5 network test).
+    Sizes that are not tile multiples (36 x 44)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers import edvr_state_shapes
+    from synth import synth_input, synth_state_dict
+    from realvsr_b200.archs import EDVR_arch as E
+    net = getattr(E, cls)(**kw).train()
+    net.load_state_dict(synth_state_dict(edvr_state_shapes(cls, **kw), 3), strict=True)
+    net = net.to("cuda")
+    x = synth_input((2, kw["nframes"], 3, 36, 44), 4).to("cuda")
+    s = 4 if cls == "EDVR" else 1
+    gt = synth_input((2, 3, 36 * s, 44 * s), 5).to("cuda")
+
+    def grads(path):
+        net.exec_path = path
+        net.zero_grad(set_to_none=True)
+        loss = F.l1_loss(net(x).float(), gt)
+        loss.backward()
+        return float(loss.detach()), {n: p.grad.detach().float().clone() for n, p in net.named_parameters()}
+
+    l32, g32 = grads("module")
+    lc8, gc8 = grads("train_c8")
+    assert abs(lc8 - l32) < 2e-2 * l32
+    for n in g32:
+        a, r = gc8[n].flatten(), g32[n].flatten()
+        cos = float(torch.dot(a, r) / (a.norm() * r.norm()).clamp_min(1e-30))
+        assert cos > 0.95, (n, cos)
+        assert 0.9 < float(a.norm() / r.norm().clamp_min(1e-30)) < 1.1, n
