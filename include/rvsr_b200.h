@@ -119,6 +119,8 @@ int rvsr_conv2d_fwd(const void *x1, const void *x2, const void *weight, const vo
  *                             tiles); 3 packs both.
  *   rvsr_c8_conv_fwd          y = act(conv(cat(x[0..nsrc)), w) + bias) [+ residual], optional fused PixelShuffle(2); nsrc sources
  *                             of C channels each (C % 16 == 0, C <= 64); also runs every data gradient (with mode-1 weights).
+ *                             residual_mode 0: y += residual.  residual_mode 2: `residual` is the OUTPUT of the activation this
+ *                             data gradient flows into, y *= (residual > 0 ? 1 : residual_slope) -- its gradient, fused.
  *   rvsr_c8_conv_wgrad        gw[co][c0 + ci][ky][kx] = sum_pixels x[pixel + (ky, kx) - pad][ci] * g[pixel][co] for the 64 input
  *                             channels of source x (OIHW fp32 [Cout][cin_total][ks][ks]; written, fixed summation order),
  *                             db[co] = sum_pixels g (may be NULL).  Cin = 64 per call, ks in {1, 3}.
@@ -134,7 +136,7 @@ int rvsr_c8_conv_pack_weight(const float *weight, void *dst, int Cout, int Cin, 
                              int w_c0, int layouts, void *stream);
 int rvsr_c8_conv_fwd(const void *const *x, const long long *x_image_stride, int nsrc, int C, const void *w_packed, const float *bias,
                      const void *residual, void *y, int N, int H, int W, int Cout, int ks, int stride, int act, int shuffle,
-                     void *stream);
+                     int residual_mode, float residual_slope, void *stream);
 size_t rvsr_c8_conv_wgrad_workspace_bytes(int N, int H, int W, int Cout);
 int rvsr_c8_conv_wgrad(const void *x, long long x_image_stride, const void *g, float *gw, float *db, int N, int H, int W, int Cin,
                        int Cout, int ks, int cin_total, int c0, void *workspace, size_t workspace_bytes, void *stream);

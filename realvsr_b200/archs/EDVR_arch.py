@@ -331,11 +331,11 @@ class _EDVRBase(nn.Module):
         bf = torch.bfloat16
         conv = lambda m, t, act=None, residual=None, shuffle=False: T.conv(t, m.weight, m.bias, act=act, residual=residual,  # noqa: E731
                                                                            shuffle=shuffle)
-        nchw = lambda t: T.from_c8(t, None, bf)  # noqa: E731
+        pair = lambda m1, m2, t: T.conv_pair(t, m1.weight, m1.bias, "lrelu", m2.weight, m2.bias, "lrelu")  # noqa: E731
 
         def trunk(blocks, t):
             for blk in blocks:  # ResidualBlock_noBN (arch_util.py:135-139): x + conv2(relu(conv1(x)))
-                t = conv(blk.conv2, conv(blk.conv1, t, "relu"), None, residual=t)
+                t = T.conv_pair(t, blk.conv1.weight, blk.conv1.bias, "relu", blk.conv2.weight, blk.conv2.bias, None, skip=True)
             return t
 
         def dcn(pack, t, feat, act=None):
@@ -380,15 +380,15 @@ class _EDVRBase(nn.Module):
             ref = [lv.view(B, N, *lv.shape[1:])[:, self.center:self.center + 1].expand(B, N, *lv.shape[1:]).reshape(lv.shape)
                    for lv in pyr]
             p = self.pcd_align  # PCD_Align.forward (EDVR_arch.py:98-132), all N frames as one batch
-            off3 = conv(p.L3_offset_conv2, conv(p.L3_offset_conv1, [pyr[2], ref[2]], "lrelu"), "lrelu")
+            off3 = pair(p.L3_offset_conv1, p.L3_offset_conv2, [pyr[2], ref[2]])
             fea3 = dcn(p.L3_dcnpack, pyr[2], off3, act=True)
             off2 = conv(p.L2_offset_conv1, [pyr[1], ref[1]], "lrelu")
-            off2 = conv(p.L2_offset_conv3, conv(p.L2_offset_conv2, [off2, T.upsample2x(off3, 2.0)], "lrelu"), "lrelu")
+            off2 = pair(p.L2_offset_conv2, p.L2_offset_conv3, [off2, T.upsample2x(off3, 2.0)])
             fea2 = conv(p.L2_fea_conv, [dcn(p.L2_dcnpack, pyr[1], off2), T.upsample2x(fea3)], "lrelu")
             off1 = conv(p.L1_offset_conv1, [pyr[0], ref[0]], "lrelu")
-            off1 = conv(p.L1_offset_conv3, conv(p.L1_offset_conv2, [off1, T.upsample2x(off2, 2.0)], "lrelu"), "lrelu")
+            off1 = pair(p.L1_offset_conv2, p.L1_offset_conv3, [off1, T.upsample2x(off2, 2.0)])
             fea1 = conv(p.L1_fea_conv, [dcn(p.L1_dcnpack, pyr[0], off1), T.upsample2x(fea2)])
-            offc = conv(p.cas_offset_conv2, conv(p.cas_offset_conv1, [fea1, ref[0]], "lrelu"), "lrelu")
+            offc = pair(p.cas_offset_conv1, p.cas_offset_conv2, [fea1, ref[0]])
             aligned = dcn(p.cas_dcnpack, fea1, offc, act=True)
             if self.w_TSA:
                 fea = tsa(self.tsa_fusion, aligned)

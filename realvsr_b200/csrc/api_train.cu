@@ -70,10 +70,11 @@ int rvsr_c8_conv_pack_weight(const float *weight, void *dst, int Cout, int Cin, 
 
 int rvsr_c8_conv_fwd(const void *const *x, const long long *x_image_stride, int nsrc, int C, const void *w_packed, const float *bias,
                      const void *residual, void *y, int N, int H, int W, int Cout, int ks, int stride, int act, int shuffle,
-                     void *stream) {
+                     int residual_mode, float residual_slope, void *stream) {
     RVSR_CHECK_ARG(x && x_image_stride && nsrc >= 1 && nsrc <= RVSR_MAX_SRC_TC, "c8 conv: 1..%d sources", RVSR_MAX_SRC_TC);
     RVSR_CHECK_ARG(N >= 0 && C > 0 && H > 0 && W > 0 && Cout > 0 && (ks == 1 || ks == 3) && (stride == 1 || stride == 2), "c8 conv: bad sizes");
     RVSR_CHECK_ARG(!shuffle || (Cout % 4 == 0 && residual == nullptr && stride == 1), "c8 conv: pixel-shuffle needs Cout %% 4 == 0, no residual");
+    RVSR_CHECK_ARG(residual_mode == 0 || (residual_mode == 2 && residual != nullptr), "c8 conv: residual_mode 0 (add) or 2 (mask)");
     if (N == 0) return RVSR_OK;
     RVSR_CHECK_ARG(w_packed && y, "c8 conv: null buffer");
     const int mode = shuffle ? 1 : 0;
@@ -92,6 +93,7 @@ int rvsr_c8_conv_fwd(const void *const *x, const long long *x_image_stride, int 
     op.out = y;
     op.out_image_stride = shuffle ? (long long)cdiv(Cout / 4, 8) * 8 * 4 * Ho * Wo : (long long)cdiv(Cout, 8) * 8 * Ho * Wo;
     op.residual = residual; op.res_image_stride = op.out_image_stride;
+    op.res_pre = residual_mode; op.res_slope = residual_slope;
     op.N = N; op.H = H; op.W = W; op.Cout = Cout; op.ks = ks; op.stride = stride; op.act = act;
     op.out_mode = shuffle ? OUT_C8_SHUFFLE2 : OUT_C8; op.sig_from = 1 << 30;
     op.bf16 = 1;

@@ -229,6 +229,7 @@ struct ConvOp {
     int dg;                // OUT_OM24: deformable groups (Cout == 27 * dg)
     FinalAdd fin;          // OUT_FINAL
     int bf16;              // tcgen05 kernels: sources, residual and output are bfloat16 (w_tc / w_tc2 packed as bfloat16)
+    float res_slope;       // res_pre == 2 (tcgen05 kernels): `residual` is a mask, out = v * (residual > 0 ? 1 : res_slope)
 };
 
 struct DcnOp {

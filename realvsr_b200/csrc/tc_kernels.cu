@@ -84,6 +84,8 @@ struct EpiArgs {
     const FinalAdd *fin;  // OUT_FINAL
     int res_pre, res_div;
     int bf16;  // 16-bit storage format of out / residual: 0 = fp16, 1 = bfloat16 (training path)
+    float res_slope;  // res_pre == 2: `residual` is a MASK tensor, out = v * (residual > 0 ? 1 : res_slope) -- the gradient through the
+                      // LeakyReLU / ReLU that produced it, fused into the data-gradient convolution feeding it (training path)
 };
 
 // 16-bit pair <-> fp32 pair in either storage format
@@ -176,11 +178,12 @@ template <int NT, int NH> struct EpiTile {
                     rr[2 * i] = f.x; rr[2 * i + 1] = f.y;
                 }
             }
-            const bool pre = e.res_pre != 0;
+            const bool pre = e.res_pre == 1, mask = e.res_pre == 2 && RES && has_res;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float a = __uint_as_float(acc[j >> 1][(j & 1) * 8 + i]) + bb[i];
-                v[i] = pre ? act_t<ACT>(a + rr[i], e.act) : act_t<ACT>(a, e.act) + rr[i];
+                if (mask) { const float t = act_t<ACT>(a, e.act); v[i] = rr[i] > 0.f ? t : e.res_slope * t; }
+                else v[i] = pre ? act_t<ACT>(a + rr[i], e.act) : act_t<ACT>(a, e.act) + rr[i];
             }
             uint4 pk;
             uint32_t *h = reinterpret_cast<uint32_t *>(&pk);
@@ -352,7 +355,7 @@ template <int ACT, bool BF, typename Release>
 __device__ __forceinline__ void epi_c8_fast(const float *bias_s, __half *out, long long out_image_stride, const __half *residual,
                                             long long res_image_stride, int H, int W, int Co8, uint32_t taddr, int half,
                                             int qbase, int n, int y, int x, bool valid, uint32_t full_bar, uint32_t full_par,
-                                            Release &&release, int n_res = -1, bool res_pre = false) {
+                                            Release &&release, int n_res = -1, int res_mode = 0, float res_slope = 0.f) {
     constexpr int NBLK = 4;  // this warp's 32 columns = 4 channel blocks
     const long long plane = (long long)H * W, pix = (long long)y * W + x;
     const int q0 = qbase + half * NBLK;  // first output channel block of this warp (qbase: blocks of earlier N-passes)
@@ -380,7 +383,7 @@ __device__ __forceinline__ void epi_c8_fast(const float *bias_s, __half *out, lo
         const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
         const uint32_t *a = (j < 2 ? a0 : a1) + (j & 1) * 8;
         float2 v[4];
-        const bool pre = has_res && res_pre;  // split-cat convolution: the other half's partial sums join before bias + activation
+        const bool pre = has_res && res_mode == 1;  // split-cat convolution: the other half's partial sums join before bias + activation
 #pragma unroll
         for (int i = 0; i < 4; ++i) {  // packed fp32 pairs (FADD2 / FMUL2): same IEEE results, half the instructions
             v[i] = add2(make_float2(__uint_as_float(a[2 * i]), __uint_as_float(a[2 * i + 1])), bb[i]);
@@ -394,8 +397,16 @@ __device__ __forceinline__ void epi_c8_fast(const float *bias_s, __half *out, lo
         }
         if (has_res && !pre) {
             const uint32_t *h = reinterpret_cast<const uint32_t *>(&res[j]);
+            if (res_mode == 2) {  // mask: gradient through the activation that produced `residual`
 #pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] = add2(v[i], unpack16x2<BF>(h[i]));
+                for (int i = 0; i < 4; ++i) {
+                    const float2 m = unpack16x2<BF>(h[i]);
+                    v[i] = make_float2(m.x > 0.f ? v[i].x : res_slope * v[i].x, m.y > 0.f ? v[i].y : res_slope * v[i].y);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[i] = add2(v[i], unpack16x2<BF>(h[i]));
+            }
         }
         uint4 pk;
         uint32_t *h = reinterpret_cast<uint32_t *>(&pk);
@@ -420,6 +431,7 @@ struct alignas(64) TcConvParams {
     const __half *residual;
     long long res_image_stride;
     int res_pre, res_div;
+    float res_slope;
     int N, H, W, Cout, act, out_mode, sig_from, subsample, dg;
     int tiles_x, tiles_y, num_tiles;
     TileDiv td;
@@ -620,7 +632,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int eg = (warp - TC_EPI_WARP0) / WPG;                  // this warp's group: tiles t == eg (mod groups)
         const int half = ((warp - TC_EPI_WARP0) % WPG) >> 2;         // WPG / 4 warps per lane quarter split the columns
         EpiArgs e{bias_s, p.out, p.out_image_stride, p.residual, p.res_image_stride, p.H, p.W, p.Cout, p.act,
-                  p.out_mode, p.sig_from, p.subsample, p.dg, &p.fin, p.res_pre, p.res_div, p.bf16};
+                  p.out_mode, p.sig_from, p.subsample, p.dg, &p.fin, p.res_pre, p.res_div, p.bf16, p.res_slope};
         EpiTile<NT, WPG / 4> ep;
         uint32_t t = (uint32_t)eg;
         for (int tile = blockIdx.x + eg * gridDim.x; tile < p.num_tiles; tile += EG * gridDim.x, t += EG) {
@@ -869,7 +881,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
         const int eg = (warp - TC_EPI_WARP0) / WPG;
         const int half = ((warp - TC_EPI_WARP0) % WPG) >> 2;
         EpiArgs e{bias_s, p.out, p.out_image_stride, p.residual, p.res_image_stride, p.H, p.W, p.Cout, p.act,
-                  p.out_mode, p.sig_from, p.subsample, p.dg, &p.fin, p.res_pre, p.res_div, p.bf16};
+                  p.out_mode, p.sig_from, p.subsample, p.dg, &p.fin, p.res_pre, p.res_div, p.bf16, p.res_slope};
         EpiTile<NT, WPG / 4> ep;
         uint32_t t = (uint32_t)eg;
         if (NT == 64 && WPG == 8 && p.out_mode == OUT_C8 && !p.subsample && p.debug == 0) {
@@ -893,7 +905,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
                                          tc_fence_before();
                                          __syncwarp();
                                          if (lane == 0) mbar_arrive_cluster(tempty0);
-                                     }, n / p.res_div, p.res_pre != 0);
+                                     }, n / p.res_div, p.res_pre, p.res_slope);
                     if (pr == cid + eg * nclusters && eg == 0 && warp == TC_EPI_WARP0 && lane == 0) STAMP(4);
                     buf += EG;
                     if (buf >= (uint32_t)NB) { buf -= NB; par ^= 1u; }
@@ -1137,7 +1149,7 @@ int launch_conv_tc(const ConvOp &op, cudaStream_t s) {
     p.w = reinterpret_cast<const __half *>(op.w_tc); p.bias = op.bias;
     p.out = op.out; p.out_image_stride = op.out_image_stride;
     p.residual = reinterpret_cast<const __half *>(op.residual); p.res_image_stride = op.res_image_stride;
-    p.res_pre = op.res_pre; p.res_div = op.res_div > 0 ? op.res_div : 1; p.bf16 = op.bf16;
+    p.res_pre = op.res_pre; p.res_div = op.res_div > 0 ? op.res_div : 1; p.bf16 = op.bf16; p.res_slope = op.res_slope;
     p.N = op.N; p.H = op.H; p.W = op.W; p.Cout = op.Cout; p.act = op.act; p.out_mode = op.out_mode;
     p.sig_from = op.sig_from; p.subsample = op.stride == 2 ? 1 : 0; p.dg = op.dg; p.fin = op.fin;
     const int valid = TC_TW - (op.ks - 1);

@@ -123,7 +123,7 @@ def _tiles(N, H, W, ks):
     return N * ((H + 3) // 4) * ((W + 32 - ks) // (33 - ks))
 
 
-def _conv_launch(xs, w_packed, bias, residual, N, H, W, C, Cout, ks, act, shuffle):
+def _conv_launch(xs, w_packed, bias, residual, N, H, W, C, Cout, ks, act, shuffle, res_mode=0, res_slope=0.0):
     dev = xs[0].device
     n = len(xs)
     ptrs = (ctypes.c_void_p * n)(*[x.data_ptr() for x in xs])
@@ -133,7 +133,7 @@ def _conv_launch(xs, w_packed, bias, residual, N, H, W, C, Cout, ks, act, shuffl
     else:
         y = torch.empty((N, (Cout + 7) // 8, H, W, 8), dtype=torch.bfloat16, device=dev)
     _lib.check(_lib.lib().rvsr_c8_conv_fwd(ptrs, strides, n, C, _p(w_packed), _p(bias), _p(residual), _p(y), N, H, W, Cout, ks, 1,
-                                           act, int(shuffle), _stream(dev)), "c8_conv_fwd")
+                                           act, int(shuffle), res_mode, res_slope, _stream(dev)), "c8_conv_fwd")
     return y
 
 
@@ -276,6 +276,85 @@ class _ConvFirstC8(torch.autograd.Function):
 def conv_first(x, weight, bias=None, act=None):
     """First convolution of the network on an NCHW image (<= 16 channels): C8 bf16 output, weight / bias gradients."""
     return _ConvFirstC8.apply(x, weight, bias, ACT[act])
+
+
+_SLOPE = {_lib.ACT_LRELU: 0.1, _lib.ACT_RELU: 0.0}
+
+
+def _wgrad(xs, gp, N, H, W, Cout, ks, need_bias):
+    """Weight (+ bias) gradient of conv(cat(xs)) given the gradient gp of its (pre-activation) output."""
+    L, dev, nsrc = _lib.lib(), gp.device, len(xs)
+    gw = torch.empty((Cout, nsrc * 64, ks, ks), dtype=torch.float32, device=dev)
+    gb = torch.empty(Cout, dtype=torch.float32, device=dev) if need_bias else None
+    ws = torch.empty(L.rvsr_c8_conv_wgrad_workspace_bytes(N, H, W, Cout), dtype=torch.uint8, device=dev)
+    for i, x in enumerate(xs):
+        _lib.check(L.rvsr_c8_conv_wgrad(_p(x), x.stride(0), _p(gp), _p(gw), _p(gb if i == 0 else None), N, H, W, 64, Cout, ks, nsrc * 64,
+                                        i * 64, _p(ws), ws.numel(), _stream(dev)), "c8_conv_wgrad")
+    return gw, gb
+
+
+def _dgrad(weight, gp, i, nsrc, Cout, ks, N, H, W, residual=None, mask=None, slope=0.0):
+    """Gradient of source i (64 channels) of conv(cat(xs), weight): conv(gp, W[:, slice_i]^T flipped) [+ residual] [* act'(mask)]."""
+    gsrc = [gp[:, 8 * k:8 * k + 8] for k in range(Cout // 64)] if Cout >= 64 else [gp]
+    wp = _pack_weight(weight, 64, Cout, ks, False, 1, nsrc * 64, i * 64, _tiles(N, H, W, ks))
+    if mask is not None:
+        return _conv_launch(gsrc, wp, None, mask, N, H, W, min(Cout, 64), 64, ks, _lib.ACT_NONE, False, 2, slope)
+    return _conv_launch(gsrc, wp, None, residual, N, H, W, min(Cout, 64), 64, ks, _lib.ACT_NONE, False)
+
+
+class _ConvPairC8(torch.autograd.Function):
+    """y = act2(conv2(act1(conv1(cat(xs))))) [+ xs[0]]: two chained 64-channel 3x3 convolutions whose intermediate has no other
+    consumer -- ResidualBlock_noBN (arch_util.py:135-139, skip = True) and the conv -> conv pairs of PCD_Align
+    (EDVR_arch.py:104-105, :112-113, :121-122, :128-129).  Knowing that, the backward fuses what autograd would run as separate
+    kernels: the gradient through act1 rides in the epilogue of conv2's data gradient (mask mode), and the skip connection's
+    gradient in the epilogue of conv1's data gradient (residual add)."""
+
+    @staticmethod
+    def forward(ctx, w1, b1, w2, b2, act1, act2, skip, *xs):
+        xs = [x if _src_ok(x) else x.contiguous() for x in xs]
+        N, C8, H, W, _ = xs[0].shape
+        if C8 != 8 or tuple(w1.shape) != (64, 64 * len(xs), 3, 3) or tuple(w2.shape) != (64, 64, 3, 3) or act1 == _lib.ACT_NONE:
+            raise NotImplementedError("conv_pair_c8: 64-channel 3x3 convolutions with an activation in between")
+        if skip and (act2 != _lib.ACT_NONE or len(xs) != 1):
+            raise NotImplementedError("conv_pair_c8: the skip connection is ResidualBlock_noBN's (one input, no final activation)")
+        w1, w2 = w1.contiguous(), w2.contiguous()
+        with torch.cuda.device(w1.device):
+            t = _tiles(N, H, W, 3)
+            h = _conv_launch(xs, _pack_weight(w1, 64, 64 * len(xs), 3, False, 0, 64 * len(xs), 0, t), b1, None, N, H, W, 64, 64, 3, act1, False)
+            y = _conv_launch([h], _pack_weight(w2, 64, 64, 3, False, 0, 64, 0, t), b2, xs[0] if skip else None, N, H, W, 64, 64, 3, act2, False)
+        ctx.meta = (act1, act2, skip, len(xs), N, H, W)
+        ctx.save_for_backward(w1, w2, h, *xs, *([y] if act2 != _lib.ACT_NONE else []))
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        act1, act2, skip, nsrc, N, H, W = ctx.meta
+        sv = ctx.saved_tensors
+        w1, w2, h, xs = sv[0], sv[1], sv[2], sv[3:3 + nsrc]
+        g = _check_c8(g, "conv_pair_c8 backward")
+        needs = ctx.needs_input_grad
+        L, dev = _lib.lib(), g.device
+        with torch.cuda.device(dev):
+            if act2 != _lib.ACT_NONE:
+                g2 = torch.empty_like(g)
+                _lib.check(L.rvsr_c8_act_bwd(_p(g), _p(sv[-1]), _p(g2), g.numel(), act2, _stream(dev)), "c8_act_bwd")
+            else:
+                g2 = g
+            gw2, gb2 = _wgrad([h], g2, N, H, W, 64, 3, needs[3]) if (needs[2] or needs[3]) else (None, None)
+            gh = _dgrad(w2, g2, 0, 1, 64, 3, N, H, W, mask=h, slope=_SLOPE[act1])      # gradient of conv1's pre-activation output
+            gw1, gb1 = _wgrad(xs, gh, N, H, W, 64, 3, needs[1]) if (needs[0] or needs[1]) else (None, None)
+            gxs = [None] * nsrc
+            for i in range(nsrc):
+                if needs[7 + i]:
+                    gxs[i] = _dgrad(w1, gh, i, nsrc, 64, 3, N, H, W, residual=g if (skip and i == 0) else None)
+        return (gw1 if needs[0] else None, gb1, gw2 if needs[2] else None, gb2, None, None, None, *gxs)
+
+
+def conv_pair(xs, w1, b1, act1, w2, b2, act2=None, skip=False):
+    """act2(conv2(act1(conv1(cat(xs))))) [+ xs]: see _ConvPairC8."""
+    if isinstance(xs, torch.Tensor):
+        xs = [xs]
+    return _ConvPairC8.apply(w1, b1, w2, b2, ACT[act1], ACT[act2], bool(skip), *xs)
 
 
 def conv(xs, weight, bias=None, act=None, residual=None, shuffle=False):

@@ -285,3 +285,36 @@ def test_other_architectures_on_the_c8_path(cls, kw):
         cos = float(torch.dot(a, r) / (a.norm() * r.norm()).clamp_min(1e-30))
         assert cos > 0.95, (n, cos)
         assert 0.9 < float(a.norm() / r.norm().clamp_min(1e-30)) < 1.1, n
+
+
+@pytest.mark.parametrize("kind", ["resblock", "pcd_pair"])
+def test_conv_pair_c8(kind):
+    """The fused two-convolution Function (activation gradient in the data-gradient epilogue, skip gradient as its residual)
+    against the same two layers as separate train_c8.conv calls -- which test_conv_forward_backward pins to torch autograd."""
+    from realvsr_b200 import train_c8 as T
+    g = torch.Generator(device="cuda").manual_seed(41)
+    N, H, W = 3, 20, 44
+    nsrc = 1 if kind == "resblock" else 2
+    xs = [_r(torch.randn(N, 64, H, W, device="cuda", generator=g)) for _ in range(nsrc)]
+    w1 = _r(torch.randn(64, 64 * nsrc, 3, 3, device="cuda", generator=g) * 0.05)
+    w2 = _r(torch.randn(64, 64, 3, 3, device="cuda", generator=g) * 0.05)
+    b1, b2 = torch.randn(64, device="cuda", generator=g) * 0.1, torch.randn(64, device="cuda", generator=g) * 0.1
+    gy = _r(torch.randn(N, 64, H, W, device="cuda", generator=g))
+
+    def run(fused):
+        leaves = [t.detach().clone().requires_grad_() for t in xs + [w1, b1, w2, b2]]
+        cx, (lw1, lb1, lw2, lb2) = [T.to_c8(t) for t in leaves[:nsrc]], leaves[nsrc:]
+        if kind == "resblock":
+            y = (T.conv_pair(cx, lw1, lb1, "relu", lw2, lb2, None, skip=True) if fused
+                 else T.conv(T.conv(cx, lw1, lb1, act="relu"), lw2, lb2, residual=cx[0]))
+        else:
+            y = (T.conv_pair(cx, lw1, lb1, "lrelu", lw2, lb2, "lrelu") if fused
+                 else T.conv(T.conv(cx, lw1, lb1, act="lrelu"), lw2, lb2, act="lrelu"))
+        y = T.from_c8(y, 64, torch.float32)
+        return y.detach(), torch.autograd.grad(y, leaves, gy)
+
+    y0, g0 = run(False)
+    y1, g1 = run(True)
+    assert torch.equal(y0, y1)                       # identical forward kernels
+    for a, r in zip(g1, g0):
+        assert a.shape == r.shape and _rel(a, r) < 1e-2   # one bf16 rounding less on the fused path
