@@ -151,6 +151,14 @@ int rvsr_c8_tsa_temporal(const void *aligned, const void *emb, const void *emb_r
                          int H, int W, void *stream);
 int rvsr_c8_tsa_temporal_bwd(const void *const *gout, const void *aligned, const void *emb, const void *emb_ref, const float *prob,
                              void *g_aligned, void *g_emb, void *g_emb_ref, int B, int N, int C, int H, int W, void *stream);
+/* TSA_Fusion's spatial attention helpers on C8 tensors (`planes` = images x channel blocks): MaxPool2d(3, 2, 1) + AvgPool2d(3, 2, 1)
+ * of one tensor in one pass (EDVR_arch.py:154-155) and the gradient w.r.t. that tensor (g_max / g_avg may be NULL; the max
+ * gradient goes to the first maximum of a window, torch's rule); out = fea * sigmoid(att) * 2 + att_add (:206-207) and its
+ * gradients g_fea, g_att (the gradient of att_add is g itself). */
+int rvsr_c8_pool_maxavg(const void *src, void *dst_max, void *dst_avg, long long planes, int H, int W, void *stream);
+int rvsr_c8_pool_maxavg_bwd(const void *src, const void *g_max, const void *g_avg, void *g_src, long long planes, int H, int W, void *stream);
+int rvsr_c8_tsa_final(const void *fea, const void *att, const void *att_add, void *out, long long n_elems, void *stream);
+int rvsr_c8_tsa_final_bwd(const void *g, const void *fea, const void *att, void *g_fea, void *g_att, long long n_elems, void *stream);
 /* ModulatedDeformConvPack.forward / its autograd (deform_conv.py:274-292, :97-153) on C8 tensors, for EDVR's shape class
  * (64 -> 64 channels, 3x3, stride 1, pad 1, 8 deformable groups).  `om` is the output of the conv_offset_mask convolution
  * as a 256-channel C8 tensor (144 offsets, 72 mask logits, 40 zero channels: the 216 outputs padded to whole 64-wide tiles);

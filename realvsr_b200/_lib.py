@@ -49,6 +49,10 @@ SIGNATURES = {
     "rvsr_c8_upsample2x": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, ctypes.c_float, c_int, c_void_p]),
     "rvsr_c8_tsa_temporal": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_void_p), c_void_p] + [c_int] * 5 + [c_void_p]),
     "rvsr_c8_tsa_temporal_bwd": (c_int, [ctypes.POINTER(c_void_p)] + [c_void_p] * 7 + [c_int] * 5 + [c_void_p]),
+    "rvsr_c8_pool_maxavg": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_void_p]),
+    "rvsr_c8_pool_maxavg_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_void_p]),
+    "rvsr_c8_tsa_final": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_void_p]),
+    "rvsr_c8_tsa_final_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_void_p]),
     "rvsr_c8_mdcn_workspace_bytes": (c_size_t, [c_int] * 4),
     "rvsr_c8_mdcn_fwd": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p, c_size_t, c_void_p]),
     "rvsr_c8_mdcn_bwd": (c_int, [c_void_p] * 9 + [c_int] * 4 + [c_void_p, c_size_t, c_void_p]),

@@ -353,22 +353,21 @@ class _EDVRBase(nn.Module):
             return conv(m, t, "lrelu")[:, :, ::2, ::2].contiguous()
 
         def tsa(m, aligned):
-            # TSA_Fusion.forward (EDVR_arch.py:168-208) on C8 tensors: convolutions as above, the rest elementwise torch ops
-            # (a C8 tensor is an ordinary 5-D tensor: channel = 8 * dim 1 + dim 4)
+            # TSA_Fusion.forward (EDVR_arch.py:168-208) on C8 tensors: convolutions as above, temporal attention / pools / final
+            # modulation as train_c8 Functions, the one remaining add is torch's
             a6 = aligned.view(B, N, *aligned.shape[1:])                                   # [B, N, 8, H, W, 8]
             emb_ref = conv(m.tAtt_2, a6[:, self.center].contiguous())                     # [B, 8, H, W, 8]
             srcs = T.tsa_temporal(aligned, conv(m.tAtt_1, aligned), emb_ref, N)           # the N x 64 channels of the 1x1 fusions
             fea = conv(m.fea_fusion, srcs, "lrelu")
             att = conv(m.sAtt_1, srcs, "lrelu")
-            pool = lambda t: (F.max_pool3d(t, (3, 3, 1), (2, 2, 1), (1, 1, 0)), F.avg_pool3d(t, (3, 3, 1), (2, 2, 1), (1, 1, 0)))  # noqa: E731
-            att = conv(m.sAtt_2, list(pool(att)), "lrelu")
+            att = conv(m.sAtt_2, T.pool_maxavg(att), "lrelu")
             att_l = conv(m.sAtt_L1, att, "lrelu")
-            att_l = conv(m.sAtt_L2, list(pool(att_l)), "lrelu")
+            att_l = conv(m.sAtt_L2, T.pool_maxavg(att_l), "lrelu")
             att_l = T.upsample2x(conv(m.sAtt_L3, att_l, "lrelu"))
             att = conv(m.sAtt_3, att, "lrelu") + att_l
             att = conv(m.sAtt_5, T.upsample2x(conv(m.sAtt_4, att, "lrelu")))
             att_add = conv(m.sAtt_add_2, conv(m.sAtt_add_1, att, "lrelu"))
-            return fea * torch.sigmoid(att) * 2 + att_add
+            return T.tsa_final(fea, att, att_add)
 
         with torch.autocast("cuda", dtype=bf):
             x_center = x[:, self.center].contiguous()

@@ -21,6 +21,10 @@ int launch_tsa_temporal_c8(const void *aligned, const void *emb, const void *emb
                            int W, cudaStream_t s);
 int launch_tsa_temporal_bwd_c8(const void *const *gout, const void *aligned, const void *emb, const void *emb_ref, const float *prob,
                                void *g_aligned, void *g_emb, void *g_emb_ref, int B, int N, int H, int W, cudaStream_t s);
+int launch_pool_maxavg_c8(const void *src, void *dmax, void *davg, long long planes, int H, int W, cudaStream_t s);
+int launch_pool_maxavg_bwd_c8(const void *src, const void *gmax, const void *gavg, void *gin, long long planes, int H, int W, cudaStream_t s);
+int launch_tsa_final_c8(const void *fea, const void *att, const void *add, void *out, long long n_elems, cudaStream_t s);
+int launch_tsa_final_bwd_c8(const void *g, const void *fea, const void *att, void *g_fea, void *g_att, long long n_elems, cudaStream_t s);
 }  // namespace rvsr
 
 using namespace rvsr;
@@ -152,6 +156,23 @@ int rvsr_c8_tsa_temporal_bwd(const void *const *gout, const void *aligned, const
     if (C != 64) { set_error("c8 tsa temporal: built for 64 channels"); return RVSR_E_UNSUPPORTED; }
     RVSR_CHECK_ARG(B == 0 || (gout && aligned && emb && emb_ref && prob && g_aligned && g_emb && g_emb_ref), "c8 tsa temporal bwd: null buffer");
     return launch_tsa_temporal_bwd_c8(gout, aligned, emb, emb_ref, prob, g_aligned, g_emb, g_emb_ref, B, N, H, W, (cudaStream_t)stream);
+}
+
+int rvsr_c8_pool_maxavg(const void *src, void *dst_max, void *dst_avg, long long planes, int H, int W, void *stream) {
+    RVSR_CHECK_ARG(planes >= 0 && H > 0 && W > 0 && (planes == 0 || (src && dst_max && dst_avg)), "c8 pool: bad arguments");
+    return launch_pool_maxavg_c8(src, dst_max, dst_avg, planes, H, W, (cudaStream_t)stream);
+}
+int rvsr_c8_pool_maxavg_bwd(const void *src, const void *g_max, const void *g_avg, void *g_src, long long planes, int H, int W, void *stream) {
+    RVSR_CHECK_ARG(planes >= 0 && H > 0 && W > 0 && (planes == 0 || (src && g_src)), "c8 pool bwd: bad arguments");
+    return launch_pool_maxavg_bwd_c8(src, g_max, g_avg, g_src, planes, H, W, (cudaStream_t)stream);
+}
+int rvsr_c8_tsa_final(const void *fea, const void *att, const void *att_add, void *out, long long n_elems, void *stream) {
+    RVSR_CHECK_ARG(n_elems >= 0 && n_elems % 8 == 0 && (n_elems == 0 || (fea && att && att_add && out)), "c8 tsa final: bad arguments");
+    return launch_tsa_final_c8(fea, att, att_add, out, n_elems, (cudaStream_t)stream);
+}
+int rvsr_c8_tsa_final_bwd(const void *g, const void *fea, const void *att, void *g_fea, void *g_att, long long n_elems, void *stream) {
+    RVSR_CHECK_ARG(n_elems >= 0 && n_elems % 8 == 0 && (n_elems == 0 || (g && fea && att && g_fea && g_att)), "c8 tsa final bwd: bad arguments");
+    return launch_tsa_final_bwd_c8(g, fea, att, g_fea, g_att, n_elems, (cudaStream_t)stream);
 }
 
 }  // extern "C"

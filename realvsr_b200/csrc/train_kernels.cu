@@ -480,44 +480,59 @@ __global__ void c8_to_nchw_kernel(const uint4 *__restrict__ src, Tout *__restric
 
 // ---- ModulatedDeformConvPack on C8 tensors: layout glue around dcn_tc_kernel / dcn_bwd_tc_kernel
 // om: the 64 -> 216 offset / mask convolution's output as a 256-channel C8 bf16 tensor (channels: 144 offsets g * 18 + 2 * tap +
-// {dy, dx}, 72 mask logits 144 + g * 9 + tap, 40 zeros -- deform_conv.py:279-283).  One thread per (image, group, pixel) writes
+// {dy, dx}, 72 mask logits 144 + g * 9 + tap, 40 zeros -- deform_conv.py:279-283).  One thread per (image, pixel) writes, group by group,
 //   om24  the forward kernel's format (see om24_from_planar_kernel), mask = sigmoid(logit), and / or
 //   off32 / msk32  planar fp32 [N][144][HW] / [N][72][HW] for the backward kernel.
-__global__ void om_from_c8_kernel(const __nv_bfloat16 *__restrict__ om, uint4 *__restrict__ om24, float *__restrict__ off32,
+__global__ void om_from_c8_kernel(const uint4 *__restrict__ om, uint4 *__restrict__ om24, float *__restrict__ off32,
                                   float *__restrict__ msk32, int HW) {
     const int pix = blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= HW) return;
-    const int g = blockIdx.y;
-    const long long n = blockIdx.z;
-    const __nv_bfloat16 *src = om + n * 32 * (long long)HW * 8;
-    auto ch = [&](int c) { return __bfloat162float(src[((long long)(c >> 3) * HW + pix) * 8 + (c & 7)]); };
-    float o[18], m[10];
+    const long long n = blockIdx.y;
+    const uint4 *src = om + n * 32 * (long long)HW + pix;
+    // One thread per pixel walks the 8 groups; every index below is a compile-time constant after unrolling, so a group's 27
+    // values come out of at most six 16-byte loads (scalar 2-byte loads of the same cells were 3x slower).
 #pragma unroll
-    for (int j = 0; j < 18; ++j) o[j] = ch(g * 18 + j);
+    for (int g = 0; g < 8; ++g) {
+        float o[18], m[10];
+        {
+            const int p0 = (g * 18) / 8, p1 = (g * 18 + 17) / 8;
+            float v[4][8];
 #pragma unroll
-    for (int j = 0; j < 9; ++j) m[j] = __fdividef(1.f, 1.f + __expf(-ch(144 + g * 9 + j)));
-    m[9] = 0.f;
-    if (om24 != nullptr) {
-        uint32_t mw[5];
+            for (int q = 0; q < 4; ++q)
+                if (p0 + q <= p1) unpack8(__ldg(src + (long long)(p0 + q) * HW), v[q]);
 #pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            const __half2 h = __floats2half2_rn(m[2 * k], m[2 * k + 1]);
-            mw[k] = *reinterpret_cast<const uint32_t *>(&h);
+            for (int j = 0; j < 18; ++j) o[j] = v[(g * 18 + j) / 8 - p0][(g * 18 + j) % 8];
+            const int m0 = (144 + g * 9) / 8, m1 = (144 + g * 9 + 8) / 8;
+            float u[2][8];
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+                if (m0 + q <= m1) unpack8(__ldg(src + (long long)(m0 + q) * HW), u[q]);
+#pragma unroll
+            for (int j = 0; j < 9; ++j) m[j] = __fdividef(1.f, 1.f + __expf(-u[(144 + g * 9 + j) / 8 - m0][(144 + g * 9 + j) % 8]));
+            m[9] = 0.f;
         }
-        uint4 *d = om24 + ((n * 24 + g * 3) * (long long)HW + pix) * 2;
-        auto f = [](float v) { return __float_as_uint(v); };
-        d[0] = make_uint4(f(o[0]), f(o[1]), f(o[2]), f(o[3])); d[1] = make_uint4(f(o[4]), f(o[5]), f(o[6]), f(o[7]));
-        d += (long long)HW * 2;
-        d[0] = make_uint4(f(o[8]), f(o[9]), f(o[10]), f(o[11])); d[1] = make_uint4(f(o[12]), f(o[13]), f(o[14]), f(o[15]));
-        d += (long long)HW * 2;
-        d[0] = make_uint4(f(o[16]), f(o[17]), mw[0], mw[1]); d[1] = make_uint4(mw[2], mw[3], mw[4], 0u);
-    }
-    if (off32 != nullptr) {
-        float *po = off32 + (n * 144 + g * 18) * (long long)HW + pix, *pm = msk32 + (n * 72 + g * 9) * (long long)HW + pix;
+        if (om24 != nullptr) {
+            uint32_t mw[5];
 #pragma unroll
-        for (int j = 0; j < 18; ++j) po[(long long)j * HW] = o[j];
+            for (int k = 0; k < 5; ++k) {
+                const __half2 h = __floats2half2_rn(m[2 * k], m[2 * k + 1]);
+                mw[k] = *reinterpret_cast<const uint32_t *>(&h);
+            }
+            uint4 *d = om24 + ((n * 24 + g * 3) * (long long)HW + pix) * 2;
+            auto f = [](float v) { return __float_as_uint(v); };
+            d[0] = make_uint4(f(o[0]), f(o[1]), f(o[2]), f(o[3])); d[1] = make_uint4(f(o[4]), f(o[5]), f(o[6]), f(o[7]));
+            d += (long long)HW * 2;
+            d[0] = make_uint4(f(o[8]), f(o[9]), f(o[10]), f(o[11])); d[1] = make_uint4(f(o[12]), f(o[13]), f(o[14]), f(o[15]));
+            d += (long long)HW * 2;
+            d[0] = make_uint4(f(o[16]), f(o[17]), mw[0], mw[1]); d[1] = make_uint4(mw[2], mw[3], mw[4], 0u);
+        }
+        if (off32 != nullptr) {
+            float *po = off32 + (n * 144 + g * 18) * (long long)HW + pix, *pm = msk32 + (n * 72 + g * 9) * (long long)HW + pix;
 #pragma unroll
-        for (int j = 0; j < 9; ++j) pm[(long long)j * HW] = m[j];
+            for (int j = 0; j < 18; ++j) po[(long long)j * HW] = o[j];
+#pragma unroll
+            for (int j = 0; j < 9; ++j) pm[(long long)j * HW] = m[j];
+        }
     }
 }
 // gradient of the 256-channel convolution output from the operator's planar fp32 gradients: offsets as they are, mask logits
@@ -673,6 +688,107 @@ __global__ void tsa_temporal_bwd_c8_kernel(TsaPtrs gout, const uint4 *__restrict
     }
 }
 
+// ---- TSA spatial attention helpers (EDVR_arch.py:154-155, :186-208) on C8 tensors
+// MaxPool2d(3, 2, 1) and AvgPool2d(3, 2, 1) (count_include_pad) of one tensor in one pass; cells = 16-byte (8-channel) units
+__global__ void pool_maxavg_c8_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dmax, uint4 *__restrict__ davg, int H, int W,
+                                      long long total) {
+    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % Wo);
+        long long r = i / Wo;
+        const int oy = (int)(r % Ho);
+        const uint4 *p = src + (r / Ho) * H * W;
+        float mx[8], sm[8], v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { mx[k] = -INFINITY; sm[k] = 0.f; }
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int y = 2 * oy + dy, x = 2 * ox + dx;
+                if (y < 0 || y >= H || x < 0 || x >= W) continue;
+                unpack8(__ldg(p + (long long)y * W + x), v);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { mx[k] = fmaxf(mx[k], v[k]); sm[k] += v[k]; }
+            }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sm[k] *= (1.f / 9.f);
+        dmax[i] = pack8(mx);
+        davg[i] = pack8(sm);
+    }
+}
+// gradient of both pools w.r.t. their common input: one thread per INPUT cell visits the <= 4 windows that contain it; the max
+// pool's gradient goes to the FIRST maximum of a window in row-major order (torch's rule), found by re-scanning the window
+__global__ void pool_maxavg_bwd_c8_kernel(const uint4 *__restrict__ src, const uint4 *__restrict__ gmax, const uint4 *__restrict__ gavg,
+                                          uint4 *__restrict__ gin, int H, int W, long long total) {
+    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W);
+        long long r = i / W;
+        const int y = (int)(r % H);
+        const long long pl = r / H;
+        const uint4 *p = src + pl * H * W;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int oy = y / 2; oy <= (y + 1) / 2; ++oy) {
+            if (oy >= Ho) continue;
+            for (int ox = x / 2; ox <= (x + 1) / 2; ++ox) {
+                if (ox >= Wo) continue;
+                const long long o = (pl * Ho + oy) * Wo + ox;
+                float ga[8], gm[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (gavg != nullptr) {
+                    unpack8(__ldg(gavg + o), ga);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) acc[k] += ga[k] * (1.f / 9.f);
+                }
+                if (gmax == nullptr) continue;
+                unpack8(__ldg(gmax + o), gm);
+                float best[8];
+                int arg[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { best[k] = -INFINITY; arg[k] = -1; }
+                for (int dy = -1; dy <= 1; ++dy)
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        const int yy = 2 * oy + dy, xx = 2 * ox + dx;
+                        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+                        float v[8];
+                        unpack8(__ldg(p + (long long)yy * W + xx), v);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            if (v[k] > best[k] || arg[k] < 0) { best[k] = v[k]; arg[k] = yy * W + xx; }
+                    }
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (arg[k] == y * W + x) acc[k] += gm[k];
+            }
+        }
+        gin[i] = pack8(acc);
+    }
+}
+// out = fea * sigmoid(att) * 2 + att_add (EDVR_arch.py:206-207) and its gradient (g_att_add = g: no kernel needed)
+__global__ void tsa_final_c8_kernel(const uint4 *__restrict__ fea, const uint4 *__restrict__ att, const uint4 *__restrict__ add,
+                                    uint4 *__restrict__ out, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float f[8], a[8], d[8];
+        unpack8(__ldg(fea + i), f); unpack8(__ldg(att + i), a); unpack8(__ldg(add + i), d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = f[k] * (2.f * __fdividef(1.f, 1.f + __expf(-a[k]))) + d[k];
+        out[i] = pack8(f);
+    }
+}
+__global__ void tsa_final_bwd_c8_kernel(const uint4 *__restrict__ g, const uint4 *__restrict__ fea, const uint4 *__restrict__ att,
+                                        uint4 *__restrict__ g_fea, uint4 *__restrict__ g_att, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float gv[8], f[8], a[8], gf[8], ga[8];
+        unpack8(__ldg(g + i), gv); unpack8(__ldg(fea + i), f); unpack8(__ldg(att + i), a);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float sg = __fdividef(1.f, 1.f + __expf(-a[k]));
+            gf[k] = gv[k] * 2.f * sg;
+            ga[k] = gv[k] * f[k] * 2.f * sg * (1.f - sg);
+        }
+        g_fea[i] = pack8(gf);
+        g_att[i] = pack8(ga);
+    }
+}
+
 static int ew_grid(long long n) {
     long long b = (n + 255) / 256;
     const long long cap = (long long)sm_count() * 16;
@@ -807,6 +923,33 @@ int launch_c8_to_nchw_bf16(const void *src, void *dst, int dst_dtype, int N, int
     return RVSR_OK;
 }
 
+int launch_pool_maxavg_c8(const void *src, void *dmax, void *davg, long long planes, int H, int W, cudaStream_t s) {
+    const long long total = planes * ((H - 1) / 2 + 1) * ((W - 1) / 2 + 1);
+    if (total == 0) return RVSR_OK;
+    pool_maxavg_c8_kernel<<<ew_grid(total), 256, 0, s>>>((const uint4 *)src, (uint4 *)dmax, (uint4 *)davg, H, W, total);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+int launch_pool_maxavg_bwd_c8(const void *src, const void *gmax, const void *gavg, void *gin, long long planes, int H, int W, cudaStream_t s) {
+    const long long total = planes * H * W;
+    if (total == 0) return RVSR_OK;
+    pool_maxavg_bwd_c8_kernel<<<ew_grid(total), 256, 0, s>>>((const uint4 *)src, (const uint4 *)gmax, (const uint4 *)gavg, (uint4 *)gin, H, W, total);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+int launch_tsa_final_c8(const void *fea, const void *att, const void *add, void *out, long long n_elems, cudaStream_t s) {
+    if (n_elems == 0) return RVSR_OK;
+    tsa_final_c8_kernel<<<ew_grid(n_elems / 8), 256, 0, s>>>((const uint4 *)fea, (const uint4 *)att, (const uint4 *)add, (uint4 *)out, n_elems / 8);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+int launch_tsa_final_bwd_c8(const void *g, const void *fea, const void *att, void *g_fea, void *g_att, long long n_elems, cudaStream_t s) {
+    if (n_elems == 0) return RVSR_OK;
+    tsa_final_bwd_c8_kernel<<<ew_grid(n_elems / 8), 256, 0, s>>>((const uint4 *)g, (const uint4 *)fea, (const uint4 *)att, (uint4 *)g_fea, (uint4 *)g_att, n_elems / 8);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
+}
+
 int launch_tsa_temporal_c8(const void *aligned, const void *emb, const void *emb_ref, void *const *out, float *prob, int B, int N, int H,
                            int W, cudaStream_t s) {
     RVSR_CHECK_ARG(N >= 1 && N <= RVSR_MAX_SRC_TC, "tsa temporal: 1..%d frames", RVSR_MAX_SRC_TC);
@@ -851,7 +994,8 @@ int c8_mdcn_fwd(const void *x, const void *om, const float *weight, const float 
     void *x16 = take(px * 128), *y16 = take(px * 128), *om24 = take(px * 768), *wtc = take(tc_dcn_weight_bytes(64, 64, 9) + 16);
     const int HW = H * W;
     cvt_bf16_to_f16_kernel<<<ew_grid((long long)px * 8), 256, 0, s>>>((const uint4 *)x, (uint4 *)x16, (long long)px * 8);
-    om_from_c8_kernel<<<dim3((HW + 127) / 128, 8, N), 128, 0, s>>>((const __nv_bfloat16 *)om, (uint4 *)om24, nullptr, nullptr, HW);
+    RVSR_CHECK_ARG(N <= 65535, "c8 mdcn: too many images");
+    om_from_c8_kernel<<<dim3((HW + 127) / 128, N), 128, 0, s>>>((const uint4 *)om, (uint4 *)om24, nullptr, nullptr, HW);
     RVSR_LAUNCH_CHECK();
     RVSR_TRY(pack_weight_dcn_tc(weight, wtc, 64, 64, 9, s));
     DcnOp op = {};
@@ -888,7 +1032,7 @@ int c8_mdcn_bwd(const void *x, const void *om, const float *weight, const void *
         RVSR_TRY(launch_act_bwd_c8(g, y, gact, (long long)px * 64, act, s));
         gp = gact;
     }
-    om_from_c8_kernel<<<dim3((HW + 127) / 128, 8, N), 128, 0, s>>>((const __nv_bfloat16 *)om, nullptr, off32, msk32, HW);
+    om_from_c8_kernel<<<dim3((HW + 127) / 128, N), 128, 0, s>>>((const uint4 *)om, nullptr, off32, msk32, HW);
     RVSR_LAUNCH_CHECK();
     RVSR_TRY(launch_convert_f32_bf16(weight, wbf, 64 * 64 * 9, s));
     RVSR_TRY(pack_wt_dcn_bwd_tc(wbf, wt, s));

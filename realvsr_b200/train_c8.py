@@ -446,6 +446,66 @@ def tsa_temporal(aligned, emb, emb_ref, N):
     return list(_TsaTemporalC8.apply(aligned, emb, emb_ref, N))
 
 
+class _PoolMaxAvgC8(torch.autograd.Function):
+    """(MaxPool2d(3, 2, 1)(x), AvgPool2d(3, 2, 1)(x)) of a C8 tensor in one pass (TSA_Fusion, EDVR_arch.py:154-155, :187, :191)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _check_c8(x, "pool_maxavg_c8")
+        N, P, H, W, _ = x.shape
+        shape = (N, P, (H - 1) // 2 + 1, (W - 1) // 2 + 1, 8)
+        mx, av = torch.empty(shape, dtype=torch.bfloat16, device=x.device), torch.empty(shape, dtype=torch.bfloat16, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().rvsr_c8_pool_maxavg(_p(x), _p(mx), _p(av), N * P, H, W, _stream(x.device)), "c8_pool_maxavg")
+        ctx.save_for_backward(x)
+        return mx, av
+
+    @staticmethod
+    def backward(ctx, g_max, g_avg):
+        (x,) = ctx.saved_tensors
+        N, P, H, W, _ = x.shape
+        g_max = None if g_max is None else _check_c8(g_max, "pool backward")
+        g_avg = None if g_avg is None else _check_c8(g_avg, "pool backward")
+        gx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().rvsr_c8_pool_maxavg_bwd(_p(x), _p(g_max), _p(g_avg), _p(gx), N * P, H, W, _stream(x.device)),
+                       "c8_pool_maxavg_bwd")
+        return gx
+
+
+def pool_maxavg(x):
+    return list(_PoolMaxAvgC8.apply(x))
+
+
+class _TsaFinalC8(torch.autograd.Function):
+    """fea * sigmoid(att) * 2 + att_add (TSA_Fusion, EDVR_arch.py:206-207)."""
+
+    @staticmethod
+    def forward(ctx, fea, att, att_add):
+        fea, att, att_add = _check_c8(fea, "tsa_final fea"), _check_c8(att, "tsa_final att"), _check_c8(att_add, "tsa_final att_add")
+        if fea.shape != att.shape or fea.shape != att_add.shape:
+            raise RuntimeError("tsa_final_c8: shapes differ")
+        out = torch.empty_like(fea)
+        with torch.cuda.device(fea.device):
+            _lib.check(_lib.lib().rvsr_c8_tsa_final(_p(fea), _p(att), _p(att_add), _p(out), fea.numel(), _stream(fea.device)), "c8_tsa_final")
+        ctx.save_for_backward(fea, att)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        fea, att = ctx.saved_tensors
+        g = _check_c8(g, "tsa_final backward")
+        g_fea, g_att = torch.empty_like(fea), torch.empty_like(att)
+        with torch.cuda.device(fea.device):
+            _lib.check(_lib.lib().rvsr_c8_tsa_final_bwd(_p(g), _p(fea), _p(att), _p(g_fea), _p(g_att), fea.numel(), _stream(fea.device)),
+                       "c8_tsa_final_bwd")
+        return g_fea, g_att, g
+
+
+def tsa_final(fea, att, att_add):
+    return _TsaFinalC8.apply(fea, att, att_add)
+
+
 # ---------------------------------------------------------------- x2 bilinear upsample (optionally scaled)
 class _Up2C8(torch.autograd.Function):
     @staticmethod

@@ -318,3 +318,30 @@ def test_conv_pair_c8(kind):
     assert torch.equal(y0, y1)                       # identical forward kernels
     for a, r in zip(g1, g0):
         assert a.shape == r.shape and _rel(a, r) < 1e-2   # one bf16 rounding less on the fused path
+
+
+def test_pool_and_tsa_final_c8():
+    """MaxPool2d(3,2,1) + AvgPool2d(3,2,1) (with TIES: bf16 feature maps have them, the gradient must go to the first maximum
+    like torch's) and fea * sigmoid(att) * 2 + att_add, forward and gradients, against torch."""
+    from realvsr_b200 import train_c8 as T
+    g = torch.Generator(device="cuda").manual_seed(51)
+    N, C, H, W = 3, 16, 11, 14
+    x = (torch.randint(0, 6, (N, C, H, W), device="cuda", generator=g).float() * 0.25).requires_grad_()   # few distinct values -> ties
+    mx_ref, av_ref = F.max_pool2d(x, 3, 2, 1), F.avg_pool2d(x, 3, 2, 1)
+    g1, g2 = _r(torch.randn(mx_ref.shape, device="cuda", generator=g)), _r(torch.randn(mx_ref.shape, device="cuda", generator=g))
+    (gx_ref,) = torch.autograd.grad([mx_ref, av_ref], [x], [g1, g2])
+    x2 = x.detach().clone().requires_grad_()
+    mx, av = T.pool_maxavg(T.to_c8(x2))
+    mx, av = T.from_c8(mx, C, torch.float32), T.from_c8(av, C, torch.float32)
+    assert torch.equal(mx, mx_ref.detach()) and _rel(av, av_ref.detach()) < 1e-2
+    (gx,) = torch.autograd.grad([mx, av], [x2], [g1, g2])
+    assert _rel(gx, gx_ref) < 1e-2
+    fea, att, add = [_r(torch.randn(N, C, H, W, device="cuda", generator=g)).requires_grad_() for _ in range(3)]
+    ref = fea * torch.sigmoid(att) * 2 + add
+    gy = _r(torch.randn(ref.shape, device="cuda", generator=g))
+    gref = torch.autograd.grad(ref, [fea, att, add], gy)
+    leaves = [t.detach().clone().requires_grad_() for t in (fea, att, add)]
+    out = T.from_c8(T.tsa_final(*[T.to_c8(t) for t in leaves]), C, torch.float32)
+    assert _rel(out, ref.detach()) < 1e-2
+    for a, r in zip(torch.autograd.grad(out, leaves, gy), gref):
+        assert _rel(a, r) < 1e-2
