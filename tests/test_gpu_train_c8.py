@@ -345,3 +345,47 @@ def test_pool_and_tsa_final_c8():
     assert _rel(out, ref.detach()) < 1e-2
     for a, r in zip(torch.autograd.grad(out, leaves, gy), gref):
         assert _rel(a, r) < 1e-2
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_dataparallel_training_step_on_the_c8_path():
+    """nn.DataParallel (the wrapper the reference's training models use, VideoSR_AllPair_model_YCbCr_Split.py:36) around the
+    module, bf16 autocast step: every replica runs the train_c8 path on its device with the broadcast weights, the gradients
+    arrive on the wrapped module's parameters and agree with the single-device step on the whole batch."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers import load_case
+    from synth import synth_normal
+    from realvsr_b200.archs import EDVR_arch as E
+    c = load_case("edvr_nf64_crop")
+    net = E.EDVR(**c["kwargs"]).train()
+    net.load_state_dict(c["sd"], strict=True)
+    net = net.to("cuda:0")
+    x = torch.cat([c["x"], c["x"].flip(3), c["x"].flip(4), c["x"].flip(3).flip(4)], 0).to("cuda:0")
+    gt = synth_normal((4,) + tuple(c["out"].shape[1:]), 56, std=0.3).to("cuda:0") + 0.5
+
+    # torch's parallel_apply re-enters autocast in the replica threads WITHOUT the dtype (they see the thread default, float16),
+    # so "bf16 autocast around a DataParallel model" is not bf16 inside the replicas -- the explicit switch is the way here
+    net.exec_path = "train_c8"
+
+    def grads(model):
+        net.zero_grad(set_to_none=True)
+        loss = F.l1_loss(model(x).float(), gt)
+        loss.backward()
+        return float(loss.detach()), [p.grad.detach().clone() for p in net.parameters()]
+
+    l1, g1 = grads(net)
+    l2, g2 = grads(torch.nn.DataParallel(net, device_ids=[0, 1]))
+    diffs = [float((a - b).abs().max() / b.abs().max().clamp_min(1e-12)) for a, b in zip(g2, g1)]
+    worst = max(diffs)
+    if worst >= 2e-2:
+        for (n_, _), d_ in zip(net.named_parameters(), diffs):
+            if d_ > 5e-3:
+                print("   %-50s %.3e" % (n_, d_))
+    print("DataParallel vs single device: loss %.6f vs %.6f, worst relative gradient difference %.2e" % (l2, l1, worst))
+    assert abs(l1 - l2) < 1e-3 * l1
+    # two devices sum a weight gradient as (batch half 0) + (batch half 1), one device in tile order: fp32 sums of the same bf16
+    # products in another order, on top of the atomics inside dcn_bwd_tc_kernel
+    assert worst < 2e-2

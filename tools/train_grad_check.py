@@ -1,3 +1,5 @@
+"""Per-parameter gradient agreement of one training step three ways (EDVR nf = 64 crop): fp32 module path, torch autocast(bf16) on
+the module path (cuDNN), and the train_c8 path.  Prints cosine / norm ratio against fp32 for every parameter."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")):
@@ -11,8 +13,9 @@ c = load_case("edvr_nf64_crop")
 net = E.EDVR(**c["kwargs"]).train()
 net.load_state_dict(c["sd"], strict=True)
 net = net.to("cuda")
-x = torch.cat([c["x"], c["x"].flip(3)], 0).to("cuda")
-gt = synth_normal((2,) + tuple(c["out"].shape[1:]), 55, std=0.3).to("cuda") + 0.5
+NB = int(os.environ.get("NB", "2"))
+x = torch.cat([c["x"], c["x"].flip(3), c["x"].flip(4), c["x"].flip(3).flip(4)][:NB], 0).to("cuda")
+gt = synth_normal((NB,) + tuple(c["out"].shape[1:]), 55, std=0.3).to("cuda") + 0.5
 def grads(path, amp):
     net.exec_path = path
     net.zero_grad(set_to_none=True)
