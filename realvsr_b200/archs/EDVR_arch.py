@@ -316,9 +316,10 @@ class _EDVRBase(nn.Module):
         want = self.exec_path == "train_c8" or (self.exec_path == "auto" and torch.is_autocast_enabled() and
                                                 torch.get_autocast_dtype("cuda") == torch.bfloat16 and
                                                 os.environ.get("RVSR_TRAIN_C8", "1") != "0")
-        ok = (x.is_cuda and self.nf == 64 and not (self._upsample and (self.is_predeblur or self.HR_in)))
+        # the frames themselves get no gradient on this path (train_c8.conv_first): an input that requires one takes the module path
+        ok = (x.is_cuda and self.nf == 64 and not x.requires_grad and not (self._upsample and (self.is_predeblur or self.HR_in)))
         if want and not ok and self.exec_path == "train_c8":
-            raise RuntimeError("realvsr_b200: exec_path='train_c8' needs CUDA input, nf == 64 and the standard stem")
+            raise RuntimeError("realvsr_b200: exec_path='train_c8' needs CUDA input without requires_grad, nf == 64 and the standard stem")
         return want and ok
 
     def _forward_c8(self, x):

@@ -82,6 +82,36 @@ def test_conv_argument_validation_without_gpu():
     assert L.rvsr_conv2d_fwd_workspace_bytes(1, 64, 64, 16, 16, 64, 3, 1) > 0
 
 
+def test_training_entry_points_validate_arguments_without_gpu():
+    """rvsr_c8_* (the bf16 training path): bad arguments come back as error codes before anything touches the device."""
+    L = _lib.lib()
+    nul = ctypes.c_void_p(0)
+    one = ctypes.c_void_p(256)   # never dereferenced: every call below fails its argument checks first
+    ptrs, strides = (ctypes.c_void_p * 1)(256), (ctypes.c_longlong * 1)(64 * 16)
+    # no sources / too many sources
+    assert L.rvsr_c8_conv_fwd(ptrs, strides, 0, 64, one, nul, nul, one, 1, 4, 4, 64, 3, 1, 0, 0, 0, 0.0, nul) == _lib.E_INVALID
+    assert b"sources" in L.rvsr_last_error()
+    # pixel shuffle with a residual; mask mode without a mask tensor; 5x5 kernel
+    assert L.rvsr_c8_conv_fwd(ptrs, strides, 1, 64, one, nul, one, one, 1, 4, 4, 256, 3, 1, 0, 1, 0, 0.0, nul) == _lib.E_INVALID
+    assert L.rvsr_c8_conv_fwd(ptrs, strides, 1, 64, one, nul, nul, one, 1, 4, 4, 64, 3, 1, 0, 0, 2, 0.1, nul) == _lib.E_INVALID
+    assert L.rvsr_c8_conv_fwd(ptrs, strides, 1, 64, one, nul, nul, one, 1, 4, 4, 64, 5, 1, 0, 0, 0, 0.0, nul) == _lib.E_INVALID
+    # shapes the tcgen05 kernels do not cover are UNSUPPORTED (NotImplementedError on the Python side), never a silent fallback
+    assert L.rvsr_c8_conv_weight_bytes(216, 64, 3, 0) == 0 and L.rvsr_c8_conv_weight_bytes(256, 64, 3, 0) > 0
+    assert L.rvsr_c8_conv_pack_weight(one, one, 216, 64, 3, 0, 0, 64, 0, 3, nul) == _lib.E_UNSUPPORTED
+    assert L.rvsr_c8_conv_pack_weight(one, ctypes.c_void_p(264), 64, 64, 3, 0, 0, 64, 0, 3, nul) == _lib.E_INVALID  # unaligned destination
+    assert L.rvsr_c8_conv_pack_weight(one, one, 64, 64, 3, 0, 1, 128, 96, 3, nul) == _lib.E_INVALID               # slice past the row
+    assert L.rvsr_c8_conv_wgrad(one, 64 * 16, one, one, nul, 1, 4, 4, 32, 64, 3, 32, 0, one, 1 << 20, nul) == _lib.E_UNSUPPORTED  # Cin != 64
+    assert L.rvsr_c8_conv_wgrad_workspace_bytes(80, 64, 64, 64) >= 148 * 6 * 128 * 64 * 4
+    assert L.rvsr_c8_act_bwd(one, one, one, 64, 0, nul) == _lib.E_INVALID                       # no activation to differentiate
+    assert L.rvsr_c8_unshuffle2_act_bwd(one, one, one, 1, 48, 4, 4, 1, nul) == _lib.E_INVALID   # C % 32
+    assert L.rvsr_c8_tsa_temporal(one, one, one, ptrs, one, 1, 5, 32, 4, 4, nul) == _lib.E_UNSUPPORTED
+    assert L.rvsr_c8_from_nchw(one, _lib.BF16, one, 1, 20, 4, 4, 2, nul) == _lib.E_INVALID      # 2 channel blocks cannot hold 20 channels
+    assert L.rvsr_c8_mdcn_fwd(one, one, one, nul, one, 1, 4, 4, 0, one, 16, nul) == _lib.E_INVALID  # workspace too small
+    # empty batches are no-ops
+    assert L.rvsr_c8_conv_fwd(ptrs, strides, 1, 64, one, nul, nul, one, 0, 4, 4, 64, 3, 1, 0, 0, 0, 0.0, nul) == _lib.OK
+    assert L.rvsr_c8_upsample2x(nul, nul, 0, 4, 4, 1.0, 0, nul) == _lib.OK
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "_lib", None)
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
