@@ -389,3 +389,45 @@ def test_dataparallel_training_step_on_the_c8_path():
     # two devices sum a weight gradient as (batch half 0) + (batch half 1), one device in tile order: fp32 sums of the same bf16
     # products in another order, on top of the atomics inside dcn_bwd_tc_kernel
     assert worst < 2e-2
+
+
+def test_graphed_step_follows_the_optimizer():
+    """train_c8.GraphedStep: the captured step re-packs the weights INSIDE the graph, so every replay sees the optimizer's last
+    update.  Three SGD steps replayed from the graph against the same three steps run eagerly: same losses, same final weights."""
+    import copy
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers import load_case
+    from synth import synth_normal
+    from realvsr_b200 import train_c8 as T
+    from realvsr_b200.archs import EDVR_arch as E
+    c = load_case("edvr_nf64_crop")
+    net = E.EDVR(**c["kwargs"]).train()
+    net.load_state_dict(c["sd"], strict=True)
+    net = net.to("cuda")
+    ref = copy.deepcopy(net)
+    x = torch.cat([c["x"], c["x"].flip(3)], 0).to("cuda")
+    gt = synth_normal((2,) + tuple(c["out"].shape[1:]), 57, std=0.3).to("cuda") + 0.5
+    lr = 2e-3
+    losses_eager = []
+    opt = torch.optim.SGD(ref.parameters(), lr=lr)
+    for _ in range(3):
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = F.l1_loss(ref(x).float(), gt)
+        loss.backward()
+        opt.step()
+        losses_eager.append(float(loss.detach()))
+    step = T.GraphedStep(net, F.l1_loss, x, gt)          # warm-up runs forward / backward only: the weights are untouched
+    opt = torch.optim.SGD(net.parameters(), lr=lr)
+    losses_graph = []
+    for _ in range(3):
+        losses_graph.append(float(step(x, gt)))
+        opt.step()
+    assert losses_eager[2] < losses_eager[0]             # the steps do something
+    for a, b in zip(losses_graph, losses_eager):
+        assert abs(a - b) < 2e-3 * b, (losses_graph, losses_eager)
+    for (n, p), q in zip(net.named_parameters(), ref.parameters()):
+        assert float((p.detach() - q.detach()).abs().max()) <= 2e-2 * lr * 50 + 1e-3 * float(q.detach().abs().max()), n
