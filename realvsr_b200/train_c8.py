@@ -2,14 +2,17 @@
 
 BASELINE cfg5 is a bf16 training step.  Under torch.autocast every nn.Conv2d of EDVR_arch.py runs on cuDNN, which
 spends more time converting NCHW <-> NHWC, reducing bias gradients and launching elementwise kernels than convolving
-(profiles/r02_cfg5_profile.txt).  Here activations stay in the inference engine's layout -- [N, C/8, H, W, 8] bfloat16,
-an ordinary 5-D torch tensor -- between layers, and each layer is one Function whose forward AND backward are this
-library's tcgen05 kernels:
+(profiles/r02_cfg5_profile.txt, lower half).  Here activations stay in the inference engine's layout -- [N, C/8, H, W, 8]
+bfloat16, an ordinary 5-D torch tensor -- between layers, and each layer is one Function whose forward AND backward are
+this library's kernels:
 
-    forward        rvsr_c8_conv_fwd (bias, activation, residual add, torch.cat of the inputs, PixelShuffle(2) fused)
-    data gradient  the same kernel with the transposed, flipped weights (one launch per concatenated input)
-    weight + bias  rvsr_c8_conv_wgrad (pixel-K GEMM on tcgen05; fp32 accumulate over the whole batch)
-    activation     rvsr_c8_act_bwd / rvsr_c8_unshuffle2_act_bwd on the saved OUTPUT (no pre-activation is stored)
+    conv / conv_pair / conv_first   forward: rvsr_c8_conv_fwd (bias, activation, residual add, torch.cat of the inputs,
+                                    PixelShuffle(2) fused); data gradient: the same kernel with the transposed, flipped weights
+                                    (one launch per concatenated input); weight + bias gradient: rvsr_c8_conv_wgrad (pixel-K
+                                    GEMM on tcgen05, fixed summation order); activation gradient from the saved OUTPUT
+    dcn_pack                        ModulatedDeformConvPack on dcn_tc_kernel / dcn_bwd_tc_kernel
+    upsample2x, tsa_temporal, pool_maxavg, tsa_final, to_c8 / from_c8     one CUDA-core kernel per direction
+    GraphedStep                     forward + loss + backward as ONE CUDA graph
 
 torch.autograd still owns the graph: it sums the gradients of a tensor with several consumers and calls these
 backwards in order.  Parameters stay fp32 OIHW nn.Parameters (the reference's state_dict contract); they are re-packed
@@ -144,6 +147,30 @@ def _src_ok(x):
     return s[4] == 1 and s[3] == 8 and s[2] == 8 * W and s[1] == 8 * W * H
 
 
+_SLOPE = {_lib.ACT_LRELU: 0.1, _lib.ACT_RELU: 0.0}
+
+
+def _wgrad(xs, gp, N, H, W, Cout, ks, need_bias):
+    """Weight (+ bias) gradient of conv(cat(xs)) given the gradient gp of its (pre-activation) output."""
+    L, dev, nsrc = _lib.lib(), gp.device, len(xs)
+    gw = torch.empty((Cout, nsrc * 64, ks, ks), dtype=torch.float32, device=dev)
+    gb = torch.empty(Cout, dtype=torch.float32, device=dev) if need_bias else None
+    ws = torch.empty(L.rvsr_c8_conv_wgrad_workspace_bytes(N, H, W, Cout), dtype=torch.uint8, device=dev)
+    for i, x in enumerate(xs):
+        _lib.check(L.rvsr_c8_conv_wgrad(_p(x), x.stride(0), _p(gp), _p(gw), _p(gb if i == 0 else None), N, H, W, 64, Cout, ks, nsrc * 64,
+                                        i * 64, _p(ws), ws.numel(), _stream(dev)), "c8_conv_wgrad")
+    return gw, gb
+
+
+def _dgrad(weight, gp, i, nsrc, Cout, ks, N, H, W, residual=None, mask=None, slope=0.0):
+    """Gradient of source i (64 channels) of conv(cat(xs), weight): conv(gp, W[:, slice_i]^T flipped) [+ residual] [* act'(mask)]."""
+    gsrc = [gp[:, 8 * k:8 * k + 8] for k in range(Cout // 64)] if Cout >= 64 else [gp]
+    wp = _pack_weight(weight, 64, Cout, ks, False, 1, nsrc * 64, i * 64, _tiles(N, H, W, ks))
+    if mask is not None:
+        return _conv_launch(gsrc, wp, None, mask, N, H, W, min(Cout, 64), 64, ks, _lib.ACT_NONE, False, 2, slope)
+    return _conv_launch(gsrc, wp, None, residual, N, H, W, min(Cout, 64), 64, ks, _lib.ACT_NONE, False)
+
+
 class _ConvC8(torch.autograd.Function):
     """y = [PixelShuffle2](act(conv(cat(xs), weight) + bias)) [+ residual]; stride 1, pad ks // 2."""
 
@@ -200,26 +227,16 @@ class _ConvC8(torch.autograd.Function):
             if needs[0] or needs[1]:
                 if C != 64:
                     raise NotImplementedError("conv_c8: the weight gradient is built for 64-channel sources")
-                gw = torch.empty((Cout, nsrc * C, ks, ks), dtype=torch.float32, device=dev)
-                gb = torch.empty(Cout, dtype=torch.float32, device=dev) if needs[1] else None
-                ws = torch.empty(L.rvsr_c8_conv_wgrad_workspace_bytes(N, H, W, Cout), dtype=torch.uint8, device=dev)
-                for i, x in enumerate(xs):
-                    _lib.check(L.rvsr_c8_conv_wgrad(_p(x), x.stride(0), _p(gp), _p(gw), _p(gb if i == 0 else None), N, H, W, C, Cout, ks,
-                                                    nsrc * C, i * C, _p(ws), ws.numel(), s), "c8_conv_wgrad")
+                gw, gb = _wgrad(xs, gp, N, H, W, Cout, ks, needs[1])
                 if not needs[0]:
                     gw = None
             gxs = [None] * nsrc
             if any(needs[5:5 + nsrc]):
                 # dX_i = conv(dY, W[:, slice_i]^T flipped): Cout gradient channels enter as 64-channel sources
-                if Cout % 64 != 0 and not (Cout < 64 and Cout % 16 == 0):
-                    raise NotImplementedError("conv_c8: the data gradient needs Cout %% 64 == 0 or Cout in {16, 32, 48} (got %d)" % Cout)
-                gc = min(Cout, 64)
-                gsrc = [gp[:, 8 * k:8 * k + 8] for k in range(Cout // 64)] if Cout >= 64 else [gp]
-                for i in range(nsrc):
-                    if not needs[5 + i]:
-                        continue
-                    wp = _pack_weight(weight, C, Cout, ks, False, 1, nsrc * C, i * C, _tiles(N, H, W, ks))
-                    gxs[i] = _conv_launch(gsrc, wp, None, None, N, H, W, gc, C, ks, _lib.ACT_NONE, False)
+                if C != 64 or (Cout % 64 != 0 and not (Cout < 64 and Cout % 16 == 0)):
+                    raise NotImplementedError("conv_c8: the data gradient needs 64-channel sources and Cout %% 64 == 0 or Cout in "
+                                              "{16, 32, 48} (got %d <- %d x %d)" % (Cout, nsrc, C))
+                gxs = [_dgrad(weight, gp, i, nsrc, Cout, ks, N, H, W) if needs[5 + i] else None for i in range(nsrc)]
         return (gw, gb, g_res, None, None, *gxs)
 
 
@@ -276,30 +293,6 @@ class _ConvFirstC8(torch.autograd.Function):
 def conv_first(x, weight, bias=None, act=None):
     """First convolution of the network on an NCHW image (<= 16 channels): C8 bf16 output, weight / bias gradients."""
     return _ConvFirstC8.apply(x, weight, bias, ACT[act])
-
-
-_SLOPE = {_lib.ACT_LRELU: 0.1, _lib.ACT_RELU: 0.0}
-
-
-def _wgrad(xs, gp, N, H, W, Cout, ks, need_bias):
-    """Weight (+ bias) gradient of conv(cat(xs)) given the gradient gp of its (pre-activation) output."""
-    L, dev, nsrc = _lib.lib(), gp.device, len(xs)
-    gw = torch.empty((Cout, nsrc * 64, ks, ks), dtype=torch.float32, device=dev)
-    gb = torch.empty(Cout, dtype=torch.float32, device=dev) if need_bias else None
-    ws = torch.empty(L.rvsr_c8_conv_wgrad_workspace_bytes(N, H, W, Cout), dtype=torch.uint8, device=dev)
-    for i, x in enumerate(xs):
-        _lib.check(L.rvsr_c8_conv_wgrad(_p(x), x.stride(0), _p(gp), _p(gw), _p(gb if i == 0 else None), N, H, W, 64, Cout, ks, nsrc * 64,
-                                        i * 64, _p(ws), ws.numel(), _stream(dev)), "c8_conv_wgrad")
-    return gw, gb
-
-
-def _dgrad(weight, gp, i, nsrc, Cout, ks, N, H, W, residual=None, mask=None, slope=0.0):
-    """Gradient of source i (64 channels) of conv(cat(xs), weight): conv(gp, W[:, slice_i]^T flipped) [+ residual] [* act'(mask)]."""
-    gsrc = [gp[:, 8 * k:8 * k + 8] for k in range(Cout // 64)] if Cout >= 64 else [gp]
-    wp = _pack_weight(weight, 64, Cout, ks, False, 1, nsrc * 64, i * 64, _tiles(N, H, W, ks))
-    if mask is not None:
-        return _conv_launch(gsrc, wp, None, mask, N, H, W, min(Cout, 64), 64, ks, _lib.ACT_NONE, False, 2, slope)
-    return _conv_launch(gsrc, wp, None, residual, N, H, W, min(Cout, 64), 64, ks, _lib.ACT_NONE, False)
 
 
 class _ConvPairC8(torch.autograd.Function):
