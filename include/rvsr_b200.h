@@ -134,6 +134,9 @@ int rvsr_c8_to_nchw(const void *src_c8, void *dst, int dst_dtype, int N, int C, 
 size_t rvsr_c8_conv_weight_bytes(int Cout, int Cin, int ks, int shuffle);
 int rvsr_c8_conv_pack_weight(const float *weight, void *dst, int Cout, int Cin, int ks, int shuffle, int mode, int w_cin_total,
                              int w_c0, int layouts, void *stream);
+/* which operand layout (rvsr_c8_conv_pack_weight's `layouts` bits) a rvsr_c8_conv_fwd launch of this shape reads: 1, 2, or 0 when the
+ * shape is not covered -- a caller may pack just that one */
+int rvsr_c8_conv_layouts(int nsrc, int C, int N, int H, int W, int Cout, int ks, int shuffle);
 int rvsr_c8_conv_fwd(const void *const *x, const long long *x_image_stride, int nsrc, int C, const void *w_packed, const float *bias,
                      const void *residual, void *y, int N, int H, int W, int Cout, int ks, int stride, int act, int shuffle,
                      int residual_mode, float residual_slope, void *stream);

@@ -72,6 +72,21 @@ int rvsr_c8_conv_pack_weight(const float *weight, void *dst, int Cout, int Cin, 
     return RVSR_OK;
 }
 
+int rvsr_c8_conv_layouts(int nsrc, int C, int N, int H, int W, int Cout, int ks, int shuffle) {
+    if (nsrc < 1 || nsrc > RVSR_MAX_SRC_TC || C <= 0 || N <= 0 || H <= 0 || W <= 0 || Cout <= 0) return 0;
+    const int mode = shuffle ? 1 : 0;
+    if (tc_conv_weight_bytes(Cout, nsrc * C, ks, mode) == 0) return 0;
+    ConvOp op = {};
+    static const char dummy = 0;   // the plan only asks whether the layouts exist, it never reads them
+    for (int i = 0; i < nsrc; ++i) op.src[i] = Src{&dummy, (long long)cdiv(C, 8) * 8 * H * W, C, 1, -1};
+    op.nsrc = nsrc;
+    op.w_tc = &dummy;
+    op.w_tc2 = tc2_weight_bytes(Cout, nsrc * C, ks, mode) > 0 ? &dummy : nullptr;
+    op.N = N; op.H = H; op.W = W; op.Cout = Cout; op.ks = ks; op.stride = 1;
+    op.out_mode = shuffle ? OUT_C8_SHUFFLE2 : OUT_C8; op.bf16 = 1;
+    return tc_conv_layouts(op);
+}
+
 int rvsr_c8_conv_fwd(const void *const *x, const long long *x_image_stride, int nsrc, int C, const void *w_packed, const float *bias,
                      const void *residual, void *y, int N, int H, int W, int Cout, int ks, int stride, int act, int shuffle,
                      int residual_mode, float residual_slope, void *stream) {

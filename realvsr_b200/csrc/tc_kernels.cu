@@ -101,8 +101,6 @@ template <bool BF> __device__ __forceinline__ uint32_t pack16x2(float a, float b
     const __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<const uint32_t *>(&h);
 }
-__device__ __forceinline__ float2 unpack16x2_rt(uint32_t u, int bf) { return bf ? unpack16x2<true>(u) : unpack16x2<false>(u); }
-__device__ __forceinline__ uint32_t pack16x2_rt(float a, float b, int bf) { return bf ? pack16x2<true>(a, b) : pack16x2<false>(a, b); }
 
 // Epilogue of one pixel (= TMEM lane) of one tile.  With NH = 2 two warps share a TMEM lane
 // quarter and take the lower / upper half of the NT accumulator columns.  Order of events:
@@ -118,7 +116,7 @@ template <int ACT> __device__ __forceinline__ float act_t(float v, int act_rt) {
     return apply_act(v, act_rt);
 }
 
-template <int NT, int NH> struct EpiTile {
+template <int NT, int NH, bool BF = false> struct EpiTile {  // BF: out / residual are bfloat16 (training path) instead of fp16
     static constexpr int HALFC = NH == 1 ? NT : ((NT / NH + 15) / 16) * 16;  // columns per warp (upper bound)
     static constexpr int CW = HALFC >= 32 ? 32 : 16;                         // columns per register chunk
     static constexpr int NCH = HALFC / CW;                                   // chunks per warp
@@ -174,11 +172,11 @@ template <int NT, int NH> struct EpiTile {
                 const uint32_t *h = reinterpret_cast<const uint32_t *>(&res[RES ? ch * (CW / 8) + j : 0]);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float2 f = unpack16x2_rt(h[i], e.bf16);
+                    const float2 f = unpack16x2<BF>(h[i]);
                     rr[2 * i] = f.x; rr[2 * i + 1] = f.y;
                 }
             }
-            const bool pre = e.res_pre == 1, mask = e.res_pre == 2 && RES && has_res;
+            const bool pre = e.res_pre == 1, mask = BF && e.res_pre == 2 && RES && has_res;  // the mask mode exists on the training path only
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float a = __uint_as_float(acc[j >> 1][(j & 1) * 8 + i]) + bb[i];
@@ -188,7 +186,7 @@ template <int NT, int NH> struct EpiTile {
             uint4 pk;
             uint32_t *h = reinterpret_cast<uint32_t *>(&pk);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) h[i] = pack16x2_rt(v[2 * i], v[2 * i + 1], e.bf16);
+            for (int i = 0; i < 4; ++i) h[i] = pack16x2<BF>(v[2 * i], v[2 * i + 1]);
             o[q * plane] = pk;
         }
     }
@@ -216,8 +214,8 @@ template <int NT, int NH> struct EpiTile {
                 uint32_t *h = reinterpret_cast<uint32_t *>(&pk[j]);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    h[k] = pack16x2_rt(act_t<ACT>(__uint_as_float(acc[g][j * 8 + 2 * k]) + b[j * 8 + 2 * k], e.act),
-                                       act_t<ACT>(__uint_as_float(acc[g][j * 8 + 2 * k + 1]) + b[j * 8 + 2 * k + 1], e.act), e.bf16);
+                    h[k] = pack16x2<BF>(act_t<ACT>(__uint_as_float(acc[g][j * 8 + 2 * k]) + b[j * 8 + 2 * k], e.act),
+                                        act_t<ACT>(__uint_as_float(acc[g][j * 8 + 2 * k + 1]) + b[j * 8 + 2 * k + 1], e.act));
             }
             st_global_256(ob + (long long)g * plane2, pk[0], pk[1]);
         }
@@ -397,7 +395,7 @@ __device__ __forceinline__ void epi_c8_fast(const float *bias_s, __half *out, lo
         }
         if (has_res && !pre) {
             const uint32_t *h = reinterpret_cast<const uint32_t *>(&res[j]);
-            if (res_mode == 2) {  // mask: gradient through the activation that produced `residual`
+            if (BF && res_mode == 2) {  // mask: gradient through the activation that produced `residual` (training path only)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float2 m = unpack16x2<BF>(h[i]);
@@ -449,7 +447,7 @@ constexpr int TC_EPI_WARP0 = 4;
 constexpr int TC_THREADS = 32 * (TC_EPI_WARP0 + TC_EPI_WARPS);
 __host__ __device__ constexpr int acc_stride(int NT) { return NT <= 32 ? 32 : (NT <= 64 ? 64 : 128); }
 
-template <int KS, int NT>
+template <int KS, int NT, bool BF = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcConvParams p) {
     constexpr int KK = KS * KS, PAD = KS / 2, VALID = TC_TW - (KS - 1), HALO_ROWS = TC_ROWS + KS - 1;
     constexpr int PLANE_BYTES = HALO_ROWS * TC_TW * 16;
@@ -562,7 +560,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             // ---- MMA issuer(s).  The issue stream is the critical path of the whole kernel (the tensor pipe
             // needs a new N=64 MMA every 48 cycles), so: whole warp on uniform values (see elect_one()), no
             // divisions, no 64-bit descriptor rebuilds, running counters instead of modulo, everything unrolled.
-            const uint32_t idesc = make_idesc(NT) | (p.bf16 ? (1u << 7) | (1u << 10) : 0u);  // a/b format: 0 = F16, 1 = BF16
+            constexpr uint32_t idesc = make_idesc(NT) | (BF ? (1u << 7) | (1u << 10) : 0u);  // a/b format: 0 = F16, 1 = BF16
             const uint32_t mw = (uint32_t)(warp - 1);
             const uint32_t nsrc = (uint32_t)p.nsrc, C8s = (uint32_t)p.C8s;
             const uint64_t adesc0 = make_desc(smem_u32(stage_s), PLANE_BYTES, 128);
@@ -633,7 +631,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int half = ((warp - TC_EPI_WARP0) % WPG) >> 2;         // WPG / 4 warps per lane quarter split the columns
         EpiArgs e{bias_s, p.out, p.out_image_stride, p.residual, p.res_image_stride, p.H, p.W, p.Cout, p.act,
                   p.out_mode, p.sig_from, p.subsample, p.dg, &p.fin, p.res_pre, p.res_div, p.bf16, p.res_slope};
-        EpiTile<NT, WPG / 4> ep;
+        EpiTile<NT, WPG / 4, BF> ep;
         uint32_t t = (uint32_t)eg;
         for (int tile = blockIdx.x + eg * gridDim.x; tile < p.num_tiles; tile += EG * gridDim.x, t += EG) {
             const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, n = tile / (p.tiles_x * p.tiles_y);
@@ -689,7 +687,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 // element strides {1, 2, 2, 1}; each tap is then a view of one phase tile shifted by (0 | 1, 0 | 1), exactly like the
 // stride-1 taps.  Kernel geometry (H, W, tiles) is that of the OUTPUT.  (Round 1 computed these layers at full resolution
 // and stored every other pixel: 4x the MMAs.)
-template <int KS, int NT, bool S2 = false>
+template <int KS, int NT, bool S2 = false, bool BF = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_tc2_kernel(const __grid_constant__ TcConvParams p) {
     constexpr int NH2 = NT / 2;
     constexpr int KK = KS * KS, PAD = KS / 2, VALID = TC_TW - (KS - 1), HALO_ROWS = S2 ? TC_ROWS + 1 : TC_ROWS + KS - 1;
@@ -798,8 +796,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
                 mbar_arrive_cluster(mapa_rank0(WPEER));
             }
         } else {  // whole warp, uniform values; only the tcgen05 instructions are predicated on one lane
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((256u >> 4) << 24) |  // M = 256 over the pair
-                                   (p.bf16 ? (1u << 7) | (1u << 10) : 0u);
+            constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((256u >> 4) << 24) |  // M = 256 over the pair
+                                       (BF ? (1u << 7) | (1u << 10) : 0u);
             const uint32_t mw = (uint32_t)(warp - 1);
             const uint32_t nsrc = (uint32_t)p.nsrc, C8s = (uint32_t)p.C8s;
             const uint64_t adesc0 = make_desc(smem_u32(stage_s), PLANE_BYTES, 128);
@@ -882,13 +880,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
         const int half = ((warp - TC_EPI_WARP0) % WPG) >> 2;
         EpiArgs e{bias_s, p.out, p.out_image_stride, p.residual, p.res_image_stride, p.H, p.W, p.Cout, p.act,
                   p.out_mode, p.sig_from, p.subsample, p.dg, &p.fin, p.res_pre, p.res_div, p.bf16, p.res_slope};
-        EpiTile<NT, WPG / 4> ep;
+        EpiTile<NT, WPG / 4, BF> ep;
         uint32_t t = (uint32_t)eg;
         if (NT == 64 && WPG == 8 && p.out_mode == OUT_C8 && !p.subsample && p.debug == 0) {
             // lean path (see epi_c8_fast): every 64-wide stride-1 convolution of the network
-            auto tiles = [&](auto act_tag, auto bf_tag) {
+            auto tiles = [&](auto act_tag) {
                 constexpr int ACT = decltype(act_tag)::value;
-                constexpr bool BF = decltype(bf_tag)::value;
                 const int Co8 = (p.Cout + 7) / 8;
                 uint32_t buf = (uint32_t)eg, par = 0;  // buf = t % NB, par = (t / NB) & 1 without divisions
                 for (int pr = cid + eg * nclusters; pr < npairs; pr += EG * nclusters) {
@@ -911,13 +908,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
                     if (buf >= (uint32_t)NB) { buf -= NB; par ^= 1u; }
                 }
             };
-            if (p.bf16) {
-                if (p.act == RVSR_ACT_LRELU) tiles(std::integral_constant<int, RVSR_ACT_LRELU>{}, std::true_type{});
-                else if (p.act == RVSR_ACT_RELU) tiles(std::integral_constant<int, RVSR_ACT_RELU>{}, std::true_type{});
-                else tiles(std::integral_constant<int, RVSR_ACT_NONE>{}, std::true_type{});
-            } else if (p.act == RVSR_ACT_LRELU) tiles(std::integral_constant<int, RVSR_ACT_LRELU>{}, std::false_type{});
-            else if (p.act == RVSR_ACT_RELU) tiles(std::integral_constant<int, RVSR_ACT_RELU>{}, std::false_type{});
-            else tiles(std::integral_constant<int, RVSR_ACT_NONE>{}, std::false_type{});
+            if (p.act == RVSR_ACT_LRELU) tiles(std::integral_constant<int, RVSR_ACT_LRELU>{});
+            else if (p.act == RVSR_ACT_RELU) tiles(std::integral_constant<int, RVSR_ACT_RELU>{});
+            else tiles(std::integral_constant<int, RVSR_ACT_NONE>{});
         } else
         for (int pr = cid + eg * nclusters; pr < npairs; pr += EG * nclusters, t += EG) {
             const int tile = 2 * pr + (int)rank;
@@ -1104,19 +1097,40 @@ bool tc_conv_supported(const ConvOp &op) {
     return tc_conv_plan(op, pl) && get_encode() != nullptr;
 }
 
-template <int KS, int NT> static int launch_conv_tc_t(const TcConvParams &p, const TcConvPlan &pl, int sms, cudaStream_t s) {
-    RVSR_TRY(ensure_max_dynamic_smem(reinterpret_cast<const void *>(&conv_tc_kernel<KS, NT>), (int)TC_SMEM_LIMIT + 1024));
+template <int KS, int NT, bool BF> static int launch_conv_tc_t(const TcConvParams &p, const TcConvPlan &pl, int sms, cudaStream_t s) {
+    RVSR_TRY(ensure_max_dynamic_smem(reinterpret_cast<const void *>(&conv_tc_kernel<KS, NT, BF>), (int)TC_SMEM_LIMIT + 1024));
     int gx = sms / pl.passes;
     if (gx < 1) gx = 1;
     if (gx > p.num_tiles) gx = p.num_tiles;
-    launch_k(conv_tc_kernel<KS, NT>, dim3(gx, pl.passes), dim3(TC_THREADS), pl.smem, s, p);
+    launch_k(conv_tc_kernel<KS, NT, BF>, dim3(gx, pl.passes), dim3(TC_THREADS), pl.smem, s, p);
     RVSR_LAUNCH_CHECK();
     return RVSR_OK;
+}
+
+static bool tc_two_cta_enabled() {
+    static const bool on = !(getenv("RVSR_TC_2CTA") != nullptr && getenv("RVSR_TC_2CTA")[0] == '0');
+    return on;
+}
+// Does a stride-1 launch of `op` run on the CTA-pair kernel, i.e. read the w_tc2 layout (else: w_tc)?  One decision, used by
+// launch_conv_tc and by callers that pack only the layout a launch will read (rvsr_c8_conv_layouts).
+static bool tc_conv_pair_stride1(const ConvOp &op, const TcConvPlan &pl) {
+    const int valid = TC_TW - (op.ks - 1);
+    const long long num_tiles = (long long)cdiv(op.W, valid) * cdiv(op.H, TC_ROWS) * op.N;
+    return (tc_two_cta_enabled() || pl.pair_only) && op.w_tc2 != nullptr && (pl.NT == 64 || pl.NT == 128) && op.ks == 3 &&
+           (num_tiles >= 4 || pl.pair_only) && (pl.NT == 128 || op.out_mode == OUT_C8) && op.stride == 1;
+}
+// bit 0: the launch reads op.w_tc, bit 1: op.w_tc2; 0: not covered.  op.w_tc / w_tc2 only need to be non-null where that layout exists.
+int tc_conv_layouts(const ConvOp &op) {
+    TcConvPlan pl;
+    if (!tc_conv_plan(op, pl)) return 0;
+    return tc_conv_pair_stride1(op, pl) ? 2 : 1;
 }
 
 int launch_conv_tc(const ConvOp &op, cudaStream_t s) {
     TcConvPlan pl;
     RVSR_CHECK_ARG(tc_conv_plan(op, pl), "tc conv: unsupported configuration");
+    RVSR_CHECK_ARG(!op.bf16 || (op.stride == 1 && (op.out_mode == OUT_C8 || op.out_mode == OUT_C8_SHUFFLE2)),
+                   "tc conv: the bf16 instances cover stride 1 with channel-blocked output");
     EncodeTiledFn enc = get_encode();
     RVSR_CHECK_ARG(enc != nullptr, "tc conv: cuTensorMapEncodeTiled unavailable");
     TcConvParams p;
@@ -1163,7 +1177,7 @@ int launch_conv_tc(const ConvOp &op, cudaStream_t s) {
     p.stamp = -1;
     const int sms = sm_count();
     // CTA-pair kernels (cta_group::2) for the 3x3 convolutions with 64- and 128-wide tiles (the bulk of the network)
-    static const bool two_cta = !(getenv("RVSR_TC_2CTA") != nullptr && getenv("RVSR_TC_2CTA")[0] == '0');
+    const bool two_cta = tc_two_cta_enabled();
     // stride 2 as a real implicit GEMM over the four phase images (RVSR_S2=0: compute at full resolution and subsample)
     static const bool s2_on = !(getenv("RVSR_S2") != nullptr && getenv("RVSR_S2")[0] == '0');
     const bool s2 = s2_on && two_cta && op.stride == 2 && op.w_tc2 != nullptr && pl.NT == 64 && op.ks == 3 && op.out_mode == OUT_C8 &&
@@ -1190,8 +1204,8 @@ int launch_conv_tc(const ConvOp &op, cudaStream_t s) {
         p.td.tpi = (uint32_t)(p.tiles_x * p.tiles_y); p.td.m_tpi = magic_div(p.td.tpi, (uint32_t)p.num_tiles);
         p.td.tx = (uint32_t)p.tiles_x; p.td.m_tx = magic_div(p.td.tx, p.td.tpi);
     }
-    if ((two_cta || pl.pair_only) && op.w_tc2 != nullptr && (pl.NT == 64 || pl.NT == 128) && op.ks == 3 && (p.num_tiles >= 4 || pl.pair_only) &&
-        (pl.NT == 128 || op.out_mode == OUT_C8) && (op.stride == 1 || s2)) {
+    if (tc_conv_pair_stride1(op, pl) ||
+        (s2 && (two_cta || pl.pair_only) && op.w_tc2 != nullptr && pl.NT == 64 && op.ks == 3 && (p.num_tiles >= 4 || pl.pair_only) && op.out_mode == OUT_C8)) {
         const size_t wb2 = (size_t)op.nsrc * pl.C8s * 9 * (pl.NT / 2) * 16;
         const size_t stage = s2 ? (size_t)4 * pl.C8s * (TC_ROWS + 1) * TC_TW * 16 : (size_t)pl.C8s * (TC_ROWS + 2) * TC_TW * 16;
         const size_t fixed = wb2 + 128 + pl.NT * 4 + 512;
@@ -1214,9 +1228,15 @@ int launch_conv_tc(const ConvOp &op, cudaStream_t s) {
         if (s2) {
             RVSR_TRY(ensure_max_dynamic_smem(reinterpret_cast<const void *>(&conv_tc2_kernel<3, 64, true>), (int)TC_SMEM_LIMIT + 1024));
             launch_k(conv_tc2_kernel<3, 64, true>, dim3(2 * clusters, pl.passes), dim3(TC_THREADS), smem2, s, p);
+        } else if (pl.NT == 64 && op.bf16) {  // bf16 operands / storage (training path): separate instances, the fp16 code is untouched
+            RVSR_TRY(ensure_max_dynamic_smem(reinterpret_cast<const void *>(&conv_tc2_kernel<3, 64, false, true>), (int)TC_SMEM_LIMIT + 1024));
+            launch_k(conv_tc2_kernel<3, 64, false, true>, dim3(2 * clusters, pl.passes), dim3(TC_THREADS), smem2, s, p);
         } else if (pl.NT == 64) {
             RVSR_TRY(ensure_max_dynamic_smem(reinterpret_cast<const void *>(&conv_tc2_kernel<3, 64>), (int)TC_SMEM_LIMIT + 1024));
             launch_k(conv_tc2_kernel<3, 64>, dim3(2 * clusters, pl.passes), dim3(TC_THREADS), smem2, s, p);
+        } else if (op.bf16) {
+            RVSR_TRY(ensure_max_dynamic_smem(reinterpret_cast<const void *>(&conv_tc2_kernel<3, 128, false, true>), (int)TC_SMEM_LIMIT + 1024));
+            launch_k(conv_tc2_kernel<3, 128, false, true>, dim3(2 * clusters, pl.passes), dim3(TC_THREADS), smem2, s, p);
         } else {
             RVSR_TRY(ensure_max_dynamic_smem(reinterpret_cast<const void *>(&conv_tc2_kernel<3, 128>), (int)TC_SMEM_LIMIT + 1024));
             launch_k(conv_tc2_kernel<3, 128>, dim3(2 * clusters, pl.passes), dim3(TC_THREADS), smem2, s, p);
@@ -1226,7 +1246,7 @@ int launch_conv_tc(const ConvOp &op, cudaStream_t s) {
     }
     RVSR_CHECK_ARG(!pl.pair_only, "tc conv: this shape needs the CTA-pair kernel");
 #define RVSR_TC_CASE(KS_, NT_) \
-    if (op.ks == KS_ && pl.NT == NT_) return launch_conv_tc_t<KS_, NT_>(p, pl, sms, s);
+    if (op.ks == KS_ && pl.NT == NT_) return op.bf16 ? launch_conv_tc_t<KS_, NT_, true>(p, pl, sms, s) : launch_conv_tc_t<KS_, NT_, false>(p, pl, sms, s);
     RVSR_TC_CASE(3, 16) RVSR_TC_CASE(3, 64) RVSR_TC_CASE(3, 128)
     RVSR_TC_CASE(1, 16) RVSR_TC_CASE(1, 64) RVSR_TC_CASE(1, 128)
 #undef RVSR_TC_CASE

@@ -109,21 +109,18 @@ def from_c8(x, C=None, dtype=torch.bfloat16):
 
 
 # ---------------------------------------------------------------- convolution
-def _pack_weight(weight, Cout, Cin, ks, shuffle, mode, cin_total, c0, tiles=0):
+def _pack_weight(weight, Cout, Cin, ks, shuffle, mode, cin_total, c0, geom):
+    """fp32 OIHW parameter -> the operand layout the launch described by geom = (nsrc, C, N, H, W) will read (the library
+    decides: rvsr_c8_conv_layouts; packing the other one as well would be a second tiny launch per call)."""
     L = _lib.lib()
     nbytes = L.rvsr_c8_conv_weight_bytes(Cout, Cin, ks, int(shuffle))
-    if nbytes == 0:
+    layouts = L.rvsr_c8_conv_layouts(geom[0], geom[1], geom[2], geom[3], geom[4], Cout, ks, int(shuffle)) if nbytes else 0
+    if nbytes == 0 or layouts == 0:
         raise NotImplementedError("train_c8: convolution %d <- %d (k=%d) is not covered by the tcgen05 kernels" % (Cout, Cin, ks))
     dst = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
-    # launches of >= 4 tiles of a 3x3 convolution with 64- / 128-wide output tiles run on the CTA-pair kernel: one layout suffices
-    pair_only = ks == 3 and tiles >= 4 and Cin % 16 == 0 and Cout > 16 and Cout % 64 == 0
-    _lib.check(L.rvsr_c8_conv_pack_weight(_p(weight), _p(dst), Cout, Cin, ks, int(shuffle), mode, cin_total, c0, 2 if pair_only else 3,
+    _lib.check(L.rvsr_c8_conv_pack_weight(_p(weight), _p(dst), Cout, Cin, ks, int(shuffle), mode, cin_total, c0, layouts,
                                           _stream(weight.device)), "c8_conv_pack_weight")
     return dst
-
-
-def _tiles(N, H, W, ks):
-    return N * ((H + 3) // 4) * ((W + 32 - ks) // (33 - ks))
 
 
 def _conv_launch(xs, w_packed, bias, residual, N, H, W, C, Cout, ks, act, shuffle, res_mode=0, res_slope=0.0):
@@ -165,7 +162,7 @@ def _wgrad(xs, gp, N, H, W, Cout, ks, need_bias):
 def _dgrad(weight, gp, i, nsrc, Cout, ks, N, H, W, residual=None, mask=None, slope=0.0):
     """Gradient of source i (64 channels) of conv(cat(xs), weight): conv(gp, W[:, slice_i]^T flipped) [+ residual] [* act'(mask)]."""
     gsrc = [gp[:, 8 * k:8 * k + 8] for k in range(Cout // 64)] if Cout >= 64 else [gp]
-    wp = _pack_weight(weight, 64, Cout, ks, False, 1, nsrc * 64, i * 64, _tiles(N, H, W, ks))
+    wp = _pack_weight(weight, 64, Cout, ks, False, 1, nsrc * 64, i * 64, (len(gsrc), min(Cout, 64), N, H, W))
     if mask is not None:
         return _conv_launch(gsrc, wp, None, mask, N, H, W, min(Cout, 64), 64, ks, _lib.ACT_NONE, False, 2, slope)
     return _conv_launch(gsrc, wp, None, residual, N, H, W, min(Cout, 64), 64, ks, _lib.ACT_NONE, False)
@@ -191,7 +188,7 @@ class _ConvC8(torch.autograd.Function):
         if residual is not None:
             residual = _check_c8(residual, "conv_c8 residual")
         with torch.cuda.device(weight.device):
-            wp = _pack_weight(weight, Cout, Cin, ks, shuffle, 0, Cin, 0, _tiles(N, H, W, ks))
+            wp = _pack_weight(weight, Cout, Cin, ks, shuffle, 0, Cin, 0, (len(xs), C, N, H, W))
             y = _conv_launch(xs, wp, bias, residual, N, H, W, C, Cout, ks, act, shuffle)
         ctx.meta = (act, shuffle, N, H, W, C, Cout, ks, len(xs), residual is not None)
         needs = ctx.needs_input_grad
@@ -263,7 +260,7 @@ class _ConvFirstC8(torch.autograd.Function):
         with torch.cuda.device(x.device):
             _lib.check(_lib.lib().rvsr_c8_from_nchw(_p(xin), _lib.BF16 if xin.dtype == torch.bfloat16 else _lib.F32, _p(xp), N, C, H, W, 2,
                                                     _stream(x.device)), "c8_from_nchw")
-            wp = _pack_weight(w16, Cout, 16, 3, False, 0, 16, 0, _tiles(N, H, W, 3))
+            wp = _pack_weight(w16, Cout, 16, 3, False, 0, 16, 0, (1, 16, N, H, W))
             y = _conv_launch([xp[:N]], wp, bias, None, N, H, W, 16, Cout, 3, act, False)
         ctx.meta = (act, N, C, H, W, Cout)
         ctx.save_for_backward(xp, *([y] if act != _lib.ACT_NONE else []))
@@ -312,9 +309,10 @@ class _ConvPairC8(torch.autograd.Function):
             raise NotImplementedError("conv_pair_c8: the skip connection is ResidualBlock_noBN's (one input, no final activation)")
         w1, w2 = w1.contiguous(), w2.contiguous()
         with torch.cuda.device(w1.device):
-            t = _tiles(N, H, W, 3)
-            h = _conv_launch(xs, _pack_weight(w1, 64, 64 * len(xs), 3, False, 0, 64 * len(xs), 0, t), b1, None, N, H, W, 64, 64, 3, act1, False)
-            y = _conv_launch([h], _pack_weight(w2, 64, 64, 3, False, 0, 64, 0, t), b2, xs[0] if skip else None, N, H, W, 64, 64, 3, act2, False)
+            h = _conv_launch(xs, _pack_weight(w1, 64, 64 * len(xs), 3, False, 0, 64 * len(xs), 0, (len(xs), 64, N, H, W)), b1, None, N, H, W, 64, 64,
+                             3, act1, False)
+            y = _conv_launch([h], _pack_weight(w2, 64, 64, 3, False, 0, 64, 0, (1, 64, N, H, W)), b2, xs[0] if skip else None, N, H, W, 64, 64, 3,
+                             act2, False)
         ctx.meta = (act1, act2, skip, len(xs), N, H, W)
         ctx.save_for_backward(w1, w2, h, *xs, *([y] if act2 != _lib.ACT_NONE else []))
         return y

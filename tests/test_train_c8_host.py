@@ -13,13 +13,21 @@ def test_cpu_tensors_are_rejected_not_routed_elsewhere():
         T.conv(torch.zeros(1, 8, 4, 4, 8, dtype=torch.bfloat16), torch.zeros(64, 64, 3, 3))
 
 
-def test_tile_count_matches_the_kernel_geometry():
-    """_tiles decides which weight layout a launch will read (CTA-pair kernel from 4 tiles on): 4 rows x 30 (3x3) / 32 (1x1)
-    valid columns per tile, as tc_kernels.cu's launch_conv_tc computes them."""
-    from realvsr_b200.train_c8 import _tiles
-    assert _tiles(1, 4, 30, 3) == 1 and _tiles(1, 4, 31, 3) == 2 and _tiles(1, 5, 30, 3) == 2
-    assert _tiles(80, 64, 64, 3) == 80 * 16 * 3
-    assert _tiles(2, 8, 32, 1) == 2 * 2 * 1 and _tiles(2, 8, 33, 1) == 2 * 2 * 2
+def test_weight_layout_decision_is_the_librarys():
+    """rvsr_c8_conv_layouts: which packed operand layout a launch reads -- the CTA-pair kernel's from 4 tiles on (4 rows x 30
+    valid columns per tile for 3x3), the single-CTA kernels' below that and for 1x1 / 16-wide outputs.  The Python side packs
+    exactly what this returns, so the decision exists once (tc_kernels.cu)."""
+    from realvsr_b200 import _lib
+    L = _lib.lib()
+    assert L.rvsr_c8_conv_layouts(1, 64, 1, 4, 30, 64, 3, 0) == 1      # 1 tile
+    assert L.rvsr_c8_conv_layouts(1, 64, 1, 8, 60, 64, 3, 0) == 2      # 4 tiles
+    assert L.rvsr_c8_conv_layouts(2, 64, 80, 64, 64, 64, 3, 0) == 2    # torch.cat of two sources
+    assert L.rvsr_c8_conv_layouts(4, 64, 16, 64, 64, 64, 3, 0) == 2    # data gradient of a 256-channel output: pair kernel only
+    assert L.rvsr_c8_conv_layouts(1, 64, 16, 64, 64, 256, 3, 1) == 2   # pixel-shuffle convolution
+    assert L.rvsr_c8_conv_layouts(5, 64, 16, 64, 64, 64, 1, 0) == 1    # 1x1
+    assert L.rvsr_c8_conv_layouts(1, 64, 16, 256, 256, 16, 3, 0) == 1  # conv_last on the 16-wide tile
+    assert L.rvsr_c8_conv_layouts(1, 64, 16, 64, 64, 216, 3, 0) == 0   # not a whole number of 64-wide tiles
+    assert L.rvsr_c8_conv_layouts(1, 24, 16, 64, 64, 64, 3, 0) == 0    # source channels not a multiple of 16
 
 
 def test_training_path_routing_rules():
