@@ -431,3 +431,40 @@ def test_graphed_step_follows_the_optimizer():
         assert abs(a - b) < 2e-3 * b, (losses_graph, losses_eager)
     for (n, p), q in zip(net.named_parameters(), ref.parameters()):
         assert float((p.detach() - q.detach()).abs().max()) <= 2e-2 * lr * 50 + 1e-3 * float(q.detach().abs().max()), n
+
+
+def test_ft_tsa_only_freezing_on_the_c8_path():
+    """The reference's `ft_tsa_only` option freezes every parameter whose name lacks 'tsa_fusion'
+    (VideoSR_AllPair_model_YCbCr_Split.py:94-99).  On the train_c8 path frozen layers must skip their weight gradients but
+    still pass the data gradient back to the TSA module; the TSA gradients equal those of the unfrozen step."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers import load_case
+    from synth import synth_normal
+    from realvsr_b200.archs import EDVR_arch as E
+    c = load_case("edvr_nf64_crop")
+    net = E.EDVR(**c["kwargs"]).train()
+    net.load_state_dict(c["sd"], strict=True)
+    net = net.to("cuda")
+    net.exec_path = "train_c8"
+    x = c["x"].to("cuda")
+    gt = synth_normal(tuple(c["out"].shape), 58, std=0.3).to("cuda") + 0.5
+
+    def step():
+        net.zero_grad(set_to_none=True)
+        F.l1_loss(net(x).float(), gt).backward()
+        return {n: (None if p.grad is None else p.grad.detach().clone()) for n, p in net.named_parameters()}
+
+    full = step()
+    for n, p in net.named_parameters():
+        p.requires_grad = "tsa_fusion" in n
+    part = step()
+    for n in full:
+        if "tsa_fusion" in n:
+            # identical kernels on identical data; only the fp32 atomics inside dcn_bwd_tc_kernel (not on this path: the DCN
+            # sits before the TSA module) could differ -- so bit-identical
+            assert torch.equal(part[n], full[n]), n
+        else:
+            assert part[n] is None, n
