@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
 
     if (warp < WG_PROD_WARPS) {
         // ---- x halo producers: rows -1 .. 5 of the tile, 34 columns from -1, all 8 channel blocks; rows 0 .. 4 go to both copies.
-        // The loads of tile t + 1 are in flight while tile t is written to shared memory (two register sets).
+        // The loads of the next WG_AHEAD - 1 tiles are in flight while a tile is written to shared memory (WG_AHEAD register sets).
         const long long plane = (long long)p.H * p.W;
         int cell[WG_PER_THREAD];  // this thread's cells of the halo: (block, row, column) -> offsets, fixed for the whole kernel
         int off_a[WG_PER_THREAD], off_b[WG_PER_THREAD], rowi[WG_PER_THREAD], coli[WG_PER_THREAD];
