@@ -44,6 +44,7 @@ struct alignas(64) TcDcnBwdParams {
     int N, H, W;
     int tiles_x, tiles_y, num_tiles;
     TileDiv td;
+    int combine;  // neighbouring lanes merge their reductions into shared cells (RVSR_DCN_BWD_COMBINE=0: every lane scatters alone)
 };
 
 __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
@@ -170,6 +171,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) dcn_bwd_tc_kernel(const __grid_
     } else if (warp >= BW_GATHER_WARP0) {
         const int lq = warp & 3, qq = (warp - BW_GATHER_WARP0) >> 2;
         const int m = lq * 32 + lane;
+        const bool combine = p.combine != 0;
         const long long plane = (long long)p.H * p.W;
         uint32_t c = 0;  // steps consumed
         for (int t = 0; t < T; ++t) {
@@ -232,18 +234,30 @@ __global__ void __launch_bounds__(BW_THREADS, 1) dcn_bwd_tc_kernel(const __grid_
                     go[plane] = inside ? mk * g_dx : 0.f;
                     p.gmask[((long long)n * 72 + blk * 9 + tap) * plane + pix] = inside ? g_m : 0.f;
                 }
-                // grad_input: scatter grad_col * mask * bilinear weight to the (valid) corners (.cu:674-690)
-                auto scatter = [&](bool ok, int yy, int xx, float w) {
+                // grad_input: scatter grad_col * mask * bilinear weight to the (valid) corners (.cu:674-690).  The kernel runs at the
+                // L2's atomic rate, so neighbours combine first: lanes are adjacent pixels of one row, and wherever the offset field
+                // is smooth lane L's right-hand cells (x0 + 1) ARE lane L + 1's left-hand cells (same y0, x0' = x0 + 1).  Lane L + 1
+                // then adds lane L's right-hand contributions to its own (10 shuffles) and lane L skips those two reductions:
+                // up to half of the red.global.add.v4.f32 traffic disappears.
+                const float a00 = w00 * mk, a01 = w01 * mk, a10 = w10 * mk, a11 = w11 * mk;
+                const int py0 = __shfl_up_sync(0xffffffffu, y0, 1), px0 = __shfl_up_sync(0xffffffffu, x0, 1);
+                const int pin = __shfl_up_sync(0xffffffffu, (int)inside, 1);
+                const bool take = combine && lane > 0 && inside && pin != 0 && py0 == y0 && px0 + 1 == x0;
+                const bool given = __shfl_down_sync(0xffffffffu, (int)take, 1) != 0 && lane < 31;
+                const float pa01 = __shfl_up_sync(0xffffffffu, a01, 1), pa11 = __shfl_up_sync(0xffffffffu, a11, 1);
+                float pg[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) pg[k] = __shfl_up_sync(0xffffffffu, gc[k], 1);
+                auto scatter = [&](bool ok, int yy, int xx, float a, float pa) {  // pa != 0: plus the previous lane's share of this cell
                     if (!ok) return;
                     float *d = gxp + ((long long)yy * p.W + xx) * 8;
-                    const float a = w * mk;
-                    red_add_v4(d, a * gc[0], a * gc[1], a * gc[2], a * gc[3]);
-                    red_add_v4(d + 4, a * gc[4], a * gc[5], a * gc[6], a * gc[7]);
+                    red_add_v4(d, fmaf(pa, pg[0], a * gc[0]), fmaf(pa, pg[1], a * gc[1]), fmaf(pa, pg[2], a * gc[2]), fmaf(pa, pg[3], a * gc[3]));
+                    red_add_v4(d + 4, fmaf(pa, pg[4], a * gc[4]), fmaf(pa, pg[5], a * gc[5]), fmaf(pa, pg[6], a * gc[6]), fmaf(pa, pg[7], a * gc[7]));
                 };
-                scatter(vy0 && vx0, y0, x0, w00);
-                scatter(vy0 && vx1, y0, x1, w01);
-                scatter(vy1 && vx0, y1, x0, w10);
-                scatter(vy1 && vx1, y1, x1, w11);
+                scatter(vy0 && vx0, y0, x0, a00, take ? pa01 : 0.f);
+                scatter(vy0 && vx1 && !given, y0, x1, a01, 0.f);
+                scatter(vy1 && vx0, y1, x0, a10, take ? pa11 : 0.f);
+                scatter(vy1 && vx1 && !given, y1, x1, a11, 0.f);
                 // modulated sample -> bf16 -> MN-major A operand of the weight-gradient GEMM
                 if (part == 0) mbar_wait(BAR(B_SEMPTY + st), (((uint32_t)t * (18 / BW_SPS / BW_SS) + u / BW_SS) & 1) ^ 1);
                 uint4 pk;
@@ -379,6 +393,8 @@ int launch_dcn_bwd_tc_core(const void *x8, const void *g8, const float *off32, c
     }
     p.x = (const __nv_bfloat16 *)x8; p.offset = off32; p.mask = msk32; p.wt = (const __nv_bfloat16 *)wt; p.gx = gx8; p.goffset = goff32; p.gmask = gmsk32; p.gw = gw32;
     p.N = B; p.H = H; p.W = W;
+    static const bool comb = !(getenv("RVSR_DCN_BWD_COMBINE") != nullptr && getenv("RVSR_DCN_BWD_COMBINE")[0] == '0');
+    p.combine = comb ? 1 : 0;
     p.tiles_x = cdiv(W, TC_TW); p.tiles_y = cdiv(H, TC_ROWS); p.num_tiles = p.tiles_x * p.tiles_y * B;
     p.td.tpi = (uint32_t)(p.tiles_x * p.tiles_y); p.td.m_tpi = magic_div(p.td.tpi, (uint32_t)p.num_tiles);
     p.td.tx = (uint32_t)p.tiles_x; p.td.m_tx = magic_div(p.td.tx, p.td.tpi);
