@@ -134,6 +134,10 @@ int rvsr_c8_to_nchw(const void *src_c8, void *dst, int dst_dtype, int N, int C, 
 size_t rvsr_c8_conv_weight_bytes(int Cout, int Cin, int ks, int shuffle);
 int rvsr_c8_conv_pack_weight(const float *weight, void *dst, int Cout, int Cin, int ks, int shuffle, int mode, int w_cin_total,
                              int w_c0, int layouts, void *stream);
+/* rvsr_c8_conv_pack_weight for several views of ONE weight tensor in one launch (a layer's forward operand and the operands of its
+ * data gradients): spec holds 8 ints per view {Cout, Cin, ks, shuffle, mode, w_cin_total, w_c0, layouts}, dst[k] is sized by
+ * rvsr_c8_conv_weight_bytes of view k; at most 8 layouts in total */
+int rvsr_c8_conv_pack_weights(const float *weight, int nviews, const int *spec, void *const *dst, void *stream);
 /* which operand layout (rvsr_c8_conv_pack_weight's `layouts` bits) a rvsr_c8_conv_fwd launch of this shape reads: 1, 2, or 0 when the
  * shape is not covered -- a caller may pack just that one */
 int rvsr_c8_conv_layouts(int nsrc, int C, int N, int H, int W, int Cout, int ks, int shuffle);

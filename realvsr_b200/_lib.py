@@ -40,6 +40,7 @@ SIGNATURES = {
     "rvsr_c8_to_nchw": (c_int, [c_void_p, c_void_p, c_int] + [c_int] * 5 + [c_void_p]),
     "rvsr_c8_conv_weight_bytes": (c_size_t, [c_int] * 4),
     "rvsr_c8_conv_pack_weight": (c_int, [c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
+    "rvsr_c8_conv_pack_weights": (c_int, [c_void_p, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_void_p), c_void_p]),
     "rvsr_c8_conv_layouts": (c_int, [c_int] * 8),
     "rvsr_c8_conv_fwd": (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(ctypes.c_longlong), c_int, c_int, c_void_p,
                                  c_void_p, c_void_p, c_void_p] + [c_int] * 9 + [ctypes.c_float, c_void_p]),

@@ -72,6 +72,35 @@ int rvsr_c8_conv_pack_weight(const float *weight, void *dst, int Cout, int Cin, 
     return RVSR_OK;
 }
 
+int rvsr_c8_conv_pack_weights(const float *weight, int nviews, const int *spec, void *const *dst, void *stream) {
+    RVSR_CHECK_ARG(weight && spec && dst && nviews >= 1, "c8 pack weights: bad arguments");
+    int dims[RVSR_PACK_MAX_VIEWS][5];
+    WeightView wv[RVSR_PACK_MAX_VIEWS];
+    void *out[RVSR_PACK_MAX_VIEWS];
+    int n = 0;
+    for (int k = 0; k < nviews; ++k) {
+        const int *v = spec + 8 * k;
+        const int Cout = v[0], Cin = v[1], ks = v[2], shuffle = v[3] ? 1 : 0, mode = v[4], tot = v[5], c0 = v[6], layouts = v[7];
+        RVSR_CHECK_ARG(Cout > 0 && Cin > 0 && (ks == 1 || ks == 3) && (mode == 0 || mode == 1) && dst[k] != nullptr, "c8 pack weights: view %d", k);
+        RVSR_CHECK_ARG(((uintptr_t)dst[k] & 255) == 0, "c8 pack weights: destination must be 256-byte aligned");
+        const size_t a = tc_conv_weight_bytes(Cout, Cin, ks, shuffle);
+        if (a == 0) { set_error("c8 pack weights: shape %d x %d x %d not covered by the tcgen05 kernels", Cout, Cin, ks); return RVSR_E_UNSUPPORTED; }
+        const long long KK = ks * ks;
+        RVSR_CHECK_ARG(c0 >= 0 && c0 + (mode == 0 ? Cin : Cout) <= tot, "c8 pack weights: channel slice");
+        const WeightView w = mode == 0 ? WeightView{c0 * KK, tot * KK, KK, 1, 1} : WeightView{c0 * KK + KK - 1, KK, tot * KK, -1, 1};
+        for (int lay = 1; lay <= 2; lay <<= 1) {
+            if (!(layouts & lay) || (lay == 2 && tc2_weight_bytes(Cout, Cin, ks, shuffle) == 0)) continue;
+            RVSR_CHECK_ARG(n < RVSR_PACK_MAX_VIEWS, "c8 pack weights: more than %d layouts in one call", RVSR_PACK_MAX_VIEWS);
+            dims[n][0] = Cout; dims[n][1] = Cin; dims[n][2] = ks; dims[n][3] = shuffle; dims[n][4] = lay == 2;
+            wv[n] = w;
+            out[n] = lay == 2 ? (char *)dst[k] + align_up(a, 256) : dst[k];
+            ++n;
+        }
+    }
+    if (n == 0) return RVSR_OK;
+    return pack_weight_views(weight, n, dims, wv, out, (cudaStream_t)stream);
+}
+
 int rvsr_c8_conv_layouts(int nsrc, int C, int N, int H, int W, int Cout, int ks, int shuffle) {
     if (nsrc < 1 || nsrc > RVSR_MAX_SRC_TC || C <= 0 || N <= 0 || H <= 0 || W <= 0 || Cout <= 0) return 0;
     const int mode = shuffle ? 1 : 0;

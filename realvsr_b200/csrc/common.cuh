@@ -210,6 +210,8 @@ struct WeightView {
     int bf16;  // destination format: 0 = fp16, 1 = bfloat16
 };
 
+#define RVSR_PACK_MAX_VIEWS 8
+
 struct ConvOp {
     Src src[RVSR_MAX_SRC_TC];
     int nsrc;

@@ -159,6 +159,7 @@ bool tc_conv_supported(const ConvOp &op);
 int launch_conv_tc(const ConvOp &op, cudaStream_t s);
 size_t tc_conv_weight_bytes(int Cout, int Cin, int ks, int mode = 0);
 // mode: 0 plain, 1 pixel-shuffle column order, 2 OUT_OM24 column order (Cout == 27 * dg)
+int pack_weight_views(const float *w, int n, const int (*dims)[5], const WeightView *wv, void *const *dst, cudaStream_t s);
 int tc_conv_layouts(const ConvOp &op);  // which packed weight layout a stride-1 launch reads: 1 = w_tc, 2 = w_tc2, 0 = not covered
 int pack_weight_tc(const float *w_oihw, void *dst, int Cout, int Cin, int ks, int mode, cudaStream_t s, const WeightView *view = nullptr);
 size_t tc2_weight_bytes(int Cout, int Cin, int ks, int mode = 0);

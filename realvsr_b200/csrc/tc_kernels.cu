@@ -962,30 +962,49 @@ size_t tc_dcn_weight_bytes(int Cout, int C, int K) { return (Cout == 64 && C == 
 __device__ __forceinline__ uint16_t to_16(float v, int bf) {
     return bf ? __bfloat16_as_ushort(__float2bfloat16_rn(v)) : __half_as_ushort(__float2half_rn(v));
 }
+// conv output channel of column n of N-pass pss (modes: 0 plain, 1 pixel-shuffle order, 2 OUT_OM24 order); >= Cout: padding
+__device__ __forceinline__ int pack_col_channel(int n, int pss, int NT, int mode, int Cout) {
+    if (mode == 1) return shuffle_col_to_channel(n, pss, NT);
+    if (mode == 2) {  // OUT_OM24: column = local group * 32 + [dy0 dx0 .. dy8 dx8 m0 .. m8]
+        const int dg = Cout / 27, g = pss * 4 + n / 32, j = n % 32;
+        return (g < dg && j < 27) ? (j < 18 ? g * 18 + j : 18 * dg + g * 9 + (j - 18)) : Cout;
+    }
+    return pss * NT + n;
+}
+// element i of the single-CTA layout [pass][tap][Q][NT][8]
+__device__ __forceinline__ uint16_t pack_tc_elem(const float *__restrict__ w, long long i, int Cout, int Cin, int KK, int Q, int NT, int mode,
+                                                 const WeightView &wv) {
+    const int e = (int)(i % 8);
+    long long r = i / 8;
+    const int n = (int)(r % NT);
+    r /= NT;
+    const int q = (int)(r % Q);
+    r /= Q;
+    const int tap = (int)(r % KK);
+    const int pss = (int)(r / KK);
+    const int cin = q * 8 + e, co = pack_col_channel(n, pss, NT, mode, Cout);
+    return to_16((co < Cout && cin < Cin) ? w[wv.base + (long long)co * wv.s_co + (long long)cin * wv.s_ci + (long long)tap * wv.s_tap] : 0.f, wv.bf16);
+}
+// element i of the CTA-pair layout [pass][rank][tap][Q][NT/2][8] (3x3)
+__device__ __forceinline__ uint16_t pack_tc2_elem(const float *__restrict__ w, long long i, int Cout, int Q, int NT, int mode, const WeightView &wv) {
+    const int NH = NT / 2;
+    const int e = (int)(i % 8);
+    long long r = i / 8;
+    const int nrow = (int)(r % NH);
+    r /= NH;
+    const int q = (int)(r % Q);
+    r /= Q;
+    const int tap = (int)(r % 9);
+    r /= 9;
+    const int rank = (int)(r % 2);
+    const int pss = (int)(r / 2);
+    const int cin = q * 8 + e, co = pack_col_channel(rank * NH + nrow, pss, NT, mode, Cout);
+    return to_16(co < Cout ? w[wv.base + (long long)co * wv.s_co + (long long)cin * wv.s_ci + (long long)tap * wv.s_tap] : 0.f, wv.bf16);
+}
 __global__ void pack_weight_tc_kernel(const float *__restrict__ w, uint16_t *__restrict__ dst, int Cout, int Cin, int KK,
                                       int Q, int NT, int mode, long long total, WeightView wv) {
-    const int dg = Cout / 27;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int e = (int)(i % 8);
-        long long r = i / 8;
-        const int n = (int)(r % NT);
-        r /= NT;
-        const int q = (int)(r % Q);
-        r /= Q;
-        const int tap = (int)(r % KK);
-        const int pss = (int)(r / KK);
-        const int cin = q * 8 + e;
-        int co;
-        if (mode == 1) {  // pixel shuffle column order
-            co = shuffle_col_to_channel(n, pss, NT);
-        } else if (mode == 2) {  // OUT_OM24: column = local group * 32 + [dy0 dx0 .. dy8 dx8 m0 .. m8]
-            const int g = pss * 4 + n / 32, j = n % 32;
-            co = (g < dg && j < 27) ? (j < 18 ? g * 18 + j : 18 * dg + g * 9 + (j - 18)) : Cout;
-        } else {
-            co = pss * NT + n;
-        }
-        dst[i] = to_16((co < Cout && cin < Cin) ? w[wv.base + (long long)co * wv.s_co + (long long)cin * wv.s_ci + (long long)tap * wv.s_tap] : 0.f, wv.bf16);
-    }
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = pack_tc_elem(w, i, Cout, Cin, KK, Q, NT, mode, wv);
 }
 int pack_weight_tc(const float *w_oihw, void *dst, int Cout, int Cin, int ks, int mode, cudaStream_t s, const WeightView *view) {
     const WeightView wv = view ? *view : WeightView{0, (long long)Cin * ks * ks, ks * ks, 1, 0};
@@ -1011,30 +1030,45 @@ size_t tc2_weight_bytes(int Cout, int Cin, int ks, int mode) {
 }
 __global__ void pack_weight_tc2_kernel(const float *__restrict__ w, uint16_t *__restrict__ dst, int Cout, int Cin, int Q, int NT,
                                        int mode, long long total, WeightView wv) {
-    const int dg = Cout / 27, NH = NT / 2;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int e = (int)(i % 8);
-        long long r = i / 8;
-        const int nrow = (int)(r % NH);
-        r /= NH;
-        const int q = (int)(r % Q);
-        r /= Q;
-        const int tap = (int)(r % 9);
-        r /= 9;
-        const int rank = (int)(r % 2);
-        const int pss = (int)(r / 2);
-        const int n = rank * NH + nrow, cin = q * 8 + e;
-        int co;
-        if (mode == 1) {
-            co = shuffle_col_to_channel(n, pss, NT);
-        } else if (mode == 2) {
-            const int g = pss * 4 + n / 32, j = n % 32;
-            co = (g < dg && j < 27) ? (j < 18 ? g * 18 + j : 18 * dg + g * 9 + (j - 18)) : Cout;
-        } else {
-            co = pss * NT + n;
-        }
-        dst[i] = to_16(co < Cout ? w[wv.base + (long long)co * wv.s_co + (long long)cin * wv.s_ci + (long long)tap * wv.s_tap] : 0.f, wv.bf16);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = pack_tc2_elem(w, i, Cout, Q, NT, mode, wv);
+}
+// Several views of ONE weight tensor in one launch (grid.y = view): the forward operand of a convolution and the transposed,
+// flipped operands of its data gradients (training path: one tiny launch per layer and step instead of one per view)
+struct PackView {
+    uint16_t *dst;
+    int Cout, Cin, KK, Q, NT, mode, pair;  // pair: CTA-pair layout (else single-CTA)
+    long long total;
+    WeightView wv;
+};
+struct PackViews { PackView v[RVSR_PACK_MAX_VIEWS]; };
+__global__ void pack_weight_views_kernel(const float *__restrict__ w, const __grid_constant__ PackViews pv) {
+    const PackView &j = pv.v[blockIdx.y];
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < j.total; i += (long long)gridDim.x * blockDim.x)
+        j.dst[i] = j.pair ? pack_tc2_elem(w, i, j.Cout, j.Q, j.NT, j.mode, j.wv) : pack_tc_elem(w, i, j.Cout, j.Cin, j.KK, j.Q, j.NT, j.mode, j.wv);
+}
+// views[k]: {Cout, Cin, ks, shuffle mode, pair layout?} + WeightView; dst[k] sized by tc_conv_weight_bytes
+int pack_weight_views(const float *w, int n, const int (*dims)[5], const WeightView *wv, void *const *dst, cudaStream_t s) {
+    RVSR_CHECK_ARG(n >= 1 && n <= RVSR_PACK_MAX_VIEWS, "tc pack: 1..%d views", RVSR_PACK_MAX_VIEWS);
+    PackViews pv;
+    memset(&pv, 0, sizeof(pv));
+    long long most = 0;
+    for (int k = 0; k < n; ++k) {
+        const int Cout = dims[k][0], Cin = dims[k][1], ks = dims[k][2], mode = dims[k][3], pair = dims[k][4];
+        const int NT = tc_pick_nt(Cout, mode);
+        RVSR_CHECK_ARG(NT != 0 && (!pair || tc2_weight_bytes(Cout, Cin, ks, mode) > 0), "tc pack: unsupported view %d", k);
+        PackView &j = pv.v[k];
+        j.dst = reinterpret_cast<uint16_t *>(dst[k]); j.Cout = Cout; j.Cin = Cin; j.KK = ks * ks; j.NT = NT; j.mode = mode; j.pair = pair;
+        j.Q = pair ? Cin / 8 : pad16(Cin) / 8;
+        j.total = pair ? (long long)tc_passes(Cout, NT, mode) * 2 * 9 * (Cin / 8) * (NT / 2) * 8
+                       : (long long)tc_passes(Cout, NT, mode) * ks * ks * j.Q * NT * 8;
+        j.wv = wv[k];
+        if (j.total > most) most = j.total;
     }
+    const int gx = (int)((most + 255) / 256 < 1024 ? (most + 255) / 256 : 1024);
+    pack_weight_views_kernel<<<dim3(gx, n), 256, 0, s>>>(w, pv);
+    RVSR_LAUNCH_CHECK();
+    return RVSR_OK;
 }
 int pack_weight_tc2(const float *w_oihw, void *dst, int Cout, int Cin, int ks, int mode, cudaStream_t s, const WeightView *view) {
     const WeightView wv = view ? *view : WeightView{0, (long long)Cin * 9, 9, 1, 0};

@@ -109,18 +109,35 @@ def from_c8(x, C=None, dtype=torch.bfloat16):
 
 
 # ---------------------------------------------------------------- convolution
-def _pack_weight(weight, Cout, Cin, ks, shuffle, mode, cin_total, c0, geom):
-    """fp32 OIHW parameter -> the operand layout the launch described by geom = (nsrc, C, N, H, W) will read (the library
-    decides: rvsr_c8_conv_layouts; packing the other one as well would be a second tiny launch per call)."""
+def _pack_weights(weight, views):
+    """fp32 OIHW parameter -> the kernels' operand layout, several views in ONE launch.  views: (Cout, Cin, ks, shuffle, mode,
+    cin_total, c0, geom) with mode 0 = forward operand over input channels [c0, c0 + Cin), 1 = operand of the data gradient of
+    input channels [c0, c0 + Cout); geom = (nsrc, C, N, H, W) of the launch that will read it -- the library decides which of
+    its two layouts that launch reads (rvsr_c8_conv_layouts) and only that one is packed."""
     L = _lib.lib()
-    nbytes = L.rvsr_c8_conv_weight_bytes(Cout, Cin, ks, int(shuffle))
-    layouts = L.rvsr_c8_conv_layouts(geom[0], geom[1], geom[2], geom[3], geom[4], Cout, ks, int(shuffle)) if nbytes else 0
-    if nbytes == 0 or layouts == 0:
-        raise NotImplementedError("train_c8: convolution %d <- %d (k=%d) is not covered by the tcgen05 kernels" % (Cout, Cin, ks))
-    dst = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
-    _lib.check(L.rvsr_c8_conv_pack_weight(_p(weight), _p(dst), Cout, Cin, ks, int(shuffle), mode, cin_total, c0, layouts,
-                                          _stream(weight.device)), "c8_conv_pack_weight")
-    return dst
+    n = len(views)
+    spec = (ctypes.c_int * (8 * n))()
+    dsts = []
+    for k, (Cout, Cin, ks, shuffle, mode, cin_total, c0, geom) in enumerate(views):
+        nbytes = L.rvsr_c8_conv_weight_bytes(Cout, Cin, ks, int(shuffle))
+        layouts = L.rvsr_c8_conv_layouts(geom[0], geom[1], geom[2], geom[3], geom[4], Cout, ks, int(shuffle)) if nbytes else 0
+        if nbytes == 0 or layouts == 0:
+            raise NotImplementedError("train_c8: convolution %d <- %d (k=%d) is not covered by the tcgen05 kernels" % (Cout, Cin, ks))
+        spec[8 * k:8 * k + 8] = [Cout, Cin, ks, int(shuffle), mode, cin_total, c0, layouts]
+        dsts.append(torch.empty(nbytes, dtype=torch.uint8, device=weight.device))
+    ptrs = (ctypes.c_void_p * n)(*[d.data_ptr() for d in dsts])
+    _lib.check(L.rvsr_c8_conv_pack_weights(_p(weight), n, spec, ptrs, _stream(weight.device)), "c8_conv_pack_weights")
+    return dsts
+
+
+def _pack_weight(weight, Cout, Cin, ks, shuffle, mode, cin_total, c0, geom):
+    return _pack_weights(weight, [(Cout, Cin, ks, shuffle, mode, cin_total, c0, geom)])[0]
+
+
+def _dgrad_views(nsrc, Cout, ks, N, H, W, needs):
+    """views of the data-gradient operands of the sources that need a gradient (see _dgrad)"""
+    ng = Cout // 64 if Cout >= 64 else 1
+    return [(64, Cout, ks, False, 1, nsrc * 64, i * 64, (ng, min(Cout, 64), N, H, W)) for i in range(nsrc) if needs[i]]
 
 
 def _conv_launch(xs, w_packed, bias, residual, N, H, W, C, Cout, ks, act, shuffle, res_mode=0, res_slope=0.0):
@@ -159,10 +176,12 @@ def _wgrad(xs, gp, N, H, W, Cout, ks, need_bias):
     return gw, gb
 
 
-def _dgrad(weight, gp, i, nsrc, Cout, ks, N, H, W, residual=None, mask=None, slope=0.0):
-    """Gradient of source i (64 channels) of conv(cat(xs), weight): conv(gp, W[:, slice_i]^T flipped) [+ residual] [* act'(mask)]."""
+def _dgrad(weight, gp, i, nsrc, Cout, ks, N, H, W, residual=None, mask=None, slope=0.0, wp=None):
+    """Gradient of source i (64 channels) of conv(cat(xs), weight): conv(gp, W[:, slice_i]^T flipped) [+ residual] [* act'(mask)].
+    wp: the operand packed in the forward pass (one launch with the forward operand), else it is packed here."""
     gsrc = [gp[:, 8 * k:8 * k + 8] for k in range(Cout // 64)] if Cout >= 64 else [gp]
-    wp = _pack_weight(weight, 64, Cout, ks, False, 1, nsrc * 64, i * 64, (len(gsrc), min(Cout, 64), N, H, W))
+    if wp is None:
+        wp = _pack_weight(weight, 64, Cout, ks, False, 1, nsrc * 64, i * 64, (len(gsrc), min(Cout, 64), N, H, W))
     if mask is not None:
         return _conv_launch(gsrc, wp, None, mask, N, H, W, min(Cout, 64), 64, ks, _lib.ACT_NONE, False, 2, slope)
     return _conv_launch(gsrc, wp, None, residual, N, H, W, min(Cout, 64), 64, ks, _lib.ACT_NONE, False)
@@ -187,11 +206,16 @@ class _ConvC8(torch.autograd.Function):
         weight = weight.contiguous()
         if residual is not None:
             residual = _check_c8(residual, "conv_c8 residual")
-        with torch.cuda.device(weight.device):
-            wp = _pack_weight(weight, Cout, Cin, ks, shuffle, 0, Cin, 0, (len(xs), C, N, H, W))
-            y = _conv_launch(xs, wp, bias, residual, N, H, W, C, Cout, ks, act, shuffle)
-        ctx.meta = (act, shuffle, N, H, W, C, Cout, ks, len(xs), residual is not None)
         needs = ctx.needs_input_grad
+        dg_ok = C == 64 and (Cout % 64 == 0 or (Cout < 64 and Cout % 16 == 0))
+        with torch.cuda.device(weight.device):
+            views = [(Cout, Cin, ks, shuffle, 0, Cin, 0, (len(xs), C, N, H, W))]
+            if dg_ok:
+                views += _dgrad_views(len(xs), Cout, ks, N, H, W, needs[5:5 + len(xs)])
+            packs = _pack_weights(weight, views)   # the forward operand and those of the data gradients: one launch
+            y = _conv_launch(xs, packs[0], bias, residual, N, H, W, C, Cout, ks, act, shuffle)
+        ctx.dgrad_packs = packs[1:] if dg_ok else None
+        ctx.meta = (act, shuffle, N, H, W, C, Cout, ks, len(xs), residual is not None)
         ctx.saved_x = bool(needs[0] or needs[1])
         ctx.save_for_backward(weight, *(xs if ctx.saved_x else []), *([y] if act != _lib.ACT_NONE else []))
         return y
@@ -233,7 +257,8 @@ class _ConvC8(torch.autograd.Function):
                 if C != 64 or (Cout % 64 != 0 and not (Cout < 64 and Cout % 16 == 0)):
                     raise NotImplementedError("conv_c8: the data gradient needs 64-channel sources and Cout %% 64 == 0 or Cout in "
                                               "{16, 32, 48} (got %d <- %d x %d)" % (Cout, nsrc, C))
-                gxs = [_dgrad(weight, gp, i, nsrc, Cout, ks, N, H, W) if needs[5 + i] else None for i in range(nsrc)]
+                packs = iter(ctx.dgrad_packs)
+                gxs = [_dgrad(weight, gp, i, nsrc, Cout, ks, N, H, W, wp=next(packs)) if needs[5 + i] else None for i in range(nsrc)]
         return (gw, gb, g_res, None, None, *gxs)
 
 
@@ -308,11 +333,14 @@ class _ConvPairC8(torch.autograd.Function):
         if skip and (act2 != _lib.ACT_NONE or len(xs) != 1):
             raise NotImplementedError("conv_pair_c8: the skip connection is ResidualBlock_noBN's (one input, no final activation)")
         w1, w2 = w1.contiguous(), w2.contiguous()
+        needs = ctx.needs_input_grad
         with torch.cuda.device(w1.device):
-            h = _conv_launch(xs, _pack_weight(w1, 64, 64 * len(xs), 3, False, 0, 64 * len(xs), 0, (len(xs), 64, N, H, W)), b1, None, N, H, W, 64, 64,
-                             3, act1, False)
-            y = _conv_launch([h], _pack_weight(w2, 64, 64, 3, False, 0, 64, 0, (1, 64, N, H, W)), b2, xs[0] if skip else None, N, H, W, 64, 64, 3,
-                             act2, False)
+            p1 = _pack_weights(w1, [(64, 64 * len(xs), 3, False, 0, 64 * len(xs), 0, (len(xs), 64, N, H, W))] +
+                               _dgrad_views(len(xs), 64, 3, N, H, W, needs[7:7 + len(xs)]))
+            p2 = _pack_weights(w2, [(64, 64, 3, False, 0, 64, 0, (1, 64, N, H, W))] + _dgrad_views(1, 64, 3, N, H, W, [True]))
+            h = _conv_launch(xs, p1[0], b1, None, N, H, W, 64, 64, 3, act1, False)
+            y = _conv_launch([h], p2[0], b2, xs[0] if skip else None, N, H, W, 64, 64, 3, act2, False)
+        ctx.packs = (p1[1:], p2[1])
         ctx.meta = (act1, act2, skip, len(xs), N, H, W)
         ctx.save_for_backward(w1, w2, h, *xs, *([y] if act2 != _lib.ACT_NONE else []))
         return y
@@ -332,12 +360,13 @@ class _ConvPairC8(torch.autograd.Function):
             else:
                 g2 = g
             gw2, gb2 = _wgrad([h], g2, N, H, W, 64, 3, needs[3]) if (needs[2] or needs[3]) else (None, None)
-            gh = _dgrad(w2, g2, 0, 1, 64, 3, N, H, W, mask=h, slope=_SLOPE[act1])      # gradient of conv1's pre-activation output
+            packs1, pack2 = iter(ctx.packs[0]), ctx.packs[1]
+            gh = _dgrad(w2, g2, 0, 1, 64, 3, N, H, W, mask=h, slope=_SLOPE[act1], wp=pack2)  # gradient of conv1's pre-activation output
             gw1, gb1 = _wgrad(xs, gh, N, H, W, 64, 3, needs[1]) if (needs[0] or needs[1]) else (None, None)
             gxs = [None] * nsrc
             for i in range(nsrc):
                 if needs[7 + i]:
-                    gxs[i] = _dgrad(w1, gh, i, nsrc, 64, 3, N, H, W, residual=g if (skip and i == 0) else None)
+                    gxs[i] = _dgrad(w1, gh, i, nsrc, 64, 3, N, H, W, residual=g if (skip and i == 0) else None, wp=next(packs1))
         return (gw1 if needs[0] else None, gb1, gw2 if needs[2] else None, gb2, None, None, None, *gxs)
 
 
