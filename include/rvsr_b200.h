@@ -121,9 +121,11 @@ int rvsr_conv2d_fwd(const void *x1, const void *x2, const void *weight, const vo
  *                             of C channels each (C % 16 == 0, C <= 64); also runs every data gradient (with mode-1 weights).
  *                             residual_mode 0: y += residual.  residual_mode 2: `residual` is the OUTPUT of the activation this
  *                             data gradient flows into, y *= (residual > 0 ? 1 : residual_slope) -- its gradient, fused.
- *   rvsr_c8_conv_wgrad        gw[co][c0 + ci][ky][kx] = sum_pixels x[pixel + (ky, kx) - pad][ci] * g[pixel][co] for the 64 input
- *                             channels of source x (OIHW fp32 [Cout][cin_total][ks][ks]; written, fixed summation order),
- *                             db[co] = sum_pixels g (may be NULL).  Cin = 64 per call, ks in {1, 3}.
+ *   rvsr_c8_conv_wgrad        njobs (<= 8) weight gradients of one geometry in one launch (the sources of a torch.cat convolution,
+ *                             the two convolutions of a fused pair).  Job j: gw[j][co][c0[j] + ci][ky][kx] = sum_pixels
+ *                             x[j][pixel + (ky, kx) - pad][ci] * g[j][pixel][co] for the 64 input channels of source x[j] (OIHW fp32
+ *                             [Cout][cin_total[j]][ks][ks]; written, fixed summation order), db[j][co] = sum_pixels g[j] (may be
+ *                             NULL).  Cin = 64 per job, ks in {1, 3}.
  *   rvsr_c8_act_bwd           out = y > 0 ? g : slope * g  (LeakyReLU(0.1) / ReLU given the layer OUTPUT y)
  *   rvsr_c8_unshuffle2_act_bwd  gradient through lrelu(PixelShuffle(2)(.)): g, y [N][C/4 ch][2H][2W] -> out [N][C ch][H][W]
  *   rvsr_c8_upsample2x        bilinear x2 (align_corners=False) times `scale`, or (backward = 1) its adjoint. */
@@ -144,9 +146,10 @@ int rvsr_c8_conv_layouts(int nsrc, int C, int N, int H, int W, int Cout, int ks,
 int rvsr_c8_conv_fwd(const void *const *x, const long long *x_image_stride, int nsrc, int C, const void *w_packed, const float *bias,
                      const void *residual, void *y, int N, int H, int W, int Cout, int ks, int stride, int act, int shuffle,
                      int residual_mode, float residual_slope, void *stream);
-size_t rvsr_c8_conv_wgrad_workspace_bytes(int N, int H, int W, int Cout);
-int rvsr_c8_conv_wgrad(const void *x, long long x_image_stride, const void *g, float *gw, float *db, int N, int H, int W, int Cin,
-                       int Cout, int ks, int cin_total, int c0, void *workspace, size_t workspace_bytes, void *stream);
+size_t rvsr_c8_conv_wgrad_workspace_bytes(int njobs, int N, int H, int W, int Cout);
+int rvsr_c8_conv_wgrad(int njobs, const void *const *x, const long long *x_image_stride, const void *const *g, float *const *gw,
+                       float *const *db, const int *cin_total, const int *c0, int N, int H, int W, int Cin, int Cout, int ks,
+                       void *workspace, size_t workspace_bytes, void *stream);
 int rvsr_c8_act_bwd(const void *g, const void *y, void *out, long long n_elems, int act, void *stream);
 int rvsr_c8_unshuffle2_act_bwd(const void *g, const void *y, void *out, int N, int C, int H, int W, int act, void *stream);
 int rvsr_c8_upsample2x(const void *src, void *dst, long long planes, int H, int W, float scale, int backward, void *stream);

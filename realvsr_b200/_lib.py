@@ -44,8 +44,10 @@ SIGNATURES = {
     "rvsr_c8_conv_layouts": (c_int, [c_int] * 8),
     "rvsr_c8_conv_fwd": (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(ctypes.c_longlong), c_int, c_int, c_void_p,
                                  c_void_p, c_void_p, c_void_p] + [c_int] * 9 + [ctypes.c_float, c_void_p]),
-    "rvsr_c8_conv_wgrad_workspace_bytes": (c_size_t, [c_int] * 4),
-    "rvsr_c8_conv_wgrad": (c_int, [c_void_p, ctypes.c_longlong, c_void_p, c_void_p, c_void_p] + [c_int] * 8 + [c_void_p, c_size_t, c_void_p]),
+    "rvsr_c8_conv_wgrad_workspace_bytes": (c_size_t, [c_int] * 5),
+    "rvsr_c8_conv_wgrad": (c_int, [c_int, ctypes.POINTER(c_void_p), ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(c_void_p),
+                                   ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), ctypes.POINTER(c_int), ctypes.POINTER(c_int)] +
+                           [c_int] * 6 + [c_void_p, c_size_t, c_void_p]),
     "rvsr_c8_act_bwd": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p]),
     "rvsr_c8_unshuffle2_act_bwd": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
     "rvsr_c8_upsample2x": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, ctypes.c_float, c_int, c_void_p]),

@@ -4,9 +4,10 @@
 
 namespace rvsr {
 bool conv_wgrad_tc_supported(int Cin, int ks, int stride);
-size_t conv_wgrad_tc_workspace_bytes(int N, int H, int W, int Cout);
-int launch_conv_wgrad_tc(const void *x_c8, long long x_image_stride, const void *g_c8, float *gw, float *db, int N, int H, int W,
-                         int Cout, int ks, int cin_total, int c0, void *workspace, size_t workspace_bytes, cudaStream_t s);
+size_t conv_wgrad_tc_workspace_bytes(int njobs, int N, int H, int W, int Cout);
+int launch_conv_wgrad_tc(int njobs, const void *const *x_c8, const long long *x_image_stride, const void *const *g_c8, float *const *gw,
+                         float *const *db, const int *cin_total, const int *c0, int N, int H, int W, int Cout, int ks, void *workspace,
+                         size_t workspace_bytes, cudaStream_t s);
 int launch_act_bwd_c8(const void *g, const void *y, void *out, long long n_elems, int act, cudaStream_t s);
 int launch_unshuffle2_act_bwd_c8(const void *g, const void *y, void *out, int N, int C, int H, int W, int act, cudaStream_t s);
 int launch_upsample2x_c8(const void *src, void *dst, long long planes, int H, int W, float scale, int backward, cudaStream_t s);
@@ -149,15 +150,18 @@ int rvsr_c8_conv_fwd(const void *const *x, const long long *x_image_stride, int 
     return launch_conv_tc(op, (cudaStream_t)stream);
 }
 
-size_t rvsr_c8_conv_wgrad_workspace_bytes(int N, int H, int W, int Cout) {
-    return (N > 0 && H > 0 && W > 0 && Cout > 0) ? conv_wgrad_tc_workspace_bytes(N, H, W, Cout) : 512;
+size_t rvsr_c8_conv_wgrad_workspace_bytes(int njobs, int N, int H, int W, int Cout) {
+    return (njobs > 0 && N > 0 && H > 0 && W > 0 && Cout > 0) ? conv_wgrad_tc_workspace_bytes(njobs, N, H, W, Cout) : 512;
 }
-int rvsr_c8_conv_wgrad(const void *x, long long x_image_stride, const void *g, float *gw, float *db, int N, int H, int W, int Cin,
-                       int Cout, int ks, int cin_total, int c0, void *workspace, size_t workspace_bytes, void *stream) {
+int rvsr_c8_conv_wgrad(int njobs, const void *const *x, const long long *x_image_stride, const void *const *g, float *const *gw,
+                       float *const *db, const int *cin_total, const int *c0, int N, int H, int W, int Cin, int Cout, int ks,
+                       void *workspace, size_t workspace_bytes, void *stream) {
+    RVSR_CHECK_ARG(njobs >= 1 && x && x_image_stride && g && gw && db && cin_total && c0, "c8 conv wgrad: bad job arrays");
     RVSR_CHECK_ARG(N >= 0 && H > 0 && W > 0 && Cout > 0, "c8 conv wgrad: bad sizes");
     if (!conv_wgrad_tc_supported(Cin, ks, 1)) { set_error("c8 conv wgrad: built for 64 input channels, 3x3 / 1x1, stride 1"); return RVSR_E_UNSUPPORTED; }
-    RVSR_CHECK_ARG(gw && (N == 0 || (x && g && workspace)), "c8 conv wgrad: null buffer");
-    return launch_conv_wgrad_tc(x, x_image_stride, g, gw, db, N, H, W, Cout, ks, cin_total, c0, workspace, workspace_bytes, (cudaStream_t)stream);
+    RVSR_CHECK_ARG(N == 0 || workspace, "c8 conv wgrad: null workspace");
+    return launch_conv_wgrad_tc(njobs, x, x_image_stride, g, gw, db, cin_total, c0, N, H, W, Cout, ks, workspace, workspace_bytes,
+                                (cudaStream_t)stream);
 }
 
 int rvsr_c8_act_bwd(const void *g, const void *y, void *out, long long n_elems, int act, void *stream) {

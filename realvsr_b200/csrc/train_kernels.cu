@@ -48,13 +48,17 @@ constexpr int WG_STAGES = 3;
 constexpr int WG_HALO_ELEMS = 8 * (WG_XROWS + 1) * WG_XCOLS;  // 16-byte cells loaded per tile: rows -1 .. 5
 constexpr int WG_PER_THREAD = (WG_HALO_ELEMS + 32 * WG_PROD_WARPS - 1) / (32 * WG_PROD_WARPS);
 
+constexpr int WG_MAX_JOBS = 8;
+// One launch runs up to WG_MAX_JOBS independent (x, g) pairs of the same geometry (blockIdx.z = job): the sources of a torch.cat
+// convolution (same g), the two convolutions of a fused pair -- each job costs a launch's fixed ~10 us otherwise.
 struct alignas(64) WgradParams {
-    CUtensorMap tmap_g;        // [W * 8, H, N * g_planes] bf16, box {256, 4, 8}
-    const uint4 *x;            // C8 bf16: 16-byte cells [N][planes][H][W]
-    long long x_image_stride;  // cells between images
+    CUtensorMap tmap_g[WG_MAX_JOBS];        // [W * 8, H, N * g_planes] bf16, box {256, 4, 8}
+    const uint4 *x[WG_MAX_JOBS];            // C8 bf16: 16-byte cells [N][planes][H][W]
+    long long x_image_stride[WG_MAX_JOBS];  // cells between images
+    int bias_jobs;             // bit j: job j also sums the bias gradient
     int g_planes;              // channel blocks per image of g
-    float *partial;            // [passes][CTAs][6][128][64] fp32: every CTA's accumulators (summed by wgrad_reduce_kernel)
-    float *bias_partial;       // [passes][CTAs][64] fp32 or null
+    float *partial;            // [jobs][passes][CTAs][6][128][64] fp32: every CTA's accumulators (summed by wgrad_reduce_kernel)
+    float *bias_partial;       // [jobs][passes][CTAs][64] fp32
     int Cout, N, H, W;
     int tiles_x, tiles_y, num_tiles;
     TileDiv td;
@@ -77,7 +81,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
     const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
-    const int pass = blockIdx.y;
+    const int pass = blockIdx.y, job = blockIdx.z;
+    const size_t cta = ((size_t)job * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;  // this CTA's slot in partial / bias_partial
+    const bool want_bias = (p.bias_jobs >> job) & 1;
     const int T = blockIdx.x < (unsigned)p.num_tiles ? (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
     if (threadIdx.x == 0) {
@@ -87,7 +93,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
         }
         mbar_init(BAR(B_DONE), 1);
         fence_barrier_init();
-        prefetch_tensormap(&p.tmap_g);
+        prefetch_tensormap(&p.tmap_g[job]);
     }
     if (warp == WG_WARP_MMA) tmem_alloc(smem_u32(tmem_slot), 512);
     tc_fence_before();
@@ -116,7 +122,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
             int tx, ty, n;
             tile_coords(p.td, tile, tx, ty, n);
             const int y0 = ty * TC_ROWS - 1, x0 = tx * TC_TW - 1;
-            const uint4 *src = p.x + (long long)n * p.x_image_stride;
+            const uint4 *src = p.x[job] + (long long)n * p.x_image_stride[job];
 #pragma unroll
             for (int i = 0; i < WG_PER_THREAD; ++i) {
                 const int gy = y0 + rowi[i], gx = x0 + coli[i];
@@ -163,7 +169,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
             tc_fence_after();
             const int q = warp & 3, hf = warp >> 2;
             const int m = q * 32 + lane;
-            float *part = p.partial + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 6 * 128 + m) * 64 + hf * 32;
+            float *part = p.partial + (cta * 6 * 128 + m) * 64 + hf * 32;
 #pragma unroll 1
             for (int b = 0; b < 6; ++b) {
                 if (b >= 3 && q >= 2) break;  // rows 64-127 of the dy = +1 accumulators are not weights
@@ -189,7 +195,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
                 tile_coords(p.td, tile, tx, ty, n);
                 mbar_wait(BAR(B_EMPTY + st), ((t / WG_STAGES) & 1) ^ 1);
                 mbar_expect_tx(BAR(B_FULL + st), WG_G_BYTES);
-                tma_load_3d(smem_u32(stage_s + st * WG_STAGE), &p.tmap_g, BAR(B_FULL + st), tx * TC_TW * 8, ty * TC_ROWS,
+                tma_load_3d(smem_u32(stage_s + st * WG_STAGE), &p.tmap_g[job], BAR(B_FULL + st), tx * TC_TW * 8, ty * TC_ROWS,
                             n * p.g_planes + pass * 8);
             }
         }
@@ -232,7 +238,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
         for (int t = 0; t < T; ++t) {
             const int st = t % WG_STAGES;
             mbar_wait_sleep(BAR(B_FULL + st), (t / WG_STAGES) & 1, 200);
-            if (p.bias_partial != nullptr) {
+            if (want_bias) {
                 const uint4 *g = reinterpret_cast<const uint4 *>(stage_s + st * WG_STAGE) + j;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {  // cell i * 64 + j: channel block i / 2
@@ -248,8 +254,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(B_EMPTY + st));
         }
-        if (p.bias_partial != nullptr) {
-            float *bp = p.bias_partial + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 64;
+        if (want_bias) {
+            float *bp = p.bias_partial + cta * 64;
 #pragma unroll
             for (int q = 0; q < 8; ++q)
 #pragma unroll
@@ -271,9 +277,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
 // groups of 4 consecutive output channels x 4 slices of the CTA range: 16-byte loads, 4 in flight per thread (the partials are
 // up to 29 MB, mostly L2-resident: memory-level parallelism is what this kernel needs), then a fixed-order sum of the 4 slices
 // (bit-reproducible gradients, which atomics would not give).
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float *__restrict__ partial, const float *__restrict__ bias_partial,
-                                                           float *__restrict__ gw, float *__restrict__ db, int ctas, int Cout, int cin_total,
-                                                           int c0, int ks) {
+struct WgradOut {
+    float *gw[WG_MAX_JOBS], *db[WG_MAX_JOBS];
+    int cin_total[WG_MAX_JOBS], c0[WG_MAX_JOBS];
+};
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float *__restrict__ partial_all, const float *__restrict__ bias_partial_all,
+                                                           const __grid_constant__ WgradOut out, int ctas, int Cout, int ks) {
+    const int job = blockIdx.y, passes = (Cout + 63) / 64;
+    const float *partial = partial_all + (size_t)job * passes * ctas * 6 * 128 * 64;
+    const float *bias_partial = bias_partial_all + (size_t)job * passes * ctas * 64;
+    float *gw = out.gw[job], *db = out.db[job];
+    const int cin_total = out.cin_total[job], c0 = out.c0[job];
     const int KK = ks * ks, Cq = Cout / 4;
     const int grp = blockIdx.x * 64 + (threadIdx.x & 63), slice = threadIdx.x >> 6;
     __shared__ float4 sm[4][64];
@@ -810,46 +824,59 @@ static int wgrad_ctas(int num_tiles, int passes) {
     if (gx > num_tiles) gx = num_tiles;
     return gx < 1 ? 1 : gx;
 }
-size_t conv_wgrad_tc_workspace_bytes(int N, int H, int W, int Cout) {
+size_t conv_wgrad_tc_workspace_bytes(int njobs, int N, int H, int W, int Cout) {
     const int passes = cdiv(Cout, 64), tiles = cdiv(W, TC_TW) * cdiv(H, TC_ROWS) * N;
-    const size_t ctas = (size_t)wgrad_ctas(tiles, passes) * passes;
+    const size_t ctas = (size_t)wgrad_ctas(tiles, passes * njobs) * passes * njobs;
     return align_up(ctas * 6 * 128 * 64 * 4, 256) + align_up(ctas * 64 * 4, 256) + 512;
 }
-// gw: OIHW fp32 [Cout][cin_total][ks][ks], the slice of input channels [c0, c0 + 64) is WRITTEN; db: [Cout] fp32 or null, written.
-int launch_conv_wgrad_tc(const void *x_c8, long long x_image_stride, const void *g_c8, float *gw, float *db, int N, int H, int W,
-                         int Cout, int ks, int cin_total, int c0, void *workspace, size_t workspace_bytes, cudaStream_t s) {
+// njobs independent weight gradients of one geometry.  Job j: gw[j] (OIHW fp32 [Cout][cin_total[j]][ks][ks]) gets the slice of
+// input channels [c0[j], c0[j] + 64) WRITTEN from source x[j] and output gradient g[j]; db[j] ([Cout] fp32, may be null) written.
+int launch_conv_wgrad_tc(int njobs, const void *const *x_c8, const long long *x_image_stride, const void *const *g_c8, float *const *gw,
+                         float *const *db, const int *cin_total, const int *c0, int N, int H, int W, int Cout, int ks, void *workspace,
+                         size_t workspace_bytes, cudaStream_t s) {
+    RVSR_CHECK_ARG(njobs >= 1 && njobs <= WG_MAX_JOBS, "conv wgrad: 1..%d jobs", WG_MAX_JOBS);
     RVSR_CHECK_ARG(Cout > 0 && Cout % 8 == 0, "conv wgrad: Cout %d is not a multiple of 8", Cout);
-    RVSR_CHECK_ARG(x_image_stride % 8 == 0, "conv wgrad: image stride");
-    RVSR_CHECK_ARG(c0 >= 0 && c0 + 64 <= cin_total, "conv wgrad: channel slice");
-    RVSR_CHECK_ARG(workspace_bytes >= conv_wgrad_tc_workspace_bytes(N, H, W, Cout), "conv wgrad: workspace too small");
+    RVSR_CHECK_ARG(workspace_bytes >= conv_wgrad_tc_workspace_bytes(njobs, N, H, W, Cout), "conv wgrad: workspace too small");
+    for (int j = 0; j < njobs; ++j) {
+        RVSR_CHECK_ARG(x_image_stride[j] % 8 == 0, "conv wgrad: image stride");
+        RVSR_CHECK_ARG(c0[j] >= 0 && c0[j] + 64 <= cin_total[j], "conv wgrad: channel slice");
+        RVSR_CHECK_ARG(gw[j] != nullptr && (N == 0 || (x_c8[j] != nullptr && g_c8[j] != nullptr)), "conv wgrad: null buffer (job %d)", j);
+    }
     if (N == 0) {
-        RVSR_CHECK_ARG(c0 == 0 && cin_total == 64, "conv wgrad: empty batch with a channel slice");
-        RVSR_CUDA(cudaMemsetAsync(gw, 0, (size_t)Cout * 64 * ks * ks * 4, s));
-        if (db) RVSR_CUDA(cudaMemsetAsync(db, 0, (size_t)Cout * 4, s));
+        for (int j = 0; j < njobs; ++j) {
+            RVSR_CHECK_ARG(c0[j] == 0 && cin_total[j] == 64, "conv wgrad: empty batch with a channel slice");
+            RVSR_CUDA(cudaMemsetAsync(gw[j], 0, (size_t)Cout * 64 * ks * ks * 4, s));
+            if (db[j]) RVSR_CUDA(cudaMemsetAsync(db[j], 0, (size_t)Cout * 4, s));
+        }
         return RVSR_OK;
     }
     EncodeTiledFn enc = get_encode();
     RVSR_CHECK_ARG(enc != nullptr, "conv wgrad: cuTensorMapEncodeTiled unavailable");
     WgradParams p;
     memset(&p, 0, sizeof(p));
+    WgradOut out;
+    memset(&out, 0, sizeof(out));
     const int gpl = Cout / 8;
-    {
+    for (int j = 0; j < njobs; ++j) {
         const cuuint64_t dims[3] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)N * gpl};
         const cuuint64_t strides[2] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
         const cuuint32_t box[3] = {(cuuint32_t)TC_TW * 8, (cuuint32_t)TC_ROWS, 8};
         const cuuint32_t estr[3] = {1, 1, 1};
-        CUresult r = enc(&p.tmap_g, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(g_c8), dims, strides, box, estr,
+        CUresult r = enc(&p.tmap_g[j], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(g_c8[j]), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("conv wgrad: cuTensorMapEncodeTiled failed (%d)", (int)r); return RVSR_E_CUDA; }
+        p.x[j] = reinterpret_cast<const uint4 *>(x_c8[j]); p.x_image_stride[j] = x_image_stride[j] / 8;
+        if (db[j] != nullptr) p.bias_jobs |= 1 << j;
+        out.gw[j] = gw[j]; out.db[j] = db[j]; out.cin_total[j] = cin_total[j]; out.c0[j] = c0[j];
     }
     p.tiles_x = cdiv(W, TC_TW); p.tiles_y = cdiv(H, TC_ROWS); p.num_tiles = p.tiles_x * p.tiles_y * N;
-    const int passes = cdiv(Cout, 64), gx = wgrad_ctas(p.num_tiles, passes);
+    const int passes = cdiv(Cout, 64), gx = wgrad_ctas(p.num_tiles, passes * njobs);
     char *wsp = reinterpret_cast<char *>(workspace);
     wsp += (256 - (size_t)((uintptr_t)wsp % 256)) % 256;
     p.partial = reinterpret_cast<float *>(wsp);
-    p.bias_partial = db != nullptr ? reinterpret_cast<float *>(wsp + align_up((size_t)gx * passes * 6 * 128 * 64 * 4, 256)) : nullptr;
-    p.x = reinterpret_cast<const uint4 *>(x_c8); p.x_image_stride = x_image_stride / 8; p.g_planes = gpl;
+    p.bias_partial = reinterpret_cast<float *>(wsp + align_up((size_t)gx * passes * njobs * 6 * 128 * 64 * 4, 256));
+    p.g_planes = gpl;
     p.Cout = Cout; p.N = N; p.H = H; p.W = W; p.ks = ks;
     static const int dbg = getenv("RVSR_WG_DEBUG") ? atoi(getenv("RVSR_WG_DEBUG")) : 0;
     p.debug = dbg;
@@ -857,12 +884,12 @@ int launch_conv_wgrad_tc(const void *x_c8, long long x_image_stride, const void 
     p.td.tx = (uint32_t)p.tiles_x; p.td.m_tx = magic_div(p.td.tx, p.td.tpi);
     const size_t smem = (size_t)WG_STAGES * WG_STAGE + 8 * 16 + 2 * 64 * 4 + 1024;
     RVSR_TRY(ensure_max_dynamic_smem(reinterpret_cast<const void *>(&conv_wgrad_tc_kernel), (int)smem));
-    conv_wgrad_tc_kernel<<<dim3(gx, passes), WG_THREADS, smem, s>>>(p);
+    conv_wgrad_tc_kernel<<<dim3(gx, passes, njobs), WG_THREADS, smem, s>>>(p);
     RVSR_LAUNCH_CHECK();
     const int groups = ks * ks * 64 * (Cout / 4);  // Cout % 8 == 0
     int rb = (groups + 63) / 64;
     if (rb * 256 < Cout) rb = (Cout + 255) / 256;  // the bias sums ride on the first threads
-    wgrad_reduce_kernel<<<rb, 256, 0, s>>>(p.partial, p.bias_partial, gw, db, gx, Cout, cin_total, c0, ks);
+    wgrad_reduce_kernel<<<dim3(rb, njobs), 256, 0, s>>>(p.partial, p.bias_partial, out, gx, Cout, ks);
     RVSR_LAUNCH_CHECK();
     return RVSR_OK;
 }

@@ -164,15 +164,31 @@ def _src_ok(x):
 _SLOPE = {_lib.ACT_LRELU: 0.1, _lib.ACT_RELU: 0.0}
 
 
-def _wgrad(xs, gp, N, H, W, Cout, ks, need_bias):
-    """Weight (+ bias) gradient of conv(cat(xs)) given the gradient gp of its (pre-activation) output."""
-    L, dev, nsrc = _lib.lib(), gp.device, len(xs)
+def _wgrad_jobs(jobs, N, H, W, Cout, ks):
+    """Up to 8 weight gradients of one geometry in ONE launch.  jobs: (x, g, gw, cin_total, c0, gb or None): gw[:, c0:c0 + 64] and
+    gb are written from source x and output gradient g."""
+    L, n = _lib.lib(), len(jobs)
+    dev = jobs[0][1].device
+    arr = lambda ctype, vals: (ctype * n)(*vals)  # noqa: E731
+    ws = torch.empty(L.rvsr_c8_conv_wgrad_workspace_bytes(n, N, H, W, Cout), dtype=torch.uint8, device=dev)
+    _lib.check(L.rvsr_c8_conv_wgrad(n, arr(ctypes.c_void_p, [j[0].data_ptr() for j in jobs]), arr(ctypes.c_longlong, [j[0].stride(0) for j in jobs]),
+                                    arr(ctypes.c_void_p, [j[1].data_ptr() for j in jobs]), arr(ctypes.c_void_p, [j[2].data_ptr() for j in jobs]),
+                                    arr(ctypes.c_void_p, [0 if j[5] is None else j[5].data_ptr() for j in jobs]),
+                                    arr(ctypes.c_int, [j[3] for j in jobs]), arr(ctypes.c_int, [j[4] for j in jobs]),
+                                    N, H, W, 64, Cout, ks, _p(ws), ws.numel(), _stream(dev)), "c8_conv_wgrad")
+
+
+def _wgrad_alloc(nsrc, Cout, ks, need_bias, dev):
     gw = torch.empty((Cout, nsrc * 64, ks, ks), dtype=torch.float32, device=dev)
-    gb = torch.empty(Cout, dtype=torch.float32, device=dev) if need_bias else None
-    ws = torch.empty(L.rvsr_c8_conv_wgrad_workspace_bytes(N, H, W, Cout), dtype=torch.uint8, device=dev)
-    for i, x in enumerate(xs):
-        _lib.check(L.rvsr_c8_conv_wgrad(_p(x), x.stride(0), _p(gp), _p(gw), _p(gb if i == 0 else None), N, H, W, 64, Cout, ks, nsrc * 64,
-                                        i * 64, _p(ws), ws.numel(), _stream(dev)), "c8_conv_wgrad")
+    return gw, (torch.empty(Cout, dtype=torch.float32, device=dev) if need_bias else None)
+
+
+def _wgrad(xs, gp, N, H, W, Cout, ks, need_bias):
+    """Weight (+ bias) gradient of conv(cat(xs)) given the gradient gp of its (pre-activation) output: one job per source."""
+    gw, gb = _wgrad_alloc(len(xs), Cout, ks, need_bias, gp.device)
+    jobs = [(x, gp, gw, len(xs) * 64, i * 64, gb if i == 0 else None) for i, x in enumerate(xs)]
+    for k in range(0, len(jobs), 8):
+        _wgrad_jobs(jobs[k:k + 8], N, H, W, Cout, ks)
     return gw, gb
 
 
@@ -304,11 +320,8 @@ class _ConvFirstC8(torch.autograd.Function):
                 _lib.check(L.rvsr_c8_act_bwd(_p(g), _p(ctx.saved_tensors[1]), _p(gp), g.numel(), act, s), "c8_act_bwd")
             else:
                 gp = g
-            gw = torch.empty((Cout, 64, 3, 3), dtype=torch.float32, device=dev)
-            gb = torch.empty(Cout, dtype=torch.float32, device=dev) if ctx.needs_input_grad[2] else None
-            ws = torch.empty(L.rvsr_c8_conv_wgrad_workspace_bytes(N, H, W, Cout), dtype=torch.uint8, device=dev)
-            _lib.check(L.rvsr_c8_conv_wgrad(_p(xp), xp.stride(0), _p(gp), _p(gw), _p(gb), N, H, W, 64, Cout, 3, 64, 0, _p(ws), ws.numel(), s),
-                       "c8_conv_wgrad")
+            gw, gb = _wgrad_alloc(1, Cout, 3, ctx.needs_input_grad[2], dev)
+            _wgrad_jobs([(xp, gp, gw, 64, 0, gb)], N, H, W, Cout, 3)
         return None, gw[:, :C].contiguous(), gb, None
 
 
@@ -359,10 +372,18 @@ class _ConvPairC8(torch.autograd.Function):
                 _lib.check(L.rvsr_c8_act_bwd(_p(g), _p(sv[-1]), _p(g2), g.numel(), act2, _stream(dev)), "c8_act_bwd")
             else:
                 g2 = g
-            gw2, gb2 = _wgrad([h], g2, N, H, W, 64, 3, needs[3]) if (needs[2] or needs[3]) else (None, None)
             packs1, pack2 = iter(ctx.packs[0]), ctx.packs[1]
             gh = _dgrad(w2, g2, 0, 1, 64, 3, N, H, W, mask=h, slope=_SLOPE[act1], wp=pack2)  # gradient of conv1's pre-activation output
-            gw1, gb1 = _wgrad(xs, gh, N, H, W, 64, 3, needs[1]) if (needs[0] or needs[1]) else (None, None)
+            gw1 = gb1 = gw2 = gb2 = None
+            jobs = []
+            if needs[2] or needs[3]:
+                gw2, gb2 = _wgrad_alloc(1, 64, 3, needs[3], dev)
+                jobs.append((h, g2, gw2, 64, 0, gb2))
+            if needs[0] or needs[1]:
+                gw1, gb1 = _wgrad_alloc(nsrc, 64, 3, needs[1], dev)
+                jobs += [(x, gh, gw1, nsrc * 64, i * 64, gb1 if i == 0 else None) for i, x in enumerate(xs)]
+            if jobs:
+                _wgrad_jobs(jobs, N, H, W, 64, 3)  # both convolutions' weight gradients: one launch
             gxs = [None] * nsrc
             for i in range(nsrc):
                 if needs[7 + i]:

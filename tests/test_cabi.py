@@ -100,8 +100,12 @@ def test_training_entry_points_validate_arguments_without_gpu():
     assert L.rvsr_c8_conv_pack_weight(one, one, 216, 64, 3, 0, 0, 64, 0, 3, nul) == _lib.E_UNSUPPORTED
     assert L.rvsr_c8_conv_pack_weight(one, ctypes.c_void_p(264), 64, 64, 3, 0, 0, 64, 0, 3, nul) == _lib.E_INVALID  # unaligned destination
     assert L.rvsr_c8_conv_pack_weight(one, one, 64, 64, 3, 0, 1, 128, 96, 3, nul) == _lib.E_INVALID               # slice past the row
-    assert L.rvsr_c8_conv_wgrad(one, 64 * 16, one, one, nul, 1, 4, 4, 32, 64, 3, 32, 0, one, 1 << 20, nul) == _lib.E_UNSUPPORTED  # Cin != 64
-    assert L.rvsr_c8_conv_wgrad_workspace_bytes(80, 64, 64, 64) >= 148 * 6 * 128 * 64 * 4
+    job = ((ctypes.c_void_p * 1)(256), (ctypes.c_longlong * 1)(64 * 16), (ctypes.c_void_p * 1)(256), (ctypes.c_void_p * 1)(256),
+           (ctypes.c_void_p * 1)(0), (ctypes.c_int * 1)(64), (ctypes.c_int * 1)(0))
+    assert L.rvsr_c8_conv_wgrad(1, *job, 1, 4, 4, 32, 64, 3, one, 1 << 20, nul) == _lib.E_UNSUPPORTED   # Cin != 64
+    assert L.rvsr_c8_conv_wgrad(0, *job, 1, 4, 4, 64, 64, 3, one, 1 << 20, nul) == _lib.E_INVALID       # no jobs
+    assert L.rvsr_c8_conv_wgrad_workspace_bytes(1, 80, 64, 64, 64) >= 148 * 6 * 128 * 64 * 4
+    assert L.rvsr_c8_conv_wgrad_workspace_bytes(3, 80, 64, 64, 64) >= 147 * 6 * 128 * 64 * 4           # 3 jobs share the SMs
     assert L.rvsr_c8_act_bwd(one, one, one, 64, 0, nul) == _lib.E_INVALID                       # no activation to differentiate
     assert L.rvsr_c8_unshuffle2_act_bwd(one, one, one, 1, 48, 4, 4, 1, nul) == _lib.E_INVALID   # C % 32
     assert L.rvsr_c8_tsa_temporal(one, one, one, ptrs, one, 1, 5, 32, 4, 4, nul) == _lib.E_UNSUPPORTED

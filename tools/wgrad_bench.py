@@ -29,10 +29,12 @@ for (N, H, W, Cout) in [(80, 64, 64, 64), (40, 64, 64, 64), (16, 64, 64, 64), (4
     x = torch.randn(N, 8, H, W, 8, device=dev).bfloat16()
     g = torch.randn(N, Cout // 8, H, W, 8, device=dev).bfloat16()
     dw = torch.zeros(Cout, 64, 3, 3, device=dev)
-    ws = torch.empty(L.rvsr_c8_conv_wgrad_workspace_bytes(N, H, W, Cout), dtype=torch.uint8, device=dev)
+    ws = torch.empty(L.rvsr_c8_conv_wgrad_workspace_bytes(1, N, H, W, Cout), dtype=torch.uint8, device=dev)
     db = torch.zeros(Cout, device=dev)
+    JOB = ((ctypes.c_void_p * 1)(x.data_ptr()), (ctypes.c_longlong * 1)(x.stride(0)), (ctypes.c_void_p * 1)(g.data_ptr()), (ctypes.c_void_p * 1)(dw.data_ptr()),
+           (ctypes.c_void_p * 1)(db.data_ptr()), (ctypes.c_int * 1)(64), (ctypes.c_int * 1)(0))
     w = torch.randn(Cout, 64, 3, 3, device=dev) * 0.05
-    t_w = timeit(lambda st: _lib.check(L.rvsr_c8_conv_wgrad(x.data_ptr(), x.stride(0), g.data_ptr(), dw.data_ptr(), db.data_ptr(), N, H, W, 64, Cout, 3, 64, 0, ws.data_ptr(), ws.numel(), S(st))))
+    t_w = timeit(lambda st: _lib.check(L.rvsr_c8_conv_wgrad(1, *JOB, N, H, W, 64, Cout, 3, ws.data_ptr(), ws.numel(), S(st))))
     wp = T._pack_weight(w, Cout, 64, 3, False, 0, 64, 0)
     t_f = timeit(lambda st: T._conv_launch([x], wp, None, None, N, H, W, 64, Cout, 3, 1, False))
     fl = 2.0 * N * H * W * 64 * Cout * 9
