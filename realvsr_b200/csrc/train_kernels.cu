@@ -367,25 +367,62 @@ __global__ void act_bwd_c8_kernel(const uint4 *__restrict__ g, const uint4 *__re
 
 // Gradient through lrelu(PixelShuffle(2)(conv)) (EDVR_arch.py:313-314): g, y are [N][C2/8][2H][2W][8] (C2 = C / 4 channels),
 // out is the gradient of the conv output [N][C/8][H][W][8]: out[n, 4c + 2i + j, h, w] = g[n, c, 2h + i, 2w + j] * act'(y[...]).
-// One thread per (n, output channel block q, h, w): its 8 channels 8q .. 8q+7 = c in {2q, 2q + 1} x (i, j).
-__global__ void unshuffle2_act_bwd_kernel(const __nv_bfloat16 *__restrict__ g, const __nv_bfloat16 *__restrict__ y, uint4 *__restrict__ out,
-                                          int C8, int H, int W, long long total, float slope, int has_act) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int w = (int)(i % W);
-        long long r = i / W;
+// A lane owns one high-resolution pixel of one input block (one 16-byte load of g and of y); the four lanes of a 2x2 quad
+// (lane = 4 * quad + 2i + j) then hold the 32 values of FOUR output cells (blocks 4P .. 4P + 3 at the low-resolution pixel): lane
+// k = 2i + j of the quad assembles block 4P + k from everybody's channels 2k, 2k + 1 with 16 quad shuffles and stores 16 bytes.
+// Loads are contiguous per half warp (16 pixels of a row), stores per 8 lanes.
+__global__ void unshuffle2_act_bwd_kernel(const uint4 *__restrict__ g, const uint4 *__restrict__ y, uint4 *__restrict__ out, int P2, int H, int W,
+                                          long long total_quads, float slope, int has_act) {
+    const int lane = threadIdx.x & 31, k = lane & 3;
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int Wq = (W + 7) / 8;  // a warp covers 8 low-resolution pixels of one row
+    for (long long wq = warp0; wq * 8 < total_quads; wq += nwarps) {
+        const int wx = (int)(wq % Wq);
+        long long r = wq / Wq;
         const int h = (int)(r % H);
         r /= H;
-        const int q = (int)(r % C8);
-        const long long n = r / C8;
-        float v[8];
+        const int P = (int)(r % P2);
+        const long long n = r / P2;
+        const int w = wx * 8 + (lane >> 2);
+        const bool ok = w < W;
+        uint32_t v[4] = {0u, 0u, 0u, 0u};
+        if (ok) {
+            const long long src = ((n * P2 + P) * (2 * H) + (2 * h + (k >> 1))) * (long long)(2 * W) + (2 * w + (k & 1));
+            const uint4 gv = __ldg(g + src);
+            v[0] = gv.x; v[1] = gv.y; v[2] = gv.z; v[3] = gv.w;
+            if (has_act) {
+                const uint4 yv = __ldg(y + src);
+                const uint32_t yy[4] = {yv.x, yv.y, yv.z, yv.w};
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int ch = q * 8 + e, c = ch >> 2, ii = (ch >> 1) & 1, jj = ch & 1;
-            const long long src = (((n * (C8 / 4) + (c >> 3)) * (2 * H) + (2 * h + ii)) * (long long)(2 * W) + (2 * w + jj)) * 8 + (c & 7);
-            const float gv = __bfloat162float(g[src]);
-            v[e] = (!has_act || __bfloat162float(y[src]) > 0.f) ? gv : slope * gv;
+                for (int q = 0; q < 4; ++q) {  // two bf16 channels per word
+                    const float g0 = __uint_as_float(v[q] << 16), g1 = __uint_as_float(v[q] & 0xffff0000u);
+                    const float y0 = __uint_as_float(yy[q] << 16), y1 = __uint_as_float(yy[q] & 0xffff0000u);
+                    const __nv_bfloat162 o = __floats2bfloat162_rn(y0 > 0.f ? g0 : slope * g0, y1 > 0.f ? g1 : slope * g1);
+                    v[q] = *reinterpret_cast<const uint32_t *>(&o);
+                }
+            }
         }
-        out[i] = pack8(v);
+        // word q of a lane = its channels (2q, 2q + 1) of block P, i.e. output block 4P + q, elements 4 * {0, 1} + (its k)
+        uint32_t got[4];
+#pragma unroll
+        for (int src_k = 0; src_k < 4; ++src_k) {
+            uint32_t t = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t s_ = __shfl_sync(0xffffffffu, v[q], (lane & ~3) | src_k);
+                if (q == k) t = s_;
+            }
+            got[src_k] = t;  // lane src_k's channels (2k, 2k + 1)
+        }
+        if (ok) {
+            // output cell of block 4P + k: element e = 4 * (channel parity) + sub-pixel: [c=2k: k'=0..3][c=2k+1: k'=0..3]
+            uint4 o;
+            o.x = (got[0] & 0xffffu) | (got[1] << 16);
+            o.y = (got[2] & 0xffffu) | (got[3] << 16);
+            o.z = (got[0] >> 16) | (got[1] & 0xffff0000u);
+            o.w = (got[2] >> 16) | (got[3] & 0xffff0000u);
+            out[((n * (4 * P2) + 4 * P + k) * H + h) * (long long)W + w] = o;
+        }
     }
 }
 
@@ -906,10 +943,10 @@ int launch_act_bwd_c8(const void *g, const void *y, void *out, long long n_elems
 // g, y: [N][C/32][2H][2W][8] -> out: [N][C/8][H][W][8]; act = RVSR_ACT_NONE: pure pixel-unshuffle (y unused)
 int launch_unshuffle2_act_bwd_c8(const void *g, const void *y, void *out, int N, int C, int H, int W, int act, cudaStream_t s) {
     RVSR_CHECK_ARG(C % 32 == 0, "unshuffle: C %d is not a multiple of 32", C);
-    const long long total = (long long)N * (C / 8) * H * W;
-    if (total == 0) return RVSR_OK;
-    unshuffle2_act_bwd_kernel<<<ew_grid(total), 256, 0, s>>>((const __nv_bfloat16 *)g, (const __nv_bfloat16 *)y, (uint4 *)out, C / 8, H, W,
-                                                            total, act == RVSR_ACT_LRELU ? 0.1f : 0.f, act != RVSR_ACT_NONE);
+    const long long quads = (long long)N * (C / 32) * H * ((W + 7) / 8) * 8;  // low-resolution pixels x input blocks, rows padded to 8
+    if (quads == 0) return RVSR_OK;
+    unshuffle2_act_bwd_kernel<<<ew_grid(quads * 4), 256, 0, s>>>((const uint4 *)g, (const uint4 *)y, (uint4 *)out, C / 32, H, W, quads,
+                                                                act == RVSR_ACT_LRELU ? 0.1f : 0.f, act != RVSR_ACT_NONE);
     RVSR_LAUNCH_CHECK();
     return RVSR_OK;
 }

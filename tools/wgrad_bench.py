@@ -35,7 +35,7 @@ for (N, H, W, Cout) in [(80, 64, 64, 64), (40, 64, 64, 64), (16, 64, 64, 64), (4
            (ctypes.c_void_p * 1)(db.data_ptr()), (ctypes.c_int * 1)(64), (ctypes.c_int * 1)(0))
     w = torch.randn(Cout, 64, 3, 3, device=dev) * 0.05
     t_w = timeit(lambda st: _lib.check(L.rvsr_c8_conv_wgrad(1, *JOB, N, H, W, 64, Cout, 3, ws.data_ptr(), ws.numel(), S(st))))
-    wp = T._pack_weight(w, Cout, 64, 3, False, 0, 64, 0)
+    wp = T._pack_weight(w, Cout, 64, 3, False, 0, 64, 0, (1, 64, N, H, W))
     t_f = timeit(lambda st: T._conv_launch([x], wp, None, None, N, H, W, 64, Cout, 3, 1, False))
     fl = 2.0 * N * H * W * 64 * Cout * 9
     print("N=%3d %3dx%3d Cout=%3d: wgrad %7.1f us (%5.2f PFLOP/s)   fwd conv %7.1f us (%5.2f PFLOP/s)" % (N, H, W, Cout, t_w, fl / t_w * 1e-9, t_f, fl / t_f * 1e-9))
