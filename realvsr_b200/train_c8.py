@@ -34,7 +34,28 @@ def _p(t):
 
 
 def _stream(dev):
-    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    # the raw handle of torch's current stream on `dev` (torch.cuda.current_stream(dev).cuda_stream costs ~8 us of Python per call,
+    # and a training step makes ~1000 calls)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(idx))
+
+
+class _OnDevice(object):
+    """`with _OnDevice(dev)` only when dev is not already the current device (the context manager costs ~10 us of Python)."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, dev):
+        idx = dev.index
+        self.ctx = None if (idx is None or idx == torch.cuda.current_device()) else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            return self.ctx.__exit__(*exc)
+        return False
 
 
 def channels(t):
@@ -59,7 +80,7 @@ def _to_c8_raw(x, planes=None):
     y = torch.empty((N, planes, H, W, 8), dtype=torch.bfloat16, device=x.device)
     if planes > (C + 7) // 8:
         y[:, (C + 7) // 8:].zero_()
-    with torch.cuda.device(x.device):
+    with _OnDevice(x.device):
         _lib.check(_lib.lib().rvsr_c8_from_nchw(_p(x), _lib.BF16 if x.dtype == torch.bfloat16 else _lib.F32, _p(y), N, C, H, W,
                                                 planes, _stream(x.device)), "c8_from_nchw")
     return y
@@ -68,7 +89,7 @@ def _to_c8_raw(x, planes=None):
 def _from_c8_raw(x, C, dtype):
     N, planes, H, W, _ = x.shape
     y = torch.empty((N, C, H, W), dtype=dtype, device=x.device)
-    with torch.cuda.device(x.device):
+    with _OnDevice(x.device):
         _lib.check(_lib.lib().rvsr_c8_to_nchw(_p(x), _p(y), _lib.BF16 if dtype == torch.bfloat16 else _lib.F32, N, C, H, W,
                                               planes, _stream(x.device)), "c8_to_nchw")
     return y
@@ -224,7 +245,7 @@ class _ConvC8(torch.autograd.Function):
             residual = _check_c8(residual, "conv_c8 residual")
         needs = ctx.needs_input_grad
         dg_ok = C == 64 and (Cout % 64 == 0 or (Cout < 64 and Cout % 16 == 0))
-        with torch.cuda.device(weight.device):
+        with _OnDevice(weight.device):
             views = [(Cout, Cin, ks, shuffle, 0, Cin, 0, (len(xs), C, N, H, W))]
             if dg_ok:
                 views += _dgrad_views(len(xs), Cout, ks, N, H, W, needs[5:5 + len(xs)])
@@ -247,7 +268,7 @@ class _ConvC8(torch.autograd.Function):
         dev = weight.device
         g = _check_c8(g, "conv_c8 backward")
         needs = ctx.needs_input_grad
-        with torch.cuda.device(dev):
+        with _OnDevice(dev):
             s = _stream(dev)
             g_res = g if has_res and needs[2] else None  # the residual joins after the activation: its gradient is g itself
             if has_res and act != _lib.ACT_NONE:
@@ -298,7 +319,7 @@ class _ConvFirstC8(torch.autograd.Function):
         xin = x if x.dtype in (torch.bfloat16, torch.float32) else x.float()
         xin = xin.contiguous()
         w16 = torch.nn.functional.pad(weight.detach(), (0, 0, 0, 0, 0, 16 - C)).contiguous()
-        with torch.cuda.device(x.device):
+        with _OnDevice(x.device):
             _lib.check(_lib.lib().rvsr_c8_from_nchw(_p(xin), _lib.BF16 if xin.dtype == torch.bfloat16 else _lib.F32, _p(xp), N, C, H, W, 2,
                                                     _stream(x.device)), "c8_from_nchw")
             wp = _pack_weight(w16, Cout, 16, 3, False, 0, 16, 0, (1, 16, N, H, W))
@@ -313,7 +334,7 @@ class _ConvFirstC8(torch.autograd.Function):
         xp = ctx.saved_tensors[0]
         g = _check_c8(g, "conv_first_c8 backward")
         L, dev = _lib.lib(), g.device
-        with torch.cuda.device(dev):
+        with _OnDevice(dev):
             s = _stream(dev)
             if act != _lib.ACT_NONE:
                 gp = torch.empty_like(g)
@@ -347,7 +368,7 @@ class _ConvPairC8(torch.autograd.Function):
             raise NotImplementedError("conv_pair_c8: the skip connection is ResidualBlock_noBN's (one input, no final activation)")
         w1, w2 = w1.contiguous(), w2.contiguous()
         needs = ctx.needs_input_grad
-        with torch.cuda.device(w1.device):
+        with _OnDevice(w1.device):
             p1 = _pack_weights(w1, [(64, 64 * len(xs), 3, False, 0, 64 * len(xs), 0, (len(xs), 64, N, H, W))] +
                                _dgrad_views(len(xs), 64, 3, N, H, W, needs[7:7 + len(xs)]))
             p2 = _pack_weights(w2, [(64, 64, 3, False, 0, 64, 0, (1, 64, N, H, W))] + _dgrad_views(1, 64, 3, N, H, W, [True]))
@@ -366,7 +387,7 @@ class _ConvPairC8(torch.autograd.Function):
         g = _check_c8(g, "conv_pair_c8 backward")
         needs = ctx.needs_input_grad
         L, dev = _lib.lib(), g.device
-        with torch.cuda.device(dev):
+        with _OnDevice(dev):
             if act2 != _lib.ACT_NONE:
                 g2 = torch.empty_like(g)
                 _lib.check(L.rvsr_c8_act_bwd(_p(g), _p(sv[-1]), _p(g2), g.numel(), act2, _stream(dev)), "c8_act_bwd")
@@ -419,7 +440,7 @@ class _DcnPackC8(torch.autograd.Function):
         weight = weight.contiguous()
         y = torch.empty_like(x)
         L = _lib.lib()
-        with torch.cuda.device(x.device):
+        with _OnDevice(x.device):
             ws = torch.empty(L.rvsr_c8_mdcn_workspace_bytes(N, H, W, 0), dtype=torch.uint8, device=x.device)
             _lib.check(L.rvsr_c8_mdcn_fwd(_p(x), _p(om), _p(weight), _p(bias), _p(y), N, H, W, act, _p(ws), ws.numel(), _stream(x.device)),
                        "c8_mdcn_fwd")
@@ -437,7 +458,7 @@ class _DcnPackC8(torch.autograd.Function):
         gw = torch.empty_like(weight)
         gb = torch.empty(64, dtype=torch.float32, device=x.device) if ctx.with_bias else None
         L = _lib.lib()
-        with torch.cuda.device(x.device):
+        with _OnDevice(x.device):
             ws = torch.empty(L.rvsr_c8_mdcn_workspace_bytes(N, H, W, 1), dtype=torch.uint8, device=x.device)
             _lib.check(L.rvsr_c8_mdcn_bwd(_p(x), _p(om), _p(weight), _p(g), _p(y), _p(gx), _p(gom), _p(gw), _p(gb), N, H, W, ctx.act,
                                           _p(ws), ws.numel(), _stream(x.device)), "c8_mdcn_bwd")
@@ -462,7 +483,7 @@ class _TsaTemporalC8(torch.autograd.Function):
         outs = [torch.empty_like(emb_ref) for _ in range(N)]
         prob = torch.empty((B, N, H, W), dtype=torch.float32, device=emb.device)
         ptrs = (ctypes.c_void_p * N)(*[o.data_ptr() for o in outs])
-        with torch.cuda.device(emb.device):
+        with _OnDevice(emb.device):
             _lib.check(_lib.lib().rvsr_c8_tsa_temporal(_p(aligned), _p(emb), _p(emb_ref), ptrs, _p(prob), B, N, 64, H, W, _stream(emb.device)),
                        "c8_tsa_temporal")
         ctx.N = N
@@ -477,7 +498,7 @@ class _TsaTemporalC8(torch.autograd.Function):
         gouts = [None if g is None else _check_c8(g, "tsa backward") for g in gouts]
         ptrs = (ctypes.c_void_p * N)(*[0 if g is None else g.data_ptr() for g in gouts])
         g_aligned, g_emb, g_emb_ref = torch.empty_like(aligned), torch.empty_like(emb), torch.empty_like(emb_ref)
-        with torch.cuda.device(emb.device):
+        with _OnDevice(emb.device):
             _lib.check(_lib.lib().rvsr_c8_tsa_temporal_bwd(ptrs, _p(aligned), _p(emb), _p(emb_ref), _p(prob), _p(g_aligned), _p(g_emb),
                                                            _p(g_emb_ref), B, N, 64, H, W, _stream(emb.device)), "c8_tsa_temporal_bwd")
         return g_aligned, g_emb, g_emb_ref, None
@@ -496,7 +517,7 @@ class _PoolMaxAvgC8(torch.autograd.Function):
         N, P, H, W, _ = x.shape
         shape = (N, P, (H - 1) // 2 + 1, (W - 1) // 2 + 1, 8)
         mx, av = torch.empty(shape, dtype=torch.bfloat16, device=x.device), torch.empty(shape, dtype=torch.bfloat16, device=x.device)
-        with torch.cuda.device(x.device):
+        with _OnDevice(x.device):
             _lib.check(_lib.lib().rvsr_c8_pool_maxavg(_p(x), _p(mx), _p(av), N * P, H, W, _stream(x.device)), "c8_pool_maxavg")
         ctx.save_for_backward(x)
         return mx, av
@@ -508,7 +529,7 @@ class _PoolMaxAvgC8(torch.autograd.Function):
         g_max = None if g_max is None else _check_c8(g_max, "pool backward")
         g_avg = None if g_avg is None else _check_c8(g_avg, "pool backward")
         gx = torch.empty_like(x)
-        with torch.cuda.device(x.device):
+        with _OnDevice(x.device):
             _lib.check(_lib.lib().rvsr_c8_pool_maxavg_bwd(_p(x), _p(g_max), _p(g_avg), _p(gx), N * P, H, W, _stream(x.device)),
                        "c8_pool_maxavg_bwd")
         return gx
@@ -527,7 +548,7 @@ class _TsaFinalC8(torch.autograd.Function):
         if fea.shape != att.shape or fea.shape != att_add.shape:
             raise RuntimeError("tsa_final_c8: shapes differ")
         out = torch.empty_like(fea)
-        with torch.cuda.device(fea.device):
+        with _OnDevice(fea.device):
             _lib.check(_lib.lib().rvsr_c8_tsa_final(_p(fea), _p(att), _p(att_add), _p(out), fea.numel(), _stream(fea.device)), "c8_tsa_final")
         ctx.save_for_backward(fea, att)
         return out
@@ -537,7 +558,7 @@ class _TsaFinalC8(torch.autograd.Function):
         fea, att = ctx.saved_tensors
         g = _check_c8(g, "tsa_final backward")
         g_fea, g_att = torch.empty_like(fea), torch.empty_like(att)
-        with torch.cuda.device(fea.device):
+        with _OnDevice(fea.device):
             _lib.check(_lib.lib().rvsr_c8_tsa_final_bwd(_p(g), _p(fea), _p(att), _p(g_fea), _p(g_att), fea.numel(), _stream(fea.device)),
                        "c8_tsa_final_bwd")
         return g_fea, g_att, g
@@ -555,7 +576,7 @@ class _Up2C8(torch.autograd.Function):
         N, P, H, W, _ = x.shape
         ctx.scale = float(scale)
         y = torch.empty((N, P, 2 * H, 2 * W, 8), dtype=torch.bfloat16, device=x.device)
-        with torch.cuda.device(x.device):
+        with _OnDevice(x.device):
             _lib.check(_lib.lib().rvsr_c8_upsample2x(_p(x), _p(y), N * P, H, W, ctx.scale, 0, _stream(x.device)), "c8_upsample2x")
         return y
 
@@ -564,7 +585,7 @@ class _Up2C8(torch.autograd.Function):
         g = _check_c8(g, "upsample2x_c8 backward")
         N, P, H2, W2, _ = g.shape
         gx = torch.empty((N, P, H2 // 2, W2 // 2, 8), dtype=torch.bfloat16, device=g.device)
-        with torch.cuda.device(g.device):
+        with _OnDevice(g.device):
             _lib.check(_lib.lib().rvsr_c8_upsample2x(_p(g), _p(gx), N * P, H2 // 2, W2 // 2, ctx.scale, 1, _stream(g.device)),
                        "c8_upsample2x (adjoint)")
         return gx, None
