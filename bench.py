@@ -203,6 +203,8 @@ def cfg5_time(dev):
 
         net.exec_path = "auto"
         out["bf16_c8_eager"] = timed(eager(True))   # before the graph: a captured graph's private memory pool perturbs the allocator
+        out["bf16_c8_eager"]["note"] = ("host-bound: ~1000 launches per step issued from Python (10-11 ms of host time on an idle core, "
+                                        "12.0 ms/step; more when the host is shared) -- the graph entry is the device-bound number")
         net.zero_grad(set_to_none=True)
         gs = train_c8.GraphedStep(net, F.l1_loss, x, gt)
         out["bf16_c8_graph"] = timed(lambda: gs(x, gt))
