@@ -130,6 +130,9 @@ def from_c8(x, C=None, dtype=torch.bfloat16):
 
 
 # ---------------------------------------------------------------- convolution
+_PACK_INFO = {}
+
+
 def _pack_weights(weight, views):
     """fp32 OIHW parameter -> the kernels' operand layout, several views in ONE launch.  views: (Cout, Cin, ks, shuffle, mode,
     cin_total, c0, geom) with mode 0 = forward operand over input channels [c0, c0 + Cin), 1 = operand of the data gradient of
@@ -140,8 +143,13 @@ def _pack_weights(weight, views):
     spec = (ctypes.c_int * (8 * n))()
     dsts = []
     for k, (Cout, Cin, ks, shuffle, mode, cin_total, c0, geom) in enumerate(views):
-        nbytes = L.rvsr_c8_conv_weight_bytes(Cout, Cin, ks, int(shuffle))
-        layouts = L.rvsr_c8_conv_layouts(geom[0], geom[1], geom[2], geom[3], geom[4], Cout, ks, int(shuffle)) if nbytes else 0
+        key = (Cout, Cin, ks, bool(shuffle), geom)
+        hit = _PACK_INFO.get(key)
+        if hit is None:  # pure functions of the shape: asked once per shape, not once per step
+            nbytes = L.rvsr_c8_conv_weight_bytes(Cout, Cin, ks, int(shuffle))
+            layouts = L.rvsr_c8_conv_layouts(geom[0], geom[1], geom[2], geom[3], geom[4], Cout, ks, int(shuffle)) if nbytes else 0
+            hit = _PACK_INFO[key] = (nbytes, layouts)
+        nbytes, layouts = hit
         if nbytes == 0 or layouts == 0:
             raise NotImplementedError("train_c8: convolution %d <- %d (k=%d) is not covered by the tcgen05 kernels" % (Cout, Cin, ks))
         spec[8 * k:8 * k + 8] = [Cout, Cin, ks, int(shuffle), mode, cin_total, c0, layouts]
@@ -185,13 +193,20 @@ def _src_ok(x):
 _SLOPE = {_lib.ACT_LRELU: 0.1, _lib.ACT_RELU: 0.0}
 
 
+_WGRAD_WS = {}
+
+
 def _wgrad_jobs(jobs, N, H, W, Cout, ks):
     """Up to 8 weight gradients of one geometry in ONE launch.  jobs: (x, g, gw, cin_total, c0, gb or None): gw[:, c0:c0 + 64] and
     gb are written from source x and output gradient g."""
     L, n = _lib.lib(), len(jobs)
     dev = jobs[0][1].device
     arr = lambda ctype, vals: (ctype * n)(*vals)  # noqa: E731
-    ws = torch.empty(L.rvsr_c8_conv_wgrad_workspace_bytes(n, N, H, W, Cout), dtype=torch.uint8, device=dev)
+    key = (n, N, H, W, Cout)
+    nbytes = _WGRAD_WS.get(key)
+    if nbytes is None:
+        nbytes = _WGRAD_WS[key] = L.rvsr_c8_conv_wgrad_workspace_bytes(n, N, H, W, Cout)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     _lib.check(L.rvsr_c8_conv_wgrad(n, arr(ctypes.c_void_p, [j[0].data_ptr() for j in jobs]), arr(ctypes.c_longlong, [j[0].stride(0) for j in jobs]),
                                     arr(ctypes.c_void_p, [j[1].data_ptr() for j in jobs]), arr(ctypes.c_void_p, [j[2].data_ptr() for j in jobs]),
                                     arr(ctypes.c_void_p, [0 if j[5] is None else j[5].data_ptr() for j in jobs]),
