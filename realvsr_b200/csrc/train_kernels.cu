@@ -27,11 +27,12 @@ namespace {
 // ---------------------------------------------------------------- weight gradient on tcgen05
 // Per 128-pixel tile (4 rows x 32 columns) and K step (16 consecutive pixels of one row):
 //   B operand  = g tile   [8 co blocks][4 rows][32 px][8]   (TMA, dense box)            N = 64 output channels
-//   A operand  = x halo   [16 blocks][6 rows][34 px][8]: blocks 0-7 the tile's halo from row -1, blocks 8-15 THE SAME halo from
-//                row 0 -- so one M = 128 instruction covers taps (dy, dx) [rows 0-63] and (dy + 1, dx) [rows 64-127] of all 64
-//                input channels.  A tap is a shifted start address, exactly as in the forward kernels.  The halo is 34 pixels
+//   A operand  = x halo   [7 rows][8 channel blocks][34 px][8], ROW-major on purpose: the 16 MN chunks of an M = 128 operand sit one
+//                block stride (544 B) apart, so chunks 0-7 are the 8 channel blocks of halo row r and chunks 8-15 THE SAME blocks of
+//                row r + 1 -- one instruction covers taps (dy, dx) [rows 0-63] and (dy + 1, dx) [rows 64-127] of all 64 input
+//                channels from ONE copy of the halo.  A tap is a shifted start address, exactly as in the forward kernels.  The halo is 34 pixels
 //                wide (K steps must not wrap at dx = +1), which no dense TMA box delivers (<= 256 elements per dimension), so
-//                sixteen producer warps assemble it with 16-byte loads (zero fill outside the image) and write both copies.
+//                sixteen producer warps assemble it with 16-byte loads (zero fill outside the image).
 //   D          = six 128 x 64 fp32 accumulators in TMEM, resident over ALL tiles of the CTA: (dy -1|0, dx -1), (.., dx 0),
 //                (.., dx +1), then (dy +1|unused, dx -1..+1): 6 instructions per K step for 9 taps (75 % useful rows).
 // One red.global.add.v4.f32 pass per CTA at the end into dW^T [9][64][Cout] fp32 (zeroed by the caller).  The bias gradient
@@ -39,13 +40,14 @@ namespace {
 constexpr int WG_PROD_WARPS = 16, WG_WARP_TMA = 16, WG_WARP_MMA = 17, WG_WARP_BIAS0 = 18, WG_BIAS_WARPS = 2;
 constexpr int WG_AHEAD = 4;  // register sets of a producer thread = halo tiles whose loads are in flight ahead of the shared-memory ring
 constexpr int WG_THREADS = 32 * (WG_WARP_BIAS0 + WG_BIAS_WARPS);
-constexpr int WG_XCOLS = 34, WG_XROWS = 6;
-constexpr int WG_XPLANE = WG_XROWS * WG_XCOLS * 16;  // 3264 B per channel block
-constexpr int WG_XCOPY = 8 * WG_XPLANE;              // 26112
+constexpr int WG_XCOLS = 34, WG_XROWS = 7;           // halo: rows -1 .. 5, columns -1 .. 32
+constexpr int WG_XBLOCK = WG_XCOLS * 16;             // 544 B: one channel block of one row
+constexpr int WG_XROW = 8 * WG_XBLOCK;               // 4352 B: one row, [8 channel blocks][34 px][8]
+constexpr int WG_X_BYTES = WG_XROWS * WG_XROW;       // 30464
 constexpr int WG_G_BYTES = 8 * 128 * 16;             // 16384
-constexpr int WG_STAGE = WG_G_BYTES + 2 * WG_XCOPY;  // 68608 (a multiple of 128: the TMA destination stays aligned)
-constexpr int WG_STAGES = 3;
-constexpr int WG_HALO_ELEMS = 8 * (WG_XROWS + 1) * WG_XCOLS;  // 16-byte cells loaded per tile: rows -1 .. 5
+constexpr int WG_STAGE = WG_G_BYTES + WG_X_BYTES;    // 46848 (a multiple of 128: the TMA destination stays aligned)
+constexpr int WG_STAGES = 4;
+constexpr int WG_HALO_ELEMS = 8 * WG_XROWS * WG_XCOLS;  // 16-byte cells loaded per tile
 constexpr int WG_PER_THREAD = (WG_HALO_ELEMS + 32 * WG_PROD_WARPS - 1) / (32 * WG_PROD_WARPS);
 
 constexpr int WG_MAX_JOBS = 8;
@@ -102,20 +104,19 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
     const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
     if (warp < WG_PROD_WARPS) {
-        // ---- x halo producers: rows -1 .. 5 of the tile, 34 columns from -1, all 8 channel blocks; rows 0 .. 4 go to both copies.
+        // ---- x halo producers: rows -1 .. 5 of the tile, 34 columns from -1, all 8 channel blocks.
         // The loads of the next WG_AHEAD - 1 tiles are in flight while a tile is written to shared memory (WG_AHEAD register sets).
         const long long plane = (long long)p.H * p.W;
         int cell[WG_PER_THREAD];  // this thread's cells of the halo: (block, row, column) -> offsets, fixed for the whole kernel
-        int off_a[WG_PER_THREAD], off_b[WG_PER_THREAD], rowi[WG_PER_THREAD], coli[WG_PER_THREAD];
+        int off_s[WG_PER_THREAD], rowi[WG_PER_THREAD], coli[WG_PER_THREAD];
 #pragma unroll
         for (int i = 0; i < WG_PER_THREAD; ++i) {
             const int idx = (int)threadIdx.x + i * 32 * WG_PROD_WARPS;
-            const int pl = idx / ((WG_XROWS + 1) * WG_XCOLS), rem = idx - pl * ((WG_XROWS + 1) * WG_XCOLS);
+            const int pl = idx / (WG_XROWS * WG_XCOLS), rem = idx - pl * (WG_XROWS * WG_XCOLS);
             const int row = rem / WG_XCOLS, col = rem - row * WG_XCOLS;
             cell[i] = idx < WG_HALO_ELEMS ? pl : -1;
             rowi[i] = row; coli[i] = col;
-            off_a[i] = row < WG_XROWS ? (pl * WG_XROWS + row) * WG_XCOLS + col : -1;
-            off_b[i] = row >= 1 ? ((8 + pl) * WG_XROWS + row - 1) * WG_XCOLS + col : -1;
+            off_s[i] = (row * 8 + pl) * WG_XCOLS + col;  // 16-byte units in the stage's halo: [row][block][column]
         }
         auto load_tile = [&](int t, uint4 (&v)[WG_PER_THREAD]) {
             const int tile = blockIdx.x + t * gridDim.x;
@@ -137,10 +138,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
             uint4 *xa = reinterpret_cast<uint4 *>(stage_s + st * WG_STAGE + WG_G_BYTES);
 #pragma unroll
             for (int i = 0; i < WG_PER_THREAD; ++i) {
-                if (cell[i] >= 0 && !(p.debug & 2)) {
-                    if (off_a[i] >= 0) xa[off_a[i]] = v[i];
-                    if (off_b[i] >= 0) xa[off_b[i]] = v[i];
-                }
+                if (cell[i] >= 0 && !(p.debug & 2)) xa[off_s[i]] = v[i];
             }
             fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
             __syncwarp();
@@ -215,8 +213,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
 #pragma unroll
                         for (int b = 0; b < 6; ++b) {
                             if ((p.ks == 1 && b != 1) || (p.debug & 1)) continue;
-                            const uint32_t a = x0 + (uint32_t)((r + (b >= 3 ? 2 : 0)) * WG_XCOLS + h * 16 + (b % 3)) * 16;
-                            umma_f16(tmem_base + (uint32_t)b * 64, make_desc(a, 128, WG_XPLANE), bdesc, idesc, (t | r | h) ? 1u : 0u);
+                            const uint32_t a = x0 + (uint32_t)(r + (b >= 3 ? 2 : 0)) * WG_XROW + (uint32_t)(h * 16 + (b % 3)) * 16;
+                            umma_f16(tmem_base + (uint32_t)b * 64, make_desc(a, 128, WG_XBLOCK), bdesc, idesc, (t | r | h) ? 1u : 0u);
                         }
                     }
                 umma_commit(BAR(B_EMPTY + st));
