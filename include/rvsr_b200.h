@@ -11,7 +11,7 @@
  *   - all device work is enqueued on the cudaStream_t passed as `stream` (void*),
  *     no host synchronisation, no allocation inside per-call entry points; the caller
  *     owns every buffer including the workspace.
- *   - dtype codes: RVSR_F32 = 0, RVSR_F16 = 1, RVSR_BF16 = 2 (DCN operator only).
+ *   - dtype codes: RVSR_F32 = 0, RVSR_F16 = 1, RVSR_BF16 = 2 (DCN operator and training entry points).
  *   - "NCHW" tensors are contiguous like the reference's; the inference engine's
  *     activation layout (channel-blocked [N][C/8][H][W][8]) stays private to it.  Only the
  *     training entry points (rvsr_c8_*) take channel-blocked bf16 tensors.
@@ -28,7 +28,7 @@ extern "C" {
 
 #define RVSR_F32 0
 #define RVSR_F16 1
-#define RVSR_BF16 2 /* DCN operator (rvsr_mdcn_fwd / rvsr_mdcn_bwd) only: bfloat16 tensors in and out -- the dtype of a
+#define RVSR_BF16 2 /* DCN operator (rvsr_mdcn_fwd / rvsr_mdcn_bwd) and the rvsr_c8_* training entry points: bfloat16 tensors in and out -- the dtype of a
                        torch.autocast(bfloat16) training step (BASELINE cfg5).  EDVR's shape class (64 -> 64, 3x3, stride 1,
                        8 deformable groups) runs on tcgen05 in both directions (bf16 / fp16 operands, fp32 accumulate); other
                        shapes are widened to the fp32 CUDA-core kernels and rounded once.  The reference's extension has no
