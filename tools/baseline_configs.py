@@ -35,7 +35,8 @@ if "cfg4" in which:
     del net, x, y
     torch.cuda.empty_cache()
 if "cfg5" in which:
-    # training step: batch 16, 5x3x64x64 patches, forward + backward + L1 loss (module path, fp32 DCN backward kernel)
+    # training step: batch 16, 5x3x64x64 patches, forward + backward + L1 loss in fp32 (module path, fp32 DCN backward kernel); the bf16
+    # step on the train_c8 path (BASELINE cfg5 proper) is bench.py's `cfg5` key / tools/cfg5_profile.py
     kw = dict(nf=64, nc=3, nframes=5, groups=8, front_RBs=5, back_RBs=10, w_TSA=True)
     net = E.EDVR(**kw)
     net.load_state_dict(synth_state_dict(edvr_state_shapes("EDVR", **kw), 7), strict=True)
