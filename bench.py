@@ -244,6 +244,11 @@ def gpu_reference_times(dev):
                 x = synth_input((b, 5, 3, H, W), 8).to(dev).to(tdt)
                 ms = ref_gpu.time_forward(sd, x, steps=3, warmup=2, groups=CFG["groups"], w_TSA=True, upsample=True)
                 out["%s_b%d" % (prec, b)] = dict(ms=ms, frames_per_s=b / (ms * 1e-3))
+        # BASELINE cfg5's counterpart: the reference's training step (fp32: its extension has no bf16 dispatch), same batch
+        x = synth_input((16, 5, 3, 64, 64), 9).to(dev)
+        gt = synth_input((16, 3, 256, 256), 10).to(dev)
+        ms, loss = ref_gpu.time_train_step(sd, x, gt, steps=3, warmup=2, groups=CFG["groups"], w_TSA=True, upsample=True)
+        out["cfg5_train_step_fp32"] = dict(ms=ms, loss=loss, workload="B=16, 5x3x64x64 -> 256x256, forward + L1 + backward, fp32, eager")
         torch.cuda.empty_cache()
         return out
     except Exception as e:  # a checker failure must not take the product's numbers down

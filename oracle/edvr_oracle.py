@@ -217,10 +217,11 @@ def _count(sd, prefix):
 
 
 def edvr_forward(sd, x, groups=8, center=None, w_TSA=True, upsample=True, is_predeblur=False,
-                 HR_in=False, dcn=dcn_forward, taps=None):
+                 HR_in=False, dcn=dcn_forward, taps=None, detach=True):
     """``EDVR.forward`` (upsample=True, EDVR_arch.py:258-320) or ``EDVR_NoUp.forward``
-    (upsample=False, :358-404) from a reference-keyed ``state_dict``."""
-    sd = {k: v.detach().to(x.dtype) for k, v in sd.items()}
+    (upsample=False, :358-404) from a reference-keyed ``state_dict``.  detach=False keeps the weights in the autograd graph
+    (oracle/ref_gpu.py times the reference's training step that way, with a differentiable ``dcn``)."""
+    sd = {k: (v.detach() if detach else v).to(x.dtype) for k, v in sd.items()}
     B, N, C, H, W = x.shape
     center = N // 2 if center is None else center
     x_center = x[:, center].contiguous()

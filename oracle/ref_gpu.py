@@ -68,3 +68,59 @@ def time_forward(sd, x, steps=5, warmup=2, **kw):
                 ts.append(e0.elapsed_time(e1))
     ts.sort()
     return ts[len(ts) // 2]
+
+
+class _RefDcnTrain(torch.autograd.Function):
+    """The reference extension's forward AND backward wired into autograd the way the reference's own
+    ``ModulatedDeformConvFunction`` does it (deform_conv.py:97-141): zero-initialised gradient tensors, two empty dummy
+    buffers, one ``modulated_deform_conv_cuda_backward`` call (deform_conv_cuda.cpp:571-685)."""
+
+    @staticmethod
+    def forward(ctx, x, offset, mask, weight, bias, stride, padding, dilation, groups, deformable_groups):
+        ctx.cfg = (stride, padding, dilation, groups, deformable_groups)
+        x, offset, mask, weight = x.contiguous(), offset.contiguous(), mask.contiguous(), weight.contiguous()
+        ctx.save_for_backward(x, offset, mask, weight, bias)
+        return ref_dcn(x, offset, mask, weight, bias, stride, padding, dilation, groups, deformable_groups)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        x, offset, mask, weight, bias = ctx.saved_tensors
+        stride, padding, dilation, groups, dg = ctx.cfg
+        gx, go, gm, gw, gb = (torch.zeros_like(t) for t in (x, offset, mask, weight, bias))
+        _ext.modulated_deform_conv_cuda_backward(x, weight, bias, x.new_empty(0), offset, mask, x.new_empty(0), gx, gw, gb, go, gm,
+                                                 grad_output.contiguous(), weight.shape[2], weight.shape[3], stride, stride, padding,
+                                                 padding, dilation, dilation, groups, dg, True)
+        return gx, go, gm, gw, gb, None, None, None, None, None
+
+
+def ref_dcn_train(x, offset, mask, weight, bias, stride=1, padding=1, dilation=1, groups=1, deformable_groups=1):
+    assert available() and bias is not None
+    return _RefDcnTrain.apply(x, offset, mask, weight, bias, stride, padding, dilation, groups, deformable_groups)
+
+
+def time_train_step(sd, x, gt, steps=3, warmup=2, **kw):
+    """CUDA-event time (ms, median) of one fp32 training step of the reference network (forward, L1 loss, backward) on torch
+    CUDA ops + the reference extension -- the reference trains in fp32 and its extension has no bfloat16 dispatch."""
+    params = {k: v.to(device=x.device, dtype=x.dtype).requires_grad_() for k, v in sd.items()}
+    ts = []
+    for i in range(warmup + steps):
+        for p_ in params.values():
+            p_.grad = None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loss = torch.nn.functional.l1_loss(O.edvr_forward(params, x, dcn=ref_dcn_train, detach=False, **kw), gt)
+        loss.backward()
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= warmup:
+            ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2], float(loss.detach())
+
+
+def train_grads(sd, x, gt, **kw):
+    """(loss, {name: gradient}) of one fp32 training step of the reference network through the reference extension's backward."""
+    params = {k: v.to(device=x.device, dtype=x.dtype).requires_grad_() for k, v in sd.items()}
+    loss = torch.nn.functional.l1_loss(O.edvr_forward(params, x, dcn=ref_dcn_train, detach=False, **kw), gt)
+    loss.backward()
+    return float(loss.detach()), {k: v.grad.detach().clone() for k, v in params.items()}

@@ -155,3 +155,39 @@ def test_1080p_window_fp16_engine_vs_fp32_engine():
     print("1080p window: fp16 engine vs fp32 engine %.2e" % e)
     assert y16.shape == (1, 3, 1088, 1920) and e < 1e-2
     assert y16[..., :4 * h, :4 * w].shape == (1, 3, 1080, 1920)
+
+
+def test_training_gradients_against_the_reference_extension_backward():
+    """The reference's OWN training arithmetic on this GPU -- its op sequence on torch CUDA ops with its deform_conv_cuda
+    extension's forward and backward (oracle/ref_gpu.py, built unmodified into oracle/_ref) -- against the product's fp32
+    module path (this repo's DCN forward / backward kernels): same loss, every parameter's gradient within 1e-3 of the tensor's
+    max (the reference's col2im atomics and cuDNN's algorithm choices are the only differences; TF32 off on both sides)."""
+    from oracle import ref_gpu
+    if not ref_gpu.available():
+        pytest.skip("oracle/_ref/deform_conv_cuda.so not built")
+    from helpers import load_case
+    from synth import synth_normal
+    from realvsr_b200.archs import EDVR_arch as E
+    c = load_case("edvr_nf64_crop")
+    x = torch.cat([c["x"], c["x"].flip(3)], 0).cuda()
+    gt = synth_normal((2,) + tuple(c["out"].shape[1:]), 59, std=0.3).cuda() + 0.5
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        kw = c["kwargs"]
+        l_ref, g_ref = ref_gpu.train_grads(c["sd"], x, gt, groups=kw["groups"], w_TSA=kw["w_TSA"], upsample=True)
+        net = E.EDVR(**kw).train()
+        net.load_state_dict(c["sd"], strict=True)
+        net = net.cuda()
+        net.exec_path = "module"
+        loss = torch.nn.functional.l1_loss(net(x), gt)
+        loss.backward()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    assert abs(float(loss.detach()) - l_ref) < 1e-5 * l_ref
+    worst = (0.0, "")
+    for n, p in net.named_parameters():
+        e = float((p.grad - g_ref[n]).abs().max() / g_ref[n].abs().max().clamp_min(1e-30))
+        worst = max(worst, (e, n))
+        assert e < 1e-3, (n, e)
+    print("fp32 module path vs the reference extension's training step: worst relative gradient difference %.2e (%s)" % worst)
