@@ -180,6 +180,11 @@ int rvsr_c8_mdcn_fwd(const void *x, const void *om, const float *weight, const f
 int rvsr_c8_mdcn_bwd(const void *x, const void *om, const float *weight, const void *g, const void *y, void *gx, void *gom, float *gw,
                      float *gb, int N, int H, int W, int act, void *workspace, size_t workspace_bytes, void *stream);
 
+/* F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=False) * scale on a contiguous NCHW tensor (planes = N * C) of
+ * dtype RVSR_F32 / F16 / BF16, or (backward = 1) its adjoint: src = gradient of the [2H][2W] result, dst = gradient of the input.
+ * The reference calls it at EDVR_arch.py:53-57, :109-121, :195-202 -- torch's NCHW kernel for it is 16 % of an fp32 training step. */
+int rvsr_upsample2x_nchw(const void *src, void *dst, long long planes, int H, int W, float scale, int backward, int dtype, void *stream);
+
 /* ------------------------------------------------------------------ EDVR engine
  * Replaces EDVR.forward / EDVR_NoUp.forward (EDVR_arch.py:258-320, :358-404) and everything
  * they call (PCD_Align :98-132, TSA_Fusion :168-208, ResidualBlock_noBN arch_util.py:135-139)

@@ -60,6 +60,7 @@ SIGNATURES = {
     "rvsr_c8_mdcn_workspace_bytes": (c_size_t, [c_int] * 4),
     "rvsr_c8_mdcn_fwd": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p, c_size_t, c_void_p]),
     "rvsr_c8_mdcn_bwd": (c_int, [c_void_p] * 9 + [c_int] * 4 + [c_void_p, c_size_t, c_void_p]),
+    "rvsr_upsample2x_nchw": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, ctypes.c_float, c_int, c_int, c_void_p]),
     "rvsr_frames_from_u8": (c_int, [c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),
     "rvsr_frames_to_u8": (c_int, [c_void_p, c_int, c_void_p] + [c_int] * 5 + [c_void_p]),
     "rvsr_engine_create": (c_int, [ctypes.POINTER(EdvrConfig), ctypes.POINTER(c_void_p)]),

@@ -40,7 +40,9 @@ def _conv3(cin, cout, stride=1):
 
 
 def _up2(t):
-    return F.interpolate(t, scale_factor=2, mode='bilinear', align_corners=False)
+    """F.interpolate(t, scale_factor=2, mode='bilinear', align_corners=False) (EDVR_arch.py:53-57, :109-121, :195-202)"""
+    from .. import ops
+    return ops.upsample2x(t)
 
 
 class Predeblur_ResNet_Pyramid(nn.Module):

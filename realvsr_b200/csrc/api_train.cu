@@ -26,6 +26,7 @@ int launch_pool_maxavg_c8(const void *src, void *dmax, void *davg, long long pla
 int launch_pool_maxavg_bwd_c8(const void *src, const void *gmax, const void *gavg, void *gin, long long planes, int H, int W, cudaStream_t s);
 int launch_tsa_final_c8(const void *fea, const void *att, const void *add, void *out, long long n_elems, cudaStream_t s);
 int launch_tsa_final_bwd_c8(const void *g, const void *fea, const void *att, void *g_fea, void *g_att, long long n_elems, cudaStream_t s);
+int launch_upsample2x_nchw(const void *src, void *dst, long long planes, int H, int W, float scale, int backward, int dtype, cudaStream_t s);
 }  // namespace rvsr
 
 using namespace rvsr;
@@ -221,6 +222,11 @@ int rvsr_c8_tsa_final(const void *fea, const void *att, const void *att_add, voi
 int rvsr_c8_tsa_final_bwd(const void *g, const void *fea, const void *att, void *g_fea, void *g_att, long long n_elems, void *stream) {
     RVSR_CHECK_ARG(n_elems >= 0 && n_elems % 8 == 0 && (n_elems == 0 || (g && fea && att && g_fea && g_att)), "c8 tsa final bwd: bad arguments");
     return launch_tsa_final_bwd_c8(g, fea, att, g_fea, g_att, n_elems, (cudaStream_t)stream);
+}
+
+int rvsr_upsample2x_nchw(const void *src, void *dst, long long planes, int H, int W, float scale, int backward, int dtype, void *stream) {
+    RVSR_CHECK_ARG(planes >= 0 && H > 0 && W > 0 && (planes == 0 || (src && dst)), "upsample2x (NCHW): bad arguments");
+    return launch_upsample2x_nchw(src, dst, planes, H, W, scale, backward, dtype, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -74,3 +74,40 @@ def mdcn_pack(x, feat, w_offset_mask, b_offset_mask, weight, bias, deformable_gr
                                         ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)),
                    "mdcn_pack")
     return y
+
+
+class _Upsample2xNCHW(torch.autograd.Function):
+    """F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=False) on a CUDA NCHW tensor (fp32 / fp16 / bf16), with its
+    exact adjoint as backward.  torch's NCHW kernel for this op gives one thread an output pixel and loops over all images x
+    channels inside it (a [80, 64, 16, 16] tensor runs on 1024 threads): 9.7 ms of the 60 ms fp32 training step."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        N, C, H, W = x.shape
+        y = x.new_empty((N, C, 2 * H, 2 * W))
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().rvsr_upsample2x_nchw(_p(x), _p(y), N * C, H, W, 1.0, 0, _DT[x.dtype],
+                                                       ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)), "upsample2x_nchw")
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        N, C, H2, W2 = g.shape
+        gx = g.new_empty((N, C, H2 // 2, W2 // 2))
+        with torch.cuda.device(g.device):
+            _lib.check(_lib.lib().rvsr_upsample2x_nchw(_p(g), _p(gx), N * C, H2 // 2, W2 // 2, 1.0, 1, _DT[g.dtype],
+                                                       ctypes.c_void_p(torch.cuda.current_stream(g.device).cuda_stream)), "upsample2x_nchw (adjoint)")
+        return gx
+
+
+_DT = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
+
+
+def upsample2x(x):
+    """x2 bilinear upsample (align_corners=False) of an NCHW tensor: this library's kernel on CUDA tensors of a supported dtype,
+    torch's op otherwise (CPU tensors: the reference's own arithmetic)."""
+    if x.is_cuda and x.dim() == 4 and x.dtype in _DT:
+        return _Upsample2xNCHW.apply(x)
+    return torch.nn.functional.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)

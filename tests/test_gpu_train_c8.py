@@ -468,3 +468,21 @@ def test_ft_tsa_only_freezing_on_the_c8_path():
             assert torch.equal(part[n], full[n]), n
         else:
             assert part[n] is None, n
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-6), (torch.float16, 2e-3), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("shape", [(2, 5, 7, 9), (3, 8, 16, 16), (1, 3, 1, 5)])
+def test_upsample2x_nchw_module_path(dtype, tol, shape):
+    """ops.upsample2x (the module path's F.interpolate x2 replacement on CUDA NCHW tensors) forward and adjoint against torch."""
+    from realvsr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(61)
+    x = torch.randn(shape, device="cuda", generator=g).to(dtype).requires_grad_()
+    ref = F.interpolate(x.float(), scale_factor=2, mode="bilinear", align_corners=False)
+    gy = torch.randn(ref.shape, device="cuda", generator=g).to(dtype)
+    (gx_ref,) = torch.autograd.grad(ref, [x], gy.float())
+    x2 = x.detach().clone().requires_grad_()
+    y = ops.upsample2x(x2)
+    assert y.dtype == dtype and y.shape == ref.shape
+    assert _rel(y, ref.detach()) < tol
+    (gx,) = torch.autograd.grad(y, [x2], gy)
+    assert _rel(gx, gx_ref) < tol
