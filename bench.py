@@ -165,7 +165,8 @@ def cfg5_time(dev):
     convolution forward / data gradient / weight gradient and the DCN operator on this library's tcgen05 kernels
     (channel-blocked bf16 tensors); `graph` replays the whole step as one CUDA graph (train_c8.GraphedStep), `eager` issues
     its ~1000 launches from Python.  bf16_cudnn_*: the same step on the nn.Module graph (torch's cuDNN convolutions + this
-    repo's DCN operator), the round-1/2 path, for comparison.  fp32: module path, CUDA-core DCN kernels (gradient parity)."""
+    repo's DCN operator and x2 upsample kernels), for comparison.  fp32: module path, CUDA-core DCN kernels (gradient parity with
+    the reference's extension, whose own step is gpu_reference.cfg5_train_step_fp32)."""
     import torch
     import torch.nn.functional as F
     from helpers import edvr_state_shapes
