@@ -896,6 +896,8 @@ __global__ void __launch_bounds__(NTHREADS) dcn_bwd_simt_kernel(const DcnBwdOp o
                 if (vy1 && vx0) load8<float>(xq + ((long long)y1 * op.W + x0) * 8, v10);
                 if (vy1 && vx1) load8<float>(xq + ((long long)y1 * op.W + x1) * 8, v11);
                 float g_dy = 0.f, g_dx = 0.f, g_m = 0.f;
+                const bool whole = c == 0 && cend == 8;  // the group covers the whole channel block (EDVR: 8 channels per group):
+                float gmv[8];                            // its 8 contributions to a corner go out as two vector reductions
                 for (int cc = c; cc < cend; ++cc) {
                     const float gc = gcol[t * 8 + cc][p];
                     const float val = hy * (hx * v00[cc] + lx * v01[cc]) + ly * (hx * v10[cc] + lx * v11[cc]);
@@ -903,10 +905,26 @@ __global__ void __launch_bounds__(NTHREADS) dcn_bwd_simt_kernel(const DcnBwdOp o
                     g_dy += gc * m * (hx * (v10[cc] - v00[cc]) + lx * (v11[cc] - v01[cc]));
                     g_dx += gc * m * (hy * (v01[cc] - v00[cc]) + ly * (v11[cc] - v10[cc]));
                     const float gm = gc * m;
+                    gmv[cc] = gm;
+                    if (whole) continue;
                     if (vy0 && vx0) atomicAdd(gxq + ((long long)y0 * op.W + x0) * 8 + cc, gm * hy * hx);
                     if (vy0 && vx1) atomicAdd(gxq + ((long long)y0 * op.W + x1) * 8 + cc, gm * hy * lx);
                     if (vy1 && vx0) atomicAdd(gxq + ((long long)y1 * op.W + x0) * 8 + cc, gm * ly * hx);
                     if (vy1 && vx1) atomicAdd(gxq + ((long long)y1 * op.W + x1) * 8 + cc, gm * ly * lx);
+                }
+                if (whole) {  // 32 scalar atomics -> 8 red.global.add.v4.f32 (same values, same fp32 adds)
+                    auto corner = [&](bool ok, int yy, int xx, float w) {
+                        if (!ok) return;
+                        float *d = gxq + ((long long)yy * op.W + xx) * 8;
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(gmv[0] * w), "f"(gmv[1] * w), "f"(gmv[2] * w),
+                                     "f"(gmv[3] * w) : "memory");
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + 4), "f"(gmv[4] * w), "f"(gmv[5] * w), "f"(gmv[6] * w),
+                                     "f"(gmv[7] * w) : "memory");
+                    };
+                    corner(vy0 && vx0, y0, x0, hy * hx);
+                    corner(vy0 && vx1, y0, x1, hy * lx);
+                    corner(vy1 && vx0, y1, x0, ly * hx);
+                    corner(vy1 && vx1, y1, x1, ly * lx);
                 }
                 atomicAdd(op.goffset + (long long)n * op.dg * 2 * K * plane + oc, g_dy);
                 atomicAdd(op.goffset + (long long)n * op.dg * 2 * K * plane + oc + plane, g_dx);
