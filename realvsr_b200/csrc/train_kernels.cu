@@ -912,7 +912,8 @@ bool conv_wgrad_tc_supported(int Cin, int ks, int stride) {
 // CTAs per pass.  Measured cost model of one launch (us): 8 + 0.08 * CTAs (each CTA writes 147 KB of partial sums that the
 // reduce kernel reads back) + 2 * tiles / CTAs  ->  minimum at CTAs = 5 * sqrt(tiles)
 static int wgrad_ctas(int num_tiles, int passes) {
-    int gx = (int)(5.0 * sqrt((double)num_tiles));
+    static const double scale = getenv("RVSR_WG_CTA_SCALE") ? atof(getenv("RVSR_WG_CTA_SCALE")) : 5.0;
+    int gx = (int)(scale * sqrt((double)num_tiles));
     const int cap = sm_count() / passes > 0 ? sm_count() / passes : 1;
     if (gx > cap) gx = cap;
     if (gx > num_tiles) gx = num_tiles;

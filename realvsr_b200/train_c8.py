@@ -20,7 +20,9 @@ into the kernels' operand layout on every call because an optimizer step changes
 a Function: an unsupported shape raises NotImplementedError (the caller, EDVR._forward_c8, only routes supported layers
 here).
 """
+import contextlib
 import ctypes
+import os
 
 import torch
 
@@ -129,6 +131,55 @@ def from_c8(x, C=None, dtype=torch.bfloat16):
     return _FromC8.apply(x, channels(x) if C is None else C, dtype)
 
 
+# ---------------------------------------------------------------- side streams of a captured step
+class _Defer:
+    """Side streams of GraphedStep: parallel branches of the captured graph.
+    * Weight gradients.  Nothing downstream of a layer's backward reads its weight gradient, so inside a captured step the
+      weight-gradient launches go to a SIDE stream: their under-filled grids and tails overlap the data-gradient chain on the
+      main stream.  autograd cannot express that (AccumulateGrad runs on the main stream as soon as backward returns), so in
+      this mode backward returns None for the parameters and `finish` stores the gradients in parameter.grad after the join.
+      Inputs of a side-stream launch are kept alive until the main stream has waited for it (LAG launches later), so the
+      allocator cannot hand their memory to a main-stream kernel in between.
+    * Operand packing.  The packed operands depend on the parameters only: their launches go to a second stream that runs
+      ahead of the layers (each convolution waits for its own operand's event)."""
+    active = False     # weight gradients on `side` (during backward)
+    packing = False    # operand packing on `pack_stream` (whole step)
+    side = pack_stream = None
+    wgrad_wanted = False
+    pending = []       # [event after the launch on the side stream, input references or None, [(parameter, gradient)]]
+    keep = []          # packed operands of this step
+    LAG = 3
+
+    @classmethod
+    def begin(cls, dev, wgrad=True, packing=True):
+        if cls.side is None or cls.side.device != dev:
+            cls.side, cls.pack_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        cls.pending, cls.keep = [], []
+        cls.wgrad_wanted, cls.packing = wgrad, packing
+        if packing:
+            cls.pack_stream.wait_stream(torch.cuda.current_stream(dev))
+
+    @classmethod
+    def begin_backward(cls, dev):
+        cls.active = cls.wgrad_wanted
+        if cls.active:
+            cls.side.wait_stream(torch.cuda.current_stream(dev))
+
+    @classmethod
+    def finish(cls, dev):
+        """Join the side streams and deliver the gradients: parameter.grad = gradient (summed when a parameter has several)."""
+        main = torch.cuda.current_stream(dev)
+        if cls.active:
+            main.wait_stream(cls.side)
+        if cls.packing:
+            main.wait_stream(cls.pack_stream)
+        cls.active = cls.packing = False
+        pending, cls.pending, cls.keep = cls.pending, [], []
+        for _, _, outs in pending:
+            for prm, grad in outs:
+                prm.grad = grad if prm.grad is None else prm.grad + grad
+
+
 # ---------------------------------------------------------------- convolution
 _PACK_INFO = {}
 
@@ -141,7 +192,7 @@ def _pack_weights(weight, views):
     L = _lib.lib()
     n = len(views)
     spec = (ctypes.c_int * (8 * n))()
-    dsts = []
+    sizes = []
     for k, (Cout, Cin, ks, shuffle, mode, cin_total, c0, geom) in enumerate(views):
         key = (Cout, Cin, ks, bool(shuffle), geom)
         hit = _PACK_INFO.get(key)
@@ -153,9 +204,19 @@ def _pack_weights(weight, views):
         if nbytes == 0 or layouts == 0:
             raise NotImplementedError("train_c8: convolution %d <- %d (k=%d) is not covered by the tcgen05 kernels" % (Cout, Cin, ks))
         spec[8 * k:8 * k + 8] = [Cout, Cin, ks, int(shuffle), mode, cin_total, c0, layouts]
-        dsts.append(torch.empty(nbytes, dtype=torch.uint8, device=weight.device))
-    ptrs = (ctypes.c_void_p * n)(*[d.data_ptr() for d in dsts])
-    _lib.check(L.rvsr_c8_conv_pack_weights(_p(weight), n, spec, ptrs, _stream(weight.device)), "c8_conv_pack_weights")
+        sizes.append(nbytes)
+    dev = weight.device
+    ahead = _Defer.packing and isinstance(weight, torch.nn.Parameter)   # a derived weight is produced on the main stream
+    with torch.cuda.stream(_Defer.pack_stream) if ahead else contextlib.nullcontext():
+        dsts = [torch.empty(b, dtype=torch.uint8, device=dev) for b in sizes]
+        ptrs = (ctypes.c_void_p * n)(*[d.data_ptr() for d in dsts])
+        _lib.check(L.rvsr_c8_conv_pack_weights(_p(weight), n, spec, ptrs, _stream(dev)), "c8_conv_pack_weights")
+        if ahead:
+            ev = torch.cuda.Event()
+            ev.record(_Defer.pack_stream)
+    if ahead:
+        torch.cuda.current_stream(dev).wait_event(ev)
+        _Defer.keep.append(dsts)   # the pack stream's allocator must not reuse them while main-stream kernels read them
     return dsts
 
 
@@ -219,13 +280,42 @@ def _wgrad_alloc(nsrc, Cout, ks, need_bias, dev):
     return gw, (torch.empty(Cout, dtype=torch.float32, device=dev) if need_bias else None)
 
 
-def _wgrad(xs, gp, N, H, W, Cout, ks, need_bias):
-    """Weight (+ bias) gradient of conv(cat(xs)) given the gradient gp of its (pre-activation) output: one job per source."""
-    gw, gb = _wgrad_alloc(len(xs), Cout, ks, need_bias, gp.device)
+def _wgrad_launch(jobs, N, H, W, Cout, ks, params, outs):
+    """Launch the weight-gradient jobs (8 per launch).  params: the tensors that receive a gradient; outs(): [(parameter,
+    gradient tensor)] the jobs produce, called on the launch stream after the launches.  Returns True when the gradients travel
+    through _Defer (the caller then returns None to autograd); a derived (non-leaf) weight, e.g. the permuted offset / mask
+    convolution, always takes autograd's route."""
+    if not _Defer.active or any(q is not None and not q.is_leaf for q in params):
+        for k in range(0, len(jobs), 8):
+            _wgrad_jobs(jobs[k:k + 8], N, H, W, Cout, ks)
+        return False
+    dev = jobs[0][1].device
+    main, side = torch.cuda.current_stream(dev), _Defer.side
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        for k in range(0, len(jobs), 8):
+            _wgrad_jobs(jobs[k:k + 8], N, H, W, Cout, ks)
+        produced = outs()
+        ev = torch.cuda.Event()
+        ev.record(side)
+    _Defer.pending.append([ev, jobs, produced])
+    live = [q for q in _Defer.pending if q[1] is not None]
+    if len(live) > _Defer.LAG:
+        main.wait_event(live[0][0])
+        live[0][1] = None
+    return True
+
+
+def _wgrad(xs, gp, N, H, W, Cout, ks, params):
+    """Weight (+ bias) gradient of conv(cat(xs)) given the gradient gp of its (pre-activation) output: one job per source.
+    params = (weight or None, bias or None): the parameters that need a gradient.  Returns (gw, gb), None where not needed or
+    where _Defer delivers it."""
+    gw, gb = _wgrad_alloc(len(xs), Cout, ks, params[1] is not None, gp.device)
     jobs = [(x, gp, gw, len(xs) * 64, i * 64, gb if i == 0 else None) for i, x in enumerate(xs)]
-    for k in range(0, len(jobs), 8):
-        _wgrad_jobs(jobs[k:k + 8], N, H, W, Cout, ks)
-    return gw, gb
+    outs = [(p, t) for p, t in zip(params, (gw, gb)) if p is not None]
+    if _wgrad_launch(jobs, N, H, W, Cout, ks, params, lambda: outs):
+        return None, None
+    return (gw if params[0] is not None else None), gb
 
 
 def _dgrad(weight, gp, i, nsrc, Cout, ks, N, H, W, residual=None, mask=None, slope=0.0, wp=None):
@@ -255,6 +345,7 @@ class _ConvC8(torch.autograd.Function):
             raise RuntimeError("conv_c8: weight expects %d input channels, sources give %d x %d" % (Cin, len(xs), C))
         if weight.dtype != torch.float32 or (bias is not None and bias.dtype != torch.float32):
             raise RuntimeError("conv_c8: parameters must be fp32 (the reference's state_dict dtype)")
+        ctx.params = (weight, bias)
         weight = weight.contiguous()
         if residual is not None:
             residual = _check_c8(residual, "conv_c8 residual")
@@ -300,9 +391,7 @@ class _ConvC8(torch.autograd.Function):
             if needs[0] or needs[1]:
                 if C != 64:
                     raise NotImplementedError("conv_c8: the weight gradient is built for 64-channel sources")
-                gw, gb = _wgrad(xs, gp, N, H, W, Cout, ks, needs[1])
-                if not needs[0]:
-                    gw = None
+                gw, gb = _wgrad(xs, gp, N, H, W, Cout, ks, (ctx.params[0] if needs[0] else None, ctx.params[1] if needs[1] else None))
             gxs = [None] * nsrc
             if any(needs[5:5 + nsrc]):
                 # dX_i = conv(dY, W[:, slice_i]^T flipped): Cout gradient channels enter as 64-channel sources
@@ -340,6 +429,7 @@ class _ConvFirstC8(torch.autograd.Function):
             wp = _pack_weight(w16, Cout, 16, 3, False, 0, 16, 0, (1, 16, N, H, W))
             y = _conv_launch([xp[:N]], wp, bias, None, N, H, W, 16, Cout, 3, act, False)
         ctx.meta = (act, N, C, H, W, Cout)
+        ctx.params = (weight, bias)
         ctx.save_for_backward(xp, *([y] if act != _lib.ACT_NONE else []))
         return y
 
@@ -356,9 +446,17 @@ class _ConvFirstC8(torch.autograd.Function):
                 _lib.check(L.rvsr_c8_act_bwd(_p(g), _p(ctx.saved_tensors[1]), _p(gp), g.numel(), act, s), "c8_act_bwd")
             else:
                 gp = g
-            gw, gb = _wgrad_alloc(1, Cout, 3, ctx.needs_input_grad[2], dev)
-            _wgrad_jobs([(xp, gp, gw, 64, 0, gb)], N, H, W, Cout, 3)
-        return None, gw[:, :C].contiguous(), gb, None
+            needs = ctx.needs_input_grad
+            gw, gb = _wgrad_alloc(1, Cout, 3, needs[2], dev)
+            res = []
+
+            def outs():
+                res.append(gw[:, :C].contiguous())
+                return ([(ctx.params[0], res[0])] if needs[1] else []) + ([(ctx.params[1], gb)] if needs[2] else [])
+            if _wgrad_launch([(xp, gp, gw, 64, 0, gb)], N, H, W, Cout, 3, ctx.params, outs):
+                return None, None, None, None
+            outs()
+        return None, (res[0] if needs[1] else None), gb, None
 
 
 def conv_first(x, weight, bias=None, act=None):
@@ -381,6 +479,7 @@ class _ConvPairC8(torch.autograd.Function):
             raise NotImplementedError("conv_pair_c8: 64-channel 3x3 convolutions with an activation in between")
         if skip and (act2 != _lib.ACT_NONE or len(xs) != 1):
             raise NotImplementedError("conv_pair_c8: the skip connection is ResidualBlock_noBN's (one input, no final activation)")
+        ctx.params = (w1, b1, w2, b2)
         w1, w2 = w1.contiguous(), w2.contiguous()
         needs = ctx.needs_input_grad
         with _OnDevice(w1.device):
@@ -418,8 +517,11 @@ class _ConvPairC8(torch.autograd.Function):
             if needs[0] or needs[1]:
                 gw1, gb1 = _wgrad_alloc(nsrc, 64, 3, needs[1], dev)
                 jobs += [(x, gh, gw1, nsrc * 64, i * 64, gb1 if i == 0 else None) for i, x in enumerate(xs)]
-            if jobs:
-                _wgrad_jobs(jobs, N, H, W, 64, 3)  # both convolutions' weight gradients: one launch
+            if jobs:  # both convolutions' weight gradients: one launch
+                prm = ctx.params
+                outs = [(prm[k], t) for k, t in enumerate((gw1, gb1, gw2, gb2)) if needs[k] and t is not None]
+                if _wgrad_launch(jobs, N, H, W, 64, 3, prm, lambda: outs):
+                    gw1 = gb1 = gw2 = gb2 = None
             gxs = [None] * nsrc
             for i in range(nsrc):
                 if needs[7 + i]:
@@ -626,12 +728,17 @@ class GraphedStep:
             optimizer.step()
 
     The usual whole-network capture rules apply (torch.cuda.graphs): static shapes, optimizer.zero_grad(set_to_none=True) must
-    NOT be called between replays (the graph owns the .grad tensors)."""
+    NOT be called between replays (the graph owns the .grad tensors), and no autograd graph of an earlier eager step over the
+    same parameters may still be alive at construction (drop such a `loss` first: it pins the parameters' gradient accumulators
+    to the stream that step ran on, which invalidates the capture)."""
 
-    def __init__(self, net, loss_fn, x, target, amp_dtype=torch.bfloat16, warmup=3):
+    def __init__(self, net, loss_fn, x, target, amp_dtype=torch.bfloat16, warmup=3, overlap_wgrad=None, pack_ahead=None):
         if not x.is_cuda:
             raise NotImplementedError("GraphedStep: CUDA tensors only")
         self.net, self.loss_fn, self.amp_dtype = net, loss_fn, amp_dtype
+        # weight-gradient launches as a parallel branch of the graph (see _Defer); RVSR_WGRAD_OVERLAP=0 keeps one stream
+        self.overlap_wgrad = (os.environ.get("RVSR_WGRAD_OVERLAP", "1") != "0") if overlap_wgrad is None else bool(overlap_wgrad)
+        self.overlap_pack = (os.environ.get("RVSR_PACK_AHEAD", "1") != "0") if pack_ahead is None else bool(pack_ahead)
         self.x, self.target = x.detach().clone(), target.detach().clone()
         side = torch.cuda.Stream(device=x.device)
         side.wait_stream(torch.cuda.current_stream(x.device))
@@ -642,13 +749,21 @@ class GraphedStep:
         torch.cuda.current_stream(x.device).wait_stream(side)
         net.zero_grad(set_to_none=True)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        prio = int(os.environ.get("RVSR_GRAPH_PRIO", "1"))   # main branch at high priority: the side branches fill its gaps
+        kw = dict(stream=torch.cuda.Stream(device=x.device, priority=-1)) if prio else {}
+        _Defer.LAG = int(os.environ.get("RVSR_WGRAD_LAG", "3"))
+        with torch.cuda.graph(self.graph, **kw):
             self.loss = self._fwd_bwd()
 
     def _fwd_bwd(self):
-        with torch.autocast("cuda", dtype=self.amp_dtype, enabled=self.amp_dtype is not None):
-            loss = self.loss_fn(self.net(self.x).float(), self.target)
-        loss.backward()
+        _Defer.begin(self.x.device, self.overlap_wgrad, self.overlap_pack)
+        try:
+            with torch.autocast("cuda", dtype=self.amp_dtype, enabled=self.amp_dtype is not None):
+                loss = self.loss_fn(self.net(self.x).float(), self.target)
+            _Defer.begin_backward(self.x.device)
+            loss.backward()
+        finally:
+            _Defer.finish(self.x.device)
         return loss.detach()
 
     def __call__(self, x, target):

@@ -433,6 +433,44 @@ def test_graphed_step_follows_the_optimizer():
         assert float((p.detach() - q.detach()).abs().max()) <= 2e-2 * lr * 50 + 1e-3 * float(q.detach().abs().max()), n
 
 
+@pytest.mark.parametrize("overlap", [False, True])
+def test_graphed_step_gradients_equal_the_eager_step(overlap):
+    """Every parameter's gradient after one replay of GraphedStep equals the eager step's -- with the weight-gradient launches on
+    the main stream and as a parallel branch of the graph (train_c8._Defer: gradients delivered to .grad behind autograd's back;
+    derived weights such as the permuted offset / mask convolution must still take autograd's route).  The convolution weight
+    gradients are summed in a fixed order (bit-identical); the DCN backward's atomics reorder sums, hence the small tolerance."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers import load_case
+    from synth import synth_normal
+    from realvsr_b200 import train_c8 as T
+    from realvsr_b200.archs import EDVR_arch as E
+    c = load_case("edvr_nf64_crop")
+    net = E.EDVR(**c["kwargs"]).train()
+    net.load_state_dict(c["sd"], strict=True)
+    net = net.to("cuda")
+    x = torch.cat([c["x"], c["x"].flip(3)], 0).to("cuda")
+    gt = synth_normal((2,) + tuple(c["out"].shape[1:]), 58, std=0.3).to("cuda") + 0.5
+    net.zero_grad(set_to_none=True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        loss = F.l1_loss(net(x).float(), gt)
+    loss.backward()
+    eager = {n: p.grad.detach().clone() for n, p in net.named_parameters()}
+    loss_eager = float(loss.detach())
+    del loss   # a live autograd graph of the same parameters pins their AccumulateGrad nodes to the stream it ran on
+    step = T.GraphedStep(net, F.l1_loss, x, gt, overlap_wgrad=overlap, pack_ahead=overlap)
+    for _ in range(2):   # a replay overwrites, never accumulates
+        lg = step(x, gt)
+    assert abs(float(lg) - loss_eager) < 1e-4 * loss_eager
+    assert not T._Defer.active and not T._Defer.packing and not T._Defer.pending and not T._Defer.keep
+    for n, p in net.named_parameters():
+        assert p.grad is not None, n
+        a, b = p.grad.float(), eager[n].float()
+        assert float((a - b).abs().max()) <= 2e-2 * float(b.abs().max()) + 1e-7, n
+
+
 def test_ft_tsa_only_freezing_on_the_c8_path():
     """The reference's `ft_tsa_only` option freezes every parameter whose name lacks 'tsa_fusion'
     (VideoSR_AllPair_model_YCbCr_Split.py:94-99).  On the train_c8 path frozen layers must skip their weight gradients but
