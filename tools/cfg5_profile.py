@@ -35,6 +35,15 @@ e1.record(); torch.cuda.synchronize()
 print('cfg5 step: %.2f ms (AMP=%s, RVSR_TRAIN_C8=%s, CL=%s, GRAPH=%s)' % (e0.elapsed_time(e1) / 5, os.environ.get('AMP', '0'), os.environ.get('RVSR_TRAIN_C8', '1'), os.environ.get('CL', '0'), os.environ.get('GRAPH', '0')))
 if os.environ.get('NOPROF', '0') == '1': sys.exit(0)
 from torch.profiler import profile, ProfilerActivity
+if os.environ.get('ATEN', '0') == '1':   # which torch operators (with shapes) are still on the step: eager only
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
+        step()
+        torch.cuda.synchronize()
+    rows = [e for e in prof.key_averages(group_by_input_shape=True) if e.key.startswith('aten::') and e.self_device_time_total > 0]
+    rows.sort(key=lambda e: -e.self_device_time_total)
+    for e in rows[:40]:
+        print('%-34s n=%3d  %8.1f us  %s' % (e.key, e.count, e.self_device_time_total, str(e.input_shapes)[:150]))
+    sys.exit(0)
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     for _ in range(3): step()
     torch.cuda.synchronize()
