@@ -514,6 +514,17 @@ def test_ft_tsa_only_freezing_on_the_c8_path():
             assert torch.equal(part[n], full[n]), n
         else:
             assert part[n] is None, n
+    # the same frozen network replayed from a graph with its parallel branches (train_c8._Defer): frozen layers launch no weight
+    # gradient on the side stream and get no .grad; the derived offset / mask weights of frozen packs are packed on the main stream
+    from realvsr_b200 import train_c8 as T
+    net.zero_grad(set_to_none=True)
+    gs = T.GraphedStep(net, F.l1_loss, x, gt, amp_dtype=None)
+    gs(x, gt)
+    for n, p in net.named_parameters():
+        if "tsa_fusion" in n:
+            assert torch.equal(p.grad, full[n]), n
+        else:
+            assert p.grad is None, n
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-6), (torch.float16, 2e-3), (torch.bfloat16, 1e-2)])
