@@ -40,6 +40,9 @@ struct alignas(64) TcDcnBwdParams {
     const __nv_bfloat16 *wt;      // BW_WT_BYTES
     float *gx;                    // [N][8][H][W][8] fp32, zeroed
     float *goffset, *gmask;       // planar fp32 (every element written)
+    __nv_bfloat16 *gom_c8;        // if non-null, INSTEAD of goffset / gmask: gradient of the pack's 256-channel offset / mask
+                                  // convolution output, channel-blocked bf16 [N][32][H][W][8] (channels as deform_conv.py:279-283:
+                                  // g * 18 + 2 * tap + {dy, dx} | 144 + g * 9 + tap through the sigmoid); channels 0..215 written
     float *gw;                    // [64 co][64 c][9] fp32, zeroed
     int N, H, W;
     int tiles_x, tiles_y, num_tiles;
@@ -228,7 +231,15 @@ __global__ void __launch_bounds__(BW_THREADS, 1) dcn_bwd_tc_kernel(const __grid_
                     g_dx = fmaf(gc[k], hy * (v01[k] - v00[k]) + ly * (v11[k] - v10[k]), g_dx);   // d val / d px
                     colv[k] = inside ? mk * val : 0.f;
                 }
-                if (valid) {
+                if (valid && p.gom_c8 != nullptr) {
+                    // straight into the offset / mask convolution's gradient tensor: the (dy, dx) pair is one 4-byte store, the
+                    // mask logit's gradient goes through the sigmoid here (mk is its output)
+                    const int co = blk * 18 + 2 * tap, cm = 144 + blk * 9 + tap;
+                    __nv_bfloat16 *base = p.gom_c8 + ((long long)n * 32 * plane + pix) * 8;
+                    *reinterpret_cast<__nv_bfloat162 *>(base + (long long)(co >> 3) * plane * 8 + (co & 7)) =
+                        __floats2bfloat162_rn(inside ? mk * g_dy : 0.f, inside ? mk * g_dx : 0.f);
+                    base[(long long)(cm >> 3) * plane * 8 + (cm & 7)] = __float2bfloat16_rn(inside ? g_m * mk * (1.f - mk) : 0.f);
+                } else if (valid) {
                     float *go = p.goffset + ((long long)n * 144 + blk * 18 + 2 * tap) * plane + pix;
                     go[0] = inside ? mk * g_dy : 0.f;
                     go[plane] = inside ? mk * g_dx : 0.f;
@@ -376,9 +387,10 @@ int pack_wt_dcn_bwd_tc(const void *weight_bf16, void *wt, cudaStream_t s) {
 }
 // The kernel itself on its native buffers: x8 / g8 channel-blocked bf16 [B][8][H][W][8], off32 / msk32 planar fp32 ([B][144][H][W],
 // [B][72][H][W], mask already sigmoid-ed), wt from pack_wt_dcn_bwd_tc.  gx8 (fp32 channel-blocked) and gw32 ([64][64][9]) must be
-// ZEROED by the caller; goff32 / gmsk32 (planar fp32) are fully written.
+// ZEROED by the caller; goff32 / gmsk32 (planar fp32) are fully written -- or, when gom_c8 is given, channels 0..215 of that
+// channel-blocked bf16 [B][32][H][W][8] tensor instead (see TcDcnBwdParams::gom_c8; the caller zeroes channels 216..255).
 int launch_dcn_bwd_tc_core(const void *x8, const void *g8, const float *off32, const float *msk32, const void *wt, float *gx8, float *goff32,
-                           float *gmsk32, float *gw32, int B, int H, int W, cudaStream_t s) {
+                           float *gmsk32, float *gw32, int B, int H, int W, cudaStream_t s, void *gom_c8) {
     TcDcnBwdParams p;
     memset(&p, 0, sizeof(p));
     {
@@ -392,6 +404,7 @@ int launch_dcn_bwd_tc_core(const void *x8, const void *g8, const float *off32, c
         if (r != CUDA_SUCCESS) { set_error("dcn bwd (tensor cores): cuTensorMapEncodeTiled failed (%d)", (int)r); return RVSR_E_CUDA; }
     }
     p.x = (const __nv_bfloat16 *)x8; p.offset = off32; p.mask = msk32; p.wt = (const __nv_bfloat16 *)wt; p.gx = gx8; p.goffset = goff32; p.gmask = gmsk32; p.gw = gw32;
+    p.gom_c8 = (__nv_bfloat16 *)gom_c8;
     p.N = B; p.H = H; p.W = W;
     static const bool comb = !(getenv("RVSR_DCN_BWD_COMBINE") != nullptr && getenv("RVSR_DCN_BWD_COMBINE")[0] == '0');
     p.combine = comb ? 1 : 0;
@@ -432,7 +445,7 @@ int launch_dcn_bwd_tc(const void *input, const void *offset, const void *mask, c
     RVSR_CUDA(cudaMemsetAsync(gx8, 0, px * 64 * 4, s));
     RVSR_CUDA(cudaMemsetAsync(gw32, 0, (size_t)64 * 64 * 9 * 4, s));
     RVSR_CUDA(cudaMemsetAsync(gb32, 0, 64 * 4, s));
-    RVSR_TRY(launch_dcn_bwd_tc_core(x8, g8, off32, msk32, wt, gx8, goff32, gmsk32, gw32, B, H, W, s));
+    RVSR_TRY(launch_dcn_bwd_tc_core(x8, g8, off32, msk32, wt, gx8, goff32, gmsk32, gw32, B, H, W, s, nullptr));
     if (grad_bias != nullptr) {
         bias_grad_bf16_kernel<<<dim3(64, B < 32 ? B : 32), 256, 0, s>>>((const __nv_bfloat16 *)grad_output, gb32, 64, HW, B);
         RVSR_LAUNCH_CHECK();

@@ -19,7 +19,7 @@ namespace rvsr {
 size_t dcn_bwd_tc_wt_bytes();
 int pack_wt_dcn_bwd_tc(const void *weight_bf16, void *wt, cudaStream_t s);
 int launch_dcn_bwd_tc_core(const void *x8, const void *g8, const float *off32, const float *msk32, const void *wt, float *gx8, float *goff32,
-                           float *gmsk32, float *gw32, int B, int H, int W, cudaStream_t s);
+                           float *gmsk32, float *gw32, int B, int H, int W, cudaStream_t s, void *gom_c8);
 int launch_act_bwd_c8(const void *g, const void *y, void *out, long long n_elems, int act, cudaStream_t s);
 
 namespace {
@@ -1180,14 +1180,21 @@ int c8_mdcn_bwd(const void *x, const void *om, const float *weight, const void *
     RVSR_TRY(launch_convert_f32_bf16(weight, wbf, 64 * 64 * 9, s));
     RVSR_TRY(pack_wt_dcn_bwd_tc(wbf, wt, s));
     RVSR_CUDA(cudaMemsetAsync(gx32, 0, px * 256, s));
-    RVSR_TRY(launch_dcn_bwd_tc_core(x, gp, off32, msk32, wt, gx32, goff32, gmsk32, gw, N, H, W, s));
+    // offset / mask gradients: written by the kernel straight into gom (bf16, channel-blocked, through the sigmoid); RVSR_DCN_BWD_GOM=0
+    // keeps the planar fp32 round trip + om_grad_to_c8_kernel (bit-identical results) for A/B runs
+    static const bool direct = !(getenv("RVSR_DCN_BWD_GOM") != nullptr && getenv("RVSR_DCN_BWD_GOM")[0] == '0');
+    if (direct)  // the 40 padding channels (blocks 27..31 of every image) get no gradient
+        RVSR_CUDA(cudaMemset2DAsync((char *)gom + (size_t)27 * HW * 16, (size_t)32 * HW * 16, 0, (size_t)5 * HW * 16, (size_t)N, s));
+    RVSR_TRY(launch_dcn_bwd_tc_core(x, gp, off32, msk32, wt, gx32, goff32, gmsk32, gw, N, H, W, s, direct ? gom : nullptr));
     if (gb != nullptr) {
         bias_grad_c8_kernel<<<dim3(HW >= 4096 ? 16 : 1, 8, N < 8 ? N : 8), 256, 0, s>>>((const uint4 *)gp, gb, HW, N);
         RVSR_LAUNCH_CHECK();
     }
     RVSR_TRY(launch_convert_f32_bf16(gx32, gx, (long long)px * 64, s));
-    om_grad_to_c8_kernel<<<dim3((HW + 127) / 128, 32, N), 128, 0, s>>>(goff32, gmsk32, msk32, (uint4 *)gom, HW);
-    RVSR_LAUNCH_CHECK();
+    if (!direct) {
+        om_grad_to_c8_kernel<<<dim3((HW + 127) / 128, 32, N), 128, 0, s>>>(goff32, gmsk32, msk32, (uint4 *)gom, HW);
+        RVSR_LAUNCH_CHECK();
+    }
     return RVSR_OK;
 }
 
